@@ -1,0 +1,110 @@
+// context.cu -- device bring-up, lane pool.  See include/svt_b200.h.
+#include "common.cuh"
+#include "../../include/svt_b200.h"
+
+namespace b200 {
+
+static Context g_ctx;
+Context& ctx() { return g_ctx; }
+
+void Lane::reserve(size_t bytes) {
+    if (bytes <= cap) return;
+    size_t ncap = cap ? cap : (size_t(4) << 20);
+    while (ncap < bytes) ncap *= 2;
+    uint8_t* nh = nullptr;
+    uint8_t* nd = nullptr;
+    B200_CUDA_CHECK(cudaHostAlloc(&nh, ncap, cudaHostAllocDefault));
+    B200_CUDA_CHECK(cudaMalloc(&nd, ncap));
+    if (h_buf) {
+        // growing in the middle of a call: preserve what was staged so far
+        B200_CUDA_CHECK(cudaStreamSynchronize(stream));
+        memcpy(nh, h_buf, used);
+        B200_CUDA_CHECK(cudaMemcpy(nd, d_buf, used, cudaMemcpyDeviceToDevice));
+        B200_CUDA_CHECK(cudaFreeHost(h_buf));
+        B200_CUDA_CHECK(cudaFree(d_buf));
+    }
+    h_buf = nh;
+    d_buf = nd;
+    cap   = ncap;
+}
+
+void require_ready() {
+    if (!g_ctx.ready) {
+        fprintf(stderr,
+                "[svt_b200] FATAL: entry point called before a successful svt_b200_init(); this "
+                "library has no CPU fallback.\n");
+        abort();
+    }
+}
+
+Lane* lane_acquire() {
+    require_ready();
+    std::lock_guard<std::mutex> lk(g_ctx.mu);
+    for (Lane* l : g_ctx.lanes)
+        if (!l->busy) {
+            l->busy = true;
+            l->used = 0;
+            B200_CUDA_CHECK(cudaSetDevice(g_ctx.device));
+            return l;
+        }
+    B200_CUDA_CHECK(cudaSetDevice(g_ctx.device));
+    Lane* l = new Lane();
+    B200_CUDA_CHECK(cudaStreamCreateWithFlags(&l->stream, cudaStreamNonBlocking));
+    l->busy = true;
+    g_ctx.lanes.push_back(l);
+    return l;
+}
+
+void lane_release(Lane* l) {
+    std::lock_guard<std::mutex> lk(g_ctx.mu);
+    l->busy = false;
+}
+
+void count_launch(int n) { __atomic_fetch_add(&g_ctx.launches, (unsigned long long)n, __ATOMIC_RELAXED); }
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" int svt_b200_init(int device) {
+    Context& c = ctx();
+    std::lock_guard<std::mutex> lk(c.mu);
+    if (c.ready) return c.device == device || device < 0 ? SVT_B200_OK : SVT_B200_ERR_ALREADY_INIT;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) return SVT_B200_ERR_NO_DEVICE;
+    if (device < 0) device = 0;
+    if (device >= n) return SVT_B200_ERR_NO_DEVICE;
+    cudaDeviceProp p;
+    if (cudaGetDeviceProperties(&p, device) != cudaSuccess) return SVT_B200_ERR_NO_DEVICE;
+    if (p.major != 10) {
+        fprintf(stderr, "[svt_b200] device %d is sm_%d%d; this library is built for sm_100a only\n", device, p.major,
+                p.minor);
+        return SVT_B200_ERR_BAD_ARCH;
+    }
+    if (cudaSetDevice(device) != cudaSuccess) return SVT_B200_ERR_NO_DEVICE;
+    c.device   = device;
+    c.sm_count = p.multiProcessorCount;
+    c.max_smem = (int)p.sharedMemPerBlockOptin;
+    c.ready    = true;
+    return SVT_B200_OK;
+}
+
+extern "C" void svt_b200_shutdown(void) {
+    Context& c = ctx();
+    std::lock_guard<std::mutex> lk(c.mu);
+    if (!c.ready) return;
+    cudaSetDevice(c.device);
+    for (Lane* l : c.lanes) {
+        cudaStreamSynchronize(l->stream);
+        if (l->h_buf) cudaFreeHost(l->h_buf);
+        if (l->d_buf) cudaFree(l->d_buf);
+        cudaStreamDestroy(l->stream);
+        delete l;
+    }
+    c.lanes.clear();
+    c.ready = false;
+}
+
+extern "C" int svt_b200_sm_count(void) { return ctx().ready ? ctx().sm_count : 0; }
+extern "C" unsigned long long svt_b200_launch_count(void) { return ctx().launches; }
+extern "C" const char* svt_b200_version(void) { return "svt_b200 0.1 (sm_100a)"; }

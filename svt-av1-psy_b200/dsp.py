@@ -1,0 +1,121 @@
+"""Host-side mirror of the reference's dispatched DSP functions, bound to libsvtav1_b200.so.
+
+Function names and argument meaning follow the reference's function pointers
+(Source/Lib/Codec/aom_dsp_rtcd.h / common_dsp_rtcd.h); buffers are numpy arrays where the C code
+takes pointers.  Every call goes through the C ABI (include/svt_b200.h) -- nothing here computes.
+"""
+import ctypes as ct
+
+import numpy as np
+
+from . import lib
+
+c_u8p = ct.POINTER(ct.c_uint8)
+c_u16p = ct.POINTER(ct.c_uint16)
+c_i16p = ct.POINTER(ct.c_int16)
+c_i32p = ct.POINTER(ct.c_int32)
+c_u32p = ct.POINTER(ct.c_uint32)
+c_i64p = ct.POINTER(ct.c_int64)
+c_u64p = ct.POINTER(ct.c_uint64)
+c_f64p = ct.POINTER(ct.c_double)
+vp = ct.c_void_p
+
+
+def _ptr(a, typ=vp, byte_off=0):
+    """pointer to (a.data + byte_off); `a` must be a numpy array (kept alive by the caller)."""
+    if a is None:
+        return ct.cast(0, typ)
+    return ct.cast(a.ctypes.data + int(byte_off), typ)
+
+
+class SadSearchItem(ct.Structure):
+    _fields_ = [("src_off", ct.c_uint64), ("ref_off", ct.c_uint64), ("src_stride", ct.c_uint32),
+                ("ref_stride", ct.c_uint32), ("ref_step", ct.c_uint32), ("block_w", ct.c_uint16),
+                ("block_h", ct.c_uint16), ("sa_w", ct.c_int16), ("sa_h", ct.c_int16),
+                ("skip_search_line", ct.c_uint16), ("reserved", ct.c_uint16)]
+
+
+SAD_ITEM_DTYPE = np.dtype([("src_off", "<u8"), ("ref_off", "<u8"), ("src_stride", "<u4"), ("ref_stride", "<u4"),
+                           ("ref_step", "<u4"), ("block_w", "<u2"), ("block_h", "<u2"), ("sa_w", "<i2"),
+                           ("sa_h", "<i2"), ("skip_search_line", "<u2"), ("reserved", "<u2")])
+SAD_RESULT_DTYPE = np.dtype([("best_sad", "<u4"), ("x", "<i2"), ("y", "<i2")])
+assert SAD_ITEM_DTYPE.itemsize == ct.sizeof(SadSearchItem) == 40
+
+# ------------------------------------------------------------------------------------------------
+# signatures
+# ------------------------------------------------------------------------------------------------
+lib.svt_b200_init.argtypes = [ct.c_int]
+lib.svt_b200_init.restype = ct.c_int
+lib.svt_b200_shutdown.restype = None
+lib.svt_b200_sm_count.restype = ct.c_int
+lib.svt_b200_launch_count.restype = ct.c_ulonglong
+lib.svt_b200_version.restype = ct.c_char_p
+
+lib.svt_b200_sad_loop_kernel.argtypes = [vp, ct.c_uint32, vp, ct.c_uint32, ct.c_uint32, ct.c_uint32, c_u64p, c_i16p,
+                                         c_i16p, ct.c_uint32, ct.c_uint8, ct.c_int16, ct.c_int16]
+lib.svt_b200_sad_loop_kernel.restype = None
+lib.svt_b200_nxm_sad_kernel.argtypes = [vp, ct.c_uint32, vp, ct.c_uint32, ct.c_uint32, ct.c_uint32]
+lib.svt_b200_nxm_sad_kernel.restype = ct.c_uint32
+lib.svt_b200_sad_search_batch_host.argtypes = [vp, ct.c_size_t, vp, ct.c_size_t, vp, ct.c_int, vp]
+lib.svt_b200_sad_search_batch_host.restype = ct.c_int
+lib.svt_b200_sad_search_batch_dev.argtypes = [vp, vp, vp, ct.c_int, vp, ct.c_int, ct.c_int, ct.c_int, ct.c_int,
+                                              ct.c_int, vp]
+lib.svt_b200_sad_search_batch_dev.restype = ct.c_int
+
+_initialised = False
+
+
+def init(device=0):
+    """Bind the library to a CUDA device (svt_b200_init).  Raises if no sm_100 device is usable."""
+    global _initialised
+    rc = lib.svt_b200_init(int(device))
+    if rc != 0:
+        raise RuntimeError("svt_b200_init(%d) failed with %d: an sm_100 (B200) device is required; "
+                           "there is no CPU fallback" % (device, rc))
+    _initialised = True
+    return rc
+
+
+def shutdown():
+    global _initialised
+    lib.svt_b200_shutdown()
+    _initialised = False
+
+
+def launch_count():
+    return int(lib.svt_b200_launch_count())
+
+
+# ------------------------------------------------------------------------------------------------
+# K1 / K3
+# ------------------------------------------------------------------------------------------------
+def svt_sad_loop_kernel(src, src_off, src_stride, ref, ref_off, ref_stride, block_height, block_width,
+                        src_stride_raw, skip_search_line, search_area_width, search_area_height,
+                        x_init=0, y_init=0):
+    """aom_dsp_rtcd.h:779.  `src`/`ref` are flat uint8 arrays, *_off the element offsets of the block /
+    window origin.  Returns (best_sad, x_search_center, y_search_center)."""
+    best = ct.c_uint64(0)
+    xs = ct.c_int16(x_init)
+    ys = ct.c_int16(y_init)
+    lib.svt_b200_sad_loop_kernel(_ptr(src, vp, src_off), src_stride, _ptr(ref, vp, ref_off), ref_stride, block_height,
+                                 block_width, ct.byref(best), ct.byref(xs), ct.byref(ys), src_stride_raw,
+                                 skip_search_line, search_area_width, search_area_height)
+    return int(best.value), int(xs.value), int(ys.value)
+
+
+def svt_nxm_sad_kernel(src, src_off, src_stride, ref, ref_off, ref_stride, height, width):
+    return int(lib.svt_b200_nxm_sad_kernel(_ptr(src, vp, src_off), src_stride, _ptr(ref, vp, ref_off), ref_stride,
+                                           height, width))
+
+
+def sad_search_batch_host(src_plane, ref_plane, items):
+    """T2: items is a numpy structured array of SAD_ITEM_DTYPE; returns SAD_RESULT_DTYPE array."""
+    items = np.ascontiguousarray(items, dtype=SAD_ITEM_DTYPE)
+    res = np.zeros(len(items), dtype=SAD_RESULT_DTYPE)
+    rc = lib.svt_b200_sad_search_batch_host(_ptr(src_plane), src_plane.nbytes, _ptr(ref_plane), ref_plane.nbytes,
+                                            _ptr(items), len(items), _ptr(res))
+    if rc != 0:
+        raise RuntimeError("svt_b200_sad_search_batch_host rc=%d" % rc)
+    return res
+
+
