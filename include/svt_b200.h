@@ -108,6 +108,93 @@ SVT_B200_API int svt_b200_sad_search_batch_dev(const uint8_t* d_src_plane, const
                                                SvtB200SadSearchResult* d_results, int max_block_w, int max_block_h,
                                                int max_sa_w, int max_sa_h, int max_row_mult, void* stream);
 
+
+/* ------------------------------------------------------------------------------------------ */
+/* K5/K6  2-D transforms  (reference: Source/Lib/Codec/transforms.c, inv_transforms.c)          */
+/* ------------------------------------------------------------------------------------------ */
+/* tx_size / tx_type use the reference's TxSize / TxType enumerators (Source/Lib/Codec/definitions.h):
+ * TX_4X4=0, 8X8, 16X16, 32X32, 64X64, 4X8, 8X4, 8X16, 16X8, 16X32, 32X16, 32X64, 64X32, 4X16, 16X4,
+ * 8X32, 32X8, 16X64, 64X16=18;  DCT_DCT=0, ADST_DCT, DCT_ADST, ADST_ADST, FLIPADST_DCT, DCT_FLIPADST,
+ * FLIPADST_FLIPADST, ADST_FLIPADST, FLIPADST_ADST, IDTX, V_DCT, H_DCT, V_ADST, H_ADST, V_FLIPADST,
+ * H_FLIPADST=15. */
+SVT_B200_API int svt_b200_txfm_valid(int tx_size, int tx_type);
+
+/* T1 generic forms.  svt_av1_fwd_txfm2d_WxH (aom_dsp_rtcd.h:121-197; C: av1_tranform_two_d_core_c,
+ * transforms.c:2259) and svt_av1_inv_txfm2d_add_WxH (common_dsp_rtcd.h:106-142; C: inv_txfm2d_add_c,
+ * inv_transforms.c:2459).  Output of the forward transform is W*H int32, row-major, stride W.
+ * Input of the inverse is min(W,32) x min(H,32) packed coefficients (inv_transforms.c:2567-2686). */
+SVT_B200_API void svt_b200_fwd_txfm2d(int16_t* input, int32_t* output, uint32_t input_stride, int tx_type,
+                                      int tx_size, uint8_t bit_depth);
+SVT_B200_API void svt_b200_inv_txfm2d_add(const int32_t* input, uint16_t* output_r, int32_t stride_r,
+                                          uint16_t* output_w, int32_t stride_w, int tx_type, int tx_size, int32_t bd);
+/* svt_av1_inv_txfm_add (common_dsp_rtcd.h:144; C: inv_transforms.c:3177): 8-bit pixels. */
+SVT_B200_API void svt_b200_inv_txfm_add_8bit(const int32_t* dqcoeff, uint8_t* dst_r, int32_t stride_r, uint8_t* dst_w,
+                                             int32_t stride_w, int tx_type, int tx_size);
+
+/* T1 named forms, one per reference pointer, identical argument lists. */
+#define SVT_B200_DECL_FWD(WxH)                                                                              \
+    SVT_B200_API void svt_b200_av1_fwd_txfm2d_##WxH(int16_t* input, int32_t* output, uint32_t input_stride, \
+                                                    int transform_type, uint8_t bit_depth);
+SVT_B200_DECL_FWD(4x4) SVT_B200_DECL_FWD(8x8) SVT_B200_DECL_FWD(16x16) SVT_B200_DECL_FWD(32x32) SVT_B200_DECL_FWD(64x64)
+SVT_B200_DECL_FWD(4x8) SVT_B200_DECL_FWD(8x4) SVT_B200_DECL_FWD(8x16) SVT_B200_DECL_FWD(16x8) SVT_B200_DECL_FWD(16x32)
+SVT_B200_DECL_FWD(32x16) SVT_B200_DECL_FWD(32x64) SVT_B200_DECL_FWD(64x32) SVT_B200_DECL_FWD(4x16) SVT_B200_DECL_FWD(16x4)
+SVT_B200_DECL_FWD(8x32) SVT_B200_DECL_FWD(32x8) SVT_B200_DECL_FWD(16x64) SVT_B200_DECL_FWD(64x16)
+#undef SVT_B200_DECL_FWD
+#define SVT_B200_DECL_INV_A(WxH)                                                                                \
+    SVT_B200_API void svt_b200_av1_inv_txfm2d_add_##WxH(const int32_t* input, uint16_t* output_r, int32_t stride_r, \
+                                                        uint16_t* output_w, int32_t stride_w, int tx_type, int32_t bd);
+#define SVT_B200_DECL_INV_B(WxH)                                                                                \
+    SVT_B200_API void svt_b200_av1_inv_txfm2d_add_##WxH(const int32_t* input, uint16_t* output_r, int32_t stride_r, \
+                                                        uint16_t* output_w, int32_t stride_w, int tx_type,       \
+                                                        int tx_size, int32_t bd);
+#define SVT_B200_DECL_INV_C(WxH)                                                                                \
+    SVT_B200_API void svt_b200_av1_inv_txfm2d_add_##WxH(const int32_t* input, uint16_t* output_r, int32_t stride_r, \
+                                                        uint16_t* output_w, int32_t stride_w, int tx_type,       \
+                                                        int tx_size, int32_t eob, int32_t bd);
+SVT_B200_DECL_INV_A(4x4) SVT_B200_DECL_INV_A(8x8) SVT_B200_DECL_INV_A(16x16) SVT_B200_DECL_INV_A(32x32) SVT_B200_DECL_INV_A(64x64)
+SVT_B200_DECL_INV_B(4x8) SVT_B200_DECL_INV_B(8x4) SVT_B200_DECL_INV_B(4x16) SVT_B200_DECL_INV_B(16x4)
+SVT_B200_DECL_INV_C(8x16) SVT_B200_DECL_INV_C(16x8) SVT_B200_DECL_INV_C(16x32) SVT_B200_DECL_INV_C(32x16) SVT_B200_DECL_INV_C(32x8)
+SVT_B200_DECL_INV_C(8x32) SVT_B200_DECL_INV_C(32x64) SVT_B200_DECL_INV_C(64x32) SVT_B200_DECL_INV_C(16x64) SVT_B200_DECL_INV_C(64x16)
+#undef SVT_B200_DECL_INV_A
+#undef SVT_B200_DECL_INV_B
+#undef SVT_B200_DECL_INV_C
+
+/* T2 work items.  Offsets are in ELEMENTS of the respective plane (int16 residual, int32 coeff,
+ * pixels). */
+typedef struct SvtB200FwdTxfmItem {
+    uint64_t src_off;    /* residual block origin */
+    uint64_t dst_off;    /* W*H contiguous int32 */
+    uint32_t src_stride;
+    uint8_t  tx_size;
+    uint8_t  tx_type;
+    uint16_t reserved;
+} SvtB200FwdTxfmItem;
+
+typedef struct SvtB200InvTxfmItem {
+    uint64_t coef_off;   /* min(W,32)*min(H,32) packed int32 */
+    uint64_t pred_off;   /* prediction read  (output_r) */
+    uint64_t recon_off;  /* reconstruction written (output_w) */
+    uint32_t pred_stride;
+    uint32_t recon_stride;
+    uint8_t  tx_size;
+    uint8_t  tx_type;
+    uint8_t  bd;
+    uint8_t  reserved;
+    uint32_t reserved2;
+} SvtB200InvTxfmItem;
+
+/* items must be ordered: the n_small items whose W*H <= 64 first, then the n_large others. */
+SVT_B200_API int svt_b200_fwd_txfm_batch_dev(const int16_t* d_residual, int32_t* d_coeff,
+                                             const SvtB200FwdTxfmItem* d_items, int n_small, int n_large,
+                                             int max_small_tx_size, int max_large_tx_size, void* stream);
+SVT_B200_API int svt_b200_inv_txfm_batch_dev(const int32_t* d_coeff, const void* d_pred, void* d_recon,
+                                             const SvtB200InvTxfmItem* d_items, int n_small, int n_large,
+                                             int max_small_tx_size, int max_large_tx_size, int pixel_bytes,
+                                             void* stream);
+/* any order; the library groups the items itself */
+SVT_B200_API int svt_b200_fwd_txfm_batch_host(const int16_t* residual, size_t residual_elems, int32_t* coeff,
+                                              size_t coeff_elems, const SvtB200FwdTxfmItem* items, int n_items);
+
 #ifdef __cplusplus
 }
 #endif

@@ -70,6 +70,7 @@ void     require_ready();  // aborts loudly when svt_b200_init() has not succeed
 Lane*    lane_acquire();
 void     lane_release(Lane* l);
 void     count_launch(int n = 1);
+void     txfm_tables_init();  // txfm.cu: uploads the transform constant tables
 
 struct LaneGuard {
     Lane* l;

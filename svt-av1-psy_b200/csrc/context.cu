@@ -85,6 +85,7 @@ extern "C" int svt_b200_init(int device) {
     c.device   = device;
     c.sm_count = p.multiProcessorCount;
     c.max_smem = (int)p.sharedMemPerBlockOptin;
+    txfm_tables_init();
     c.ready    = true;
     return SVT_B200_OK;
 }

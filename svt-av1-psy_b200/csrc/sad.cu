@@ -268,18 +268,19 @@ static void launch_sad_search(const uint8_t* d_src, const uint8_t* d_ref, const 
                               SvtB200SadSearchResult* d_results, size_t smem, cudaStream_t st) {
     if (n <= 0) return;
     Context& c = ctx();
-    if (smem > (size_t)c.max_smem) smem = c.max_smem;
+    const size_t dyn_max = (size_t)c.max_smem - 2048;  // opt-in limit minus this kernel's static shared memory
+    if (smem > dyn_max) smem = dyn_max;
     if (smem < 32 * 1024) smem = 32 * 1024;
     static std::mutex attr_mu;
     static size_t     attr_set = 0;
     {
         std::lock_guard<std::mutex> lk(attr_mu);
         if (smem > attr_set) {
-            B200_CUDA_CHECK(cudaFuncSetAttribute(sad_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.max_smem));
-            attr_set = c.max_smem;
+            B200_CUDA_CHECK(cudaFuncSetAttribute(sad_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_max));
+            attr_set = dyn_max;
         }
     }
-    int ctas_per_sm = (int)((size_t)c.max_smem / (smem + 1024));
+    int ctas_per_sm = (int)(dyn_max / (smem + 1024));
     if (ctas_per_sm < 1) ctas_per_sm = 1;
     if (ctas_per_sm > 8) ctas_per_sm = 8;
     int grid = grid_for(n, ctas_per_sm);

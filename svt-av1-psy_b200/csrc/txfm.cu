@@ -1,0 +1,413 @@
+// txfm.cu -- K5 forward 2-D transforms, K6 inverse 2-D transforms + reconstruction (sm_100a).
+//
+// Reference behaviour restated: av1_tranform_two_d_core_c (Source/Lib/Codec/transforms.c:2259-2324)
+// and inv_txfm2d_add_c (Source/Lib/Codec/inv_transforms.c:2459-2534), for all 19 transform sizes and
+// 16 transform types, 8/10/12-bit.  The 2-D configuration table (flips, per-pass kernel, cos_bit,
+// shifts) is dumped from the reference (txfm_cfg.inc); the 1-D networks are txfm_graphs.inc.
+//
+// B200 mapping: one thread TEAM per transform block -- a warp for blocks of <= 64 coefficients
+// (8 blocks per CTA), the whole 256-thread CTA above.  The block lives in two ping-pong shared-memory
+// planes in element-major order with an odd pitch, so the column pass, the transposing hand-over and
+// the row pass are all bank-conflict free; residual loads / coefficient stores are coalesced rows.
+#include "txfm_tables.cuh"
+#include "../../include/svt_b200.h"
+
+namespace b200 {
+
+static TxCfg h_txcfg[19][16];
+const TxCfg& host_txcfg(int size, int type) { return h_txcfg[size][type]; }
+
+void txfm_tables_init() {
+    // graph directory: walk the .inc once more, this time only for the BEGIN markers
+    struct Ent { int tag, n, st; };
+    enum { FDCT4, FDCT8, FDCT16, FDCT32, FDCT64, FADST8, FADST16, IDCT4, IDCT8, IDCT16, IDCT32, IDCT64, IADST8, IADST16 };
+    static const Ent ents[] = {
+#define TXG_BEGIN(tag, n, st) {tag, n, st},
+#define TXG_END(tag)
+#define TXG_NODE(...)
+#include "txfm_graphs.inc"
+#undef TXG_BEGIN
+#undef TXG_END
+#undef TXG_NODE
+    };
+    static const int tag2type[14][2] = {{0, TT_DCT4}, {0, TT_DCT8}, {0, TT_DCT16}, {0, TT_DCT32}, {0, TT_DCT64},
+                                        {0, TT_ADST8}, {0, TT_ADST16}, {1, TT_DCT4}, {1, TT_DCT8}, {1, TT_DCT16},
+                                        {1, TT_DCT32}, {1, TT_DCT64}, {1, TT_ADST8}, {1, TT_ADST16}};
+    GraphDesc gd[2][TT_TYPES];
+    memset(gd, 0, sizeof(gd));
+    int off = 0;
+    for (const Ent& e : ents) {
+        gd[tag2type[e.tag][0]][tag2type[e.tag][1]] = GraphDesc{off, e.n, e.st};
+        off += e.n * e.st;
+    }
+    B200_CUDA_CHECK(cudaMemcpyToSymbol(c_graph, gd, sizeof(gd)));
+
+    memset(h_txcfg, 0, sizeof(h_txcfg));
+    static int32_t cosv[7][64], sinv[7][5];
+#define TXC(sz, ty, v, fud, flr, fs0, fs1, fs2, fcbc, fcbr, ftc, ftr, iud, ilr, is0, is1, icbc, icbr, itc, itr) \
+    h_txcfg[sz][ty] = TxCfg{v, fud, flr, fs0, fs1, fs2, fcbc, fcbr, ftc, ftr, iud, ilr, is0, is1, icbc, icbr, itc, itr};
+#define TXCOS(bit, ...) { const int32_t t[64] = {__VA_ARGS__}; memcpy(cosv[bit - 10], t, sizeof(t)); }
+#define TXSIN(bit, ...) { const int32_t t[5] = {__VA_ARGS__}; memcpy(sinv[bit - 10], t, sizeof(t)); }
+#include "txfm_cfg.inc"
+#undef TXC
+#undef TXCOS
+#undef TXSIN
+    B200_CUDA_CHECK(cudaMemcpyToSymbol(c_txcfg, h_txcfg, sizeof(h_txcfg)));
+    B200_CUDA_CHECK(cudaMemcpyToSymbol(c_cospi, cosv, sizeof(cosv)));
+    B200_CUDA_CHECK(cudaMemcpyToSymbol(c_sinpi, sinv, sizeof(sinv)));
+}
+
+__host__ __device__ inline int rect_log_ratio(int w, int h) {  // get_rect_tx_log_ratio
+    if (w == h) return 0;
+    if (w > h) return w == 2 * h ? 1 : (w == 4 * h ? 2 : 3);
+    return h == 2 * w ? -1 : (h == 4 * w ? -2 : -3);
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward
+// ------------------------------------------------------------------------------------------------
+template <int TEAM>
+__global__ void __launch_bounds__(256)
+fwd_txfm_kernel(const int16_t* __restrict__ src_base, int32_t* __restrict__ dst_base,
+                const SvtB200FwdTxfmItem* __restrict__ items, int n_items, int plane_ints) {
+    extern __shared__ __align__(16) int32_t tsm[];
+    constexpr int TEAMS = 256 / TEAM;
+    const int     team  = threadIdx.x / TEAM, tid = threadIdx.x % TEAM;
+    int32_t*      A     = tsm + (size_t)team * 2 * plane_ints;
+    int32_t*      B     = A + plane_ints;
+
+    for (int it = blockIdx.x * TEAMS + team; it < n_items; it += gridDim.x * TEAMS) {
+        const SvtB200FwdTxfmItem item = items[it];
+        const int   sz = item.tx_size, W = tx_w(sz), H = tx_h(sz);
+        const TxCfg cfg = c_txcfg[sz][item.tx_type];
+        const int16_t* src = src_base + item.src_off;
+        int32_t*       dst = dst_base + item.dst_off;
+        const int P1 = W + 1, P2 = H + 1;
+        // load, optional up/down flip, pre-shift (transforms.c:2286-2294)
+        for (int idx = tid; idx < W * H; idx += TEAM) {
+            const int r = idx / W, c = idx - r * W;
+            const int rr = cfg.f_ud ? (H - 1 - r) : r;
+            A[r * P1 + c] = round_shift_arr((int32_t)src[(size_t)rr * item.src_stride + c], -cfg.f_s0);
+        }
+        team_sync<TEAM>();
+        int32_t* R = txfm_pass_1d<TEAM>(cfg.f_tc, 0, A, B, H, W, P1, cfg.f_cbc, 0, tid);
+        int32_t* O = (R == A) ? B : A;
+        // round-shift, optional left/right flip, hand over transposed (element = column)
+        for (int idx = tid; idx < W * H; idx += TEAM) {
+            const int r = idx / W, c = idx - r * W;
+            const int cc = cfg.f_lr ? (W - 1 - c) : c;
+            O[cc * P2 + r] = round_shift_arr(R[r * P1 + c], -cfg.f_s1);
+        }
+        team_sync<TEAM>();
+        int32_t* R2 = txfm_pass_1d<TEAM>(cfg.f_tr, 0, O, R, W, H, P2, cfg.f_cbr, 0, tid);
+        const int rect = rect_log_ratio(W, H);
+        for (int idx = tid; idx < W * H; idx += TEAM) {
+            const int r = idx / W, c = idx - r * W;
+            int32_t   v = round_shift_arr(R2[c * P2 + r], -cfg.f_s2);
+            if (rect == 1 || rect == -1) v = round_shift64((long long)v * kNewSqrt2, 12);
+            dst[idx] = v;
+        }
+        team_sync<TEAM>();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// inverse + reconstruction
+// ------------------------------------------------------------------------------------------------
+template <int TEAM, typename PIX>
+__global__ void __launch_bounds__(256)
+inv_txfm_kernel(const int32_t* __restrict__ coef_base, const PIX* __restrict__ pred_base, PIX* __restrict__ recon_base,
+                const SvtB200InvTxfmItem* __restrict__ items, int n_items, int plane_ints) {
+    extern __shared__ __align__(16) int32_t tsm[];
+    constexpr int TEAMS = 256 / TEAM;
+    const int     team  = threadIdx.x / TEAM, tid = threadIdx.x % TEAM;
+    int32_t*      A     = tsm + (size_t)team * 2 * plane_ints;
+    int32_t*      B     = A + plane_ints;
+
+    for (int it = blockIdx.x * TEAMS + team; it < n_items; it += gridDim.x * TEAMS) {
+        const SvtB200InvTxfmItem item = items[it];
+        const int   sz = item.tx_size, W = tx_w(sz), H = tx_h(sz), bd = item.bd;
+        const TxCfg cfg = c_txcfg[sz][item.tx_type];
+        const int32_t* in = coef_base + item.coef_off;
+        const int Wp = W > 32 ? 32 : W, Hp = H > 32 ? 32 : H;  // 64-point dims arrive packed (inv_transforms.c:2567-2686)
+        const int P1 = H + 1, P2 = W + 1;
+        const int rect = rect_log_ratio(W, H);
+        const int row_clamp = bd + 8;
+        const int col_clamp = (bd + 6) > 16 ? (bd + 6) : 16;
+        const int opt_row = bd == 8 ? 16 : (bd == 10 ? 18 : 20);  // svt_av1_gen_inv_stage_range
+        const int opt_col = bd == 12 ? 18 : 16;
+        // rows first: element = column, vector = row
+        for (int idx = tid; idx < W * H; idx += TEAM) {
+            const int r = idx / W, c = idx - r * W;
+            int32_t   v = (r < Hp && c < Wp) ? in[r * Wp + c] : 0;
+            if (rect == 1 || rect == -1) v = round_shift64((long long)v * kNewInvSqrt2, 12);
+            A[c * P1 + r] = clamp_bits(v, row_clamp);
+        }
+        team_sync<TEAM>();
+        int32_t* R = txfm_pass_1d<TEAM>(cfg.i_tr, 1, A, B, W, H, P1, cfg.i_cbr, opt_row, tid);
+        int32_t* O = (R == A) ? B : A;
+        for (int idx = tid; idx < W * H; idx += TEAM) {
+            const int r = idx / W, c = idx - r * W;
+            const int cs = cfg.i_lr ? (W - 1 - c) : c;
+            O[r * P2 + c] = clamp_bits(round_shift_arr(R[cs * P1 + r], -cfg.i_s0), col_clamp);
+        }
+        team_sync<TEAM>();
+        int32_t* R2 = txfm_pass_1d<TEAM>(cfg.i_tc, 1, O, R, H, W, P2, cfg.i_cbc, opt_col, tid);
+        const PIX* pr = pred_base + item.pred_off;
+        PIX*       pw = recon_base + item.recon_off;
+        const long long int_max = (1ll << (7 + bd)) - 1 + (914ll << (bd - 7));  // check_range, inv_transforms.c:2401
+        const int       pix_max = (1 << bd) - 1;
+        for (int idx = tid; idx < W * H; idx += TEAM) {
+            const int r = idx / W, c = idx - r * W;
+            const int rs = cfg.i_ud ? (H - 1 - r) : r;
+            long long t  = (long long)round_shift_arr(R2[rs * P2 + c], -cfg.i_s1);
+            t            = t < -int_max - 1 ? -int_max - 1 : (t > int_max ? int_max : t);
+            int p        = (int)pr[(size_t)r * item.pred_stride + c] + (int)t;
+            p            = p < 0 ? 0 : (p > pix_max ? pix_max : p);
+            pw[(size_t)r * item.recon_stride + c] = (PIX)p;
+        }
+        team_sync<TEAM>();
+    }
+}
+
+static inline int plane_ints_for(int sz) {
+    const int W = tx_w(sz), H = tx_h(sz);
+    const int a = H * (W + 1), b = W * (H + 1);
+    return ((a > b ? a : b) + 3) & ~3;
+}
+
+template <typename K>
+static void set_smem_attr(K kernel, size_t smem) {
+    if (smem > 48 * 1024) B200_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+}
+
+void launch_fwd_txfm(const int16_t* d_src, int32_t* d_dst, const SvtB200FwdTxfmItem* d_items, int n, int max_tx_size_plane,
+                     bool small, cudaStream_t st) {
+    if (n <= 0) return;
+    if (small) {
+        const size_t smem = (size_t)8 * 2 * max_tx_size_plane * 4;
+        fwd_txfm_kernel<32><<<grid_for((n + 7) / 8, 8), 256, smem, st>>>(d_src, d_dst, d_items, n, max_tx_size_plane);
+    } else {
+        const size_t smem = (size_t)2 * max_tx_size_plane * 4;
+        static bool attr = false;
+        if (!attr) { set_smem_attr(fwd_txfm_kernel<256>, 64 * 1024); attr = true; }
+        fwd_txfm_kernel<256><<<grid_for(n, smem > 24 * 1024 ? 4 : 8), 256, smem, st>>>(d_src, d_dst, d_items, n, max_tx_size_plane);
+    }
+    B200_LAUNCH_CHECK();
+}
+
+template <typename PIX>
+void launch_inv_txfm(const int32_t* d_coef, const PIX* d_pred, PIX* d_recon, const SvtB200InvTxfmItem* d_items, int n,
+                     int plane, bool small, cudaStream_t st) {
+    if (n <= 0) return;
+    if (small) {
+        const size_t smem = (size_t)8 * 2 * plane * 4;
+        inv_txfm_kernel<32, PIX><<<grid_for((n + 7) / 8, 8), 256, smem, st>>>(d_coef, d_pred, d_recon, d_items, n, plane);
+    } else {
+        const size_t smem = (size_t)2 * plane * 4;
+        static bool attr = false;
+        if (!attr) { set_smem_attr(inv_txfm_kernel<256, PIX>, 64 * 1024); attr = true; }
+        inv_txfm_kernel<256, PIX><<<grid_for(n, smem > 24 * 1024 ? 4 : 8), 256, smem, st>>>(d_coef, d_pred, d_recon, d_items, n, plane);
+    }
+    B200_LAUNCH_CHECK();
+}
+
+static inline bool is_small(int sz) { return tx_w(sz) * tx_h(sz) <= 64; }
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" int svt_b200_txfm_valid(int tx_size, int tx_type) {
+    if (tx_size < 0 || tx_size >= 19 || tx_type < 0 || tx_type >= 16) return 0;
+    require_ready();
+    return host_txcfg(tx_size, tx_type).valid;
+}
+
+extern "C" int svt_b200_fwd_txfm_batch_dev(const int16_t* d_residual, int32_t* d_coeff, const SvtB200FwdTxfmItem* d_items,
+                                           int n_small, int n_large, int max_small_tx_size, int max_large_tx_size,
+                                           void* stream) {
+    require_ready();
+    if (n_small > 0) launch_fwd_txfm(d_residual, d_coeff, d_items, n_small, plane_ints_for(max_small_tx_size), true, (cudaStream_t)stream);
+    if (n_large > 0)
+        launch_fwd_txfm(d_residual, d_coeff, d_items + n_small, n_large, plane_ints_for(max_large_tx_size), false, (cudaStream_t)stream);
+    return SVT_B200_OK;
+}
+
+extern "C" int svt_b200_inv_txfm_batch_dev(const int32_t* d_coeff, const void* d_pred, void* d_recon,
+                                           const SvtB200InvTxfmItem* d_items, int n_small, int n_large,
+                                           int max_small_tx_size, int max_large_tx_size, int pixel_bytes, void* stream) {
+    require_ready();
+    cudaStream_t st = (cudaStream_t)stream;
+    if (pixel_bytes == 1) {
+        if (n_small > 0) launch_inv_txfm<uint8_t>(d_coeff, (const uint8_t*)d_pred, (uint8_t*)d_recon, d_items, n_small, plane_ints_for(max_small_tx_size), true, st);
+        if (n_large > 0) launch_inv_txfm<uint8_t>(d_coeff, (const uint8_t*)d_pred, (uint8_t*)d_recon, d_items + n_small, n_large, plane_ints_for(max_large_tx_size), false, st);
+    } else if (pixel_bytes == 2) {
+        if (n_small > 0) launch_inv_txfm<uint16_t>(d_coeff, (const uint16_t*)d_pred, (uint16_t*)d_recon, d_items, n_small, plane_ints_for(max_small_tx_size), true, st);
+        if (n_large > 0) launch_inv_txfm<uint16_t>(d_coeff, (const uint16_t*)d_pred, (uint16_t*)d_recon, d_items + n_small, n_large, plane_ints_for(max_large_tx_size), false, st);
+    } else
+        return SVT_B200_ERR_BAD_ARG;
+    return SVT_B200_OK;
+}
+
+// ---- T1: svt_av1_fwd_txfm2d_WxH (aom_dsp_rtcd.h:121-197; C: transforms.c:2388-2631) ----------------
+extern "C" void svt_b200_fwd_txfm2d(int16_t* input, int32_t* output, uint32_t input_stride, int tx_type, int tx_size,
+                                    uint8_t bit_depth) {
+    (void)bit_depth;  // the forward arithmetic does not depend on it (stage ranges are assert-only)
+    require_ready();
+    const int W = tx_w(tx_size), H = tx_h(tx_size);
+    if (!host_txcfg(tx_size, tx_type).valid) {
+        fprintf(stderr, "[svt_b200] FATAL: invalid (tx_size=%d, tx_type=%d)\n", tx_size, tx_type);
+        abort();
+    }
+    LaneGuard l;
+    size_t o_src = l->alloc((size_t)W * H * 2), o_it = l->alloc(sizeof(SvtB200FwdTxfmItem));
+    size_t in_end = l->used;
+    size_t o_dst = l->alloc((size_t)W * H * 4);
+    for (int r = 0; r < H; r++) memcpy(l->h<int16_t>(o_src) + r * W, input + (size_t)r * input_stride, W * 2);
+    SvtB200FwdTxfmItem* it = l->h<SvtB200FwdTxfmItem>(o_it);
+    memset(it, 0, sizeof(*it));
+    it->src_stride = W;
+    it->tx_size = (uint8_t)tx_size;
+    it->tx_type = (uint8_t)tx_type;
+    l->h2d(0, in_end);
+    const bool small = is_small(tx_size);
+    launch_fwd_txfm(l->d<int16_t>(o_src), l->d<int32_t>(o_dst), l->d<SvtB200FwdTxfmItem>(o_it), 1, plane_ints_for(tx_size), small, l->stream);
+    l->d2h(o_dst, (size_t)W * H * 4);
+    l->sync();
+    memcpy(output, l->h<int32_t>(o_dst), (size_t)W * H * 4);
+}
+
+// ---- T1: svt_av1_inv_txfm2d_add_WxH (common_dsp_rtcd.h:106-142; C: inv_transforms.c:2545-2716) ----
+extern "C" void svt_b200_inv_txfm2d_add(const int32_t* input, uint16_t* output_r, int32_t stride_r, uint16_t* output_w,
+                                        int32_t stride_w, int tx_type, int tx_size, int32_t bd) {
+    require_ready();
+    const int W = tx_w(tx_size), H = tx_h(tx_size);
+    const int Wp = W > 32 ? 32 : W, Hp = H > 32 ? 32 : H;
+    if (!host_txcfg(tx_size, tx_type).valid) {
+        fprintf(stderr, "[svt_b200] FATAL: invalid (tx_size=%d, tx_type=%d)\n", tx_size, tx_type);
+        abort();
+    }
+    LaneGuard l;
+    size_t o_in = l->alloc((size_t)Wp * Hp * 4), o_pred = l->alloc((size_t)W * H * 2), o_it = l->alloc(sizeof(SvtB200InvTxfmItem));
+    size_t in_end = l->used;
+    size_t o_out = l->alloc((size_t)W * H * 2);
+    memcpy(l->h<int32_t>(o_in), input, (size_t)Wp * Hp * 4);
+    for (int r = 0; r < H; r++) memcpy(l->h<uint16_t>(o_pred) + r * W, output_r + (size_t)r * stride_r, W * 2);
+    SvtB200InvTxfmItem* it = l->h<SvtB200InvTxfmItem>(o_it);
+    memset(it, 0, sizeof(*it));
+    it->pred_stride = it->recon_stride = W;
+    it->tx_size = (uint8_t)tx_size;
+    it->tx_type = (uint8_t)tx_type;
+    it->bd = (uint8_t)bd;
+    l->h2d(0, in_end);
+    launch_inv_txfm<uint16_t>(l->d<int32_t>(o_in), l->d<uint16_t>(o_pred), l->d<uint16_t>(o_out), l->d<SvtB200InvTxfmItem>(o_it), 1,
+                              plane_ints_for(tx_size), is_small(tx_size), l->stream);
+    l->d2h(o_out, (size_t)W * H * 2);
+    l->sync();
+    for (int r = 0; r < H; r++) memcpy(output_w + (size_t)r * stride_w, l->h<uint16_t>(o_out) + r * W, W * 2);
+}
+
+// T2 host variants: caller-owned host planes, one call per batch.
+extern "C" int svt_b200_fwd_txfm_batch_host(const int16_t* residual, size_t residual_elems, int32_t* coeff, size_t coeff_elems,
+                                            const SvtB200FwdTxfmItem* items, int n_items) {
+    require_ready();
+    if (n_items <= 0) return n_items == 0 ? SVT_B200_OK : SVT_B200_ERR_BAD_ARG;
+    LaneGuard l;
+    size_t o_src = l->alloc(residual_elems * 2), o_it = l->alloc(sizeof(SvtB200FwdTxfmItem) * n_items);
+    size_t in_end = l->used;
+    size_t o_dst = l->alloc(coeff_elems * 4);
+    memcpy(l->h<int16_t>(o_src), residual, residual_elems * 2);
+    SvtB200FwdTxfmItem* hi = l->h<SvtB200FwdTxfmItem>(o_it);
+    int ns = 0, nl = 0, ps_max = 0, pl_max = 0;
+    for (int i = 0; i < n_items; i++) {
+        if (items[i].tx_size >= 19 || !host_txcfg(items[i].tx_size, items[i].tx_type).valid) return SVT_B200_ERR_BAD_ARG;
+        if (is_small(items[i].tx_size)) ns++;
+    }
+    int ps = 0, pl = ns;
+    for (int i = 0; i < n_items; i++) {
+        const int sz = items[i].tx_size, pi = plane_ints_for(sz);
+        if (is_small(sz)) {
+            hi[ps++] = items[i];
+            if (pi > ps_max) ps_max = pi;
+        } else {
+            hi[pl++] = items[i];
+            nl++;
+            if (pi > pl_max) pl_max = pi;
+        }
+    }
+    l->h2d(0, in_end);
+    if (ns) launch_fwd_txfm(l->d<int16_t>(o_src), l->d<int32_t>(o_dst), l->d<SvtB200FwdTxfmItem>(o_it), ns, ps_max, true, l->stream);
+    if (nl) launch_fwd_txfm(l->d<int16_t>(o_src), l->d<int32_t>(o_dst), l->d<SvtB200FwdTxfmItem>(o_it) + ns, nl, pl_max, false, l->stream);
+    l->d2h(o_dst, coeff_elems * 4);
+    l->sync();
+    // only the regions the items cover were written; copy those back
+    for (int i = 0; i < n_items; i++) {
+        const int W = tx_w(items[i].tx_size), H = tx_h(items[i].tx_size);
+        memcpy(coeff + items[i].dst_off, l->h<int32_t>(o_dst) + items[i].dst_off, (size_t)W * H * 4);
+    }
+    return SVT_B200_OK;
+}
+
+extern "C" void svt_b200_inv_txfm_add_8bit(const int32_t* dqcoeff, uint8_t* dst_r, int32_t stride_r, uint8_t* dst_w,
+                                           int32_t stride_w, int tx_type, int tx_size) {
+    require_ready();
+    const int W = tx_w(tx_size), H = tx_h(tx_size);
+    const int Wp = W > 32 ? 32 : W, Hp = H > 32 ? 32 : H;
+    if (!host_txcfg(tx_size, tx_type).valid) {
+        fprintf(stderr, "[svt_b200] FATAL: invalid (tx_size=%d, tx_type=%d)\n", tx_size, tx_type);
+        abort();
+    }
+    LaneGuard l;
+    size_t o_in = l->alloc((size_t)Wp * Hp * 4), o_pred = l->alloc((size_t)W * H), o_it = l->alloc(sizeof(SvtB200InvTxfmItem));
+    size_t in_end = l->used;
+    size_t o_out = l->alloc((size_t)W * H);
+    memcpy(l->h<int32_t>(o_in), dqcoeff, (size_t)Wp * Hp * 4);
+    for (int r = 0; r < H; r++) memcpy(l->h<uint8_t>(o_pred) + r * W, dst_r + (size_t)r * stride_r, W);
+    SvtB200InvTxfmItem* it = l->h<SvtB200InvTxfmItem>(o_it);
+    memset(it, 0, sizeof(*it));
+    it->pred_stride = it->recon_stride = W;
+    it->tx_size = (uint8_t)tx_size;
+    it->tx_type = (uint8_t)tx_type;
+    it->bd = 8;
+    l->h2d(0, in_end);
+    launch_inv_txfm<uint8_t>(l->d<int32_t>(o_in), l->d<uint8_t>(o_pred), l->d<uint8_t>(o_out), l->d<SvtB200InvTxfmItem>(o_it), 1,
+                             plane_ints_for(tx_size), is_small(tx_size), l->stream);
+    l->d2h(o_out, (size_t)W * H);
+    l->sync();
+    for (int r = 0; r < H; r++) memcpy(dst_w + (size_t)r * stride_w, l->h<uint8_t>(o_out) + r * W, W);
+}
+
+// ---- named T1 wrappers: one symbol per reference function pointer --------------------------------
+#define B200_FWD(WxH, SZ)                                                                                       \
+    extern "C" void svt_b200_av1_fwd_txfm2d_##WxH(int16_t* input, int32_t* output, uint32_t input_stride,        \
+                                                  int transform_type, uint8_t bit_depth) {                       \
+        svt_b200_fwd_txfm2d(input, output, input_stride, transform_type, SZ, bit_depth);                         \
+    }
+B200_FWD(4x4, 0) B200_FWD(8x8, 1) B200_FWD(16x16, 2) B200_FWD(32x32, 3) B200_FWD(64x64, 4) B200_FWD(4x8, 5) B200_FWD(8x4, 6)
+B200_FWD(8x16, 7) B200_FWD(16x8, 8) B200_FWD(16x32, 9) B200_FWD(32x16, 10) B200_FWD(32x64, 11) B200_FWD(64x32, 12)
+B200_FWD(4x16, 13) B200_FWD(16x4, 14) B200_FWD(8x32, 15) B200_FWD(32x8, 16) B200_FWD(16x64, 17) B200_FWD(64x16, 18)
+#define B200_INV_A(WxH, SZ)                                                                                     \
+    extern "C" void svt_b200_av1_inv_txfm2d_add_##WxH(const int32_t* input, uint16_t* output_r, int32_t stride_r, \
+                                                      uint16_t* output_w, int32_t stride_w, int tx_type, int32_t bd) { \
+        svt_b200_inv_txfm2d_add(input, output_r, stride_r, output_w, stride_w, tx_type, SZ, bd);                 \
+    }
+#define B200_INV_B(WxH, SZ)                                                                                     \
+    extern "C" void svt_b200_av1_inv_txfm2d_add_##WxH(const int32_t* input, uint16_t* output_r, int32_t stride_r, \
+                                                      uint16_t* output_w, int32_t stride_w, int tx_type,         \
+                                                      int tx_size, int32_t bd) {                                 \
+        (void)tx_size;                                                                                           \
+        svt_b200_inv_txfm2d_add(input, output_r, stride_r, output_w, stride_w, tx_type, SZ, bd);                 \
+    }
+#define B200_INV_C(WxH, SZ)                                                                                     \
+    extern "C" void svt_b200_av1_inv_txfm2d_add_##WxH(const int32_t* input, uint16_t* output_r, int32_t stride_r, \
+                                                      uint16_t* output_w, int32_t stride_w, int tx_type,         \
+                                                      int tx_size, int32_t eob, int32_t bd) {                    \
+        (void)tx_size;                                                                                           \
+        (void)eob;                                                                                               \
+        svt_b200_inv_txfm2d_add(input, output_r, stride_r, output_w, stride_w, tx_type, SZ, bd);                 \
+    }
+B200_INV_A(4x4, 0) B200_INV_A(8x8, 1) B200_INV_A(16x16, 2) B200_INV_A(32x32, 3) B200_INV_A(64x64, 4)
+B200_INV_B(4x8, 5) B200_INV_B(8x4, 6) B200_INV_B(4x16, 13) B200_INV_B(16x4, 14)
+B200_INV_C(8x16, 7) B200_INV_C(16x8, 8) B200_INV_C(16x32, 9) B200_INV_C(32x16, 10) B200_INV_C(32x64, 11) B200_INV_C(64x32, 12)
+B200_INV_C(8x32, 15) B200_INV_C(32x8, 16) B200_INV_C(16x64, 17) B200_INV_C(64x16, 18)

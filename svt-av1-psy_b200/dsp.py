@@ -119,3 +119,70 @@ def sad_search_batch_host(src_plane, ref_plane, items):
     return res
 
 
+
+# ------------------------------------------------------------------------------------------------
+# K5 / K6 transforms
+# ------------------------------------------------------------------------------------------------
+TX_W = [4, 8, 16, 32, 64, 4, 8, 8, 16, 16, 32, 32, 64, 4, 16, 8, 32, 16, 64]
+TX_H = [4, 8, 16, 32, 64, 8, 4, 16, 8, 32, 16, 64, 32, 16, 4, 32, 8, 64, 16]
+TX_NAME = ["%dx%d" % (w, h) for w, h in zip(TX_W, TX_H)]
+
+FWD_ITEM_DTYPE = np.dtype([("src_off", "<u8"), ("dst_off", "<u8"), ("src_stride", "<u4"), ("tx_size", "u1"),
+                           ("tx_type", "u1"), ("reserved", "<u2")])
+INV_ITEM_DTYPE = np.dtype([("coef_off", "<u8"), ("pred_off", "<u8"), ("recon_off", "<u8"), ("pred_stride", "<u4"),
+                           ("recon_stride", "<u4"), ("tx_size", "u1"), ("tx_type", "u1"), ("bd", "u1"),
+                           ("reserved", "u1"), ("reserved2", "<u4")])
+assert FWD_ITEM_DTYPE.itemsize == 24 and INV_ITEM_DTYPE.itemsize == 40
+
+lib.svt_b200_txfm_valid.argtypes = [ct.c_int, ct.c_int]
+lib.svt_b200_txfm_valid.restype = ct.c_int
+lib.svt_b200_fwd_txfm2d.argtypes = [vp, vp, ct.c_uint32, ct.c_int, ct.c_int, ct.c_uint8]
+lib.svt_b200_fwd_txfm2d.restype = None
+lib.svt_b200_inv_txfm2d_add.argtypes = [vp, vp, ct.c_int32, vp, ct.c_int32, ct.c_int, ct.c_int, ct.c_int32]
+lib.svt_b200_inv_txfm2d_add.restype = None
+lib.svt_b200_inv_txfm_add_8bit.argtypes = [vp, vp, ct.c_int32, vp, ct.c_int32, ct.c_int, ct.c_int]
+lib.svt_b200_inv_txfm_add_8bit.restype = None
+lib.svt_b200_fwd_txfm_batch_host.argtypes = [vp, ct.c_size_t, vp, ct.c_size_t, vp, ct.c_int]
+lib.svt_b200_fwd_txfm_batch_host.restype = ct.c_int
+lib.svt_b200_fwd_txfm_batch_dev.argtypes = [vp, vp, vp, ct.c_int, ct.c_int, ct.c_int, ct.c_int, vp]
+lib.svt_b200_fwd_txfm_batch_dev.restype = ct.c_int
+lib.svt_b200_inv_txfm_batch_dev.argtypes = [vp, vp, vp, vp, ct.c_int, ct.c_int, ct.c_int, ct.c_int, ct.c_int, vp]
+lib.svt_b200_inv_txfm_batch_dev.restype = ct.c_int
+
+
+def txfm_valid(tx_size, tx_type):
+    return bool(lib.svt_b200_txfm_valid(tx_size, tx_type))
+
+
+def svt_av1_fwd_txfm2d(residual, stride, tx_type, tx_size, bit_depth=8, named=False):
+    """svt_av1_fwd_txfm2d_WxH: int16 residual (flat, `stride`) -> int32[W*H]."""
+    out = np.zeros(TX_W[tx_size] * TX_H[tx_size], np.int32)
+    if named:
+        f = getattr(lib, "svt_b200_av1_fwd_txfm2d_" + TX_NAME[tx_size])
+        f.argtypes = [vp, vp, ct.c_uint32, ct.c_int, ct.c_uint8]
+        f.restype = None
+        f(_ptr(residual), _ptr(out), stride, tx_type, bit_depth)
+    else:
+        lib.svt_b200_fwd_txfm2d(_ptr(residual), _ptr(out), stride, tx_type, tx_size, bit_depth)
+    return out
+
+
+def svt_av1_inv_txfm2d_add(coeff, pred, stride_r, stride_w, tx_type, tx_size, bd):
+    """svt_av1_inv_txfm2d_add_WxH on uint16 pixels; returns the written recon plane (H*stride_w)."""
+    out = np.zeros(TX_H[tx_size] * stride_w, np.uint16)
+    lib.svt_b200_inv_txfm2d_add(_ptr(coeff), _ptr(pred), stride_r, _ptr(out), stride_w, tx_type, tx_size, bd)
+    return out
+
+
+def svt_av1_inv_txfm_add(coeff, pred8, stride_r, stride_w, tx_type, tx_size):
+    out = np.zeros(TX_H[tx_size] * stride_w, np.uint8)
+    lib.svt_b200_inv_txfm_add_8bit(_ptr(coeff), _ptr(pred8), stride_r, _ptr(out), stride_w, tx_type, tx_size)
+    return out
+
+
+def fwd_txfm_batch_host(residual, coeff, items):
+    items = np.ascontiguousarray(items, dtype=FWD_ITEM_DTYPE)
+    rc = lib.svt_b200_fwd_txfm_batch_host(_ptr(residual), residual.size, _ptr(coeff), coeff.size, _ptr(items), len(items))
+    if rc != 0:
+        raise RuntimeError("svt_b200_fwd_txfm_batch_host rc=%d" % rc)
+    return coeff

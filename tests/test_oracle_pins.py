@@ -23,3 +23,44 @@ def test_port_sad_loop_matches_reference(oracle, refc, pattern):
                 b = sad_loop_call(refc, "svt_sad_loop_kernel_c", src, 0, src_stride, ref, 0, ref_stride, bh, bw,
                                   ref_stride, skip, sa_w, sa_h, -7, -9)
                 assert a == b, (bw, bh, sa_w, sa_h, skip)
+
+
+# ---- transforms: restatement vs unmodified reference, every size x valid type ------------------
+from txfm_helpers import (TX_H, TX_W, coeff_input, mask_written, port_fwd, port_inv, ref_fwd, ref_inv,  # noqa: E402
+                          residual_input, valid)
+
+
+def test_port_txfm_valid_table(oracle):
+    for sz in range(19):
+        for ty in range(16):
+            assert bool(oracle.port.port_txfm_valid(sz, ty)) == valid(sz, ty)
+
+
+@pytest.mark.parametrize("kind", ["random", "max", "min"])
+def test_port_fwd_txfm_matches_reference(oracle, refc, kind):
+    r = rng(10)
+    for sz in range(19):
+        for ty in range(16):
+            if not valid(sz, ty):
+                continue
+            for bd in (8, 10):
+                res, stride = residual_input(r, sz, bd, kind)
+                a = port_fwd(oracle.port, res, stride, ty, sz)
+                b = ref_fwd(refc, res, stride, ty, sz, bd)
+                assert np.array_equal(a, b), (sz, ty, bd)
+
+
+@pytest.mark.parametrize("kind", ["real", "sparse", "dc", "extreme", "zero"])
+def test_port_inv_txfm_matches_reference(oracle, refc, kind):
+    r = rng(11)
+    for sz in range(19):
+        for ty in range(16):
+            if not valid(sz, ty):
+                continue
+            for bd in (8, 10):
+                w, h = TX_W[sz], TX_H[sz]
+                c = coeff_input(r, sz, bd, kind, lambda res, st: ref_fwd(refc, res, st, ty, sz, bd))
+                pred = r.integers(0, 1 << bd, h * (w + 5)).astype(np.uint16)
+                a = port_inv(oracle.port, c, pred, w + 5, w + 2, ty, sz, bd)
+                b = ref_inv(refc, c, pred, w + 5, w + 2, ty, sz, bd)
+                assert np.array_equal(mask_written(a, w + 2, w, h), mask_written(b, w + 2, w, h)), (sz, ty, bd)
