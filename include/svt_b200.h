@@ -195,6 +195,50 @@ SVT_B200_API int svt_b200_inv_txfm_batch_dev(const int32_t* d_coeff, const void*
 SVT_B200_API int svt_b200_fwd_txfm_batch_host(const int16_t* residual, size_t residual_elems, int32_t* coeff,
                                               size_t coeff_elems, const SvtB200FwdTxfmItem* items, int n_items);
 
+/* ------------------------------------------------------------------------------------------ */
+/* K7  quantize / dequantize  (reference: Source/Lib/Codec/full_loop.c:29-516)                  */
+/* ------------------------------------------------------------------------------------------ */
+/* T1: identical argument lists to svt_aom_quantize_b / svt_aom_highbd_quantize_b /
+ * svt_av1_quantize_b_qm / svt_av1_highbd_quantize_b_qm / svt_av1_quantize_fp{,_32x32,_64x64,_qm} /
+ * svt_av1_highbd_quantize_fp{,_qm} (aom_dsp_rtcd.h:247-263).  TranLow = int32_t, QmVal = uint8_t. */
+#define SVT_B200_QARGS                                                                                         \
+    const int32_t *coeff_ptr, intptr_t n_coeffs, const int16_t *zbin_ptr, const int16_t *round_ptr,            \
+        const int16_t *quant_ptr, const int16_t *quant_shift_ptr, int32_t *qcoeff_ptr, int32_t *dqcoeff_ptr,   \
+        const int16_t *dequant_ptr, uint16_t *eob_ptr, const int16_t *scan, const int16_t *iscan
+SVT_B200_API void svt_b200_aom_quantize_b(SVT_B200_QARGS, const uint8_t* qm_ptr, const uint8_t* iqm_ptr, int32_t log_scale);
+SVT_B200_API void svt_b200_aom_highbd_quantize_b(SVT_B200_QARGS, const uint8_t* qm_ptr, const uint8_t* iqm_ptr, int32_t log_scale);
+SVT_B200_API void svt_b200_av1_quantize_b_qm(SVT_B200_QARGS, const uint8_t* qm_ptr, const uint8_t* iqm_ptr, int32_t log_scale);
+SVT_B200_API void svt_b200_av1_highbd_quantize_b_qm(SVT_B200_QARGS, const uint8_t* qm_ptr, const uint8_t* iqm_ptr, int32_t log_scale);
+SVT_B200_API void svt_b200_av1_quantize_fp(SVT_B200_QARGS);
+SVT_B200_API void svt_b200_av1_quantize_fp_32x32(SVT_B200_QARGS);
+SVT_B200_API void svt_b200_av1_quantize_fp_64x64(SVT_B200_QARGS);
+SVT_B200_API void svt_b200_av1_quantize_fp_qm(SVT_B200_QARGS, const uint8_t* qm_ptr, const uint8_t* iqm_ptr, int16_t log_scale);
+SVT_B200_API void svt_b200_av1_highbd_quantize_fp(SVT_B200_QARGS, int16_t log_scale);
+SVT_B200_API void svt_b200_av1_highbd_quantize_fp_qm(SVT_B200_QARGS, const uint8_t* qm_ptr, const uint8_t* iqm_ptr, int16_t log_scale);
+#undef SVT_B200_QARGS
+
+enum { SVT_B200_QUANT_B_LBD = 0, SVT_B200_QUANT_B_HBD = 1, SVT_B200_QUANT_FP_LBD = 2, SVT_B200_QUANT_FP_HBD = 3 };
+#define SVT_B200_NO_QM 0xffffffffu
+
+/* T2 work item: one coefficient block.  Offsets in elements of the respective base array. */
+typedef struct SvtB200QuantItem {
+    uint64_t coeff_off;
+    uint64_t q_off;
+    uint64_t dq_off;
+    uint32_t scan_off;   /* into the int16 scan-table buffer */
+    uint32_t qm_off;     /* into the uint8 QM buffer, SVT_B200_NO_QM = no matrix */
+    uint32_t iqm_off;
+    uint32_t n_coeffs;
+    int16_t  zbin[2], round[2], quant[2], quant_shift[2], dequant[2]; /* [0]=DC, [1]=AC (MacroblockPlane *_qtx) */
+    uint8_t  mode;       /* SVT_B200_QUANT_* */
+    uint8_t  log_scale;
+    uint16_t reserved;
+} SvtB200QuantItem;
+
+SVT_B200_API int svt_b200_quant_batch_dev(const int32_t* d_coeff, int32_t* d_qcoeff, int32_t* d_dqcoeff,
+                                          const int16_t* d_scan, const uint8_t* d_qm, const SvtB200QuantItem* d_items,
+                                          int n_items, uint16_t* d_eobs, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

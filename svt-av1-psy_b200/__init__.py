@@ -27,8 +27,8 @@ lib = _ct.CDLL(LIB_PATH)
 
 def declared_symbols():
     """Names of all functions declared SVT_B200_API in include/svt_b200.h."""
-    txt = open(HEADER_PATH).read()
-    txt = _re.sub(r"/\*.*?\*/", "", txt, flags=_re.S)
+    import subprocess as _sp
+    txt = _sp.run(["gcc", "-E", "-P", HEADER_PATH], capture_output=True, text=True, check=True).stdout
     return sorted(set(_re.findall(r"\b(svt_b200_\w+)\s*\(", txt)))
 
 

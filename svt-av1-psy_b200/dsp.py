@@ -186,3 +186,46 @@ def fwd_txfm_batch_host(residual, coeff, items):
     if rc != 0:
         raise RuntimeError("svt_b200_fwd_txfm_batch_host rc=%d" % rc)
     return coeff
+
+# ------------------------------------------------------------------------------------------------
+# K7 quantize / dequantize
+# ------------------------------------------------------------------------------------------------
+QUANT_B_LBD, QUANT_B_HBD, QUANT_FP_LBD, QUANT_FP_HBD = 0, 1, 2, 3
+NO_QM = 0xffffffff
+QUANT_ITEM_DTYPE = np.dtype([("coeff_off", "<u8"), ("q_off", "<u8"), ("dq_off", "<u8"), ("scan_off", "<u4"),
+                             ("qm_off", "<u4"), ("iqm_off", "<u4"), ("n_coeffs", "<u4"), ("zbin", "<i2", 2),
+                             ("round", "<i2", 2), ("quant", "<i2", 2), ("quant_shift", "<i2", 2), ("dequant", "<i2", 2),
+                             ("mode", "u1"), ("log_scale", "u1"), ("reserved", "<u2")])
+assert QUANT_ITEM_DTYPE.itemsize == 64
+_QA = [vp, ct.c_ssize_t, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+for _n, _extra in (("aom_quantize_b", [vp, vp, ct.c_int32]), ("aom_highbd_quantize_b", [vp, vp, ct.c_int32]),
+                   ("av1_quantize_b_qm", [vp, vp, ct.c_int32]), ("av1_highbd_quantize_b_qm", [vp, vp, ct.c_int32]),
+                   ("av1_quantize_fp", []), ("av1_quantize_fp_32x32", []), ("av1_quantize_fp_64x64", []),
+                   ("av1_quantize_fp_qm", [vp, vp, ct.c_int16]), ("av1_highbd_quantize_fp", [ct.c_int16]),
+                   ("av1_highbd_quantize_fp_qm", [vp, vp, ct.c_int16])):
+    _f = getattr(lib, "svt_b200_" + _n)
+    _f.argtypes = _QA + _extra
+    _f.restype = None
+lib.svt_b200_quant_batch_dev.argtypes = [vp, vp, vp, vp, vp, vp, ct.c_int, vp, vp]
+lib.svt_b200_quant_batch_dev.restype = ct.c_int
+
+
+def quantize(name, coeff, tables, scan, qm=None, iqm=None, log_scale=None):
+    """Call the T1 quantizer `name` (reference pointer name without the svt_ prefix, e.g.
+    'aom_quantize_b', 'av1_quantize_fp_qm').  tables = dict(zbin, round, quant, quant_shift, dequant) of
+    int16[2].  Returns (qcoeff, dqcoeff, eob)."""
+    n = coeff.size
+    q = np.full(n, 0x5a5a5a5a, np.int32)
+    dq = np.full(n, 0x5a5a5a5a, np.int32)
+    eob = ct.c_uint16(0xffff)
+    args = [_ptr(coeff), n, _ptr(tables["zbin"]), _ptr(tables["round"]), _ptr(tables["quant"]),
+            _ptr(tables["quant_shift"]), _ptr(q), _ptr(dq), _ptr(tables["dequant"]), ct.cast(ct.byref(eob), vp),
+            _ptr(scan), _ptr(scan)]
+    f = getattr(lib, "svt_b200_" + name)
+    nextra = len(f.argtypes) - 12
+    if nextra == 3:
+        args += [_ptr(qm), _ptr(iqm), log_scale]
+    elif nextra == 1:
+        args += [log_scale]
+    f(*args)
+    return q, dq, int(eob.value)

@@ -64,3 +64,18 @@ def test_port_inv_txfm_matches_reference(oracle, refc, kind):
                 a = port_inv(oracle.port, c, pred, w + 5, w + 2, ty, sz, bd)
                 b = ref_inv(refc, c, pred, w + 5, w + 2, ty, sz, bd)
                 assert np.array_equal(mask_written(a, w + 2, w, h), mask_written(b, w + 2, w, h)), (sz, ty, bd)
+
+
+# ---- quantizers -----------------------------------------------------------------------------------
+import quant_helpers as qh  # noqa: E402
+
+
+def test_port_quantizers_match_reference(oracle, refc):
+    r = rng(30)
+    n = 0
+    for v, c, t, sc, qm, iqm, ls in qh.cases(r):
+        a = qh.call_port(oracle.port, v[2], c, t, sc, qm, iqm, ls)
+        b = qh.call_ref(refc, v[1], c, t, sc, qh.ref_extra(v, qm, iqm, ls))
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and a[2] == b[2], (v[0], c.size, ls, qm is not None)
+        n += 1
+    assert n > 1000
