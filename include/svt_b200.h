@@ -239,6 +239,69 @@ SVT_B200_API int svt_b200_quant_batch_dev(const int32_t* d_coeff, int32_t* d_qco
                                           const int16_t* d_scan, const uint8_t* d_qm, const SvtB200QuantItem* d_items,
                                           int n_items, uint16_t* d_eobs, void* stream);
 
+/* ------------------------------------------------------------------------------------------ */
+/* K4  Hadamard / SATD  (reference: Source/Lib/C_DEFAULT/picture_operators_c.c:188-330)        */
+/* ------------------------------------------------------------------------------------------ */
+/* T1: svt_aom_hadamard_{4x4,8x8,16x16,32x32} (common_dsp_rtcd.h:1075-1083), svt_aom_satd (:210). */
+SVT_B200_API void svt_b200_aom_hadamard_4x4(const int16_t* src_diff, ptrdiff_t src_stride, int32_t* coeff);
+SVT_B200_API void svt_b200_aom_hadamard_8x8(const int16_t* src_diff, ptrdiff_t src_stride, int32_t* coeff);
+SVT_B200_API void svt_b200_aom_hadamard_16x16(const int16_t* src_diff, ptrdiff_t src_stride, int32_t* coeff);
+SVT_B200_API void svt_b200_aom_hadamard_32x32(const int16_t* src_diff, ptrdiff_t src_stride, int32_t* coeff);
+SVT_B200_API int  svt_b200_aom_satd(const int32_t* coeff, int length);
+
+typedef struct SvtB200HadamardItem {
+    uint64_t src_off;    /* int16 residual elements */
+    uint64_t coeff_off;  /* int32 elements (ignored when no coefficient plane is given) */
+    uint32_t src_stride;
+    uint32_t size;       /* 4, 8, 16 or 32 */
+} SvtB200HadamardItem;
+/* T2: fused Hadamard + sum|coeff| per item; d_coeff_or_null may be NULL (SATD only). */
+SVT_B200_API int svt_b200_hadamard_satd_batch_dev(const int16_t* d_residual, const SvtB200HadamardItem* d_items,
+                                                  int n_items, int32_t* d_coeff_or_null, int32_t* d_satd, void* stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* K2  SAD pyramid + full-pel search  (reference: Source/Lib/Codec/motion_estimation.c:98-817) */
+/* ------------------------------------------------------------------------------------------ */
+/* T1: identical argument lists to aom_dsp_rtcd.h:842-855 (bool passed as uint8_t). */
+SVT_B200_API void svt_b200_ext_all_sad_calculation_8x8_16x16(uint8_t* src, uint32_t src_stride, uint8_t* ref,
+                                                             uint32_t ref_stride, uint32_t mv, uint32_t* p_best_sad_8x8,
+                                                             uint32_t* p_best_sad_16x16, uint32_t* p_best_mv8x8,
+                                                             uint32_t* p_best_mv16x16, uint32_t p_eight_sad16x16[16][8],
+                                                             uint32_t p_eight_sad8x8[64][8], uint8_t sub_sad);
+SVT_B200_API void svt_b200_ext_eight_sad_calculation_32x32_64x64(uint32_t p_sad16x16[16][8], uint32_t* p_best_sad_32x32,
+                                                                 uint32_t* p_best_sad_64x64, uint32_t* p_best_mv32x32,
+                                                                 uint32_t* p_best_mv64x64, uint32_t mv,
+                                                                 uint32_t p_sad32x32[4][8]);
+SVT_B200_API void svt_b200_ext_sad_calculation_8x8_16x16(uint8_t* src, uint32_t src_stride, uint8_t* ref,
+                                                         uint32_t ref_stride, uint32_t* p_best_sad_8x8,
+                                                         uint32_t* p_best_sad_16x16, uint32_t* p_best_mv8x8,
+                                                         uint32_t* p_best_mv16x16, uint32_t mv, uint32_t* p_sad16x16,
+                                                         uint32_t* p_sad8x8, uint8_t sub_sad);
+SVT_B200_API void svt_b200_ext_sad_calculation_32x32_64x64(uint32_t* p_sad16x16, uint32_t* p_best_sad_32x32,
+                                                           uint32_t* p_best_sad_64x64, uint32_t* p_best_mv32x32,
+                                                           uint32_t* p_best_mv64x64, uint32_t mv, uint32_t* p_sad32x32);
+SVT_B200_API void svt_b200_initialize_buffer_32bits(uint32_t* pointer, uint32_t count128, uint32_t count32, uint32_t value);
+
+/* T2: open_loop_me_fullpel_search_sblock (motion_estimation.c:781) for one 64x64 block and one
+ * reference: all sa_w x sa_h integer positions, best SAD + MV for the 85 square PUs
+ * (me_context.h:54-75 order).  MV = ((org_y + y) << 16) | ((org_x + x) & 0xffff). */
+typedef struct SvtB200FullpelItem {
+    uint64_t src_off;    /* 64x64 source block origin (bytes) */
+    uint64_t ref_off;    /* reference sample of search position (0,0) (bytes) */
+    uint32_t src_stride;
+    uint32_t ref_stride;
+    int16_t  sa_w, sa_h;
+    int16_t  org_x, org_y; /* x/y_search_area_origin */
+    uint8_t  sub_sad;      /* me_search_method == SUB_SAD_SEARCH */
+    uint8_t  reserved[7];
+} SvtB200FullpelItem;
+SVT_B200_API int svt_b200_fullpel_search_batch_dev(const uint8_t* d_src_plane, const uint8_t* d_ref_plane,
+                                                   const SvtB200FullpelItem* d_items, int n_items, uint32_t* d_best_sad,
+                                                   uint32_t* d_best_mv, void* stream);
+SVT_B200_API int svt_b200_fullpel_search_batch_host(const uint8_t* src_plane, size_t src_bytes, const uint8_t* ref_plane,
+                                                    size_t ref_bytes, const SvtB200FullpelItem* items, int n_items,
+                                                    uint32_t* best_sad, uint32_t* best_mv);
+
 #ifdef __cplusplus
 }
 #endif

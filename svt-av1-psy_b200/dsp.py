@@ -229,3 +229,57 @@ def quantize(name, coeff, tables, scan, qm=None, iqm=None, log_scale=None):
         args += [log_scale]
     f(*args)
     return q, dq, int(eob.value)
+
+# ------------------------------------------------------------------------------------------------
+# K4 Hadamard / SATD, K2 SAD pyramid + full-pel search
+# ------------------------------------------------------------------------------------------------
+HADAMARD_ITEM_DTYPE = np.dtype([("src_off", "<u8"), ("coeff_off", "<u8"), ("src_stride", "<u4"), ("size", "<u4")])
+FULLPEL_ITEM_DTYPE = np.dtype([("src_off", "<u8"), ("ref_off", "<u8"), ("src_stride", "<u4"), ("ref_stride", "<u4"),
+                               ("sa_w", "<i2"), ("sa_h", "<i2"), ("org_x", "<i2"), ("org_y", "<i2"), ("sub_sad", "u1"),
+                               ("reserved", "u1", 7)])
+assert HADAMARD_ITEM_DTYPE.itemsize == 24 and FULLPEL_ITEM_DTYPE.itemsize == 40
+for _n in ("4x4", "8x8", "16x16", "32x32"):
+    _f = getattr(lib, "svt_b200_aom_hadamard_" + _n)
+    _f.argtypes = [vp, ct.c_ssize_t, vp]
+    _f.restype = None
+lib.svt_b200_aom_satd.argtypes = [vp, ct.c_int]
+lib.svt_b200_aom_satd.restype = ct.c_int
+lib.svt_b200_hadamard_satd_batch_dev.argtypes = [vp, vp, ct.c_int, vp, vp, vp]
+lib.svt_b200_hadamard_satd_batch_dev.restype = ct.c_int
+lib.svt_b200_ext_all_sad_calculation_8x8_16x16.argtypes = [vp, ct.c_uint32, vp, ct.c_uint32, ct.c_uint32, vp, vp, vp, vp,
+                                                           vp, vp, ct.c_uint8]
+lib.svt_b200_ext_all_sad_calculation_8x8_16x16.restype = None
+lib.svt_b200_ext_eight_sad_calculation_32x32_64x64.argtypes = [vp, vp, vp, vp, vp, ct.c_uint32, vp]
+lib.svt_b200_ext_eight_sad_calculation_32x32_64x64.restype = None
+lib.svt_b200_ext_sad_calculation_8x8_16x16.argtypes = [vp, ct.c_uint32, vp, ct.c_uint32, vp, vp, vp, vp, ct.c_uint32, vp,
+                                                       vp, ct.c_uint8]
+lib.svt_b200_ext_sad_calculation_8x8_16x16.restype = None
+lib.svt_b200_ext_sad_calculation_32x32_64x64.argtypes = [vp, vp, vp, vp, vp, ct.c_uint32, vp]
+lib.svt_b200_ext_sad_calculation_32x32_64x64.restype = None
+lib.svt_b200_initialize_buffer_32bits.argtypes = [vp, ct.c_uint32, ct.c_uint32, ct.c_uint32]
+lib.svt_b200_initialize_buffer_32bits.restype = None
+lib.svt_b200_fullpel_search_batch_dev.argtypes = [vp, vp, vp, ct.c_int, vp, vp, vp]
+lib.svt_b200_fullpel_search_batch_dev.restype = ct.c_int
+lib.svt_b200_fullpel_search_batch_host.argtypes = [vp, ct.c_size_t, vp, ct.c_size_t, vp, ct.c_int, vp, vp]
+lib.svt_b200_fullpel_search_batch_host.restype = ct.c_int
+
+
+def svt_aom_hadamard(src_diff, stride, n):
+    out = np.zeros(n * n, np.int32)
+    getattr(lib, "svt_b200_aom_hadamard_%dx%d" % (n, n))(_ptr(src_diff), stride, _ptr(out))
+    return out
+
+
+def svt_aom_satd(coeff):
+    return int(lib.svt_b200_aom_satd(_ptr(coeff), coeff.size))
+
+
+def fullpel_search_batch_host(src_plane, ref_plane, items):
+    items = np.ascontiguousarray(items, dtype=FULLPEL_ITEM_DTYPE)
+    sad = np.zeros((len(items), 85), np.uint32)
+    mv = np.zeros((len(items), 85), np.uint32)
+    rc = lib.svt_b200_fullpel_search_batch_host(_ptr(src_plane), src_plane.nbytes, _ptr(ref_plane), ref_plane.nbytes,
+                                                _ptr(items), len(items), _ptr(sad), _ptr(mv))
+    if rc != 0:
+        raise RuntimeError("svt_b200_fullpel_search_batch_host rc=%d" % rc)
+    return sad, mv

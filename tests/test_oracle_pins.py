@@ -79,3 +79,36 @@ def test_port_quantizers_match_reference(oracle, refc):
         assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and a[2] == b[2], (v[0], c.size, ls, qm is not None)
         n += 1
     assert n > 1000
+
+
+# ---- Hadamard / SATD / SAD pyramid ---------------------------------------------------------------
+import me_helpers as mh  # noqa: E402
+
+
+def test_port_hadamard_matches_reference(oracle, refc):
+    r = rng(40)
+    for n in (4, 8, 16, 32):
+        for kind in ("random", "max", "min"):
+            stride = n + 7
+            if kind == "random":
+                src = r.integers(-255, 256, n * stride).astype(np.int16)
+            else:
+                src = np.full(n * stride, 255 if kind == "max" else -255, np.int16)
+            a = mh.hadamard_call(oracle.port, "port_hadamard", src, stride, n)
+            b = mh.hadamard_call(refc, "svt_aom_hadamard_%dx%d_c" % (n, n), src, stride, n)
+            assert np.array_equal(a, b), (n, kind)
+            assert oracle.port.port_satd(oracle.p(a), a.size) == refc.svt_aom_satd_c(oracle.p(a), a.size)
+
+
+def test_port_fullpel_matches_reference_kernels(oracle, refc):
+    r = rng(41)
+    for (sa_w, sa_h, sub) in [(8, 3, 0), (16, 9, 0), (11, 4, 0), (8, 3, 1), (13, 2, 1), (3, 3, 0)]:
+        ss, rs = 64 + 16, 64 + sa_w + 9
+        src = r.integers(0, 256, ss * 64, dtype=np.uint8)
+        ref = r.integers(0, 256, rs * (64 + sa_h), dtype=np.uint8)
+        if sa_w == 16:  # force ties: flat content
+            src[:] = 100
+            ref[:] = 103
+        a = mh.port_fullpel(oracle.port, src, 0, ss, ref, 0, rs, sa_w, sa_h, -5, 7, sub)
+        b = mh.ref_fullpel(refc, src, 0, ss, ref, 0, rs, sa_w, sa_h, -5, 7, sub)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]), (sa_w, sa_h, sub)
