@@ -302,6 +302,59 @@ SVT_B200_API int svt_b200_fullpel_search_batch_host(const uint8_t* src_plane, si
                                                     size_t ref_bytes, const SvtB200FullpelItem* items, int n_items,
                                                     uint32_t* best_sad, uint32_t* best_mv);
 
+/* ------------------------------------------------------------------------------------------ */
+/* K8  CDEF  (reference: Source/Lib/Codec/cdef.c, enc_cdef.c, cdef_process.c)                   */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct SvtB200CdefList { uint8_t by, bx; } SvtB200CdefList; /* == CdefList, definitions.h:256-259 */
+
+/* T1: common_dsp_rtcd.h:1015-1029, aom_dsp_rtcd.h:62-64,242.  `bsize` is the reference BlockSize
+ * enumerator (BLOCK_4X4=0, BLOCK_4X8=1, BLOCK_8X4=2, BLOCK_8X8=3); `in` points into a tile of pitch
+ * CDEF_BSTRIDE (144) with at least 2 valid rows/columns around the block. */
+SVT_B200_API uint8_t  svt_b200_aom_cdef_find_dir(const uint16_t* img, int32_t stride, int32_t* var, int32_t coeff_shift);
+SVT_B200_API void     svt_b200_aom_cdef_find_dir_dual(const uint16_t* img1, const uint16_t* img2, int stride, int32_t* var1,
+                                                      int32_t* var2, int32_t coeff_shift, uint8_t* out1, uint8_t* out2);
+SVT_B200_API void     svt_b200_cdef_filter_block(uint8_t* dst8, uint16_t* dst16, int32_t dstride, const uint16_t* in,
+                                                 int32_t pri_strength, int32_t sec_strength, int32_t dir,
+                                                 int32_t pri_damping, int32_t sec_damping, int32_t bsize,
+                                                 int32_t coeff_shift, uint8_t subsampling_factor);
+SVT_B200_API void     svt_b200_aom_copy_rect8_8bit_to_16bit(uint16_t* dst, int32_t dstride, const uint8_t* src,
+                                                            int32_t sstride, int32_t v, int32_t h);
+SVT_B200_API uint64_t svt_b200_compute_cdef_dist_16bit(const uint16_t* dst, int32_t dstride, const uint16_t* src,
+                                                       const SvtB200CdefList* dlist, int32_t cdef_count, int32_t bsize,
+                                                       int32_t coeff_shift, int32_t pli, uint8_t subsampling_factor);
+SVT_B200_API uint64_t svt_b200_compute_cdef_dist_8bit(const uint8_t* dst8, int32_t dstride, const uint8_t* src8,
+                                                      const SvtB200CdefList* dlist, int32_t cdef_count, int32_t bsize,
+                                                      int32_t coeff_shift, int32_t pli, uint8_t subsampling_factor);
+SVT_B200_API uint64_t svt_b200_search_one_dual(int* lev0, int* lev1, int nb_strengths, uint64_t** mse[2], int sb_count,
+                                               int start_gi, int end_gi);
+
+/* T2: whole-picture CDEF strength search (cdef_seg_search, cdef_process.c:106-352) and apply
+ * (svt_av1_cdef_frame, enc_cdef.c:284).  4:2:0, width/height multiples of 8, all pointers DEVICE
+ * memory pointing at the first visible pixel of each plane.  recon_* = deblocked reconstruction
+ * (filter input), src_* = source picture.  Pixels are uint8 (bit_depth 8) or uint16. */
+typedef struct SvtB200CdefFrame {
+    const void* recon_y; const void* recon_cb; const void* recon_cr;
+    const void* src_y;   const void* src_cb;   const void* src_cr;
+    int32_t recon_stride_y, recon_stride_c, src_stride_y, src_stride_c; /* in pixels */
+    int32_t width, height;       /* luma */
+    int32_t bit_depth;
+    int32_t damping;             /* 3 + (base_q_idx >> 6) */
+    int32_t subsampling_factor;  /* CdefSearchControls.subsampling_factor */
+    int32_t reserved;
+} SvtB200CdefFrame;
+/* d_skip8x8: one byte per luma 8x8 (raster, (width/8) per row), non-zero = skip (not in the cdef
+ * list).  strengths: candidate (pri*4+sec) codes per gi, -1 = not tested for chroma.
+ * d_mse: [2][nfb][n_strengths] uint64 laid out like pcs->mse_seg; d_dir/d_var: [nfb][64]. */
+SVT_B200_API int svt_b200_cdef_search_frame_dev(const SvtB200CdefFrame* frame, const uint8_t* d_skip8x8,
+                                                const int* d_strengths_y, const int* d_strengths_uv, int n_strengths,
+                                                uint64_t* d_mse, uint8_t* d_dir, int32_t* d_var, void* stream);
+/* d_fb_strength_idx: per filter block index into the frame's strength tables (-1 = leave untouched);
+ * output planes receive the filtered pixels of non-skip blocks only (copy the input first). */
+SVT_B200_API int svt_b200_cdef_apply_frame_dev(const SvtB200CdefFrame* frame, const uint8_t* d_skip8x8,
+                                               const int8_t* d_fb_strength_idx, const int* d_y_strength,
+                                               const int* d_uv_strength, void* d_out_y, void* d_out_cb, void* d_out_cr,
+                                               int out_stride_y, int out_stride_c, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

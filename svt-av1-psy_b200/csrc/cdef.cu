@@ -1,0 +1,618 @@
+// cdef.cu -- K8 CDEF: direction search, constrained directional filter, distortion, strength search,
+// frame apply (sm_100a).
+//
+// Reference behaviour restated: svt_aom_cdef_find_dir_c (Source/Lib/Codec/cdef.c:150-210),
+// constrain/adjust_strength (:85-134), svt_cdef_filter_block_c (:253-305), svt_cdef_filter_fb (:339-430),
+// dist_8xn_* / mse_* / svt_aom_compute_cdef_dist{,_8bit}_c (Source/Lib/Codec/enc_cdef.c:23-233),
+// svt_search_one_dual_c (:627-690), the tile build of cdef_seg_search (Source/Lib/Codec/cdef_process.c:
+// 106-352: CDEF_VERY_LARGE outside the frame, pre-filter neighbours inside).
+//
+// B200 mapping (T2): one CTA per 64x64 filter block.  The CTA stages the padded 16-bit tile of each
+// plane in shared memory once, finds the 64 luma directions (one thread per 8x8), then for every
+// candidate strength filters all non-skip blocks straight from the tile -- one thread per block row --
+// and reduces the distortion against the source picture with 8-lane shuffles; the filtered pixels of
+// the search never leave registers.  The luma distortion's double-precision formula is evaluated
+// with round-to-nearest intrinsics in the reference's operand order (FMA contraction is disabled
+// for the whole library), which makes it IEEE-identical to the C code.
+#include "common.cuh"
+#include "../../include/svt_b200.h"
+
+namespace b200 {
+
+constexpr int kVeryLarge = 0x7f7f;  // CDEF_VERY_LARGE (cdef.h:38)
+constexpr int kTP        = 88;      // tile pitch in uint16 (>= 64 + 2*8, keeps rows 16-B aligned)
+constexpr int kTileRows  = 64 + 6;
+
+__device__ __forceinline__ int msb32(uint32_t n) { return 31 - __clz(n); }
+__device__ __forceinline__ int cdef_constrain(int diff, int threshold, int damping) {
+    if (!threshold) return 0;
+    const int shift = max(0, damping - msb32((uint32_t)threshold));
+    const int ad    = abs(diff);
+    const int v     = min(ad, max(0, threshold - (ad >> shift)));
+    return diff < 0 ? -v : v;
+}
+__device__ __forceinline__ int cdef_adjust_strength(int strength, int var) {
+    const int i = (var >> 6) ? min(msb32((uint32_t)(var >> 6)), 12) : 0;
+    return var ? (strength * (4 + i) + 8) >> 4 : 0;
+}
+
+// Cdef_Directions (AV1 spec 7.15.3) as (dy, dx) pairs for k = 0, 1
+__constant__ int8_t c_cdef_dir[8][2][2] = {{{-1, 1}, {-2, 2}}, {{0, 1}, {-1, 2}}, {{0, 1}, {0, 2}}, {{0, 1}, {1, 2}},
+                                           {{1, 1}, {2, 2}},   {{1, 0}, {2, 1}},  {{1, 0}, {2, 0}}, {{1, 0}, {2, -1}}};
+
+// direction + variance of one 8x8 (cdef.c:150-210)
+__device__ int cdef_find_dir_dev(const uint16_t* img, int stride, int* var, int coeff_shift) {
+    int cost[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int partial[8][15];
+#pragma unroll
+    for (int d = 0; d < 8; d++)
+#pragma unroll
+        for (int k = 0; k < 15; k++) partial[d][k] = 0;
+    for (int i = 0; i < 8; i++)
+        for (int j = 0; j < 8; j++) {
+            const int x = ((int)img[i * stride + j] >> coeff_shift) - 128;
+            partial[0][i + j] += x;
+            partial[1][i + j / 2] += x;
+            partial[2][i] += x;
+            partial[3][3 + i - j / 2] += x;
+            partial[4][7 + i - j] += x;
+            partial[5][3 - i / 2 + j] += x;
+            partial[6][j] += x;
+            partial[7][i / 2 + j] += x;
+        }
+    const int div_table[9] = {0, 840, 420, 280, 210, 168, 140, 120, 105};
+    for (int i = 0; i < 8; i++) {
+        cost[2] += partial[2][i] * partial[2][i];
+        cost[6] += partial[6][i] * partial[6][i];
+    }
+    cost[2] *= div_table[8];
+    cost[6] *= div_table[8];
+    for (int i = 0; i < 7; i++) {
+        cost[0] += (partial[0][i] * partial[0][i] + partial[0][14 - i] * partial[0][14 - i]) * div_table[i + 1];
+        cost[4] += (partial[4][i] * partial[4][i] + partial[4][14 - i] * partial[4][14 - i]) * div_table[i + 1];
+    }
+    cost[0] += partial[0][7] * partial[0][7] * div_table[8];
+    cost[4] += partial[4][7] * partial[4][7] * div_table[8];
+    for (int i = 1; i < 8; i += 2) {
+        for (int j = 0; j < 5; j++) cost[i] += partial[i][3 + j] * partial[i][3 + j];
+        cost[i] *= div_table[8];
+        for (int j = 0; j < 3; j++)
+            cost[i] += (partial[i][j] * partial[i][j] + partial[i][10 - j] * partial[i][10 - j]) * div_table[2 * j + 2];
+    }
+    int best_cost = 0, best_dir = 0;
+    for (int i = 0; i < 8; i++)
+        if (cost[i] > best_cost) {
+            best_cost = cost[i];
+            best_dir  = i;
+        }
+    *var = (best_cost - cost[(best_dir + 4) & 7]) >> 10;
+    return best_dir;
+}
+
+// one filtered pixel (cdef.c:262-302); `in` points at the pixel, s = tile pitch
+__device__ __forceinline__ int cdef_filter_px(const uint16_t* in, int s, int pri_strength, int sec_strength, int dir,
+                                              int pri_damping, int sec_damping, int coeff_shift) {
+    const int  ptap0 = ((pri_strength >> coeff_shift) & 1) ? 3 : 4, ptap1 = ((pri_strength >> coeff_shift) & 1) ? 3 : 2;
+    const int  x     = (int16_t)in[0];
+    int        sum = 0, mx = x, mn = x;
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        const int po = c_cdef_dir[dir][k][0] * s + c_cdef_dir[dir][k][1];
+        const int d2 = (dir + 2) & 7, d6 = (dir + 6) & 7;
+        const int s0o = c_cdef_dir[d2][k][0] * s + c_cdef_dir[d2][k][1];
+        const int s2o = c_cdef_dir[d6][k][0] * s + c_cdef_dir[d6][k][1];
+        const int p0 = (int16_t)in[po], p1 = (int16_t)in[-po];
+        const int q0 = (int16_t)in[s0o], q1 = (int16_t)in[-s0o], q2 = (int16_t)in[s2o], q3 = (int16_t)in[-s2o];
+        const int pt = k ? ptap1 : ptap0, st = k ? 1 : 2;
+        sum = (int16_t)(sum + (int16_t)(pt * cdef_constrain(p0 - x, pri_strength, pri_damping)));
+        sum = (int16_t)(sum + (int16_t)(pt * cdef_constrain(p1 - x, pri_strength, pri_damping)));
+        if (p0 != kVeryLarge) mx = max(p0, mx);
+        if (p1 != kVeryLarge) mx = max(p1, mx);
+        mn = min(min(p0, p1), mn);
+        if (q0 != kVeryLarge) mx = max(q0, mx);
+        if (q1 != kVeryLarge) mx = max(q1, mx);
+        if (q2 != kVeryLarge) mx = max(q2, mx);
+        if (q3 != kVeryLarge) mx = max(q3, mx);
+        mn = min(min(min(q0, q1), min(q2, q3)), mn);
+        sum = (int16_t)(sum + (int16_t)(st * cdef_constrain(q0 - x, sec_strength, sec_damping)));
+        sum = (int16_t)(sum + (int16_t)(st * cdef_constrain(q1 - x, sec_strength, sec_damping)));
+        sum = (int16_t)(sum + (int16_t)(st * cdef_constrain(q2 - x, sec_strength, sec_damping)));
+        sum = (int16_t)(sum + (int16_t)(st * cdef_constrain(q3 - x, sec_strength, sec_damping)));
+    }
+    int y = (int16_t)x + ((8 + sum - (sum < 0)) >> 4);
+    y     = y < mn ? mn : (y > mx ? mx : y);
+    return (int16_t)y;
+}
+
+// luma psy distortion of one 8xN block from its five moments (enc_cdef.c:41-47); exact IEEE sequence
+__device__ __forceinline__ unsigned long long cdef_dist_from_sums(unsigned long long sum_s, unsigned long long sum_d,
+                                                                  unsigned long long sum_s2, unsigned long long sum_d2,
+                                                                  unsigned long long sum_sd, int coeff_shift) {
+    const unsigned long long svar = sum_s2 - ((sum_s * sum_s + 32) >> 6);
+    const unsigned long long dvar = sum_d2 - ((sum_d * sum_d + 32) >> 6);
+    const double num0 = __ull2double_rn(sum_d2 + sum_s2 - 2 * sum_sd);
+    const double a    = __dmul_rn(num0, .5);
+    const double b    = __ull2double_rn(svar + dvar + (unsigned long long)(400 << 2 * coeff_shift));
+    const double num  = __dmul_rn(a, b);
+    const double den  = __dsqrt_rn(__dadd_rn((double)(20000 << 4 * coeff_shift), __dmul_rn(__ull2double_rn(svar), __ull2double_rn(dvar))));
+    return (unsigned long long)floor(__dadd_rn(.5, __ddiv_rn(num, den)));
+}
+
+// ------------------------------------------------------------------------------------------------
+// T1 kernels
+// ------------------------------------------------------------------------------------------------
+__global__ void find_dir_kernel(const uint16_t* img, int stride, int coeff_shift, int n, const int* offs, int* out) {
+    const int t = threadIdx.x;
+    if (t < n) {
+        int var;
+        out[2 * t]     = cdef_find_dir_dev(img + offs[t], stride, &var, coeff_shift);
+        out[2 * t + 1] = var;
+    }
+}
+
+// in_c: copy of the caller's tile rows [-2, h+2) x cols [-2, w+2), pitch = w + 4
+__global__ void filter_block_kernel(const uint16_t* in_c, int w, int h, int pri, int sec, int dir, int pd, int sd, int cs,
+                                    int subs, uint16_t* out) {
+    const int p = w + 4;
+    for (int idx = threadIdx.x; idx < w * h; idx += blockDim.x) {
+        const int i = idx / w, j = idx - i * w;
+        if (i % subs) continue;
+        out[idx] = (uint16_t)cdef_filter_px(in_c + (i + 2) * p + j + 2, p, pri, sec, dir, pd, sd, cs);
+    }
+}
+
+template <typename T>
+__global__ void cdef_dist_kernel(const T* dst, int dstride, const T* src, const uint8_t* dlist, int count, int bw_log2,
+                                 int bh_log2, int coeff_shift, int pli, int subs, unsigned long long* out) {
+    __shared__ unsigned long long tot;
+    if (threadIdx.x == 0) tot = 0;
+    __syncthreads();
+    const int bw = 1 << bw_log2, bh = 1 << bh_log2;
+    for (int bi = threadIdx.x; bi < count; bi += blockDim.x) {
+        const int by = dlist[2 * bi], bx = dlist[2 * bi + 1];
+        const T*  s  = src + ((size_t)bi << (bw_log2 + bh_log2));
+        const T*  d  = dst + (size_t)(by << bh_log2) * dstride + (bx << bw_log2);
+        unsigned long long v;
+        if (bw == 8 && bh == 8 && pli == 0) {
+            unsigned long long ss = 0, sd_ = 0, s2 = 0, d2 = 0, sdp = 0;
+            for (int i = 0; i < 8; i += subs)
+                for (int j = 0; j < 8; j++) {
+                    const unsigned long long a = s[8 * i + j], b = d[i * dstride + j];
+                    ss += a; sd_ += b; s2 += a * a; d2 += b * b; sdp += a * b;
+                }
+            v = cdef_dist_from_sums(ss, sd_, s2, d2, sdp, coeff_shift);
+        } else {
+            v = 0;
+            for (int i = 0; i < bh; i += subs)
+                for (int j = 0; j < bw; j++) {
+                    const int e = (int)d[i * dstride + j] - (int)s[bw * i + j];
+                    v += (unsigned long long)(long long)(e * e);
+                }
+        }
+        atomicAdd(&tot, v);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) *out = tot >> (2 * coeff_shift);
+}
+
+// svt_search_one_dual: tot[j][k] = sum_i min(best_i, mse0[i][j] + mse1[i][k])
+__global__ void search_one_dual_kernel(const unsigned long long* mse0, const unsigned long long* mse1, int sb_count, int ng,
+                                       const int* lev0, const int* lev1, int nb, int start_gi, unsigned long long* out) {
+    extern __shared__ unsigned long long tot[];  // ng*ng
+    for (int p = threadIdx.x; p < ng * ng; p += blockDim.x) {
+        const int j = p / ng, k = p - j * ng;
+        unsigned long long acc = 0;
+        if (j >= start_gi && k >= start_gi)
+            for (int i = 0; i < sb_count; i++) {
+                unsigned long long best = 1ull << 63;
+                for (int g = 0; g < nb; g++) {
+                    const unsigned long long c = mse0[(size_t)i * ng + lev0[g]] + mse1[(size_t)i * ng + lev1[g]];
+                    best = c < best ? c : best;
+                }
+                const unsigned long long c = mse0[(size_t)i * ng + j] + mse1[(size_t)i * ng + k];
+                acc += c < best ? c : best;
+            }
+        tot[p] = acc;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long bt = 1ull << 63;
+        int b0 = 0, b1 = 0;
+        for (int j = start_gi; j < ng; j++)
+            for (int k = start_gi; k < ng; k++)
+                if (tot[j * ng + k] < bt) {
+                    bt = tot[j * ng + k];
+                    b0 = j;
+                    b1 = k;
+                }
+        out[0] = bt;
+        out[1] = (unsigned long long)b0;
+        out[2] = (unsigned long long)b1;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// T2: per-filter-block search (all planes, all candidate strengths) and frame apply
+// ------------------------------------------------------------------------------------------------
+template <typename PIX>
+__device__ void stage_cdef_tile(uint16_t* tile, const PIX* plane, int stride, int plane_w, int plane_h, int fbr, int fbc,
+                                int nvfb, int nhfb, int bw, int bh, int vsz, int hsz) {
+    // tile origin (row 3, col 8) = first pixel of the filter block; everything not copied stays
+    // CDEF_VERY_LARGE (cdef_process.c:211-230)
+    const int yoff = 3 * (fbr != 0), xoff = 8 * (fbc != 0);
+    const int ysize = vsz + 3 * (fbr + 1 < nvfb) + yoff, xsize = hsz + 8 * (fbc + 1 < nhfb) + xoff;
+    (void)plane_w; (void)plane_h;
+    for (int i = threadIdx.x; i < kTileRows * kTP; i += blockDim.x) tile[i] = (uint16_t)kVeryLarge;
+    __syncthreads();
+    const int py0 = fbr * bh - yoff, px0 = fbc * bw - xoff;
+    for (int i = threadIdx.x; i < ysize * xsize; i += blockDim.x) {
+        const int r = i / xsize, c = i - r * xsize;
+        tile[(3 - yoff + r) * kTP + (8 - xoff + c)] = (uint16_t)plane[(size_t)(py0 + r) * stride + px0 + c];
+    }
+    __syncthreads();
+}
+
+template <typename PIX>
+__global__ void __launch_bounds__(256)
+cdef_search_kernel(SvtB200CdefFrame f, const uint8_t* __restrict__ skip8x8, const int* __restrict__ strengths_y,
+                   const int* __restrict__ strengths_uv, int n_strengths, unsigned long long* __restrict__ mse /*[2][nfb][n_strengths]*/,
+                   uint8_t* __restrict__ dir_out /*[nfb][64]*/, int* __restrict__ var_out /*[nfb][64]*/) {
+    __shared__ uint16_t tile[kTileRows * kTP];
+    __shared__ uint8_t  s_dir[64];
+    __shared__ int      s_var[64];
+    __shared__ uint8_t  s_list[64];  // by*8+bx of the non-skip 8x8s, raster order (svt_sb_compute_cdef_list)
+    __shared__ int      s_count;
+    __shared__ unsigned long long s_acc;
+    const int nhfb = (f.width + 63) >> 6, nvfb = (f.height + 63) >> 6, nfb = nhfb * nvfb;
+    const int cs = f.bit_depth > 8 ? f.bit_depth - 8 : 0;
+    const int w8 = (f.width + 7) >> 3, h8 = (f.height + 7) >> 3;
+    for (int fb = blockIdx.x; fb < nfb; fb += gridDim.x) {
+        const int fbr = fb / nhfb, fbc = fb - fbr * nhfb;
+        if (threadIdx.x == 0) {
+            int n = 0;
+            for (int by = 0; by < 8; by++)
+                for (int bx = 0; bx < 8; bx++) {
+                    const int gy = fbr * 8 + by, gx = fbc * 8 + bx;
+                    if (gy < h8 && gx < w8 && !skip8x8[gy * w8 + gx]) s_list[n++] = (uint8_t)(by * 8 + bx);
+                }
+            s_count = n;
+        }
+        __syncthreads();
+        const int count = s_count;
+        if (count == 0) {
+            for (int g = threadIdx.x; g < n_strengths; g += blockDim.x) {
+                mse[(size_t)(0 * nfb + fb) * n_strengths + g] = 0;
+                mse[(size_t)(1 * nfb + fb) * n_strengths + g] = 0;
+            }
+            __syncthreads();
+            continue;
+        }
+        for (int pli = 0; pli < 3; pli++) {
+            const int dec = pli ? 1 : 0;
+            const PIX* rec = (const PIX*)(pli == 0 ? f.recon_y : (pli == 1 ? f.recon_cb : f.recon_cr));
+            const PIX* src = (const PIX*)(pli == 0 ? f.src_y : (pli == 1 ? f.src_cb : f.src_cr));
+            const int rstride = pli ? f.recon_stride_c : f.recon_stride_y, sstride = pli ? f.src_stride_c : f.src_stride_y;
+            const int pw = f.width >> dec, ph = f.height >> dec, fbs = 64 >> dec;
+            const int hsz = min(fbs, pw - fbc * fbs), vsz = min(fbs, ph - fbr * fbs);
+            stage_cdef_tile<PIX>(tile, rec, rstride, pw, ph, fbr, fbc, nvfb, nhfb, fbs, fbs, vsz, hsz);
+            if (pli == 0) {
+                if ((int)threadIdx.x < count) {
+                    const int b = s_list[threadIdx.x], by = b >> 3, bx = b & 7;
+                    int var;
+                    s_dir[b] = (uint8_t)cdef_find_dir_dev(tile + (3 + 8 * by) * kTP + 8 + 8 * bx, kTP, &var, cs);
+                    s_var[b] = var;
+                    dir_out[(size_t)fb * 64 + b] = s_dir[b];
+                    var_out[(size_t)fb * 64 + b] = var;
+                }
+                __syncthreads();
+            }
+            const int bsz = 8 >> dec;                       // block edge in this plane
+            int subs = f.subsampling_factor;
+            subs = min(subs, dec ? 1 : 4);                  // cdef_process.c:243-248 (4:2:0 chroma = BLOCK_4X4)
+            const int rows_per_blk = bsz / subs;
+            const int damping = f.damping + cs - (pli != 0);
+            for (int g = 0; g < n_strengths; g++) {
+                const int sv = pli ? strengths_uv[g] : strengths_y[g];
+                if (threadIdx.x == 0) s_acc = 0;
+                __syncthreads();
+                if (sv >= 0) {
+                    const int pri = (sv / 4) << cs;
+                    int sec = sv % 4;
+                    sec = (sec + (sec == 3)) << cs;
+                    // unit = (block, processed row); the rows of one block sit in adjacent lanes
+                    for (int u = threadIdx.x; u < ((count * rows_per_blk + 31) & ~31); u += blockDim.x) {  // whole warps stay in the loop (shuffles)
+                        unsigned long long ss = 0, sdv = 0, s2 = 0, d2 = 0, sdp = 0, se = 0;
+                        const bool live = u < count * rows_per_blk;
+                        if (live) {
+                            const int bi = u / rows_per_blk, ri = (u - bi * rows_per_blk) * subs;
+                            const int b = s_list[bi], by = b >> 3, bx = b & 7;
+                            const int t = pli ? pri : cdef_adjust_strength(pri, s_var[b]);
+                            const int d = pri ? s_dir[b] : 0;
+                            const uint16_t* in = tile + (3 + bsz * by + ri) * kTP + 8 + bsz * bx;
+                            const PIX* sp = src + (size_t)(fbr * fbs + bsz * by + ri) * sstride + fbc * fbs + bsz * bx;
+                            for (int j = 0; j < bsz; j++) {
+                                const unsigned long long y = (unsigned long long)(uint16_t)cdef_filter_px(in + j, kTP, t, sec, d, damping, damping, cs);
+                                const unsigned long long o = sp[j];
+                                if (pli == 0) { ss += y; sdv += o; s2 += y * y; d2 += o * o; sdp += y * o; }
+                                else { const long long e = (long long)o - (long long)y; se += (unsigned long long)(e * e); }
+                            }
+                        }
+                        if (pli == 0) {
+                            // reduce the rows_per_blk rows of a block (2, 4 or 8 adjacent lanes)
+                            for (int o = rows_per_blk >> 1; o > 0; o >>= 1) {
+                                ss += __shfl_xor_sync(0xffffffffu, ss, o);
+                                sdv += __shfl_xor_sync(0xffffffffu, sdv, o);
+                                s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+                                d2 += __shfl_xor_sync(0xffffffffu, d2, o);
+                                sdp += __shfl_xor_sync(0xffffffffu, sdp, o);
+                            }
+                            if (live && (u % rows_per_blk) == 0) atomicAdd(&s_acc, cdef_dist_from_sums(ss, sdv, s2, d2, sdp, cs));
+                        } else if (live && se) {
+                            atomicAdd(&s_acc, se);
+                        }
+                    }
+                }
+                __syncthreads();
+                if (threadIdx.x == 0) {
+                    unsigned long long* m = mse + (size_t)((pli ? 1 : 0) * nfb + fb) * n_strengths + g;
+                    // enc: mse_seg = (sum >> 2*coeff_shift) * subsampling_factor; untested chroma = default_mse_uv*64
+                    const unsigned long long v = sv >= 0 ? (s_acc >> (2 * cs)) * (unsigned long long)subs : 0;
+                    if (pli == 0) *m = v;
+                    else if (sv < 0) *m = 1040400ull * 64ull;
+                    else if (pli == 1) *m = v;
+                    else *m += v;
+                }
+                __syncthreads();
+            }
+        }
+    }
+}
+
+// frame apply (svt_av1_cdef_frame, enc_cdef.c:284-600): per filter block strengths already chosen
+template <typename PIX>
+__global__ void __launch_bounds__(256)
+cdef_apply_kernel(SvtB200CdefFrame f, const uint8_t* __restrict__ skip8x8, const int8_t* __restrict__ fb_strength_idx,
+                  const int* __restrict__ y_strength, const int* __restrict__ uv_strength, PIX* out_y, PIX* out_cb, PIX* out_cr,
+                  int out_stride_y, int out_stride_c) {
+    __shared__ uint16_t tile[kTileRows * kTP];
+    __shared__ uint8_t  s_dir[64];
+    __shared__ int      s_var[64];
+    __shared__ uint8_t  s_list[64];
+    __shared__ int      s_count;
+    const int nhfb = (f.width + 63) >> 6, nvfb = (f.height + 63) >> 6, nfb = nhfb * nvfb;
+    const int cs = f.bit_depth > 8 ? f.bit_depth - 8 : 0;
+    const int w8 = (f.width + 7) >> 3, h8 = (f.height + 7) >> 3;
+    for (int fb = blockIdx.x; fb < nfb; fb += gridDim.x) {
+        const int fbr = fb / nhfb, fbc = fb - fbr * nhfb;
+        const int sidx = fb_strength_idx[fb];
+        if (sidx < 0) continue;  // uniform per CTA
+        const int ys = y_strength[sidx], us = uv_strength[sidx];
+        if (ys == 0 && us == 0) continue;
+        if (threadIdx.x == 0) {
+            int n = 0;
+            for (int by = 0; by < 8; by++)
+                for (int bx = 0; bx < 8; bx++) {
+                    const int gy = fbr * 8 + by, gx = fbc * 8 + bx;
+                    if (gy < h8 && gx < w8 && !skip8x8[gy * w8 + gx]) s_list[n++] = (uint8_t)(by * 8 + bx);
+                }
+            s_count = n;
+        }
+        __syncthreads();
+        const int count = s_count;
+        for (int pli = 0; pli < 3 && count; pli++) {
+            const int dec = pli ? 1 : 0;
+            const PIX* rec = (const PIX*)(pli == 0 ? f.recon_y : (pli == 1 ? f.recon_cb : f.recon_cr));
+            PIX* out = pli == 0 ? out_y : (pli == 1 ? out_cb : out_cr);
+            const int rstride = pli ? f.recon_stride_c : f.recon_stride_y, ostride = pli ? out_stride_c : out_stride_y;
+            const int pw = f.width >> dec, ph = f.height >> dec, fbs = 64 >> dec;
+            const int hsz = min(fbs, pw - fbc * fbs), vsz = min(fbs, ph - fbr * fbs);
+            stage_cdef_tile<PIX>(tile, rec, rstride, pw, ph, fbr, fbc, nvfb, nhfb, fbs, fbs, vsz, hsz);
+            if (pli == 0) {
+                if ((int)threadIdx.x < count) {
+                    const int b = s_list[threadIdx.x];
+                    int var;
+                    s_dir[b] = (uint8_t)cdef_find_dir_dev(tile + (3 + 8 * (b >> 3)) * kTP + 8 + 8 * (b & 7), kTP, &var, cs);
+                    s_var[b] = var;
+                }
+                __syncthreads();
+            }
+            const int sv = pli ? us : ys;
+            const int pri = (sv / 4) << cs;
+            int sec = sv % 4;
+            sec = (sec + (sec == 3)) << cs;
+            const int bsz = 8 >> dec, damping = f.damping + cs - (pli != 0);
+            if (pri || sec)
+                for (int u = threadIdx.x; u < count * bsz; u += blockDim.x) {
+                    const int bi = u / bsz, ri = u - bi * bsz;
+                    const int b = s_list[bi], by = b >> 3, bx = b & 7;
+                    const int t = pli ? pri : cdef_adjust_strength(pri, s_var[b]);
+                    const int d = pri ? s_dir[b] : 0;
+                    const uint16_t* in = tile + (3 + bsz * by + ri) * kTP + 8 + bsz * bx;
+                    PIX* op = out + (size_t)(fbr * fbs + bsz * by + ri) * ostride + fbc * fbs + bsz * bx;
+                    for (int j = 0; j < bsz; j++) op[j] = (PIX)cdef_filter_px(in + j, kTP, t, sec, d, damping, damping, cs);
+                }
+            __syncthreads();
+        }
+    }
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+// ---- T1 ------------------------------------------------------------------------------------------
+static void find_dir_t1(const uint16_t* const* imgs, int n, int stride, int coeff_shift, int* dirs, int* vars) {
+    require_ready();
+    LaneGuard l;
+    const size_t blk = 7 * (size_t)stride + 8;
+    size_t o_img = l->alloc(n * blk * 2), o_off = l->alloc(n * 4);
+    size_t in_end = l->used;
+    size_t o_out = l->alloc(n * 8);
+    for (int i = 0; i < n; i++) {
+        memcpy(l->h<uint16_t>(o_img) + i * blk, imgs[i], blk * 2);
+        l->h<int>(o_off)[i] = (int)(i * blk);
+    }
+    l->h2d(0, in_end);
+    find_dir_kernel<<<1, 32, 0, l->stream>>>(l->d<uint16_t>(o_img), stride, coeff_shift, n, l->d<int>(o_off), l->d<int>(o_out));
+    B200_LAUNCH_CHECK();
+    l->d2h(o_out, n * 8);
+    l->sync();
+    for (int i = 0; i < n; i++) {
+        dirs[i] = l->h<int>(o_out)[2 * i];
+        vars[i] = l->h<int>(o_out)[2 * i + 1];
+    }
+}
+
+extern "C" uint8_t svt_b200_aom_cdef_find_dir(const uint16_t* img, int32_t stride, int32_t* var, int32_t coeff_shift) {
+    int d, v;
+    find_dir_t1(&img, 1, stride, coeff_shift, &d, &v);
+    *var = v;
+    return (uint8_t)d;
+}
+extern "C" void svt_b200_aom_cdef_find_dir_dual(const uint16_t* img1, const uint16_t* img2, int stride, int32_t* var1,
+                                                int32_t* var2, int32_t coeff_shift, uint8_t* out1, uint8_t* out2) {
+    const uint16_t* imgs[2] = {img1, img2};
+    int d[2], v[2];
+    find_dir_t1(imgs, 2, stride, coeff_shift, d, v);
+    *var1 = v[0];
+    *var2 = v[1];
+    *out1 = (uint8_t)d[0];
+    *out2 = (uint8_t)d[1];
+}
+
+extern "C" void svt_b200_cdef_filter_block(uint8_t* dst8, uint16_t* dst16, int32_t dstride, const uint16_t* in,
+                                           int32_t pri_strength, int32_t sec_strength, int32_t dir, int32_t pri_damping,
+                                           int32_t sec_damping, int32_t bsize, int32_t coeff_shift, uint8_t subsampling_factor) {
+    require_ready();
+    // BlockSize: BLOCK_4X4=0, 4X8=1, 8X4=2, 8X8=3 (definitions.h:765-768)
+    const int h = 4 << (bsize == 3 || bsize == 1), w = 4 << (bsize == 3 || bsize == 2);
+    const int S = 144;  // CDEF_BSTRIDE (cdef.h:35)
+    LaneGuard l;
+    const int p = w + 4;
+    size_t o_in = l->alloc((size_t)p * (h + 4) * 2);
+    size_t in_end = l->used;
+    size_t o_out = l->alloc((size_t)w * h * 2);
+    for (int r = -2; r < h + 2; r++) memcpy(l->h<uint16_t>(o_in) + (r + 2) * p, in + r * S - 2, p * 2);
+    l->h2d(0, in_end);
+    filter_block_kernel<<<1, 64, 0, l->stream>>>(l->d<uint16_t>(o_in), w, h, pri_strength, sec_strength, dir, pri_damping, sec_damping,
+                                                 coeff_shift, subsampling_factor ? subsampling_factor : 1, l->d<uint16_t>(o_out));
+    B200_LAUNCH_CHECK();
+    l->d2h(o_out, (size_t)w * h * 2);
+    l->sync();
+    const uint16_t* o = l->h<uint16_t>(o_out);
+    const int subs = subsampling_factor ? subsampling_factor : 1;
+    for (int i = 0; i < h; i += subs)
+        for (int j = 0; j < w; j++) {
+            if (dst8) dst8[i * dstride + j] = (uint8_t)o[i * w + j];
+            else dst16[i * dstride + j] = o[i * w + j];
+        }
+}
+
+extern "C" void svt_b200_aom_copy_rect8_8bit_to_16bit(uint16_t* dst, int32_t dstride, const uint8_t* src, int32_t sstride,
+                                                      int32_t v, int32_t h) {
+    // A widening host-to-host copy: the T2 path performs this conversion while staging the tile on
+    // the device (stage_cdef_tile); the T1 form has no device work to do.
+    for (int i = 0; i < v; i++)
+        for (int j = 0; j < h; j++) dst[i * dstride + j] = src[i * sstride + j];
+}
+
+template <typename T>
+static uint64_t cdef_dist_t1(const T* dst, int32_t dstride, const T* src, const uint8_t* dlist, int32_t count, int32_t bsize,
+                             int32_t coeff_shift, int32_t pli, uint8_t subs) {
+    require_ready();
+    if (count <= 0) return 0;
+    const int bh_l2 = (bsize == 3 || bsize == 1) ? 3 : 2, bw_l2 = (bsize == 3 || bsize == 2) ? 3 : 2;
+    int maxby = 0, maxbx = 0;
+    for (int i = 0; i < count; i++) {
+        if (dlist[2 * i] > maxby) maxby = dlist[2 * i];
+        if (dlist[2 * i + 1] > maxbx) maxbx = dlist[2 * i + 1];
+    }
+    const size_t rows = ((size_t)maxby + 1) << bh_l2, cols = ((size_t)maxbx + 1) << bw_l2;
+    const size_t dbytes = ((rows - 1) * dstride + cols) * sizeof(T), sbytes = ((size_t)count << (bw_l2 + bh_l2)) * sizeof(T);
+    LaneGuard l;
+    size_t o_d = l->alloc(dbytes), o_s = l->alloc(sbytes), o_l = l->alloc(2 * count);
+    size_t in_end = l->used;
+    size_t o_o = l->alloc(8);
+    memcpy(l->h<uint8_t>(o_d), dst, dbytes);
+    memcpy(l->h<uint8_t>(o_s), src, sbytes);
+    memcpy(l->h<uint8_t>(o_l), dlist, 2 * count);
+    l->h2d(0, in_end);
+    cdef_dist_kernel<T><<<1, 64, 0, l->stream>>>(l->d<T>(o_d), dstride, l->d<T>(o_s), l->d<uint8_t>(o_l), count, bw_l2, bh_l2,
+                                                 coeff_shift, pli, subs ? subs : 1, l->d<unsigned long long>(o_o));
+    B200_LAUNCH_CHECK();
+    l->d2h(o_o, 8);
+    l->sync();
+    return *l->h<uint64_t>(o_o);
+}
+extern "C" uint64_t svt_b200_compute_cdef_dist_16bit(const uint16_t* dst, int32_t dstride, const uint16_t* src,
+                                                     const SvtB200CdefList* dlist, int32_t cdef_count, int32_t bsize,
+                                                     int32_t coeff_shift, int32_t pli, uint8_t subsampling_factor) {
+    return cdef_dist_t1<uint16_t>(dst, dstride, src, (const uint8_t*)dlist, cdef_count, bsize, coeff_shift, pli, subsampling_factor);
+}
+extern "C" uint64_t svt_b200_compute_cdef_dist_8bit(const uint8_t* dst8, int32_t dstride, const uint8_t* src8,
+                                                    const SvtB200CdefList* dlist, int32_t cdef_count, int32_t bsize,
+                                                    int32_t coeff_shift, int32_t pli, uint8_t subsampling_factor) {
+    return cdef_dist_t1<uint8_t>(dst8, dstride, src8, (const uint8_t*)dlist, cdef_count, bsize, coeff_shift, pli, subsampling_factor);
+}
+
+extern "C" uint64_t svt_b200_search_one_dual(int* lev0, int* lev1, int nb_strengths, uint64_t** mse[2], int sb_count,
+                                             int start_gi, int end_gi) {
+    require_ready();
+    const int ng = end_gi;
+    LaneGuard l;
+    size_t o_m0 = l->alloc((size_t)sb_count * ng * 8), o_m1 = l->alloc((size_t)sb_count * ng * 8), o_lv = l->alloc(2 * 64 * 4);
+    size_t in_end = l->used;
+    size_t o_o = l->alloc(24);
+    for (int i = 0; i < sb_count; i++) {
+        memcpy(l->h<uint64_t>(o_m0) + (size_t)i * ng, mse[0][i], (size_t)ng * 8);
+        memcpy(l->h<uint64_t>(o_m1) + (size_t)i * ng, mse[1][i], (size_t)ng * 8);
+    }
+    memcpy(l->h<int>(o_lv), lev0, nb_strengths * 4);
+    memcpy(l->h<int>(o_lv) + 64, lev1, nb_strengths * 4);
+    l->h2d(0, in_end);
+    search_one_dual_kernel<<<1, 256, (size_t)ng * ng * 8, l->stream>>>(l->d<unsigned long long>(o_m0), l->d<unsigned long long>(o_m1),
+                                                                     sb_count, ng, l->d<int>(o_lv), l->d<int>(o_lv) + 64, nb_strengths,
+                                                                     start_gi, l->d<unsigned long long>(o_o));
+    B200_LAUNCH_CHECK();
+    l->d2h(o_o, 24);
+    l->sync();
+    const uint64_t* o = l->h<uint64_t>(o_o);
+    lev0[nb_strengths] = (int)o[1];
+    lev1[nb_strengths] = (int)o[2];
+    return o[0];
+}
+
+// ---- T2 ------------------------------------------------------------------------------------------
+extern "C" int svt_b200_cdef_search_frame_dev(const SvtB200CdefFrame* frame, const uint8_t* d_skip8x8, const int* d_strengths_y,
+                                              const int* d_strengths_uv, int n_strengths, uint64_t* d_mse, uint8_t* d_dir,
+                                              int32_t* d_var, void* stream) {
+    require_ready();
+    if (!frame || n_strengths <= 0 || n_strengths > 64) return SVT_B200_ERR_BAD_ARG;
+    const int nfb = ((frame->width + 63) >> 6) * ((frame->height + 63) >> 6);
+    if (frame->bit_depth > 8)
+        cdef_search_kernel<uint16_t><<<grid_for(nfb, 4), 256, 0, (cudaStream_t)stream>>>(*frame, d_skip8x8, d_strengths_y, d_strengths_uv,
+                                                                                      n_strengths, (unsigned long long*)d_mse, d_dir, d_var);
+    else
+        cdef_search_kernel<uint8_t><<<grid_for(nfb, 4), 256, 0, (cudaStream_t)stream>>>(*frame, d_skip8x8, d_strengths_y, d_strengths_uv,
+                                                                                     n_strengths, (unsigned long long*)d_mse, d_dir, d_var);
+    B200_LAUNCH_CHECK();
+    return SVT_B200_OK;
+}
+
+extern "C" int svt_b200_cdef_apply_frame_dev(const SvtB200CdefFrame* frame, const uint8_t* d_skip8x8, const int8_t* d_fb_strength_idx,
+                                             const int* d_y_strength, const int* d_uv_strength, void* d_out_y, void* d_out_cb,
+                                             void* d_out_cr, int out_stride_y, int out_stride_c, void* stream) {
+    require_ready();
+    if (!frame) return SVT_B200_ERR_BAD_ARG;
+    const int nfb = ((frame->width + 63) >> 6) * ((frame->height + 63) >> 6);
+    if (frame->bit_depth > 8)
+        cdef_apply_kernel<uint16_t><<<grid_for(nfb, 4), 256, 0, (cudaStream_t)stream>>>(*frame, d_skip8x8, d_fb_strength_idx, d_y_strength,
+                                                                                     d_uv_strength, (uint16_t*)d_out_y, (uint16_t*)d_out_cb,
+                                                                                     (uint16_t*)d_out_cr, out_stride_y, out_stride_c);
+    else
+        cdef_apply_kernel<uint8_t><<<grid_for(nfb, 4), 256, 0, (cudaStream_t)stream>>>(*frame, d_skip8x8, d_fb_strength_idx, d_y_strength,
+                                                                                    d_uv_strength, (uint8_t*)d_out_y, (uint8_t*)d_out_cb,
+                                                                                    (uint8_t*)d_out_cr, out_stride_y, out_stride_c);
+    B200_LAUNCH_CHECK();
+    return SVT_B200_OK;
+}

@@ -283,3 +283,44 @@ def fullpel_search_batch_host(src_plane, ref_plane, items):
     if rc != 0:
         raise RuntimeError("svt_b200_fullpel_search_batch_host rc=%d" % rc)
     return sad, mv
+
+# ------------------------------------------------------------------------------------------------
+# K8 CDEF
+# ------------------------------------------------------------------------------------------------
+class CdefFrame(ct.Structure):
+    _fields_ = [("recon_y", vp), ("recon_cb", vp), ("recon_cr", vp), ("src_y", vp), ("src_cb", vp), ("src_cr", vp),
+                ("recon_stride_y", ct.c_int32), ("recon_stride_c", ct.c_int32), ("src_stride_y", ct.c_int32),
+                ("src_stride_c", ct.c_int32), ("width", ct.c_int32), ("height", ct.c_int32), ("bit_depth", ct.c_int32),
+                ("damping", ct.c_int32), ("subsampling_factor", ct.c_int32), ("reserved", ct.c_int32)]
+
+
+lib.svt_b200_aom_cdef_find_dir.argtypes = [vp, ct.c_int32, vp, ct.c_int32]
+lib.svt_b200_aom_cdef_find_dir.restype = ct.c_uint8
+lib.svt_b200_aom_cdef_find_dir_dual.argtypes = [vp, vp, ct.c_int, vp, vp, ct.c_int32, vp, vp]
+lib.svt_b200_aom_cdef_find_dir_dual.restype = None
+lib.svt_b200_cdef_filter_block.argtypes = [vp, vp, ct.c_int32, vp, ct.c_int32, ct.c_int32, ct.c_int32, ct.c_int32, ct.c_int32,
+                                           ct.c_int32, ct.c_int32, ct.c_uint8]
+lib.svt_b200_cdef_filter_block.restype = None
+lib.svt_b200_aom_copy_rect8_8bit_to_16bit.argtypes = [vp, ct.c_int32, vp, ct.c_int32, ct.c_int32, ct.c_int32]
+lib.svt_b200_aom_copy_rect8_8bit_to_16bit.restype = None
+for _n in ("16bit", "8bit"):
+    _f = getattr(lib, "svt_b200_compute_cdef_dist_" + _n)
+    _f.argtypes = [vp, ct.c_int32, vp, vp, ct.c_int32, ct.c_int32, ct.c_int32, ct.c_int32, ct.c_uint8]
+    _f.restype = ct.c_uint64
+lib.svt_b200_search_one_dual.argtypes = [vp, vp, ct.c_int, vp, ct.c_int, ct.c_int, ct.c_int]
+lib.svt_b200_search_one_dual.restype = ct.c_uint64
+lib.svt_b200_cdef_search_frame_dev.argtypes = [ct.POINTER(CdefFrame), vp, vp, vp, ct.c_int, vp, vp, vp, vp]
+lib.svt_b200_cdef_search_frame_dev.restype = ct.c_int
+lib.svt_b200_cdef_apply_frame_dev.argtypes = [ct.POINTER(CdefFrame), vp, vp, vp, vp, vp, vp, vp, ct.c_int, ct.c_int, vp]
+lib.svt_b200_cdef_apply_frame_dev.restype = ct.c_int
+
+
+def cdef_frame_desc(rec, src, width, height, bit_depth, damping, subsampling):
+    """rec/src: lists of three 2-D torch CUDA tensors (uint8 or int16/uint16 storage)."""
+    f = CdefFrame()
+    f.recon_y, f.recon_cb, f.recon_cr = (t.data_ptr() for t in rec)
+    f.src_y, f.src_cb, f.src_cr = (t.data_ptr() for t in src)
+    f.recon_stride_y, f.recon_stride_c = rec[0].stride(0), rec[1].stride(0)
+    f.src_stride_y, f.src_stride_c = src[0].stride(0), src[1].stride(0)
+    f.width, f.height, f.bit_depth, f.damping, f.subsampling_factor = width, height, bit_depth, damping, subsampling
+    return f

@@ -112,3 +112,20 @@ def test_port_fullpel_matches_reference_kernels(oracle, refc):
         a = mh.port_fullpel(oracle.port, src, 0, ss, ref, 0, rs, sa_w, sa_h, -5, 7, sub)
         b = mh.ref_fullpel(refc, src, 0, ss, ref, 0, rs, sa_w, sa_h, -5, 7, sub)
         assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]), (sa_w, sa_h, sub)
+
+
+# ---- CDEF ----------------------------------------------------------------------------------------
+import cdef_helpers as ch  # noqa: E402
+
+
+@pytest.mark.parametrize("bd,subs", [(8, 1), (8, 4), (10, 2)])
+def test_port_cdef_search_matches_reference(oracle, refc, bd, subs):
+    r = rng(60 + bd + subs)
+    W, H = 208, 136  # not multiples of 64: partial filter blocks on the right / bottom (last ones >= 16x8 luma)
+    rec, src, skip = ch.make_frame(r, W, H, bd)
+    sy = [0, 4, 9, 17, 35, 63, 2]
+    su = [0, 4, -1, 17, 20, 63, 3]
+    a = ch.port_cdef_search(oracle.port, rec, src, skip, W, H, bd, 5, subs, sy, su)
+    b = ch.ref_cdef_search(refc, rec, src, skip, W, H, bd, 5, subs, sy, su)
+    assert np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+    assert np.array_equal(a[0], b[0])
