@@ -355,6 +355,70 @@ SVT_B200_API int svt_b200_cdef_apply_frame_dev(const SvtB200CdefFrame* frame, co
                                                const int* d_uv_strength, void* d_out_y, void* d_out_cb, void* d_out_cr,
                                                int out_stride_y, int out_stride_c, void* stream);
 
+/* ------------------------------------------------------------------------------------------ */
+/* K9/K11  Wiener filter + statistics  (reference: convolve.c:100-237, restoration_pick.c:659) */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct SvtB200ConvolveParams { /* layout of ConvolveParams, Source/Lib/Codec/definitions.h:572-585 */
+    int32_t   ref;
+    int32_t   do_average;
+    uint16_t* dst;
+    int32_t   dst_stride;
+    int32_t   round_0;
+    int32_t   round_1;
+    int32_t   plane;
+    int32_t   is_compound;
+    int32_t   use_jnt_comp_avg;
+    int32_t   fwd_offset;
+    int32_t   bck_offset;
+    int32_t   use_dist_wtd_comp_avg;
+} SvtB200ConvolveParams;
+
+/* T1: common_dsp_rtcd.h:173-175 (w, h <= 64; the caller's buffer must be readable 3 rows/columns
+ * before and 4 after the unit, as for the reference); aom_dsp_rtcd.h:66-68.  High-bit-depth pixel
+ * pointers are plain uint16_t* here (the reference passes CONVERT_TO_BYTEPTR disguises). */
+SVT_B200_API void svt_b200_av1_wiener_convolve_add_src(const uint8_t* src, ptrdiff_t src_stride, uint8_t* dst,
+                                                       ptrdiff_t dst_stride, const int16_t* filter_x,
+                                                       const int16_t* filter_y, int32_t w, int32_t h,
+                                                       const SvtB200ConvolveParams* conv_params);
+SVT_B200_API void svt_b200_av1_highbd_wiener_convolve_add_src(const uint16_t* src, ptrdiff_t src_stride, uint16_t* dst,
+                                                              ptrdiff_t dst_stride, const int16_t* filter_x,
+                                                              const int16_t* filter_y, int32_t w, int32_t h,
+                                                              const SvtB200ConvolveParams* conv_params, int32_t bd);
+SVT_B200_API void svt_b200_av1_compute_stats(int32_t wiener_win, const uint8_t* dgd, const uint8_t* src, int32_t h_start,
+                                             int32_t h_end, int32_t v_start, int32_t v_end, int32_t dgd_stride,
+                                             int32_t src_stride, int64_t* M, int64_t* H);
+SVT_B200_API void svt_b200_av1_compute_stats_highbd(int32_t wiener_win, const uint16_t* dgd, const uint16_t* src,
+                                                    int32_t h_start, int32_t h_end, int32_t v_start, int32_t v_end,
+                                                    int32_t dgd_stride, int32_t src_stride, int64_t* M, int64_t* H,
+                                                    int32_t bit_depth);
+
+/* T2.  Offsets/strides in pixels of the device planes. */
+typedef struct SvtB200WienerUnit {
+    uint64_t src_off;
+    uint64_t dst_off;
+    int32_t  src_stride;
+    int32_t  dst_stride;
+    uint16_t w, h;         /* <= 64 */
+    uint32_t reserved;
+    int16_t  hfilter[8];   /* WienerInfo.hfilter / vfilter: 7 taps + 0 */
+    int16_t  vfilter[8];
+} SvtB200WienerUnit;
+SVT_B200_API int svt_b200_wiener_units_dev(const void* d_src, void* d_dst, const SvtB200WienerUnit* d_units, int n_units,
+                                           int bit_depth, void* stream);
+
+typedef struct SvtB200StatsItem {
+    uint64_t dgd_off;      /* plane origin of this item (the h/v limits are relative to it) */
+    uint64_t src_off;
+    int32_t  dgd_stride;
+    int32_t  src_stride;
+    int32_t  h_start, h_end, v_start, v_end;
+    int32_t  wiener_win;   /* 7, 5 or 3 */
+    int32_t  reserved;
+} SvtB200StatsItem;
+/* d_M: [n_items][49], d_H: [n_items][49*49] (first win^2 resp. win^4 entries used, reference layout) */
+SVT_B200_API int svt_b200_compute_stats_batch_dev(const void* d_dgd, const void* d_src, const SvtB200StatsItem* d_items,
+                                                  int n_items, int bit_depth, int64_t* d_M, int64_t* d_H, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -324,3 +324,34 @@ def cdef_frame_desc(rec, src, width, height, bit_depth, damping, subsampling):
     f.src_stride_y, f.src_stride_c = src[0].stride(0), src[1].stride(0)
     f.width, f.height, f.bit_depth, f.damping, f.subsampling_factor = width, height, bit_depth, damping, subsampling
     return f
+
+# ------------------------------------------------------------------------------------------------
+# K9 / K11 Wiener
+# ------------------------------------------------------------------------------------------------
+class ConvolveParams(ct.Structure):
+    _fields_ = [("ref", ct.c_int32), ("do_average", ct.c_int32), ("dst", vp), ("dst_stride", ct.c_int32),
+                ("round_0", ct.c_int32), ("round_1", ct.c_int32), ("plane", ct.c_int32), ("is_compound", ct.c_int32),
+                ("use_jnt_comp_avg", ct.c_int32), ("fwd_offset", ct.c_int32), ("bck_offset", ct.c_int32),
+                ("use_dist_wtd_comp_avg", ct.c_int32)]
+
+
+WIENER_UNIT_DTYPE = np.dtype([("src_off", "<u8"), ("dst_off", "<u8"), ("src_stride", "<i4"), ("dst_stride", "<i4"), ("w", "<u2"),
+                              ("h", "<u2"), ("reserved", "<u4"), ("hfilter", "<i2", 8), ("vfilter", "<i2", 8)])
+STATS_ITEM_DTYPE = np.dtype([("dgd_off", "<u8"), ("src_off", "<u8"), ("dgd_stride", "<i4"), ("src_stride", "<i4"),
+                             ("h_start", "<i4"), ("h_end", "<i4"), ("v_start", "<i4"), ("v_end", "<i4"), ("wiener_win", "<i4"),
+                             ("reserved", "<i4")])
+assert WIENER_UNIT_DTYPE.itemsize == 64 and STATS_ITEM_DTYPE.itemsize == 48
+lib.svt_b200_av1_wiener_convolve_add_src.argtypes = [vp, ct.c_ssize_t, vp, ct.c_ssize_t, vp, vp, ct.c_int32, ct.c_int32,
+                                                     ct.POINTER(ConvolveParams)]
+lib.svt_b200_av1_wiener_convolve_add_src.restype = None
+lib.svt_b200_av1_highbd_wiener_convolve_add_src.argtypes = [vp, ct.c_ssize_t, vp, ct.c_ssize_t, vp, vp, ct.c_int32, ct.c_int32,
+                                                            ct.POINTER(ConvolveParams), ct.c_int32]
+lib.svt_b200_av1_highbd_wiener_convolve_add_src.restype = None
+lib.svt_b200_av1_compute_stats.argtypes = [ct.c_int32, vp, vp] + [ct.c_int32] * 6 + [vp, vp]
+lib.svt_b200_av1_compute_stats.restype = None
+lib.svt_b200_av1_compute_stats_highbd.argtypes = [ct.c_int32, vp, vp] + [ct.c_int32] * 6 + [vp, vp, ct.c_int32]
+lib.svt_b200_av1_compute_stats_highbd.restype = None
+lib.svt_b200_wiener_units_dev.argtypes = [vp, vp, vp, ct.c_int, ct.c_int, vp]
+lib.svt_b200_wiener_units_dev.restype = ct.c_int
+lib.svt_b200_compute_stats_batch_dev.argtypes = [vp, vp, vp, ct.c_int, ct.c_int, vp, vp, vp]
+lib.svt_b200_compute_stats_batch_dev.restype = ct.c_int

@@ -129,3 +129,35 @@ def test_port_cdef_search_matches_reference(oracle, refc, bd, subs):
     b = ch.ref_cdef_search(refc, rec, src, skip, W, H, bd, 5, subs, sy, su)
     assert np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
     assert np.array_equal(a[0], b[0])
+
+
+# ---- Wiener --------------------------------------------------------------------------------------
+import rest_helpers as rh  # noqa: E402
+
+
+def test_port_wiener_convolve_matches_reference(oracle, refc):
+    r = rng(80)
+    for bd in (8, 10, 12):
+        dt = np.uint8 if bd == 8 else np.uint16
+        for (w, h) in [(64, 64), (48, 56), (16, 8), (64, 20)]:
+            ss = w + 16
+            src = r.integers(0, 1 << bd, ss * (h + 16)).astype(dt)
+            if w == 48:
+                src[:] = (1 << bd) - 1
+            fx, fy = rh.wiener_taps(r), rh.wiener_taps(r)
+            off = 5 * ss + 6
+            a = rh.port_wiener(oracle.port, src.astype(np.uint16), off, ss, w, h, fx, fy, bd, 1 if bd == 8 else 0)
+            b = rh.ref_wiener(refc, src, off, ss, w, h, fx, fy, bd)
+            assert np.array_equal(a, b.astype(np.uint16)), (bd, w, h)
+
+
+def test_port_compute_stats_matches_reference(oracle, refc):
+    r = rng(81)
+    for bd in (8, 10, 12):
+        dt = np.uint8 if bd == 8 else np.uint16
+        for win in (7, 5, 3):
+            W, Hh = 72, 56
+            dgd = r.integers(0, 1 << bd, W * Hh).astype(dt); src = r.integers(0, 1 << bd, W * Hh).astype(dt)
+            a = rh.port_stats(oracle.port, win, dgd.astype(np.uint16), src.astype(np.uint16), 5, 61, 4, 50, W, W, bd)
+            b = rh.ref_stats(refc, win, dgd, src, 5, 61, 4, 50, W, W, bd)
+            assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]), (bd, win)
