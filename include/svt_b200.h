@@ -419,6 +419,45 @@ typedef struct SvtB200StatsItem {
 SVT_B200_API int svt_b200_compute_stats_batch_dev(const void* d_dgd, const void* d_src, const SvtB200StatsItem* d_items,
                                                   int n_items, int bit_depth, int64_t* d_M, int64_t* d_H, void* stream);
 
+/* ------------------------------------------------------------------------------------------ */
+/* K10/K12  self-guided restoration  (reference: restoration.c:634-992, restoration_pick.c:167-498) */
+/* ------------------------------------------------------------------------------------------ */
+/* T1: common_dsp_rtcd.h:177-181, aom_dsp_rtcd.h:79-81,215.  `params` is the reference's
+ * SgrParamsType {int32 r[2]; int32 s[2]} passed as 4 ints.  High-bit-depth pixel pointers are plain
+ * uint16_t* carried in the uint8_t* arguments (no CONVERT_TO_BYTEPTR shift). */
+SVT_B200_API void    svt_b200_av1_selfguided_restoration(const uint8_t* dgd8, int32_t width, int32_t height, int32_t dgd_stride,
+                                                         int32_t* flt0, int32_t* flt1, int32_t flt_stride,
+                                                         int32_t sgr_params_idx, int32_t bit_depth, int32_t highbd);
+SVT_B200_API void    svt_b200_apply_selfguided_restoration(const uint8_t* dat8, int32_t width, int32_t height, int32_t stride,
+                                                           int32_t eps, const int32_t* xqd, uint8_t* dst8, int32_t dst_stride,
+                                                           int32_t* tmpbuf, int32_t bit_depth, int32_t highbd);
+SVT_B200_API int64_t svt_b200_av1_lowbd_pixel_proj_error(const uint8_t* src8, int32_t width, int32_t height, int32_t src_stride,
+                                                         const uint8_t* dat8, int32_t dat_stride, int32_t* flt0,
+                                                         int32_t flt0_stride, int32_t* flt1, int32_t flt1_stride, int32_t xq[2],
+                                                         const int32_t* params);
+SVT_B200_API int64_t svt_b200_av1_highbd_pixel_proj_error(const uint16_t* src, int32_t width, int32_t height, int32_t src_stride,
+                                                          const uint16_t* dat, int32_t dat_stride, int32_t* flt0,
+                                                          int32_t flt0_stride, int32_t* flt1, int32_t flt1_stride, int32_t xq[2],
+                                                          const int32_t* params);
+SVT_B200_API void    svt_b200_get_proj_subspace(const uint8_t* src8, int width, int height, int src_stride, const uint8_t* dat8,
+                                                int dat_stride, int use_highbitdepth, int32_t* flt0, int flt0_stride,
+                                                int32_t* flt1, int flt1_stride, int* xq, const int32_t* params);
+
+/* T2: batch of processing units (<= 128 x 128) over a device plane that is readable 3 pixels
+ * around every unit. */
+typedef struct SvtB200SgrUnit {
+    uint64_t dgd_off;   /* pixels */
+    uint64_t flt0_off;  /* int32 elements */
+    uint64_t flt1_off;
+    int32_t  dgd_stride;
+    int32_t  flt_stride;
+    uint16_t w, h;
+    uint16_t params_idx; /* 0..15, svt_aom_eb_sgr_params */
+    uint16_t reserved;
+} SvtB200SgrUnit;
+SVT_B200_API int svt_b200_sgr_units_dev(const void* d_dgd, const SvtB200SgrUnit* d_units, int n_units, int32_t* d_flt0,
+                                        int32_t* d_flt1, int bit_depth, int max_w, int max_h, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

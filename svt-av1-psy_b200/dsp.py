@@ -355,3 +355,24 @@ lib.svt_b200_wiener_units_dev.argtypes = [vp, vp, vp, ct.c_int, ct.c_int, vp]
 lib.svt_b200_wiener_units_dev.restype = ct.c_int
 lib.svt_b200_compute_stats_batch_dev.argtypes = [vp, vp, vp, ct.c_int, ct.c_int, vp, vp, vp]
 lib.svt_b200_compute_stats_batch_dev.restype = ct.c_int
+
+# ------------------------------------------------------------------------------------------------
+# K10 / K12 self-guided restoration
+# ------------------------------------------------------------------------------------------------
+SGR_UNIT_DTYPE = np.dtype([("dgd_off", "<u8"), ("flt0_off", "<u8"), ("flt1_off", "<u8"), ("dgd_stride", "<i4"), ("flt_stride", "<i4"),
+                           ("w", "<u2"), ("h", "<u2"), ("params_idx", "<u2"), ("reserved", "<u2")])
+assert SGR_UNIT_DTYPE.itemsize == 40
+lib.svt_b200_av1_selfguided_restoration.argtypes = [vp, ct.c_int32, ct.c_int32, ct.c_int32, vp, vp, ct.c_int32, ct.c_int32, ct.c_int32,
+                                                    ct.c_int32]
+lib.svt_b200_av1_selfguided_restoration.restype = None
+lib.svt_b200_apply_selfguided_restoration.argtypes = [vp, ct.c_int32, ct.c_int32, ct.c_int32, ct.c_int32, vp, vp, ct.c_int32, vp,
+                                                      ct.c_int32, ct.c_int32]
+lib.svt_b200_apply_selfguided_restoration.restype = None
+for _n in ("lowbd", "highbd"):
+    _f = getattr(lib, "svt_b200_av1_%s_pixel_proj_error" % _n)
+    _f.argtypes = [vp, ct.c_int32, ct.c_int32, ct.c_int32, vp, ct.c_int32, vp, ct.c_int32, vp, ct.c_int32, vp, vp]
+    _f.restype = ct.c_int64
+lib.svt_b200_get_proj_subspace.argtypes = [vp, ct.c_int, ct.c_int, ct.c_int, vp, ct.c_int, ct.c_int, vp, ct.c_int, vp, ct.c_int, vp, vp]
+lib.svt_b200_get_proj_subspace.restype = None
+lib.svt_b200_sgr_units_dev.argtypes = [vp, vp, ct.c_int, vp, vp, ct.c_int, ct.c_int, ct.c_int, vp]
+lib.svt_b200_sgr_units_dev.restype = ct.c_int

@@ -74,3 +74,29 @@ def port_stats(port, win, dgd16, src16, hs, he, vs, ve, dst, sst, bd):
     port.port_compute_stats.restype = None
     port.port_compute_stats(win, P(dgd16), P(src16), hs, he, vs, ve, dst, sst, P(M), P(H), bd)
     return M[:win * win], H[:win ** 4]
+
+
+# ---- self-guided ---------------------------------------------------------------------------------
+SGR_PARAMS = [(2, 1, 140, 3236), (2, 1, 112, 2158), (2, 1, 93, 1618), (2, 1, 80, 1438), (2, 1, 70, 1295), (2, 1, 58, 1177),
+              (2, 1, 47, 1079), (2, 1, 37, 996), (2, 1, 30, 925), (2, 1, 25, 863), (0, 1, -1, 2589), (0, 1, -1, 1618),
+              (0, 1, -1, 1177), (0, 1, -1, 925), (2, 0, 56, -1), (2, 0, 22, -1)]
+
+
+def bptr(a, off_elems=0):
+    """the reference's pixel pointer convention: uint8* for 8-bit, CONVERT_TO_BYTEPTR (addr >> 1) for uint16"""
+    addr = a.ctypes.data + off_elems * a.itemsize
+    return ct.c_void_p(addr if a.dtype == np.uint8 else addr >> 1)
+
+
+def ref_selfguided(refc, dgd, off, w, h, stride, idx, bd):
+    f0 = np.full(w * h, -12345, np.int32); f1 = np.full(w * h, -12345, np.int32)
+    f = refc.svt_av1_selfguided_restoration_c; f.restype = None
+    f(bptr(dgd, off), w, h, stride, P(f0), P(f1), w, idx, bd, int(dgd.dtype != np.uint8))
+    return f0, f1
+
+
+def port_selfguided(port, dgd16, off, w, h, stride, idx, bd):
+    f0 = np.full(w * h, -12345, np.int32); f1 = np.full(w * h, -12345, np.int32)
+    port.port_selfguided.restype = None
+    port.port_selfguided(P(dgd16, off), w, h, stride, P(f0), P(f1), w, idx, bd)
+    return f0, f1

@@ -1,5 +1,7 @@
 """Pin the C restatement (oracle/port) against the UNMODIFIED reference objects (oracle/_ref),
 on the reference's own test matrices.  CPU only."""
+import ctypes as ct
+
 import numpy as np
 import pytest
 
@@ -161,3 +163,63 @@ def test_port_compute_stats_matches_reference(oracle, refc):
             a = rh.port_stats(oracle.port, win, dgd.astype(np.uint16), src.astype(np.uint16), 5, 61, 4, 50, W, W, bd)
             b = rh.ref_stats(refc, win, dgd, src, 5, 61, 4, 50, W, W, bd)
             assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]), (bd, win)
+
+
+# ---- self-guided filter + projection ----------------------------------------------------------
+def _sgr_inputs(r, bd, w, h, kind):
+    dt = np.uint8 if bd == 8 else np.uint16
+    stride = w + 14
+    n = stride * (h + 8)
+    if kind == "random":
+        a = r.integers(0, 1 << bd, n)
+    elif kind == "smooth":
+        yy, xx = np.mgrid[0:h + 8, 0:stride]
+        a = np.clip((np.sin(xx / 9.0) + np.cos(yy / 6.0)) * (40 << (bd - 8)) + (128 << (bd - 8)) + r.integers(-3, 4, (h + 8, stride)), 0,
+                    (1 << bd) - 1).reshape(-1)
+    else:
+        a = np.full(n, (1 << bd) - 1)
+    return a.astype(dt), stride, 4 * stride + 5
+
+
+def test_port_selfguided_and_projection_match_reference(oracle, refc):
+    r = rng(100)
+    ppe8 = refc.svt_av1_lowbd_pixel_proj_error_c; ppe8.restype = ct.c_int64
+    ppe16 = refc.svt_av1_highbd_pixel_proj_error_c; ppe16.restype = ct.c_int64
+    gps = refc.svt_get_proj_subspace_c; gps.restype = None
+    app = refc.svt_apply_selfguided_restoration_c; app.restype = None
+    oracle.port.port_pixel_proj_error.restype = ct.c_int64
+    for bd in (8, 10, 12):
+        for (w, h) in [(64, 64), (48, 33), (8, 8), (96, 21)]:
+            for kind in ("random", "smooth", "max"):
+                dgd, stride, off = _sgr_inputs(r, bd, w, h, kind)
+                src, _, _ = _sgr_inputs(r, bd, w, h, "smooth")
+                for idx in (0, 5, 9, 10, 13, 14, 15):
+                    a = rh.port_selfguided(oracle.port, dgd.astype(np.uint16), off, w, h, stride, idx, bd)
+                    b = rh.ref_selfguided(refc, dgd, off, w, h, stride, idx, bd)
+                    prm = np.array(rh.SGR_PARAMS[idx], np.int32)
+                    if prm[0] > 0:
+                        assert np.array_equal(a[0], b[0]), (bd, w, h, kind, idx)
+                    if prm[1] > 0:
+                        assert np.array_equal(a[1], b[1]), (bd, w, h, kind, idx)
+                    # projection subspace + error on these filter outputs
+                    xq_a = np.zeros(2, np.int32); xq_b = np.zeros(2, np.int32)
+                    gps(rh.bptr(src, off), w, h, stride, rh.bptr(dgd, off), stride, int(bd > 8), rh.P(b[0]), w, rh.P(b[1]), w, rh.P(xq_b),
+                        rh.P(prm))
+                    s16, d16 = src.astype(np.uint16), dgd.astype(np.uint16)
+                    oracle.port.port_get_proj_subspace(rh.P(s16, off), w, h, stride, rh.P(d16, off), stride, rh.P(b[0]), w, rh.P(b[1]), w,
+                                                       rh.P(xq_a), rh.P(prm))
+                    assert np.array_equal(xq_a, xq_b), (bd, w, h, kind, idx)
+                    xq = np.array([int(r.integers(-96, 32)), int(r.integers(-32, 96))], np.int32)
+                    eb = (ppe8 if bd == 8 else ppe16)(rh.bptr(src, off), w, h, stride, rh.bptr(dgd, off), stride, rh.P(b[0]), w, rh.P(b[1]),
+                                                      w, rh.P(xq), rh.P(prm))
+                    ea = oracle.port.port_pixel_proj_error(rh.P(s16, off), w, h, stride, rh.P(d16, off), stride, rh.P(b[0]), w, rh.P(b[1]),
+                                                           w, rh.P(xq), rh.P(prm), int(bd > 8))
+                    assert ea == eb, (bd, w, h, kind, idx)
+                # apply
+                xqd = np.array([-32, 31], np.int32)
+                da = np.zeros(h * w, np.uint16); db = np.zeros(h * w, dgd.dtype)
+                tmp = np.zeros(2 * 161 * 161 * 4 + 1024, np.int32)
+                app(rh.bptr(dgd, off), w, h, stride, 3, rh.P(xqd), rh.bptr(db), w, rh.P(tmp), bd, int(bd > 8))
+                oracle.port.port_sgr_apply.restype = None
+                oracle.port.port_sgr_apply(rh.P(dgd.astype(np.uint16), off), w, h, stride, 3, rh.P(xqd), rh.P(da), w, bd)
+                assert np.array_equal(da, db.astype(np.uint16)), (bd, w, h, kind)
