@@ -458,6 +458,53 @@ typedef struct SvtB200SgrUnit {
 SVT_B200_API int svt_b200_sgr_units_dev(const void* d_dgd, const SvtB200SgrUnit* d_units, int n_units, int32_t* d_flt0,
                                         int32_t* d_flt1, int bit_depth, int max_w, int max_h, void* stream);
 
+/* ------------------------------------------------------------------------------------------ */
+/* K13 + T2 open-loop ME for a whole picture  (reference: pic_analysis_process.c:130-160,      */
+/*      2138-2190; motion_estimation.c:781-2390; me_process.c:97-291)                          */
+/* ------------------------------------------------------------------------------------------ */
+/* T1: downsample_2d (aom_dsp_rtcd.h:841). */
+SVT_B200_API void svt_b200_downsample_2d(uint8_t* input_samples, uint32_t input_stride, uint32_t input_area_width,
+                                         uint32_t input_area_height, uint8_t* decim_samples, uint32_t decim_stride,
+                                         uint32_t decim_step);
+
+/* One 8-bit luma pyramid (EbPaReferenceObject, reference_object.c:257-290).  Index 0 = 1/16
+ * resolution, 1 = 1/4, 2 = full.  plane[] are DEVICE pointers to the start of each padded buffer;
+ * the visible picture starts at (org_x, org_y).  The full plane needs >= 64+8 pixels of padding,
+ * the 1/4 and 1/16 planes the reference's 32 / 16. */
+typedef struct SvtB200MePicture {
+    const uint8_t* plane[3];
+    int32_t stride[3];
+    int32_t org_x[3];
+    int32_t org_y[3];
+    int32_t width[3];
+    int32_t height[3];
+    int32_t reserved[2];
+} SvtB200MePicture;
+
+/* Per-reference search geometry, i.e. the MeContext values the reference derives before searching:
+ * hme_l0_sa_* = output of get_hme_l0_search_area (motion_estimation.c:1800-1866) for this reference,
+ * hme_l1/l2_sa_* = me_ctx->hme_l1_sa / hme_l2_sa, me_sa_* = MIN(sa_min * scaled_distance, sa_max)
+ * (motion_estimation.c:1296-1304). */
+typedef struct SvtB200MeParams {
+    int32_t hme_l0_sa_w, hme_l0_sa_h;
+    int32_t hme_l1_sa_w, hme_l1_sa_h;
+    int32_t hme_l2_sa_w, hme_l2_sa_h;
+    int32_t me_sa_w, me_sa_h;
+    int32_t hme_sub_sad;        /* hme_search_method == SUB_SAD_SEARCH */
+    int32_t me_sub_sad;         /* me_search_method  == SUB_SAD_SEARCH */
+    int32_t check_zero_centre;  /* me_ctx->is_ref: run check_00_center before the full-pel search */
+    int32_t reserved;
+} SvtB200MeParams;
+
+/* fills the 1/4 and 1/16 planes (interior + replicated padding) from the full plane */
+SVT_B200_API int svt_b200_build_hme_pyramid_dev(const SvtB200MePicture* pic, void* stream);
+/* cur / refs / params are HOST structs holding device plane pointers.  Outputs (device):
+ * d_best_sad, d_best_mv: [n_refs][n_b64][85]; d_hme_centre: [n_refs][n_b64][2] (x, y);
+ * d_hme_sad: [n_refs][n_b64]. */
+SVT_B200_API int svt_b200_me_picture_dev(const SvtB200MePicture* cur, const SvtB200MePicture* refs,
+                                         const SvtB200MeParams* params, int n_refs, uint32_t* d_best_sad,
+                                         uint32_t* d_best_mv, int16_t* d_hme_centre, uint64_t* d_hme_sad, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

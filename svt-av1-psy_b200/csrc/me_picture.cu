@@ -1,0 +1,348 @@
+// me_picture.cu -- T2 open-loop motion estimation for a whole picture: HME pyramid construction (K13),
+// HME level 0/1/2, final search centre, zero-centre check and the 85-PU full-pel search (sm_100a).
+//
+// Reference behaviour restated (the "core" open-loop path; see DESIGN.md for the MeContext controls
+// that are honoured and those that are not):
+//   svt_aom_downsample_2d_c + svt_aom_generate_padding   Source/Lib/Codec/pic_analysis_process.c:130-160, 2138-2190
+//   hme_level_0 / hme_level_1 / hme_level_2               Source/Lib/Codec/motion_estimation.c:820-1113
+//   hme_level{0,1,2}_b64 region loops                     :1906-2180
+//   set_final_seach_centre_sb (HME level-2 branch)        :2182-2390
+//   check_00_center                                       :1139-1210
+//   integer_search_b64 search-area derivation + clipping  :1249-1520
+//   open_loop_me_fullpel_search_sblock                    :781-817   (kernel: me_pyramid.cu)
+//
+// Pipeline per picture (all references, all 64x64 blocks in every launch):
+//   prepare(L0) -> sad_search -> finish(L0) -> prepare(L1) -> sad_search -> finish(L1) ->
+//   prepare(L2) -> sad_search -> finish(L2) -> centre (+ optional zero-centre check, builds the
+//   full-pel items) -> fullpel_search.
+// The search kernels are the ones behind the T1 entry points (sad.cu / me_pyramid.cu); the small
+// prepare/finish kernels only do the reference's window arithmetic, one thread per (ref, b64, region).
+#include "common.cuh"
+#include "../../include/svt_b200.h"
+
+namespace b200 {
+
+void launch_sad_search(const uint8_t* d_src, const uint8_t* d_ref, const SvtB200SadSearchItem* d_items, int n,
+                       SvtB200SadSearchResult* d_results, size_t smem, cudaStream_t st);
+
+// ---- K13 ----------------------------------------------------------------------------------------
+__global__ void downsample_2d_kernel(const uint8_t* __restrict__ in, int in_stride, int in_w, int in_h, uint8_t* __restrict__ out,
+                                     int out_stride, int step) {
+    const int half = step >> 1;
+    const int ow = (in_w - half + step - 1) / step, oh = (in_h - half + step - 1) / step;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < ow * oh; idx += gridDim.x * blockDim.x) {
+        const int oy = idx / ow, ox = idx - oy * ow;
+        const int y = half + oy * step, x = half + ox * step;
+        const uint32_t s = (uint32_t)in[(size_t)(y - 1) * in_stride + x - 1] + in[(size_t)(y - 1) * in_stride + x] +
+                           in[(size_t)y * in_stride + x - 1] + in[(size_t)y * in_stride + x];
+        out[(size_t)oy * out_stride + ox] = (uint8_t)((s + 2) >> 2);
+    }
+}
+// replicate the w x h interior (at (org_x, org_y)) into the surrounding padding (svt_aom_generate_padding)
+__global__ void pad_plane_kernel(uint8_t* buf, int stride, int w, int h, int org_x, int org_y) {
+    const int tw = w + 2 * org_x, th = h + 2 * org_y;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < tw * th; idx += gridDim.x * blockDim.x) {
+        const int y = idx / tw, x = idx - y * tw;
+        if (x >= org_x && x < org_x + w && y >= org_y && y < org_y + h) continue;
+        const int sx = min(max(x, org_x), org_x + w - 1), sy = min(max(y, org_y), org_y + h - 1);
+        buf[(size_t)y * stride + x] = buf[(size_t)sy * stride + sx];
+    }
+}
+
+// ---- HME window arithmetic (shared by the three levels) ---------------------------------------
+struct HmeSide {  // kept per item between prepare and finish
+    int16_t origin_x, origin_y;
+};
+
+__device__ __forceinline__ void hme_clip(int16_t org, int16_t& origin, int16_t& sa, int16_t pad, int16_t pic, bool round8) {
+    if ((int16_t)(org + origin) < -pad) {
+        origin = (int16_t)(-pad - org);
+        sa     = (int16_t)(sa - (-pad - (org + origin)));  // (sic) evaluates to sa: origin was just moved
+    }
+    if ((int16_t)(org + origin) > (int16_t)(pic - 1)) origin = (int16_t)(origin - ((org + origin) - (pic - 1)));
+    if ((int16_t)(org + origin + sa) > pic) {
+        const int16_t v = (int16_t)(sa - ((org + origin + sa) - pic));
+        sa = v > 1 ? v : (int16_t)1;
+    }
+    if (round8) sa = (sa < 8) ? sa : (int16_t)(sa & ~0x07);
+}
+
+// level 0: 1/16 picture, 1: 1/4, 2: full
+__global__ void hme_prepare_kernel(SvtB200MePicture cur, const SvtB200MePicture* __restrict__ refs, const SvtB200MeParams* __restrict__ prm,
+                                   int n_refs, int n_b64, int b64_w, int level, const int16_t* __restrict__ prev_x,
+                                   const int16_t* __restrict__ prev_y, SvtB200SadSearchItem* __restrict__ items, HmeSide* __restrict__ side) {
+    const int total = n_refs * n_b64 * 4;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        const int reg = idx & 3, b = (idx >> 2) % n_b64, r = (idx >> 2) / n_b64;
+        const int sr_w = reg & 1, sr_h = reg >> 1;
+        const SvtB200MePicture rp = refs[r];
+        const SvtB200MeParams  p  = prm[r];
+        const int bx = b % b64_w, by = b / b64_w;
+        const int shift = 2 - level;
+        const int full_x = bx * 64, full_y = by * 64;
+        const int blk_w = min(64, cur.width[2] - full_x) >> shift, blk_h = min(64, cur.height[2] - full_y) >> shift;
+        const int16_t org_x = (int16_t)(full_x >> shift), org_y = (int16_t)(full_y >> shift);
+        int16_t sa_w, sa_h, ox, oy, pad_w, pad_h;
+        if (level == 0) {
+            sa_w = (int16_t)((p.hme_l0_sa_w + 7) & ~0x07);
+            sa_h = (int16_t)p.hme_l0_sa_h;
+            ox   = (int16_t)(-(int16_t)((sa_w * 2) >> 1) + sa_w * sr_w);
+            oy   = (int16_t)(-(int16_t)((sa_h * 2) >> 1) + sa_h * sr_h);
+            pad_w = (int16_t)(rp.org_x[0] - 1);
+            pad_h = (int16_t)(rp.org_y[0] - 1);
+        } else if (level == 1) {
+            sa_w = (int16_t)((p.hme_l1_sa_w + 7) & ~0x07);
+            sa_h = (int16_t)p.hme_l1_sa_h;
+            ox   = (int16_t)(-(sa_w >> 1) + (prev_x[idx] >> 1));
+            oy   = (int16_t)(-(sa_h >> 1) + (prev_y[idx] >> 1));
+            pad_w = (int16_t)(rp.org_x[1] - 1);
+            pad_h = (int16_t)(rp.org_y[1] - 1);
+        } else {
+            sa_w = (int16_t)((p.hme_l2_sa_w + 7) & ~0x07);
+            sa_h = (int16_t)p.hme_l2_sa_h;
+            ox   = (int16_t)(-(sa_w >> 1) + prev_x[idx]);
+            oy   = (int16_t)(-(sa_h >> 1) + prev_y[idx]);
+            pad_w = pad_h = 63;
+        }
+        hme_clip(org_x, ox, sa_w, pad_w, (int16_t)rp.width[level], true);
+        hme_clip(org_y, oy, sa_h, pad_h, (int16_t)rp.height[level], false);
+        const int sub = p.hme_sub_sad ? 1 : 0;
+        SvtB200SadSearchItem it;
+        it.src_off    = (uint64_t)(uintptr_t)(cur.plane[level] + (size_t)(cur.org_y[level] + org_y) * cur.stride[level] + cur.org_x[level] + org_x);
+        it.ref_off    = (uint64_t)(uintptr_t)(rp.plane[level] + (size_t)(rp.org_y[level] + org_y + oy) * rp.stride[level] + rp.org_x[level] + org_x + ox);
+        it.src_stride = (uint32_t)(cur.stride[level] << sub);
+        it.ref_stride = (uint32_t)(rp.stride[level] << sub);
+        it.ref_step   = (uint32_t)rp.stride[level];
+        it.block_w    = (uint16_t)blk_w;
+        it.block_h    = (uint16_t)(blk_h >> sub);
+        it.sa_w       = sa_w;
+        it.sa_h       = sa_h;
+        it.skip_search_line = 0;
+        it.reserved   = 0;
+        items[idx]    = it;
+        side[idx]     = HmeSide{ox, oy};
+    }
+}
+
+__global__ void hme_finish_kernel(const SvtB200SadSearchResult* __restrict__ res, const HmeSide* __restrict__ side,
+                                  const SvtB200MeParams* __restrict__ prm, int n_refs, int n_b64, int level, int16_t* __restrict__ out_x,
+                                  int16_t* __restrict__ out_y, uint64_t* __restrict__ out_sad) {
+    const int total = n_refs * n_b64 * 4;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        const int r = (idx >> 2) / n_b64;
+        const SvtB200SadSearchResult q = res[idx];
+        const int mul = level == 0 ? 4 : (level == 1 ? 2 : 1);
+        uint64_t sad = q.best_sad;
+        if (prm[r].hme_sub_sad) sad *= 2;
+        out_sad[idx] = sad;
+        out_x[idx]   = (int16_t)((int16_t)(q.x + side[idx].origin_x) * mul);
+        out_y[idx]   = (int16_t)((int16_t)(q.y + side[idx].origin_y) * mul);
+    }
+}
+
+// one warp per (ref, b64): final HME centre, optional zero-centre check, full-pel search item
+__global__ void me_centre_kernel(SvtB200MePicture cur, const SvtB200MePicture* __restrict__ refs, const SvtB200MeParams* __restrict__ prm,
+                                 int n_refs, int n_b64, int b64_w, const int16_t* __restrict__ l2x, const int16_t* __restrict__ l2y,
+                                 const uint64_t* __restrict__ l2sad, int16_t* __restrict__ hme_sc /*[n][2]*/, uint64_t* __restrict__ hme_sad,
+                                 SvtB200FullpelItem* __restrict__ items) {
+    const int lane = threadIdx.x & 31;
+    const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    for (int i = wid; i < n_refs * n_b64; i += nw) {
+        const int b = i % n_b64, r = i / n_b64;
+        const SvtB200MePicture rp = refs[r];
+        const SvtB200MeParams  p  = prm[r];
+        // region scan order of set_final_seach_centre_sb: [w=0][h=0] first, then w inner / h outer, strict '<'
+        int16_t  cx = l2x[i * 4], cy = l2y[i * 4];
+        uint64_t cs = l2sad[i * 4];
+        for (int reg = 1; reg < 4; reg++)
+            if (l2sad[i * 4 + reg] < cs) {
+                cs = l2sad[i * 4 + reg];
+                cx = l2x[i * 4 + reg];
+                cy = l2y[i * 4 + reg];
+            }
+        const int bx = b % b64_w, by = b / b64_w;
+        const int16_t org_x = (int16_t)(bx * 64), org_y = (int16_t)(by * 64);
+        const int blk_w = min(64, cur.width[2] - org_x), blk_h = min(64, cur.height[2] - org_y);
+        const uint8_t* src = cur.plane[2] + (size_t)(cur.org_y[2] + org_y) * cur.stride[2] + cur.org_x[2] + org_x;
+        int16_t sx = cx, sy = cy;
+        if (p.check_zero_centre && (sx != 0 || sy != 0)) {
+            // check_00_center: SADs on every other row (x2), zero MV wins ties
+            const int16_t pw = 63, ph = 63, W = (int16_t)rp.width[2], H = (int16_t)rp.height[2];
+            if ((int16_t)(org_x + sx) < -pw) sx = (int16_t)(-pw - org_x);
+            if ((int16_t)(org_x + sx) > (int16_t)(W - 1)) sx = (int16_t)(sx - ((org_x + sx) - (W - 1)));
+            if ((int16_t)(org_y + sy) < -ph) sy = (int16_t)(-ph - org_y);
+            if ((int16_t)(org_y + sy) > (int16_t)(H - 1)) sy = (int16_t)(sy - ((org_y + sy) - (H - 1)));
+            const uint8_t* r0 = rp.plane[2] + (size_t)(rp.org_y[2] + org_y) * rp.stride[2] + rp.org_x[2] + org_x;
+            const uint8_t* r1 = r0 + (ptrdiff_t)sy * rp.stride[2] + sx;
+            uint32_t z = 0, hsad = 0;
+            for (int t = lane; t < (blk_h >> 1) * blk_w; t += 32) {
+                const int yy = (t / blk_w) * 2, xx = t % blk_w;
+                const int s = src[(size_t)yy * cur.stride[2] + xx];
+                z += (uint32_t)abs(s - (int)r0[(size_t)yy * rp.stride[2] + xx]);
+                hsad += (uint32_t)abs(s - (int)r1[(ptrdiff_t)yy * rp.stride[2] + xx]);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                z += __shfl_xor_sync(0xffffffffu, z, o);
+                hsad += __shfl_xor_sync(0xffffffffu, hsad, o);
+            }
+            z <<= 1;
+            hsad <<= 1;
+            if (z <= hsad) sx = sy = 0;  // MIN(zero_cost, hme_cost) == zero_cost
+        }
+        if (lane == 0) {
+            hme_sc[2 * i]     = cx;
+            hme_sc[2 * i + 1] = cy;
+            hme_sad[i]        = cs;
+            // integer_search_b64 (:1296-1320, :1440-1496)
+            int16_t sa_w = (int16_t)((max(1, p.me_sa_w) + 7) & ~0x07), sa_h = (int16_t)max(3, p.me_sa_h);
+            int16_t ox = (int16_t)(sx - (sa_w >> 1)), oy = (int16_t)(sy - (sa_h >> 1));
+            const int16_t pw = 63, ph = 63, W = (int16_t)cur.width[2], H = (int16_t)cur.height[2];
+            {
+                const bool left = (int16_t)(org_x + ox) < -pw;
+                const int16_t nox = left ? (int16_t)(-pw - org_x) : ox;
+                // the reference evaluates the width correction with the ALREADY corrected origin
+                sa_w = ((int16_t)(org_x + nox) < -pw) ? (int16_t)(sa_w - (-pw - (org_x + nox))) : sa_w;
+                ox = nox;
+                ox = ((int16_t)(org_x + ox) > (int16_t)(W - 1)) ? (int16_t)(ox - ((org_x + ox) - (W - 1))) : ox;
+                sa_w = ((int16_t)(org_x + ox + sa_w) > W) ? (int16_t)max(1, sa_w - ((org_x + ox + sa_w) - W)) : sa_w;
+                sa_w = (sa_w < 8) ? sa_w : (int16_t)(sa_w & ~0x07);
+                const bool top = (int16_t)(org_y + oy) < -ph;
+                const int16_t noy = top ? (int16_t)(-ph - org_y) : oy;
+                sa_h = ((int16_t)(org_y + noy) < -ph) ? (int16_t)(sa_h - (-ph - (org_y + noy))) : sa_h;
+                oy = noy;
+                oy = ((int16_t)(org_y + oy) > (int16_t)(H - 1)) ? (int16_t)(oy - ((org_y + oy) - (H - 1))) : oy;
+                sa_h = ((int16_t)(org_y + oy + sa_h) > H) ? (int16_t)max(1, sa_h - ((org_y + oy + sa_h) - H)) : sa_h;
+            }
+            SvtB200FullpelItem it;
+            it.src_off    = (uint64_t)(uintptr_t)src;
+            it.ref_off    = (uint64_t)(uintptr_t)(rp.plane[2] + (ptrdiff_t)(rp.org_y[2] + org_y + oy) * rp.stride[2] + rp.org_x[2] + org_x + ox);
+            it.src_stride = (uint32_t)cur.stride[2];
+            it.ref_stride = (uint32_t)rp.stride[2];
+            it.sa_w = sa_w;
+            it.sa_h = sa_h;
+            it.org_x = ox;
+            it.org_y = oy;
+            it.sub_sad = (uint8_t)(p.me_sub_sad ? 1 : 0);
+            for (int k = 0; k < 7; k++) it.reserved[k] = 0;
+            items[i] = it;
+        }
+    }
+}
+
+struct MeWorkspace {
+    size_t cap = 0;  // in (ref, b64) pairs
+    SvtB200SadSearchItem* items = nullptr;
+    SvtB200SadSearchResult* res = nullptr;
+    HmeSide* side = nullptr;
+    int16_t *x[3] = {nullptr, nullptr, nullptr}, *y[3] = {nullptr, nullptr, nullptr};
+    uint64_t* sad[3] = {nullptr, nullptr, nullptr};
+    SvtB200FullpelItem* fp_items = nullptr;
+    SvtB200MePicture* refs = nullptr;
+    SvtB200MeParams* prm = nullptr;
+};
+static MeWorkspace g_me_ws;
+static std::mutex  g_me_mu;
+
+static void me_ws_reserve(size_t pairs) {
+    MeWorkspace& w = g_me_ws;
+    if (pairs <= w.cap) return;
+    auto fr = [](void* p) { if (p) cudaFree(p); };
+    fr(w.items); fr(w.res); fr(w.side); fr(w.fp_items); fr(w.refs); fr(w.prm);
+    for (int l = 0; l < 3; l++) { fr(w.x[l]); fr(w.y[l]); fr(w.sad[l]); }
+    w.cap = pairs * 2;
+    const size_t n4 = w.cap * 4;
+    B200_CUDA_CHECK(cudaMalloc(&w.items, n4 * sizeof(SvtB200SadSearchItem)));
+    B200_CUDA_CHECK(cudaMalloc(&w.res, n4 * sizeof(SvtB200SadSearchResult)));
+    B200_CUDA_CHECK(cudaMalloc(&w.side, n4 * sizeof(HmeSide)));
+    for (int l = 0; l < 3; l++) {
+        B200_CUDA_CHECK(cudaMalloc(&w.x[l], n4 * 2));
+        B200_CUDA_CHECK(cudaMalloc(&w.y[l], n4 * 2));
+        B200_CUDA_CHECK(cudaMalloc(&w.sad[l], n4 * 8));
+    }
+    B200_CUDA_CHECK(cudaMalloc(&w.fp_items, w.cap * sizeof(SvtB200FullpelItem)));
+    B200_CUDA_CHECK(cudaMalloc(&w.refs, 16 * sizeof(SvtB200MePicture)));
+    B200_CUDA_CHECK(cudaMalloc(&w.prm, 16 * sizeof(SvtB200MeParams)));
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+// T1: downsample_2d (aom_dsp_rtcd.h:841)
+extern "C" void svt_b200_downsample_2d(uint8_t* input_samples, uint32_t input_stride, uint32_t input_area_width, uint32_t input_area_height,
+                                       uint8_t* decim_samples, uint32_t decim_stride, uint32_t decim_step) {
+    require_ready();
+    const uint32_t half = decim_step >> 1;
+    if (input_area_width <= half || input_area_height <= half) return;
+    const uint32_t ow = (input_area_width - half + decim_step - 1) / decim_step, oh = (input_area_height - half + decim_step - 1) / decim_step;
+    LaneGuard l;
+    size_t o_in = l->alloc((size_t)input_area_height * input_area_width);
+    size_t in_end = l->used;
+    size_t o_out = l->alloc((size_t)ow * oh);
+    for (uint32_t r = 0; r < input_area_height; r++) memcpy(l->h<uint8_t>(o_in) + (size_t)r * input_area_width, input_samples + (size_t)r * input_stride, input_area_width);
+    l->h2d(0, in_end);
+    downsample_2d_kernel<<<grid_for((ow * oh + 255) / 256, 8), 256, 0, l->stream>>>(l->d<uint8_t>(o_in), (int)input_area_width, (int)input_area_width,
+                                                                                 (int)input_area_height, l->d<uint8_t>(o_out), (int)ow, (int)decim_step);
+    B200_LAUNCH_CHECK();
+    l->d2h(o_out, (size_t)ow * oh);
+    l->sync();
+    for (uint32_t r = 0; r < oh; r++) memcpy(decim_samples + (size_t)r * decim_stride, l->h<uint8_t>(o_out) + (size_t)r * ow, ow);
+}
+
+// T2: build the padded 1/4 and 1/16 luma planes of one picture on the device
+extern "C" int svt_b200_build_hme_pyramid_dev(const SvtB200MePicture* pic, void* stream) {
+    require_ready();
+    if (!pic) return SVT_B200_ERR_BAD_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    for (int lvl = 1; lvl >= 0; lvl--) {  // quarter from full, sixteenth from quarter
+        const int s = lvl + 1;
+        const uint8_t* in = pic->plane[s] + (size_t)pic->org_y[s] * pic->stride[s] + pic->org_x[s];
+        uint8_t* out = const_cast<uint8_t*>(pic->plane[lvl]) + (size_t)pic->org_y[lvl] * pic->stride[lvl] + pic->org_x[lvl];
+        const int n = pic->width[lvl] * pic->height[lvl];
+        downsample_2d_kernel<<<grid_for((n + 255) / 256, 8), 256, 0, st>>>(in, pic->stride[s], pic->width[s], pic->height[s], out, pic->stride[lvl], 2);
+        B200_LAUNCH_CHECK();
+        const int tn = (pic->width[lvl] + 2 * pic->org_x[lvl]) * (pic->height[lvl] + 2 * pic->org_y[lvl]);
+        pad_plane_kernel<<<grid_for((tn + 255) / 256, 8), 256, 0, st>>>(const_cast<uint8_t*>(pic->plane[lvl]), pic->stride[lvl], pic->width[lvl],
+                                                                      pic->height[lvl], pic->org_x[lvl], pic->org_y[lvl]);
+        B200_LAUNCH_CHECK();
+    }
+    return SVT_B200_OK;
+}
+
+extern "C" int svt_b200_me_picture_dev(const SvtB200MePicture* cur, const SvtB200MePicture* refs, const SvtB200MeParams* params, int n_refs,
+                                       uint32_t* d_best_sad, uint32_t* d_best_mv, int16_t* d_hme_centre, uint64_t* d_hme_sad, void* stream) {
+    require_ready();
+    if (!cur || !refs || !params || n_refs <= 0 || n_refs > 16) return SVT_B200_ERR_BAD_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int b64_w = (cur->width[2] + 63) >> 6, b64_h = (cur->height[2] + 63) >> 6, n_b64 = b64_w * b64_h;
+    const int pairs = n_refs * n_b64, n4 = pairs * 4;
+    std::lock_guard<std::mutex> lk(g_me_mu);
+    me_ws_reserve((size_t)pairs);
+    MeWorkspace& w = g_me_ws;
+    B200_CUDA_CHECK(cudaMemcpyAsync(w.refs, refs, n_refs * sizeof(SvtB200MePicture), cudaMemcpyHostToDevice, st));
+    B200_CUDA_CHECK(cudaMemcpyAsync(w.prm, params, n_refs * sizeof(SvtB200MeParams), cudaMemcpyHostToDevice, st));
+    const int g = grid_for((n4 + 255) / 256, 8);
+    int max_l0_w = 8, max_l0_h = 1;
+    for (int r = 0; r < n_refs; r++) {
+        max_l0_w = max_l0_w > ((params[r].hme_l0_sa_w + 7) & ~7) ? max_l0_w : ((params[r].hme_l0_sa_w + 7) & ~7);
+        max_l0_h = max_l0_h > params[r].hme_l0_sa_h ? max_l0_h : params[r].hme_l0_sa_h;
+    }
+    for (int level = 0; level < 3; level++) {
+        hme_prepare_kernel<<<g, 256, 0, st>>>(*cur, w.refs, w.prm, n_refs, n_b64, b64_w, level, level ? w.x[level - 1] : nullptr,
+                                              level ? w.y[level - 1] : nullptr, w.items, w.side);
+        B200_LAUNCH_CHECK();
+        const int bs = 16 << level;
+        // shared-memory bound for this level's searches (the kernel adapts its tiling to what it gets)
+        const int saw = level == 0 ? max_l0_w : 16, sah = level == 0 ? max_l0_h : 8;
+        const size_t lw = ((saw + bs + 3) >> 2) + 10;
+        const size_t smem = (size_t)(((bs + 15) >> 4) << 2) * 4 * bs + 2048 * 4 + 64 + (size_t)(sah - 1 + 2 * (bs - 1) + 1) * lw * 4;
+        launch_sad_search(nullptr, nullptr, w.items, n4, w.res, smem, st);
+        hme_finish_kernel<<<g, 256, 0, st>>>(w.res, w.side, w.prm, n_refs, n_b64, level, w.x[level], w.y[level], w.sad[level]);
+        B200_LAUNCH_CHECK();
+    }
+    me_centre_kernel<<<grid_for((pairs * 32 + 255) / 256, 8), 256, 0, st>>>(*cur, w.refs, w.prm, n_refs, n_b64, b64_w, w.x[2], w.y[2], w.sad[2],
+                                                                          d_hme_centre, d_hme_sad, w.fp_items);
+    B200_LAUNCH_CHECK();
+    return svt_b200_fullpel_search_batch_dev(nullptr, nullptr, w.fp_items, pairs, d_best_sad, d_best_mv, stream);
+}

@@ -264,7 +264,7 @@ __global__ void nxm_sad_kernel(const uint8_t* __restrict__ src, uint32_t src_str
     if (threadIdx.x == 0) *out = tot;
 }
 
-static void launch_sad_search(const uint8_t* d_src, const uint8_t* d_ref, const SvtB200SadSearchItem* d_items, int n,
+void launch_sad_search(const uint8_t* d_src, const uint8_t* d_ref, const SvtB200SadSearchItem* d_items, int n,
                               SvtB200SadSearchResult* d_results, size_t smem, cudaStream_t st) {
     if (n <= 0) return;
     Context& c = ctx();

@@ -376,3 +376,49 @@ lib.svt_b200_get_proj_subspace.argtypes = [vp, ct.c_int, ct.c_int, ct.c_int, vp,
 lib.svt_b200_get_proj_subspace.restype = None
 lib.svt_b200_sgr_units_dev.argtypes = [vp, vp, ct.c_int, vp, vp, ct.c_int, ct.c_int, ct.c_int, vp]
 lib.svt_b200_sgr_units_dev.restype = ct.c_int
+
+# ------------------------------------------------------------------------------------------------
+# K13 + T2 open-loop ME for a whole picture
+# ------------------------------------------------------------------------------------------------
+class MePicture(ct.Structure):
+    _fields_ = [("plane", vp * 3), ("stride", ct.c_int32 * 3), ("org_x", ct.c_int32 * 3), ("org_y", ct.c_int32 * 3),
+                ("width", ct.c_int32 * 3), ("height", ct.c_int32 * 3), ("reserved", ct.c_int32 * 2)]
+
+
+class MeParams(ct.Structure):
+    _fields_ = [("hme_l0_sa_w", ct.c_int32), ("hme_l0_sa_h", ct.c_int32), ("hme_l1_sa_w", ct.c_int32), ("hme_l1_sa_h", ct.c_int32),
+                ("hme_l2_sa_w", ct.c_int32), ("hme_l2_sa_h", ct.c_int32), ("me_sa_w", ct.c_int32), ("me_sa_h", ct.c_int32),
+                ("hme_sub_sad", ct.c_int32), ("me_sub_sad", ct.c_int32), ("check_zero_centre", ct.c_int32), ("reserved", ct.c_int32)]
+
+
+lib.svt_b200_downsample_2d.argtypes = [vp, ct.c_uint32, ct.c_uint32, ct.c_uint32, vp, ct.c_uint32, ct.c_uint32]
+lib.svt_b200_downsample_2d.restype = None
+lib.svt_b200_build_hme_pyramid_dev.argtypes = [ct.POINTER(MePicture), vp]
+lib.svt_b200_build_hme_pyramid_dev.restype = ct.c_int
+lib.svt_b200_me_picture_dev.argtypes = [ct.POINTER(MePicture), ct.POINTER(MePicture), ct.POINTER(MeParams), ct.c_int, vp, vp, vp, vp, vp]
+lib.svt_b200_me_picture_dev.restype = ct.c_int
+
+ME_PAD = (16, 32, 72)  # padding of the 1/16, 1/4 and full luma planes (the reference uses 16 / 32 / 64+)
+
+
+def me_plane_shapes(width, height):
+    """[(h_total, w_total, org, w, h)] for levels 0 (1/16), 1 (1/4), 2 (full); strides are 16-byte multiples"""
+    out = []
+    for lvl in range(3):
+        w, h, pad = width >> (2 - lvl), height >> (2 - lvl), ME_PAD[lvl]
+        stride = (w + 2 * pad + 15) & ~15
+        out.append((h + 2 * pad, stride, pad, w, h))
+    return out
+
+
+def me_picture_desc(planes, width, height):
+    """planes: three 2-D uint8 torch CUDA tensors (padded buffers) as laid out by me_plane_shapes()"""
+    p = MePicture()
+    for lvl, (th, stride, pad, w, h) in enumerate(me_plane_shapes(width, height)):
+        p.plane[lvl] = planes[lvl].data_ptr()
+        p.stride[lvl] = planes[lvl].stride(0)
+        p.org_x[lvl] = pad
+        p.org_y[lvl] = pad
+        p.width[lvl] = w
+        p.height[lvl] = h
+    return p

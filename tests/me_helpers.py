@@ -62,3 +62,132 @@ def hadamard_call(lib, name, src, stride, n):
     else:
         f(P(src), ct.c_ssize_t(stride), P(out))
     return out
+
+
+# ---- whole-picture open-loop ME, driven on the reference kernels ------------------------------------
+def i16(v):
+    v &= 0xffff
+    return v - 0x10000 if v & 0x8000 else v
+
+
+def build_pyramid_np(full, width, height, shapes):
+    """numpy restatement of svt_aom_downsample_2d_c + svt_aom_generate_padding (checked against the
+    reference function in test_oracle_pins)."""
+    planes = [None, None, None]
+    th, stride, pad, w, h = shapes[2]
+    buf = np.zeros((th, stride), np.uint8)
+    buf[pad:pad + h, pad:pad + w] = full
+    planes[2] = pad_np(buf, pad, w, h)
+    src = full.astype(np.uint32)
+    for lvl in (1, 0):
+        th, stride, pad, w, h = shapes[lvl]
+        d = ((src[0::2, 0::2] + src[0::2, 1::2] + src[1::2, 0::2] + src[1::2, 1::2] + 2) >> 2)[:h, :w]
+        buf = np.zeros((th, stride), np.uint8)
+        buf[pad:pad + h, pad:pad + w] = d
+        planes[lvl] = pad_np(buf, pad, w, h)
+        src = d.astype(np.uint32)
+    return planes
+
+
+def pad_np(buf, pad, w, h):
+    inner = buf[pad:pad + h, pad:pad + w]
+    buf[:, :] = np.pad(inner, ((pad, buf.shape[0] - pad - h), (pad, buf.shape[1] - pad - w)), mode="edge")
+    return buf
+
+
+def hme_clip(org, origin, sa, pad, pic, round8):
+    if i16(org + origin) < -pad:
+        origin = i16(-pad - org)
+        sa = i16(sa - (-pad - (org + origin)))
+    if i16(org + origin) > pic - 1:
+        origin = i16(origin - ((org + origin) - (pic - 1)))
+    if i16(org + origin + sa) > pic:
+        sa = max(1, i16(sa - ((org + origin + sa) - pic)))
+    if round8:
+        sa = sa if sa < 8 else sa & ~7
+    return origin, sa
+
+
+def ref_me_picture(refc, cur, refs, shapes, width, height, params, sad_fn="svt_sad_loop_kernel_c"):
+    """cur/refs: lists of 3 padded numpy planes.  Returns (best_sad, best_mv, hme_centre, hme_sad)."""
+    from helpers import sad_loop_call
+    b64_w, b64_h = (width + 63) // 64, (height + 63) // 64
+    nb = b64_w * b64_h
+    R = len(refs)
+    out_sad = np.zeros((R, nb, 85), np.uint32); out_mv = np.zeros((R, nb, 85), np.uint32)
+    out_c = np.zeros((R, nb, 2), np.int16); out_hs = np.zeros((R, nb), np.uint64)
+    curf = [p.reshape(-1) for p in cur]
+    for r in range(R):
+        p = params[r]
+        reff = [q.reshape(-1) for q in refs[r]]
+        sub = 1 if p["hme_sub_sad"] else 0
+        for b in range(nb):
+            bx, by = b % b64_w, b // b64_w
+            prev = [(0, 0)] * 4
+            lsad = [0] * 4
+            for level in range(3):
+                th, stride, pad, w, h = shapes[level]
+                sh = 2 - level
+                org_x, org_y = (bx * 64) >> sh, (by * 64) >> sh
+                blk_w, blk_h = min(64, width - bx * 64) >> sh, min(64, height - by * 64) >> sh
+                nxt = []
+                for reg in range(4):
+                    sr_w, sr_h = reg & 1, reg >> 1
+                    if level == 0:
+                        sa_w = (p["hme_l0_sa_w"] + 7) & ~7; sa_h = p["hme_l0_sa_h"]
+                        ox = i16(-((sa_w * 2) >> 1) + sa_w * sr_w); oy = i16(-((sa_h * 2) >> 1) + sa_h * sr_h)
+                        pw = ph = pad - 1
+                    elif level == 1:
+                        sa_w = (p["hme_l1_sa_w"] + 7) & ~7; sa_h = p["hme_l1_sa_h"]
+                        ox = i16(-(sa_w >> 1) + (prev[reg][0] >> 1)); oy = i16(-(sa_h >> 1) + (prev[reg][1] >> 1))
+                        pw = ph = pad - 1
+                    else:
+                        sa_w = (p["hme_l2_sa_w"] + 7) & ~7; sa_h = p["hme_l2_sa_h"]
+                        ox = i16(-(sa_w >> 1) + prev[reg][0]); oy = i16(-(sa_h >> 1) + prev[reg][1])
+                        pw = ph = 63
+                    ox, sa_w = hme_clip(org_x, ox, sa_w, pw, w, True)
+                    oy, sa_h = hme_clip(org_y, oy, sa_h, ph, h, False)
+                    s_off = (pad + org_y) * stride + pad + org_x
+                    r_off = (pad + org_y + oy) * stride + pad + org_x + ox
+                    best, x, y = sad_loop_call(refc, sad_fn, curf[level], s_off, stride << sub, reff[level], r_off, stride << sub,
+                                               blk_h >> sub, blk_w, stride, 0, sa_w, sa_h)
+                    if sub:
+                        best *= 2
+                    mul = 4 if level == 0 else (2 if level == 1 else 1)
+                    nxt.append((i16(i16(x + ox) * mul), i16(i16(y + oy) * mul)))
+                    lsad[reg] = best
+                prev = nxt
+            cx, cy, cs = prev[0][0], prev[0][1], lsad[0]
+            for reg in range(1, 4):
+                if lsad[reg] < cs:
+                    cs, cx, cy = lsad[reg], prev[reg][0], prev[reg][1]
+            out_c[r, b] = (cx, cy); out_hs[r, b] = cs
+            th, stride, pad, w, h = shapes[2]
+            org_x, org_y = bx * 64, by * 64
+            blk_w, blk_h = min(64, width - org_x), min(64, height - org_y)
+            sx, sy = cx, cy
+            s_off = (pad + org_y) * stride + pad + org_x
+            if p["check_zero_centre"] and (sx != 0 or sy != 0):
+                if i16(org_x + sx) < -63: sx = i16(-63 - org_x)
+                if i16(org_x + sx) > w - 1: sx = i16(sx - ((org_x + sx) - (w - 1)))
+                if i16(org_y + sy) < -63: sy = i16(-63 - org_y)
+                if i16(org_y + sy) > h - 1: sy = i16(sy - ((org_y + sy) - (h - 1)))
+                f = refc.svt_nxm_sad_kernel_helper_c; f.restype = ct.c_uint32
+                z = f(P(curf[2], s_off), ct.c_uint32(stride * 2), P(reff[2], s_off), ct.c_uint32(stride * 2), blk_h >> 1, blk_w) << 1
+                hs = f(P(curf[2], s_off), ct.c_uint32(stride * 2), P(reff[2], s_off + sy * stride + sx), ct.c_uint32(stride * 2), blk_h >> 1,
+                       blk_w) << 1
+                if z <= hs:
+                    sx = sy = 0
+            sa_w = (max(1, p["me_sa_w"]) + 7) & ~7; sa_h = max(3, p["me_sa_h"])
+            ox, oy = i16(sx - (sa_w >> 1)), i16(sy - (sa_h >> 1))
+            if i16(org_x + ox) < -63: ox = i16(-63 - org_x)
+            if i16(org_x + ox) > width - 1: ox = i16(ox - ((org_x + ox) - (width - 1)))
+            if i16(org_x + ox + sa_w) > width: sa_w = max(1, sa_w - ((org_x + ox + sa_w) - width))
+            sa_w = sa_w if sa_w < 8 else sa_w & ~7
+            if i16(org_y + oy) < -63: oy = i16(-63 - org_y)
+            if i16(org_y + oy) > height - 1: oy = i16(oy - ((org_y + oy) - (height - 1)))
+            if i16(org_y + oy + sa_h) > height: sa_h = max(1, sa_h - ((org_y + oy + sa_h) - height))
+            r_off = (pad + org_y + oy) * stride + pad + org_x + ox
+            sad, mv = ref_fullpel(refc, curf[2], s_off, stride, reff[2], r_off, stride, sa_w, sa_h, ox, oy, p["me_sub_sad"])
+            out_sad[r, b] = sad; out_mv[r, b] = mv
+    return out_sad, out_mv, out_c, out_hs
