@@ -1,0 +1,385 @@
+#!/usr/bin/env python3
+"""bench.py -- the driver's measurement contract for the svt-av1-psy B200 DSP tier.
+
+  python bench.py --gpus N --steps K --warmup W                 B200 arm (libsvtav1_b200.so, T2 entry points)
+  python bench.py --impl reference --gpus N --steps K --warmup W  reference arm: the reference's own kernels
+                                                                (oracle/_ref, AVX2 intrinsics tier where it
+                                                                builds without NASM, else C) on all host cores
+
+A "step" = the hot-path DSP work of ONE 1920x1080 8-bit 4:2:0 frame at preset-8 / CRF-30 settings
+(svt-av1-psy_b200/workload.py): open-loop ME (HME pyramid + 85-PU full-pel search, 2 references),
+forward transform + quantize + inverse/reconstruction of every sample, CDEF search + apply, Wiener
+statistics + filter.  Prints ONE JSON line (rank 0).
+
+`value`  : frames/s with every input already resident in HBM (CUDA events on the launch stream).
+`e2e`    : same metric through the host-buffer path: per step the source picture, residual and
+           prediction are copied from pinned host memory and the ME results, quantised coefficients,
+           CDEF costs, Wiener statistics and the filtered picture are read back, inside the timed region.
+"""
+import argparse
+import ctypes as ct
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "1080p preset-8 hot-path (ME + transform/quant + CDEF + Wiener) frames/sec"
+N_FRAME_SETS = 4  # rotated between steps so that consecutive steps do not hit a warm L2
+
+
+# ------------------------------------------------------------------------------------------------------
+# reference arm: the reference's own kernels over the same work lists (oracle/ref_driver.c)
+# ------------------------------------------------------------------------------------------------------
+def aligned_zeros(n, dtype, align=64):
+    """numpy array whose data pointer is `align`-byte aligned (the AVX2 kernels use aligned stores)"""
+    isz = np.dtype(dtype).itemsize
+    raw = np.zeros(n * isz + align, np.uint8)
+    off = (-raw.ctypes.data) % align
+    return raw[off:off + n * isz].view(dtype)
+
+
+class RefFrame:
+    def __init__(self, wl, ref):
+        from oracle import support as me_np
+        self.wl, self.ref = wl, ref
+        W, H = wl.width, wl.height
+        self.cur_pyr = me_np.build_pyramid_np(wl.cur[0], W, H, wl.me_shapes)
+        self.ref_pyrs = [me_np.build_pyramid_np(r[0], W, H, wl.me_shapes) for r in wl.refs]
+        self.cur_desc = me_np.ref_pic_desc(self.cur_pyr, wl.me_shapes)
+        self.ref_descs = (me_np.RefMePicture * wl.n_refs)(*[me_np.ref_pic_desc(p, wl.me_shapes) for p in self.ref_pyrs])
+        self.prm = (me_np.RefMeParams * wl.n_refs)()
+        for i, p in enumerate(wl.me_params):
+            for k, v in p.items():
+                setattr(self.prm[i], k, v)
+        nb = ((W + 63) // 64) * ((H + 63) // 64)
+        self.me_sad = np.zeros((wl.n_refs, nb, 85), np.uint32)
+        self.me_mv = np.zeros_like(self.me_sad)
+        self.me_c = np.zeros((wl.n_refs, nb, 2), np.int16)
+        self.me_hs = np.zeros((wl.n_refs, nb), np.uint64)
+        self.cur_flat = np.concatenate([p.reshape(-1) for p in wl.cur])
+        res = np.concatenate([p.reshape(-1) for p in wl.residual])
+        self.residual = aligned_zeros(res.size, np.int16)
+        self.residual[:] = res
+        _, n_pad = wl.padded_offsets()
+        self.pred = self._pad_planes(wl.pred)
+        self.recon = np.zeros(n_pad, np.uint8)
+        self.cdef_out = np.zeros(n_pad, np.uint8)
+        self.final = np.zeros(n_pad, np.uint8)
+        self.coeff = aligned_zeros(wl.n_coeffs, np.int32)
+        self.q = aligned_zeros(wl.n_coeffs, np.int32)
+        self.dq = aligned_zeros(wl.n_coeffs, np.int32)
+        self.eobs = np.zeros(len(wl.quant_items), np.uint16)
+        self.fwd = np.ascontiguousarray(wl.fwd_items)
+        self.inv = np.ascontiguousarray(wl.inv_items)
+        self.qi = np.ascontiguousarray(wl.quant_items)
+        self.mse = np.zeros((2, nb, len(wl.cdef_str_y)), np.uint64)
+        self.dirs = np.zeros((nb, 64), np.uint8)
+        self.vars = np.zeros((nb, 64), np.int32)
+        self.M = np.zeros((len(wl.stats_items), 49), np.int64)
+        self.Hm = np.zeros((len(wl.stats_items), 2401), np.int64)
+        for f in ("ref_me_picture", "ref_fwd_txfm_batch", "ref_quant_batch", "ref_inv_txfm_batch_8bit", "ref_cdef_search_frame",
+                  "ref_cdef_apply_frame", "ref_compute_stats_batch", "ref_wiener_units_8bit"):
+            getattr(ref, f).restype = None
+
+    def _pad_planes(self, planes):
+        wl = self.wl
+        off, n = wl.padded_offsets()
+        buf = np.zeros(n, np.uint8)
+        for p in range(3):
+            th, st = wl.padded_shape(p)
+            w, h = wl.plane_dims[p]
+            buf[off[p]:off[p] + th * st].reshape(th, st)[:, :w + 2 * wl.PAD] = np.pad(planes[p], wl.PAD, mode="edge")
+        return buf
+
+    def _extend(self, buf):
+        wl = self.wl
+        off, _ = wl.padded_offsets()
+        for p in range(3):
+            th, st = wl.padded_shape(p)
+            w, h = wl.plane_dims[p]
+            v = buf[off[p]:off[p] + th * st].reshape(th, st)
+            v[:, :w + 2 * wl.PAD] = np.pad(v[wl.PAD:wl.PAD + h, wl.PAD:wl.PAD + w], wl.PAD, mode="edge")
+
+    def _cdef_frame(self):
+        from oracle import support as me_np
+        wl = self.wl
+        off, _ = wl.padded_offsets()
+        soff, _ = wl.flat_offsets()
+        f = me_np.RefCdefFrame()
+        ptrs = []
+        for p in range(3):
+            th, st = wl.padded_shape(p)
+            ptrs.append(self.recon.ctypes.data + off[p] + wl.PAD * st + wl.PAD)
+        f.recon_y, f.recon_cb, f.recon_cr = ptrs
+        f.src_y, f.src_cb, f.src_cr = [self.cur_flat.ctypes.data + soff[p] for p in range(3)]
+        f.recon_stride_y, f.recon_stride_c = wl.padded_shape(0)[1], wl.padded_shape(1)[1]
+        f.src_stride_y, f.src_stride_c = wl.plane_dims[0][0], wl.plane_dims[1][0]
+        f.width, f.height, f.bit_depth, f.damping, f.subsampling_factor = wl.width, wl.height, 8, wl.cdef_damping, wl.cdef_subsampling
+        return f
+
+    def step(self):
+        wl, ref = self.wl, self.ref
+        P = lambda a, o=0: ct.c_void_p(a.ctypes.data + o)  # noqa: E731
+        # ME (the numpy pyramid build is input preparation and stays outside, like the resident refs)
+        ref.ref_me_picture(ct.byref(self.cur_desc), self.ref_descs, self.prm, wl.n_refs, P(self.me_sad), P(self.me_mv), P(self.me_c), P(self.me_hs))
+        ref.ref_fwd_txfm_batch(P(self.residual), P(self.coeff), P(self.fwd), len(self.fwd))
+        ref.ref_quant_batch(P(self.coeff), P(self.q), P(self.dq), P(wl.scan_table), P(wl.iscan_table), P(wl.qm_table), P(self.qi), len(self.qi), P(self.eobs))
+        ref.ref_inv_txfm_batch_8bit(P(self.dq), P(self.pred), P(self.recon), P(self.inv), len(self.inv))
+        f = self._cdef_frame()
+        ref.ref_cdef_search_frame(ct.byref(f), P(wl.skip8x8), P(wl.cdef_str_y), P(wl.cdef_str_uv), len(wl.cdef_str_y), P(self.mse), P(self.dirs),
+                                  P(self.vars))
+        np.copyto(self.cdef_out, self.recon)
+        off, _ = wl.padded_offsets()
+        outs = [self.cdef_out.ctypes.data + off[p] + wl.PAD * wl.padded_shape(p)[1] + wl.PAD for p in range(3)]
+        ref.ref_cdef_apply_frame(ct.byref(f), P(wl.skip8x8), P(wl.cdef_fb_idx), P(wl.cdef_apply_y), P(wl.cdef_apply_uv), ct.c_void_p(outs[0]),
+                                 ct.c_void_p(outs[1]), ct.c_void_p(outs[2]), wl.padded_shape(0)[1], wl.padded_shape(1)[1])
+        self._extend(self.cdef_out)
+        ref.ref_compute_stats_batch(P(self.cdef_out), P(self.cur_flat), P(np.ascontiguousarray(wl.stats_items)), len(wl.stats_items), P(self.M),
+                                    P(self.Hm))
+        ref.ref_wiener_units_8bit(P(self.cdef_out), P(self.final), P(np.ascontiguousarray(wl.wiener_units)), len(wl.wiener_units))
+
+
+def load_reference():
+    import oracle
+    if oracle.ref is None:
+        return None, "port", 0
+    tier = oracle.ref.ref_set_tier(1)
+    return oracle.ref, ("reference" if tier == 1 else "reference"), tier
+
+
+def time_reference(wl, steps, warmup):
+    ref, kind, tier = load_reference()
+    if ref is None:
+        return None
+    fr = RefFrame(wl, ref)
+    cores = ref.ref_num_threads()
+    for _ in range(warmup):
+        fr.step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        fr.step()
+    dt = time.perf_counter() - t0
+    return dict(fps=steps / dt, ms=1e3 * dt / steps, cores=cores, kind=kind,
+                tier="avx2-intrinsics (inverse transform: C, no NASM)" if tier == 1 else "c", frame=fr)
+
+
+# ------------------------------------------------------------------------------------------------------
+# clocks sampling (nvidia-smi) during the timed region
+# ------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.samples, self.index, self.stop_flag, self.th = [], index, False, None
+
+    def _run(self):
+        while not self.stop_flag:
+            try:
+                o = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                   capture_output=True, text=True, timeout=5).stdout.strip()
+                if o:
+                    self.samples.append([x.strip() for x in o.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def start(self):
+        self.th = threading.Thread(target=self._run, daemon=True)
+        self.th.start()
+
+    def stop(self):
+        self.stop_flag = True
+        if self.th:
+            self.th.join(timeout=6)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
+        mx = max(int(s[1]) for s in self.samples if s[1].isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for s in self.samples for i in range(4) if len(s) > 2 + i and s[2 + i].lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": reasons, "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--width", type=int, default=1920)
+    ap.add_argument("--height", type=int, default=1080)
+    ap.add_argument("--check", action="store_true", help="compare one frame of B200 output with the reference arm")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    warmup = max(args.warmup, 3)
+
+    import svt_av1_psy_b200  # noqa: F401  (ImportError = library not built: there is no fallback)
+    from svt_av1_psy_b200.workload import FrameWorkload
+
+    config = {"workload": "configs[1]: 1920x1080 8-bit 4:2:0 synthetic, preset 8 CRF 30 hot path (ME 2 refs + TX + CDEF + Wiener), 1 frame/step",
+              "width": args.width, "height": args.height, "frame_sets": N_FRAME_SETS,
+              "l2": "steps rotate over %d distinct frame sets (~65 MB each, >126 MB L2 in total)" % N_FRAME_SETS,
+              "parallelism": "frame-parallel x%d (no data-path collective; recon exchange = all_gather of the filtered frame)" % world}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        wl = FrameWorkload(args.width, args.height)
+        steps = min(args.steps, 5)
+        t = time_reference(wl, steps, min(warmup, 1))
+        if t is None:
+            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libsvtav1_ref.so is not built"}))
+            return
+        out = {"impl": "reference", "metric": METRIC, "value": round(t["fps"], 3), "unit": "frames/s", "n_gpus": args.gpus, "steps": steps,
+               "warmup": min(warmup, 1), "ms_per_step": round(t["ms"], 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+               "dtype": "u8", "data": "synthetic", "config": config,
+               "cpu_baseline": {"value": round(t["fps"], 3), "unit": "frames/s", "cores": t["cores"], "kind": "reference",
+                                "sample": "%d full frames, tier %s" % (steps, t["tier"])},
+               "e2e": {"value": round(t["fps"], 3), "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(out))
+        return
+
+    import torch
+    import torch.distributed as dist
+    from svt_av1_psy_b200 import dsp
+    from svt_av1_psy_b200.pipeline import FramePipeline
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dsp.init(local_rank)
+    sets = [FramePipeline(FrameWorkload(args.width, args.height, seed=20260923 + 17 * (rank * N_FRAME_SETS + i)), torch) for i in range(N_FRAME_SETS)]
+    wl0 = sets[0].wl
+    stream = torch.cuda.Stream()
+    gathered = torch.empty((world,) + tuple(sets[0].final.shape), dtype=torch.uint8, device="cuda") if world > 1 else None
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def run(n, e2e, stage_acc=None):
+        ev = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(n)] if stage_acc is not None else None
+        with torch.cuda.stream(stream):
+            start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            start.record()
+            for i in range(n):
+                fp = sets[i % N_FRAME_SETS]
+                if e2e:
+                    fp.load_inputs()
+                fp.step(ev[i] if ev else None)
+                if world > 1:  # reconstructed-reference exchange (the path's one real collective)
+                    dist.all_gather_into_tensor(gathered.view(-1), fp.final)
+                if e2e:
+                    fp.read_outputs()
+            end.record()
+        torch.cuda.synchronize()
+        if stage_acc is not None:
+            for i in range(n):
+                for k in range(4):
+                    stage_acc[k] += ev[i][k].elapsed_time(ev[i][k + 1])
+        return start.elapsed_time(end)
+
+    if args.check and rank == 0:
+        check_against_reference(sets[0], torch)
+
+    # ---- resident-input timing ---------------------------------------------------------------------------
+    run(warmup, False)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    l0 = dsp.launch_count()
+    stage_ms = [0.0] * 4
+    ms = run(args.steps, False, stage_ms)
+    launches = dsp.launch_count() - l0
+    barrier()
+    # ---- end-to-end timing -----------------------------------------------------------------------------------
+    run(warmup, True)
+    barrier()
+    ms_e2e = run(args.steps, True)
+    clocks = sampler.stop()
+    t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = float(t[0]), float(t[1])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    fps = world * args.steps / (ms / 1e3)
+    fps_e2e = world * args.steps / (ms_e2e / 1e3)
+    alg = wl0.algorithmic_bytes()
+    stage_ms = [x / args.steps for x in stage_ms]
+    names = list(FramePipeline.STAGES)
+    dom = int(np.argmax(stage_ms))
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    ach = alg[names[dom]] / (stage_ms[dom] / 1e3) / 1e9
+    roofline = {"bound": "hbm", "kernel": {"me": "sad_search_kernel+fullpel_search_kernel", "tx": "fwd_txfm_kernel+quant_kernel+inv_txfm_kernel",
+                                           "cdef": "cdef_search_kernel+cdef_apply_kernel", "rest": "stats_accum_kernel+wiener_convolve_kernel"}[names[dom]],
+                "stage": names[dom], "achieved": round(ach, 2), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 5),
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
+                "traffic": None, "algorithmic_bytes_per_launch_group": alg[names[dom]],
+                "note": "integer kernels that re-use shared-memory tiles heavily: instruction/latency bound, not HBM bound (SURVEY 8d)"}
+    out = {"metric": METRIC, "value": round(fps, 2), "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": warmup,
+           "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+           "data": "synthetic", "config": config, "clocks": clocks,
+           "e2e": {"value": round(fps_e2e, 2), "unit": "frames/s", "h2d_bytes_per_step": int(sets[0].h2d_bytes), "d2h_bytes_per_step": int(sets[0].d2h_bytes),
+                   "ms_per_step": round(ms_e2e / args.steps, 4)},
+           "gpu_launches": int(launches), "roofline": roofline,
+           "stages_ms": {n: round(v, 4) for n, v in zip(names, stage_ms)},
+           "stages_algorithmic_gbs": {n: round(alg[n] / (v / 1e3) / 1e9, 2) for n, v in zip(names, stage_ms)}}
+    if world == 1 and not args.no_cpu_baseline:
+        t = time_reference(wl0, 2, 1)
+        if t is not None:
+            out["cpu_baseline"] = {"value": round(t["fps"], 3), "unit": "frames/s", "cores": t["cores"], "kind": "reference",
+                                   "sample": "2 full frames of the same workload, tier %s" % t["tier"]}
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def check_against_reference(fp, torch):
+    """one frame through both arms, every output compared bit for bit"""
+    ref, _, _ = load_reference()
+    assert ref is not None, "oracle/_ref missing"
+    ref.ref_set_tier(0)
+    fr = RefFrame(fp.wl, ref)
+    fr.step()
+    fp.load_inputs()
+    fp.step()
+    torch.cuda.synchronize()
+    cmp = [("me_sad", fp.me_sad, fr.me_sad), ("me_mv", fp.me_mv, fr.me_mv), ("hme_centre", fp.me_centre, fr.me_c), ("coeff", fp.coeff, fr.coeff),
+           ("qcoeff", fp.qcoeff, fr.q), ("dqcoeff", fp.dqcoeff, fr.dq), ("eob", fp.eobs, fr.eobs), ("recon", fp.recon, fr.recon),
+           ("cdef_mse", fp.cdef_mse, fr.mse), ("cdef_dir", fp.cdef_dir, fr.dirs), ("cdef_out", fp.cdef_out, fr.cdef_out), ("wiener_M", fp.M, fr.M),
+           ("wiener_H", fp.Hm, fr.Hm), ("final", fp.final, fr.final)]
+    bad = []
+    for name, a, b in cmp:
+        a = a.cpu().numpy()
+        if not np.array_equal(a.view(np.uint8).reshape(-1), np.ascontiguousarray(b).view(np.uint8).reshape(-1)):
+            bad.append(name)
+    if bad:
+        raise SystemExit("PARITY FAILURE vs reference: " + ", ".join(bad))
+    print("parity vs reference C tier: all %d outputs bit-exact" % len(cmp), file=sys.stderr)
+
+
+if __name__ == "__main__":
+    main()

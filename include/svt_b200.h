@@ -167,7 +167,9 @@ typedef struct SvtB200FwdTxfmItem {
     uint32_t src_stride;
     uint8_t  tx_size;
     uint8_t  tx_type;
-    uint16_t reserved;
+    uint16_t reserved;   /* bit 0: packed output -- only the top-left min(W,32) x min(H,32) coefficients are
+                            written, at stride min(W,32) (the re-pack half of svt_handle_transform64x64 etc.,
+                            transforms.c:2374-2542); dst must then hold min(W,32)*min(H,32) int32 */
 } SvtB200FwdTxfmItem;
 
 typedef struct SvtB200InvTxfmItem {
@@ -496,6 +498,9 @@ typedef struct SvtB200MeParams {
     int32_t reserved;
 } SvtB200MeParams;
 
+/* replicate the w x h interior at (org_x, org_y) of an 8-bit device plane into its padding
+ * (svt_aom_generate_padding / svt_extend_frame) */
+SVT_B200_API int svt_b200_extend_plane_dev(uint8_t* d_buf, int stride, int w, int h, int org_x, int org_y, void* stream);
 /* fills the 1/4 and 1/16 planes (interior + replicated padding) from the full plane */
 SVT_B200_API int svt_b200_build_hme_pyramid_dev(const SvtB200MePicture* pic, void* stream);
 /* cur / refs / params are HOST structs holding device plane pointers.  Outputs (device):

@@ -283,15 +283,24 @@ static void fwd_one(int16_t* in, int32_t* out, uint32_t stride, int ty, int sz) 
 
 static struct { const int16_t* residual; int32_t* coeff; const RefFwdItem* items; } g_fwd;
 static void fwd_body(int i) {
-    fwd_one((int16_t*)g_fwd.residual + g_fwd.items[i].src_off, g_fwd.coeff + g_fwd.items[i].dst_off, g_fwd.items[i].src_stride,
-            g_fwd.items[i].tx_type, g_fwd.items[i].tx_size);
+    const RefFwdItem* it = &g_fwd.items[i];
+    const int W = TXW[it->tx_size], H = TXH[it->tx_size];
+    if ((it->reserved & 1) && (W > 32 || H > 32)) {
+        /* packed output: the re-pack half of svt_handle_transform64x64 & co (transforms.c:2374-2542) */
+        DECLARE_ALIGNED(64, int32_t, tmp[64 * 64]);
+        const int Wp = W > 32 ? 32 : W, Hp = H > 32 ? 32 : H;
+        fwd_one((int16_t*)g_fwd.residual + it->src_off, tmp, it->src_stride, it->tx_type, it->tx_size);
+        for (int r = 0; r < Hp; r++) memcpy(g_fwd.coeff + it->dst_off + (size_t)r * Wp, tmp + (size_t)r * W, (size_t)Wp * sizeof(int32_t));
+        return;
+    }
+    fwd_one((int16_t*)g_fwd.residual + it->src_off, g_fwd.coeff + it->dst_off, it->src_stride, it->tx_type, it->tx_size);
 }
 void ref_fwd_txfm_batch(const int16_t* residual, int32_t* coeff, const RefFwdItem* items, int n) {
     g_fwd.residual = residual; g_fwd.coeff = coeff; g_fwd.items = items;
     par_for(n, 64, fwd_body);
 }
 
-static struct { const int32_t* coeff; int32_t *q, *dq; const int16_t* scan; const uint8_t* qm; const RefQuantItem* items; uint16_t* eobs; } g_q;
+static struct { const int32_t* coeff; int32_t *q, *dq; const int16_t *scan, *iscan; const uint8_t* qm; const RefQuantItem* items; uint16_t* eobs; } g_q;
 static void quant_body(int i) {
     const int32_t* coeff = g_q.coeff;
     int32_t *q = g_q.q, *dq = g_q.dq;
@@ -300,32 +309,43 @@ static void quant_body(int i) {
     const uint8_t* wm = it->qm_off == 0xffffffffu ? NULL : g_q.qm + it->qm_off;
     const uint8_t* im = it->iqm_off == 0xffffffffu ? NULL : g_q.qm + it->iqm_off;
     const int16_t* sc = g_q.scan + it->scan_off;
+    const int16_t* isc = g_q.iscan + it->scan_off; /* the SIMD tiers derive eob from the inverse scan */
+    /* MacroblockPlane tables are int16[8] = {DC, AC x 7}; the SIMD tiers load all eight lanes */
+    DECLARE_ALIGNED(16, int16_t, zbin[8]);
+    DECLARE_ALIGNED(16, int16_t, round[8]);
+    DECLARE_ALIGNED(16, int16_t, quant[8]);
+    DECLARE_ALIGNED(16, int16_t, quant_shift[8]);
+    DECLARE_ALIGNED(16, int16_t, dequant[8]);
+    for (int k = 0; k < 8; k++) {
+        zbin[k] = it->zbin[k != 0]; round[k] = it->round[k != 0]; quant[k] = it->quant[k != 0];
+        quant_shift[k] = it->quant_shift[k != 0]; dequant[k] = it->dequant[k != 0];
+    }
     if (it->mode == 2) { /* SVT_B200_QUANT_FP_LBD */
         if (wm || im)
-            svt_av1_quantize_fp_qm(coeff + it->coeff_off, it->n_coeffs, it->zbin, it->round, it->quant, it->quant_shift, q + it->q_off,
-                                   dq + it->dq_off, it->dequant, &eobs[i], sc, sc, wm, im, it->log_scale);
+            svt_av1_quantize_fp_qm(coeff + it->coeff_off, it->n_coeffs, zbin, round, quant, quant_shift, q + it->q_off,
+                                   dq + it->dq_off, dequant, &eobs[i], sc, isc, wm, im, it->log_scale);
         else if (it->log_scale == 0)
-            svt_av1_quantize_fp(coeff + it->coeff_off, it->n_coeffs, it->zbin, it->round, it->quant, it->quant_shift, q + it->q_off,
-                                dq + it->dq_off, it->dequant, &eobs[i], sc, sc);
+            svt_av1_quantize_fp(coeff + it->coeff_off, it->n_coeffs, zbin, round, quant, quant_shift, q + it->q_off,
+                                dq + it->dq_off, dequant, &eobs[i], sc, isc);
         else if (it->log_scale == 1)
-            svt_av1_quantize_fp_32x32(coeff + it->coeff_off, it->n_coeffs, it->zbin, it->round, it->quant, it->quant_shift, q + it->q_off,
-                                      dq + it->dq_off, it->dequant, &eobs[i], sc, sc);
+            svt_av1_quantize_fp_32x32(coeff + it->coeff_off, it->n_coeffs, zbin, round, quant, quant_shift, q + it->q_off,
+                                      dq + it->dq_off, dequant, &eobs[i], sc, isc);
         else
-            svt_av1_quantize_fp_64x64(coeff + it->coeff_off, it->n_coeffs, it->zbin, it->round, it->quant, it->quant_shift, q + it->q_off,
-                                      dq + it->dq_off, it->dequant, &eobs[i], sc, sc);
+            svt_av1_quantize_fp_64x64(coeff + it->coeff_off, it->n_coeffs, zbin, round, quant, quant_shift, q + it->q_off,
+                                      dq + it->dq_off, dequant, &eobs[i], sc, isc);
     } else if (it->mode == 0)
-        svt_aom_quantize_b(coeff + it->coeff_off, it->n_coeffs, it->zbin, it->round, it->quant, it->quant_shift, q + it->q_off, dq + it->dq_off,
-                           it->dequant, &eobs[i], sc, sc, wm, im, it->log_scale);
+        svt_aom_quantize_b(coeff + it->coeff_off, it->n_coeffs, zbin, round, quant, quant_shift, q + it->q_off, dq + it->dq_off,
+                           dequant, &eobs[i], sc, isc, wm, im, it->log_scale);
     else if (it->mode == 1)
-        svt_aom_highbd_quantize_b(coeff + it->coeff_off, it->n_coeffs, it->zbin, it->round, it->quant, it->quant_shift, q + it->q_off,
-                                  dq + it->dq_off, it->dequant, &eobs[i], sc, sc, wm, im, it->log_scale);
+        svt_aom_highbd_quantize_b(coeff + it->coeff_off, it->n_coeffs, zbin, round, quant, quant_shift, q + it->q_off,
+                                  dq + it->dq_off, dequant, &eobs[i], sc, isc, wm, im, it->log_scale);
     else
-        svt_av1_highbd_quantize_fp_qm(coeff + it->coeff_off, it->n_coeffs, it->zbin, it->round, it->quant, it->quant_shift, q + it->q_off,
-                                      dq + it->dq_off, it->dequant, &eobs[i], sc, sc, wm, im, it->log_scale);
+        svt_av1_highbd_quantize_fp_qm(coeff + it->coeff_off, it->n_coeffs, zbin, round, quant, quant_shift, q + it->q_off,
+                                      dq + it->dq_off, dequant, &eobs[i], sc, isc, wm, im, it->log_scale);
 }
-void ref_quant_batch(const int32_t* coeff, int32_t* q, int32_t* dq, const int16_t* scan, const uint8_t* qm, const RefQuantItem* items, int n,
-                     uint16_t* eobs) {
-    g_q.coeff = coeff; g_q.q = q; g_q.dq = dq; g_q.scan = scan; g_q.qm = qm; g_q.items = items; g_q.eobs = eobs;
+void ref_quant_batch(const int32_t* coeff, int32_t* q, int32_t* dq, const int16_t* scan, const int16_t* iscan, const uint8_t* qm,
+                     const RefQuantItem* items, int n, uint16_t* eobs) {
+    g_q.coeff = coeff; g_q.q = q; g_q.dq = dq; g_q.scan = scan; g_q.iscan = iscan; g_q.qm = qm; g_q.items = items; g_q.eobs = eobs;
     par_for(n, 64, quant_body);
 }
 

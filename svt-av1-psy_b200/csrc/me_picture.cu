@@ -290,6 +290,15 @@ extern "C" void svt_b200_downsample_2d(uint8_t* input_samples, uint32_t input_st
     for (uint32_t r = 0; r < oh; r++) memcpy(decim_samples + (size_t)r * decim_stride, l->h<uint8_t>(o_out) + (size_t)r * ow, ow);
 }
 
+extern "C" int svt_b200_extend_plane_dev(uint8_t* d_buf, int stride, int w, int h, int org_x, int org_y, void* stream) {
+    require_ready();
+    if (!d_buf || w <= 0 || h <= 0) return SVT_B200_ERR_BAD_ARG;
+    const int tn = (w + 2 * org_x) * (h + 2 * org_y);
+    pad_plane_kernel<<<grid_for((tn + 255) / 256, 8), 256, 0, (cudaStream_t)stream>>>(d_buf, stride, w, h, org_x, org_y);
+    B200_LAUNCH_CHECK();
+    return SVT_B200_OK;
+}
+
 // T2: build the padded 1/4 and 1/16 luma planes of one picture on the device
 extern "C" int svt_b200_build_hme_pyramid_dev(const SvtB200MePicture* pic, void* stream) {
     require_ready();

@@ -105,7 +105,11 @@ fwd_txfm_kernel(const int16_t* __restrict__ src_base, int32_t* __restrict__ dst_
             const int r = idx / W, c = idx - r * W;
             int32_t   v = round_shift_arr(R2[c * P2 + r], -cfg.f_s2);
             if (rect == 1 || rect == -1) v = round_shift64((long long)v * kNewSqrt2, 12);
-            dst[idx] = v;
+            if (item.reserved & 1) {  // packed output: keep the top-left min(W,32) x min(H,32) (svt_handle_transform64x64 repack, transforms.c:2374)
+                const int Wp = W > 32 ? 32 : W, Hp = H > 32 ? 32 : H;
+                if (r < Hp && c < Wp) dst[r * Wp + c] = v;
+            } else
+                dst[idx] = v;
         }
         team_sync<TEAM>();
     }

@@ -1,0 +1,209 @@
+"""Host-side mirror of the reference's process kernels for the hot path: a FramePipeline owns the
+device-resident planes / work lists of one frame set and enqueues the T2 entry points of
+libsvtav1_b200.so in the order the reference's ME -> EncDec(final pass) -> CDEF -> REST processes hand
+work to the dispatched DSP functions.  torch is used for device memory, streams
+and events only; every computation is a C-ABI call.
+"""
+import ctypes as ct
+
+import numpy as np
+
+from . import dsp
+from .dsp import lib
+
+
+def _t(torch, arr, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(arr))
+    return t.cuda(non_blocking=False)
+
+
+class FramePipeline:
+    def __init__(self, wl, torch, device="cuda"):
+        self.wl, self.torch = wl, torch
+        W, H = wl.width, wl.height
+        T = torch
+        # ---- ME: padded pyramids (current + references) -------------------------------------------
+        self.cur_planes = [T.zeros((s[0], s[1]), dtype=T.uint8, device=device) for s in wl.me_shapes]
+        self.ref_planes = [[T.zeros((s[0], s[1]), dtype=T.uint8, device=device) for s in wl.me_shapes] for _ in range(wl.n_refs)]
+        pad = wl.me_shapes[2][2]
+        self._full_pad = pad
+        for r, ref in enumerate(wl.refs):
+            self._upload_full(self.ref_planes[r], ref[0])
+            d = dsp.me_picture_desc(self.ref_planes[r], W, H)
+            assert lib.svt_b200_build_hme_pyramid_dev(ct.byref(d), None) == 0
+        self.cur_desc = dsp.me_picture_desc(self.cur_planes, W, H)
+        self.ref_descs = (dsp.MePicture * wl.n_refs)(*[dsp.me_picture_desc(p, W, H) for p in self.ref_planes])
+        self.me_prm = (dsp.MeParams * wl.n_refs)()
+        for i, p in enumerate(wl.me_params):
+            for k, v in p.items():
+                setattr(self.me_prm[i], k, v)
+        nb = ((W + 63) // 64) * ((H + 63) // 64)
+        self.n_b64 = nb
+        self.me_sad = T.zeros((wl.n_refs, nb, 85), dtype=T.int32, device=device)
+        self.me_mv = T.zeros_like(self.me_sad)
+        self.me_centre = T.zeros((wl.n_refs, nb, 2), dtype=T.int16, device=device)
+        self.me_hme_sad = T.zeros((wl.n_refs, nb), dtype=T.int64, device=device)
+        # ---- TX ---------------------------------------------------------------------------------------
+        _, n_flat = wl.flat_offsets()
+        _, n_pad = wl.padded_offsets()
+        self.cur_flat = T.zeros(n_flat, dtype=T.uint8, device=device)      # source picture Y|U|V
+        self.residual = T.zeros(n_flat, dtype=T.int16, device=device)
+        self.pred = T.zeros(n_pad, dtype=T.uint8, device=device)           # padded planes
+        self.recon = T.zeros(n_pad, dtype=T.uint8, device=device)
+        self.cdef_out = T.zeros(n_pad, dtype=T.uint8, device=device)
+        self.final = T.zeros(n_pad, dtype=T.uint8, device=device)
+        self.coeff = T.zeros(wl.n_coeffs, dtype=T.int32, device=device)
+        self.qcoeff = T.zeros_like(self.coeff)
+        self.dqcoeff = T.zeros_like(self.coeff)
+        self.eobs = T.zeros(len(wl.quant_items), dtype=T.int16, device=device)
+        self.fwd_items = _t(T, wl.fwd_items.view(np.uint8))
+        self.inv_items = _t(T, wl.inv_items.view(np.uint8))
+        self.quant_items = _t(T, wl.quant_items.view(np.uint8))
+        self.scan = _t(T, wl.scan_table)
+        self.qm = _t(T, wl.qm_table)
+        # ---- CDEF -------------------------------------------------------------------------------------
+        self.skip = _t(T, wl.skip8x8)
+        self.str_y, self.str_uv = _t(T, wl.cdef_str_y), _t(T, wl.cdef_str_uv)
+        self.cdef_mse = T.zeros((2, nb, len(wl.cdef_str_y)), dtype=T.int64, device=device)
+        self.cdef_dir = T.zeros((nb, 64), dtype=T.uint8, device=device)
+        self.cdef_var = T.zeros((nb, 64), dtype=T.int32, device=device)
+        self.fb_idx = _t(T, wl.cdef_fb_idx)
+        self.app_y, self.app_uv = _t(T, wl.cdef_apply_y), _t(T, wl.cdef_apply_uv)
+        # ---- REST -------------------------------------------------------------------------------------
+        self.stats_items = _t(T, wl.stats_items.view(np.uint8))
+        self.wiener_units = _t(T, wl.wiener_units.view(np.uint8))
+        self.M = T.zeros((len(wl.stats_items), 49), dtype=T.int64, device=device)
+        self.Hm = T.zeros((len(wl.stats_items), 2401), dtype=T.int64, device=device)
+        # ---- host staging for the end-to-end arm ------------------------------------------------------
+        self.h_cur = T.from_numpy(np.concatenate([p.reshape(-1) for p in wl.cur])).pin_memory()
+        self.h_res = T.from_numpy(np.concatenate([p.reshape(-1) for p in wl.residual])).pin_memory()
+        self.h_pred = T.from_numpy(self._pad_planes(wl.pred)).pin_memory()
+        self.h_out = {k: T.empty_like(v, device="cpu").pin_memory() for k, v in
+                      dict(me_sad=self.me_sad, me_mv=self.me_mv, q=self.qcoeff, eobs=self.eobs, mse=self.cdef_mse, M=self.M, H=self.Hm,
+                           final=self.final).items()}
+        self.load_inputs()
+        T.cuda.synchronize()
+
+    # -- helpers ------------------------------------------------------------------------------------------
+    def _pad_planes(self, planes):
+        wl = self.wl
+        off, n = wl.padded_offsets()
+        buf = np.zeros(n, np.uint8)
+        for p in range(3):
+            th, st = wl.padded_shape(p)
+            w, h = wl.plane_dims[p]
+            v = buf[off[p]:off[p] + th * st].reshape(th, st)
+            v[:, :w + 2 * wl.PAD] = np.pad(planes[p], wl.PAD, mode="edge")
+        return buf
+
+    def _upload_full(self, planes, luma):
+        pad, (H, W) = self._full_pad, luma.shape
+        st = planes[2].shape[1]
+        buf = np.zeros(planes[2].shape, np.uint8)
+        buf[:, :W + 2 * pad] = np.pad(luma, pad, mode="edge")
+        buf[:, W + 2 * pad:] = 0
+        planes[2].copy_(self.torch.from_numpy(buf))
+
+    def plane_views(self, flat, padded=True):
+        """[(tensor_2d_interior_origin_ptr, stride)] for the three planes of a padded flat buffer"""
+        wl = self.wl
+        out = []
+        off, _ = wl.padded_offsets() if padded else wl.flat_offsets()
+        for p in range(3):
+            if padded:
+                th, st = wl.padded_shape(p)
+                out.append((flat.data_ptr() + off[p] + wl.PAD * st + wl.PAD, st))
+            else:
+                out.append((flat.data_ptr() + off[p], wl.plane_dims[p][0]))
+        return out
+
+    def load_inputs(self, stream=None):
+        """host -> device copy of one frame's inputs (source picture, residual, prediction)"""
+        T = self.torch
+        self.cur_flat.copy_(self.h_cur, non_blocking=True)
+        self.residual.copy_(self.h_res, non_blocking=True)
+        self.pred.copy_(self.h_pred, non_blocking=True)
+        W, H, pad = self.wl.width, self.wl.height, self._full_pad
+        # the full-resolution luma of the ME pyramid is the padded source picture
+        self.cur_planes[2][pad:pad + H, pad:pad + W].copy_(self.cur_flat[:W * H].view(H, W))
+        s = T.cuda.current_stream().cuda_stream
+        assert lib.svt_b200_extend_plane_dev(self.cur_planes[2].data_ptr(), self.cur_planes[2].stride(0), W, H, pad, pad, s) == 0
+
+    def read_outputs(self):
+        for k, src in dict(me_sad=self.me_sad, me_mv=self.me_mv, q=self.qcoeff, eobs=self.eobs, mse=self.cdef_mse, M=self.M, H=self.Hm,
+                           final=self.final).items():
+            self.h_out[k].copy_(src, non_blocking=True)
+
+    @property
+    def h2d_bytes(self):
+        return self.h_cur.numel() + self.h_res.numel() * 2 + self.h_pred.numel()
+
+    @property
+    def d2h_bytes(self):
+        return sum(v.numel() * v.element_size() for v in self.h_out.values())
+
+    # -- stages ---------------------------------------------------------------------------------------------
+    def stage_me(self, s):
+        assert lib.svt_b200_build_hme_pyramid_dev(ct.byref(self.cur_desc), s) == 0
+        rc = lib.svt_b200_me_picture_dev(ct.byref(self.cur_desc), self.ref_descs, self.me_prm, self.wl.n_refs, self.me_sad.data_ptr(),
+                                         self.me_mv.data_ptr(), self.me_centre.data_ptr(), self.me_hme_sad.data_ptr(), s)
+        assert rc == 0
+
+    def stage_tx(self, s):
+        wl = self.wl
+        rc = lib.svt_b200_fwd_txfm_batch_dev(self.residual.data_ptr(), self.coeff.data_ptr(), self.fwd_items.data_ptr(), wl.n_small, wl.n_large,
+                                             wl.max_small, wl.max_large, s)
+        assert rc == 0
+        rc = lib.svt_b200_quant_batch_dev(self.coeff.data_ptr(), self.qcoeff.data_ptr(), self.dqcoeff.data_ptr(), self.scan.data_ptr(),
+                                          self.qm.data_ptr(), self.quant_items.data_ptr(), len(wl.quant_items), self.eobs.data_ptr(), s)
+        assert rc == 0
+        rc = lib.svt_b200_inv_txfm_batch_dev(self.dqcoeff.data_ptr(), self.pred.data_ptr(), self.recon.data_ptr(), self.inv_items.data_ptr(),
+                                             wl.n_small, wl.n_large, wl.max_small, wl.max_large, 1, s)
+        assert rc == 0
+
+    def cdef_frame(self, recon_flat):
+        wl = self.wl
+        f = dsp.CdefFrame()
+        (f.recon_y, sy), (f.recon_cb, sc), (f.recon_cr, _) = self.plane_views(recon_flat, True)
+        (f.src_y, ssy), (f.src_cb, ssc), (f.src_cr, _) = self.plane_views(self.cur_flat, False)
+        f.recon_stride_y, f.recon_stride_c, f.src_stride_y, f.src_stride_c = sy, sc, ssy, ssc
+        f.width, f.height, f.bit_depth, f.damping, f.subsampling_factor = wl.width, wl.height, 8, wl.cdef_damping, wl.cdef_subsampling
+        return f
+
+    def stage_cdef(self, s):
+        f = self.cdef_frame(self.recon)
+        rc = lib.svt_b200_cdef_search_frame_dev(ct.byref(f), self.skip.data_ptr(), self.str_y.data_ptr(), self.str_uv.data_ptr(),
+                                                len(self.wl.cdef_str_y), self.cdef_mse.data_ptr(), self.cdef_dir.data_ptr(),
+                                                self.cdef_var.data_ptr(), s)
+        assert rc == 0
+        self.cdef_out.copy_(self.recon, non_blocking=True)  # svt_av1_cdef_frame filters in place
+        (oy, sy), (ocb, sc), (ocr, _) = self.plane_views(self.cdef_out, True)
+        rc = lib.svt_b200_cdef_apply_frame_dev(ct.byref(f), self.skip.data_ptr(), self.fb_idx.data_ptr(), self.app_y.data_ptr(),
+                                               self.app_uv.data_ptr(), oy, ocb, ocr, sy, sc, s)
+        assert rc == 0
+
+    def stage_rest(self, s):
+        wl = self.wl
+        off, _ = wl.padded_offsets()
+        for p in range(3):  # svt_extend_frame: restoration reads beyond the picture edge
+            th, st = wl.padded_shape(p)
+            w, h = wl.plane_dims[p]
+            assert lib.svt_b200_extend_plane_dev(self.cdef_out.data_ptr() + off[p], st, w, h, wl.PAD, wl.PAD, s) == 0
+        rc = lib.svt_b200_compute_stats_batch_dev(self.cdef_out.data_ptr(), self.cur_flat.data_ptr(), self.stats_items.data_ptr(),
+                                                  len(wl.stats_items), 8, self.M.data_ptr(), self.Hm.data_ptr(), s)
+        assert rc == 0
+        rc = lib.svt_b200_wiener_units_dev(self.cdef_out.data_ptr(), self.final.data_ptr(), self.wiener_units.data_ptr(), len(wl.wiener_units), 8, s)
+        assert rc == 0
+
+    STAGES = ("me", "tx", "cdef", "rest")
+
+    def step(self, events=None):
+        """enqueue one frame of hot-path work on torch's current stream"""
+        T = self.torch
+        s = T.cuda.current_stream().cuda_stream
+        for i, name in enumerate(self.STAGES):
+            if events is not None:
+                events[i].record()
+            getattr(self, "stage_" + name)(s)
+        if events is not None:
+            events[len(self.STAGES)].record()

@@ -1,0 +1,235 @@
+"""Synthetic "1080p preset-8 hot path" workload: the per-frame work lists the B200 T2 entry points
+(and, in bench.py's reference arm, the reference's own kernels) are driven with.
+
+One frame of work = what the reference's ME, EncDec (final encode pass), CDEF and REST process
+kernels hand to the dispatched DSP functions for one 8-bit 4:2:0 picture at M8 / CRF 30 settings
+(search geometry from enc_mode_config.c:138-345 with qp 30, reference distance 1):
+
+  ME     HME L0 4 regions of 16x4, L1/L2 8x3, full-pel 8x3, SUB_SAD, 2 references, every 64x64 block
+  TX     forward transform -> fp quantizer with quantisation matrices (PSY default) -> inverse +
+         reconstruction, every luma and chroma sample once, in a 64..4 transform-size mix
+  CDEF   strength search over 6 (luma, chroma) candidates on the non-skip 8x8 blocks, then apply
+  REST   Wiener statistics (7x7 luma, 5x5 chroma) per restoration unit + separable Wiener filter
+
+Content follows SURVEY.md 8(d): multi-octave block noise panorama + global pan + sensor noise, seeded.
+Everything here is plain numpy data preparation; it performs no DSP.
+"""
+import numpy as np
+
+from . import dsp
+
+TX_W, TX_H = dsp.TX_W, dsp.TX_H
+
+
+def synth_sequence(width, height, n_frames, seed=20260923):
+    """list of (Y, U, V) uint8 planes"""
+    r = np.random.default_rng(seed)
+    pw, ph = width + 64 + 3 * n_frames, height + 64 + n_frames
+    pano = np.full((ph, pw), 128.0)
+    for size, amp in ((64, 60), (16, 35), (4, 18), (1, 8)):
+        g = r.normal(0, 1, ((ph + size - 1) // size + 1, (pw + size - 1) // size + 1))
+        pano += np.kron(g, np.ones((size, size)))[:ph, :pw] * (amp / 3.0)
+    frames = []
+    for t in range(n_frames):
+        y = pano[32 + t:32 + t + height, 32 + 3 * t:32 + 3 * t + width] + r.normal(0, 2, (height, width))
+        yy = np.clip(y, 0, 255)
+        c = 128 + 0.25 * (yy[0::2, 0::2] - 128)
+        frames.append((yy.astype(np.uint8), np.clip(c + 3, 0, 255).astype(np.uint8), np.clip(c - 3, 0, 255).astype(np.uint8)))
+    return frames
+
+
+def zigzag_scan(w, h):
+    """a diagonal scan over a w x h (row-major, stride w) coefficient block"""
+    order = sorted(((y + x, y if (y + x) & 1 else x, y, x) for y in range(h) for x in range(w)))
+    return np.array([y * w + x for _, _, y, x in order], np.int16)
+
+
+def quant_tables(d_dc, d_ac):
+    return {"zbin": np.array([(84 * d_dc + 64) >> 7, (84 * d_ac + 64) >> 7], np.int16),
+            "round": np.array([(64 * d_dc) >> 7, (64 * d_ac) >> 7], np.int16),
+            "quant": np.array([(1 << 16) // d_dc, (1 << 16) // d_ac], np.uint16).astype(np.int16),
+            "quant_shift": np.array([0, 0], np.int16),
+            "dequant": np.array([d_dc, d_ac], np.int16)}
+
+
+class FrameWorkload:
+    PAD = 16  # border of the reconstruction planes (restoration reads 3(+1) pixels beyond the picture)
+
+    def __init__(self, width=1920, height=1080, seed=20260923, n_refs=2):
+        assert width % 8 == 0 and height % 8 == 0
+        self.width, self.height, self.n_refs = width, height, n_refs
+        seq = synth_sequence(width, height, n_refs + 1, seed)
+        self.cur = seq[1]
+        self.refs = [seq[0], seq[2]][:n_refs]
+        self.me_shapes = dsp.me_plane_shapes(width, height)
+        # M8 / 1080p / crf 30 / distance 1 (module docstring)
+        self.me_params = [dict(hme_l0_sa_w=16, hme_l0_sa_h=4, hme_l1_sa_w=8, hme_l1_sa_h=3, hme_l2_sa_w=8, hme_l2_sa_h=3, me_sa_w=8,
+                               me_sa_h=3, hme_sub_sad=1, me_sub_sad=1, check_zero_centre=1) for _ in range(n_refs)]
+        self.plane_dims = [(width, height), (width // 2, height // 2), (width // 2, height // 2)]
+        # prediction = previous picture (zero-motion inter prediction); residual = cur - pred
+        self.pred = [self.refs[0][p] for p in range(3)]
+        self.residual = [self.cur[p].astype(np.int16) - self.pred[p].astype(np.int16) for p in range(3)]
+        self._build_tx_items()
+        self._build_cdef()
+        self._build_rest()
+
+    # -- planes as flat buffers ---------------------------------------------------------------------
+    def flat_offsets(self, itemsize_elems=1):
+        off, o = [], 0
+        for (w, h) in self.plane_dims:
+            off.append(o)
+            o += w * h
+        return off, o
+
+    def padded_shape(self, p):
+        w, h = self.plane_dims[p]
+        return h + 2 * self.PAD, (w + 2 * self.PAD + 15) & ~15
+
+    def padded_offsets(self):
+        off, o = [], 0
+        for p in range(3):
+            th, st = self.padded_shape(p)
+            off.append(o)
+            o += th * st
+        return off, o
+
+    # -- transform / quant / inverse work lists ---------------------------------------------------------
+    def _build_tx_items(self):
+        W, H = self.width, self.height
+        res_off, _ = self.flat_offsets()
+        rec_off, _ = self.padded_offsets()
+        pattern = [4] * 2 + [3] * 6 + [2] * 8 + [1] * 3 + [0] * 1
+        types_small = [0] * 7 + [3, 9, 10]
+        fwd, inv, qnt = [], [], []
+        coef_pos = 0
+        sizes_used = set()
+        k = 0
+        for sby in range(0, H, 64):
+            for sbx in range(0, W, 64):
+                sz_l = pattern[k % len(pattern)]
+                k += 1
+                if sby + 64 > H or sbx + 64 > W:
+                    sz_l = 1  # partial superblock: 8x8 luma / 4x4 chroma tiles the remainder exactly
+                for p in range(3):
+                    dec = 1 if p else 0
+                    sz = sz_l if p == 0 else max(sz_l - 1, 0)
+                    bw, bh = TX_W[sz], TX_H[sz]
+                    pw, ph = self.plane_dims[p]
+                    x0, y0 = sbx >> dec, sby >> dec
+                    x1, y1 = min(x0 + (64 >> dec), pw), min(y0 + (64 >> dec), ph)
+                    th, st = self.padded_shape(p)
+                    j = 0
+                    for y in range(y0, y1, bh):
+                        for x in range(x0, x1, bw):
+                            if y + bh > ph or x + bw > pw:
+                                continue
+                            ty = types_small[(k + j) % len(types_small)] if max(bw, bh) <= 16 else 0
+                            j += 1
+                            n = min(bw, 32) * min(bh, 32)
+                            fwd.append((res_off[p] + y * pw + x, coef_pos, pw, sz, ty, 1))
+                            rpos = rec_off[p] + (self.PAD + y) * st + self.PAD + x
+                            inv.append((coef_pos, rpos, rpos, st, st, sz, ty, 8, 0, 0))
+                            qnt.append((coef_pos, sz))
+                            coef_pos += n
+                            sizes_used.add(sz)
+        self.fwd_items = np.array(fwd, dtype=dsp.FWD_ITEM_DTYPE)
+        self.inv_items = np.array(inv, dtype=dsp.INV_ITEM_DTYPE)
+        self.n_coeffs = coef_pos
+        # scan / QM tables, one entry per transform size in use
+        scan_parts, qm_parts, scan_off, qm_off = [], [], {}, {}
+        so = qo = 0
+        r = np.random.default_rng(7)
+        for sz in sorted(sizes_used):
+            w, h = min(TX_W[sz], 32), min(TX_H[sz], 32)
+            sc = zigzag_scan(w, h)
+            scan_off[sz] = so
+            scan_parts.append(sc)
+            so += sc.size
+            qm = r.integers(26, 40, w * h).astype(np.uint8)
+            iqm = r.integers(26, 40, w * h).astype(np.uint8)
+            qm_off[sz] = (qo, qo + w * h)
+            qm_parts += [qm, iqm]
+            qo += 2 * w * h
+        self.scan_table = np.concatenate(scan_parts)
+        self.iscan_table = np.concatenate([np.argsort(sc).astype(np.int16) for sc in scan_parts])  # inverse permutations
+        self.qm_table = np.concatenate(qm_parts)
+        t = quant_tables(52, 61)
+        q = np.zeros(len(qnt), dtype=dsp.QUANT_ITEM_DTYPE)
+        cp = np.array([c for c, _ in qnt], np.uint64)
+        szs = np.array([s for _, s in qnt])
+        q["coeff_off"] = q["q_off"] = q["dq_off"] = cp
+        q["scan_off"] = [scan_off[s] for s in szs]
+        q["qm_off"] = [qm_off[s][0] for s in szs]
+        q["iqm_off"] = [qm_off[s][1] for s in szs]
+        q["n_coeffs"] = [min(TX_W[s], 32) * min(TX_H[s], 32) for s in szs]
+        for name in ("zbin", "round", "quant", "quant_shift", "dequant"):
+            q[name] = t[name]
+        q["mode"] = dsp.QUANT_FP_LBD
+        # log_scale of av1_get_tx_scale: 0 up to 256 coefficients... 1 for 512/1024, 2 for 64x64-class
+        q["log_scale"] = [2 if TX_W[s] * TX_H[s] > 1024 else (1 if TX_W[s] * TX_H[s] > 256 else 0) for s in szs]
+        self.quant_items = q
+        small = np.array([TX_W[s] * TX_H[s] <= 64 for s in self.fwd_items["tx_size"]])
+        order = np.concatenate([np.nonzero(small)[0], np.nonzero(~small)[0]])
+        self.fwd_items = self.fwd_items[order]
+        self.inv_items = self.inv_items[order]
+        self.n_small = int(small.sum())
+        self.n_large = int((~small).sum())
+
+        def max_size(mask):
+            ss = set(int(s) for s in self.fwd_items["tx_size"][mask])
+            return max(ss, key=lambda s: max(TX_H[s] * (TX_W[s] + 1), TX_W[s] * (TX_H[s] + 1))) if ss else 0
+        srt_small = np.arange(len(order)) < self.n_small
+        self.max_small, self.max_large = max_size(srt_small), max_size(~srt_small)
+
+    # -- CDEF ---------------------------------------------------------------------------------------------
+    def _build_cdef(self):
+        r = np.random.default_rng(11)
+        self.skip8x8 = (r.random(((self.height + 7) // 8, (self.width + 7) // 8)) < 0.10).astype(np.uint8)
+        self.cdef_str_y = np.array([0, 4, 9, 17, 20, 35], np.int32)
+        self.cdef_str_uv = np.array([0, 4, 8, 17, -1, 20], np.int32)
+        self.cdef_damping = 3 + (120 >> 6)
+        self.cdef_subsampling = 4  # CDEF search level of M8 (enc_mode_config.c:1066-1088)
+        nfb = ((self.width + 63) // 64) * ((self.height + 63) // 64)
+        self.cdef_fb_idx = (np.arange(nfb) % 4).astype(np.int8)
+        self.cdef_apply_y = np.array([4, 9, 17, 0], np.int32)
+        self.cdef_apply_uv = np.array([4, 8, 0, 0], np.int32)
+
+    # -- restoration ------------------------------------------------------------------------------------------
+    def _build_rest(self):
+        r = np.random.default_rng(13)
+        rec_off, _ = self.padded_offsets()
+        src_off, _ = self.flat_offsets()
+        stats, units = [], []
+        for p in range(3):
+            pw, ph = self.plane_dims[p]
+            th, st = self.padded_shape(p)
+            ru = 256 if p == 0 else 128
+            win = 7 if p == 0 else 5
+            for y0 in range(0, ph, ru):
+                for x0 in range(0, pw, ru):
+                    x1, y1 = min(x0 + ru, pw), min(y0 + ru, ph)
+                    stats.append((rec_off[p] + self.PAD * st + self.PAD, src_off[p], st, pw, x0, x1, y0, y1, win, 0))
+                    t0, t1, t2 = int(r.integers(-5, 11)), int(r.integers(-23, 9)), int(r.integers(-17, 47))
+                    taps = np.array([t0, t1, t2, -2 * (t0 + t1 + t2), t2, t1, t0, 0], np.int16)
+                    if p:
+                        taps[0] = taps[6] = 0  # chroma uses the 5-tap window
+                        taps[3] = -2 * (taps[1] + taps[2])
+                    for uy in range(y0, y1, 64):
+                        for ux in range(x0, x1, 64):
+                            uw, uh = min(64, x1 - ux), min(64, y1 - uy)
+                            pos = rec_off[p] + (self.PAD + uy) * st + self.PAD + ux
+                            units.append((pos, pos, st, st, uw, uh, 0, taps, taps))
+        self.stats_items = np.array(stats, dtype=dsp.STATS_ITEM_DTYPE)
+        self.wiener_units = np.array(units, dtype=dsp.WIENER_UNIT_DTYPE)
+
+    # -- algorithmic bytes per frame -----------------------------------------------------------
+    def algorithmic_bytes(self):
+        W, H, R = self.width, self.height, self.n_refs
+        n64 = ((W + 63) // 64) * ((H + 63) // 64)
+        n_samples = int(1.5 * W * H)
+        return {
+            "me": int((1 + R) * 1.3125 * W * H + n64 * R * 85 * 8),
+            "tx": int(n_samples * 24),          # (22 + 2*bpp) bytes per sample, bpp = 1
+            "cdef": int(2 * n_samples + n_samples + n64 * 2 * len(self.cdef_str_y) * 8),
+            "rest": int(2 * n_samples + len(self.stats_items) * (49 + 2401) * 8 + 2 * n_samples),
+        }

@@ -223,3 +223,31 @@ def test_port_selfguided_and_projection_match_reference(oracle, refc):
                 oracle.port.port_sgr_apply.restype = None
                 oracle.port.port_sgr_apply(rh.P(dgd.astype(np.uint16), off), w, h, stride, 3, rh.P(xqd), rh.P(da), w, bd)
                 assert np.array_equal(da, db.astype(np.uint16)), (bd, w, h, kind)
+
+
+# ---- picture-level reference drivers (oracle/ref_driver.c) ---------------------------------------
+def test_ref_driver_me_matches_numpy_driver_and_avx2_tier(oracle, refc):
+    from test_me_picture import _content
+    r = rng(130)
+    W, H = 320, 200
+    ME_PAD = (16, 32, 72)
+    shapes = []
+    for lvl in range(3):
+        w, h, pad = W >> (2 - lvl), H >> (2 - lvl), ME_PAD[lvl]
+        shapes.append((h + 2 * pad, (w + 2 * pad + 15) & ~15, pad, w, h))
+    cur = mh.build_pyramid_np(_content(r, W, H, (0, 0)), W, H, shapes)
+    refs = [mh.build_pyramid_np(_content(r, W, H, (5, -3)), W, H, shapes), mh.build_pyramid_np(_content(r, W, H, (-19, 9)), W, H, shapes)]
+    params = [dict(hme_l0_sa_w=16, hme_l0_sa_h=8, hme_l1_sa_w=8, hme_l1_sa_h=3, hme_l2_sa_w=8, hme_l2_sa_h=3, me_sa_w=8, me_sa_h=3,
+                   hme_sub_sad=0, me_sub_sad=0, check_zero_centre=1),
+              dict(hme_l0_sa_w=32, hme_l0_sa_h=12, hme_l1_sa_w=8, hme_l1_sa_h=3, hme_l2_sa_w=8, hme_l2_sa_h=3, me_sa_w=16, me_sa_h=5,
+                   hme_sub_sad=1, me_sub_sad=1, check_zero_centre=0)]
+    refc.ref_set_tier(0)
+    a = mh.ref_me_picture(refc, cur, refs, shapes, W, H, params)
+    b = mh.ref_me_picture_c(refc, cur, refs, shapes, W, H, params)
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+    if refc.ref_set_tier(1) == 1:  # the intrinsics-only AVX2 tier must agree with the C tier
+        c = mh.ref_me_picture_c(refc, cur, refs, shapes, W, H, params)
+        for x, y in zip(b, c):
+            assert np.array_equal(x, y)
+    refc.ref_set_tier(0)
