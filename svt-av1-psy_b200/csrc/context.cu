@@ -35,6 +35,9 @@ void require_ready() {
                 "library has no CPU fallback.\n");
         abort();
     }
+    // Encoder worker threads (and host frameworks sharing the process) may have another CUDA
+    // context / device current on this thread: always re-bind the library's device first.
+    B200_CUDA_CHECK(cudaSetDevice(g_ctx.device));
 }
 
 Lane* lane_acquire() {
