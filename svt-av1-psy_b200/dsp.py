@@ -422,3 +422,41 @@ def me_picture_desc(planes, width, height):
         p.width[lvl] = w
         p.height[lvl] = h
     return p
+lib.svt_b200_extend_plane_dev.argtypes = [vp, ct.c_int, ct.c_int, ct.c_int, ct.c_int, ct.c_int, vp]
+lib.svt_b200_extend_plane_dev.restype = ct.c_int
+
+
+def unbound_symbols():
+    """declared C-ABI symbols that have no ctypes signature yet (calling those would truncate pointers)"""
+    from . import declared_symbols
+    return [s for s in declared_symbols() if getattr(lib, s).argtypes is None and s not in
+            ("svt_b200_shutdown", "svt_b200_sm_count", "svt_b200_launch_count", "svt_b200_version")]
+
+for _i, _n in enumerate(TX_NAME):
+    _f = getattr(lib, "svt_b200_av1_fwd_txfm2d_" + _n)
+    _f.argtypes = [vp, vp, ct.c_uint32, ct.c_int, ct.c_uint8]
+    _f.restype = None
+    _g = getattr(lib, "svt_b200_av1_inv_txfm2d_add_" + _n)
+    _base = [vp, vp, ct.c_int32, vp, ct.c_int32, ct.c_int]
+    if _i in (0, 1, 2, 3, 4):
+        _g.argtypes = _base + [ct.c_int32]
+    elif _i in (5, 6, 13, 14):
+        _g.argtypes = _base + [ct.c_int, ct.c_int32]
+    else:
+        _g.argtypes = _base + [ct.c_int, ct.c_int32, ct.c_int32]
+    _g.restype = None
+
+
+def svt_av1_inv_txfm2d_add_named(coeff, pred, stride_r, stride_w, tx_type, tx_size, bd):
+    """the per-size named entry point (same argument list as the reference pointer of that size)"""
+    out = np.zeros(TX_H[tx_size] * stride_w, np.uint16)
+    g = getattr(lib, "svt_b200_av1_inv_txfm2d_add_" + TX_NAME[tx_size])
+    args = [_ptr(coeff), _ptr(pred), stride_r, _ptr(out), stride_w, tx_type]
+    if tx_size in (0, 1, 2, 3, 4):
+        args += [bd]
+    elif tx_size in (5, 6, 13, 14):
+        args += [tx_size, bd]
+    else:
+        args += [tx_size, TX_W[tx_size] * TX_H[tx_size], bd]
+    g(*args)
+    return out

@@ -52,3 +52,8 @@ def test_product_never_imports_oracle():
             if fn.endswith((".py", ".cu", ".cuh", ".h", ".cpp", ".c")):
                 txt = open(os.path.join(dp, fn), errors="ignore").read()
                 assert "import oracle" not in txt and "oracle/" not in txt.replace("oracle/ ", ""), (dp, fn)
+
+
+def test_every_declared_symbol_has_a_ctypes_signature():
+    import svt_av1_psy_b200 as pkg
+    assert pkg.dsp.unbound_symbols() == []
