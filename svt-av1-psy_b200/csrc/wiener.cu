@@ -103,17 +103,21 @@ __global__ void stats_avg_kernel(const PIX* __restrict__ dgd_base, const SvtB200
 }
 
 constexpr int kStatsWarps = 8;
+constexpr int kStatsMaxParts = 16;  // CTAs cooperating on one restoration unit
 
-// acc layout per item: [0, 49*49) = H (upper-triangle tiles only), [2401, 2450) = M
+// partial layout per (item, part): [0, 49*49) = H (upper-triangle tiles only), [2401, 2450) = M
 template <typename PIX>
 __global__ void __launch_bounds__(kStatsWarps * 32)
 stats_accum_kernel(const PIX* __restrict__ dgd_base, const PIX* __restrict__ src_base, const SvtB200StatsItem* __restrict__ items,
-                   const int* __restrict__ avg_in, int ctas_per_item, long long* __restrict__ acc, int flush_pixels) {
+                   const int* __restrict__ avg_in, int ctas_per_item, long long* __restrict__ partial, int flush_pixels) {
+    __shared__ unsigned long long s_acc[2450];
     const int it = blockIdx.x / ctas_per_item, part = blockIdx.x % ctas_per_item;
     const SvtB200StatsItem s = items[it];
     const int win = s.wiener_win, half = win >> 1, win2 = win * win;
     const int avg = avg_in[it];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < 2450; i += blockDim.x) s_acc[i] = 0;
+    __syncthreads();
     // lane -> (a, b) with a <= b < win
     int a = -1, b = -1;
     {
@@ -131,19 +135,24 @@ stats_accum_kernel(const PIX* __restrict__ dgd_base, const PIX* __restrict__ src
     for (int i = 0; i < 49; i++) hacc[i] = 0;
 #pragma unroll
     for (int i = 0; i < 7; i++) macc[i] = 0;
-    long long* A = acc + (size_t)it * 2450;
     const PIX* dgd = dgd_base + s.dgd_off;
     const PIX* src = src_base + s.src_off;
     const int gw = part * kStatsWarps + warp, GW = ctas_per_item * kStatsWarps;
     int pending = 0;
+    // int32 partial sums -> the CTA's int64 totals in shared memory (8 warps contend at most)
     auto flush = [&]() {
         if (live) {
-            for (int l1 = 0; l1 < win; l1++)
-                for (int l2 = 0; l2 < win; l2++)
-                    if (hacc[l1 * 7 + l2]) atomicAdd((unsigned long long*)&A[(a * win + l1) * win2 + (b * win + l2)], (unsigned long long)(long long)hacc[l1 * 7 + l2]);
-            if (diag)
-                for (int l1 = 0; l1 < win; l1++)
-                    if (macc[l1]) atomicAdd((unsigned long long*)&A[2401 + a * win + l1], (unsigned long long)(long long)macc[l1]);
+#pragma unroll
+            for (int l1 = 0; l1 < 7; l1++)
+#pragma unroll
+                for (int l2 = 0; l2 < 7; l2++)
+                    if (l1 < win && l2 < win && hacc[l1 * 7 + l2])
+                        atomicAdd(&s_acc[(a * win + l1) * win2 + (b * win + l2)], (unsigned long long)(long long)hacc[l1 * 7 + l2]);
+            if (diag) {
+#pragma unroll
+                for (int l1 = 0; l1 < 7; l1++)
+                    if (l1 < win && macc[l1]) atomicAdd(&s_acc[2401 + a * win + l1], (unsigned long long)(long long)macc[l1]);
+            }
         }
 #pragma unroll
         for (int i = 0; i < 49; i++) hacc[i] = 0;
@@ -162,6 +171,14 @@ stats_accum_kernel(const PIX* __restrict__ dgd_base, const PIX* __restrict__ src
                 ya[l] = (int)dgd[row + j + a - half] - avg;
                 yb[l] = (int)dgd[row + j + b - half] - avg;
             }
+        // software-pipelined: the loads of row i+1 are issued before the 49 MACs of row i
+        int na = 0, nb = 0, nx = 0;
+        if (live) {
+            const ptrdiff_t row = (ptrdiff_t)(s.v_start + half) * s.dgd_stride;
+            na = (int)dgd[row + j + a - half] - avg;
+            nb = (int)dgd[row + j + b - half] - avg;
+            if (diag) nx = (int)src[(ptrdiff_t)s.v_start * s.src_stride + j] - avg;
+        }
         for (int i = s.v_start; i < s.v_end; i++) {
             if (live) {
 #pragma unroll
@@ -170,17 +187,21 @@ stats_accum_kernel(const PIX* __restrict__ dgd_base, const PIX* __restrict__ src
                     yb[l] = yb[l + 1];
                 }
                 // after the shift the strip occupies slots 0..win-1; the newest row goes to slot win-1
-                const ptrdiff_t row = (ptrdiff_t)(i + half) * s.dgd_stride;
-                const int na = (int)dgd[row + j + a - half] - avg, nb = (int)dgd[row + j + b - half] - avg;
                 if (win == 7) { ya[6] = na; yb[6] = nb; }
                 else if (win == 5) { ya[4] = na; yb[4] = nb; }
                 else { ya[2] = na; yb[2] = nb; }
+                const int x = nx;
+                if (i + 1 < s.v_end) {
+                    const ptrdiff_t row = (ptrdiff_t)(i + 1 + half) * s.dgd_stride;
+                    na = (int)dgd[row + j + a - half] - avg;
+                    nb = (int)dgd[row + j + b - half] - avg;
+                    if (diag) nx = (int)src[(ptrdiff_t)(i + 1) * s.src_stride + j] - avg;
+                }
 #pragma unroll
                 for (int l1 = 0; l1 < 7; l1++)
 #pragma unroll
                     for (int l2 = 0; l2 < 7; l2++) hacc[l1 * 7 + l2] += ya[l1] * yb[l2];
                 if (diag) {
-                    const int x = (int)src[(ptrdiff_t)i * s.src_stride + j] - avg;
 #pragma unroll
                     for (int l1 = 0; l1 < 7; l1++) macc[l1] += ya[l1] * x;
                 }
@@ -189,13 +210,23 @@ stats_accum_kernel(const PIX* __restrict__ dgd_base, const PIX* __restrict__ src
         }
     }
     flush();
+    __syncthreads();
+    long long* P = partial + ((size_t)it * ctas_per_item + part) * 2450;
+    for (int i = threadIdx.x; i < 2450; i += blockDim.x) P[i] = (long long)s_acc[i];
 }
 
-__global__ void stats_finalize_kernel(const long long* __restrict__ acc, const SvtB200StatsItem* __restrict__ items, int n_items,
-                                      int divider, long long* __restrict__ M_out, long long* __restrict__ H_out) {
+__global__ void stats_finalize_kernel(const long long* __restrict__ partial, int parts, const SvtB200StatsItem* __restrict__ items,
+                                      int n_items, int divider, long long* __restrict__ M_out, long long* __restrict__ H_out) {
+    __shared__ long long A[2450];
     for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
         const int win = items[it].wiener_win, win2 = win * win;
-        const long long* A = acc + (size_t)it * 2450;
+        __syncthreads();
+        for (int i = threadIdx.x; i < 2450; i += blockDim.x) {
+            long long v = 0;
+            for (int p = 0; p < parts; p++) v += partial[((size_t)it * parts + p) * 2450 + i];
+            A[i] = v;
+        }
+        __syncthreads();
         long long* M = M_out + (size_t)it * 49;
         long long* H = H_out + (size_t)it * 2401;
         for (int k = threadIdx.x; k < win2; k += blockDim.x) M[k] = A[2401 + k] / divider;
@@ -225,13 +256,12 @@ static void launch_stats(const PIX* d_dgd, const PIX* d_src, const SvtB200StatsI
     const int divider = bd == 12 ? 16 : (bd == 10 ? 4 : 1);
     int cpi = (ctx().sm_count * 4) / (n > 0 ? n : 1);
     if (cpi < 1) cpi = 1;
-    if (cpi > 16) cpi = 16;
-    B200_CUDA_CHECK(cudaMemsetAsync(d_acc, 0, (size_t)n * 2450 * 8, st));
+    if (cpi > kStatsMaxParts) cpi = kStatsMaxParts;
     stats_avg_kernel<PIX><<<grid_for(n, 4), 256, 0, st>>>(d_dgd, d_items, n, d_avg);
     B200_LAUNCH_CHECK();
     stats_accum_kernel<PIX><<<n * cpi, kStatsWarps * 32, 0, st>>>(d_dgd, d_src, d_items, d_avg, cpi, d_acc, (int)fp);
     B200_LAUNCH_CHECK();
-    stats_finalize_kernel<<<grid_for(n, 4), 256, 0, st>>>(d_acc, d_items, n, divider, d_M, d_H);
+    stats_finalize_kernel<<<grid_for(n, 4), 256, 0, st>>>(d_acc, cpi, d_items, n, divider, d_M, d_H);
     B200_LAUNCH_CHECK();
 }
 
@@ -245,7 +275,7 @@ static void stats_t1(int wiener_win, const PIX* dgd, const PIX* src, int h_start
     LaneGuard l;
     size_t o_d = l->alloc((size_t)dw * dh * sizeof(PIX)), o_s = l->alloc((size_t)w * h * sizeof(PIX)), o_it = l->alloc(sizeof(SvtB200StatsItem));
     size_t in_end = l->used;
-    size_t o_M = l->alloc(49 * 8), o_H = l->alloc(2401 * 8), o_acc = l->alloc(2450 * 8), o_avg = l->alloc(16);
+    size_t o_M = l->alloc(49 * 8), o_H = l->alloc(2401 * 8), o_acc = l->alloc((size_t)kStatsMaxParts * 2450 * 8), o_avg = l->alloc(16);
     for (int r = 0; r < dh; r++)
         memcpy(l->h<PIX>(o_d) + (size_t)r * dw, dgd + (ptrdiff_t)(v_start - half + r) * dgd_stride + h_start - half, dw * sizeof(PIX));
     for (int r = 0; r < h; r++) memcpy(l->h<PIX>(o_s) + (size_t)r * w, src + (ptrdiff_t)(v_start + r) * src_stride + h_start, w * sizeof(PIX));
@@ -344,7 +374,7 @@ extern "C" int svt_b200_compute_stats_batch_dev(const void* d_dgd, const void* d
     if ((size_t)n_items > g_stats_cap) {
         if (g_stats_acc) { cudaFree(g_stats_acc); cudaFree(g_stats_avg); }
         g_stats_cap = (size_t)n_items * 2;
-        B200_CUDA_CHECK(cudaMalloc(&g_stats_acc, g_stats_cap * 2450 * 8));
+        B200_CUDA_CHECK(cudaMalloc(&g_stats_acc, g_stats_cap * kStatsMaxParts * 2450 * 8));
         B200_CUDA_CHECK(cudaMalloc(&g_stats_avg, g_stats_cap * 4));
     }
     if (bit_depth > 8)
