@@ -104,6 +104,7 @@ __global__ void stats_avg_kernel(const PIX* __restrict__ dgd_base, const SvtB200
 
 constexpr int kStatsWarps = 8;
 constexpr int kStatsMaxParts = 16;  // CTAs cooperating on one restoration unit
+constexpr int kStatsTileW = 32, kStatsTileH = 64, kStatsPitch = kStatsTileW + 6 + 2;
 
 // partial layout per (item, part): [0, 49*49) = H (upper-triangle tiles only), [2401, 2450) = M
 template <typename PIX>
@@ -111,6 +112,8 @@ __global__ void __launch_bounds__(kStatsWarps * 32)
 stats_accum_kernel(const PIX* __restrict__ dgd_base, const PIX* __restrict__ src_base, const SvtB200StatsItem* __restrict__ items,
                    const int* __restrict__ avg_in, int ctas_per_item, long long* __restrict__ partial, int flush_pixels) {
     __shared__ unsigned long long s_acc[2450];
+    __shared__ int16_t s_d[(kStatsTileH + 6) * kStatsPitch];
+    __shared__ int16_t s_x[kStatsTileH * kStatsTileW];
     const int it = blockIdx.x / ctas_per_item, part = blockIdx.x % ctas_per_item;
     const SvtB200StatsItem s = items[it];
     const int win = s.wiener_win, half = win >> 1, win2 = win * win;
@@ -137,7 +140,6 @@ stats_accum_kernel(const PIX* __restrict__ dgd_base, const PIX* __restrict__ src
     for (int i = 0; i < 7; i++) macc[i] = 0;
     const PIX* dgd = dgd_base + s.dgd_off;
     const PIX* src = src_base + s.src_off;
-    const int gw = part * kStatsWarps + warp, GW = ctas_per_item * kStatsWarps;
     int pending = 0;
     // int32 partial sums -> the CTA's int64 totals in shared memory (8 warps contend at most)
     auto flush = [&]() {
@@ -160,53 +162,60 @@ stats_accum_kernel(const PIX* __restrict__ dgd_base, const PIX* __restrict__ src
         for (int i = 0; i < 7; i++) macc[i] = 0;
         pending = 0;
     };
-    for (int j = s.h_start + gw; j < s.h_end; j += GW) {
-        int ya[7], yb[7];
-        // prime the sliding strips with rows v_start-half .. v_start+half-1
-#pragma unroll
-        for (int l = 0; l < 7; l++) ya[l] = yb[l] = 0;
-        if (live)
-            for (int l = 1; l < win; l++) {
-                const ptrdiff_t row = (ptrdiff_t)(s.v_start - half + l - 1) * s.dgd_stride;
-                ya[l] = (int)dgd[row + j + a - half] - avg;
-                yb[l] = (int)dgd[row + j + b - half] - avg;
+    // The CTA walks its share of the unit in 32-column x 64-row tiles staged in shared memory as
+    // (pixel - avg): the DRAM latency is paid once per tile by all 256 threads, the MAC loop reads
+    // shared memory only.  Warp w owns columns 4w..4w+3 of the tile, one after the other.
+    const int W = s.h_end - s.h_start;
+    for (int g = part; g * kStatsTileW < W; g += ctas_per_item) {
+        const int c0 = s.h_start + g * kStatsTileW, ncols = min(kStatsTileW, s.h_end - c0);
+        for (int r0 = s.v_start; r0 < s.v_end; r0 += kStatsTileH) {
+            const int nrows = min(kStatsTileH, s.v_end - r0);
+            __syncthreads();
+            for (int t = threadIdx.x; t < (nrows + 2 * half) * (ncols + 2 * half); t += blockDim.x) {
+                const int rr = t / (ncols + 2 * half), cc = t - rr * (ncols + 2 * half);
+                s_d[rr * kStatsPitch + cc] = (int16_t)((int)dgd[(ptrdiff_t)(r0 - half + rr) * s.dgd_stride + c0 - half + cc] - avg);
             }
-        // software-pipelined: the loads of row i+1 are issued before the 49 MACs of row i
-        int na = 0, nb = 0, nx = 0;
-        if (live) {
-            const ptrdiff_t row = (ptrdiff_t)(s.v_start + half) * s.dgd_stride;
-            na = (int)dgd[row + j + a - half] - avg;
-            nb = (int)dgd[row + j + b - half] - avg;
-            if (diag) nx = (int)src[(ptrdiff_t)s.v_start * s.src_stride + j] - avg;
-        }
-        for (int i = s.v_start; i < s.v_end; i++) {
-            if (live) {
+            for (int t = threadIdx.x; t < nrows * ncols; t += blockDim.x) {
+                const int rr = t / ncols, cc = t - rr * ncols;
+                s_x[rr * kStatsTileW + cc] = (int16_t)((int)src[(ptrdiff_t)(r0 + rr) * s.src_stride + c0 + cc] - avg);
+            }
+            __syncthreads();
+            for (int k = 0; k < kStatsTileW / kStatsWarps; k++) {
+                const int cw = warp * (kStatsTileW / kStatsWarps) + k;
+                if (cw >= ncols) break;  // warp-uniform
+                int ya[7], yb[7];
 #pragma unroll
-                for (int l = 0; l < 6; l++) {
-                    ya[l] = ya[l + 1];
-                    yb[l] = yb[l + 1];
-                }
-                // after the shift the strip occupies slots 0..win-1; the newest row goes to slot win-1
-                if (win == 7) { ya[6] = na; yb[6] = nb; }
-                else if (win == 5) { ya[4] = na; yb[4] = nb; }
-                else { ya[2] = na; yb[2] = nb; }
-                const int x = nx;
-                if (i + 1 < s.v_end) {
-                    const ptrdiff_t row = (ptrdiff_t)(i + 1 + half) * s.dgd_stride;
-                    na = (int)dgd[row + j + a - half] - avg;
-                    nb = (int)dgd[row + j + b - half] - avg;
-                    if (diag) nx = (int)src[(ptrdiff_t)(i + 1) * s.src_stride + j] - avg;
-                }
+                for (int l = 0; l < 7; l++) ya[l] = yb[l] = 0;
+                if (live)
+                    for (int l = 1; l < win; l++) {
+                        ya[l] = s_d[(l - 1) * kStatsPitch + cw + a];
+                        yb[l] = s_d[(l - 1) * kStatsPitch + cw + b];
+                    }
+                for (int i = 0; i < nrows; i++) {
+                    if (live) {
 #pragma unroll
-                for (int l1 = 0; l1 < 7; l1++)
+                        for (int l = 0; l < 6; l++) {
+                            ya[l] = ya[l + 1];
+                            yb[l] = yb[l + 1];
+                        }
+                        // after the shift the strip occupies slots 0..win-1; the newest row goes to slot win-1
+                        const int na = s_d[(i + win - 1) * kStatsPitch + cw + a], nb = s_d[(i + win - 1) * kStatsPitch + cw + b];
+                        if (win == 7) { ya[6] = na; yb[6] = nb; }
+                        else if (win == 5) { ya[4] = na; yb[4] = nb; }
+                        else { ya[2] = na; yb[2] = nb; }
 #pragma unroll
-                    for (int l2 = 0; l2 < 7; l2++) hacc[l1 * 7 + l2] += ya[l1] * yb[l2];
-                if (diag) {
+                        for (int l1 = 0; l1 < 7; l1++)
 #pragma unroll
-                    for (int l1 = 0; l1 < 7; l1++) macc[l1] += ya[l1] * x;
+                            for (int l2 = 0; l2 < 7; l2++) hacc[l1 * 7 + l2] += ya[l1] * yb[l2];
+                        if (diag) {
+                            const int x = s_x[i * kStatsTileW + cw];
+#pragma unroll
+                            for (int l1 = 0; l1 < 7; l1++) macc[l1] += ya[l1] * x;
+                        }
+                    }
+                    if (++pending >= flush_pixels) flush();
                 }
             }
-            if (++pending >= flush_pixels) flush();
         }
     }
     flush();
