@@ -107,6 +107,11 @@ constexpr int kStatsMaxParts = 16;  // CTAs cooperating on one restoration unit
 constexpr int kStatsTileW = 32, kStatsTileH = 64, kStatsPitch = kStatsTileW + 6 + 2;
 
 // partial layout per (item, part): [0, 49*49) = H (upper-triangle tiles only), [2401, 2450) = M
+//
+// Data path is always the 7x7 geometry: a 5x5 (3x3) window is the centre of the 7x7 one, so the
+// lanes of a narrower window simply own the centred column pairs and only the centred 5 (3) strip
+// rows are flushed.  The row loop is unrolled by 7 so that the sliding strips live in a register
+// ring with compile-time indices -- the loop body is branch-free straight-line IMADs.
 template <typename PIX>
 __global__ void __launch_bounds__(kStatsWarps * 32)
 stats_accum_kernel(const PIX* __restrict__ dgd_base, const PIX* __restrict__ src_base, const SvtB200StatsItem* __restrict__ items,
@@ -116,23 +121,24 @@ stats_accum_kernel(const PIX* __restrict__ dgd_base, const PIX* __restrict__ src
     __shared__ int16_t s_x[kStatsTileH * kStatsTileW];
     const int it = blockIdx.x / ctas_per_item, part = blockIdx.x % ctas_per_item;
     const SvtB200StatsItem s = items[it];
-    const int win = s.wiener_win, half = win >> 1, win2 = win * win;
+    const int win = s.wiener_win, off = (7 - win) >> 1, win2 = win * win;  // off: first physical row/column of the window
     const int avg = avg_in[it];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int i = threadIdx.x; i < 2450; i += blockDim.x) s_acc[i] = 0;
     __syncthreads();
-    // lane -> (a, b) with a <= b < win
-    int a = -1, b = -1;
+    // lane -> logical column pair (a, b), a <= b < win; idle lanes shadow pair (0,0) and never flush
+    int a = 0, b = 0;
+    bool live = false;
     {
         int t = lane;
-        for (int aa = 0; aa < win && a < 0; aa++) {
+        for (int aa = 0; aa < win && !live; aa++) {
             const int cnt = win - aa;
-            if (t < cnt) { a = aa; b = aa + t; }
+            if (t < cnt) { a = aa; b = aa + t; live = true; }
             else t -= cnt;
         }
     }
-    const bool live = a >= 0;
     const bool diag = live && a == b;
+    const int pa = a + off, pb = b + off;  // physical columns inside the 7-wide strip
     int hacc[49], macc[7];
 #pragma unroll
     for (int i = 0; i < 49; i++) hacc[i] = 0;
@@ -143,37 +149,33 @@ stats_accum_kernel(const PIX* __restrict__ dgd_base, const PIX* __restrict__ src
     int pending = 0;
     // int32 partial sums -> the CTA's int64 totals in shared memory (8 warps contend at most)
     auto flush = [&]() {
-        if (live) {
 #pragma unroll
-            for (int l1 = 0; l1 < 7; l1++)
+        for (int l1 = 0; l1 < 7; l1++)
 #pragma unroll
-                for (int l2 = 0; l2 < 7; l2++)
-                    if (l1 < win && l2 < win && hacc[l1 * 7 + l2])
-                        atomicAdd(&s_acc[(a * win + l1) * win2 + (b * win + l2)], (unsigned long long)(long long)hacc[l1 * 7 + l2]);
-            if (diag) {
-#pragma unroll
-                for (int l1 = 0; l1 < 7; l1++)
-                    if (l1 < win && macc[l1]) atomicAdd(&s_acc[2401 + a * win + l1], (unsigned long long)(long long)macc[l1]);
+            for (int l2 = 0; l2 < 7; l2++) {
+                const int q1 = l1 - off, q2 = l2 - off;  // logical strip rows
+                if (live && q1 >= 0 && q1 < win && q2 >= 0 && q2 < win && hacc[l1 * 7 + l2])
+                    atomicAdd(&s_acc[(a * win + q1) * win2 + (b * win + q2)], (unsigned long long)(long long)hacc[l1 * 7 + l2]);
+                hacc[l1 * 7 + l2] = 0;
             }
+#pragma unroll
+        for (int l1 = 0; l1 < 7; l1++) {
+            const int q1 = l1 - off;
+            if (diag && q1 >= 0 && q1 < win && macc[l1]) atomicAdd(&s_acc[2401 + a * win + q1], (unsigned long long)(long long)macc[l1]);
+            macc[l1] = 0;
         }
-#pragma unroll
-        for (int i = 0; i < 49; i++) hacc[i] = 0;
-#pragma unroll
-        for (int i = 0; i < 7; i++) macc[i] = 0;
         pending = 0;
     };
-    // The CTA walks its share of the unit in 32-column x 64-row tiles staged in shared memory as
-    // (pixel - avg): the DRAM latency is paid once per tile by all 256 threads, the MAC loop reads
-    // shared memory only.  Warp w owns columns 4w..4w+3 of the tile, one after the other.
     const int W = s.h_end - s.h_start;
     for (int g = part; g * kStatsTileW < W; g += ctas_per_item) {
         const int c0 = s.h_start + g * kStatsTileW, ncols = min(kStatsTileW, s.h_end - c0);
         for (int r0 = s.v_start; r0 < s.v_end; r0 += kStatsTileH) {
             const int nrows = min(kStatsTileH, s.v_end - r0);
             __syncthreads();
-            for (int t = threadIdx.x; t < (nrows + 2 * half) * (ncols + 2 * half); t += blockDim.x) {
-                const int rr = t / (ncols + 2 * half), cc = t - rr * (ncols + 2 * half);
-                s_d[rr * kStatsPitch + cc] = (int16_t)((int)dgd[(ptrdiff_t)(r0 - half + rr) * s.dgd_stride + c0 - half + cc] - avg);
+            // rows r0-3 .. r0+nrows+2, columns c0-3 .. c0+ncols+2 as (pixel - avg)
+            for (int t = threadIdx.x; t < (nrows + 6) * (ncols + 6); t += blockDim.x) {
+                const int rr = t / (ncols + 6), cc = t - rr * (ncols + 6);
+                s_d[rr * kStatsPitch + cc] = (int16_t)((int)dgd[(ptrdiff_t)(r0 - 3 + rr) * s.dgd_stride + c0 - 3 + cc] - avg);
             }
             for (int t = threadIdx.x; t < nrows * ncols; t += blockDim.x) {
                 const int rr = t / ncols, cc = t - rr * ncols;
@@ -183,37 +185,60 @@ stats_accum_kernel(const PIX* __restrict__ dgd_base, const PIX* __restrict__ src
             for (int k = 0; k < kStatsTileW / kStatsWarps; k++) {
                 const int cw = warp * (kStatsTileW / kStatsWarps) + k;
                 if (cw >= ncols) break;  // warp-uniform
-                int ya[7], yb[7];
+                if (pending + nrows > flush_pixels) flush();
+                pending += nrows;
+                const int16_t* da = s_d + cw + pa;
+                const int16_t* db = s_d + cw + pb;
+                const int16_t* dx = s_x + cw;
+                // register ring: slot (r mod 7) holds tile row r
+                int ra[7], rb[7];
 #pragma unroll
-                for (int l = 0; l < 7; l++) ya[l] = yb[l] = 0;
-                if (live)
-                    for (int l = 1; l < win; l++) {
-                        ya[l] = s_d[(l - 1) * kStatsPitch + cw + a];
-                        yb[l] = s_d[(l - 1) * kStatsPitch + cw + b];
+                for (int l = 0; l < 6; l++) {
+                    ra[l] = da[l * kStatsPitch];
+                    rb[l] = db[l * kStatsPitch];
+                }
+                ra[6] = rb[6] = 0;
+                int i0 = 0;
+                for (; i0 + 7 <= nrows; i0 += 7) {
+#pragma unroll
+                    for (int t = 0; t < 7; t++) {
+                        // pixel row i0+t uses tile rows i0+t .. i0+t+6; the new one goes to slot (t+6) % 7
+                        ra[(t + 6) % 7] = da[(i0 + t + 6) * kStatsPitch];
+                        rb[(t + 6) % 7] = db[(i0 + t + 6) * kStatsPitch];
+                        const int x = dx[(i0 + t) * kStatsTileW];
+#pragma unroll
+                        for (int l1 = 0; l1 < 7; l1++) {
+#pragma unroll
+                            for (int l2 = 0; l2 < 7; l2++) hacc[l1 * 7 + l2] += ra[(t + l1) % 7] * rb[(t + l2) % 7];
+                            macc[l1] += ra[(t + l1) % 7] * x;
+                        }
                     }
-                for (int i = 0; i < nrows; i++) {
-                    if (live) {
+                }
+                // tail (< 7 rows): same arithmetic with a shifting strip
+                if (i0 < nrows) {
+                    int ya[7], yb[7];
+#pragma unroll
+                    for (int l = 0; l < 6; l++) {
+                        ya[l + 1] = da[(i0 + l) * kStatsPitch];
+                        yb[l + 1] = db[(i0 + l) * kStatsPitch];
+                    }
+                    ya[0] = yb[0] = 0;
+                    for (int i = i0; i < nrows; i++) {
 #pragma unroll
                         for (int l = 0; l < 6; l++) {
                             ya[l] = ya[l + 1];
                             yb[l] = yb[l + 1];
                         }
-                        // after the shift the strip occupies slots 0..win-1; the newest row goes to slot win-1
-                        const int na = s_d[(i + win - 1) * kStatsPitch + cw + a], nb = s_d[(i + win - 1) * kStatsPitch + cw + b];
-                        if (win == 7) { ya[6] = na; yb[6] = nb; }
-                        else if (win == 5) { ya[4] = na; yb[4] = nb; }
-                        else { ya[2] = na; yb[2] = nb; }
+                        ya[6] = da[(i + 6) * kStatsPitch];
+                        yb[6] = db[(i + 6) * kStatsPitch];
+                        const int x = dx[i * kStatsTileW];
 #pragma unroll
-                        for (int l1 = 0; l1 < 7; l1++)
+                        for (int l1 = 0; l1 < 7; l1++) {
 #pragma unroll
                             for (int l2 = 0; l2 < 7; l2++) hacc[l1 * 7 + l2] += ya[l1] * yb[l2];
-                        if (diag) {
-                            const int x = s_x[i * kStatsTileW + cw];
-#pragma unroll
-                            for (int l1 = 0; l1 < 7; l1++) macc[l1] += ya[l1] * x;
+                            macc[l1] += ya[l1] * x;
                         }
                     }
-                    if (++pending >= flush_pixels) flush();
                 }
             }
         }
