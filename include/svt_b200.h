@@ -185,7 +185,9 @@ typedef struct SvtB200InvTxfmItem {
     uint32_t reserved2;
 } SvtB200InvTxfmItem;
 
-/* items must be ordered: the n_small items whose W*H <= 64 first, then the n_large others. */
+/* items must be ordered: the n_small items whose W*H <= SVT_B200_TXFM_SMALL_MAX_COEFFS first (they are
+ * processed one warp per block), then the n_large others (one CTA per block). */
+#define SVT_B200_TXFM_SMALL_MAX_COEFFS 256
 SVT_B200_API int svt_b200_fwd_txfm_batch_dev(const int16_t* d_residual, int32_t* d_coeff,
                                              const SvtB200FwdTxfmItem* d_items, int n_small, int n_large,
                                              int max_small_tx_size, int max_large_tx_size, void* stream);

@@ -5,7 +5,7 @@
 // 16 transform types, 8/10/12-bit.  The 2-D configuration table (flips, per-pass kernel, cos_bit,
 // shifts) is dumped from the reference (txfm_cfg.inc); the 1-D networks are txfm_graphs.inc.
 //
-// B200 mapping: one thread TEAM per transform block -- a warp for blocks of <= 64 coefficients
+// B200 mapping: one thread TEAM per transform block -- a warp for blocks of <= 256 coefficients
 // (8 blocks per CTA), the whole 256-thread CTA above.  The block lives in two ping-pong shared-memory
 // planes in element-major order with an odd pitch, so the column pass, the transposing hand-over and
 // the row pass are all bank-conflict free; residual loads / coefficient stores are coalesced rows.
@@ -79,13 +79,14 @@ fwd_txfm_kernel(const int16_t* __restrict__ src_base, int32_t* __restrict__ dst_
     for (int it = blockIdx.x * TEAMS + team; it < n_items; it += gridDim.x * TEAMS) {
         const SvtB200FwdTxfmItem item = items[it];
         const int   sz = item.tx_size, W = tx_w(sz), H = tx_h(sz);
+        const int   lgW = 31 - __clz(W);
         const TxCfg cfg = c_txcfg[sz][item.tx_type];
         const int16_t* src = src_base + item.src_off;
         int32_t*       dst = dst_base + item.dst_off;
         const int P1 = W + 1, P2 = H + 1;
         // load, optional up/down flip, pre-shift (transforms.c:2286-2294)
         for (int idx = tid; idx < W * H; idx += TEAM) {
-            const int r = idx / W, c = idx - r * W;
+            const int r = idx >> lgW, c = idx & (W - 1);
             const int rr = cfg.f_ud ? (H - 1 - r) : r;
             A[r * P1 + c] = round_shift_arr((int32_t)src[(size_t)rr * item.src_stride + c], -cfg.f_s0);
         }
@@ -94,7 +95,7 @@ fwd_txfm_kernel(const int16_t* __restrict__ src_base, int32_t* __restrict__ dst_
         int32_t* O = (R == A) ? B : A;
         // round-shift, optional left/right flip, hand over transposed (element = column)
         for (int idx = tid; idx < W * H; idx += TEAM) {
-            const int r = idx / W, c = idx - r * W;
+            const int r = idx >> lgW, c = idx & (W - 1);
             const int cc = cfg.f_lr ? (W - 1 - c) : c;
             O[cc * P2 + r] = round_shift_arr(R[r * P1 + c], -cfg.f_s1);
         }
@@ -102,7 +103,7 @@ fwd_txfm_kernel(const int16_t* __restrict__ src_base, int32_t* __restrict__ dst_
         int32_t* R2 = txfm_pass_1d<TEAM>(cfg.f_tr, 0, O, R, W, H, P2, cfg.f_cbr, 0, tid);
         const int rect = rect_log_ratio(W, H);
         for (int idx = tid; idx < W * H; idx += TEAM) {
-            const int r = idx / W, c = idx - r * W;
+            const int r = idx >> lgW, c = idx & (W - 1);
             int32_t   v = round_shift_arr(R2[c * P2 + r], -cfg.f_s2);
             if (rect == 1 || rect == -1) v = round_shift64((long long)v * kNewSqrt2, 12);
             if (item.reserved & 1) {  // packed output: keep the top-left min(W,32) x min(H,32) (svt_handle_transform64x64 repack, transforms.c:2374)
@@ -131,6 +132,7 @@ inv_txfm_kernel(const int32_t* __restrict__ coef_base, const PIX* __restrict__ p
     for (int it = blockIdx.x * TEAMS + team; it < n_items; it += gridDim.x * TEAMS) {
         const SvtB200InvTxfmItem item = items[it];
         const int   sz = item.tx_size, W = tx_w(sz), H = tx_h(sz), bd = item.bd;
+        const int   lgW = 31 - __clz(W);
         const TxCfg cfg = c_txcfg[sz][item.tx_type];
         const int32_t* in = coef_base + item.coef_off;
         const int Wp = W > 32 ? 32 : W, Hp = H > 32 ? 32 : H;  // 64-point dims arrive packed (inv_transforms.c:2567-2686)
@@ -142,7 +144,7 @@ inv_txfm_kernel(const int32_t* __restrict__ coef_base, const PIX* __restrict__ p
         const int opt_col = bd == 12 ? 18 : 16;
         // rows first: element = column, vector = row
         for (int idx = tid; idx < W * H; idx += TEAM) {
-            const int r = idx / W, c = idx - r * W;
+            const int r = idx >> lgW, c = idx & (W - 1);
             int32_t   v = (r < Hp && c < Wp) ? in[r * Wp + c] : 0;
             if (rect == 1 || rect == -1) v = round_shift64((long long)v * kNewInvSqrt2, 12);
             A[c * P1 + r] = clamp_bits(v, row_clamp);
@@ -151,7 +153,7 @@ inv_txfm_kernel(const int32_t* __restrict__ coef_base, const PIX* __restrict__ p
         int32_t* R = txfm_pass_1d<TEAM>(cfg.i_tr, 1, A, B, W, H, P1, cfg.i_cbr, opt_row, tid);
         int32_t* O = (R == A) ? B : A;
         for (int idx = tid; idx < W * H; idx += TEAM) {
-            const int r = idx / W, c = idx - r * W;
+            const int r = idx >> lgW, c = idx & (W - 1);
             const int cs = cfg.i_lr ? (W - 1 - c) : c;
             O[r * P2 + c] = clamp_bits(round_shift_arr(R[cs * P1 + r], -cfg.i_s0), col_clamp);
         }
@@ -162,7 +164,7 @@ inv_txfm_kernel(const int32_t* __restrict__ coef_base, const PIX* __restrict__ p
         const long long int_max = (1ll << (7 + bd)) - 1 + (914ll << (bd - 7));  // check_range, inv_transforms.c:2401
         const int       pix_max = (1 << bd) - 1;
         for (int idx = tid; idx < W * H; idx += TEAM) {
-            const int r = idx / W, c = idx - r * W;
+            const int r = idx >> lgW, c = idx & (W - 1);
             const int rs = cfg.i_ud ? (H - 1 - r) : r;
             long long t  = (long long)round_shift_arr(R2[rs * P2 + c], -cfg.i_s1);
             t            = t < -int_max - 1 ? -int_max - 1 : (t > int_max ? int_max : t);
@@ -216,7 +218,7 @@ void launch_inv_txfm(const int32_t* d_coef, const PIX* d_pred, PIX* d_recon, con
     B200_LAUNCH_CHECK();
 }
 
-static inline bool is_small(int sz) { return tx_w(sz) * tx_h(sz) <= 64; }
+static inline bool is_small(int sz) { return tx_w(sz) * tx_h(sz) <= SVT_B200_TXFM_SMALL_MAX_COEFFS; }
 
 }  // namespace b200
 

@@ -95,13 +95,14 @@ __device__ int32_t* txfm_pass_1d(int type, int inverse, int32_t* x, int32_t* y, 
                                  int clampb, int tid) {
     const GraphDesc g    = c_graph[inverse][type];
     const int       tot  = N * V;
+    const int       lgV  = 31 - __clz(V);  // V is a power of two (4..64)
     if (g.stages > 0) {
         const int32_t* cosv = c_cospi[cos_bit - 10];
         const long long rnd = 1ll << (cos_bit - 1);
         for (int s = 0; s < g.stages; s++) {
             const uint32_t* nodes = g_txfm_nodes + g.off + s * N;
             for (int idx = tid; idx < tot; idx += TEAM) {
-                const int      i  = idx / V, v = idx - i * V;
+                const int      i  = idx >> lgV, v = idx & (V - 1);
                 const uint32_t nd = __ldg(nodes + i);
                 const int      a = nd & 63, b = (nd >> 6) & 63;
                 const int      wa = (int)(int8_t)(nd >> 12), wb = (int)(int8_t)(nd >> 20);
@@ -135,7 +136,7 @@ __device__ int32_t* txfm_pass_1d(int type, int inverse, int32_t* x, int32_t* y, 
         const int32_t* sp = c_sinpi[cos_bit - 10];
         const uint32_t s1 = sp[1], s2 = sp[2], s3 = sp[3], s4 = sp[4];
         for (int idx = tid; idx < tot; idx += TEAM) {
-            const int      i = idx / V, v = idx - i * V;
+            const int      i = idx >> lgV, v = idx & (V - 1);
             const uint32_t x0 = x[v], x1 = x[P + v], x2 = x[2 * P + v], x3 = x[3 * P + v];
             uint32_t       o;
             if (!inverse) {
@@ -160,7 +161,7 @@ __device__ int32_t* txfm_pass_1d(int type, int inverse, int32_t* x, int32_t* y, 
     }
     // identity kernels (transforms.c:2205-2236, inv_transforms.c:2331-2362)
     for (int idx = tid; idx < tot; idx += TEAM) {
-        const int     i = idx / V, v = idx - i * V;
+        const int     i = idx >> lgV, v = idx & (V - 1);
         const int32_t xv = x[i * P + v];
         int32_t       r;
         switch (type) {

@@ -126,6 +126,7 @@ def sad_search_batch_host(src_plane, ref_plane, items):
 TX_W = [4, 8, 16, 32, 64, 4, 8, 8, 16, 16, 32, 32, 64, 4, 16, 8, 32, 16, 64]
 TX_H = [4, 8, 16, 32, 64, 8, 4, 16, 8, 32, 16, 64, 32, 16, 4, 32, 8, 64, 16]
 TX_NAME = ["%dx%d" % (w, h) for w, h in zip(TX_W, TX_H)]
+TXFM_SMALL_MAX_COEFFS = 256  # SVT_B200_TXFM_SMALL_MAX_COEFFS
 
 FWD_ITEM_DTYPE = np.dtype([("src_off", "<u8"), ("dst_off", "<u8"), ("src_stride", "<u4"), ("tx_size", "u1"),
                            ("tx_type", "u1"), ("reserved", "<u2")])

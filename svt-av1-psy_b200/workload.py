@@ -168,7 +168,7 @@ class FrameWorkload:
         # log_scale of av1_get_tx_scale: 0 up to 256 coefficients... 1 for 512/1024, 2 for 64x64-class
         q["log_scale"] = [2 if TX_W[s] * TX_H[s] > 1024 else (1 if TX_W[s] * TX_H[s] > 256 else 0) for s in szs]
         self.quant_items = q
-        small = np.array([TX_W[s] * TX_H[s] <= 64 for s in self.fwd_items["tx_size"]])
+        small = np.array([TX_W[s] * TX_H[s] <= dsp.TXFM_SMALL_MAX_COEFFS for s in self.fwd_items["tx_size"]])
         order = np.concatenate([np.nonzero(small)[0], np.nonzero(~small)[0]])
         self.fwd_items = self.fwd_items[order]
         self.inv_items = self.inv_items[order]
