@@ -15,6 +15,8 @@
 // feed 49 multiply-accumulates per pixel.  The 7 diagonal lanes also accumulate M.  Products are
 // accumulated in int32 for as many pixels as cannot overflow, then flushed to the int64 totals with
 // 64-bit atomics; a finalize kernel mirrors the triangle and applies the bit-depth divider.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 #include "../../include/svt_b200.h"
 
@@ -79,27 +81,31 @@ wiener_convolve_kernel(const PIX* __restrict__ src_base, PIX* __restrict__ dst_b
 // ---------------------------------------------------------------------------------------------
 // K11
 // ---------------------------------------------------------------------------------------------
+// Pixel total of every item's region (find_average, restoration_pick.c, divides it by w*h): kSumParts
+// CTAs per item, one warp per row, totals combined with one 64-bit atomic per warp.
+constexpr int kSumParts = 16;
 template <typename PIX>
-__global__ void stats_avg_kernel(const PIX* __restrict__ dgd_base, const SvtB200StatsItem* __restrict__ items, int n_items,
-                                 int* __restrict__ avg_out) {
-    __shared__ unsigned long long tot;
-    for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
-        const SvtB200StatsItem s = items[it];
-        if (threadIdx.x == 0) tot = 0;
-        __syncthreads();
-        const int w = s.h_end - s.h_start, h = s.v_end - s.v_start;
-        unsigned long long acc = 0;
-        for (int i = threadIdx.x; i < w * h; i += blockDim.x) {
-            const int r = i / w, c = i - r * w;
-            acc += dgd_base[s.dgd_off + (ptrdiff_t)(s.v_start + r) * s.dgd_stride + s.h_start + c];
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-        if ((threadIdx.x & 31) == 0) atomicAdd(&tot, acc);
-        __syncthreads();
-        if (threadIdx.x == 0) avg_out[it] = (int)(tot / (unsigned long long)(w * h));  // find_average (restoration_pick.c)
-        __syncthreads();
+__global__ void __launch_bounds__(256)
+stats_sum_kernel(const PIX* __restrict__ dgd_base, const SvtB200StatsItem* __restrict__ items, unsigned long long* __restrict__ tot_out) {
+    const int it = blockIdx.x / kSumParts, part = blockIdx.x % kSumParts;
+    const SvtB200StatsItem s = items[it];
+    const int w = s.h_end - s.h_start, h = s.v_end - s.v_start;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    unsigned int acc = 0;  // <= (rows per warp) * (cols per lane) * 4095: far below 2^32 for any restoration unit
+    unsigned long long wide = 0;
+    for (int r = part * 8 + warp; r < h; r += kSumParts * 8) {
+        const PIX* row = dgd_base + s.dgd_off + (ptrdiff_t)(s.v_start + r) * s.dgd_stride + s.h_start;
+        for (int c = lane; c < w; c += 32) acc += row[c];
+        if (acc > 0xf0000000u) { wide += acc; acc = 0; }
     }
+    wide += acc;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) wide += __shfl_xor_sync(0xffffffffu, wide, o);
+    if (lane == 0 && wide) atomicAdd(&tot_out[it], wide);
+}
+
+__device__ __forceinline__ int stats_average(const unsigned long long* tot, int it, const SvtB200StatsItem& s) {
+    return (int)(tot[it] / (unsigned long long)((s.h_end - s.h_start) * (s.v_end - s.v_start)));
 }
 
 constexpr int kStatsWarps = 8;
@@ -115,14 +121,14 @@ constexpr int kStatsTileW = 32, kStatsTileH = 64, kStatsPitch = kStatsTileW + 6 
 template <typename PIX>
 __global__ void __launch_bounds__(kStatsWarps * 32)
 stats_accum_kernel(const PIX* __restrict__ dgd_base, const PIX* __restrict__ src_base, const SvtB200StatsItem* __restrict__ items,
-                   const int* __restrict__ avg_in, int ctas_per_item, long long* __restrict__ partial, int flush_pixels) {
+                   const unsigned long long* __restrict__ tot_in, int ctas_per_item, long long* __restrict__ partial, int flush_pixels) {
     __shared__ unsigned long long s_acc[2450];
     __shared__ int16_t s_d[(kStatsTileH + 6) * kStatsPitch];
     __shared__ int16_t s_x[kStatsTileH * kStatsTileW];
     const int it = blockIdx.x / ctas_per_item, part = blockIdx.x % ctas_per_item;
     const SvtB200StatsItem s = items[it];
     const int win = s.wiener_win, off = (7 - win) >> 1, win2 = win * win;  // off: first physical row/column of the window
-    const int avg = avg_in[it];
+    const int avg = stats_average(tot_in, it, s);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int i = threadIdx.x; i < 2450; i += blockDim.x) s_acc[i] = 0;
     __syncthreads();
@@ -249,8 +255,174 @@ stats_accum_kernel(const PIX* __restrict__ dgd_base, const PIX* __restrict__ src
     for (int i = threadIdx.x; i < 2450; i += blockDim.x) P[i] = (long long)s_acc[i];
 }
 
+// ---------------------------------------------------------------------------------------------
+// K11, 8-bit pixels: the contraction on the tensor cores.
+//
+// H = Y^T Y is a Gram matrix with K = pixels.  |pixel - avg| <= 255 is exact in f16, every product
+// (<= 255^2) is exact in f32 and a sum of up to 256 of them stays below 2^24, so an f16 x f16 -> f32
+// MMA chain over 256 pixels is EXACT integer arithmetic; the f32 accumulators are then converted and
+// added to int32 totals in shared memory (good for 33025 pixels), which fold into the CTA's int64
+// partial.  Bit-exact with the reference for any input; tests/test_wiener.py holds the extremes.
+//
+// Matrix rows are ordered i = 8*kx + ky (window column kx, window row ky < WIN); row 7 is x = src - avg
+// (so M = row 7 of the same product) and rows with ky >= WIN are don't-care padding.  One
+// mma.m16n8k16 K-step covers a 2-row x 8-column block of pixels, k = 2*column + row: a fragment
+// register then holds (d[r][c], d[r+1][c]), which the tile stores pre-paired as one 32-bit word per
+// (r, c) -- any window shift is a plain word index, and with a row pitch == 4 (mod 32) words the 8
+// window rows x 4 columns a warp fetches per load land in 32 distinct banks.  The B fragment of
+// n-tile kx is also one half of the A fragment of m-tile kx/2, so a K-step costs 2*WIN loads for
+// all of its MMAs.  Only the tiles of the upper triangle (m-tile m, n-tile n >= 2m) are computed.
+constexpr int kMmaWarps = 4;
+constexpr int kMmaTW = 64, kMmaTH = 32;
+constexpr int kMmaPitch = 100;                                // words per pair-row
+constexpr int kMmaPRows = kMmaTH + 8;                         // py <= TH-2, plus window/padding row <= 8
+constexpr int kMmaXBase = kMmaPRows * kMmaPitch + 28;         // x rows sit on banks 28..31 like a window row 7
+constexpr int kMmaWords = kMmaXBase + kMmaTH * kMmaPitch;
+constexpr int kMmaAccMax = 16 * 128;                          // 16 output tiles x 128 accumulators (WIN = 7)
+constexpr int kMmaFoldPixels = 33025 - kMmaTW * kMmaTH;       // 2^31 / 255^2, minus the tile about to be added
+static_assert(kMmaPitch % 32 == 4 && (kMmaPRows * kMmaPitch) % 32 == 0, "bank layout");
+static_assert(kMmaTW + 6 <= kMmaPitch && kMmaAccMax <= 2450, "layout");
+
+__device__ __forceinline__ void mma_16816_f16f32(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                                 uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+__device__ __forceinline__ uint32_t pack_pair_f16(int lo, int hi) {
+    const __half2 h = __halves2half2(__int2half_rn(lo), __int2half_rn(hi));  // |v| <= 255: exact
+    return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+__host__ __device__ __forceinline__ int mma_tile_index(int win, int m, int n) { return m * win - m * (m - 1) + n - 2 * m; }
+
+template <int WIN>
+__device__ __forceinline__ void stats_mma_body(const uint8_t* __restrict__ dgd, const uint8_t* __restrict__ src, const SvtB200StatsItem& s,
+                                               const int avg, const int part, const int parts, long long* __restrict__ P,
+                                               uint32_t* __restrict__ tile, int* __restrict__ s32) {
+    constexpr int NT = WIN, MT = (WIN + 1) / 2, HALF = WIN / 2, OFF = 3 - HALF;
+    constexpr int NTILES = MT * WIN - MT * (MT - 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    // word offset of this lane's fragment row in n-tile n, relative to the K-step's (py, px) word
+    int boff[NT];
+#pragma unroll
+    for (int n = 0; n < NT; n++) boff[n] = (OFF + g) * kMmaPitch + OFF + n + t;
+    if (g == 7) boff[0] = kMmaXBase + t;
+    float acc[NTILES][4];
+#pragma unroll
+    for (int i = 0; i < NTILES; i++) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+    for (int i = threadIdx.x; i < NTILES * 128; i += kMmaWarps * 32) s32[i] = 0;
+    __syncthreads();
+    auto flush_regs = [&]() {
+#pragma unroll
+        for (int i = 0; i < NTILES; i++)
+#pragma unroll
+            for (int r = 0; r < 4; r++) {
+                atomicAdd(&s32[(i * 4 + r) * 32 + lane], __float2int_rn(acc[i][r]));
+                acc[i][r] = 0.f;
+            }
+    };
+    const int W = s.h_end - s.h_start, H = s.v_end - s.v_start;
+    const int ntx = (W + kMmaTW - 1) / kMmaTW, nty = (H + kMmaTH - 1) / kMmaTH;
+    const int vlo = s.v_start - HALF, vhi = s.v_end + HALF, hlo = s.h_start - HALF, hhi = s.h_end + HALF;
+    int  ksteps = 0, pending = 0;
+    bool spilled = false;
+    for (int tl = part; tl < ntx * nty; tl += parts) {
+        const int ty = tl / ntx, tx = tl - ty * ntx;
+        const int r0 = s.v_start + ty * kMmaTH, c0 = s.h_start + tx * kMmaTW;
+        const int nrows = min(kMmaTH, s.v_end - r0), ncols = min(kMmaTW, s.h_end - c0);
+        if (pending > kMmaFoldPixels) {  // CTA-uniform: fold the int32 totals into the int64 partial
+            flush_regs();
+            ksteps = 0;
+            __syncthreads();
+            for (int i = threadIdx.x; i < NTILES * 128; i += kMmaWarps * 32) {
+                P[i] = (spilled ? P[i] : 0) + s32[i];
+                s32[i] = 0;
+            }
+            spilled = true;
+            pending = 0;
+        }
+        __syncthreads();
+        // pair words of d = dgd - avg for tile rows/cols -3.. (zero outside what the reference reads)
+        for (int w = threadIdx.x; w < (kMmaTW + 6) * 4; w += kMmaWarps * 32) {
+            const int  seg = w / (kMmaTW + 6), c = w - seg * (kMmaTW + 6);
+            const int  col = c0 - 3 + c;
+            const bool cv = col >= hlo && col < hhi;
+            const int  rbeg = seg * (kMmaPRows / 4);
+            auto ld = [&](int rr) {
+                const int row = r0 - 3 + rr;
+                return (cv && row >= vlo && row < vhi) ? (int)dgd[(ptrdiff_t)row * s.dgd_stride + col] - avg : 0;
+            };
+            int lo = ld(rbeg);
+#pragma unroll
+            for (int k = 0; k < kMmaPRows / 4; k++) {
+                const int hi = ld(rbeg + k + 1);
+                tile[(rbeg + k) * kMmaPitch + c] = pack_pair_f16(lo, hi);
+                lo = hi;
+            }
+        }
+        for (int w = threadIdx.x; w < (kMmaTH / 2) * kMmaTW; w += kMmaWarps * 32) {
+            const int  r = (w / kMmaTW) * 2, c = w % kMmaTW;
+            const bool cv = c < ncols;
+            const uint8_t* p = src + (ptrdiff_t)(r0 + r) * s.src_stride + c0 + c;
+            const int lo = (cv && r < nrows) ? (int)p[0] - avg : 0;
+            const int hi = (cv && r + 1 < nrows) ? (int)p[s.src_stride] - avg : 0;
+            tile[kMmaXBase + r * kMmaPitch + c] = pack_pair_f16(lo, hi);
+        }
+        __syncthreads();
+        const int cgs = (ncols + 7) >> 3, nsteps = cgs * ((nrows + 1) >> 1);
+        for (int st = warp; st < nsteps; st += kMmaWarps) {
+            const int rp = st / cgs, px = (st - rp * cgs) * 8, py = rp * 2;
+            const uint32_t* base = tile + py * kMmaPitch + px;
+            // pixels of this K-step outside the region contribute nothing: zero them in the B operand
+            const uint32_t rowmask = (py + 1 < nrows) ? 0xffffffffu : 0x0000ffffu;
+            const uint32_t m0 = (px + t < ncols) ? rowmask : 0u, m1 = (px + t + 4 < ncols) ? rowmask : 0u;
+            uint32_t f0[NT], f1[NT];
+#pragma unroll
+            for (int n = 0; n < NT; n++) {
+                f0[n] = base[boff[n]];
+                f1[n] = base[boff[n] + 4];
+            }
+#pragma unroll
+            for (int m = 0; m < MT; m++) {
+                constexpr int last = NT - 1;
+                const int     lo = 2 * m, hi = 2 * m + 1 <= last ? 2 * m + 1 : last;
+#pragma unroll
+                for (int n = 2 * m; n < NT; n++)
+                    mma_16816_f16f32(acc[m * WIN - m * (m - 1) + n - 2 * m], f0[lo], f0[hi], f1[lo], f1[hi], f0[n] & m0, f1[n] & m1);
+            }
+            if (++ksteps == 16) {  // 256 pixels: the f32 sums are still exact integers
+                flush_regs();
+                ksteps = 0;
+            }
+        }
+        pending += nrows * ncols;
+    }
+    flush_regs();
+    __syncthreads();
+    for (int i = threadIdx.x; i < NTILES * 128; i += kMmaWarps * 32) P[i] = (spilled ? P[i] : 0) + s32[i];
+}
+
+__global__ void __launch_bounds__(kMmaWarps * 32)
+stats_mma_kernel(const uint8_t* __restrict__ dgd_base, const uint8_t* __restrict__ src_base, const SvtB200StatsItem* __restrict__ items,
+                 const unsigned long long* __restrict__ tot_in, int ctas_per_item, long long* __restrict__ partial) {
+    __shared__ uint32_t tile[kMmaWords];
+    __shared__ int      s32[kMmaAccMax];
+    const int it = blockIdx.x / ctas_per_item, part = blockIdx.x % ctas_per_item;
+    const SvtB200StatsItem s = items[it];
+    const int avg = stats_average(tot_in, it, s);
+    long long* P = partial + ((size_t)it * ctas_per_item + part) * 2450;
+    const uint8_t* dgd = dgd_base + s.dgd_off;
+    const uint8_t* src = src_base + s.src_off;
+    if (s.wiener_win == 7) stats_mma_body<7>(dgd, src, s, avg, part, ctas_per_item, P, tile, s32);
+    else if (s.wiener_win == 5) stats_mma_body<5>(dgd, src, s, avg, part, ctas_per_item, P, tile, s32);
+    else stats_mma_body<3>(dgd, src, s, avg, part, ctas_per_item, P, tile, s32);
+}
+
 __global__ void stats_finalize_kernel(const long long* __restrict__ partial, int parts, const SvtB200StatsItem* __restrict__ items,
-                                      int n_items, int divider, long long* __restrict__ M_out, long long* __restrict__ H_out) {
+                                      int n_items, int divider, int mma_layout, long long* __restrict__ M_out,
+                                      long long* __restrict__ H_out) {
     __shared__ long long A[2450];
     for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
         const int win = items[it].wiener_win, win2 = win * win;
@@ -263,6 +435,25 @@ __global__ void stats_finalize_kernel(const long long* __restrict__ partial, int
         __syncthreads();
         long long* M = M_out + (size_t)it * 49;
         long long* H = H_out + (size_t)it * 2401;
+        if (mma_layout) {
+            // accumulator (row i = 8*kx+ky, column j) of the MMA lives in tile (i/16, j/8), C-fragment
+            // register ((i/8)&1)*2 + (j&1) of lane (i&7)*4 + (j&7)/2; M is matrix row 7
+            for (int k = threadIdx.x; k < win2; k += blockDim.x) {
+                const int ka = k / win, kq = k - ka * win;
+                M[k] = A[(mma_tile_index(win, 0, ka) * 4 + (kq & 1)) * 32 + 28 + (kq >> 1)] / divider;
+            }
+            for (int p = threadIdx.x; p < win2 * win2; p += blockDim.x) {
+                const int k = p / win2, l = p - k * win2;
+                int ka = k / win, kq = k - ka * win, la = l / win, lq = l - la * win;
+                if (ka > la) {
+                    int x = ka; ka = la; la = x;
+                    x = kq; kq = lq; lq = x;
+                }
+                const int idx = mma_tile_index(win, ka >> 1, la), reg = (ka & 1) * 2 + (lq & 1), lane = kq * 4 + (lq >> 1);
+                H[p] = A[(idx * 4 + reg) * 32 + lane] / divider;
+            }
+            continue;
+        }
         for (int k = threadIdx.x; k < win2; k += blockDim.x) M[k] = A[2401 + k] / divider;
         for (int p = threadIdx.x; p < win2 * win2; p += blockDim.x) {
             const int k = p / win2, l = p - k * win2;
@@ -276,13 +467,13 @@ __global__ void stats_finalize_kernel(const long long* __restrict__ partial, int
 }
 
 static long long* g_stats_acc = nullptr;
-static int*       g_stats_avg = nullptr;
+static unsigned long long* g_stats_avg = nullptr;
 static size_t     g_stats_cap = 0;
 static std::mutex g_stats_mu;
 
 template <typename PIX>
 static void launch_stats(const PIX* d_dgd, const PIX* d_src, const SvtB200StatsItem* d_items, int n, int bd, long long* d_M,
-                         long long* d_H, long long* d_acc, int* d_avg, cudaStream_t st) {
+                         long long* d_H, long long* d_acc, unsigned long long* d_tot, cudaStream_t st) {
     const int maxv = (1 << bd) - 1;
     long long fp = 2147483647ll / ((long long)maxv * maxv);
     if (fp > 30000) fp = 30000;
@@ -291,11 +482,16 @@ static void launch_stats(const PIX* d_dgd, const PIX* d_src, const SvtB200StatsI
     int cpi = (ctx().sm_count * 4) / (n > 0 ? n : 1);
     if (cpi < 1) cpi = 1;
     if (cpi > kStatsMaxParts) cpi = kStatsMaxParts;
-    stats_avg_kernel<PIX><<<grid_for(n, 4), 256, 0, st>>>(d_dgd, d_items, n, d_avg);
+    B200_CUDA_CHECK(cudaMemsetAsync(d_tot, 0, (size_t)n * sizeof(unsigned long long), st));
+    stats_sum_kernel<PIX><<<n * kSumParts, 256, 0, st>>>(d_dgd, d_items, d_tot);
     B200_LAUNCH_CHECK();
-    stats_accum_kernel<PIX><<<n * cpi, kStatsWarps * 32, 0, st>>>(d_dgd, d_src, d_items, d_avg, cpi, d_acc, (int)fp);
+    if constexpr (sizeof(PIX) == 1) {
+        stats_mma_kernel<<<n * cpi, kMmaWarps * 32, 0, st>>>(d_dgd, d_src, d_items, d_tot, cpi, d_acc);
+    } else {
+        stats_accum_kernel<PIX><<<n * cpi, kStatsWarps * 32, 0, st>>>(d_dgd, d_src, d_items, d_tot, cpi, d_acc, (int)fp);
+    }
     B200_LAUNCH_CHECK();
-    stats_finalize_kernel<<<grid_for(n, 4), 256, 0, st>>>(d_acc, cpi, d_items, n, divider, d_M, d_H);
+    stats_finalize_kernel<<<grid_for(n, 4), 256, 0, st>>>(d_acc, cpi, d_items, n, divider, sizeof(PIX) == 1, d_M, d_H);
     B200_LAUNCH_CHECK();
 }
 
@@ -326,7 +522,7 @@ static void stats_t1(int wiener_win, const PIX* dgd, const PIX* src, int h_start
     it->wiener_win = wiener_win;
     l->h2d(0, in_end);
     launch_stats<PIX>(l->d<PIX>(o_d), l->d<PIX>(o_s), l->d<SvtB200StatsItem>(o_it), 1, bd, l->d<long long>(o_M), l->d<long long>(o_H),
-                      l->d<long long>(o_acc), l->d<int>(o_avg), l->stream);
+                      l->d<long long>(o_acc), l->d<unsigned long long>(o_avg), l->stream);
     l->d2h(o_M, (o_H + 2401 * 8) - o_M);
     l->sync();
     memcpy(M, l->h<int64_t>(o_M), (size_t)win2 * 8);
@@ -409,7 +605,7 @@ extern "C" int svt_b200_compute_stats_batch_dev(const void* d_dgd, const void* d
         if (g_stats_acc) { cudaFree(g_stats_acc); cudaFree(g_stats_avg); }
         g_stats_cap = (size_t)n_items * 2;
         B200_CUDA_CHECK(cudaMalloc(&g_stats_acc, g_stats_cap * kStatsMaxParts * 2450 * 8));
-        B200_CUDA_CHECK(cudaMalloc(&g_stats_avg, g_stats_cap * 4));
+        B200_CUDA_CHECK(cudaMalloc(&g_stats_avg, g_stats_cap * 8));
     }
     if (bit_depth > 8)
         launch_stats<uint16_t>((const uint16_t*)d_dgd, (const uint16_t*)d_src, d_items, n_items, bit_depth, (long long*)d_M, (long long*)d_H,

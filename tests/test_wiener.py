@@ -60,3 +60,26 @@ def test_compute_stats_t1(b200, oracle):
                         b200.lib.svt_b200_av1_compute_stats_highbd(win, rh.P(dgd), rh.P(src), hs, he, vs, ve, W, W, rh.P(M), rh.P(H), bd)
                     assert np.array_equal(M[:win * win], want[0]), (bd, win, W, kind)
                     assert np.array_equal(H[:win ** 4], want[1]), (bd, win, W, kind)
+
+
+def test_compute_stats_large_region_8bit(b200, oracle):
+    """A region far larger than a restoration unit: every CTA of the tensor-core kernel passes the
+    33025-pixel bound of its int32 totals and must fold them into the int64 partial on the way; the
+    half-black / half-white picture gives long runs of same-sign maximal products."""
+    r = rng(92)
+    W, Hh, hs, he, vs, ve = 840, 726, 3, 837, 3, 723
+    yy, xx = np.mgrid[0:Hh, 0:W]
+    for kind in ("random", "halves"):
+        if kind == "random":
+            dgd = r.integers(0, 256, W * Hh).astype(np.uint8); src = r.integers(0, 256, W * Hh).astype(np.uint8)
+        else:
+            dgd = ((xx > W // 2) * 255).astype(np.uint8).reshape(-1); src = ((yy > Hh // 2) * 255).astype(np.uint8).reshape(-1)
+        for win in (7, 5):
+            if oracle.ref is not None:
+                want = rh.ref_stats(oracle.ref, win, dgd, src, hs, he, vs, ve, W, W, 8)
+            else:
+                want = rh.port_stats(oracle.port, win, dgd.astype(np.uint16), src.astype(np.uint16), hs, he, vs, ve, W, W, 8)
+            M = np.zeros(49, np.int64); H = np.zeros(2401, np.int64)
+            b200.lib.svt_b200_av1_compute_stats(win, rh.P(dgd), rh.P(src), hs, he, vs, ve, W, W, rh.P(M), rh.P(H))
+            assert np.array_equal(M[:win * win], want[0]), (win, kind)
+            assert np.array_equal(H[:win ** 4], want[1]), (win, kind)
