@@ -22,6 +22,7 @@ namespace b200 {
 constexpr int kVeryLarge = 0x7f7f;  // CDEF_VERY_LARGE (cdef.h:38)
 constexpr int kTP        = 88;      // tile pitch in uint16 (>= 64 + 2*8, keeps rows 16-B aligned)
 constexpr int kTileRows  = 64 + 6;
+constexpr int kGChunk    = 8;       // candidate strengths evaluated between two CTA barriers of the search
 
 __device__ __forceinline__ int msb32(uint32_t n) { return 31 - __clz(n); }
 __device__ __forceinline__ int cdef_constrain(int diff, int threshold, int damping) {
@@ -262,7 +263,8 @@ cdef_search_kernel(SvtB200CdefFrame f, const uint8_t* __restrict__ skip8x8, cons
     __shared__ int      s_var[64];
     __shared__ uint8_t  s_list[64];  // by*8+bx of the non-skip 8x8s, raster order (svt_sb_compute_cdef_list)
     __shared__ int      s_count;
-    __shared__ unsigned long long s_acc;
+    __shared__ unsigned long long s_acc[kGChunk];
+    __shared__ unsigned int       s_blk[kGChunk][64][5];  // luma: per strength, per block: sum_s, sum_d, sum_s2, sum_d2, sum_sd
     const int nhfb = (f.width + 63) >> 6, nvfb = (f.height + 63) >> 6, nfb = nhfb * nvfb;
     const int cs = f.bit_depth > 8 ? f.bit_depth - 8 : 0;
     const int w8 = (f.width + 7) >> 3, h8 = (f.height + 7) >> 3;
@@ -311,52 +313,74 @@ cdef_search_kernel(SvtB200CdefFrame f, const uint8_t* __restrict__ skip8x8, cons
             subs = min(subs, dec ? 1 : 4);                  // cdef_process.c:243-248 (4:2:0 chroma = BLOCK_4X4)
             const int rows_per_blk = bsz / subs;
             const int damping = f.damping + cs - (pli != 0);
-            for (int g = 0; g < n_strengths; g++) {
-                const int sv = pli ? strengths_uv[g] : strengths_y[g];
-                if (threadIdx.x == 0) s_acc = 0;
+            // One thread per filtered pixel: idx -> (block, processed row, column), so a warp reads whole
+            // 8- (4-) pixel row segments of the tile and of the source picture.  Candidate strengths are
+            // taken kGChunk at a time, each with its own accumulators, so the CTA synchronises per chunk
+            // and not per strength.
+            const int ppb = bsz * rows_per_blk, lg_bsz = 3 - dec;  // processed pixels per block: 64/32/16 (luma), 16 (chroma)
+            const int seg = min(ppb, 32);                          // lanes that share a block
+            for (int g0 = 0; g0 < n_strengths; g0 += kGChunk) {
+                const int ng = min(kGChunk, n_strengths - g0);
+                for (int i = threadIdx.x; i < kGChunk * 64 * 5; i += blockDim.x) (&s_blk[0][0][0])[i] = 0;
+                if (threadIdx.x < kGChunk) s_acc[threadIdx.x] = 0;
                 __syncthreads();
-                if (sv >= 0) {
-                    const int pri = (sv / 4) << cs;
-                    int sec = sv % 4;
-                    sec = (sec + (sec == 3)) << cs;
-                    // unit = (block, processed row); the rows of one block sit in adjacent lanes
-                    for (int u = threadIdx.x; u < ((count * rows_per_blk + 31) & ~31); u += blockDim.x) {  // whole warps stay in the loop (shuffles)
-                        unsigned long long ss = 0, sdv = 0, s2 = 0, d2 = 0, sdp = 0, se = 0;
-                        const bool live = u < count * rows_per_blk;
-                        if (live) {
-                            const int bi = u / rows_per_blk, ri = (u - bi * rows_per_blk) * subs;
-                            const int b = s_list[bi], by = b >> 3, bx = b & 7;
-                            const int t = pli ? pri : cdef_adjust_strength(pri, s_var[b]);
-                            const int d = pri ? s_dir[b] : 0;
-                            const uint16_t* in = tile + (3 + bsz * by + ri) * kTP + 8 + bsz * bx;
-                            const PIX* sp = src + (size_t)(fbr * fbs + bsz * by + ri) * sstride + fbc * fbs + bsz * bx;
-                            for (int j = 0; j < bsz; j++) {
-                                const unsigned long long y = (unsigned long long)(uint16_t)cdef_filter_px(in + j, kTP, t, sec, d, damping, damping, cs);
-                                const unsigned long long o = sp[j];
-                                if (pli == 0) { ss += y; sdv += o; s2 += y * y; d2 += o * o; sdp += y * o; }
-                                else { const long long e = (long long)o - (long long)y; se += (unsigned long long)(e * e); }
-                            }
-                        }
+                for (int idx = threadIdx.x; idx < ((count * ppb + 31) & ~31); idx += blockDim.x) {  // whole warps stay in the loop (shuffles)
+                    const bool live = idx < count * ppb;
+                    const int  bi = live ? idx / ppb : 0, within = idx - (idx / ppb) * ppb;
+                    const int  ri = (within >> lg_bsz) * subs, j = within & (bsz - 1);
+                    const int  b = s_list[bi], by = b >> 3, bx = b & 7;
+                    const uint16_t* in = tile + (3 + bsz * by + ri) * kTP + 8 + bsz * bx + j;
+                    const unsigned int o = live ? (unsigned int)src[(size_t)(fbr * fbs + bsz * by + ri) * sstride + fbc * fbs + bsz * bx + j] : 0u;
+                    const int var = s_var[b], dirb = s_dir[b];
+                    for (int gi = 0; gi < ng; gi++) {
+                        const int sv = pli ? strengths_uv[g0 + gi] : strengths_y[g0 + gi];
+                        if (sv < 0) continue;  // CTA-uniform
+                        const int pri = (sv / 4) << cs;
+                        int sec = sv % 4;
+                        sec = (sec + (sec == 3)) << cs;
+                        const int t = pli ? pri : cdef_adjust_strength(pri, var);
+                        const unsigned int y = live ? (unsigned int)(uint16_t)cdef_filter_px(in, kTP, t, sec, pri ? dirb : 0, damping, damping, cs) : 0u;
                         if (pli == 0) {
-                            // reduce the rows_per_blk rows of a block (2, 4 or 8 adjacent lanes)
-                            for (int o = rows_per_blk >> 1; o > 0; o >>= 1) {
-                                ss += __shfl_xor_sync(0xffffffffu, ss, o);
-                                sdv += __shfl_xor_sync(0xffffffffu, sdv, o);
-                                s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-                                d2 += __shfl_xor_sync(0xffffffffu, d2, o);
-                                sdp += __shfl_xor_sync(0xffffffffu, sdp, o);
+                            // five moments of the block (<= 64 pixels of <= 12 bits: fit 32 bits)
+                            unsigned int ss = y, sdv = o, s2 = y * y, d2 = o * o, sdp = y * o;
+                            for (int sh = seg >> 1; sh > 0; sh >>= 1) {
+                                ss += __shfl_xor_sync(0xffffffffu, ss, sh);
+                                sdv += __shfl_xor_sync(0xffffffffu, sdv, sh);
+                                s2 += __shfl_xor_sync(0xffffffffu, s2, sh);
+                                d2 += __shfl_xor_sync(0xffffffffu, d2, sh);
+                                sdp += __shfl_xor_sync(0xffffffffu, sdp, sh);
                             }
-                            if (live && (u % rows_per_blk) == 0) atomicAdd(&s_acc, cdef_dist_from_sums(ss, sdv, s2, d2, sdp, cs));
-                        } else if (live && se) {
-                            atomicAdd(&s_acc, se);
+                            if (live && (idx & (seg - 1)) == 0) {
+                                unsigned int* sb = s_blk[gi][bi];
+                                atomicAdd(sb + 0, ss);
+                                atomicAdd(sb + 1, sdv);
+                                atomicAdd(sb + 2, s2);
+                                atomicAdd(sb + 3, d2);
+                                atomicAdd(sb + 4, sdp);
+                            }
+                        } else {
+                            const int e = (int)o - (int)y;
+                            unsigned int se = (unsigned int)(e * e);
+                            for (int sh = 16; sh > 0; sh >>= 1) se += __shfl_xor_sync(0xffffffffu, se, sh);
+                            if ((threadIdx.x & 31) == 0 && se) atomicAdd(&s_acc[gi], (unsigned long long)se);
                         }
                     }
                 }
                 __syncthreads();
-                if (threadIdx.x == 0) {
+                if (pli == 0) {
+                    for (int q = threadIdx.x; q < ng * count; q += blockDim.x) {
+                        const int gi = q / count, bi = q - gi * count;
+                        if (strengths_y[g0 + gi] < 0) continue;
+                        const unsigned int* sb = s_blk[gi][bi];
+                        atomicAdd(&s_acc[gi], cdef_dist_from_sums(sb[0], sb[1], sb[2], sb[3], sb[4], cs));
+                    }
+                    __syncthreads();
+                }
+                if ((int)threadIdx.x < ng) {
+                    const int g = g0 + threadIdx.x, sv = pli ? strengths_uv[g] : strengths_y[g];
                     unsigned long long* m = mse + (size_t)((pli ? 1 : 0) * nfb + fb) * n_strengths + g;
                     // enc: mse_seg = (sum >> 2*coeff_shift) * subsampling_factor; untested chroma = default_mse_uv*64
-                    const unsigned long long v = sv >= 0 ? (s_acc >> (2 * cs)) * (unsigned long long)subs : 0;
+                    const unsigned long long v = sv >= 0 ? (s_acc[threadIdx.x] >> (2 * cs)) * (unsigned long long)subs : 0;
                     if (pli == 0) *m = v;
                     else if (sv < 0) *m = 1040400ull * 64ull;
                     else if (pli == 1) *m = v;
@@ -422,14 +446,14 @@ cdef_apply_kernel(SvtB200CdefFrame f, const uint8_t* __restrict__ skip8x8, const
             sec = (sec + (sec == 3)) << cs;
             const int bsz = 8 >> dec, damping = f.damping + cs - (pli != 0);
             if (pri || sec)
-                for (int u = threadIdx.x; u < count * bsz; u += blockDim.x) {
-                    const int bi = u / bsz, ri = u - bi * bsz;
+                for (int idx = threadIdx.x; idx < count * bsz * bsz; idx += blockDim.x) {  // one thread per pixel
+                    const int lg = 3 - dec, bi = idx >> (2 * lg), ri = (idx >> lg) & (bsz - 1), j = idx & (bsz - 1);
                     const int b = s_list[bi], by = b >> 3, bx = b & 7;
                     const int t = pli ? pri : cdef_adjust_strength(pri, s_var[b]);
                     const int d = pri ? s_dir[b] : 0;
-                    const uint16_t* in = tile + (3 + bsz * by + ri) * kTP + 8 + bsz * bx;
-                    PIX* op = out + (size_t)(fbr * fbs + bsz * by + ri) * ostride + fbc * fbs + bsz * bx;
-                    for (int j = 0; j < bsz; j++) op[j] = (PIX)cdef_filter_px(in + j, kTP, t, sec, d, damping, damping, cs);
+                    const uint16_t* in = tile + (3 + bsz * by + ri) * kTP + 8 + bsz * bx + j;
+                    out[(size_t)(fbr * fbs + bsz * by + ri) * ostride + fbc * fbs + bsz * bx + j] =
+                        (PIX)cdef_filter_px(in, kTP, t, sec, d, damping, damping, cs);
                 }
             __syncthreads();
         }
