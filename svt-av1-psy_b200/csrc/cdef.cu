@@ -41,88 +41,121 @@ __device__ __forceinline__ int cdef_adjust_strength(int strength, int var) {
 __constant__ int8_t c_cdef_dir[8][2][2] = {{{-1, 1}, {-2, 2}}, {{0, 1}, {-1, 2}}, {{0, 1}, {0, 2}}, {{0, 1}, {1, 2}},
                                            {{1, 1}, {2, 2}},   {{1, 0}, {2, 1}},  {{1, 0}, {2, 0}}, {{1, 0}, {2, -1}}};
 
-// direction + variance of one 8x8 (cdef.c:150-210)
-__device__ int cdef_find_dir_dev(const uint16_t* img, int stride, int* var, int coeff_shift) {
-    int cost[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    int partial[8][15];
+// direction + variance of one 8x8 (cdef.c:150-210).  The 64 centred pixels sit in registers and the
+// eight directions are evaluated one after the other, each with its own (compile-time indexed) line sums.
+template <int D>
+__device__ __forceinline__ int cdef_dir_bin(int i, int j) {
+    return D == 0 ? i + j : D == 1 ? i + j / 2 : D == 2 ? i : D == 3 ? 3 + i - j / 2 : D == 4 ? 7 + i - j : D == 5 ? 3 - i / 2 + j : D == 6 ? j : i / 2 + j;
+}
+__device__ __forceinline__ constexpr int cdef_div(int n) {  // 840 / n, the weight of a line of n pixels
+    return n == 1 ? 840 : n == 2 ? 420 : n == 3 ? 280 : n == 4 ? 210 : n == 5 ? 168 : n == 6 ? 140 : n == 7 ? 120 : 105;
+}
+template <int D>
+__device__ __forceinline__ int cdef_dir_cost(const int (&x)[64]) {
+    constexpr int NB = (D == 2 || D == 6) ? 8 : (D & 1) ? 11 : 15;
+    int p[NB];
 #pragma unroll
-    for (int d = 0; d < 8; d++)
+    for (int k = 0; k < NB; k++) p[k] = 0;
 #pragma unroll
-        for (int k = 0; k < 15; k++) partial[d][k] = 0;
     for (int i = 0; i < 8; i++)
-        for (int j = 0; j < 8; j++) {
-            const int x = ((int)img[i * stride + j] >> coeff_shift) - 128;
-            partial[0][i + j] += x;
-            partial[1][i + j / 2] += x;
-            partial[2][i] += x;
-            partial[3][3 + i - j / 2] += x;
-            partial[4][7 + i - j] += x;
-            partial[5][3 - i / 2 + j] += x;
-            partial[6][j] += x;
-            partial[7][i / 2 + j] += x;
-        }
-    const int div_table[9] = {0, 840, 420, 280, 210, 168, 140, 120, 105};
-    for (int i = 0; i < 8; i++) {
-        cost[2] += partial[2][i] * partial[2][i];
-        cost[6] += partial[6][i] * partial[6][i];
+#pragma unroll
+        for (int j = 0; j < 8; j++) p[cdef_dir_bin<D>(i, j)] += x[i * 8 + j];
+    int cost = 0;
+    if (D == 2 || D == 6) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) cost += p[i] * p[i];
+        cost *= cdef_div(8);
+    } else if (D & 1) {
+#pragma unroll
+        for (int j = 0; j < 5; j++) cost += p[3 + j] * p[3 + j];
+        cost *= cdef_div(8);
+#pragma unroll
+        for (int j = 0; j < 3; j++) cost += (p[j] * p[j] + p[10 - j] * p[10 - j]) * cdef_div(2 * j + 2);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 7; i++) cost += (p[i] * p[i] + p[14 - i] * p[14 - i]) * cdef_div(i + 1);
+        cost += p[7] * p[7] * cdef_div(8);
     }
-    cost[2] *= div_table[8];
-    cost[6] *= div_table[8];
-    for (int i = 0; i < 7; i++) {
-        cost[0] += (partial[0][i] * partial[0][i] + partial[0][14 - i] * partial[0][14 - i]) * div_table[i + 1];
-        cost[4] += (partial[4][i] * partial[4][i] + partial[4][14 - i] * partial[4][14 - i]) * div_table[i + 1];
-    }
-    cost[0] += partial[0][7] * partial[0][7] * div_table[8];
-    cost[4] += partial[4][7] * partial[4][7] * div_table[8];
-    for (int i = 1; i < 8; i += 2) {
-        for (int j = 0; j < 5; j++) cost[i] += partial[i][3 + j] * partial[i][3 + j];
-        cost[i] *= div_table[8];
-        for (int j = 0; j < 3; j++)
-            cost[i] += (partial[i][j] * partial[i][j] + partial[i][10 - j] * partial[i][10 - j]) * div_table[2 * j + 2];
-    }
+    return cost;
+}
+template <typename T>
+__device__ int cdef_find_dir_dev(const T* img, int stride, int* var, int coeff_shift) {
+    int x[64];
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+#pragma unroll
+        for (int j = 0; j < 8; j++) x[i * 8 + j] = ((int)img[i * stride + j] >> coeff_shift) - 128;
+    const int cost[8] = {cdef_dir_cost<0>(x), cdef_dir_cost<1>(x), cdef_dir_cost<2>(x), cdef_dir_cost<3>(x),
+                         cdef_dir_cost<4>(x), cdef_dir_cost<5>(x), cdef_dir_cost<6>(x), cdef_dir_cost<7>(x)};
     int best_cost = 0, best_dir = 0;
+#pragma unroll
     for (int i = 0; i < 8; i++)
         if (cost[i] > best_cost) {
             best_cost = cost[i];
             best_dir  = i;
         }
-    *var = (best_cost - cost[(best_dir + 4) & 7]) >> 10;
+    int opp = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) opp = (i == ((best_dir + 4) & 7)) ? cost[i] : opp;
+    *var = (best_cost - opp) >> 10;
     return best_dir;
 }
 
-// one filtered pixel (cdef.c:262-302); `in` points at the pixel, s = tile pitch
-__device__ __forceinline__ int cdef_filter_px(const uint16_t* in, int s, int pri_strength, int sec_strength, int dir,
-                                              int pri_damping, int sec_damping, int coeff_shift) {
-    const int  ptap0 = ((pri_strength >> coeff_shift) & 1) ? 3 : 4, ptap1 = ((pri_strength >> coeff_shift) & 1) ? 3 : 2;
-    const int  x     = (int16_t)in[0];
-    int        sum = 0, mx = x, mn = x;
+// Taps of one pixel along direction `dir` (cdef.c:262-302), reduced to what every candidate strength
+// shares: |tap - x|, its sign, and the min / max over the taps that are inside the picture.
+// Slots 0..3 primary (k=0: +,-; k=1: +,-), 4..7 secondary k=0, 8..11 secondary k=1.
+struct CdefTaps {
+    int ad[12];
+    int sg[12];
+    int mn, mx;
+};
+__device__ __forceinline__ void cdef_load_taps(const uint16_t* in, int s, int dir, int x, CdefTaps& T) {
+    int mx = x, mn = x;
+    auto put = [&](int slot, int v) {
+        const int diff = v - x;
+        T.ad[slot] = abs(diff);
+        T.sg[slot] = diff < 0 ? -1 : 1;
+        mx = max(mx, v == kVeryLarge ? 0 : v);  // CDEF_VERY_LARGE marks "outside": never the maximum
+        mn = min(mn, v);
+    };
+    const int d2 = (dir + 2) & 7, d6 = (dir + 6) & 7;
 #pragma unroll
     for (int k = 0; k < 2; k++) {
-        const int po = c_cdef_dir[dir][k][0] * s + c_cdef_dir[dir][k][1];
-        const int d2 = (dir + 2) & 7, d6 = (dir + 6) & 7;
+        const int po  = c_cdef_dir[dir][k][0] * s + c_cdef_dir[dir][k][1];
         const int s0o = c_cdef_dir[d2][k][0] * s + c_cdef_dir[d2][k][1];
         const int s2o = c_cdef_dir[d6][k][0] * s + c_cdef_dir[d6][k][1];
-        const int p0 = (int16_t)in[po], p1 = (int16_t)in[-po];
-        const int q0 = (int16_t)in[s0o], q1 = (int16_t)in[-s0o], q2 = (int16_t)in[s2o], q3 = (int16_t)in[-s2o];
-        const int pt = k ? ptap1 : ptap0, st = k ? 1 : 2;
-        sum = (int16_t)(sum + (int16_t)(pt * cdef_constrain(p0 - x, pri_strength, pri_damping)));
-        sum = (int16_t)(sum + (int16_t)(pt * cdef_constrain(p1 - x, pri_strength, pri_damping)));
-        if (p0 != kVeryLarge) mx = max(p0, mx);
-        if (p1 != kVeryLarge) mx = max(p1, mx);
-        mn = min(min(p0, p1), mn);
-        if (q0 != kVeryLarge) mx = max(q0, mx);
-        if (q1 != kVeryLarge) mx = max(q1, mx);
-        if (q2 != kVeryLarge) mx = max(q2, mx);
-        if (q3 != kVeryLarge) mx = max(q3, mx);
-        mn = min(min(min(q0, q1), min(q2, q3)), mn);
-        sum = (int16_t)(sum + (int16_t)(st * cdef_constrain(q0 - x, sec_strength, sec_damping)));
-        sum = (int16_t)(sum + (int16_t)(st * cdef_constrain(q1 - x, sec_strength, sec_damping)));
-        sum = (int16_t)(sum + (int16_t)(st * cdef_constrain(q2 - x, sec_strength, sec_damping)));
-        sum = (int16_t)(sum + (int16_t)(st * cdef_constrain(q3 - x, sec_strength, sec_damping)));
+        put(2 * k, in[po]);
+        put(2 * k + 1, in[-po]);
+        put(4 + 4 * k, in[s0o]);
+        put(5 + 4 * k, in[-s0o]);
+        put(6 + 4 * k, in[s2o]);
+        put(7 + 4 * k, in[-s2o]);
     }
-    int y = (int16_t)x + ((8 + sum - (sum < 0)) >> 4);
-    y     = y < mn ? mn : (y > mx ? mx : y);
-    return (int16_t)y;
+    T.mn = mn;
+    T.mx = mx;
+}
+// The filtered pixel for one (primary, secondary) strength.  constrain() (cdef.c:85-93) with a zero
+// threshold yields zero by itself here: max(0, 0 - (|d| >> shift)) = 0.  The reference accumulates in
+// int16; |sum| <= 2*(4+2)*240 + 4*(2+1)*64 for 12-bit content, so the int32 sum below is the same number.
+__device__ __forceinline__ int cdef_eval_taps(const CdefTaps& T, int x, int pri, int sec, int pri_damping, int sec_damping,
+                                              int coeff_shift) {
+    const int shp = max(0, pri_damping - msb32((uint32_t)pri)), shs = max(0, sec_damping - msb32((uint32_t)sec));
+    auto c = [&](int slot, int thr, int sh) { return min(T.ad[slot], max(0, thr - (T.ad[slot] >> sh))) * T.sg[slot]; };
+    const int pk0 = c(0, pri, shp) + c(1, pri, shp), pk1 = c(2, pri, shp) + c(3, pri, shp);
+    const int sk0 = c(4, sec, shs) + c(5, sec, shs) + c(6, sec, shs) + c(7, sec, shs);
+    const int sk1 = c(8, sec, shs) + c(9, sec, shs) + c(10, sec, shs) + c(11, sec, shs);
+    const int odd = (pri >> coeff_shift) & 1;
+    const int sum = (odd ? 3 : 4) * pk0 + (odd ? 3 : 2) * pk1 + 2 * sk0 + sk1;
+    const int y   = x + ((8 + sum - (sum < 0)) >> 4);
+    return y < T.mn ? T.mn : (y > T.mx ? T.mx : y);
+}
+// one filtered pixel; `in` points at the pixel, s = tile pitch
+__device__ __forceinline__ int cdef_filter_px(const uint16_t* in, int s, int pri_strength, int sec_strength, int dir,
+                                              int pri_damping, int sec_damping, int coeff_shift) {
+    CdefTaps  T;
+    const int x = in[0];
+    cdef_load_taps(in, s, dir, x, T);
+    return cdef_eval_taps(T, x, pri_strength, sec_strength, pri_damping, sec_damping, coeff_shift);
 }
 
 // luma psy distortion of one 8xN block from its five moments (enc_cdef.c:41-47); exact IEEE sequence
@@ -253,93 +286,123 @@ __device__ void stage_cdef_tile(uint16_t* tile, const PIX* plane, int stride, in
     __syncthreads();
 }
 
+// direction + variance of every non-skip 8x8 luma block of the frame: one thread per block
+template <typename PIX>
+__global__ void __launch_bounds__(128)
+cdef_dir_kernel(SvtB200CdefFrame f, const uint8_t* __restrict__ skip8x8, uint8_t* __restrict__ dir_out /*[nfb][64]*/,
+                int* __restrict__ var_out /*[nfb][64]*/) {
+    const int w8 = (f.width + 7) >> 3, h8 = (f.height + 7) >> 3, nhfb = (f.width + 63) >> 6;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= w8 * h8) return;
+    const int gy = t / w8, gx = t - gy * w8;
+    if (skip8x8[t]) return;
+    const int cs = f.bit_depth > 8 ? f.bit_depth - 8 : 0;
+    int       var;
+    const int dir = cdef_find_dir_dev((const PIX*)f.recon_y + (size_t)gy * 8 * f.recon_stride_y + gx * 8, f.recon_stride_y, &var, cs);
+    const size_t o = (size_t)((gy >> 3) * nhfb + (gx >> 3)) * 64 + (gy & 7) * 8 + (gx & 7);
+    dir_out[o] = (uint8_t)dir;
+    var_out[o] = var;
+}
+
+// Strength search: one CTA per (filter block, plane).  mse[1] (chroma) must be zero on entry: the two
+// chroma planes add into it.
 template <typename PIX>
 __global__ void __launch_bounds__(256)
 cdef_search_kernel(SvtB200CdefFrame f, const uint8_t* __restrict__ skip8x8, const int* __restrict__ strengths_y,
                    const int* __restrict__ strengths_uv, int n_strengths, unsigned long long* __restrict__ mse /*[2][nfb][n_strengths]*/,
-                   uint8_t* __restrict__ dir_out /*[nfb][64]*/, int* __restrict__ var_out /*[nfb][64]*/) {
+                   const uint8_t* __restrict__ dir_in /*[nfb][64]*/, const int* __restrict__ var_in /*[nfb][64]*/) {
     __shared__ uint16_t tile[kTileRows * kTP];
     __shared__ uint8_t  s_dir[64];
     __shared__ int      s_var[64];
     __shared__ uint8_t  s_list[64];  // by*8+bx of the non-skip 8x8s, raster order (svt_sb_compute_cdef_list)
     __shared__ int      s_count;
+    __shared__ unsigned s_ballot[2];
     __shared__ unsigned long long s_acc[kGChunk];
     __shared__ unsigned int       s_blk[kGChunk][64][5];  // luma: per strength, per block: sum_s, sum_d, sum_s2, sum_d2, sum_sd
     const int nhfb = (f.width + 63) >> 6, nvfb = (f.height + 63) >> 6, nfb = nhfb * nvfb;
     const int cs = f.bit_depth > 8 ? f.bit_depth - 8 : 0;
     const int w8 = (f.width + 7) >> 3, h8 = (f.height + 7) >> 3;
-    for (int fb = blockIdx.x; fb < nfb; fb += gridDim.x) {
+    for (int work = blockIdx.x; work < nfb * 3; work += gridDim.x) {
+        const int fb = work / 3, pli = work - fb * 3;
         const int fbr = fb / nhfb, fbc = fb - fbr * nhfb;
-        if (threadIdx.x == 0) {
-            int n = 0;
-            for (int by = 0; by < 8; by++)
-                for (int bx = 0; bx < 8; bx++) {
-                    const int gy = fbr * 8 + by, gx = fbc * 8 + bx;
-                    if (gy < h8 && gx < w8 && !skip8x8[gy * w8 + gx]) s_list[n++] = (uint8_t)(by * 8 + bx);
-                }
-            s_count = n;
+        __syncthreads();
+        if (threadIdx.x < 64) {  // ordered list of the non-skip blocks: ballot + prefix count
+            const int  by = threadIdx.x >> 3, bx = threadIdx.x & 7, gy = fbr * 8 + by, gx = fbc * 8 + bx;
+            const bool on = gy < h8 && gx < w8 && !skip8x8[gy * w8 + gx];
+            const unsigned m = __ballot_sync(0xffffffffu, on);
+            s_dir[threadIdx.x] = dir_in[(size_t)fb * 64 + threadIdx.x];
+            s_var[threadIdx.x] = var_in[(size_t)fb * 64 + threadIdx.x];
+            if ((threadIdx.x & 31) == 0) s_ballot[threadIdx.x >> 5] = m;
+        }
+        __syncthreads();
+        {
+            const unsigned m0 = s_ballot[0], m1 = s_ballot[1];
+            if (threadIdx.x < 64) {
+                const unsigned mine = threadIdx.x < 32 ? m0 : m1, lane = threadIdx.x & 31;
+                if ((mine >> lane) & 1) s_list[(threadIdx.x < 32 ? 0 : __popc(m0)) + __popc(mine & ((1u << lane) - 1))] = (uint8_t)threadIdx.x;
+            }
+            if (threadIdx.x == 0) s_count = __popc(m0) + __popc(m1);
         }
         __syncthreads();
         const int count = s_count;
         if (count == 0) {
-            for (int g = threadIdx.x; g < n_strengths; g += blockDim.x) {
-                mse[(size_t)(0 * nfb + fb) * n_strengths + g] = 0;
-                mse[(size_t)(1 * nfb + fb) * n_strengths + g] = 0;
-            }
-            __syncthreads();
+            if (pli == 0)
+                for (int g = threadIdx.x; g < n_strengths; g += blockDim.x) mse[(size_t)fb * n_strengths + g] = 0;
             continue;
         }
-        for (int pli = 0; pli < 3; pli++) {
-            const int dec = pli ? 1 : 0;
-            const PIX* rec = (const PIX*)(pli == 0 ? f.recon_y : (pli == 1 ? f.recon_cb : f.recon_cr));
-            const PIX* src = (const PIX*)(pli == 0 ? f.src_y : (pli == 1 ? f.src_cb : f.src_cr));
-            const int rstride = pli ? f.recon_stride_c : f.recon_stride_y, sstride = pli ? f.src_stride_c : f.src_stride_y;
-            const int pw = f.width >> dec, ph = f.height >> dec, fbs = 64 >> dec;
-            const int hsz = min(fbs, pw - fbc * fbs), vsz = min(fbs, ph - fbr * fbs);
-            stage_cdef_tile<PIX>(tile, rec, rstride, pw, ph, fbr, fbc, nvfb, nhfb, fbs, fbs, vsz, hsz);
-            if (pli == 0) {
-                if ((int)threadIdx.x < count) {
-                    const int b = s_list[threadIdx.x], by = b >> 3, bx = b & 7;
-                    int var;
-                    s_dir[b] = (uint8_t)cdef_find_dir_dev(tile + (3 + 8 * by) * kTP + 8 + 8 * bx, kTP, &var, cs);
-                    s_var[b] = var;
-                    dir_out[(size_t)fb * 64 + b] = s_dir[b];
-                    var_out[(size_t)fb * 64 + b] = var;
-                }
-                __syncthreads();
+        const int dec = pli ? 1 : 0;
+        const PIX* rec = (const PIX*)(pli == 0 ? f.recon_y : (pli == 1 ? f.recon_cb : f.recon_cr));
+        const PIX* src = (const PIX*)(pli == 0 ? f.src_y : (pli == 1 ? f.src_cb : f.src_cr));
+        const int rstride = pli ? f.recon_stride_c : f.recon_stride_y, sstride = pli ? f.src_stride_c : f.src_stride_y;
+        const int pw = f.width >> dec, ph = f.height >> dec, fbs = 64 >> dec;
+        const int hsz = min(fbs, pw - fbc * fbs), vsz = min(fbs, ph - fbr * fbs);
+        stage_cdef_tile<PIX>(tile, rec, rstride, pw, ph, fbr, fbc, nvfb, nhfb, fbs, fbs, vsz, hsz);
+        const int bsz = 8 >> dec;                       // block edge in this plane
+        int subs = f.subsampling_factor;
+        subs = min(subs, dec ? 1 : 4);                  // cdef_process.c:243-248 (4:2:0 chroma = BLOCK_4X4)
+        const int rows_per_blk = bsz / subs;
+        const int damping = f.damping + cs - (pli != 0);
+        const int* strengths = pli ? strengths_uv : strengths_y;
+        // One thread per filtered pixel: idx -> (block, processed row, column), so a warp reads whole
+        // 8- (4-) pixel row segments of the tile and of the source picture.  The taps of a pixel are
+        // fetched once per direction (the block's own for strengths with a primary part, direction 0
+        // for the others) and shared by all candidate strengths; strengths are taken kGChunk at a
+        // time, each with its own accumulators, so the CTA synchronises per chunk, not per strength.
+        const int ppb = bsz * rows_per_blk, lg_bsz = 3 - dec;  // processed pixels per block: 64/32/16 (luma), 16 (chroma)
+        const int seg = min(ppb, 32);                          // lanes that share a block
+        for (int g0 = 0; g0 < n_strengths; g0 += kGChunk) {
+            const int ng = min(kGChunk, n_strengths - g0);
+            for (int i = threadIdx.x; i < kGChunk * 64 * 5; i += blockDim.x) (&s_blk[0][0][0])[i] = 0;
+            if (threadIdx.x < kGChunk) s_acc[threadIdx.x] = 0;
+            unsigned with_pri = 0, without_pri = 0;  // which strengths of the chunk have / lack a primary part
+            for (int gi = 0; gi < ng; gi++) {
+                const int sv = strengths[g0 + gi];
+                if (sv >= 0) (sv / 4 ? with_pri : without_pri) |= 1u << gi;
             }
-            const int bsz = 8 >> dec;                       // block edge in this plane
-            int subs = f.subsampling_factor;
-            subs = min(subs, dec ? 1 : 4);                  // cdef_process.c:243-248 (4:2:0 chroma = BLOCK_4X4)
-            const int rows_per_blk = bsz / subs;
-            const int damping = f.damping + cs - (pli != 0);
-            // One thread per filtered pixel: idx -> (block, processed row, column), so a warp reads whole
-            // 8- (4-) pixel row segments of the tile and of the source picture.  Candidate strengths are
-            // taken kGChunk at a time, each with its own accumulators, so the CTA synchronises per chunk
-            // and not per strength.
-            const int ppb = bsz * rows_per_blk, lg_bsz = 3 - dec;  // processed pixels per block: 64/32/16 (luma), 16 (chroma)
-            const int seg = min(ppb, 32);                          // lanes that share a block
-            for (int g0 = 0; g0 < n_strengths; g0 += kGChunk) {
-                const int ng = min(kGChunk, n_strengths - g0);
-                for (int i = threadIdx.x; i < kGChunk * 64 * 5; i += blockDim.x) (&s_blk[0][0][0])[i] = 0;
-                if (threadIdx.x < kGChunk) s_acc[threadIdx.x] = 0;
-                __syncthreads();
-                for (int idx = threadIdx.x; idx < ((count * ppb + 31) & ~31); idx += blockDim.x) {  // whole warps stay in the loop (shuffles)
-                    const bool live = idx < count * ppb;
-                    const int  bi = live ? idx / ppb : 0, within = idx - (idx / ppb) * ppb;
-                    const int  ri = (within >> lg_bsz) * subs, j = within & (bsz - 1);
-                    const int  b = s_list[bi], by = b >> 3, bx = b & 7;
-                    const uint16_t* in = tile + (3 + bsz * by + ri) * kTP + 8 + bsz * bx + j;
-                    const unsigned int o = live ? (unsigned int)src[(size_t)(fbr * fbs + bsz * by + ri) * sstride + fbc * fbs + bsz * bx + j] : 0u;
-                    const int var = s_var[b], dirb = s_dir[b];
+            __syncthreads();
+            for (int idx = threadIdx.x; idx < ((count * ppb + 31) & ~31); idx += blockDim.x) {  // whole warps stay in the loop (shuffles)
+                const bool live = idx < count * ppb;
+                const int  bi = live ? idx / ppb : 0, within = idx - (idx / ppb) * ppb;
+                const int  ri = (within >> lg_bsz) * subs, j = within & (bsz - 1);
+                const int  b = s_list[bi], by = b >> 3, bx = b & 7;
+                const uint16_t* in = tile + (3 + bsz * by + ri) * kTP + 8 + bsz * bx + j;
+                const unsigned int o = live ? (unsigned int)src[(size_t)(fbr * fbs + bsz * by + ri) * sstride + fbc * fbs + bsz * bx + j] : 0u;
+                const int x = in[0], var = s_var[b], dirb = s_dir[b];
+#pragma unroll 1
+                for (int pass = 0; pass < 2; pass++) {
+                    const unsigned todo = pass ? without_pri : with_pri;
+                    if (!todo) continue;  // CTA-uniform
+                    CdefTaps T;
+                    cdef_load_taps(in, kTP, pass ? 0 : dirb, x, T);
+#pragma unroll 1
                     for (int gi = 0; gi < ng; gi++) {
-                        const int sv = pli ? strengths_uv[g0 + gi] : strengths_y[g0 + gi];
-                        if (sv < 0) continue;  // CTA-uniform
+                        if (!((todo >> gi) & 1)) continue;  // CTA-uniform
+                        const int sv = strengths[g0 + gi];
                         const int pri = (sv / 4) << cs;
                         int sec = sv % 4;
                         sec = (sec + (sec == 3)) << cs;
                         const int t = pli ? pri : cdef_adjust_strength(pri, var);
-                        const unsigned int y = live ? (unsigned int)(uint16_t)cdef_filter_px(in, kTP, t, sec, pri ? dirb : 0, damping, damping, cs) : 0u;
+                        const unsigned int y = live ? (unsigned int)cdef_eval_taps(T, x, t, sec, damping, damping, cs) : 0u;
                         if (pli == 0) {
                             // five moments of the block (<= 64 pixels of <= 12 bits: fit 32 bits)
                             unsigned int ss = y, sdv = o, s2 = y * y, d2 = o * o, sdp = y * o;
@@ -366,28 +429,26 @@ cdef_search_kernel(SvtB200CdefFrame f, const uint8_t* __restrict__ skip8x8, cons
                         }
                     }
                 }
-                __syncthreads();
-                if (pli == 0) {
-                    for (int q = threadIdx.x; q < ng * count; q += blockDim.x) {
-                        const int gi = q / count, bi = q - gi * count;
-                        if (strengths_y[g0 + gi] < 0) continue;
-                        const unsigned int* sb = s_blk[gi][bi];
-                        atomicAdd(&s_acc[gi], cdef_dist_from_sums(sb[0], sb[1], sb[2], sb[3], sb[4], cs));
-                    }
-                    __syncthreads();
-                }
-                if ((int)threadIdx.x < ng) {
-                    const int g = g0 + threadIdx.x, sv = pli ? strengths_uv[g] : strengths_y[g];
-                    unsigned long long* m = mse + (size_t)((pli ? 1 : 0) * nfb + fb) * n_strengths + g;
-                    // enc: mse_seg = (sum >> 2*coeff_shift) * subsampling_factor; untested chroma = default_mse_uv*64
-                    const unsigned long long v = sv >= 0 ? (s_acc[threadIdx.x] >> (2 * cs)) * (unsigned long long)subs : 0;
-                    if (pli == 0) *m = v;
-                    else if (sv < 0) *m = 1040400ull * 64ull;
-                    else if (pli == 1) *m = v;
-                    else *m += v;
+            }
+            __syncthreads();
+            if (pli == 0) {
+                for (int q = threadIdx.x; q < ng * count; q += blockDim.x) {
+                    const int gi = q / count, bi = q - gi * count;
+                    if (strengths_y[g0 + gi] < 0) continue;
+                    const unsigned int* sb = s_blk[gi][bi];
+                    atomicAdd(&s_acc[gi], cdef_dist_from_sums(sb[0], sb[1], sb[2], sb[3], sb[4], cs));
                 }
                 __syncthreads();
             }
+            if ((int)threadIdx.x < ng) {
+                const int g = g0 + threadIdx.x, sv = strengths[g];
+                unsigned long long* m = mse + (size_t)((pli ? 1 : 0) * nfb + fb) * n_strengths + g;
+                // enc: mse_seg = (sum >> 2*coeff_shift) * subsampling_factor; untested chroma = default_mse_uv*64
+                const unsigned long long v = sv >= 0 ? (s_acc[threadIdx.x] >> (2 * cs)) * (unsigned long long)subs : 0;
+                if (pli == 0) *m = v;
+                else atomicAdd(m, sv < 0 ? (pli == 1 ? 1040400ull * 64ull : 0ull) : v);
+            }
+            __syncthreads();
         }
     }
 }
@@ -613,12 +674,20 @@ extern "C" int svt_b200_cdef_search_frame_dev(const SvtB200CdefFrame* frame, con
     require_ready();
     if (!frame || n_strengths <= 0 || n_strengths > 64) return SVT_B200_ERR_BAD_ARG;
     const int nfb = ((frame->width + 63) >> 6) * ((frame->height + 63) >> 6);
-    if (frame->bit_depth > 8)
-        cdef_search_kernel<uint16_t><<<grid_for(nfb, 4), 256, 0, (cudaStream_t)stream>>>(*frame, d_skip8x8, d_strengths_y, d_strengths_uv,
-                                                                                      n_strengths, (unsigned long long*)d_mse, d_dir, d_var);
-    else
-        cdef_search_kernel<uint8_t><<<grid_for(nfb, 4), 256, 0, (cudaStream_t)stream>>>(*frame, d_skip8x8, d_strengths_y, d_strengths_uv,
-                                                                                     n_strengths, (unsigned long long*)d_mse, d_dir, d_var);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nblk = ((frame->width + 7) >> 3) * ((frame->height + 7) >> 3);
+    B200_CUDA_CHECK(cudaMemsetAsync(d_mse + (size_t)nfb * n_strengths, 0, (size_t)nfb * n_strengths * sizeof(uint64_t), st));
+    if (frame->bit_depth > 8) {
+        cdef_dir_kernel<uint16_t><<<(nblk + 127) / 128, 128, 0, st>>>(*frame, d_skip8x8, d_dir, d_var);
+        B200_LAUNCH_CHECK();
+        cdef_search_kernel<uint16_t><<<grid_for((long long)nfb * 3, 6), 256, 0, st>>>(*frame, d_skip8x8, d_strengths_y, d_strengths_uv, n_strengths,
+                                                                                (unsigned long long*)d_mse, d_dir, d_var);
+    } else {
+        cdef_dir_kernel<uint8_t><<<(nblk + 127) / 128, 128, 0, st>>>(*frame, d_skip8x8, d_dir, d_var);
+        B200_LAUNCH_CHECK();
+        cdef_search_kernel<uint8_t><<<grid_for((long long)nfb * 3, 6), 256, 0, st>>>(*frame, d_skip8x8, d_strengths_y, d_strengths_uv, n_strengths,
+                                                                               (unsigned long long*)d_mse, d_dir, d_var);
+    }
     B200_LAUNCH_CHECK();
     return SVT_B200_OK;
 }
