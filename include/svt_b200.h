@@ -185,15 +185,18 @@ typedef struct SvtB200InvTxfmItem {
     uint32_t reserved2;
 } SvtB200InvTxfmItem;
 
-/* items must be ordered: the n_small items whose W*H <= SVT_B200_TXFM_SMALL_MAX_COEFFS first (they are
- * processed one warp per block), then the n_large others (one CTA per block). */
-#define SVT_B200_TXFM_SMALL_MAX_COEFFS 256
+/* A transform block is processed by a team of max(W,H) threads; its "team class" is
+ * log2(max(W,H)) - 2 (0: 4x4 .. 4: the 64-point sizes).  Items must be ordered by class: the
+ * n_per_class[0] class-0 items first, then class 1, ...; within a class, keeping equal (tx_size,
+ * tx_type) together lets the teams that share a warp run in lock step. */
+#define SVT_B200_TXFM_CLASSES 5
+SVT_B200_API int svt_b200_txfm_team_class(int tx_size);
 SVT_B200_API int svt_b200_fwd_txfm_batch_dev(const int16_t* d_residual, int32_t* d_coeff,
-                                             const SvtB200FwdTxfmItem* d_items, int n_small, int n_large,
-                                             int max_small_tx_size, int max_large_tx_size, void* stream);
+                                             const SvtB200FwdTxfmItem* d_items,
+                                             const int n_per_class[SVT_B200_TXFM_CLASSES], void* stream);
 SVT_B200_API int svt_b200_inv_txfm_batch_dev(const int32_t* d_coeff, const void* d_pred, void* d_recon,
-                                             const SvtB200InvTxfmItem* d_items, int n_small, int n_large,
-                                             int max_small_tx_size, int max_large_tx_size, int pixel_bytes,
+                                             const SvtB200InvTxfmItem* d_items,
+                                             const int n_per_class[SVT_B200_TXFM_CLASSES], int pixel_bytes,
                                              void* stream);
 /* any order; the library groups the items itself */
 SVT_B200_API int svt_b200_fwd_txfm_batch_host(const int16_t* residual, size_t residual_elems, int32_t* coeff,
@@ -353,11 +356,14 @@ SVT_B200_API int svt_b200_cdef_search_frame_dev(const SvtB200CdefFrame* frame, c
                                                 const int* d_strengths_y, const int* d_strengths_uv, int n_strengths,
                                                 uint64_t* d_mse, uint8_t* d_dir, int32_t* d_var, void* stream);
 /* d_fb_strength_idx: per filter block index into the frame's strength tables (-1 = leave untouched);
- * output planes receive the filtered pixels of non-skip blocks only (copy the input first). */
+ * output planes receive the filtered pixels of non-skip blocks only (copy the input first).
+ * d_dir/d_var: the [nfb][64] arrays svt_b200_cdef_search_frame_dev wrote for this reconstruction (the
+ * reference keeps them in pcs->cdef_dir_data between search and apply); both NULL = recompute. */
 SVT_B200_API int svt_b200_cdef_apply_frame_dev(const SvtB200CdefFrame* frame, const uint8_t* d_skip8x8,
                                                const int8_t* d_fb_strength_idx, const int* d_y_strength,
-                                               const int* d_uv_strength, void* d_out_y, void* d_out_cb, void* d_out_cr,
-                                               int out_stride_y, int out_stride_c, void* stream);
+                                               const int* d_uv_strength, const uint8_t* d_dir, const int32_t* d_var,
+                                               void* d_out_y, void* d_out_cb, void* d_out_cr, int out_stride_y,
+                                               int out_stride_c, void* stream);
 
 /* ------------------------------------------------------------------------------------------ */
 /* K9/K11  Wiener filter + statistics  (reference: convolve.c:100-237, restoration_pick.c:659) */

@@ -14,6 +14,8 @@
 // the search never leave registers.  The luma distortion's double-precision formula is evaluated
 // with round-to-nearest intrinsics in the reference's operand order (FMA contraction is disabled
 // for the whole library), which makes it IEEE-identical to the C code.
+#include <mutex>
+
 #include "common.cuh"
 #include "../../include/svt_b200.h"
 
@@ -271,17 +273,22 @@ __global__ void search_one_dual_kernel(const unsigned long long* mse0, const uns
 template <typename PIX>
 __device__ void stage_cdef_tile(uint16_t* tile, const PIX* plane, int stride, int plane_w, int plane_h, int fbr, int fbc,
                                 int nvfb, int nhfb, int bw, int bh, int vsz, int hsz) {
-    // tile origin (row 3, col 8) = first pixel of the filter block; everything not copied stays
-    // CDEF_VERY_LARGE (cdef_process.c:211-230)
+    // tile origin (row 3, col 8) = first pixel of the filter block; everything outside the copied
+    // rectangle is CDEF_VERY_LARGE (cdef_process.c:211-230).  One pass, two pixels per thread and store.
     const int yoff = 3 * (fbr != 0), xoff = 8 * (fbc != 0);
     const int ysize = vsz + 3 * (fbr + 1 < nvfb) + yoff, xsize = hsz + 8 * (fbc + 1 < nhfb) + xoff;
     (void)plane_w; (void)plane_h;
-    for (int i = threadIdx.x; i < kTileRows * kTP; i += blockDim.x) tile[i] = (uint16_t)kVeryLarge;
-    __syncthreads();
     const int py0 = fbr * bh - yoff, px0 = fbc * bw - xoff;
-    for (int i = threadIdx.x; i < ysize * xsize; i += blockDim.x) {
-        const int r = i / xsize, c = i - r * xsize;
-        tile[(3 - yoff + r) * kTP + (8 - xoff + c)] = (uint16_t)plane[(size_t)(py0 + r) * stride + px0 + c];
+    constexpr int kPairs = (64 + 16) / 2;  // columns 0..79 are the ones ever read
+    for (int i = threadIdx.x; i < kTileRows * kPairs; i += blockDim.x) {
+        const int r = i / kPairs, c = (i - r * kPairs) * 2;
+        const int rr = r - (3 - yoff), cc = c - (8 - xoff);  // cc is even, xsize is a multiple of 4: the pair is in or out together
+        uint32_t v = (uint32_t)kVeryLarge * 0x10001u;
+        if (rr >= 0 && rr < ysize && cc >= 0 && cc < xsize) {
+            const PIX* p = plane + (size_t)(py0 + rr) * stride + px0 + cc;
+            v = (uint32_t)p[0] | ((uint32_t)p[1] << 16);
+        }
+        *reinterpret_cast<uint32_t*>(tile + r * kTP + c) = v;
     }
     __syncthreads();
 }
@@ -453,70 +460,64 @@ cdef_search_kernel(SvtB200CdefFrame f, const uint8_t* __restrict__ skip8x8, cons
     }
 }
 
-// frame apply (svt_av1_cdef_frame, enc_cdef.c:284-600): per filter block strengths already chosen
+// frame apply (svt_av1_cdef_frame, enc_cdef.c:284-600): per filter block strengths already chosen,
+// directions/variances as found by cdef_dir_kernel.  One CTA per (filter block, plane), one thread per pixel.
 template <typename PIX>
 __global__ void __launch_bounds__(256)
 cdef_apply_kernel(SvtB200CdefFrame f, const uint8_t* __restrict__ skip8x8, const int8_t* __restrict__ fb_strength_idx,
-                  const int* __restrict__ y_strength, const int* __restrict__ uv_strength, PIX* out_y, PIX* out_cb, PIX* out_cr,
-                  int out_stride_y, int out_stride_c) {
+                  const int* __restrict__ y_strength, const int* __restrict__ uv_strength, const uint8_t* __restrict__ dir_in,
+                  const int* __restrict__ var_in, PIX* out_y, PIX* out_cb, PIX* out_cr, int out_stride_y, int out_stride_c) {
     __shared__ uint16_t tile[kTileRows * kTP];
     __shared__ uint8_t  s_dir[64];
     __shared__ int      s_var[64];
     __shared__ uint8_t  s_list[64];
-    __shared__ int      s_count;
+    __shared__ unsigned s_ballot[2];
     const int nhfb = (f.width + 63) >> 6, nvfb = (f.height + 63) >> 6, nfb = nhfb * nvfb;
     const int cs = f.bit_depth > 8 ? f.bit_depth - 8 : 0;
     const int w8 = (f.width + 7) >> 3, h8 = (f.height + 7) >> 3;
-    for (int fb = blockIdx.x; fb < nfb; fb += gridDim.x) {
+    for (int work = blockIdx.x; work < nfb * 3; work += gridDim.x) {
+        const int fb = work / 3, pli = work - fb * 3;
         const int fbr = fb / nhfb, fbc = fb - fbr * nhfb;
         const int sidx = fb_strength_idx[fb];
         if (sidx < 0) continue;  // uniform per CTA
-        const int ys = y_strength[sidx], us = uv_strength[sidx];
-        if (ys == 0 && us == 0) continue;
-        if (threadIdx.x == 0) {
-            int n = 0;
-            for (int by = 0; by < 8; by++)
-                for (int bx = 0; bx < 8; bx++) {
-                    const int gy = fbr * 8 + by, gx = fbc * 8 + bx;
-                    if (gy < h8 && gx < w8 && !skip8x8[gy * w8 + gx]) s_list[n++] = (uint8_t)(by * 8 + bx);
-                }
-            s_count = n;
+        const int sv = pli ? uv_strength[sidx] : y_strength[sidx];
+        const int pri = (sv / 4) << cs;
+        int sec = sv % 4;
+        sec = (sec + (sec == 3)) << cs;
+        if (!(pri || sec)) continue;
+        __syncthreads();
+        if (threadIdx.x < 64) {
+            const int  by = threadIdx.x >> 3, bx = threadIdx.x & 7, gy = fbr * 8 + by, gx = fbc * 8 + bx;
+            const bool on = gy < h8 && gx < w8 && !skip8x8[gy * w8 + gx];
+            const unsigned m = __ballot_sync(0xffffffffu, on);
+            s_dir[threadIdx.x] = dir_in[(size_t)fb * 64 + threadIdx.x];
+            s_var[threadIdx.x] = var_in[(size_t)fb * 64 + threadIdx.x];
+            if ((threadIdx.x & 31) == 0) s_ballot[threadIdx.x >> 5] = m;
         }
         __syncthreads();
-        const int count = s_count;
-        for (int pli = 0; pli < 3 && count; pli++) {
-            const int dec = pli ? 1 : 0;
-            const PIX* rec = (const PIX*)(pli == 0 ? f.recon_y : (pli == 1 ? f.recon_cb : f.recon_cr));
-            PIX* out = pli == 0 ? out_y : (pli == 1 ? out_cb : out_cr);
-            const int rstride = pli ? f.recon_stride_c : f.recon_stride_y, ostride = pli ? out_stride_c : out_stride_y;
-            const int pw = f.width >> dec, ph = f.height >> dec, fbs = 64 >> dec;
-            const int hsz = min(fbs, pw - fbc * fbs), vsz = min(fbs, ph - fbr * fbs);
-            stage_cdef_tile<PIX>(tile, rec, rstride, pw, ph, fbr, fbc, nvfb, nhfb, fbs, fbs, vsz, hsz);
-            if (pli == 0) {
-                if ((int)threadIdx.x < count) {
-                    const int b = s_list[threadIdx.x];
-                    int var;
-                    s_dir[b] = (uint8_t)cdef_find_dir_dev(tile + (3 + 8 * (b >> 3)) * kTP + 8 + 8 * (b & 7), kTP, &var, cs);
-                    s_var[b] = var;
-                }
-                __syncthreads();
-            }
-            const int sv = pli ? us : ys;
-            const int pri = (sv / 4) << cs;
-            int sec = sv % 4;
-            sec = (sec + (sec == 3)) << cs;
-            const int bsz = 8 >> dec, damping = f.damping + cs - (pli != 0);
-            if (pri || sec)
-                for (int idx = threadIdx.x; idx < count * bsz * bsz; idx += blockDim.x) {  // one thread per pixel
-                    const int lg = 3 - dec, bi = idx >> (2 * lg), ri = (idx >> lg) & (bsz - 1), j = idx & (bsz - 1);
-                    const int b = s_list[bi], by = b >> 3, bx = b & 7;
-                    const int t = pli ? pri : cdef_adjust_strength(pri, s_var[b]);
-                    const int d = pri ? s_dir[b] : 0;
-                    const uint16_t* in = tile + (3 + bsz * by + ri) * kTP + 8 + bsz * bx + j;
-                    out[(size_t)(fbr * fbs + bsz * by + ri) * ostride + fbc * fbs + bsz * bx + j] =
-                        (PIX)cdef_filter_px(in, kTP, t, sec, d, damping, damping, cs);
-                }
-            __syncthreads();
+        const unsigned m0 = s_ballot[0], m1 = s_ballot[1];
+        const int count = __popc(m0) + __popc(m1);
+        if (count == 0) continue;
+        if (threadIdx.x < 64) {
+            const unsigned mine = threadIdx.x < 32 ? m0 : m1, lane = threadIdx.x & 31;
+            if ((mine >> lane) & 1) s_list[(threadIdx.x < 32 ? 0 : __popc(m0)) + __popc(mine & ((1u << lane) - 1))] = (uint8_t)threadIdx.x;
+        }
+        const int dec = pli ? 1 : 0;
+        const PIX* rec = (const PIX*)(pli == 0 ? f.recon_y : (pli == 1 ? f.recon_cb : f.recon_cr));
+        PIX* out = pli == 0 ? out_y : (pli == 1 ? out_cb : out_cr);
+        const int rstride = pli ? f.recon_stride_c : f.recon_stride_y, ostride = pli ? out_stride_c : out_stride_y;
+        const int pw = f.width >> dec, ph = f.height >> dec, fbs = 64 >> dec;
+        const int hsz = min(fbs, pw - fbc * fbs), vsz = min(fbs, ph - fbr * fbs);
+        stage_cdef_tile<PIX>(tile, rec, rstride, pw, ph, fbr, fbc, nvfb, nhfb, fbs, fbs, vsz, hsz);  // ends with a barrier
+        const int bsz = 8 >> dec, damping = f.damping + cs - (pli != 0);
+        for (int idx = threadIdx.x; idx < count * bsz * bsz; idx += blockDim.x) {
+            const int lg = 3 - dec, bi = idx >> (2 * lg), ri = (idx >> lg) & (bsz - 1), j = idx & (bsz - 1);
+            const int b = s_list[bi], by = b >> 3, bx = b & 7;
+            const int t = pli ? pri : cdef_adjust_strength(pri, s_var[b]);
+            const int d = pri ? s_dir[b] : 0;
+            const uint16_t* in = tile + (3 + bsz * by + ri) * kTP + 8 + bsz * bx + j;
+            out[(size_t)(fbr * fbs + bsz * by + ri) * ostride + fbc * fbs + bsz * bx + j] =
+                (PIX)cdef_filter_px(in, kTP, t, sec, d, damping, damping, cs);
         }
     }
 }
@@ -692,20 +693,44 @@ extern "C" int svt_b200_cdef_search_frame_dev(const SvtB200CdefFrame* frame, con
     return SVT_B200_OK;
 }
 
+static uint8_t*   g_cdef_dir = nullptr;  // direction/variance scratch for apply calls that do not bring their own
+static int32_t*   g_cdef_var = nullptr;
+static size_t     g_cdef_cap = 0;
+static std::mutex g_cdef_mu;
+
 extern "C" int svt_b200_cdef_apply_frame_dev(const SvtB200CdefFrame* frame, const uint8_t* d_skip8x8, const int8_t* d_fb_strength_idx,
-                                             const int* d_y_strength, const int* d_uv_strength, void* d_out_y, void* d_out_cb,
-                                             void* d_out_cr, int out_stride_y, int out_stride_c, void* stream) {
+                                             const int* d_y_strength, const int* d_uv_strength, const uint8_t* d_dir,
+                                             const int32_t* d_var, void* d_out_y, void* d_out_cb, void* d_out_cr, int out_stride_y,
+                                             int out_stride_c, void* stream) {
     require_ready();
-    if (!frame) return SVT_B200_ERR_BAD_ARG;
+    if (!frame || ((d_dir == nullptr) != (d_var == nullptr))) return SVT_B200_ERR_BAD_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
     const int nfb = ((frame->width + 63) >> 6) * ((frame->height + 63) >> 6);
+    const int nblk = ((frame->width + 7) >> 3) * ((frame->height + 7) >> 3);
+    std::unique_lock<std::mutex> lk(g_cdef_mu, std::defer_lock);
+    if (!d_dir) {  // calls that share the scratch are serialised on the host (the stream orders the device side)
+        lk.lock();
+        if ((size_t)nfb > g_cdef_cap) {
+            if (g_cdef_dir) { cudaFree(g_cdef_dir); cudaFree(g_cdef_var); }
+            g_cdef_cap = (size_t)nfb * 2;
+            B200_CUDA_CHECK(cudaMalloc(&g_cdef_dir, g_cdef_cap * 64));
+            B200_CUDA_CHECK(cudaMalloc(&g_cdef_var, g_cdef_cap * 64 * 4));
+        }
+        if (frame->bit_depth > 8) cdef_dir_kernel<uint16_t><<<(nblk + 127) / 128, 128, 0, st>>>(*frame, d_skip8x8, g_cdef_dir, g_cdef_var);
+        else cdef_dir_kernel<uint8_t><<<(nblk + 127) / 128, 128, 0, st>>>(*frame, d_skip8x8, g_cdef_dir, g_cdef_var);
+        B200_LAUNCH_CHECK();
+        d_dir = g_cdef_dir;
+        d_var = g_cdef_var;
+    }
     if (frame->bit_depth > 8)
-        cdef_apply_kernel<uint16_t><<<grid_for(nfb, 4), 256, 0, (cudaStream_t)stream>>>(*frame, d_skip8x8, d_fb_strength_idx, d_y_strength,
-                                                                                     d_uv_strength, (uint16_t*)d_out_y, (uint16_t*)d_out_cb,
-                                                                                     (uint16_t*)d_out_cr, out_stride_y, out_stride_c);
+        cdef_apply_kernel<uint16_t><<<grid_for((long long)nfb * 3, 6), 256, 0, st>>>(*frame, d_skip8x8, d_fb_strength_idx, d_y_strength, d_uv_strength,
+                                                                               d_dir, d_var, (uint16_t*)d_out_y, (uint16_t*)d_out_cb,
+                                                                               (uint16_t*)d_out_cr, out_stride_y, out_stride_c);
     else
-        cdef_apply_kernel<uint8_t><<<grid_for(nfb, 4), 256, 0, (cudaStream_t)stream>>>(*frame, d_skip8x8, d_fb_strength_idx, d_y_strength,
-                                                                                    d_uv_strength, (uint8_t*)d_out_y, (uint8_t*)d_out_cb,
-                                                                                    (uint8_t*)d_out_cr, out_stride_y, out_stride_c);
+        cdef_apply_kernel<uint8_t><<<grid_for((long long)nfb * 3, 6), 256, 0, st>>>(*frame, d_skip8x8, d_fb_strength_idx, d_y_strength, d_uv_strength,
+                                                                              d_dir, d_var, (uint8_t*)d_out_y, (uint8_t*)d_out_cb,
+                                                                              (uint8_t*)d_out_cr, out_stride_y, out_stride_c);
     B200_LAUNCH_CHECK();
+    if (lk.owns_lock()) B200_CUDA_CHECK(cudaStreamSynchronize(st));  // the scratch is free again when the call returns
     return SVT_B200_OK;
 }

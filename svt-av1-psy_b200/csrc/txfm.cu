@@ -5,10 +5,11 @@
 // 16 transform types, 8/10/12-bit.  The 2-D configuration table (flips, per-pass kernel, cos_bit,
 // shifts) is dumped from the reference (txfm_cfg.inc); the 1-D networks are txfm_graphs.inc.
 //
-// B200 mapping: one thread TEAM per transform block -- a warp for blocks of <= 256 coefficients
-// (8 blocks per CTA), the whole 256-thread CTA above.  The block lives in two ping-pong shared-memory
-// planes in element-major order with an odd pitch, so the column pass, the transposing hand-over and
-// the row pass are all bank-conflict free; residual loads / coefficient stores are coalesced rows.
+// B200 mapping: a team of max(W,H) threads per transform block (4, 8, 16, 32 or 64: the block's
+// "team class"), one thread per column in the column pass and one per row in the row pass, each
+// running the generated straight-line network on its vector in registers (txfm_tables.cuh).  The
+// block sits in shared memory in element-major order with an odd pitch, so the passes and the
+// transposing hand-over are bank-conflict free; residual loads / coefficient stores are coalesced rows.
 #include "txfm_tables.cuh"
 #include "../../include/svt_b200.h"
 
@@ -18,30 +19,6 @@ static TxCfg h_txcfg[19][16];
 const TxCfg& host_txcfg(int size, int type) { return h_txcfg[size][type]; }
 
 void txfm_tables_init() {
-    // graph directory: walk the .inc once more, this time only for the BEGIN markers
-    struct Ent { int tag, n, st; };
-    enum { FDCT4, FDCT8, FDCT16, FDCT32, FDCT64, FADST8, FADST16, IDCT4, IDCT8, IDCT16, IDCT32, IDCT64, IADST8, IADST16 };
-    static const Ent ents[] = {
-#define TXG_BEGIN(tag, n, st) {tag, n, st},
-#define TXG_END(tag)
-#define TXG_NODE(...)
-#include "txfm_graphs.inc"
-#undef TXG_BEGIN
-#undef TXG_END
-#undef TXG_NODE
-    };
-    static const int tag2type[14][2] = {{0, TT_DCT4}, {0, TT_DCT8}, {0, TT_DCT16}, {0, TT_DCT32}, {0, TT_DCT64},
-                                        {0, TT_ADST8}, {0, TT_ADST16}, {1, TT_DCT4}, {1, TT_DCT8}, {1, TT_DCT16},
-                                        {1, TT_DCT32}, {1, TT_DCT64}, {1, TT_ADST8}, {1, TT_ADST16}};
-    GraphDesc gd[2][TT_TYPES];
-    memset(gd, 0, sizeof(gd));
-    int off = 0;
-    for (const Ent& e : ents) {
-        gd[tag2type[e.tag][0]][tag2type[e.tag][1]] = GraphDesc{off, e.n, e.st};
-        off += e.n * e.st;
-    }
-    B200_CUDA_CHECK(cudaMemcpyToSymbol(c_graph, gd, sizeof(gd)));
-
     memset(h_txcfg, 0, sizeof(h_txcfg));
     static int32_t cosv[7][64], sinv[7][5];
 #define TXC(sz, ty, v, fud, flr, fs0, fs1, fs2, fcbc, fcbr, ftc, ftr, iud, ilr, is0, is1, icbc, icbr, itc, itr) \
@@ -67,14 +44,14 @@ __host__ __device__ inline int rect_log_ratio(int w, int h) {  // get_rect_tx_lo
 // forward
 // ------------------------------------------------------------------------------------------------
 template <int TEAM>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(TEAM >= 64 ? 64 : 256)
 fwd_txfm_kernel(const int16_t* __restrict__ src_base, int32_t* __restrict__ dst_base,
-                const SvtB200FwdTxfmItem* __restrict__ items, int n_items, int plane_ints) {
+                const SvtB200FwdTxfmItem* __restrict__ items, int n_items) {
     extern __shared__ __align__(16) int32_t tsm[];
-    constexpr int TEAMS = 256 / TEAM;
+    constexpr int THREADS = TEAM >= 64 ? 64 : 256, TEAMS = THREADS / TEAM, PLANE = TEAM * (TEAM + 1);
     const int     team  = threadIdx.x / TEAM, tid = threadIdx.x % TEAM;
-    int32_t*      A     = tsm + (size_t)team * 2 * plane_ints;
-    int32_t*      B     = A + plane_ints;
+    int32_t*      A     = tsm + (size_t)team * 2 * PLANE;
+    int32_t*      B     = A + PLANE;
 
     for (int it = blockIdx.x * TEAMS + team; it < n_items; it += gridDim.x * TEAMS) {
         const SvtB200FwdTxfmItem item = items[it];
@@ -91,20 +68,21 @@ fwd_txfm_kernel(const int16_t* __restrict__ src_base, int32_t* __restrict__ dst_
             A[r * P1 + c] = round_shift_arr((int32_t)src[(size_t)rr * item.src_stride + c], -cfg.f_s0);
         }
         team_sync<TEAM>();
-        int32_t* R = txfm_pass_1d<TEAM>(cfg.f_tc, 0, A, B, H, W, P1, cfg.f_cbc, 0, tid);
-        int32_t* O = (R == A) ? B : A;
+        txfm_pass_1d<TEAM, false>(cfg.f_tc, A, H, W, P1, cfg.f_cbc, 0, tid);  // columns: vector v = column v
+        team_sync<TEAM>();
         // round-shift, optional left/right flip, hand over transposed (element = column)
         for (int idx = tid; idx < W * H; idx += TEAM) {
             const int r = idx >> lgW, c = idx & (W - 1);
             const int cc = cfg.f_lr ? (W - 1 - c) : c;
-            O[cc * P2 + r] = round_shift_arr(R[r * P1 + c], -cfg.f_s1);
+            B[cc * P2 + r] = round_shift_arr(A[r * P1 + c], -cfg.f_s1);
         }
         team_sync<TEAM>();
-        int32_t* R2 = txfm_pass_1d<TEAM>(cfg.f_tr, 0, O, R, W, H, P2, cfg.f_cbr, 0, tid);
+        txfm_pass_1d<TEAM, false>(cfg.f_tr, B, W, H, P2, cfg.f_cbr, 0, tid);  // rows: vector v = row v
+        team_sync<TEAM>();
         const int rect = rect_log_ratio(W, H);
         for (int idx = tid; idx < W * H; idx += TEAM) {
             const int r = idx >> lgW, c = idx & (W - 1);
-            int32_t   v = round_shift_arr(R2[c * P2 + r], -cfg.f_s2);
+            int32_t   v = round_shift_arr(B[c * P2 + r], -cfg.f_s2);
             if (rect == 1 || rect == -1) v = round_shift64((long long)v * kNewSqrt2, 12);
             if (item.reserved & 1) {  // packed output: keep the top-left min(W,32) x min(H,32) (svt_handle_transform64x64 repack, transforms.c:2374)
                 const int Wp = W > 32 ? 32 : W, Hp = H > 32 ? 32 : H;
@@ -120,14 +98,14 @@ fwd_txfm_kernel(const int16_t* __restrict__ src_base, int32_t* __restrict__ dst_
 // inverse + reconstruction
 // ------------------------------------------------------------------------------------------------
 template <int TEAM, typename PIX>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(TEAM >= 64 ? 64 : 256)
 inv_txfm_kernel(const int32_t* __restrict__ coef_base, const PIX* __restrict__ pred_base, PIX* __restrict__ recon_base,
-                const SvtB200InvTxfmItem* __restrict__ items, int n_items, int plane_ints) {
+                const SvtB200InvTxfmItem* __restrict__ items, int n_items) {
     extern __shared__ __align__(16) int32_t tsm[];
-    constexpr int TEAMS = 256 / TEAM;
+    constexpr int THREADS = TEAM >= 64 ? 64 : 256, TEAMS = THREADS / TEAM, PLANE = TEAM * (TEAM + 1);
     const int     team  = threadIdx.x / TEAM, tid = threadIdx.x % TEAM;
-    int32_t*      A     = tsm + (size_t)team * 2 * plane_ints;
-    int32_t*      B     = A + plane_ints;
+    int32_t*      A     = tsm + (size_t)team * 2 * PLANE;
+    int32_t*      B     = A + PLANE;
 
     for (int it = blockIdx.x * TEAMS + team; it < n_items; it += gridDim.x * TEAMS) {
         const SvtB200InvTxfmItem item = items[it];
@@ -150,15 +128,16 @@ inv_txfm_kernel(const int32_t* __restrict__ coef_base, const PIX* __restrict__ p
             A[c * P1 + r] = clamp_bits(v, row_clamp);
         }
         team_sync<TEAM>();
-        int32_t* R = txfm_pass_1d<TEAM>(cfg.i_tr, 1, A, B, W, H, P1, cfg.i_cbr, opt_row, tid);
-        int32_t* O = (R == A) ? B : A;
+        txfm_pass_1d<TEAM, true>(cfg.i_tr, A, W, H, P1, cfg.i_cbr, opt_row, tid);
+        team_sync<TEAM>();
         for (int idx = tid; idx < W * H; idx += TEAM) {
             const int r = idx >> lgW, c = idx & (W - 1);
             const int cs = cfg.i_lr ? (W - 1 - c) : c;
-            O[r * P2 + c] = clamp_bits(round_shift_arr(R[cs * P1 + r], -cfg.i_s0), col_clamp);
+            B[r * P2 + c] = clamp_bits(round_shift_arr(A[cs * P1 + r], -cfg.i_s0), col_clamp);
         }
         team_sync<TEAM>();
-        int32_t* R2 = txfm_pass_1d<TEAM>(cfg.i_tc, 1, O, R, H, W, P2, cfg.i_cbc, opt_col, tid);
+        txfm_pass_1d<TEAM, true>(cfg.i_tc, B, H, W, P2, cfg.i_cbc, opt_col, tid);
+        team_sync<TEAM>();
         const PIX* pr = pred_base + item.pred_off;
         PIX*       pw = recon_base + item.recon_off;
         const long long int_max = (1ll << (7 + bd)) - 1 + (914ll << (bd - 7));  // check_range, inv_transforms.c:2401
@@ -166,7 +145,7 @@ inv_txfm_kernel(const int32_t* __restrict__ coef_base, const PIX* __restrict__ p
         for (int idx = tid; idx < W * H; idx += TEAM) {
             const int r = idx >> lgW, c = idx & (W - 1);
             const int rs = cfg.i_ud ? (H - 1 - r) : r;
-            long long t  = (long long)round_shift_arr(R2[rs * P2 + c], -cfg.i_s1);
+            long long t  = (long long)round_shift_arr(B[rs * P2 + c], -cfg.i_s1);
             t            = t < -int_max - 1 ? -int_max - 1 : (t > int_max ? int_max : t);
             int p        = (int)pr[(size_t)r * item.pred_stride + c] + (int)t;
             p            = p < 0 ? 0 : (p > pix_max ? pix_max : p);
@@ -176,10 +155,10 @@ inv_txfm_kernel(const int32_t* __restrict__ coef_base, const PIX* __restrict__ p
     }
 }
 
-static inline int plane_ints_for(int sz) {
-    const int W = tx_w(sz), H = tx_h(sz);
-    const int a = H * (W + 1), b = W * (H + 1);
-    return ((a > b ? a : b) + 3) & ~3;
+// team class of a transform size: log2(max(W,H)) - 2
+static inline int tx_class(int sz) {
+    const int m = tx_w(sz) > tx_h(sz) ? tx_w(sz) : tx_h(sz);
+    return m == 4 ? 0 : (m == 8 ? 1 : (m == 16 ? 2 : (m == 32 ? 3 : 4)));
 }
 
 template <typename K>
@@ -187,38 +166,50 @@ static void set_smem_attr(K kernel, size_t smem) {
     if (smem > 48 * 1024) B200_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 }
 
-void launch_fwd_txfm(const int16_t* d_src, int32_t* d_dst, const SvtB200FwdTxfmItem* d_items, int n, int max_tx_size_plane,
-                     bool small, cudaStream_t st) {
-    if (n <= 0) return;
-    if (small) {
-        const size_t smem = (size_t)8 * 2 * max_tx_size_plane * 4;
-        fwd_txfm_kernel<32><<<grid_for((n + 7) / 8, 8), 256, smem, st>>>(d_src, d_dst, d_items, n, max_tx_size_plane);
-    } else {
-        const size_t smem = (size_t)2 * max_tx_size_plane * 4;
-        static bool attr = false;
-        if (!attr) { set_smem_attr(fwd_txfm_kernel<256>, 64 * 1024); attr = true; }
-        fwd_txfm_kernel<256><<<grid_for(n, smem > 24 * 1024 ? 4 : 8), 256, smem, st>>>(d_src, d_dst, d_items, n, max_tx_size_plane);
-    }
+template <int TEAM>
+static void launch_fwd_class(const int16_t* d_src, int32_t* d_dst, const SvtB200FwdTxfmItem* d_items, int n, cudaStream_t st) {
+    constexpr int    THREADS = TEAM >= 64 ? 64 : 256, TEAMS = THREADS / TEAM;
+    constexpr size_t smem = (size_t)TEAMS * 2 * TEAM * (TEAM + 1) * 4;
+    static bool attr = false;
+    if (!attr) { set_smem_attr(fwd_txfm_kernel<TEAM>, smem); attr = true; }
+    const int per_sm = (int)((200 * 1024) / (smem + 1024)) < 2048 / THREADS ? (int)((200 * 1024) / (smem + 1024)) : 2048 / THREADS;
+    fwd_txfm_kernel<TEAM><<<grid_for((n + TEAMS - 1) / TEAMS, per_sm), THREADS, smem, st>>>(d_src, d_dst, d_items, n);
     B200_LAUNCH_CHECK();
 }
+void launch_fwd_txfm(const int16_t* d_src, int32_t* d_dst, const SvtB200FwdTxfmItem* d_items, int n, int cls, cudaStream_t st) {
+    if (n <= 0) return;
+    switch (cls) {
+    case 0: launch_fwd_class<4>(d_src, d_dst, d_items, n, st); break;
+    case 1: launch_fwd_class<8>(d_src, d_dst, d_items, n, st); break;
+    case 2: launch_fwd_class<16>(d_src, d_dst, d_items, n, st); break;
+    case 3: launch_fwd_class<32>(d_src, d_dst, d_items, n, st); break;
+    default: launch_fwd_class<64>(d_src, d_dst, d_items, n, st); break;
+    }
+}
 
+template <int TEAM, typename PIX>
+static void launch_inv_class(const int32_t* d_coef, const PIX* d_pred, PIX* d_recon, const SvtB200InvTxfmItem* d_items, int n,
+                             cudaStream_t st) {
+    constexpr int    THREADS = TEAM >= 64 ? 64 : 256, TEAMS = THREADS / TEAM;
+    constexpr size_t smem = (size_t)TEAMS * 2 * TEAM * (TEAM + 1) * 4;
+    static bool attr = false;
+    if (!attr) { set_smem_attr(inv_txfm_kernel<TEAM, PIX>, smem); attr = true; }
+    const int per_sm = (int)((200 * 1024) / (smem + 1024)) < 2048 / THREADS ? (int)((200 * 1024) / (smem + 1024)) : 2048 / THREADS;
+    inv_txfm_kernel<TEAM, PIX><<<grid_for((n + TEAMS - 1) / TEAMS, per_sm), THREADS, smem, st>>>(d_coef, d_pred, d_recon, d_items, n);
+    B200_LAUNCH_CHECK();
+}
 template <typename PIX>
-void launch_inv_txfm(const int32_t* d_coef, const PIX* d_pred, PIX* d_recon, const SvtB200InvTxfmItem* d_items, int n,
-                     int plane, bool small, cudaStream_t st) {
+void launch_inv_txfm(const int32_t* d_coef, const PIX* d_pred, PIX* d_recon, const SvtB200InvTxfmItem* d_items, int n, int cls,
+                     cudaStream_t st) {
     if (n <= 0) return;
-    if (small) {
-        const size_t smem = (size_t)8 * 2 * plane * 4;
-        inv_txfm_kernel<32, PIX><<<grid_for((n + 7) / 8, 8), 256, smem, st>>>(d_coef, d_pred, d_recon, d_items, n, plane);
-    } else {
-        const size_t smem = (size_t)2 * plane * 4;
-        static bool attr = false;
-        if (!attr) { set_smem_attr(inv_txfm_kernel<256, PIX>, 64 * 1024); attr = true; }
-        inv_txfm_kernel<256, PIX><<<grid_for(n, smem > 24 * 1024 ? 4 : 8), 256, smem, st>>>(d_coef, d_pred, d_recon, d_items, n, plane);
+    switch (cls) {
+    case 0: launch_inv_class<4, PIX>(d_coef, d_pred, d_recon, d_items, n, st); break;
+    case 1: launch_inv_class<8, PIX>(d_coef, d_pred, d_recon, d_items, n, st); break;
+    case 2: launch_inv_class<16, PIX>(d_coef, d_pred, d_recon, d_items, n, st); break;
+    case 3: launch_inv_class<32, PIX>(d_coef, d_pred, d_recon, d_items, n, st); break;
+    default: launch_inv_class<64, PIX>(d_coef, d_pred, d_recon, d_items, n, st); break;
     }
-    B200_LAUNCH_CHECK();
 }
-
-static inline bool is_small(int sz) { return tx_w(sz) * tx_h(sz) <= SVT_B200_TXFM_SMALL_MAX_COEFFS; }
 
 }  // namespace b200
 
@@ -230,29 +221,34 @@ extern "C" int svt_b200_txfm_valid(int tx_size, int tx_type) {
     return host_txcfg(tx_size, tx_type).valid;
 }
 
+extern "C" int svt_b200_txfm_team_class(int tx_size) { return (tx_size < 0 || tx_size >= 19) ? -1 : tx_class(tx_size); }
+
 extern "C" int svt_b200_fwd_txfm_batch_dev(const int16_t* d_residual, int32_t* d_coeff, const SvtB200FwdTxfmItem* d_items,
-                                           int n_small, int n_large, int max_small_tx_size, int max_large_tx_size,
-                                           void* stream) {
+                                           const int n_per_class[SVT_B200_TXFM_CLASSES], void* stream) {
     require_ready();
-    if (n_small > 0) launch_fwd_txfm(d_residual, d_coeff, d_items, n_small, plane_ints_for(max_small_tx_size), true, (cudaStream_t)stream);
-    if (n_large > 0)
-        launch_fwd_txfm(d_residual, d_coeff, d_items + n_small, n_large, plane_ints_for(max_large_tx_size), false, (cudaStream_t)stream);
+    if (!n_per_class) return SVT_B200_ERR_BAD_ARG;
+    int first = 0;
+    for (int c = 0; c < SVT_B200_TXFM_CLASSES; c++) {
+        if (n_per_class[c] < 0) return SVT_B200_ERR_BAD_ARG;
+        launch_fwd_txfm(d_residual, d_coeff, d_items + first, n_per_class[c], c, (cudaStream_t)stream);
+        first += n_per_class[c];
+    }
     return SVT_B200_OK;
 }
 
 extern "C" int svt_b200_inv_txfm_batch_dev(const int32_t* d_coeff, const void* d_pred, void* d_recon,
-                                           const SvtB200InvTxfmItem* d_items, int n_small, int n_large,
-                                           int max_small_tx_size, int max_large_tx_size, int pixel_bytes, void* stream) {
+                                           const SvtB200InvTxfmItem* d_items, const int n_per_class[SVT_B200_TXFM_CLASSES],
+                                           int pixel_bytes, void* stream) {
     require_ready();
+    if (!n_per_class || (pixel_bytes != 1 && pixel_bytes != 2)) return SVT_B200_ERR_BAD_ARG;
     cudaStream_t st = (cudaStream_t)stream;
-    if (pixel_bytes == 1) {
-        if (n_small > 0) launch_inv_txfm<uint8_t>(d_coeff, (const uint8_t*)d_pred, (uint8_t*)d_recon, d_items, n_small, plane_ints_for(max_small_tx_size), true, st);
-        if (n_large > 0) launch_inv_txfm<uint8_t>(d_coeff, (const uint8_t*)d_pred, (uint8_t*)d_recon, d_items + n_small, n_large, plane_ints_for(max_large_tx_size), false, st);
-    } else if (pixel_bytes == 2) {
-        if (n_small > 0) launch_inv_txfm<uint16_t>(d_coeff, (const uint16_t*)d_pred, (uint16_t*)d_recon, d_items, n_small, plane_ints_for(max_small_tx_size), true, st);
-        if (n_large > 0) launch_inv_txfm<uint16_t>(d_coeff, (const uint16_t*)d_pred, (uint16_t*)d_recon, d_items + n_small, n_large, plane_ints_for(max_large_tx_size), false, st);
-    } else
-        return SVT_B200_ERR_BAD_ARG;
+    int first = 0;
+    for (int c = 0; c < SVT_B200_TXFM_CLASSES; c++) {
+        if (n_per_class[c] < 0) return SVT_B200_ERR_BAD_ARG;
+        if (pixel_bytes == 1) launch_inv_txfm<uint8_t>(d_coeff, (const uint8_t*)d_pred, (uint8_t*)d_recon, d_items + first, n_per_class[c], c, st);
+        else launch_inv_txfm<uint16_t>(d_coeff, (const uint16_t*)d_pred, (uint16_t*)d_recon, d_items + first, n_per_class[c], c, st);
+        first += n_per_class[c];
+    }
     return SVT_B200_OK;
 }
 
@@ -277,8 +273,7 @@ extern "C" void svt_b200_fwd_txfm2d(int16_t* input, int32_t* output, uint32_t in
     it->tx_size = (uint8_t)tx_size;
     it->tx_type = (uint8_t)tx_type;
     l->h2d(0, in_end);
-    const bool small = is_small(tx_size);
-    launch_fwd_txfm(l->d<int16_t>(o_src), l->d<int32_t>(o_dst), l->d<SvtB200FwdTxfmItem>(o_it), 1, plane_ints_for(tx_size), small, l->stream);
+    launch_fwd_txfm(l->d<int16_t>(o_src), l->d<int32_t>(o_dst), l->d<SvtB200FwdTxfmItem>(o_it), 1, tx_class(tx_size), l->stream);
     l->d2h(o_dst, (size_t)W * H * 4);
     l->sync();
     memcpy(output, l->h<int32_t>(o_dst), (size_t)W * H * 4);
@@ -308,7 +303,7 @@ extern "C" void svt_b200_inv_txfm2d_add(const int32_t* input, uint16_t* output_r
     it->bd = (uint8_t)bd;
     l->h2d(0, in_end);
     launch_inv_txfm<uint16_t>(l->d<int32_t>(o_in), l->d<uint16_t>(o_pred), l->d<uint16_t>(o_out), l->d<SvtB200InvTxfmItem>(o_it), 1,
-                              plane_ints_for(tx_size), is_small(tx_size), l->stream);
+                              tx_class(tx_size), l->stream);
     l->d2h(o_out, (size_t)W * H * 2);
     l->sync();
     for (int r = 0; r < H; r++) memcpy(output_w + (size_t)r * stride_w, l->h<uint16_t>(o_out) + r * W, W * 2);
@@ -325,26 +320,16 @@ extern "C" int svt_b200_fwd_txfm_batch_host(const int16_t* residual, size_t resi
     size_t o_dst = l->alloc(coeff_elems * 4);
     memcpy(l->h<int16_t>(o_src), residual, residual_elems * 2);
     SvtB200FwdTxfmItem* hi = l->h<SvtB200FwdTxfmItem>(o_it);
-    int ns = 0, nl = 0, ps_max = 0, pl_max = 0;
+    int cnt[SVT_B200_TXFM_CLASSES] = {0, 0, 0, 0, 0}, pos[SVT_B200_TXFM_CLASSES];
     for (int i = 0; i < n_items; i++) {
         if (items[i].tx_size >= 19 || !host_txcfg(items[i].tx_size, items[i].tx_type).valid) return SVT_B200_ERR_BAD_ARG;
-        if (is_small(items[i].tx_size)) ns++;
+        cnt[tx_class(items[i].tx_size)]++;
     }
-    int ps = 0, pl = ns;
-    for (int i = 0; i < n_items; i++) {
-        const int sz = items[i].tx_size, pi = plane_ints_for(sz);
-        if (is_small(sz)) {
-            hi[ps++] = items[i];
-            if (pi > ps_max) ps_max = pi;
-        } else {
-            hi[pl++] = items[i];
-            nl++;
-            if (pi > pl_max) pl_max = pi;
-        }
-    }
+    for (int c = 0, first = 0; c < SVT_B200_TXFM_CLASSES; first += cnt[c], c++) pos[c] = first;
+    for (int i = 0; i < n_items; i++) hi[pos[tx_class(items[i].tx_size)]++] = items[i];
     l->h2d(0, in_end);
-    if (ns) launch_fwd_txfm(l->d<int16_t>(o_src), l->d<int32_t>(o_dst), l->d<SvtB200FwdTxfmItem>(o_it), ns, ps_max, true, l->stream);
-    if (nl) launch_fwd_txfm(l->d<int16_t>(o_src), l->d<int32_t>(o_dst), l->d<SvtB200FwdTxfmItem>(o_it) + ns, nl, pl_max, false, l->stream);
+    for (int c = 0, first = 0; c < SVT_B200_TXFM_CLASSES; first += cnt[c], c++)
+        launch_fwd_txfm(l->d<int16_t>(o_src), l->d<int32_t>(o_dst), l->d<SvtB200FwdTxfmItem>(o_it) + first, cnt[c], c, l->stream);
     l->d2h(o_dst, coeff_elems * 4);
     l->sync();
     // only the regions the items cover were written; copy those back
@@ -378,7 +363,7 @@ extern "C" void svt_b200_inv_txfm_add_8bit(const int32_t* dqcoeff, uint8_t* dst_
     it->bd = 8;
     l->h2d(0, in_end);
     launch_inv_txfm<uint8_t>(l->d<int32_t>(o_in), l->d<uint8_t>(o_pred), l->d<uint8_t>(o_out), l->d<SvtB200InvTxfmItem>(o_it), 1,
-                             plane_ints_for(tx_size), is_small(tx_size), l->stream);
+                             tx_class(tx_size), l->stream);
     l->d2h(o_out, (size_t)W * H);
     l->sync();
     for (int r = 0; r < H; r++) memcpy(dst_w + (size_t)r * stride_w, l->h<uint8_t>(o_out) + r * W, W);

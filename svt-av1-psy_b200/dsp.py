@@ -126,7 +126,12 @@ def sad_search_batch_host(src_plane, ref_plane, items):
 TX_W = [4, 8, 16, 32, 64, 4, 8, 8, 16, 16, 32, 32, 64, 4, 16, 8, 32, 16, 64]
 TX_H = [4, 8, 16, 32, 64, 8, 4, 16, 8, 32, 16, 64, 32, 16, 4, 32, 8, 64, 16]
 TX_NAME = ["%dx%d" % (w, h) for w, h in zip(TX_W, TX_H)]
-TXFM_SMALL_MAX_COEFFS = 256  # SVT_B200_TXFM_SMALL_MAX_COEFFS
+TXFM_CLASSES = 5  # SVT_B200_TXFM_CLASSES
+
+
+def txfm_team_class(tx_size):
+    """log2(max(W, H)) - 2: the order key of the transform batch calls (svt_b200_txfm_team_class)."""
+    return {4: 0, 8: 1, 16: 2, 32: 3, 64: 4}[max(TX_W[tx_size], TX_H[tx_size])]
 
 FWD_ITEM_DTYPE = np.dtype([("src_off", "<u8"), ("dst_off", "<u8"), ("src_stride", "<u4"), ("tx_size", "u1"),
                            ("tx_type", "u1"), ("reserved", "<u2")])
@@ -145,9 +150,11 @@ lib.svt_b200_inv_txfm_add_8bit.argtypes = [vp, vp, ct.c_int32, vp, ct.c_int32, c
 lib.svt_b200_inv_txfm_add_8bit.restype = None
 lib.svt_b200_fwd_txfm_batch_host.argtypes = [vp, ct.c_size_t, vp, ct.c_size_t, vp, ct.c_int]
 lib.svt_b200_fwd_txfm_batch_host.restype = ct.c_int
-lib.svt_b200_fwd_txfm_batch_dev.argtypes = [vp, vp, vp, ct.c_int, ct.c_int, ct.c_int, ct.c_int, vp]
+lib.svt_b200_fwd_txfm_batch_dev.argtypes = [vp, vp, vp, ct.POINTER(ct.c_int), vp]
 lib.svt_b200_fwd_txfm_batch_dev.restype = ct.c_int
-lib.svt_b200_inv_txfm_batch_dev.argtypes = [vp, vp, vp, vp, ct.c_int, ct.c_int, ct.c_int, ct.c_int, ct.c_int, vp]
+lib.svt_b200_inv_txfm_batch_dev.argtypes = [vp, vp, vp, vp, ct.POINTER(ct.c_int), ct.c_int, vp]
+lib.svt_b200_txfm_team_class.argtypes = [ct.c_int]
+lib.svt_b200_txfm_team_class.restype = ct.c_int
 lib.svt_b200_inv_txfm_batch_dev.restype = ct.c_int
 
 
@@ -312,7 +319,7 @@ lib.svt_b200_search_one_dual.argtypes = [vp, vp, ct.c_int, vp, ct.c_int, ct.c_in
 lib.svt_b200_search_one_dual.restype = ct.c_uint64
 lib.svt_b200_cdef_search_frame_dev.argtypes = [ct.POINTER(CdefFrame), vp, vp, vp, ct.c_int, vp, vp, vp, vp]
 lib.svt_b200_cdef_search_frame_dev.restype = ct.c_int
-lib.svt_b200_cdef_apply_frame_dev.argtypes = [ct.POINTER(CdefFrame), vp, vp, vp, vp, vp, vp, vp, ct.c_int, ct.c_int, vp]
+lib.svt_b200_cdef_apply_frame_dev.argtypes = [ct.POINTER(CdefFrame), vp, vp, vp, vp, vp, vp, vp, vp, vp, ct.c_int, ct.c_int, vp]
 lib.svt_b200_cdef_apply_frame_dev.restype = ct.c_int
 
 

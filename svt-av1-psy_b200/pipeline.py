@@ -20,6 +20,7 @@ def _t(torch, arr, dtype=None):
 class FramePipeline:
     def __init__(self, wl, torch, device="cuda"):
         self.wl, self.torch = wl, torch
+        self.tx_counts = (ct.c_int * dsp.TXFM_CLASSES)(*wl.tx_class_counts)
         W, H = wl.width, wl.height
         T = torch
         # ---- ME: padded pyramids (current + references) -------------------------------------------
@@ -151,14 +152,13 @@ class FramePipeline:
 
     def stage_tx(self, s):
         wl = self.wl
-        rc = lib.svt_b200_fwd_txfm_batch_dev(self.residual.data_ptr(), self.coeff.data_ptr(), self.fwd_items.data_ptr(), wl.n_small, wl.n_large,
-                                             wl.max_small, wl.max_large, s)
+        rc = lib.svt_b200_fwd_txfm_batch_dev(self.residual.data_ptr(), self.coeff.data_ptr(), self.fwd_items.data_ptr(), self.tx_counts, s)
         assert rc == 0
         rc = lib.svt_b200_quant_batch_dev(self.coeff.data_ptr(), self.qcoeff.data_ptr(), self.dqcoeff.data_ptr(), self.scan.data_ptr(),
                                           self.qm.data_ptr(), self.quant_items.data_ptr(), len(wl.quant_items), self.eobs.data_ptr(), s)
         assert rc == 0
         rc = lib.svt_b200_inv_txfm_batch_dev(self.dqcoeff.data_ptr(), self.pred.data_ptr(), self.recon.data_ptr(), self.inv_items.data_ptr(),
-                                             wl.n_small, wl.n_large, wl.max_small, wl.max_large, 1, s)
+                                             self.tx_counts, 1, s)
         assert rc == 0
 
     def cdef_frame(self, recon_flat):
@@ -179,7 +179,7 @@ class FramePipeline:
         self.cdef_out.copy_(self.recon, non_blocking=True)  # svt_av1_cdef_frame filters in place
         (oy, sy), (ocb, sc), (ocr, _) = self.plane_views(self.cdef_out, True)
         rc = lib.svt_b200_cdef_apply_frame_dev(ct.byref(f), self.skip.data_ptr(), self.fb_idx.data_ptr(), self.app_y.data_ptr(),
-                                               self.app_uv.data_ptr(), oy, ocb, ocr, sy, sc, s)
+                                               self.app_uv.data_ptr(), self.cdef_dir.data_ptr(), self.cdef_var.data_ptr(), oy, ocb, ocr, sy, sc, s)
         assert rc == 0
 
     def stage_rest(self, s):

@@ -168,18 +168,12 @@ class FrameWorkload:
         # log_scale of av1_get_tx_scale: 0 up to 256 coefficients... 1 for 512/1024, 2 for 64x64-class
         q["log_scale"] = [2 if TX_W[s] * TX_H[s] > 1024 else (1 if TX_W[s] * TX_H[s] > 256 else 0) for s in szs]
         self.quant_items = q
-        small = np.array([TX_W[s] * TX_H[s] <= dsp.TXFM_SMALL_MAX_COEFFS for s in self.fwd_items["tx_size"]])
-        order = np.concatenate([np.nonzero(small)[0], np.nonzero(~small)[0]])
+        # batch order of the transform calls: by team class, then (tx_size, tx_type) so that teams sharing a warp agree
+        cls = np.array([dsp.txfm_team_class(int(s)) for s in self.fwd_items["tx_size"]])
+        order = np.lexsort((self.fwd_items["tx_type"], self.fwd_items["tx_size"], cls))
         self.fwd_items = self.fwd_items[order]
         self.inv_items = self.inv_items[order]
-        self.n_small = int(small.sum())
-        self.n_large = int((~small).sum())
-
-        def max_size(mask):
-            ss = set(int(s) for s in self.fwd_items["tx_size"][mask])
-            return max(ss, key=lambda s: max(TX_H[s] * (TX_W[s] + 1), TX_W[s] * (TX_H[s] + 1))) if ss else 0
-        srt_small = np.arange(len(order)) < self.n_small
-        self.max_small, self.max_large = max_size(srt_small), max_size(~srt_small)
+        self.tx_class_counts = [int((cls == c).sum()) for c in range(dsp.TXFM_CLASSES)]
 
     # -- CDEF ---------------------------------------------------------------------------------------------
     def _build_cdef(self):
