@@ -72,6 +72,18 @@ void     lane_release(Lane* l);
 void     count_launch(int n = 1);
 void     txfm_tables_init();  // txfm.cu: uploads the transform constant tables
 
+// Side streams for calls whose launches are independent of each other: fork_streams() makes the side
+// streams wait for everything already enqueued on `user`, join_streams() makes `user` wait for them.
+// One set per host thread (events are re-recorded call after call; a wait keeps the record it saw).
+struct ForkJoin {
+    static constexpr int kSide = 3;
+    cudaStream_t side[kSide];
+    cudaEvent_t  forked, done[kSide];
+    bool         ready = false;
+};
+ForkJoin& fork_streams(cudaStream_t user);
+void      join_streams(ForkJoin& fj, cudaStream_t user);
+
 struct LaneGuard {
     Lane* l;
     LaneGuard() : l(lane_acquire()) {}

@@ -112,3 +112,29 @@ extern "C" void svt_b200_shutdown(void) {
 extern "C" int svt_b200_sm_count(void) { return ctx().ready ? ctx().sm_count : 0; }
 extern "C" unsigned long long svt_b200_launch_count(void) { return ctx().launches; }
 extern "C" const char* svt_b200_version(void) { return "svt_b200 0.1 (sm_100a)"; }
+
+namespace b200 {
+
+ForkJoin& fork_streams(cudaStream_t user) {
+    static thread_local ForkJoin fj;
+    if (!fj.ready) {
+        for (int i = 0; i < ForkJoin::kSide; i++) {
+            B200_CUDA_CHECK(cudaStreamCreateWithFlags(&fj.side[i], cudaStreamNonBlocking));
+            B200_CUDA_CHECK(cudaEventCreateWithFlags(&fj.done[i], cudaEventDisableTiming));
+        }
+        B200_CUDA_CHECK(cudaEventCreateWithFlags(&fj.forked, cudaEventDisableTiming));
+        fj.ready = true;
+    }
+    B200_CUDA_CHECK(cudaEventRecord(fj.forked, user));
+    for (int i = 0; i < ForkJoin::kSide; i++) B200_CUDA_CHECK(cudaStreamWaitEvent(fj.side[i], fj.forked, 0));
+    return fj;
+}
+
+void join_streams(ForkJoin& fj, cudaStream_t user) {
+    for (int i = 0; i < ForkJoin::kSide; i++) {
+        B200_CUDA_CHECK(cudaEventRecord(fj.done[i], fj.side[i]));
+        B200_CUDA_CHECK(cudaStreamWaitEvent(user, fj.done[i], 0));
+    }
+}
+
+}  // namespace b200

@@ -23,7 +23,7 @@
 namespace b200 {
 
 void launch_sad_search(const uint8_t* d_src, const uint8_t* d_ref, const SvtB200SadSearchItem* d_items, int n,
-                       SvtB200SadSearchResult* d_results, size_t smem, cudaStream_t st);
+                       SvtB200SadSearchResult* d_results, size_t smem, int max_positions, cudaStream_t st);
 
 // ---- K13 ----------------------------------------------------------------------------------------
 __global__ void downsample_2d_kernel(const uint8_t* __restrict__ in, int in_stride, int in_w, int in_h, uint8_t* __restrict__ out,
@@ -332,10 +332,13 @@ extern "C" int svt_b200_me_picture_dev(const SvtB200MePicture* cur, const SvtB20
     B200_CUDA_CHECK(cudaMemcpyAsync(w.refs, refs, n_refs * sizeof(SvtB200MePicture), cudaMemcpyHostToDevice, st));
     B200_CUDA_CHECK(cudaMemcpyAsync(w.prm, params, n_refs * sizeof(SvtB200MeParams), cudaMemcpyHostToDevice, st));
     const int g = grid_for((n4 + 255) / 256, 8);
-    int max_l0_w = 8, max_l0_h = 1;
+    int max_l0_w = 8, max_l0_h = 1, max_pos[3] = {1, 1, 1};
     for (int r = 0; r < n_refs; r++) {
         max_l0_w = max_l0_w > ((params[r].hme_l0_sa_w + 7) & ~7) ? max_l0_w : ((params[r].hme_l0_sa_w + 7) & ~7);
         max_l0_h = max_l0_h > params[r].hme_l0_sa_h ? max_l0_h : params[r].hme_l0_sa_h;
+        const int pos[3] = {((params[r].hme_l0_sa_w + 7) & ~7) * params[r].hme_l0_sa_h, ((params[r].hme_l1_sa_w + 7) & ~7) * params[r].hme_l1_sa_h,
+                            ((params[r].hme_l2_sa_w + 7) & ~7) * params[r].hme_l2_sa_h};
+        for (int l = 0; l < 3; l++) max_pos[l] = max_pos[l] > pos[l] ? max_pos[l] : pos[l];
     }
     for (int level = 0; level < 3; level++) {
         hme_prepare_kernel<<<g, 256, 0, st>>>(*cur, w.refs, w.prm, n_refs, n_b64, b64_w, level, level ? w.x[level - 1] : nullptr,
@@ -346,7 +349,7 @@ extern "C" int svt_b200_me_picture_dev(const SvtB200MePicture* cur, const SvtB20
         const int saw = level == 0 ? max_l0_w : 16, sah = level == 0 ? max_l0_h : 8;
         const size_t lw = ((saw + bs + 3) >> 2) + 10;
         const size_t smem = (size_t)(((bs + 15) >> 4) << 2) * 4 * bs + 2048 * 4 + 64 + (size_t)(sah - 1 + 2 * (bs - 1) + 1) * lw * 4;
-        launch_sad_search(nullptr, nullptr, w.items, n4, w.res, smem, st);
+        launch_sad_search(nullptr, nullptr, w.items, n4, w.res, smem, max_pos[level], st);
         hme_finish_kernel<<<g, 256, 0, st>>>(w.res, w.side, w.prm, n_refs, n_b64, level, w.x[level], w.y[level], w.sad[level]);
         B200_LAUNCH_CHECK();
     }

@@ -245,6 +245,92 @@ sad_search_kernel(const uint8_t* __restrict__ src_plane, const uint8_t* __restri
     }
 }
 
+// Small search areas (the 8x3 / 16x4 HME and ME refinements: a few dozen positions, blocks up to
+// 64x64): the work is a few hundred VABSDIFF4 per lane, so staging through shared memory and CTA
+// barriers would be the whole cost.  One WARP per item, no shared memory: lane = (x mod 8, row slice
+// of 4); a lane walks its rows with two sliding funnel-shift windows over aligned words that come
+// straight from L1 (the 8 x-lanes of a slice read the same sectors, the source word is a broadcast),
+// the 4 slices are added with two shuffles and the raster-order first minimum is the minimum of the
+// 64-bit key (sad<<32 | y<<16 | x), as in the tiled kernel.
+constexpr int kSmallSearchMaxPos = 256;
+constexpr int kSmallWarps        = 4;
+
+// aligned-word view of `n` bytes at p: word(j) = bytes [4j, 4j+4) of the run; only words holding a valid byte are read
+struct ByteRun {
+    const uint32_t* w;
+    int shift, last;
+    __device__ __forceinline__ ByteRun(const uint8_t* p, int n) {
+        const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+        w     = reinterpret_cast<const uint32_t*>(a & ~uintptr_t(3));
+        shift = (int)(a & 3) * 8;
+        last  = (int)(((a & 3) + n - 1) >> 2);
+    }
+    __device__ __forceinline__ uint32_t raw(int j) const { return __ldg(w + (j < last ? j : last)); }
+};
+
+__global__ void __launch_bounds__(kSmallWarps * 32)
+sad_search_small_kernel(const uint8_t* __restrict__ src_plane, const uint8_t* __restrict__ ref_plane,
+                        const SvtB200SadSearchItem* __restrict__ items, int n_items, SvtB200SadSearchResult* __restrict__ results) {
+    const int it = blockIdx.x * kSmallWarps + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (it >= n_items) return;
+    const SvtB200SadSearchItem item = items[it];
+    const int bw = item.block_w, bh = item.block_h, sa_w = item.sa_w, sa_h = item.sa_h;
+    unsigned long long best = ~0ull;
+    if (sa_w > 0 && sa_h > 0 && bw > 0 && bh > 0) {
+        const bool     skip = (bw == 16 && bh <= 16 && item.skip_search_line);
+        const int      xs = lane & 7, slice = lane >> 3;
+        const int      nw = (bw + 3) >> 2, tail = bw & 3;
+        const uint32_t tailmask = tail ? ((1u << (tail * 8)) - 1u) : 0xffffffffu;
+        const uint8_t* src0 = src_plane + item.src_off;
+        const uint8_t* ref0 = ref_plane + item.ref_off;
+        for (int y = 0; y < sa_h; y++) {
+            if (skip && ((y & 1) == 0)) continue;
+            for (int x0 = 0; x0 < sa_w; x0 += 8) {
+                const bool valid = x0 + xs < sa_w;
+                const int  x = valid ? x0 + xs : sa_w - 1;  // idle lanes shadow the last column (stays inside the window)
+                uint32_t   acc = 0;
+                for (int r = slice; r < bh; r += 4) {
+                    const ByteRun S(src0 + (size_t)r * item.src_stride, bw);
+                    const ByteRun R(ref0 + (size_t)y * item.ref_step + (size_t)r * item.ref_stride + x, bw);
+                    uint32_t slo = S.raw(0), rlo = R.raw(0);
+#pragma unroll 4
+                    for (int j = 0; j < nw - 1; j++) {
+                        const uint32_t shi = S.raw(j + 1), rhi = R.raw(j + 1);
+                        acc = __vsadu4(__funnelshift_r(slo, shi, S.shift), __funnelshift_r(rlo, rhi, R.shift)) + acc;
+                        slo = shi;
+                        rlo = rhi;
+                    }
+                    const uint32_t shi = S.raw(nw), rhi = R.raw(nw);
+                    acc = __vsadu4(__funnelshift_r(slo, shi, S.shift) & tailmask, __funnelshift_r(rlo, rhi, R.shift) & tailmask) + acc;
+                }
+                acc += __shfl_xor_sync(0xffffffffu, acc, 8);
+                acc += __shfl_xor_sync(0xffffffffu, acc, 16);
+                if (valid && acc < 0xffffffu) {
+                    const unsigned long long key = ((unsigned long long)acc << 32) | ((unsigned long long)(uint32_t)y << 16) | (unsigned long long)(uint32_t)x;
+                    best = key < best ? key : best;
+                }
+            }
+        }
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) {  // the 4 slices hold identical keys; reduce over the 8 x-lanes
+            const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+            best = other < best ? other : best;
+        }
+    }
+    if (lane == 0) {
+        SvtB200SadSearchResult r;
+        if (best == ~0ull) {
+            r.best_sad = 0xffffffu;
+            r.x = r.y = -1;
+        } else {
+            r.best_sad = (uint32_t)(best >> 32);
+            r.y        = (int16_t)((best >> 16) & 0xffff);
+            r.x        = (int16_t)(best & 0xffff);
+        }
+        results[it] = r;
+    }
+}
+
 // K3: one CTA (one warp) per single-SAD item is overkill; T1 callers ask for one block at a time.
 __global__ void nxm_sad_kernel(const uint8_t* __restrict__ src, uint32_t src_stride, const uint8_t* __restrict__ ref,
                                uint32_t ref_stride, uint32_t height, uint32_t width, uint32_t* out) {
@@ -265,8 +351,13 @@ __global__ void nxm_sad_kernel(const uint8_t* __restrict__ src, uint32_t src_str
 }
 
 void launch_sad_search(const uint8_t* d_src, const uint8_t* d_ref, const SvtB200SadSearchItem* d_items, int n,
-                              SvtB200SadSearchResult* d_results, size_t smem, cudaStream_t st) {
+                              SvtB200SadSearchResult* d_results, size_t smem, int max_positions, cudaStream_t st) {
     if (n <= 0) return;
+    if (max_positions <= kSmallSearchMaxPos) {  // every item of the batch searches at most this many positions
+        sad_search_small_kernel<<<(n + kSmallWarps - 1) / kSmallWarps, kSmallWarps * 32, 0, st>>>(d_src, d_ref, d_items, n, d_results);
+        B200_LAUNCH_CHECK();
+        return;
+    }
     Context& c = ctx();
     const size_t dyn_max = (size_t)c.max_smem - 2048;  // opt-in limit minus this kernel's static shared memory
     if (smem > dyn_max) smem = dyn_max;
@@ -299,7 +390,7 @@ extern "C" int svt_b200_sad_search_batch_dev(const uint8_t* d_src_plane, const u
     require_ready();
     if (n_items < 0) return SVT_B200_ERR_BAD_ARG;
     size_t smem = smem_needed(max_block_w, max_block_h, max_sa_w, max_sa_h, max_row_mult < 1 ? 1 : max_row_mult);
-    launch_sad_search(d_src_plane, d_ref_plane, d_items, n_items, d_results, smem, (cudaStream_t)stream);
+    launch_sad_search(d_src_plane, d_ref_plane, d_items, n_items, d_results, smem, max_sa_w * max_sa_h, (cudaStream_t)stream);
     return SVT_B200_OK;
 }
 
@@ -317,15 +408,17 @@ extern "C" int svt_b200_sad_search_batch_host(const uint8_t* src_plane, size_t s
     memcpy(l->h<uint8_t>(o_ref), ref_plane, ref_bytes);
     memcpy(l->h<uint8_t>(o_it), items, sizeof(SvtB200SadSearchItem) * n_items);
     size_t smem = 0;
+    int max_pos = 0;
     for (int i = 0; i < n_items; i++) {
         const SvtB200SadSearchItem& it = items[i];
         int k = (it.ref_step && it.ref_stride % it.ref_step == 0) ? (int)(it.ref_stride / it.ref_step) : 1;
         size_t s = smem_needed(it.block_w, it.block_h, it.sa_w, it.sa_h, k);
         if (s > smem) smem = s;
+        if ((int)it.sa_w * it.sa_h > max_pos) max_pos = (int)it.sa_w * it.sa_h;
     }
     l->h2d(0, in_end);
     launch_sad_search(l->d<uint8_t>(o_src), l->d<uint8_t>(o_ref), l->d<SvtB200SadSearchItem>(o_it), n_items,
-                      l->d<SvtB200SadSearchResult>(o_res), smem, l->stream);
+                      l->d<SvtB200SadSearchResult>(o_res), smem, max_pos, l->stream);
     l->d2h(o_res, sizeof(SvtB200SadSearchResult) * n_items);
     l->sync();
     memcpy(results, l->h<uint8_t>(o_res), sizeof(SvtB200SadSearchResult) * n_items);
@@ -367,7 +460,7 @@ extern "C" void svt_b200_sad_loop_kernel(uint8_t* src, uint32_t src_stride, uint
     size_t smem = smem_needed((int)block_width, (int)block_height, search_area_width, search_area_height, k);
     l->h2d(0, in_end);
     launch_sad_search(l->d<uint8_t>(o_src), l->d<uint8_t>(o_ref), l->d<SvtB200SadSearchItem>(o_it), 1,
-                      l->d<SvtB200SadSearchResult>(o_res), smem, l->stream);
+                      l->d<SvtB200SadSearchResult>(o_res), smem, (int)search_area_width * search_area_height, l->stream);
     l->d2h(o_res, sizeof(SvtB200SadSearchResult));
     l->sync();
     const SvtB200SadSearchResult* r = l->h<SvtB200SadSearchResult>(o_res);

@@ -43,13 +43,14 @@ __host__ __device__ inline int rect_log_ratio(int w, int h) {  // get_rect_tx_lo
 // ------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------
-template <int TEAM>
-__global__ void __launch_bounds__(TEAM >= 64 ? 64 : 256)
+template <int TEAM, int THREADS>
+__global__ void __launch_bounds__(THREADS)
 fwd_txfm_kernel(const int16_t* __restrict__ src_base, int32_t* __restrict__ dst_base,
                 const SvtB200FwdTxfmItem* __restrict__ items, int n_items) {
     extern __shared__ __align__(16) int32_t tsm[];
-    constexpr int THREADS = TEAM >= 64 ? 64 : 256, TEAMS = THREADS / TEAM, PLANE = TEAM * (TEAM + 1);
-    const int     team  = threadIdx.x / TEAM, tid = threadIdx.x % TEAM;
+    // a 64-point block is alone in its CTA: all THREADS move data, the first 64 run the passes
+    constexpr int TEAMS = TEAM >= 64 ? 1 : THREADS / TEAM, PLANE = TEAM * (TEAM + 1), MOVERS = TEAM >= 64 ? THREADS : TEAM;
+    const int     team  = TEAM >= 64 ? 0 : threadIdx.x / TEAM, tid = TEAM >= 64 ? threadIdx.x : threadIdx.x % TEAM;
     int32_t*      A     = tsm + (size_t)team * 2 * PLANE;
     int32_t*      B     = A + PLANE;
 
@@ -62,7 +63,7 @@ fwd_txfm_kernel(const int16_t* __restrict__ src_base, int32_t* __restrict__ dst_
         int32_t*       dst = dst_base + item.dst_off;
         const int P1 = W + 1, P2 = H + 1;
         // load, optional up/down flip, pre-shift (transforms.c:2286-2294)
-        for (int idx = tid; idx < W * H; idx += TEAM) {
+        for (int idx = tid; idx < W * H; idx += MOVERS) {
             const int r = idx >> lgW, c = idx & (W - 1);
             const int rr = cfg.f_ud ? (H - 1 - r) : r;
             A[r * P1 + c] = round_shift_arr((int32_t)src[(size_t)rr * item.src_stride + c], -cfg.f_s0);
@@ -71,7 +72,7 @@ fwd_txfm_kernel(const int16_t* __restrict__ src_base, int32_t* __restrict__ dst_
         txfm_pass_1d<TEAM, false>(cfg.f_tc, A, H, W, P1, cfg.f_cbc, 0, tid);  // columns: vector v = column v
         team_sync<TEAM>();
         // round-shift, optional left/right flip, hand over transposed (element = column)
-        for (int idx = tid; idx < W * H; idx += TEAM) {
+        for (int idx = tid; idx < W * H; idx += MOVERS) {
             const int r = idx >> lgW, c = idx & (W - 1);
             const int cc = cfg.f_lr ? (W - 1 - c) : c;
             B[cc * P2 + r] = round_shift_arr(A[r * P1 + c], -cfg.f_s1);
@@ -80,7 +81,7 @@ fwd_txfm_kernel(const int16_t* __restrict__ src_base, int32_t* __restrict__ dst_
         txfm_pass_1d<TEAM, false>(cfg.f_tr, B, W, H, P2, cfg.f_cbr, 0, tid);  // rows: vector v = row v
         team_sync<TEAM>();
         const int rect = rect_log_ratio(W, H);
-        for (int idx = tid; idx < W * H; idx += TEAM) {
+        for (int idx = tid; idx < W * H; idx += MOVERS) {
             const int r = idx >> lgW, c = idx & (W - 1);
             int32_t   v = round_shift_arr(B[c * P2 + r], -cfg.f_s2);
             if (rect == 1 || rect == -1) v = round_shift64((long long)v * kNewSqrt2, 12);
@@ -97,13 +98,14 @@ fwd_txfm_kernel(const int16_t* __restrict__ src_base, int32_t* __restrict__ dst_
 // ------------------------------------------------------------------------------------------------
 // inverse + reconstruction
 // ------------------------------------------------------------------------------------------------
-template <int TEAM, typename PIX>
-__global__ void __launch_bounds__(TEAM >= 64 ? 64 : 256)
+template <int TEAM, int THREADS, typename PIX>
+__global__ void __launch_bounds__(THREADS)
 inv_txfm_kernel(const int32_t* __restrict__ coef_base, const PIX* __restrict__ pred_base, PIX* __restrict__ recon_base,
                 const SvtB200InvTxfmItem* __restrict__ items, int n_items) {
     extern __shared__ __align__(16) int32_t tsm[];
-    constexpr int THREADS = TEAM >= 64 ? 64 : 256, TEAMS = THREADS / TEAM, PLANE = TEAM * (TEAM + 1);
-    const int     team  = threadIdx.x / TEAM, tid = threadIdx.x % TEAM;
+    // a 64-point block is alone in its CTA: all THREADS move data, the first 64 run the passes
+    constexpr int TEAMS = TEAM >= 64 ? 1 : THREADS / TEAM, PLANE = TEAM * (TEAM + 1), MOVERS = TEAM >= 64 ? THREADS : TEAM;
+    const int     team  = TEAM >= 64 ? 0 : threadIdx.x / TEAM, tid = TEAM >= 64 ? threadIdx.x : threadIdx.x % TEAM;
     int32_t*      A     = tsm + (size_t)team * 2 * PLANE;
     int32_t*      B     = A + PLANE;
 
@@ -121,7 +123,7 @@ inv_txfm_kernel(const int32_t* __restrict__ coef_base, const PIX* __restrict__ p
         const int opt_row = bd == 8 ? 16 : (bd == 10 ? 18 : 20);  // svt_av1_gen_inv_stage_range
         const int opt_col = bd == 12 ? 18 : 16;
         // rows first: element = column, vector = row
-        for (int idx = tid; idx < W * H; idx += TEAM) {
+        for (int idx = tid; idx < W * H; idx += MOVERS) {
             const int r = idx >> lgW, c = idx & (W - 1);
             int32_t   v = (r < Hp && c < Wp) ? in[r * Wp + c] : 0;
             if (rect == 1 || rect == -1) v = round_shift64((long long)v * kNewInvSqrt2, 12);
@@ -130,7 +132,7 @@ inv_txfm_kernel(const int32_t* __restrict__ coef_base, const PIX* __restrict__ p
         team_sync<TEAM>();
         txfm_pass_1d<TEAM, true>(cfg.i_tr, A, W, H, P1, cfg.i_cbr, opt_row, tid);
         team_sync<TEAM>();
-        for (int idx = tid; idx < W * H; idx += TEAM) {
+        for (int idx = tid; idx < W * H; idx += MOVERS) {
             const int r = idx >> lgW, c = idx & (W - 1);
             const int cs = cfg.i_lr ? (W - 1 - c) : c;
             B[r * P2 + c] = clamp_bits(round_shift_arr(A[cs * P1 + r], -cfg.i_s0), col_clamp);
@@ -142,7 +144,7 @@ inv_txfm_kernel(const int32_t* __restrict__ coef_base, const PIX* __restrict__ p
         PIX*       pw = recon_base + item.recon_off;
         const long long int_max = (1ll << (7 + bd)) - 1 + (914ll << (bd - 7));  // check_range, inv_transforms.c:2401
         const int       pix_max = (1 << bd) - 1;
-        for (int idx = tid; idx < W * H; idx += TEAM) {
+        for (int idx = tid; idx < W * H; idx += MOVERS) {
             const int r = idx >> lgW, c = idx & (W - 1);
             const int rs = cfg.i_ud ? (H - 1 - r) : r;
             long long t  = (long long)round_shift_arr(B[rs * P2 + c], -cfg.i_s1);
@@ -166,14 +168,17 @@ static void set_smem_attr(K kernel, size_t smem) {
     if (smem > 48 * 1024) B200_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 }
 
+// CTA size per team class: small enough that a picture's worth of blocks of that class spreads over all SMs
+template <int TEAM> constexpr int class_threads() { return TEAM == 16 ? 128 : (TEAM == 32 ? 64 : 256); }
+
 template <int TEAM>
 static void launch_fwd_class(const int16_t* d_src, int32_t* d_dst, const SvtB200FwdTxfmItem* d_items, int n, cudaStream_t st) {
-    constexpr int    THREADS = TEAM >= 64 ? 64 : 256, TEAMS = THREADS / TEAM;
+    constexpr int    THREADS = class_threads<TEAM>(), TEAMS = TEAM >= 64 ? 1 : THREADS / TEAM;
     constexpr size_t smem = (size_t)TEAMS * 2 * TEAM * (TEAM + 1) * 4;
     static bool attr = false;
-    if (!attr) { set_smem_attr(fwd_txfm_kernel<TEAM>, smem); attr = true; }
+    if (!attr) { set_smem_attr(fwd_txfm_kernel<TEAM, THREADS>, smem); attr = true; }
     const int per_sm = (int)((200 * 1024) / (smem + 1024)) < 2048 / THREADS ? (int)((200 * 1024) / (smem + 1024)) : 2048 / THREADS;
-    fwd_txfm_kernel<TEAM><<<grid_for((n + TEAMS - 1) / TEAMS, per_sm), THREADS, smem, st>>>(d_src, d_dst, d_items, n);
+    fwd_txfm_kernel<TEAM, THREADS><<<grid_for((n + TEAMS - 1) / TEAMS, per_sm), THREADS, smem, st>>>(d_src, d_dst, d_items, n);
     B200_LAUNCH_CHECK();
 }
 void launch_fwd_txfm(const int16_t* d_src, int32_t* d_dst, const SvtB200FwdTxfmItem* d_items, int n, int cls, cudaStream_t st) {
@@ -190,12 +195,12 @@ void launch_fwd_txfm(const int16_t* d_src, int32_t* d_dst, const SvtB200FwdTxfmI
 template <int TEAM, typename PIX>
 static void launch_inv_class(const int32_t* d_coef, const PIX* d_pred, PIX* d_recon, const SvtB200InvTxfmItem* d_items, int n,
                              cudaStream_t st) {
-    constexpr int    THREADS = TEAM >= 64 ? 64 : 256, TEAMS = THREADS / TEAM;
+    constexpr int    THREADS = class_threads<TEAM>(), TEAMS = TEAM >= 64 ? 1 : THREADS / TEAM;
     constexpr size_t smem = (size_t)TEAMS * 2 * TEAM * (TEAM + 1) * 4;
     static bool attr = false;
-    if (!attr) { set_smem_attr(inv_txfm_kernel<TEAM, PIX>, smem); attr = true; }
+    if (!attr) { set_smem_attr(inv_txfm_kernel<TEAM, THREADS, PIX>, smem); attr = true; }
     const int per_sm = (int)((200 * 1024) / (smem + 1024)) < 2048 / THREADS ? (int)((200 * 1024) / (smem + 1024)) : 2048 / THREADS;
-    inv_txfm_kernel<TEAM, PIX><<<grid_for((n + TEAMS - 1) / TEAMS, per_sm), THREADS, smem, st>>>(d_coef, d_pred, d_recon, d_items, n);
+    inv_txfm_kernel<TEAM, THREADS, PIX><<<grid_for((n + TEAMS - 1) / TEAMS, per_sm), THREADS, smem, st>>>(d_coef, d_pred, d_recon, d_items, n);
     B200_LAUNCH_CHECK();
 }
 template <typename PIX>
@@ -223,16 +228,22 @@ extern "C" int svt_b200_txfm_valid(int tx_size, int tx_type) {
 
 extern "C" int svt_b200_txfm_team_class(int tx_size) { return (tx_size < 0 || tx_size >= 19) ? -1 : tx_class(tx_size); }
 
+// The five class launches of a batch are independent: the three big-block classes (few, long-running
+// CTAs) go to side streams forked from the caller's stream and joined back into it, so the many
+// small blocks fill the SMs the big ones leave idle.
 extern "C" int svt_b200_fwd_txfm_batch_dev(const int16_t* d_residual, int32_t* d_coeff, const SvtB200FwdTxfmItem* d_items,
                                            const int n_per_class[SVT_B200_TXFM_CLASSES], void* stream) {
     require_ready();
     if (!n_per_class) return SVT_B200_ERR_BAD_ARG;
-    int first = 0;
+    int first[SVT_B200_TXFM_CLASSES + 1] = {0};
     for (int c = 0; c < SVT_B200_TXFM_CLASSES; c++) {
         if (n_per_class[c] < 0) return SVT_B200_ERR_BAD_ARG;
-        launch_fwd_txfm(d_residual, d_coeff, d_items + first, n_per_class[c], c, (cudaStream_t)stream);
-        first += n_per_class[c];
+        first[c + 1] = first[c] + n_per_class[c];
     }
+    ForkJoin& fj = fork_streams((cudaStream_t)stream);
+    for (int c = SVT_B200_TXFM_CLASSES - 1; c >= 0; c--)
+        launch_fwd_txfm(d_residual, d_coeff, d_items + first[c], n_per_class[c], c, c >= 2 ? fj.side[c - 2] : (cudaStream_t)stream);
+    join_streams(fj, (cudaStream_t)stream);
     return SVT_B200_OK;
 }
 
@@ -241,14 +252,18 @@ extern "C" int svt_b200_inv_txfm_batch_dev(const int32_t* d_coeff, const void* d
                                            int pixel_bytes, void* stream) {
     require_ready();
     if (!n_per_class || (pixel_bytes != 1 && pixel_bytes != 2)) return SVT_B200_ERR_BAD_ARG;
-    cudaStream_t st = (cudaStream_t)stream;
-    int first = 0;
+    int first[SVT_B200_TXFM_CLASSES + 1] = {0};
     for (int c = 0; c < SVT_B200_TXFM_CLASSES; c++) {
         if (n_per_class[c] < 0) return SVT_B200_ERR_BAD_ARG;
-        if (pixel_bytes == 1) launch_inv_txfm<uint8_t>(d_coeff, (const uint8_t*)d_pred, (uint8_t*)d_recon, d_items + first, n_per_class[c], c, st);
-        else launch_inv_txfm<uint16_t>(d_coeff, (const uint16_t*)d_pred, (uint16_t*)d_recon, d_items + first, n_per_class[c], c, st);
-        first += n_per_class[c];
+        first[c + 1] = first[c] + n_per_class[c];
     }
+    ForkJoin& fj = fork_streams((cudaStream_t)stream);
+    for (int c = SVT_B200_TXFM_CLASSES - 1; c >= 0; c--) {
+        cudaStream_t st = c >= 2 ? fj.side[c - 2] : (cudaStream_t)stream;
+        if (pixel_bytes == 1) launch_inv_txfm<uint8_t>(d_coeff, (const uint8_t*)d_pred, (uint8_t*)d_recon, d_items + first[c], n_per_class[c], c, st);
+        else launch_inv_txfm<uint16_t>(d_coeff, (const uint16_t*)d_pred, (uint16_t*)d_recon, d_items + first[c], n_per_class[c], c, st);
+    }
+    join_streams(fj, (cudaStream_t)stream);
     return SVT_B200_OK;
 }
 
