@@ -32,6 +32,11 @@ sys.path.insert(0, ROOT)
 
 METRIC = "1080p preset-8 hot-path (ME + transform/quant + CDEF + Wiener) frames/sec"
 N_FRAME_SETS = 4  # rotated between steps so that consecutive steps do not hit a warm L2
+N_CALLS = 10      # len(FramePipeline.CALLS): the T2 entry points one frame goes through
+# dram__bytes_read.sum + dram__bytes_write.sum of the call's dominant kernel, per launch, from the ncu --set full
+# capture of this same command (profiles/README.md says which file); None = not captured for that call
+NCU_DRAM_SOURCE = "profiles/r1_top_kernels_ncu_raw.csv"
+NCU_DRAM_BYTES = {}
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -255,6 +260,7 @@ def main():
     import torch.distributed as dist
     from svt_av1_psy_b200 import dsp
     from svt_av1_psy_b200.pipeline import FramePipeline
+    assert len(FramePipeline.CALLS) == N_CALLS
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
@@ -272,7 +278,7 @@ def main():
         torch.cuda.synchronize()
 
     def run(n, e2e, stage_acc=None):
-        ev = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(n)] if stage_acc is not None else None
+        ev = [[torch.cuda.Event(enable_timing=True) for _ in range(N_CALLS + 1)] for _ in range(n)] if stage_acc is not None else None
         with torch.cuda.stream(stream):
             start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             start.record()
@@ -289,7 +295,7 @@ def main():
         torch.cuda.synchronize()
         if stage_acc is not None:
             for i in range(n):
-                for k in range(4):
+                for k in range(N_CALLS):
                     stage_acc[k] += ev[i][k].elapsed_time(ev[i][k + 1])
         return start.elapsed_time(end)
 
@@ -336,8 +342,8 @@ def main():
     sampler = ClockSampler(local_rank)
     sampler.start()
     l0 = dsp.launch_count()
-    stage_ms = [0.0] * 4
-    ms = run(args.steps, False, stage_ms)
+    call_ms = [0.0] * N_CALLS
+    ms = run(args.steps, False, call_ms)
     launches = dsp.launch_count() - l0
     barrier()
     # ---- end-to-end timing -----------------------------------------------------------------------------------
@@ -357,22 +363,32 @@ def main():
     fps = world * args.steps / (ms / 1e3)
     fps_e2e = world * args.steps / (ms_e2e / 1e3)
     alg = wl0.algorithmic_bytes()
-    stage_ms = [x / args.steps for x in stage_ms]
+    call_ms = [x / args.steps for x in call_ms]
+    calls = FramePipeline.CALLS
     names = list(FramePipeline.STAGES)
-    dom = int(np.argmax(stage_ms))
+    stage_ms = [sum(call_ms[i] for i, c in enumerate(calls) if c[1] == st) for st in names]
+    dom = int(np.argmax(call_ms))
+    dom_name, _, dom_kernels = calls[dom]
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
-    peak = float(peaks.get("hbm_gbs", 6650.0))
-    ach = alg[names[dom]] / (stage_ms[dom] / 1e3) / 1e9
-    roofline = {"bound": "hbm", "kernel": {"me": "sad_search_kernel+fullpel_search_kernel", "tx": "fwd_txfm_kernel+quant_kernel+inv_txfm_kernel",
-                                           "cdef": "cdef_search_kernel+cdef_apply_kernel", "rest": "stats_accum_kernel+wiener_convolve_kernel"}[names[dom]],
-                "stage": names[dom], "achieved": round(ach, 2), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 5),
-                "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
-                "traffic": None, "algorithmic_bytes_per_launch_group": alg[names[dom]],
-                "note": "integer kernels that re-use shared-memory tiles heavily: instruction/latency bound, not HBM bound (SURVEY 8d)"}
+    src = "MEASURED_PEAKS.json" if peaks else "fallback of /opt/skills/guides/B200_PROFILING.md"
+    if dom_name == "wiener_stats":  # the one dense contraction of the path: exact f16 MMA on the tensor cores
+        flops = 2.0 * wl0.wiener_stats_macs()
+        peak = float(peaks.get("bf16_tflops", peaks.get("dense_bf16_tflops", 2250.0)))
+        ach = flops / (call_ms[dom] / 1e3) / 1e12
+        roofline = {"bound": "tensor", "achieved": round(ach, 3), "peak": peak, "unit": "TFLOP/s", "frac": round(ach / peak, 5),
+                    "algorithmic_flops_per_call": flops}
+    else:
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        ach = alg[dom_name] / (call_ms[dom] / 1e3) / 1e9
+        roofline = {"bound": "hbm", "achieved": round(ach, 2), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 5),
+                    "algorithmic_bytes_per_call": alg[dom_name],
+                    "note": "integer kernel working out of shared-memory tiles: instruction/latency bound, not HBM bound (SURVEY 8d)"}
+    roofline.update({"call": dom_name, "kernel": dom_kernels, "ms_per_call": round(call_ms[dom], 4), "peak_source": src,
+                     "traffic": NCU_DRAM_BYTES.get(dom_name), "traffic_source": NCU_DRAM_SOURCE if dom_name in NCU_DRAM_BYTES else None})
     out = {"metric": METRIC, "value": round(fps, 2), "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": warmup,
            "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
            "data": "synthetic", "config": config, "clocks": clocks,
@@ -380,7 +396,8 @@ def main():
                    "ms_per_step": round(ms_e2e / args.steps, 4)},
            "gpu_launches": int(launches), "roofline": roofline,
            "stages_ms": {n: round(v, 4) for n, v in zip(names, stage_ms)},
-           "stages_algorithmic_gbs": {n: round(alg[n] / (v / 1e3) / 1e9, 2) for n, v in zip(names, stage_ms)}}
+           "calls_ms": {c[0]: round(v, 4) for c, v in zip(calls, call_ms)},
+           "calls_algorithmic_gbs": {c[0]: round(alg[c[0]] / (v / 1e3) / 1e9, 2) for c, v in zip(calls, call_ms) if v > 0}}
     if world == 1 and not args.no_cpu_baseline:
         t = time_reference(wl0, 2, 1)
         if t is not None:

@@ -232,7 +232,7 @@ typedef struct SvtB200QuantItem {
     uint64_t coeff_off;
     uint64_t q_off;
     uint64_t dq_off;
-    uint32_t scan_off;   /* into the int16 scan-table buffer */
+    uint32_t scan_off;   /* into the int16 scan-table (and inverse-scan-table) buffer */
     uint32_t qm_off;     /* into the uint8 QM buffer, SVT_B200_NO_QM = no matrix */
     uint32_t iqm_off;
     uint32_t n_coeffs;
@@ -242,9 +242,12 @@ typedef struct SvtB200QuantItem {
     uint16_t reserved;
 } SvtB200QuantItem;
 
+/* d_scan / d_iscan: the scan tables and their inverses (the `scan` and `iscan` arguments of the reference
+ * quantizers), same layout, addressed by SvtB200QuantItem.scan_off.  With d_iscan the blocks are walked in
+ * raster order (coalesced); d_iscan == NULL falls back to scan order through d_scan. */
 SVT_B200_API int svt_b200_quant_batch_dev(const int32_t* d_coeff, int32_t* d_qcoeff, int32_t* d_dqcoeff,
-                                          const int16_t* d_scan, const uint8_t* d_qm, const SvtB200QuantItem* d_items,
-                                          int n_items, uint16_t* d_eobs, void* stream);
+                                          const int16_t* d_scan, const int16_t* d_iscan, const uint8_t* d_qm,
+                                          const SvtB200QuantItem* d_items, int n_items, uint16_t* d_eobs, void* stream);
 
 /* ------------------------------------------------------------------------------------------ */
 /* K4  Hadamard / SATD  (reference: Source/Lib/C_DEFAULT/picture_operators_c.c:188-330)        */

@@ -314,7 +314,7 @@ cdef_dir_kernel(SvtB200CdefFrame f, const uint8_t* __restrict__ skip8x8, uint8_t
 // Strength search: one CTA per (filter block, plane).  mse[1] (chroma) must be zero on entry: the two
 // chroma planes add into it.
 template <typename PIX>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 cdef_search_kernel(SvtB200CdefFrame f, const uint8_t* __restrict__ skip8x8, const int* __restrict__ strengths_y,
                    const int* __restrict__ strengths_uv, int n_strengths, unsigned long long* __restrict__ mse /*[2][nfb][n_strengths]*/,
                    const uint8_t* __restrict__ dir_in /*[nfb][64]*/, const int* __restrict__ var_in /*[nfb][64]*/) {

@@ -174,12 +174,26 @@ __global__ void me_centre_kernel(SvtB200MePicture cur, const SvtB200MePicture* _
             if ((int16_t)(org_y + sy) > (int16_t)(H - 1)) sy = (int16_t)(sy - ((org_y + sy) - (H - 1)));
             const uint8_t* r0 = rp.plane[2] + (size_t)(rp.org_y[2] + org_y) * rp.stride[2] + rp.org_x[2] + org_x;
             const uint8_t* r1 = r0 + (ptrdiff_t)sy * rp.stride[2] + sx;
+            // lane = one of the (up to 32) rows that are summed; each row is walked word by word with
+            // funnel-shifted aligned loads, all of them independent (one global round trip per lane)
             uint32_t z = 0, hsad = 0;
-            for (int t = lane; t < (blk_h >> 1) * blk_w; t += 32) {
-                const int yy = (t / blk_w) * 2, xx = t % blk_w;
-                const int s = src[(size_t)yy * cur.stride[2] + xx];
-                z += (uint32_t)abs(s - (int)r0[(size_t)yy * rp.stride[2] + xx]);
-                hsad += (uint32_t)abs(s - (int)r1[(ptrdiff_t)yy * rp.stride[2] + xx]);
+            if (lane < (blk_h >> 1)) {
+                const int      yy = lane * 2, nw = (blk_w + 3) >> 2, tail = blk_w & 3;
+                const uint32_t tailmask = tail ? ((1u << (tail * 8)) - 1u) : 0xffffffffu;
+                const ByteRun  S(src + (size_t)yy * cur.stride[2], blk_w), A(r0 + (size_t)yy * rp.stride[2], blk_w),
+                    B(r1 + (ptrdiff_t)yy * rp.stride[2], blk_w);
+                uint32_t slo = S.raw(0), alo = A.raw(0), blo = B.raw(0);
+#pragma unroll 4
+                for (int j = 0; j < nw; j++) {
+                    const uint32_t shi = S.raw(j + 1), ahi = A.raw(j + 1), bhi = B.raw(j + 1);
+                    const uint32_t m = j == nw - 1 ? tailmask : 0xffffffffu;
+                    const uint32_t sv = __funnelshift_r(slo, shi, S.shift) & m;
+                    z    = __vsadu4(sv, __funnelshift_r(alo, ahi, A.shift) & m) + z;
+                    hsad = __vsadu4(sv, __funnelshift_r(blo, bhi, B.shift) & m) + hsad;
+                    slo = shi;
+                    alo = ahi;
+                    blo = bhi;
+                }
             }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {

@@ -145,6 +145,27 @@ __device__ __forceinline__ void stage_words(uint32_t* dst, int nwords, const uin
     }
 }
 
+// rows x nwords words of `nbytes`-byte rows at any alignment, all threads of the CTA, one word per step
+__device__ __forceinline__ void stage_rows(uint32_t* dst, int nwords, int rows, const uint8_t* g, size_t pitch, int nbytes) {
+    const int valid = (nbytes + 3) >> 2;
+#pragma unroll 4
+    for (int i = threadIdx.x; i < rows * nwords; i += kFpThreads) {
+        const int r = i / nwords, w = i - r * nwords;
+        const uintptr_t ga = reinterpret_cast<uintptr_t>(g + (size_t)r * pitch);
+        const int       shift = (int)(ga & 3) * 8, last_src = (int)(((ga & 3) + nbytes - 1) >> 2);
+        const uint32_t* gw = reinterpret_cast<const uint32_t*>(ga & ~uintptr_t(3));
+        uint32_t v = 0;
+        if (w < valid) {
+            const uint32_t lo = __ldg(gw + w);
+            const uint32_t hi = (shift && (w + 1) <= last_src) ? __ldg(gw + w + 1) : 0u;
+            v = __funnelshift_r(lo, hi, shift);
+            const int rem = nbytes - (w << 2);
+            if (rem < 4) v &= (1u << (rem * 8)) - 1u;
+        }
+        dst[r * nwords + w] = v;
+    }
+}
+
 __global__ void __launch_bounds__(kFpThreads)
 fullpel_search_kernel(const uint8_t* __restrict__ src_plane, const uint8_t* __restrict__ ref_plane,
                       const SvtB200FullpelItem* __restrict__ items, int n_items, uint32_t* __restrict__ best_sad,
@@ -152,25 +173,24 @@ fullpel_search_kernel(const uint8_t* __restrict__ src_plane, const uint8_t* __re
     __shared__ uint32_t S[64 * 16];
     __shared__ uint32_t W[kFpLines * kFpLW];
     __shared__ uint32_t sad8[kFpTW * kFpTH][65];
+    __shared__ uint32_t sadpu[kFpTW * kFpTH][21];  // 64x64, 4 x 32x32, 16 x 16x16 of every position
     __shared__ unsigned long long best[85];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
         const SvtB200FullpelItem item = items[it];
         const int sa_w = item.sa_w, sa_h = item.sa_h, sub = item.sub_sad;
         if (threadIdx.x < 85) best[threadIdx.x] = ((unsigned long long)(128u * 128u * 255u) << 32) | 0xffffffffull;
-        for (int r = warp; r < 64; r += kFpThreads / 32)
-            stage_words(S + r * 16, 16, src_plane + item.src_off + (size_t)r * item.src_stride, 64, lane, 32);
+        // flat staging: every thread's words are independent loads, so one global round trip covers the block
+        stage_rows(S, 16, 64, src_plane + item.src_off, item.src_stride, 64);
         for (int y0 = 0; y0 < sa_h; y0 += kFpTH) {
             const int th = min(kFpTH, sa_h - y0);
             for (int x0 = 0; x0 < sa_w; x0 += kFpTW) {
                 const int tw = min(kFpTW, sa_w - x0);
                 __syncthreads();
-                const uint8_t* lbase = ref_plane + item.ref_off + (size_t)y0 * item.ref_stride + x0;
-                for (int l = warp; l < th + 63; l += kFpThreads / 32)
-                    stage_words(W + l * kFpLW, kFpLW, lbase + (size_t)l * item.ref_stride, tw + 63, lane, 32);
+                stage_rows(W, kFpLW, th + 63, ref_plane + item.ref_off + (size_t)y0 * item.ref_stride + x0, item.ref_stride, tw + 63);
                 __syncthreads();
-                // 8x8 SADs: unit = (position, 8x8 block)
+                // 8x8 SADs: unit = (position, 8x8 block), stored in z-order so that the four 8x8 of a 16x16
+                // (and the four 16x16 of a 32x32) are neighbours
                 const int npos = tw * th;
                 for (int u = threadIdx.x; u < npos * 64; u += kFpThreads) {
                     const int pos = u >> 6, blk = u & 63;
@@ -178,7 +198,6 @@ fullpel_search_kernel(const uint8_t* __restrict__ src_plane, const uint8_t* __re
                     const int py = pos / tw, px = pos - py * tw;
                     const int a8 = (px & 3) * 8, wb = (px >> 2) + 2 * bx;
                     uint32_t  acc = 0;
-                    const int step = sub ? 2 : 1;
 #pragma unroll
                     for (int r = 0; r < 8; r++) {
                         if (sub && (r & 1)) continue;
@@ -188,24 +207,35 @@ fullpel_search_kernel(const uint8_t* __restrict__ src_plane, const uint8_t* __re
                         acc = __vsadu4(Sr[0], __funnelshift_r(w0, w1, a8)) + acc;
                         acc = __vsadu4(Sr[1], __funnelshift_r(w1, w2, a8)) + acc;
                     }
-                    (void)step;
                     if (sub) acc <<= 1;
                     const int y16 = by >> 1, x16 = bx >> 1;
                     sad8[pos][4 * z16_of(y16, x16) + 2 * (by & 1) + (bx & 1)] = acc;
                 }
                 __syncthreads();
+                // 16x16 / 32x32 / 64x64 sums: 16 lanes per position, lane = 16x16 z-index; two shuffle
+                // steps give the 32x32 of each quad, two more the 64x64
+                for (int u = threadIdx.x; u < ((npos * 16 + 31) & ~31); u += kFpThreads) {
+                    const int  pos = u >> 4, z = u & 15;
+                    const bool on = pos < npos;
+                    uint32_t   v16 = 0;
+                    if (on) v16 = sad8[pos][4 * z] + sad8[pos][4 * z + 1] + sad8[pos][4 * z + 2] + sad8[pos][4 * z + 3];
+                    uint32_t v32 = v16 + __shfl_xor_sync(0xffffffffu, v16, 1);
+                    v32 += __shfl_xor_sync(0xffffffffu, v32, 2);
+                    uint32_t v64 = v32 + __shfl_xor_sync(0xffffffffu, v32, 4);
+                    v64 += __shfl_xor_sync(0xffffffffu, v64, 8);
+                    if (on) {
+                        sadpu[pos][5 + z] = v16;
+                        if ((z & 3) == 0) sadpu[pos][1 + (z >> 2)] = v32;
+                        if (z == 0) sadpu[pos][0] = v64;
+                    }
+                }
+                __syncthreads();
                 // per-PU scan of this chunk's positions; key = sad<<32 | raster index
                 if (threadIdx.x < 85) {
                     const int pu = threadIdx.x;
-                    int first, count;  // range of 8x8 z-indices covered by this PU
-                    if (pu == 0) { first = 0; count = 64; }
-                    else if (pu < 5) { first = 16 * (pu - 1); count = 16; }
-                    else if (pu < 21) { first = 4 * (pu - 5); count = 4; }
-                    else { first = pu - 21; count = 1; }
                     unsigned long long b = best[pu];
                     for (int pos = 0; pos < npos; pos++) {
-                        uint32_t v = 0;
-                        for (int k = 0; k < count; k++) v += sad8[pos][first + k];
+                        const uint32_t v = pu < 21 ? sadpu[pos][pu] : sad8[pos][pu - 21];
                         const int py = pos / tw, px = pos - py * tw;
                         const unsigned long long key =
                             ((unsigned long long)v << 32) | (unsigned long long)(uint32_t)((y0 + py) * sa_w + (x0 + px));

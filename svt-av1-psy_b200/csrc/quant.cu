@@ -108,10 +108,15 @@ __device__ __forceinline__ void quant_one(const SvtB200QuantItem& it, int32_t co
     }
 }
 
-// one warp per item, 8 items per CTA: n_coeffs is 16..1024, i.e. 0.5..32 coefficients per lane
+// One warp per item, 8 items per CTA: n_coeffs is 16..1024, i.e. 0.5..32 coefficients per lane.
+// Every coefficient is quantised on its own; only the end-of-block position depends on the scan order
+// (eob = 1 + the last scan position with a non-zero level).  With the inverse scan table (the `iscan`
+// argument the reference passes to the same functions) the warp walks the block in RASTER order -- the
+// coefficient, level, dequantised and matrix accesses are all coalesced and independent -- and takes
+// eob = max(iscan[rc] + 1).  Without it the block is walked in scan order (gathered accesses).
 __global__ void __launch_bounds__(256)
 quant_kernel(const int32_t* __restrict__ coeff_base, int32_t* __restrict__ q_base, int32_t* __restrict__ dq_base,
-             const int16_t* __restrict__ scan_base, const uint8_t* __restrict__ qm_base,
+             const int16_t* __restrict__ scan_base, const int16_t* __restrict__ iscan_base, const uint8_t* __restrict__ qm_base,
              const SvtB200QuantItem* __restrict__ items, int n_items, uint16_t* __restrict__ eobs) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int idx = blockIdx.x * 8 + warp; idx < n_items; idx += gridDim.x * 8) {
@@ -119,17 +124,30 @@ quant_kernel(const int32_t* __restrict__ coeff_base, int32_t* __restrict__ q_bas
         const int32_t* coeff = coeff_base + it.coeff_off;
         int32_t*       qc    = q_base + it.q_off;
         int32_t*       dqc   = dq_base + it.dq_off;
-        const int16_t* scan  = scan_base + it.scan_off;
         const uint8_t* qm    = it.qm_off == SVT_B200_NO_QM ? nullptr : qm_base + it.qm_off;
         const uint8_t* iqm   = it.iqm_off == SVT_B200_NO_QM ? nullptr : qm_base + it.iqm_off;
         int            eob   = 0;
-        for (int i = lane; i < (int)it.n_coeffs; i += 32) {
-            const int rc = scan[i];
-            int32_t   q, dq;
-            quant_one(it, coeff[rc], rc, qm, iqm, q, dq);
-            qc[rc]  = q;
-            dqc[rc] = dq;
-            if (q) eob = i + 1;
+        if (iscan_base) {
+            const int16_t* iscan = iscan_base + it.scan_off;
+#pragma unroll 4
+            for (int rc = lane; rc < (int)it.n_coeffs; rc += 32) {
+                const int pos = iscan[rc];
+                int32_t   q, dq;
+                quant_one(it, coeff[rc], rc, qm, iqm, q, dq);
+                qc[rc]  = q;
+                dqc[rc] = dq;
+                if (q) eob = max(eob, pos + 1);
+            }
+        } else {
+            const int16_t* scan = scan_base + it.scan_off;
+            for (int i = lane; i < (int)it.n_coeffs; i += 32) {
+                const int rc = scan[i];
+                int32_t   q, dq;
+                quant_one(it, coeff[rc], rc, qm, iqm, q, dq);
+                qc[rc]  = q;
+                dqc[rc] = dq;
+                if (q) eob = i + 1;
+            }
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) eob = max(eob, __shfl_xor_sync(0xffffffffu, eob, o));
@@ -137,10 +155,10 @@ quant_kernel(const int32_t* __restrict__ coeff_base, int32_t* __restrict__ q_bas
     }
 }
 
-void launch_quant(const int32_t* d_coeff, int32_t* d_q, int32_t* d_dq, const int16_t* d_scan, const uint8_t* d_qm,
-                  const SvtB200QuantItem* d_items, int n, uint16_t* d_eobs, cudaStream_t st) {
+void launch_quant(const int32_t* d_coeff, int32_t* d_q, int32_t* d_dq, const int16_t* d_scan, const int16_t* d_iscan,
+                  const uint8_t* d_qm, const SvtB200QuantItem* d_items, int n, uint16_t* d_eobs, cudaStream_t st) {
     if (n <= 0) return;
-    quant_kernel<<<grid_for((n + 7) / 8, 8), 256, 0, st>>>(d_coeff, d_q, d_dq, d_scan, d_qm, d_items, n, d_eobs);
+    quant_kernel<<<grid_for((n + 7) / 8, 8), 256, 0, st>>>(d_coeff, d_q, d_dq, d_scan, d_iscan, d_qm, d_items, n, d_eobs);
     B200_LAUNCH_CHECK();
 }
 
@@ -179,7 +197,7 @@ static void quant_t1(int mode, const int32_t* coeff_ptr, intptr_t n_coeffs, cons
         it->dequant[k] = dequant_ptr[k];
     }
     l->h2d(0, in_end);
-    launch_quant(l->d<int32_t>(o_c), l->d<int32_t>(o_q), l->d<int32_t>(o_dq), l->d<int16_t>(o_scan), l->d<uint8_t>(o_qm),
+    launch_quant(l->d<int32_t>(o_c), l->d<int32_t>(o_q), l->d<int32_t>(o_dq), l->d<int16_t>(o_scan), nullptr, l->d<uint8_t>(o_qm),
                  l->d<SvtB200QuantItem>(o_it), 1, l->d<uint16_t>(o_eob), l->stream);
     l->d2h(o_q, (o_eob + 16) - o_q);
     l->sync();
@@ -240,10 +258,10 @@ extern "C" void svt_b200_av1_highbd_quantize_fp_qm(QARGS, const uint8_t* qm_ptr,
 }
 
 extern "C" int svt_b200_quant_batch_dev(const int32_t* d_coeff, int32_t* d_qcoeff, int32_t* d_dqcoeff, const int16_t* d_scan,
-                                        const uint8_t* d_qm, const SvtB200QuantItem* d_items, int n_items, uint16_t* d_eobs,
-                                        void* stream) {
+                                        const int16_t* d_iscan, const uint8_t* d_qm, const SvtB200QuantItem* d_items, int n_items,
+                                        uint16_t* d_eobs, void* stream) {
     require_ready();
-    if (n_items < 0) return SVT_B200_ERR_BAD_ARG;
-    launch_quant(d_coeff, d_qcoeff, d_dqcoeff, d_scan, d_qm, d_items, n_items, d_eobs, (cudaStream_t)stream);
+    if (n_items < 0 || (!d_scan && !d_iscan)) return SVT_B200_ERR_BAD_ARG;
+    launch_quant(d_coeff, d_qcoeff, d_dqcoeff, d_scan, d_iscan, d_qm, d_items, n_items, d_eobs, (cudaStream_t)stream);
     return SVT_B200_OK;
 }

@@ -255,19 +255,6 @@ sad_search_kernel(const uint8_t* __restrict__ src_plane, const uint8_t* __restri
 constexpr int kSmallSearchMaxPos = 256;
 constexpr int kSmallWarps        = 4;
 
-// aligned-word view of `n` bytes at p: word(j) = bytes [4j, 4j+4) of the run; only words holding a valid byte are read
-struct ByteRun {
-    const uint32_t* w;
-    int shift, last;
-    __device__ __forceinline__ ByteRun(const uint8_t* p, int n) {
-        const uintptr_t a = reinterpret_cast<uintptr_t>(p);
-        w     = reinterpret_cast<const uint32_t*>(a & ~uintptr_t(3));
-        shift = (int)(a & 3) * 8;
-        last  = (int)(((a & 3) + n - 1) >> 2);
-    }
-    __device__ __forceinline__ uint32_t raw(int j) const { return __ldg(w + (j < last ? j : last)); }
-};
-
 __global__ void __launch_bounds__(kSmallWarps * 32)
 sad_search_small_kernel(const uint8_t* __restrict__ src_plane, const uint8_t* __restrict__ ref_plane,
                         const SvtB200SadSearchItem* __restrict__ items, int n_items, SvtB200SadSearchResult* __restrict__ results) {

@@ -109,7 +109,7 @@ __device__ __forceinline__ int stats_average(const unsigned long long* tot, int 
 }
 
 constexpr int kStatsWarps = 8;
-constexpr int kStatsMaxParts = 16;  // CTAs cooperating on one restoration unit
+constexpr int kStatsMaxParts = 32;  // CTAs cooperating on one restoration unit
 constexpr int kStatsTileW = 32, kStatsTileH = 64, kStatsPitch = kStatsTileW + 6 + 2;
 
 // partial layout per (item, part): [0, 49*49) = H (upper-triangle tiles only), [2401, 2450) = M
@@ -290,12 +290,20 @@ __device__ __forceinline__ void mma_16816_f16f32(float (&c)[4], uint32_t a0, uin
                  : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
+// (lo, hi), |v| <= 255, as two f16 in one word without integer->float conversions: 0x6400 + n is the
+// f16 encoding of 1024 + n for 0 <= n < 1024, and subtracting 1280 from 1024 + (v + 256) is exact.
 __device__ __forceinline__ uint32_t pack_pair_f16(int lo, int hi) {
-    const __half2 h = __halves2half2(__int2half_rn(lo), __int2half_rn(hi));  // |v| <= 255: exact
+    const uint32_t bits = 0x64006400u + (uint32_t)(lo + 256) + ((uint32_t)(hi + 256) << 16);
+    const __half2  h    = __hsub2(*reinterpret_cast<const __half2*>(&bits), __float2half2_rn(1280.f));
     return *reinterpret_cast<const uint32_t*>(&h);
 }
 
 __host__ __device__ __forceinline__ int mma_tile_index(int win, int m, int n) { return m * win - m * (m - 1) + n - 2 * m; }
+// CTAs of an item that actually get pixel tiles (and so write a partial)
+__device__ __forceinline__ int stats_mma_parts(const SvtB200StatsItem& s, int ctas_per_item) {
+    const int tiles = ((s.h_end - s.h_start + kMmaTW - 1) / kMmaTW) * ((s.v_end - s.v_start + kMmaTH - 1) / kMmaTH);
+    return tiles < ctas_per_item ? tiles : ctas_per_item;
+}
 
 template <int WIN>
 __device__ __forceinline__ void stats_mma_body(const uint8_t* __restrict__ dgd, const uint8_t* __restrict__ src, const SvtB200StatsItem& s,
@@ -328,6 +336,24 @@ __device__ __forceinline__ void stats_mma_body(const uint8_t* __restrict__ dgd, 
     const int vlo = s.v_start - HALF, vhi = s.v_end + HALF, hlo = s.h_start - HALF, hhi = s.h_end + HALF;
     int  ksteps = 0, pending = 0;
     bool spilled = false;
+    // pull the rows a tile needs towards L1 (one 128-byte line per request; every address is inside the
+    // region the reference itself reads): issued for tile k+1 right before the MMA loop of tile k
+    auto prefetch_tile = [&](int tl) {
+        const int ty = tl / ntx, tx = tl - ty * ntx;
+        const int r0 = s.v_start + ty * kMmaTH, c0 = s.h_start + tx * kMmaTW;
+        for (int w = threadIdx.x; w < 2 * (kMmaPRows + 1) + kMmaTH; w += kMmaWarps * 32) {
+            const uint8_t* p;
+            if (w < 2 * (kMmaPRows + 1)) {
+                const int row = min(max(r0 - 3 + (w >> 1), vlo), vhi - 1);
+                const int col = (w & 1) ? min(c0 + kMmaTW + 2, hhi - 1) : max(c0 - 3, hlo);
+                p = dgd + (ptrdiff_t)row * s.dgd_stride + col;
+            } else {
+                const int row = min(r0 + (w - 2 * (kMmaPRows + 1)), s.v_end - 1);
+                p = src + (ptrdiff_t)row * s.src_stride + min(c0 + 32, s.h_end - 1);
+            }
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+        }
+    };
     for (int tl = part; tl < ntx * nty; tl += parts) {
         const int ty = tl / ntx, tx = tl - ty * ntx;
         const int r0 = s.v_start + ty * kMmaTH, c0 = s.h_start + tx * kMmaTW;
@@ -371,6 +397,7 @@ __device__ __forceinline__ void stats_mma_body(const uint8_t* __restrict__ dgd, 
             tile[kMmaXBase + r * kMmaPitch + c] = pack_pair_f16(lo, hi);
         }
         __syncthreads();
+        if (tl + parts < ntx * nty) prefetch_tile(tl + parts);
         const int cgs = (ncols + 7) >> 3, nsteps = cgs * ((nrows + 1) >> 1);
         for (int st = warp; st < nsteps; st += kMmaWarps) {
             const int rp = st / cgs, px = (st - rp * cgs) * 8, py = rp * 2;
@@ -412,6 +439,7 @@ stats_mma_kernel(const uint8_t* __restrict__ dgd_base, const uint8_t* __restrict
     const int it = blockIdx.x / ctas_per_item, part = blockIdx.x % ctas_per_item;
     const SvtB200StatsItem s = items[it];
     const int avg = stats_average(tot_in, it, s);
+    if (part >= stats_mma_parts(s, ctas_per_item)) return;  // more CTAs than tiles: finalize ignores the unused partials
     long long* P = partial + ((size_t)it * ctas_per_item + part) * 2450;
     const uint8_t* dgd = dgd_base + s.dgd_off;
     const uint8_t* src = src_base + s.src_off;
@@ -426,10 +454,11 @@ __global__ void stats_finalize_kernel(const long long* __restrict__ partial, int
     __shared__ long long A[2450];
     for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
         const int win = items[it].wiener_win, win2 = win * win;
+        const int used = mma_layout ? stats_mma_parts(items[it], parts) : parts;
         __syncthreads();
-        for (int i = threadIdx.x; i < 2450; i += blockDim.x) {
+        for (int i = threadIdx.x; i < (mma_layout ? kMmaAccMax : 2450); i += blockDim.x) {
             long long v = 0;
-            for (int p = 0; p < parts; p++) v += partial[((size_t)it * parts + p) * 2450 + i];
+            for (int p = 0; p < used; p++) v += partial[((size_t)it * parts + p) * 2450 + i];
             A[i] = v;
         }
         __syncthreads();
@@ -479,9 +508,10 @@ static void launch_stats(const PIX* d_dgd, const PIX* d_src, const SvtB200StatsI
     if (fp > 30000) fp = 30000;
     if (fp < 1) fp = 1;
     const int divider = bd == 12 ? 16 : (bd == 10 ? 4 : 1);
-    int cpi = (ctx().sm_count * 4) / (n > 0 ? n : 1);
+    // CTAs per item: enough for ~6 resident CTAs per SM (the tensor-core kernel gives each of them 1-2 pixel tiles)
+    int cpi = (ctx().sm_count * (sizeof(PIX) == 1 ? 6 : 4)) / (n > 0 ? n : 1);
     if (cpi < 1) cpi = 1;
-    if (cpi > kStatsMaxParts) cpi = kStatsMaxParts;
+    if (cpi > (sizeof(PIX) == 1 ? kStatsMaxParts : 16)) cpi = sizeof(PIX) == 1 ? kStatsMaxParts : 16;
     B200_CUDA_CHECK(cudaMemsetAsync(d_tot, 0, (size_t)n * sizeof(unsigned long long), st));
     stats_sum_kernel<PIX><<<n * kSumParts, 256, 0, st>>>(d_dgd, d_items, d_tot);
     B200_LAUNCH_CHECK();

@@ -214,7 +214,7 @@ for _n, _extra in (("aom_quantize_b", [vp, vp, ct.c_int32]), ("aom_highbd_quanti
     _f = getattr(lib, "svt_b200_" + _n)
     _f.argtypes = _QA + _extra
     _f.restype = None
-lib.svt_b200_quant_batch_dev.argtypes = [vp, vp, vp, vp, vp, vp, ct.c_int, vp, vp]
+lib.svt_b200_quant_batch_dev.argtypes = [vp, vp, vp, vp, vp, vp, vp, ct.c_int, vp, vp]
 lib.svt_b200_quant_batch_dev.restype = ct.c_int
 
 

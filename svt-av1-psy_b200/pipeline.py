@@ -61,6 +61,7 @@ class FramePipeline:
         self.inv_items = _t(T, wl.inv_items.view(np.uint8))
         self.quant_items = _t(T, wl.quant_items.view(np.uint8))
         self.scan = _t(T, wl.scan_table)
+        self.iscan = _t(T, wl.iscan_table)
         self.qm = _t(T, wl.qm_table)
         # ---- CDEF -------------------------------------------------------------------------------------
         self.skip = _t(T, wl.skip8x8)
@@ -143,20 +144,25 @@ class FramePipeline:
     def d2h_bytes(self):
         return sum(v.numel() * v.element_size() for v in self.h_out.values())
 
-    # -- stages ---------------------------------------------------------------------------------------------
-    def stage_me(self, s):
+    # -- the calls of one frame, in path order (each is one T2 entry point of include/svt_b200.h) -----------
+    def call_me_pyramid(self, s):
         assert lib.svt_b200_build_hme_pyramid_dev(ct.byref(self.cur_desc), s) == 0
+
+    def call_me_search(self, s):
         rc = lib.svt_b200_me_picture_dev(ct.byref(self.cur_desc), self.ref_descs, self.me_prm, self.wl.n_refs, self.me_sad.data_ptr(),
                                          self.me_mv.data_ptr(), self.me_centre.data_ptr(), self.me_hme_sad.data_ptr(), s)
         assert rc == 0
 
-    def stage_tx(self, s):
-        wl = self.wl
+    def call_fwd_txfm(self, s):
         rc = lib.svt_b200_fwd_txfm_batch_dev(self.residual.data_ptr(), self.coeff.data_ptr(), self.fwd_items.data_ptr(), self.tx_counts, s)
         assert rc == 0
-        rc = lib.svt_b200_quant_batch_dev(self.coeff.data_ptr(), self.qcoeff.data_ptr(), self.dqcoeff.data_ptr(), self.scan.data_ptr(),
-                                          self.qm.data_ptr(), self.quant_items.data_ptr(), len(wl.quant_items), self.eobs.data_ptr(), s)
+
+    def call_quant(self, s):
+        rc = lib.svt_b200_quant_batch_dev(self.coeff.data_ptr(), self.qcoeff.data_ptr(), self.dqcoeff.data_ptr(), self.scan.data_ptr(), self.iscan.data_ptr(),
+                                          self.qm.data_ptr(), self.quant_items.data_ptr(), len(self.wl.quant_items), self.eobs.data_ptr(), s)
         assert rc == 0
+
+    def call_inv_txfm(self, s):
         rc = lib.svt_b200_inv_txfm_batch_dev(self.dqcoeff.data_ptr(), self.pred.data_ptr(), self.recon.data_ptr(), self.inv_items.data_ptr(),
                                              self.tx_counts, 1, s)
         assert rc == 0
@@ -170,40 +176,77 @@ class FramePipeline:
         f.width, f.height, f.bit_depth, f.damping, f.subsampling_factor = wl.width, wl.height, 8, wl.cdef_damping, wl.cdef_subsampling
         return f
 
-    def stage_cdef(self, s):
+    def call_cdef_search(self, s):
         f = self.cdef_frame(self.recon)
         rc = lib.svt_b200_cdef_search_frame_dev(ct.byref(f), self.skip.data_ptr(), self.str_y.data_ptr(), self.str_uv.data_ptr(),
                                                 len(self.wl.cdef_str_y), self.cdef_mse.data_ptr(), self.cdef_dir.data_ptr(),
                                                 self.cdef_var.data_ptr(), s)
         assert rc == 0
+
+    def call_cdef_apply(self, s):
+        f = self.cdef_frame(self.recon)
         self.cdef_out.copy_(self.recon, non_blocking=True)  # svt_av1_cdef_frame filters in place
         (oy, sy), (ocb, sc), (ocr, _) = self.plane_views(self.cdef_out, True)
         rc = lib.svt_b200_cdef_apply_frame_dev(ct.byref(f), self.skip.data_ptr(), self.fb_idx.data_ptr(), self.app_y.data_ptr(),
                                                self.app_uv.data_ptr(), self.cdef_dir.data_ptr(), self.cdef_var.data_ptr(), oy, ocb, ocr, sy, sc, s)
         assert rc == 0
 
-    def stage_rest(self, s):
+    def call_rest_extend(self, s):
         wl = self.wl
         off, _ = wl.padded_offsets()
         for p in range(3):  # svt_extend_frame: restoration reads beyond the picture edge
             th, st = wl.padded_shape(p)
             w, h = wl.plane_dims[p]
             assert lib.svt_b200_extend_plane_dev(self.cdef_out.data_ptr() + off[p], st, w, h, wl.PAD, wl.PAD, s) == 0
+
+    def call_wiener_stats(self, s):
         rc = lib.svt_b200_compute_stats_batch_dev(self.cdef_out.data_ptr(), self.cur_flat.data_ptr(), self.stats_items.data_ptr(),
-                                                  len(wl.stats_items), 8, self.M.data_ptr(), self.Hm.data_ptr(), s)
+                                                  len(self.wl.stats_items), 8, self.M.data_ptr(), self.Hm.data_ptr(), s)
         assert rc == 0
-        rc = lib.svt_b200_wiener_units_dev(self.cdef_out.data_ptr(), self.final.data_ptr(), self.wiener_units.data_ptr(), len(wl.wiener_units), 8, s)
+
+    def call_wiener_filter(self, s):
+        rc = lib.svt_b200_wiener_units_dev(self.cdef_out.data_ptr(), self.final.data_ptr(), self.wiener_units.data_ptr(),
+                                           len(self.wl.wiener_units), 8, s)
         assert rc == 0
 
     STAGES = ("me", "tx", "cdef", "rest")
+    # (call, stage it belongs to, the kernels it launches)
+    CALLS = (("me_pyramid", "me", "downsample_2d_kernel+pad_plane_kernel"),
+             ("me_search", "me", "hme_prepare/sad_search_small/hme_finish x3 + me_centre_kernel + fullpel_search_kernel"),
+             ("fwd_txfm", "tx", "fwd_txfm_kernel<4..64>"),
+             ("quant", "tx", "quant_kernel"),
+             ("inv_txfm", "tx", "inv_txfm_kernel<4..64>"),
+             ("cdef_search", "cdef", "cdef_dir_kernel+cdef_search_kernel"),
+             ("cdef_apply", "cdef", "cdef_apply_kernel"),
+             ("rest_extend", "rest", "pad_plane_kernel"),
+             ("wiener_stats", "rest", "stats_sum_kernel+stats_mma_kernel+stats_finalize_kernel"),
+             ("wiener_filter", "rest", "wiener_convolve_kernel"))
+
+    def _stage(self, stage, s):
+        for name, st, _ in self.CALLS:
+            if st == stage:
+                getattr(self, "call_" + name)(s)
+
+    def stage_me(self, s):
+        self._stage("me", s)
+
+    def stage_tx(self, s):
+        self._stage("tx", s)
+
+    def stage_cdef(self, s):
+        self._stage("cdef", s)
+
+    def stage_rest(self, s):
+        self._stage("rest", s)
 
     def step(self, events=None):
-        """enqueue one frame of hot-path work on torch's current stream"""
+        """enqueue one frame of hot-path work on torch's current stream; `events`: len(CALLS)+1 CUDA events
+        recorded before every call and after the last one"""
         T = self.torch
         s = T.cuda.current_stream().cuda_stream
-        for i, name in enumerate(self.STAGES):
+        for i, (name, _, _) in enumerate(self.CALLS):
             if events is not None:
                 events[i].record()
-            getattr(self, "stage_" + name)(s)
+            getattr(self, "call_" + name)(s)
         if events is not None:
-            events[len(self.STAGES)].record()
+            events[len(self.CALLS)].record()

@@ -218,12 +218,32 @@ class FrameWorkload:
 
     # -- algorithmic bytes per frame -----------------------------------------------------------
     def algorithmic_bytes(self):
+        """SURVEY 8(d) figures, per call of the frame pipeline (8-bit: bpp = 1)"""
         W, H, R = self.width, self.height, self.n_refs
         n64 = ((W + 63) // 64) * ((H + 63) // 64)
-        n_samples = int(1.5 * W * H)
-        return {
-            "me": int((1 + R) * 1.3125 * W * H + n64 * R * 85 * 8),
-            "tx": int(n_samples * 24),          # (22 + 2*bpp) bytes per sample, bpp = 1
-            "cdef": int(2 * n_samples + n_samples + n64 * 2 * len(self.cdef_str_y) * 8),
-            "rest": int(2 * n_samples + len(self.stats_items) * (49 + 2401) * 8 + 2 * n_samples),
+        N = int(1.5 * W * H)  # samples = transform coefficients of the final pass
+        calls = {
+            "me_pyramid": int(1.3125 * W * H),                                    # full-res read + the two decimated levels written
+            "me_search": int((1 + R) * 1.3125 * W * H + n64 * R * 85 * 8),        # every pyramid read once + SAD/MV out
+            "fwd_txfm": 6 * N, "quant": 12 * N, "inv_txfm": 6 * N,               # (22 + 2 bpp) N in total
+            "cdef_search": int(2 * N + n64 * 2 * len(self.cdef_str_y) * 8),       # recon + source in, mse out
+            "cdef_apply": 2 * N,                                                  # recon in, filtered out
+            "rest_extend": 0,
+            "wiener_stats": int(2 * N + len(self.stats_items) * (49 + 2401) * 8),
+            "wiener_filter": 2 * N,
         }
+        stage_of = {"me_pyramid": "me", "me_search": "me", "fwd_txfm": "tx", "quant": "tx", "inv_txfm": "tx", "cdef_search": "cdef",
+                    "cdef_apply": "cdef", "rest_extend": "rest", "wiener_stats": "rest", "wiener_filter": "rest"}
+        out = dict(calls)
+        for st in ("me", "tx", "cdef", "rest"):
+            out[st] = sum(v for k, v in calls.items() if stage_of[k] == st)
+        return out
+
+    def wiener_stats_macs(self):
+        """multiply-accumulates of compute_stats: (win^2 (win^2 + 1) / 2 + win^2) per pixel"""
+        tot = 0
+        for it in self.stats_items:
+            win = int(it["wiener_win"])
+            w2 = win * win
+            tot += (int(it["h_end"]) - int(it["h_start"])) * (int(it["v_end"]) - int(it["v_start"])) * (w2 * (w2 + 1) // 2 + w2)
+        return tot
