@@ -72,19 +72,6 @@ void     lane_release(Lane* l);
 void     count_launch(int n = 1);
 void     txfm_tables_init();  // txfm.cu: uploads the transform constant tables
 
-// aligned-word view of `n` bytes at p: word(j) = bytes [4j, 4j+4) of the run; only words holding a valid byte are read
-struct ByteRun {
-    const uint32_t* w;
-    int shift, last;
-    __device__ __forceinline__ ByteRun(const uint8_t* p, int n) {
-        const uintptr_t a = reinterpret_cast<uintptr_t>(p);
-        w     = reinterpret_cast<const uint32_t*>(a & ~uintptr_t(3));
-        shift = (int)(a & 3) * 8;
-        last  = (int)(((a & 3) + n - 1) >> 2);
-    }
-    __device__ __forceinline__ uint32_t raw(int j) const { return __ldg(w + (j < last ? j : last)); }
-};
-
 // Side streams for calls whose launches are independent of each other: fork_streams() makes the side
 // streams wait for everything already enqueued on `user`, join_streams() makes `user` wait for them.
 // One set per host thread (events are re-recorded call after call; a wait keeps the record it saw).

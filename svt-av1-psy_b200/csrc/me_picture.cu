@@ -18,6 +18,7 @@
 // The search kernels are the ones behind the T1 entry points (sad.cu / me_pyramid.cu); the small
 // prepare/finish kernels only do the reference's window arithmetic, one thread per (ref, b64, region).
 #include "common.cuh"
+#include "sad_small.cuh"
 #include "../../include/svt_b200.h"
 
 namespace b200 {
@@ -67,60 +68,75 @@ __device__ __forceinline__ void hme_clip(int16_t org, int16_t& origin, int16_t& 
     if (round8) sa = (sa < 8) ? sa : (int16_t)(sa & ~0x07);
 }
 
-// level 0: 1/16 picture, 1: 1/4, 2: full
+// One HME search of region (sr_w, sr_h) of block (bx, by) at `level` (0: 1/16 picture, 1: 1/4, 2: full),
+// centred on the previous level's result (prev_x, prev_y; unused at level 0): hme_level_0/1/2 of
+// motion_estimation.c restated as "fill in the search item".
+__device__ __forceinline__ void hme_make_item(const SvtB200MePicture& cur, const SvtB200MePicture& rp, const SvtB200MeParams& p, int level,
+                                              int sr_w, int sr_h, int bx, int by, int16_t prev_x, int16_t prev_y,
+                                              SvtB200SadSearchItem& it_out, HmeSide& side_out) {
+    const int shift = 2 - level;
+    const int full_x = bx * 64, full_y = by * 64;
+    const int blk_w = min(64, cur.width[2] - full_x) >> shift, blk_h = min(64, cur.height[2] - full_y) >> shift;
+    const int16_t org_x = (int16_t)(full_x >> shift), org_y = (int16_t)(full_y >> shift);
+    int16_t sa_w, sa_h, ox, oy, pad_w, pad_h;
+    if (level == 0) {
+        sa_w = (int16_t)((p.hme_l0_sa_w + 7) & ~0x07);
+        sa_h = (int16_t)p.hme_l0_sa_h;
+        ox   = (int16_t)(-(int16_t)((sa_w * 2) >> 1) + sa_w * sr_w);
+        oy   = (int16_t)(-(int16_t)((sa_h * 2) >> 1) + sa_h * sr_h);
+        pad_w = (int16_t)(rp.org_x[0] - 1);
+        pad_h = (int16_t)(rp.org_y[0] - 1);
+    } else if (level == 1) {
+        sa_w = (int16_t)((p.hme_l1_sa_w + 7) & ~0x07);
+        sa_h = (int16_t)p.hme_l1_sa_h;
+        ox   = (int16_t)(-(sa_w >> 1) + (prev_x >> 1));
+        oy   = (int16_t)(-(sa_h >> 1) + (prev_y >> 1));
+        pad_w = (int16_t)(rp.org_x[1] - 1);
+        pad_h = (int16_t)(rp.org_y[1] - 1);
+    } else {
+        sa_w = (int16_t)((p.hme_l2_sa_w + 7) & ~0x07);
+        sa_h = (int16_t)p.hme_l2_sa_h;
+        ox   = (int16_t)(-(sa_w >> 1) + prev_x);
+        oy   = (int16_t)(-(sa_h >> 1) + prev_y);
+        pad_w = pad_h = 63;
+    }
+    hme_clip(org_x, ox, sa_w, pad_w, (int16_t)rp.width[level], true);
+    hme_clip(org_y, oy, sa_h, pad_h, (int16_t)rp.height[level], false);
+    const int sub = p.hme_sub_sad ? 1 : 0;
+    SvtB200SadSearchItem it;
+    it.src_off    = (uint64_t)(uintptr_t)(cur.plane[level] + (size_t)(cur.org_y[level] + org_y) * cur.stride[level] + cur.org_x[level] + org_x);
+    it.ref_off    = (uint64_t)(uintptr_t)(rp.plane[level] + (size_t)(rp.org_y[level] + org_y + oy) * rp.stride[level] + rp.org_x[level] + org_x + ox);
+    it.src_stride = (uint32_t)(cur.stride[level] << sub);
+    it.ref_stride = (uint32_t)(rp.stride[level] << sub);
+    it.ref_step   = (uint32_t)rp.stride[level];
+    it.block_w    = (uint16_t)blk_w;
+    it.block_h    = (uint16_t)(blk_h >> sub);
+    it.sa_w       = sa_w;
+    it.sa_h       = sa_h;
+    it.skip_search_line = 0;
+    it.reserved   = 0;
+    it_out   = it;
+    side_out = HmeSide{ox, oy};
+}
+
+__device__ __forceinline__ void hme_finish_one(const SvtB200SadSearchResult& q, const HmeSide& sd, const SvtB200MeParams& p, int level,
+                                               int16_t& out_x, int16_t& out_y, uint64_t& out_sad) {
+    const int mul = level == 0 ? 4 : (level == 1 ? 2 : 1);
+    uint64_t  sad = q.best_sad;
+    if (p.hme_sub_sad) sad *= 2;
+    out_sad = sad;
+    out_x   = (int16_t)((int16_t)(q.x + sd.origin_x) * mul);
+    out_y   = (int16_t)((int16_t)(q.y + sd.origin_y) * mul);
+}
+
 __global__ void hme_prepare_kernel(SvtB200MePicture cur, const SvtB200MePicture* __restrict__ refs, const SvtB200MeParams* __restrict__ prm,
                                    int n_refs, int n_b64, int b64_w, int level, const int16_t* __restrict__ prev_x,
                                    const int16_t* __restrict__ prev_y, SvtB200SadSearchItem* __restrict__ items, HmeSide* __restrict__ side) {
     const int total = n_refs * n_b64 * 4;
     for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
         const int reg = idx & 3, b = (idx >> 2) % n_b64, r = (idx >> 2) / n_b64;
-        const int sr_w = reg & 1, sr_h = reg >> 1;
-        const SvtB200MePicture rp = refs[r];
-        const SvtB200MeParams  p  = prm[r];
-        const int bx = b % b64_w, by = b / b64_w;
-        const int shift = 2 - level;
-        const int full_x = bx * 64, full_y = by * 64;
-        const int blk_w = min(64, cur.width[2] - full_x) >> shift, blk_h = min(64, cur.height[2] - full_y) >> shift;
-        const int16_t org_x = (int16_t)(full_x >> shift), org_y = (int16_t)(full_y >> shift);
-        int16_t sa_w, sa_h, ox, oy, pad_w, pad_h;
-        if (level == 0) {
-            sa_w = (int16_t)((p.hme_l0_sa_w + 7) & ~0x07);
-            sa_h = (int16_t)p.hme_l0_sa_h;
-            ox   = (int16_t)(-(int16_t)((sa_w * 2) >> 1) + sa_w * sr_w);
-            oy   = (int16_t)(-(int16_t)((sa_h * 2) >> 1) + sa_h * sr_h);
-            pad_w = (int16_t)(rp.org_x[0] - 1);
-            pad_h = (int16_t)(rp.org_y[0] - 1);
-        } else if (level == 1) {
-            sa_w = (int16_t)((p.hme_l1_sa_w + 7) & ~0x07);
-            sa_h = (int16_t)p.hme_l1_sa_h;
-            ox   = (int16_t)(-(sa_w >> 1) + (prev_x[idx] >> 1));
-            oy   = (int16_t)(-(sa_h >> 1) + (prev_y[idx] >> 1));
-            pad_w = (int16_t)(rp.org_x[1] - 1);
-            pad_h = (int16_t)(rp.org_y[1] - 1);
-        } else {
-            sa_w = (int16_t)((p.hme_l2_sa_w + 7) & ~0x07);
-            sa_h = (int16_t)p.hme_l2_sa_h;
-            ox   = (int16_t)(-(sa_w >> 1) + prev_x[idx]);
-            oy   = (int16_t)(-(sa_h >> 1) + prev_y[idx]);
-            pad_w = pad_h = 63;
-        }
-        hme_clip(org_x, ox, sa_w, pad_w, (int16_t)rp.width[level], true);
-        hme_clip(org_y, oy, sa_h, pad_h, (int16_t)rp.height[level], false);
-        const int sub = p.hme_sub_sad ? 1 : 0;
-        SvtB200SadSearchItem it;
-        it.src_off    = (uint64_t)(uintptr_t)(cur.plane[level] + (size_t)(cur.org_y[level] + org_y) * cur.stride[level] + cur.org_x[level] + org_x);
-        it.ref_off    = (uint64_t)(uintptr_t)(rp.plane[level] + (size_t)(rp.org_y[level] + org_y + oy) * rp.stride[level] + rp.org_x[level] + org_x + ox);
-        it.src_stride = (uint32_t)(cur.stride[level] << sub);
-        it.ref_stride = (uint32_t)(rp.stride[level] << sub);
-        it.ref_step   = (uint32_t)rp.stride[level];
-        it.block_w    = (uint16_t)blk_w;
-        it.block_h    = (uint16_t)(blk_h >> sub);
-        it.sa_w       = sa_w;
-        it.sa_h       = sa_h;
-        it.skip_search_line = 0;
-        it.reserved   = 0;
-        items[idx]    = it;
-        side[idx]     = HmeSide{ox, oy};
+        hme_make_item(cur, refs[r], prm[r], level, reg & 1, reg >> 1, b % b64_w, b / b64_w, level ? prev_x[idx] : (int16_t)0,
+                      level ? prev_y[idx] : (int16_t)0, items[idx], side[idx]);
     }
 }
 
@@ -128,19 +144,107 @@ __global__ void hme_finish_kernel(const SvtB200SadSearchResult* __restrict__ res
                                   const SvtB200MeParams* __restrict__ prm, int n_refs, int n_b64, int level, int16_t* __restrict__ out_x,
                                   int16_t* __restrict__ out_y, uint64_t* __restrict__ out_sad) {
     const int total = n_refs * n_b64 * 4;
-    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
-        const int r = (idx >> 2) / n_b64;
-        const SvtB200SadSearchResult q = res[idx];
-        const int mul = level == 0 ? 4 : (level == 1 ? 2 : 1);
-        uint64_t sad = q.best_sad;
-        if (prm[r].hme_sub_sad) sad *= 2;
-        out_sad[idx] = sad;
-        out_x[idx]   = (int16_t)((int16_t)(q.x + side[idx].origin_x) * mul);
-        out_y[idx]   = (int16_t)((int16_t)(q.y + side[idx].origin_y) * mul);
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x)
+        hme_finish_one(res[idx], side[idx], prm[(idx >> 2) / n_b64], level, out_x[idx], out_y[idx], out_sad[idx]);
+}
+
+// One warp per (ref, b64): final HME centre over the four regions' level-2 results (l2x/l2y/l2sad[4]),
+// optional zero-centre check, full-pel search item.
+__device__ __forceinline__ void me_centre_one(const SvtB200MePicture& cur, const SvtB200MePicture& rp, const SvtB200MeParams& p, int i,
+                                              int bx, int by, const int16_t* l2x, const int16_t* l2y, const uint64_t* l2sad,
+                                              int16_t* __restrict__ hme_sc, uint64_t* __restrict__ hme_sad,
+                                              SvtB200FullpelItem* __restrict__ items, int lane) {
+    // region scan order of set_final_seach_centre_sb: [w=0][h=0] first, then w inner / h outer, strict '<'
+    int16_t  cx = l2x[0], cy = l2y[0];
+    uint64_t cs = l2sad[0];
+    for (int reg = 1; reg < 4; reg++)
+        if (l2sad[reg] < cs) {
+            cs = l2sad[reg];
+            cx = l2x[reg];
+            cy = l2y[reg];
+        }
+    const int16_t org_x = (int16_t)(bx * 64), org_y = (int16_t)(by * 64);
+    const int blk_w = min(64, cur.width[2] - org_x), blk_h = min(64, cur.height[2] - org_y);
+    const uint8_t* src = cur.plane[2] + (size_t)(cur.org_y[2] + org_y) * cur.stride[2] + cur.org_x[2] + org_x;
+    int16_t sx = cx, sy = cy;
+    if (p.check_zero_centre && (sx != 0 || sy != 0)) {
+        // check_00_center: SADs on every other row (x2), zero MV wins ties
+        const int16_t pw = 63, ph = 63, W = (int16_t)rp.width[2], H = (int16_t)rp.height[2];
+        if ((int16_t)(org_x + sx) < -pw) sx = (int16_t)(-pw - org_x);
+        if ((int16_t)(org_x + sx) > (int16_t)(W - 1)) sx = (int16_t)(sx - ((org_x + sx) - (W - 1)));
+        if ((int16_t)(org_y + sy) < -ph) sy = (int16_t)(-ph - org_y);
+        if ((int16_t)(org_y + sy) > (int16_t)(H - 1)) sy = (int16_t)(sy - ((org_y + sy) - (H - 1)));
+        const uint8_t* r0 = rp.plane[2] + (size_t)(rp.org_y[2] + org_y) * rp.stride[2] + rp.org_x[2] + org_x;
+        const uint8_t* r1 = r0 + (ptrdiff_t)sy * rp.stride[2] + sx;
+        // lane = one of the (up to 32) rows that are summed; each row is walked word by word with
+        // funnel-shifted aligned loads, all of them independent (one global round trip per lane)
+        uint32_t z = 0, hsad = 0;
+        if (lane < (blk_h >> 1)) {
+            const int      yy = lane * 2, nw = (blk_w + 3) >> 2, tail = blk_w & 3;
+            const uint32_t tailmask = tail ? ((1u << (tail * 8)) - 1u) : 0xffffffffu;
+            const ByteRun  S(src + (size_t)yy * cur.stride[2], blk_w), A(r0 + (size_t)yy * rp.stride[2], blk_w),
+                B(r1 + (ptrdiff_t)yy * rp.stride[2], blk_w);
+            uint32_t slo = S.raw(0), alo = A.raw(0), blo = B.raw(0);
+#pragma unroll 4
+            for (int j = 0; j < nw; j++) {
+                const uint32_t shi = S.raw(j + 1), ahi = A.raw(j + 1), bhi = B.raw(j + 1);
+                const uint32_t m = j == nw - 1 ? tailmask : 0xffffffffu;
+                const uint32_t sv = __funnelshift_r(slo, shi, S.shift) & m;
+                z    = __vsadu4(sv, __funnelshift_r(alo, ahi, A.shift) & m) + z;
+                hsad = __vsadu4(sv, __funnelshift_r(blo, bhi, B.shift) & m) + hsad;
+                slo = shi;
+                alo = ahi;
+                blo = bhi;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            z += __shfl_xor_sync(0xffffffffu, z, o);
+            hsad += __shfl_xor_sync(0xffffffffu, hsad, o);
+        }
+        z <<= 1;
+        hsad <<= 1;
+        if (z <= hsad) sx = sy = 0;  // MIN(zero_cost, hme_cost) == zero_cost
+    }
+    if (lane == 0) {
+        hme_sc[2 * i]     = cx;
+        hme_sc[2 * i + 1] = cy;
+        hme_sad[i]        = cs;
+        // integer_search_b64 (:1296-1320, :1440-1496)
+        int16_t sa_w = (int16_t)((max(1, p.me_sa_w) + 7) & ~0x07), sa_h = (int16_t)max(3, p.me_sa_h);
+        int16_t ox = (int16_t)(sx - (sa_w >> 1)), oy = (int16_t)(sy - (sa_h >> 1));
+        const int16_t pw = 63, ph = 63, W = (int16_t)cur.width[2], H = (int16_t)cur.height[2];
+        {
+            const bool left = (int16_t)(org_x + ox) < -pw;
+            const int16_t nox = left ? (int16_t)(-pw - org_x) : ox;
+            // the reference evaluates the width correction with the ALREADY corrected origin
+            sa_w = ((int16_t)(org_x + nox) < -pw) ? (int16_t)(sa_w - (-pw - (org_x + nox))) : sa_w;
+            ox = nox;
+            ox = ((int16_t)(org_x + ox) > (int16_t)(W - 1)) ? (int16_t)(ox - ((org_x + ox) - (W - 1))) : ox;
+            sa_w = ((int16_t)(org_x + ox + sa_w) > W) ? (int16_t)max(1, sa_w - ((org_x + ox + sa_w) - W)) : sa_w;
+            sa_w = (sa_w < 8) ? sa_w : (int16_t)(sa_w & ~0x07);
+            const bool top = (int16_t)(org_y + oy) < -ph;
+            const int16_t noy = top ? (int16_t)(-ph - org_y) : oy;
+            sa_h = ((int16_t)(org_y + noy) < -ph) ? (int16_t)(sa_h - (-ph - (org_y + noy))) : sa_h;
+            oy = noy;
+            oy = ((int16_t)(org_y + oy) > (int16_t)(H - 1)) ? (int16_t)(oy - ((org_y + oy) - (H - 1))) : oy;
+            sa_h = ((int16_t)(org_y + oy + sa_h) > H) ? (int16_t)max(1, sa_h - ((org_y + oy + sa_h) - H)) : sa_h;
+        }
+        SvtB200FullpelItem it;
+        it.src_off    = (uint64_t)(uintptr_t)src;
+        it.ref_off    = (uint64_t)(uintptr_t)(rp.plane[2] + (ptrdiff_t)(rp.org_y[2] + org_y + oy) * rp.stride[2] + rp.org_x[2] + org_x + ox);
+        it.src_stride = (uint32_t)cur.stride[2];
+        it.ref_stride = (uint32_t)rp.stride[2];
+        it.sa_w = sa_w;
+        it.sa_h = sa_h;
+        it.org_x = ox;
+        it.org_y = oy;
+        it.sub_sad = (uint8_t)(p.me_sub_sad ? 1 : 0);
+        for (int k = 0; k < 7; k++) it.reserved[k] = 0;
+        items[i] = it;
     }
 }
 
-// one warp per (ref, b64): final HME centre, optional zero-centre check, full-pel search item
 __global__ void me_centre_kernel(SvtB200MePicture cur, const SvtB200MePicture* __restrict__ refs, const SvtB200MeParams* __restrict__ prm,
                                  int n_refs, int n_b64, int b64_w, const int16_t* __restrict__ l2x, const int16_t* __restrict__ l2y,
                                  const uint64_t* __restrict__ l2sad, int16_t* __restrict__ hme_sc /*[n][2]*/, uint64_t* __restrict__ hme_sad,
@@ -149,99 +253,41 @@ __global__ void me_centre_kernel(SvtB200MePicture cur, const SvtB200MePicture* _
     const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
     for (int i = wid; i < n_refs * n_b64; i += nw) {
         const int b = i % n_b64, r = i / n_b64;
-        const SvtB200MePicture rp = refs[r];
-        const SvtB200MeParams  p  = prm[r];
-        // region scan order of set_final_seach_centre_sb: [w=0][h=0] first, then w inner / h outer, strict '<'
-        int16_t  cx = l2x[i * 4], cy = l2y[i * 4];
-        uint64_t cs = l2sad[i * 4];
-        for (int reg = 1; reg < 4; reg++)
-            if (l2sad[i * 4 + reg] < cs) {
-                cs = l2sad[i * 4 + reg];
-                cx = l2x[i * 4 + reg];
-                cy = l2y[i * 4 + reg];
-            }
-        const int bx = b % b64_w, by = b / b64_w;
-        const int16_t org_x = (int16_t)(bx * 64), org_y = (int16_t)(by * 64);
-        const int blk_w = min(64, cur.width[2] - org_x), blk_h = min(64, cur.height[2] - org_y);
-        const uint8_t* src = cur.plane[2] + (size_t)(cur.org_y[2] + org_y) * cur.stride[2] + cur.org_x[2] + org_x;
-        int16_t sx = cx, sy = cy;
-        if (p.check_zero_centre && (sx != 0 || sy != 0)) {
-            // check_00_center: SADs on every other row (x2), zero MV wins ties
-            const int16_t pw = 63, ph = 63, W = (int16_t)rp.width[2], H = (int16_t)rp.height[2];
-            if ((int16_t)(org_x + sx) < -pw) sx = (int16_t)(-pw - org_x);
-            if ((int16_t)(org_x + sx) > (int16_t)(W - 1)) sx = (int16_t)(sx - ((org_x + sx) - (W - 1)));
-            if ((int16_t)(org_y + sy) < -ph) sy = (int16_t)(-ph - org_y);
-            if ((int16_t)(org_y + sy) > (int16_t)(H - 1)) sy = (int16_t)(sy - ((org_y + sy) - (H - 1)));
-            const uint8_t* r0 = rp.plane[2] + (size_t)(rp.org_y[2] + org_y) * rp.stride[2] + rp.org_x[2] + org_x;
-            const uint8_t* r1 = r0 + (ptrdiff_t)sy * rp.stride[2] + sx;
-            // lane = one of the (up to 32) rows that are summed; each row is walked word by word with
-            // funnel-shifted aligned loads, all of them independent (one global round trip per lane)
-            uint32_t z = 0, hsad = 0;
-            if (lane < (blk_h >> 1)) {
-                const int      yy = lane * 2, nw = (blk_w + 3) >> 2, tail = blk_w & 3;
-                const uint32_t tailmask = tail ? ((1u << (tail * 8)) - 1u) : 0xffffffffu;
-                const ByteRun  S(src + (size_t)yy * cur.stride[2], blk_w), A(r0 + (size_t)yy * rp.stride[2], blk_w),
-                    B(r1 + (ptrdiff_t)yy * rp.stride[2], blk_w);
-                uint32_t slo = S.raw(0), alo = A.raw(0), blo = B.raw(0);
-#pragma unroll 4
-                for (int j = 0; j < nw; j++) {
-                    const uint32_t shi = S.raw(j + 1), ahi = A.raw(j + 1), bhi = B.raw(j + 1);
-                    const uint32_t m = j == nw - 1 ? tailmask : 0xffffffffu;
-                    const uint32_t sv = __funnelshift_r(slo, shi, S.shift) & m;
-                    z    = __vsadu4(sv, __funnelshift_r(alo, ahi, A.shift) & m) + z;
-                    hsad = __vsadu4(sv, __funnelshift_r(blo, bhi, B.shift) & m) + hsad;
-                    slo = shi;
-                    alo = ahi;
-                    blo = bhi;
-                }
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                z += __shfl_xor_sync(0xffffffffu, z, o);
-                hsad += __shfl_xor_sync(0xffffffffu, hsad, o);
-            }
-            z <<= 1;
-            hsad <<= 1;
-            if (z <= hsad) sx = sy = 0;  // MIN(zero_cost, hme_cost) == zero_cost
-        }
-        if (lane == 0) {
-            hme_sc[2 * i]     = cx;
-            hme_sc[2 * i + 1] = cy;
-            hme_sad[i]        = cs;
-            // integer_search_b64 (:1296-1320, :1440-1496)
-            int16_t sa_w = (int16_t)((max(1, p.me_sa_w) + 7) & ~0x07), sa_h = (int16_t)max(3, p.me_sa_h);
-            int16_t ox = (int16_t)(sx - (sa_w >> 1)), oy = (int16_t)(sy - (sa_h >> 1));
-            const int16_t pw = 63, ph = 63, W = (int16_t)cur.width[2], H = (int16_t)cur.height[2];
-            {
-                const bool left = (int16_t)(org_x + ox) < -pw;
-                const int16_t nox = left ? (int16_t)(-pw - org_x) : ox;
-                // the reference evaluates the width correction with the ALREADY corrected origin
-                sa_w = ((int16_t)(org_x + nox) < -pw) ? (int16_t)(sa_w - (-pw - (org_x + nox))) : sa_w;
-                ox = nox;
-                ox = ((int16_t)(org_x + ox) > (int16_t)(W - 1)) ? (int16_t)(ox - ((org_x + ox) - (W - 1))) : ox;
-                sa_w = ((int16_t)(org_x + ox + sa_w) > W) ? (int16_t)max(1, sa_w - ((org_x + ox + sa_w) - W)) : sa_w;
-                sa_w = (sa_w < 8) ? sa_w : (int16_t)(sa_w & ~0x07);
-                const bool top = (int16_t)(org_y + oy) < -ph;
-                const int16_t noy = top ? (int16_t)(-ph - org_y) : oy;
-                sa_h = ((int16_t)(org_y + noy) < -ph) ? (int16_t)(sa_h - (-ph - (org_y + noy))) : sa_h;
-                oy = noy;
-                oy = ((int16_t)(org_y + oy) > (int16_t)(H - 1)) ? (int16_t)(oy - ((org_y + oy) - (H - 1))) : oy;
-                sa_h = ((int16_t)(org_y + oy + sa_h) > H) ? (int16_t)max(1, sa_h - ((org_y + oy + sa_h) - H)) : sa_h;
-            }
-            SvtB200FullpelItem it;
-            it.src_off    = (uint64_t)(uintptr_t)src;
-            it.ref_off    = (uint64_t)(uintptr_t)(rp.plane[2] + (ptrdiff_t)(rp.org_y[2] + org_y + oy) * rp.stride[2] + rp.org_x[2] + org_x + ox);
-            it.src_stride = (uint32_t)cur.stride[2];
-            it.ref_stride = (uint32_t)rp.stride[2];
-            it.sa_w = sa_w;
-            it.sa_h = sa_h;
-            it.org_x = ox;
-            it.org_y = oy;
-            it.sub_sad = (uint8_t)(p.me_sub_sad ? 1 : 0);
-            for (int k = 0; k < 7; k++) it.reserved[k] = 0;
-            items[i] = it;
-        }
+        me_centre_one(cur, refs[r], prm[r], i, b % b64_w, b / b64_w, l2x + i * 4, l2y + i * 4, l2sad + i * 4, hme_sc, hme_sad, items, lane);
     }
+}
+
+// The whole hierarchical search of one (ref, b64) pair in ONE CTA when every level's search area is small:
+// warp = search region; a warp runs level 0 -> 1 -> 2 for its region back to back (each level starts from
+// the same region's previous result, so nothing leaves the registers), the four level-2 results meet in
+// shared memory and warp 0 picks the centre and writes the full-pel item.  Replaces 3 x (prepare, search,
+// finish) + centre = 10 launches and their global round trips.
+__global__ void __launch_bounds__(128)
+hme_fused_kernel(SvtB200MePicture cur, const SvtB200MePicture* __restrict__ refs, const SvtB200MeParams* __restrict__ prm, int n_refs,
+                 int n_b64, int b64_w, int16_t* __restrict__ hme_sc, uint64_t* __restrict__ hme_sad, SvtB200FullpelItem* __restrict__ items) {
+    __shared__ int16_t  s_x[4], s_y[4];
+    __shared__ uint64_t s_sad[4];
+    const int i = blockIdx.x, reg = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = i % n_b64, r = i / n_b64, bx = b % b64_w, by = b / b64_w;
+    const SvtB200MePicture rp = refs[r];
+    const SvtB200MeParams  p  = prm[r];
+    int16_t  px = 0, py = 0;
+    uint64_t sad = 0;
+#pragma unroll 1
+    for (int level = 0; level < 3; level++) {
+        SvtB200SadSearchItem it;
+        HmeSide              sd;
+        hme_make_item(cur, rp, p, level, reg & 1, reg >> 1, bx, by, px, py, it, sd);
+        const unsigned long long best = sad_search_warp((const uint8_t*)(uintptr_t)it.src_off, (const uint8_t*)(uintptr_t)it.ref_off, it, lane);
+        hme_finish_one(sad_key_to_result(best), sd, p, level, px, py, sad);
+    }
+    if (lane == 0) {
+        s_x[reg]   = px;
+        s_y[reg]   = py;
+        s_sad[reg] = sad;
+    }
+    __syncthreads();
+    if (reg == 0) me_centre_one(cur, rp, p, i, bx, by, s_x, s_y, s_sad, hme_sc, hme_sad, items, lane);
 }
 
 struct MeWorkspace {
@@ -353,6 +399,11 @@ extern "C" int svt_b200_me_picture_dev(const SvtB200MePicture* cur, const SvtB20
         const int pos[3] = {((params[r].hme_l0_sa_w + 7) & ~7) * params[r].hme_l0_sa_h, ((params[r].hme_l1_sa_w + 7) & ~7) * params[r].hme_l1_sa_h,
                             ((params[r].hme_l2_sa_w + 7) & ~7) * params[r].hme_l2_sa_h};
         for (int l = 0; l < 3; l++) max_pos[l] = max_pos[l] > pos[l] ? max_pos[l] : pos[l];
+    }
+    if (max_pos[0] <= kSmallSearchMaxPos && max_pos[1] <= kSmallSearchMaxPos && max_pos[2] <= kSmallSearchMaxPos) {
+        hme_fused_kernel<<<pairs, 128, 0, st>>>(*cur, w.refs, w.prm, n_refs, n_b64, b64_w, d_hme_centre, d_hme_sad, w.fp_items);
+        B200_LAUNCH_CHECK();
+        return svt_b200_fullpel_search_batch_dev(nullptr, nullptr, w.fp_items, pairs, d_best_sad, d_best_mv, stream);
     }
     for (int level = 0; level < 3; level++) {
         hme_prepare_kernel<<<g, 256, 0, st>>>(*cur, w.refs, w.prm, n_refs, n_b64, b64_w, level, level ? w.x[level - 1] : nullptr,

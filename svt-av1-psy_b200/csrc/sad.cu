@@ -14,6 +14,7 @@
 // with shared-memory atomics and the winner is the minimum of the 64-bit key (sad<<32 | y<<16 | x),
 // which reproduces the raster-order first-minimum rule exactly.
 #include "common.cuh"
+#include "sad_small.cuh"
 #include "../../include/svt_b200.h"
 
 namespace b200 {
@@ -245,15 +246,7 @@ sad_search_kernel(const uint8_t* __restrict__ src_plane, const uint8_t* __restri
     }
 }
 
-// Small search areas (the 8x3 / 16x4 HME and ME refinements: a few dozen positions, blocks up to
-// 64x64): the work is a few hundred VABSDIFF4 per lane, so staging through shared memory and CTA
-// barriers would be the whole cost.  One WARP per item, no shared memory: lane = (x mod 8, row slice
-// of 4); a lane walks its rows with two sliding funnel-shift windows over aligned words that come
-// straight from L1 (the 8 x-lanes of a slice read the same sectors, the source word is a broadcast),
-// the 4 slices are added with two shuffles and the raster-order first minimum is the minimum of the
-// 64-bit key (sad<<32 | y<<16 | x), as in the tiled kernel.
-constexpr int kSmallSearchMaxPos = 256;
-constexpr int kSmallWarps        = 4;
+constexpr int kSmallWarps = 4;
 
 __global__ void __launch_bounds__(kSmallWarps * 32)
 sad_search_small_kernel(const uint8_t* __restrict__ src_plane, const uint8_t* __restrict__ ref_plane,
@@ -261,61 +254,8 @@ sad_search_small_kernel(const uint8_t* __restrict__ src_plane, const uint8_t* __
     const int it = blockIdx.x * kSmallWarps + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (it >= n_items) return;
     const SvtB200SadSearchItem item = items[it];
-    const int bw = item.block_w, bh = item.block_h, sa_w = item.sa_w, sa_h = item.sa_h;
-    unsigned long long best = ~0ull;
-    if (sa_w > 0 && sa_h > 0 && bw > 0 && bh > 0) {
-        const bool     skip = (bw == 16 && bh <= 16 && item.skip_search_line);
-        const int      xs = lane & 7, slice = lane >> 3;
-        const int      nw = (bw + 3) >> 2, tail = bw & 3;
-        const uint32_t tailmask = tail ? ((1u << (tail * 8)) - 1u) : 0xffffffffu;
-        const uint8_t* src0 = src_plane + item.src_off;
-        const uint8_t* ref0 = ref_plane + item.ref_off;
-        for (int y = 0; y < sa_h; y++) {
-            if (skip && ((y & 1) == 0)) continue;
-            for (int x0 = 0; x0 < sa_w; x0 += 8) {
-                const bool valid = x0 + xs < sa_w;
-                const int  x = valid ? x0 + xs : sa_w - 1;  // idle lanes shadow the last column (stays inside the window)
-                uint32_t   acc = 0;
-                for (int r = slice; r < bh; r += 4) {
-                    const ByteRun S(src0 + (size_t)r * item.src_stride, bw);
-                    const ByteRun R(ref0 + (size_t)y * item.ref_step + (size_t)r * item.ref_stride + x, bw);
-                    uint32_t slo = S.raw(0), rlo = R.raw(0);
-#pragma unroll 4
-                    for (int j = 0; j < nw - 1; j++) {
-                        const uint32_t shi = S.raw(j + 1), rhi = R.raw(j + 1);
-                        acc = __vsadu4(__funnelshift_r(slo, shi, S.shift), __funnelshift_r(rlo, rhi, R.shift)) + acc;
-                        slo = shi;
-                        rlo = rhi;
-                    }
-                    const uint32_t shi = S.raw(nw), rhi = R.raw(nw);
-                    acc = __vsadu4(__funnelshift_r(slo, shi, S.shift) & tailmask, __funnelshift_r(rlo, rhi, R.shift) & tailmask) + acc;
-                }
-                acc += __shfl_xor_sync(0xffffffffu, acc, 8);
-                acc += __shfl_xor_sync(0xffffffffu, acc, 16);
-                if (valid && acc < 0xffffffu) {
-                    const unsigned long long key = ((unsigned long long)acc << 32) | ((unsigned long long)(uint32_t)y << 16) | (unsigned long long)(uint32_t)x;
-                    best = key < best ? key : best;
-                }
-            }
-        }
-#pragma unroll
-        for (int o = 4; o > 0; o >>= 1) {  // the 4 slices hold identical keys; reduce over the 8 x-lanes
-            const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
-            best = other < best ? other : best;
-        }
-    }
-    if (lane == 0) {
-        SvtB200SadSearchResult r;
-        if (best == ~0ull) {
-            r.best_sad = 0xffffffu;
-            r.x = r.y = -1;
-        } else {
-            r.best_sad = (uint32_t)(best >> 32);
-            r.y        = (int16_t)((best >> 16) & 0xffff);
-            r.x        = (int16_t)(best & 0xffff);
-        }
-        results[it] = r;
-    }
+    const unsigned long long best = sad_search_warp(src_plane + item.src_off, ref_plane + item.ref_off, item, lane);
+    if (lane == 0) results[it] = sad_key_to_result(best);
 }
 
 // K3: one CTA (one warp) per single-SAD item is overkill; T1 callers ask for one block at a time.
