@@ -224,6 +224,7 @@ def main():
     ap.add_argument("--height", type=int, default=1080)
     ap.add_argument("--check", action="store_true", help="compare one frame of B200 output with the reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying one CUDA graph per step")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -236,7 +237,8 @@ def main():
     config = {"workload": "configs[1]: 1920x1080 8-bit 4:2:0 synthetic, preset 8 CRF 30 hot path (ME 2 refs + TX + CDEF + Wiener), 1 frame/step",
               "width": args.width, "height": args.height, "frame_sets": N_FRAME_SETS,
               "l2": "steps rotate over %d distinct frame sets (~65 MB each, >126 MB L2 in total)" % N_FRAME_SETS,
-              "parallelism": "frame-parallel x%d (no data-path collective; recon exchange = all_gather of the filtered frame)" % world}
+              "parallelism": "frame-parallel x%d (no data-path collective; recon exchange = all_gather of the filtered frame)" % world,
+              "launch": "eager" if args.no_graph else "one CUDA graph replay per step (the step's kernel launches captured once per frame set)"}
 
     if args.impl == "reference":
         if rank != 0:
@@ -277,6 +279,24 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    graphs = [None] * N_FRAME_SETS
+
+    def enqueue_step(i, events=None):
+        """one frame of hot-path work on the current stream: replay of the frame set's CUDA graph (the ~35
+        kernel launches of a step captured once; same kernels, same work) or, for per-call timing, eager"""
+        g = graphs[i % N_FRAME_SETS]
+        if g is not None and events is None:
+            g.replay()
+        else:
+            sets[i % N_FRAME_SETS].step(events)
+
+    def capture_graphs():
+        for k, fp in enumerate(sets):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=stream):
+                fp.step()
+            graphs[k] = g
+
     def run(n, e2e, stage_acc=None):
         ev = [[torch.cuda.Event(enable_timing=True) for _ in range(N_CALLS + 1)] for _ in range(n)] if stage_acc is not None else None
         with torch.cuda.stream(stream):
@@ -286,7 +306,7 @@ def main():
                 fp = sets[i % N_FRAME_SETS]
                 if e2e:
                     fp.load_inputs()
-                fp.step(ev[i] if ev else None)
+                enqueue_step(i, ev[i] if ev else None)
                 if world > 1:  # reconstructed-reference exchange (the path's one real collective)
                     dist.all_gather_into_tensor(gathered.view(-1), fp.final)
                 if e2e:
@@ -320,7 +340,7 @@ def main():
                 ev_in[i].record(s_in)
             with torch.cuda.stream(stream):
                 stream.wait_event(ev_in[i])
-                fp.step()
+                enqueue_step(i)
                 if world > 1:
                     dist.all_gather_into_tensor(gathered.view(-1), fp.final)
                 ev_done[i].record(stream)
@@ -339,12 +359,18 @@ def main():
     # ---- resident-input timing ---------------------------------------------------------------------------
     run(warmup, False)
     barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    # per-call profile: eager launches with an event around every T2 call (not part of the timed value)
     l0 = dsp.launch_count()
     call_ms = [0.0] * N_CALLS
-    ms = run(args.steps, False, call_ms)
+    ms_eager = run(args.steps, False, call_ms)
     launches = dsp.launch_count() - l0
+    if not args.no_graph:
+        capture_graphs()
+        run(warmup, False)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ms = run(args.steps, False)
     barrier()
     # ---- end-to-end timing -----------------------------------------------------------------------------------
     run_e2e(warmup)
@@ -394,7 +420,7 @@ def main():
            "data": "synthetic", "config": config, "clocks": clocks,
            "e2e": {"value": round(fps_e2e, 2), "unit": "frames/s", "h2d_bytes_per_step": int(sets[0].h2d_bytes), "d2h_bytes_per_step": int(sets[0].d2h_bytes),
                    "ms_per_step": round(ms_e2e / args.steps, 4)},
-           "gpu_launches": int(launches), "roofline": roofline,
+           "gpu_launches": int(launches), "eager_ms_per_step": round(ms_eager / args.steps, 4), "roofline": roofline,
            "stages_ms": {n: round(v, 4) for n, v in zip(names, stage_ms)},
            "calls_ms": {c[0]: round(v, 4) for c, v in zip(calls, call_ms)},
            "calls_algorithmic_gbs": {c[0]: round(alg[c[0]] / (v / 1e3) / 1e9, 2) for c, v in zip(calls, call_ms) if v > 0}}

@@ -262,15 +262,19 @@ __global__ void me_centre_kernel(SvtB200MePicture cur, const SvtB200MePicture* _
 // the same region's previous result, so nothing leaves the registers), the four level-2 results meet in
 // shared memory and warp 0 picks the centre and writes the full-pel item.  Replaces 3 x (prepare, search,
 // finish) + centre = 10 launches and their global round trips.
+struct MeRefTable {  // passed by value: the descriptors reach the kernel with the launch, no copy to wait for
+    SvtB200MePicture pic[16];
+    SvtB200MeParams  prm[16];
+};
 __global__ void __launch_bounds__(128)
-hme_fused_kernel(SvtB200MePicture cur, const SvtB200MePicture* __restrict__ refs, const SvtB200MeParams* __restrict__ prm, int n_refs,
-                 int n_b64, int b64_w, int16_t* __restrict__ hme_sc, uint64_t* __restrict__ hme_sad, SvtB200FullpelItem* __restrict__ items) {
+hme_fused_kernel(const SvtB200MePicture cur, const __grid_constant__ MeRefTable tab, int n_refs, int n_b64, int b64_w,
+                 int16_t* __restrict__ hme_sc, uint64_t* __restrict__ hme_sad, SvtB200FullpelItem* __restrict__ items) {
     __shared__ int16_t  s_x[4], s_y[4];
     __shared__ uint64_t s_sad[4];
     const int i = blockIdx.x, reg = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b = i % n_b64, r = i / n_b64, bx = b % b64_w, by = b / b64_w;
-    const SvtB200MePicture rp = refs[r];
-    const SvtB200MeParams  p  = prm[r];
+    const SvtB200MePicture rp = tab.pic[r];
+    const SvtB200MeParams  p  = tab.prm[r];
     int16_t  px = 0, py = 0;
     uint64_t sad = 0;
 #pragma unroll 1
@@ -389,8 +393,6 @@ extern "C" int svt_b200_me_picture_dev(const SvtB200MePicture* cur, const SvtB20
     std::lock_guard<std::mutex> lk(g_me_mu);
     me_ws_reserve((size_t)pairs);
     MeWorkspace& w = g_me_ws;
-    B200_CUDA_CHECK(cudaMemcpyAsync(w.refs, refs, n_refs * sizeof(SvtB200MePicture), cudaMemcpyHostToDevice, st));
-    B200_CUDA_CHECK(cudaMemcpyAsync(w.prm, params, n_refs * sizeof(SvtB200MeParams), cudaMemcpyHostToDevice, st));
     const int g = grid_for((n4 + 255) / 256, 8);
     int max_l0_w = 8, max_l0_h = 1, max_pos[3] = {1, 1, 1};
     for (int r = 0; r < n_refs; r++) {
@@ -401,10 +403,16 @@ extern "C" int svt_b200_me_picture_dev(const SvtB200MePicture* cur, const SvtB20
         for (int l = 0; l < 3; l++) max_pos[l] = max_pos[l] > pos[l] ? max_pos[l] : pos[l];
     }
     if (max_pos[0] <= kSmallSearchMaxPos && max_pos[1] <= kSmallSearchMaxPos && max_pos[2] <= kSmallSearchMaxPos) {
-        hme_fused_kernel<<<pairs, 128, 0, st>>>(*cur, w.refs, w.prm, n_refs, n_b64, b64_w, d_hme_centre, d_hme_sad, w.fp_items);
+        MeRefTable tab;
+        memset(&tab, 0, sizeof(tab));
+        memcpy(tab.pic, refs, n_refs * sizeof(SvtB200MePicture));
+        memcpy(tab.prm, params, n_refs * sizeof(SvtB200MeParams));
+        hme_fused_kernel<<<pairs, 128, 0, st>>>(*cur, tab, n_refs, n_b64, b64_w, d_hme_centre, d_hme_sad, w.fp_items);
         B200_LAUNCH_CHECK();
         return svt_b200_fullpel_search_batch_dev(nullptr, nullptr, w.fp_items, pairs, d_best_sad, d_best_mv, stream);
     }
+    B200_CUDA_CHECK(cudaMemcpyAsync(w.refs, refs, n_refs * sizeof(SvtB200MePicture), cudaMemcpyHostToDevice, st));
+    B200_CUDA_CHECK(cudaMemcpyAsync(w.prm, params, n_refs * sizeof(SvtB200MeParams), cudaMemcpyHostToDevice, st));
     for (int level = 0; level < 3; level++) {
         hme_prepare_kernel<<<g, 256, 0, st>>>(*cur, w.refs, w.prm, n_refs, n_b64, b64_w, level, level ? w.x[level - 1] : nullptr,
                                               level ? w.y[level - 1] : nullptr, w.items, w.side);

@@ -68,20 +68,29 @@ __device__ __forceinline__ unsigned long long sad_search_warp(const uint8_t* __r
                 const ByteRun R0(rrow + (size_t)min(y0 + 0, sa_h - 1) * item.ref_step, bw), R1(rrow + (size_t)min(y0 + 1, sa_h - 1) * item.ref_step, bw),
                     R2(rrow + (size_t)min(y0 + 2, sa_h - 1) * item.ref_step, bw), R3(rrow + (size_t)min(y0 + 3, sa_h - 1) * item.ref_step, bw);
                 uint32_t slo = S.raw(0), r0 = R0.raw(0), r1 = R1.raw(0), r2 = R2.raw(0), r3 = R3.raw(0);
-#pragma unroll 2
-                for (int j = 0; j < nw; j++) {
-                    const uint32_t m  = j == nw - 1 ? tailmask : 0xffffffffu;
-                    const uint32_t shi = S.raw(j + 1), h0 = R0.raw(j + 1), h1 = R1.raw(j + 1), h2 = R2.raw(j + 1), h3 = R3.raw(j + 1);
-                    const uint32_t sv = __funnelshift_r(slo, shi, S.shift) & m;  // one source word against four search rows
-                    acc[0] = __vsadu4(sv, __funnelshift_r(r0, h0, R0.shift) & m) + acc[0];
-                    acc[1] = __vsadu4(sv, __funnelshift_r(r1, h1, R1.shift) & m) + acc[1];
-                    acc[2] = __vsadu4(sv, __funnelshift_r(r2, h2, R2.shift) & m) + acc[2];
-                    acc[3] = __vsadu4(sv, __funnelshift_r(r3, h3, R3.shift) & m) + acc[3];
+                // all words but the last: the next aligned word always holds valid bytes, nothing to mask
+#pragma unroll 4
+                for (int j = 0; j < nw - 1; j++) {
+                    const uint32_t shi = __ldg(S.w + j + 1), h0 = __ldg(R0.w + j + 1), h1 = __ldg(R1.w + j + 1), h2 = __ldg(R2.w + j + 1),
+                                   h3 = __ldg(R3.w + j + 1);
+                    const uint32_t sv = __funnelshift_r(slo, shi, S.shift);  // one source word against four search rows
+                    acc[0] = __vsadu4(sv, __funnelshift_r(r0, h0, R0.shift)) + acc[0];
+                    acc[1] = __vsadu4(sv, __funnelshift_r(r1, h1, R1.shift)) + acc[1];
+                    acc[2] = __vsadu4(sv, __funnelshift_r(r2, h2, R2.shift)) + acc[2];
+                    acc[3] = __vsadu4(sv, __funnelshift_r(r3, h3, R3.shift)) + acc[3];
                     slo = shi;
                     r0  = h0;
                     r1  = h1;
                     r2  = h2;
                     r3  = h3;
+                }
+                {  // last word: the following aligned word may lie past the row (clamped index), bytes past bw are masked
+                    const uint32_t shi = S.raw(nw), h0 = R0.raw(nw), h1 = R1.raw(nw), h2 = R2.raw(nw), h3 = R3.raw(nw);
+                    const uint32_t sv = __funnelshift_r(slo, shi, S.shift) & tailmask;
+                    acc[0] = __vsadu4(sv, __funnelshift_r(r0, h0, R0.shift) & tailmask) + acc[0];
+                    acc[1] = __vsadu4(sv, __funnelshift_r(r1, h1, R1.shift) & tailmask) + acc[1];
+                    acc[2] = __vsadu4(sv, __funnelshift_r(r2, h2, R2.shift) & tailmask) + acc[2];
+                    acc[3] = __vsadu4(sv, __funnelshift_r(r3, h3, R3.shift) & tailmask) + acc[3];
                 }
             }
 #pragma unroll

@@ -448,51 +448,40 @@ stats_mma_kernel(const uint8_t* __restrict__ dgd_base, const uint8_t* __restrict
     else stats_mma_body<3>(dgd, src, s, avg, part, ctas_per_item, P, tile, s32);
 }
 
-__global__ void stats_finalize_kernel(const long long* __restrict__ partial, int parts, const SvtB200StatsItem* __restrict__ items,
-                                      int n_items, int divider, int mma_layout, long long* __restrict__ M_out,
-                                      long long* __restrict__ H_out) {
-    __shared__ long long A[2450];
-    for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
-        const int win = items[it].wiener_win, win2 = win * win;
-        const int used = mma_layout ? stats_mma_parts(items[it], parts) : parts;
-        __syncthreads();
-        for (int i = threadIdx.x; i < (mma_layout ? kMmaAccMax : 2450); i += blockDim.x) {
-            long long v = 0;
-            for (int p = 0; p < used; p++) v += partial[((size_t)it * parts + p) * 2450 + i];
-            A[i] = v;
-        }
-        __syncthreads();
-        long long* M = M_out + (size_t)it * 49;
-        long long* H = H_out + (size_t)it * 2401;
+// One thread per output element: it knows where its accumulator sits in a partial, adds that entry of
+// every part that was written, applies the bit-depth divider.  grid = (ceil(2450 / 256), n_items).
+__global__ void __launch_bounds__(256)
+stats_finalize_kernel(const long long* __restrict__ partial, int parts, const SvtB200StatsItem* __restrict__ items, int divider,
+                      int mma_layout, long long* __restrict__ M_out, long long* __restrict__ H_out) {
+    const int it = blockIdx.y, e = blockIdx.x * blockDim.x + threadIdx.x;
+    const int win = items[it].wiener_win, win2 = win * win;
+    if (e >= win2 * win2 + win2) return;
+    const int used = mma_layout ? stats_mma_parts(items[it], parts) : parts;
+    int       src;
+    if (e < win2 * win2) {
+        const int k = e / win2, l = e - k * win2;
+        int ka = k / win, kq = k - ka * win, la = l / win, lq = l - la * win;
         if (mma_layout) {
             // accumulator (row i = 8*kx+ky, column j) of the MMA lives in tile (i/16, j/8), C-fragment
-            // register ((i/8)&1)*2 + (j&1) of lane (i&7)*4 + (j&7)/2; M is matrix row 7
-            for (int k = threadIdx.x; k < win2; k += blockDim.x) {
-                const int ka = k / win, kq = k - ka * win;
-                M[k] = A[(mma_tile_index(win, 0, ka) * 4 + (kq & 1)) * 32 + 28 + (kq >> 1)] / divider;
+            // register ((i/8)&1)*2 + (j&1) of lane (i&7)*4 + (j&7)/2; only tiles with kx_i <= kx_j exist
+            if (ka > la) {
+                int x = ka; ka = la; la = x;
+                x = kq; kq = lq; lq = x;
             }
-            for (int p = threadIdx.x; p < win2 * win2; p += blockDim.x) {
-                const int k = p / win2, l = p - k * win2;
-                int ka = k / win, kq = k - ka * win, la = l / win, lq = l - la * win;
-                if (ka > la) {
-                    int x = ka; ka = la; la = x;
-                    x = kq; kq = lq; lq = x;
-                }
-                const int idx = mma_tile_index(win, ka >> 1, la), reg = (ka & 1) * 2 + (lq & 1), lane = kq * 4 + (lq >> 1);
-                H[p] = A[(idx * 4 + reg) * 32 + lane] / divider;
-            }
-            continue;
-        }
-        for (int k = threadIdx.x; k < win2; k += blockDim.x) M[k] = A[2401 + k] / divider;
-        for (int p = threadIdx.x; p < win2 * win2; p += blockDim.x) {
-            const int k = p / win2, l = p - k * win2;
+            src = (mma_tile_index(win, ka >> 1, la) * 4 + (ka & 1) * 2 + (lq & 1)) * 32 + kq * 4 + (lq >> 1);
+        } else {
             // tiles were accumulated for window-column pairs a<=b only: element (k,l) lives in the
             // tile of (k/win, l/win) when k/win <= l/win, else in its mirror
-            const int ka = k / win, la = l / win;
-            const long long v = (ka <= la) ? A[k * win2 + l] : A[l * win2 + k];
-            H[p] = v / divider;
+            src = (ka <= la) ? k * win2 + l : l * win2 + k;
         }
+    } else {
+        const int k = e - win2 * win2, ka = k / win, kq = k - ka * win;
+        src = mma_layout ? (mma_tile_index(win, 0, ka) * 4 + (kq & 1)) * 32 + 28 + (kq >> 1) : 2401 + k;  // M = matrix row 7
     }
+    long long v = 0;
+    for (int p = 0; p < used; p++) v += partial[((size_t)it * parts + p) * 2450 + src];
+    if (e < win2 * win2) H_out[(size_t)it * 2401 + e] = v / divider;
+    else M_out[(size_t)it * 49 + (e - win2 * win2)] = v / divider;
 }
 
 static long long* g_stats_acc = nullptr;
@@ -521,7 +510,7 @@ static void launch_stats(const PIX* d_dgd, const PIX* d_src, const SvtB200StatsI
         stats_accum_kernel<PIX><<<n * cpi, kStatsWarps * 32, 0, st>>>(d_dgd, d_src, d_items, d_tot, cpi, d_acc, (int)fp);
     }
     B200_LAUNCH_CHECK();
-    stats_finalize_kernel<<<grid_for(n, 4), 256, 0, st>>>(d_acc, cpi, d_items, n, divider, sizeof(PIX) == 1, d_M, d_H);
+    stats_finalize_kernel<<<dim3((2450 + 255) / 256, n), 256, 0, st>>>(d_acc, cpi, d_items, divider, sizeof(PIX) == 1, d_M, d_H);
     B200_LAUNCH_CHECK();
 }
 
