@@ -32,7 +32,7 @@ sys.path.insert(0, ROOT)
 
 METRIC = "1080p preset-8 hot-path (ME + transform/quant + CDEF + Wiener) frames/sec"
 N_FRAME_SETS = 4  # rotated between steps so that consecutive steps do not hit a warm L2
-N_CALLS = 10      # len(FramePipeline.CALLS): the T2 entry points one frame goes through
+N_CALLS = 8       # len(FramePipeline.CALLS): the T2 entry points one frame goes through
 # dram__bytes_read.sum + dram__bytes_write.sum of the call's dominant kernel, per launch, from the ncu --set full
 # capture of this same command (profiles/README.md says which file); None = not captured for that call
 NCU_DRAM_SOURCE = "profiles/r1_top_kernels_ncu_raw.csv"
@@ -444,15 +444,32 @@ def check_against_reference(fp, torch):
     fp.load_inputs()
     fp.step()
     torch.cuda.synchronize()
-    cmp = [("me_sad", fp.me_sad, fr.me_sad), ("me_mv", fp.me_mv, fr.me_mv), ("hme_centre", fp.me_centre, fr.me_c), ("coeff", fp.coeff, fr.coeff),
+    cmp = [("me_sad", fp.me_sad, fr.me_sad), ("me_mv", fp.me_mv, fr.me_mv), ("hme_centre", fp.me_centre, fr.me_c),
            ("qcoeff", fp.qcoeff, fr.q), ("dqcoeff", fp.dqcoeff, fr.dq), ("eob", fp.eobs, fr.eobs), ("recon", fp.recon, fr.recon),
            ("cdef_mse", fp.cdef_mse, fr.mse), ("cdef_dir", fp.cdef_dir, fr.dirs), ("cdef_out", fp.cdef_out, fr.cdef_out), ("wiener_M", fp.M, fr.M),
            ("wiener_H", fp.Hm, fr.Hm), ("final", fp.final, fr.final)]
     bad = []
-    for name, a, b in cmp:
-        a = a.cpu().numpy()
-        if not np.array_equal(a.view(np.uint8).reshape(-1), np.ascontiguousarray(b).view(np.uint8).reshape(-1)):
-            bad.append(name)
+
+    def compare(items):
+        for name, a, b in items:
+            a = a.cpu().numpy()
+            if not np.array_equal(a.view(np.uint8).reshape(-1), np.ascontiguousarray(b).view(np.uint8).reshape(-1)):
+                bad.append(name)
+
+    compare(cmp)
+    # the frame step uses the fused transform call; the same chain as three separate calls (which also
+    # materialises the forward coefficients) must give the same answers
+    s = torch.cuda.current_stream().cuda_stream
+    for t in (fp.qcoeff, fp.dqcoeff, fp.eobs, fp.recon):
+        t.zero_()
+    fp.call_fwd_txfm(s)
+    fp.call_quant(s)
+    fp.call_inv_txfm(s)
+    torch.cuda.synchronize()
+    split = [("coeff", fp.coeff, fr.coeff), ("qcoeff/3-call", fp.qcoeff, fr.q), ("dqcoeff/3-call", fp.dqcoeff, fr.dq),
+             ("eob/3-call", fp.eobs, fr.eobs), ("recon/3-call", fp.recon, fr.recon)]
+    compare(split)
+    cmp = cmp + split
     if bad:
         raise SystemExit("PARITY FAILURE vs reference: " + ", ".join(bad))
     print("parity vs reference C tier: all %d outputs bit-exact" % len(cmp), file=sys.stderr)

@@ -249,6 +249,22 @@ SVT_B200_API int svt_b200_quant_batch_dev(const int32_t* d_coeff, int32_t* d_qco
                                           const int16_t* d_scan, const int16_t* d_iscan, const uint8_t* d_qm,
                                           const SvtB200QuantItem* d_items, int n_items, uint16_t* d_eobs, void* stream);
 
+/* Fused per-block chain of the final encode pass (coding_loop.c:405-658): forward transform -> quantise
+ * -> inverse transform + reconstruction, one call, intermediates kept on chip.  Item = the three items
+ * the separate calls take (fwd.dst_off, quant.coeff_off and inv.coef_off are ignored; the forward output
+ * is always the packed min(W,32) x min(H,32) block).  Same ordering rule (team classes) as the transform
+ * batches; d_eobs[i] belongs to item i; d_dqcoeff may be NULL.  Results are bit-identical to
+ * svt_b200_fwd_txfm_batch_dev + svt_b200_quant_batch_dev + svt_b200_inv_txfm_batch_dev. */
+typedef struct SvtB200TrioItem {
+    SvtB200FwdTxfmItem fwd;
+    SvtB200QuantItem   quant;
+    SvtB200InvTxfmItem inv;
+} SvtB200TrioItem;
+SVT_B200_API int svt_b200_txfm_trio_batch_dev(const int16_t* d_residual, const void* d_pred, void* d_recon, int32_t* d_qcoeff,
+                                              int32_t* d_dqcoeff, const int16_t* d_iscan, const uint8_t* d_qm,
+                                              const SvtB200TrioItem* d_items, const int n_per_class[SVT_B200_TXFM_CLASSES],
+                                              uint16_t* d_eobs, int pixel_bytes, void* stream);
+
 /* ------------------------------------------------------------------------------------------ */
 /* K4  Hadamard / SATD  (reference: Source/Lib/C_DEFAULT/picture_operators_c.c:188-330)        */
 /* ------------------------------------------------------------------------------------------ */

@@ -11,6 +11,7 @@
 // block sits in shared memory in element-major order with an odd pitch, so the passes and the
 // transposing hand-over are bank-conflict free; residual loads / coefficient stores are coalesced rows.
 #include "txfm_tables.cuh"
+#include "quant_one.cuh"
 #include "../../include/svt_b200.h"
 
 namespace b200 {
@@ -157,6 +158,125 @@ inv_txfm_kernel(const int32_t* __restrict__ coef_base, const PIX* __restrict__ p
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// fused: forward transform -> quantise -> inverse transform + reconstruction of one block
+// (the per-block chain of the final encode pass, coding_loop.c:405-658) without leaving shared memory:
+// the coefficients and the dequantised levels never travel through HBM between the three steps.
+// ------------------------------------------------------------------------------------------------
+template <int TEAM, int THREADS, typename PIX>
+__global__ void __launch_bounds__(THREADS)
+trio_txfm_kernel(const int16_t* __restrict__ src_base, const PIX* __restrict__ pred_base, PIX* __restrict__ recon_base,
+                 int32_t* __restrict__ q_base, int32_t* __restrict__ dq_base /*may be null*/, const int16_t* __restrict__ iscan_base,
+                 const uint8_t* __restrict__ qm_base, const SvtB200TrioItem* __restrict__ items, int n_items,
+                 uint16_t* __restrict__ eobs) {
+    extern __shared__ __align__(16) int32_t tsm[];
+    constexpr int TEAMS = TEAM >= 64 ? 1 : THREADS / TEAM, PLANE = TEAM * (TEAM + 1), MOVERS = TEAM >= 64 ? THREADS : TEAM;
+    const int     team  = TEAM >= 64 ? 0 : threadIdx.x / TEAM, tid = TEAM >= 64 ? threadIdx.x : threadIdx.x % TEAM;
+    int32_t*      A     = tsm + (size_t)team * 2 * PLANE;
+    int32_t*      B     = A + PLANE;
+    __shared__ int s_eob;
+
+    for (int it = blockIdx.x * TEAMS + team; it < n_items; it += gridDim.x * TEAMS) {
+        const SvtB200TrioItem& item = items[it];
+        const int   sz = item.fwd.tx_size, W = tx_w(sz), H = tx_h(sz), bd = item.inv.bd;
+        const int   lgW = 31 - __clz(W);
+        const TxCfg cfg = c_txcfg[sz][item.fwd.tx_type];
+        const int   rect = rect_log_ratio(W, H);
+        const int   Wp = W > 32 ? 32 : W, Hp = H > 32 ? 32 : H;
+        {   // ---- forward (fwd_txfm_kernel) ----
+            const int16_t* src = src_base + item.fwd.src_off;
+            const int P1 = W + 1, P2 = H + 1, sstride = item.fwd.src_stride;
+            for (int idx = tid; idx < W * H; idx += MOVERS) {
+                const int r = idx >> lgW, c = idx & (W - 1);
+                const int rr = cfg.f_ud ? (H - 1 - r) : r;
+                A[r * P1 + c] = round_shift_arr((int32_t)src[(size_t)rr * sstride + c], -cfg.f_s0);
+            }
+            team_sync<TEAM>();
+            txfm_pass_1d<TEAM, false>(cfg.f_tc, A, H, W, P1, cfg.f_cbc, 0, tid);
+            team_sync<TEAM>();
+            for (int idx = tid; idx < W * H; idx += MOVERS) {
+                const int r = idx >> lgW, c = idx & (W - 1);
+                const int cc = cfg.f_lr ? (W - 1 - c) : c;
+                B[cc * P2 + r] = round_shift_arr(A[r * P1 + c], -cfg.f_s1);
+            }
+            team_sync<TEAM>();
+            txfm_pass_1d<TEAM, false>(cfg.f_tr, B, W, H, P2, cfg.f_cbr, 0, tid);
+            team_sync<TEAM>();
+        }
+        {   // ---- quantise the (packed) coefficients; the dequantised levels become the inverse's input plane ----
+            const SvtB200QuantItem qi = item.quant;
+            const uint8_t* qm  = qi.qm_off == SVT_B200_NO_QM ? nullptr : qm_base + qi.qm_off;
+            const uint8_t* iqm = qi.iqm_off == SVT_B200_NO_QM ? nullptr : qm_base + qi.iqm_off;
+            const int16_t* iscan = iscan_base + qi.scan_off;
+            int32_t*       qc = q_base + qi.q_off;
+            int32_t*       dqc = dq_base ? dq_base + qi.dq_off : nullptr;
+            const int P2 = H + 1, P1i = H + 1;  // forward result: B[c*P2 + r]; inverse input: A[c*P1i + r]
+            const int row_clamp = bd + 8;
+            if (TEAM >= 64 && threadIdx.x == 0) s_eob = 0;
+            int eob = 0;
+            for (int idx = tid; idx < W * H; idx += MOVERS) {
+                const int r = idx >> lgW, c = idx & (W - 1);
+                int32_t   dq = 0;
+                if (r < Hp && c < Wp) {
+                    int32_t v = round_shift_arr(B[c * P2 + r], -cfg.f_s2);
+                    if (rect == 1 || rect == -1) v = round_shift64((long long)v * kNewSqrt2, 12);
+                    const int rc = r * Wp + c;
+                    int32_t   q;
+                    quant_one(qi, v, rc, qm, iqm, q, dq);
+                    qc[rc] = q;
+                    if (dqc) dqc[rc] = dq;
+                    if (q) eob = max(eob, (int)iscan[rc] + 1);
+                    if (rect == 1 || rect == -1) dq = round_shift64((long long)dq * kNewInvSqrt2, 12);
+                    dq = clamp_bits(dq, row_clamp);
+                }
+                A[c * P1i + r] = dq;  // rows first: element = column, vector = row
+            }
+            if constexpr (TEAM >= 64) {
+                __syncthreads();
+                if (eob) atomicMax(&s_eob, eob);
+                __syncthreads();
+                if (threadIdx.x == 0) eobs[it] = (uint16_t)s_eob;
+            } else {
+                const unsigned mask = TEAM == 32 ? 0xffffffffu : (((1u << TEAM) - 1u) << ((threadIdx.x & 31) / TEAM * TEAM));
+#pragma unroll
+                for (int o = TEAM / 2; o > 0; o >>= 1) eob = max(eob, __shfl_xor_sync(mask, eob, o));
+                if (tid == 0) eobs[it] = (uint16_t)eob;
+                team_sync<TEAM>();
+            }
+        }
+        {   // ---- inverse + reconstruction (inv_txfm_kernel) ----
+            const int P1 = H + 1, P2 = W + 1;
+            const int col_clamp = (bd + 6) > 16 ? (bd + 6) : 16;
+            const int opt_row = bd == 8 ? 16 : (bd == 10 ? 18 : 20);
+            const int opt_col = bd == 12 ? 18 : 16;
+            txfm_pass_1d<TEAM, true>(cfg.i_tr, A, W, H, P1, cfg.i_cbr, opt_row, tid);
+            team_sync<TEAM>();
+            for (int idx = tid; idx < W * H; idx += MOVERS) {
+                const int r = idx >> lgW, c = idx & (W - 1);
+                const int cs = cfg.i_lr ? (W - 1 - c) : c;
+                B[r * P2 + c] = clamp_bits(round_shift_arr(A[cs * P1 + r], -cfg.i_s0), col_clamp);
+            }
+            team_sync<TEAM>();
+            txfm_pass_1d<TEAM, true>(cfg.i_tc, B, H, W, P2, cfg.i_cbc, opt_col, tid);
+            team_sync<TEAM>();
+            const PIX* pr = pred_base + item.inv.pred_off;
+            PIX*       pw = recon_base + item.inv.recon_off;
+            const long long int_max = (1ll << (7 + bd)) - 1 + (914ll << (bd - 7));
+            const int       pix_max = (1 << bd) - 1;
+            for (int idx = tid; idx < W * H; idx += MOVERS) {
+                const int r = idx >> lgW, c = idx & (W - 1);
+                const int rs = cfg.i_ud ? (H - 1 - r) : r;
+                long long t  = (long long)round_shift_arr(B[rs * P2 + c], -cfg.i_s1);
+                t            = t < -int_max - 1 ? -int_max - 1 : (t > int_max ? int_max : t);
+                int p        = (int)pr[(size_t)r * item.inv.pred_stride + c] + (int)t;
+                p            = p < 0 ? 0 : (p > pix_max ? pix_max : p);
+                pw[(size_t)r * item.inv.recon_stride + c] = (PIX)p;
+            }
+            team_sync<TEAM>();
+        }
+    }
+}
+
 // team class of a transform size: log2(max(W,H)) - 2
 static inline int tx_class(int sz) {
     const int m = tx_w(sz) > tx_h(sz) ? tx_w(sz) : tx_h(sz);
@@ -216,6 +336,41 @@ void launch_inv_txfm(const int32_t* d_coef, const PIX* d_pred, PIX* d_recon, con
     }
 }
 
+template <int TEAM, typename PIX>
+static void launch_trio_class(const int16_t* d_src, const PIX* d_pred, PIX* d_recon, int32_t* d_q, int32_t* d_dq, const int16_t* d_iscan,
+                              const uint8_t* d_qm, const SvtB200TrioItem* d_items, int n, uint16_t* d_eobs, cudaStream_t st) {
+    if (n <= 0) return;
+    constexpr int    THREADS = class_threads<TEAM>(), TEAMS = TEAM >= 64 ? 1 : THREADS / TEAM;
+    constexpr size_t smem = (size_t)TEAMS * 2 * TEAM * (TEAM + 1) * 4;
+    static bool attr = false;
+    if (!attr) { set_smem_attr(trio_txfm_kernel<TEAM, THREADS, PIX>, smem); attr = true; }
+    const int per_sm = (int)((200 * 1024) / (smem + 1024)) < 2048 / THREADS ? (int)((200 * 1024) / (smem + 1024)) : 2048 / THREADS;
+    trio_txfm_kernel<TEAM, THREADS, PIX><<<grid_for((n + TEAMS - 1) / TEAMS, per_sm), THREADS, smem, st>>>(d_src, d_pred, d_recon, d_q, d_dq, d_iscan, d_qm,
+                                                                                                     d_items, n, d_eobs);
+    B200_LAUNCH_CHECK();
+}
+template <typename PIX>
+static void launch_trio(const int16_t* d_src, const PIX* d_pred, PIX* d_recon, int32_t* d_q, int32_t* d_dq, const int16_t* d_iscan,
+                        const uint8_t* d_qm, const SvtB200TrioItem* d_items, const int* n_per_class, uint16_t* d_eobs, cudaStream_t user) {
+    int first[SVT_B200_TXFM_CLASSES + 1] = {0};
+    for (int c = 0; c < SVT_B200_TXFM_CLASSES; c++) first[c + 1] = first[c] + n_per_class[c];
+    ForkJoin& fj = fork_streams(user);
+    for (int c = SVT_B200_TXFM_CLASSES - 1; c >= 0; c--) {
+        cudaStream_t st = c >= 2 ? fj.side[c - 2] : user;
+        const SvtB200TrioItem* it = d_items + first[c];
+        uint16_t* eo = d_eobs + first[c];
+        const int n = n_per_class[c];
+        switch (c) {
+        case 0: launch_trio_class<4, PIX>(d_src, d_pred, d_recon, d_q, d_dq, d_iscan, d_qm, it, n, eo, st); break;
+        case 1: launch_trio_class<8, PIX>(d_src, d_pred, d_recon, d_q, d_dq, d_iscan, d_qm, it, n, eo, st); break;
+        case 2: launch_trio_class<16, PIX>(d_src, d_pred, d_recon, d_q, d_dq, d_iscan, d_qm, it, n, eo, st); break;
+        case 3: launch_trio_class<32, PIX>(d_src, d_pred, d_recon, d_q, d_dq, d_iscan, d_qm, it, n, eo, st); break;
+        default: launch_trio_class<64, PIX>(d_src, d_pred, d_recon, d_q, d_dq, d_iscan, d_qm, it, n, eo, st); break;
+        }
+    }
+    join_streams(fj, user);
+}
+
 }  // namespace b200
 
 using namespace b200;
@@ -264,6 +419,23 @@ extern "C" int svt_b200_inv_txfm_batch_dev(const int32_t* d_coeff, const void* d
         else launch_inv_txfm<uint16_t>(d_coeff, (const uint16_t*)d_pred, (uint16_t*)d_recon, d_items + first[c], n_per_class[c], c, st);
     }
     join_streams(fj, (cudaStream_t)stream);
+    return SVT_B200_OK;
+}
+
+extern "C" int svt_b200_txfm_trio_batch_dev(const int16_t* d_residual, const void* d_pred, void* d_recon, int32_t* d_qcoeff,
+                                            int32_t* d_dqcoeff, const int16_t* d_iscan, const uint8_t* d_qm,
+                                            const SvtB200TrioItem* d_items, const int n_per_class[SVT_B200_TXFM_CLASSES],
+                                            uint16_t* d_eobs, int pixel_bytes, void* stream) {
+    require_ready();
+    if (!n_per_class || !d_iscan || !d_qcoeff || !d_eobs || (pixel_bytes != 1 && pixel_bytes != 2)) return SVT_B200_ERR_BAD_ARG;
+    for (int c = 0; c < SVT_B200_TXFM_CLASSES; c++)
+        if (n_per_class[c] < 0) return SVT_B200_ERR_BAD_ARG;
+    if (pixel_bytes == 1)
+        launch_trio<uint8_t>(d_residual, (const uint8_t*)d_pred, (uint8_t*)d_recon, d_qcoeff, d_dqcoeff, d_iscan, d_qm, d_items, n_per_class, d_eobs,
+                             (cudaStream_t)stream);
+    else
+        launch_trio<uint16_t>(d_residual, (const uint16_t*)d_pred, (uint16_t*)d_recon, d_qcoeff, d_dqcoeff, d_iscan, d_qm, d_items, n_per_class,
+                              d_eobs, (cudaStream_t)stream);
     return SVT_B200_OK;
 }
 

@@ -205,6 +205,10 @@ QUANT_ITEM_DTYPE = np.dtype([("coeff_off", "<u8"), ("q_off", "<u8"), ("dq_off", 
                              ("round", "<i2", 2), ("quant", "<i2", 2), ("quant_shift", "<i2", 2), ("dequant", "<i2", 2),
                              ("mode", "u1"), ("log_scale", "u1"), ("reserved", "<u2")])
 assert QUANT_ITEM_DTYPE.itemsize == 64
+TRIO_ITEM_DTYPE = np.dtype([("fwd", FWD_ITEM_DTYPE), ("quant", QUANT_ITEM_DTYPE), ("inv", INV_ITEM_DTYPE)])  # SvtB200TrioItem
+assert TRIO_ITEM_DTYPE.itemsize == 128
+lib.svt_b200_txfm_trio_batch_dev.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, ct.POINTER(ct.c_int), vp, ct.c_int, vp]
+lib.svt_b200_txfm_trio_batch_dev.restype = ct.c_int
 _QA = [vp, ct.c_ssize_t, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
 for _n, _extra in (("aom_quantize_b", [vp, vp, ct.c_int32]), ("aom_highbd_quantize_b", [vp, vp, ct.c_int32]),
                    ("av1_quantize_b_qm", [vp, vp, ct.c_int32]), ("av1_highbd_quantize_b_qm", [vp, vp, ct.c_int32]),

@@ -60,6 +60,7 @@ class FramePipeline:
         self.fwd_items = _t(T, wl.fwd_items.view(np.uint8))
         self.inv_items = _t(T, wl.inv_items.view(np.uint8))
         self.quant_items = _t(T, wl.quant_items.view(np.uint8))
+        self.trio_items = _t(T, wl.trio_items.view(np.uint8))
         self.scan = _t(T, wl.scan_table)
         self.iscan = _t(T, wl.iscan_table)
         self.qm = _t(T, wl.qm_table)
@@ -153,6 +154,13 @@ class FramePipeline:
                                          self.me_mv.data_ptr(), self.me_centre.data_ptr(), self.me_hme_sad.data_ptr(), s)
         assert rc == 0
 
+    def call_txfm_trio(self, s):
+        rc = lib.svt_b200_txfm_trio_batch_dev(self.residual.data_ptr(), self.pred.data_ptr(), self.recon.data_ptr(), self.qcoeff.data_ptr(),
+                                              self.dqcoeff.data_ptr(), self.iscan.data_ptr(), self.qm.data_ptr(), self.trio_items.data_ptr(),
+                                              self.tx_counts, self.eobs.data_ptr(), 1, s)
+        assert rc == 0
+
+    # the same three steps as separate calls (TPL / MD use them individually); results are identical
     def call_fwd_txfm(self, s):
         rc = lib.svt_b200_fwd_txfm_batch_dev(self.residual.data_ptr(), self.coeff.data_ptr(), self.fwd_items.data_ptr(), self.tx_counts, s)
         assert rc == 0
@@ -213,9 +221,7 @@ class FramePipeline:
     # (call, stage it belongs to, the kernels it launches)
     CALLS = (("me_pyramid", "me", "downsample_2d_kernel+pad_plane_kernel"),
              ("me_search", "me", "hme_prepare/sad_search_small/hme_finish x3 + me_centre_kernel + fullpel_search_kernel"),
-             ("fwd_txfm", "tx", "fwd_txfm_kernel<4..64>"),
-             ("quant", "tx", "quant_kernel"),
-             ("inv_txfm", "tx", "inv_txfm_kernel<4..64>"),
+             ("txfm_trio", "tx", "trio_txfm_kernel<4..64> (forward transform + quantise + inverse transform fused)"),
              ("cdef_search", "cdef", "cdef_dir_kernel+cdef_search_kernel"),
              ("cdef_apply", "cdef", "cdef_apply_kernel"),
              ("rest_extend", "rest", "pad_plane_kernel"),

@@ -173,6 +173,10 @@ class FrameWorkload:
         order = np.lexsort((self.fwd_items["tx_type"], self.fwd_items["tx_size"], cls))
         self.fwd_items = self.fwd_items[order]
         self.inv_items = self.inv_items[order]
+        self.quant_items = self.quant_items[order]  # same block order everywhere (eobs[i] belongs to block i)
+        trio = np.zeros(len(order), dtype=dsp.TRIO_ITEM_DTYPE)  # the fused call takes the three items side by side
+        trio["fwd"], trio["quant"], trio["inv"] = self.fwd_items, self.quant_items, self.inv_items
+        self.trio_items = trio
         self.tx_class_counts = [int((cls == c).sum()) for c in range(dsp.TXFM_CLASSES)]
 
     # -- CDEF ---------------------------------------------------------------------------------------------
@@ -226,17 +230,18 @@ class FrameWorkload:
             "me_pyramid": int(1.3125 * W * H),                                    # full-res read + the two decimated levels written
             "me_search": int((1 + R) * 1.3125 * W * H + n64 * R * 85 * 8),        # every pyramid read once + SAD/MV out
             "fwd_txfm": 6 * N, "quant": 12 * N, "inv_txfm": 6 * N,               # (22 + 2 bpp) N in total
+            "txfm_trio": 24 * N,                                                  # the three steps fused: SURVEY's figure for the chain
             "cdef_search": int(2 * N + n64 * 2 * len(self.cdef_str_y) * 8),       # recon + source in, mse out
             "cdef_apply": 2 * N,                                                  # recon in, filtered out
             "rest_extend": 0,
             "wiener_stats": int(2 * N + len(self.stats_items) * (49 + 2401) * 8),
             "wiener_filter": 2 * N,
         }
-        stage_of = {"me_pyramid": "me", "me_search": "me", "fwd_txfm": "tx", "quant": "tx", "inv_txfm": "tx", "cdef_search": "cdef",
+        stage_of = {"me_pyramid": "me", "me_search": "me", "txfm_trio": "tx", "cdef_search": "cdef",
                     "cdef_apply": "cdef", "rest_extend": "rest", "wiener_stats": "rest", "wiener_filter": "rest"}
         out = dict(calls)
         for st in ("me", "tx", "cdef", "rest"):
-            out[st] = sum(v for k, v in calls.items() if stage_of[k] == st)
+            out[st] = sum(v for k, v in calls.items() if stage_of.get(k) == st)
         return out
 
     def wiener_stats_macs(self):
