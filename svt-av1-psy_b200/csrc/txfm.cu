@@ -192,15 +192,15 @@ trio_txfm_kernel(const int16_t* __restrict__ src_base, const PIX* __restrict__ p
                 A[r * P1 + c] = round_shift_arr((int32_t)src[(size_t)rr * sstride + c], -cfg.f_s0);
             }
             team_sync<TEAM>();
-            txfm_pass_1d<TEAM, false>(cfg.f_tc, A, H, W, P1, cfg.f_cbc, 0, tid);
+            txfm_pass_1d<TEAM, false, true>(cfg.f_tc, A, H, W, P1, cfg.f_cbc, 0, tid);  // rows >= Hp of the result are not needed
             team_sync<TEAM>();
-            for (int idx = tid; idx < W * H; idx += MOVERS) {
+            for (int idx = tid; idx < W * Hp; idx += MOVERS) {  // only the Hp rows that survive the packing
                 const int r = idx >> lgW, c = idx & (W - 1);
                 const int cc = cfg.f_lr ? (W - 1 - c) : c;
                 B[cc * P2 + r] = round_shift_arr(A[r * P1 + c], -cfg.f_s1);
             }
             team_sync<TEAM>();
-            txfm_pass_1d<TEAM, false>(cfg.f_tr, B, W, H, P2, cfg.f_cbr, 0, tid);
+            txfm_pass_1d<TEAM, false, true>(cfg.f_tr, B, W, Hp, P2, cfg.f_cbr, 0, tid);
             team_sync<TEAM>();
         }
         {   // ---- quantise the (packed) coefficients; the dequantised levels become the inverse's input plane ----
@@ -249,7 +249,7 @@ trio_txfm_kernel(const int16_t* __restrict__ src_base, const PIX* __restrict__ p
             const int col_clamp = (bd + 6) > 16 ? (bd + 6) : 16;
             const int opt_row = bd == 8 ? 16 : (bd == 10 ? 18 : 20);
             const int opt_col = bd == 12 ? 18 : 16;
-            txfm_pass_1d<TEAM, true>(cfg.i_tr, A, W, H, P1, cfg.i_cbr, opt_row, tid);
+            txfm_pass_1d<TEAM, true, true>(cfg.i_tr, A, W, Hp, P1, cfg.i_cbr, opt_row, tid);  // rows >= Hp are zero and stay zero
             team_sync<TEAM>();
             for (int idx = tid; idx < W * H; idx += MOVERS) {
                 const int r = idx >> lgW, c = idx & (W - 1);
@@ -257,7 +257,7 @@ trio_txfm_kernel(const int16_t* __restrict__ src_base, const PIX* __restrict__ p
                 B[r * P2 + c] = clamp_bits(round_shift_arr(A[cs * P1 + r], -cfg.i_s0), col_clamp);
             }
             team_sync<TEAM>();
-            txfm_pass_1d<TEAM, true>(cfg.i_tc, B, H, W, P2, cfg.i_cbc, opt_col, tid);
+            txfm_pass_1d<TEAM, true, true>(cfg.i_tc, B, H, W, P2, cfg.i_cbc, opt_col, tid);
             team_sync<TEAM>();
             const PIX* pr = pred_base + item.inv.pred_off;
             PIX*       pw = recon_base + item.inv.recon_off;

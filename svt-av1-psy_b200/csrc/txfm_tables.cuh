@@ -77,6 +77,12 @@ __device__ __forceinline__ int32_t txg_hbtf(int32_t w0, int32_t in0, int32_t w1,
     return (int32_t)(((long long)p0 + (long long)p1 + (1ll << (bit - 1))) >> bit);
 }
 
+// ... with one operand known to be zero
+__device__ __forceinline__ int32_t txg_hbtf1(int32_t w0, int32_t in0, int bit) {
+    const int32_t p0 = (int32_t)((uint32_t)w0 * (uint32_t)in0);
+    return (int32_t)(((long long)p0 + (1ll << (bit - 1))) >> bit);
+}
+
 #include "txfm_gen.inc"
 
 // Closed form of svt_av1_fadst4_new (transforms.c:1415-1502) / svt_av1_iadst4_new
@@ -123,7 +129,9 @@ __device__ __forceinline__ void txfm_identity(int32_t (&x)[N]) {
 }
 
 // one N-point vector in registers through the 1-D kernel `type` (a TT_* of that length)
-template <int N, bool INV>
+// PACKED: the 64-point kernels work on the packed coefficient layout -- the forward one needs only its 32
+// low outputs (x[32..63] are left undefined), the inverse one gets zeros in x[32..63]
+template <int N, bool INV, bool PACKED>
 __device__ __forceinline__ void txfm_vec(int type, int32_t (&x)[N], int cos_bit, int clampb) {
     const int32_t* cosv = c_cospi[cos_bit - 10];
     if constexpr (N == 4) {
@@ -142,32 +150,37 @@ __device__ __forceinline__ void txfm_vec(int type, int32_t (&x)[N], int cos_bit,
         if (type == TT_DCT32) { if constexpr (INV) txg_IDCT32(x, cosv, cos_bit, clampb); else txg_FDCT32(x, cosv, cos_bit, clampb); }
         else txfm_identity<32>(x);
     } else {
-        if (type == TT_DCT64) { if constexpr (INV) txg_IDCT64(x, cosv, cos_bit, clampb); else txg_FDCT64(x, cosv, cos_bit, clampb); }
+        if (type == TT_DCT64) {
+            if constexpr (INV && PACKED) txg_IDCT64_in32(x, cosv, cos_bit, clampb);
+            else if constexpr (INV) txg_IDCT64(x, cosv, cos_bit, clampb);
+            else if constexpr (PACKED) txg_FDCT64_lo32(x, cosv, cos_bit, clampb);
+            else txg_FDCT64(x, cosv, cos_bit, clampb);
+        }
         else txfm_identity<64>(x);
     }
 }
 
 // One 1-D pass over the V vectors of N points of a block held element-major in shared memory
 // (x[i*P + v]), in place: thread v of the team loads vector v, transforms it in registers, stores it.
-template <int N, int TEAM, bool INV>
+template <int N, int TEAM, bool INV, bool PACKED>
 __device__ __forceinline__ void txfm_pass_n(int type, int32_t* x, int V, int P, int cos_bit, int clampb, int tid) {
     for (int v = tid; v < V; v += TEAM) {
         int32_t r[N];
 #pragma unroll
         for (int i = 0; i < N; i++) r[i] = x[i * P + v];
-        txfm_vec<N, INV>(type, r, cos_bit, clampb);
+        txfm_vec<N, INV, PACKED>(type, r, cos_bit, clampb);
 #pragma unroll
         for (int i = 0; i < N; i++) x[i * P + v] = r[i];
     }
 }
 // a team of TEAM = max(W,H) threads only ever sees vector lengths TEAM/4 .. TEAM
-template <int TEAM, bool INV>
+template <int TEAM, bool INV, bool PACKED = false>
 __device__ __forceinline__ void txfm_pass_1d(int type, int32_t* x, int N, int V, int P, int cos_bit, int clampb, int tid) {
-    if constexpr (TEAM <= 16) { if (N == 4) return txfm_pass_n<4, TEAM, INV>(type, x, V, P, cos_bit, clampb, tid); }
-    if constexpr (TEAM >= 8 && TEAM <= 32) { if (N == 8) return txfm_pass_n<8, TEAM, INV>(type, x, V, P, cos_bit, clampb, tid); }
-    if constexpr (TEAM >= 16) { if (N == 16) return txfm_pass_n<16, TEAM, INV>(type, x, V, P, cos_bit, clampb, tid); }
-    if constexpr (TEAM >= 32) { if (N == 32) return txfm_pass_n<32, TEAM, INV>(type, x, V, P, cos_bit, clampb, tid); }
-    if constexpr (TEAM >= 64) { if (N == 64) return txfm_pass_n<64, TEAM, INV>(type, x, V, P, cos_bit, clampb, tid); }
+    if constexpr (TEAM <= 16) { if (N == 4) return txfm_pass_n<4, TEAM, INV, PACKED>(type, x, V, P, cos_bit, clampb, tid); }
+    if constexpr (TEAM >= 8 && TEAM <= 32) { if (N == 8) return txfm_pass_n<8, TEAM, INV, PACKED>(type, x, V, P, cos_bit, clampb, tid); }
+    if constexpr (TEAM >= 16) { if (N == 16) return txfm_pass_n<16, TEAM, INV, PACKED>(type, x, V, P, cos_bit, clampb, tid); }
+    if constexpr (TEAM >= 32) { if (N == 32) return txfm_pass_n<32, TEAM, INV, PACKED>(type, x, V, P, cos_bit, clampb, tid); }
+    if constexpr (TEAM >= 64) { if (N == 64) return txfm_pass_n<64, TEAM, INV, PACKED>(type, x, V, P, cos_bit, clampb, tid); }
 }
 
 }  // namespace b200

@@ -20,6 +20,7 @@ def _t(torch, arr, dtype=None):
 class FramePipeline:
     def __init__(self, wl, torch, device="cuda"):
         self.wl, self.torch = wl, torch
+        self._side = self._forked = self._joined = None
         self.tx_counts = (ct.c_int * dsp.TXFM_CLASSES)(*wl.tx_class_counts)
         W, H = wl.width, wl.height
         T = torch
@@ -246,13 +247,30 @@ class FramePipeline:
         self._stage("rest", s)
 
     def step(self, events=None):
-        """enqueue one frame of hot-path work on torch's current stream; `events`: len(CALLS)+1 CUDA events
-        recorded before every call and after the last one"""
+        """Enqueue one frame of hot-path work on torch's current stream.
+
+        Motion estimation reads only source pictures; transform -> CDEF -> restoration reads only the
+        residual/prediction of the block pass: the two chains share no data (in the encoder they are
+        different pipeline stages working on different pictures at the same moment), so the step runs ME
+        on a side stream, concurrently with the reconstruction chain, and joins at the end.
+        With `events` (len(CALLS)+1 CUDA events, recorded before every call and after the last) the calls
+        run strictly one after the other instead, so that each call can be timed on its own."""
         T = self.torch
-        s = T.cuda.current_stream().cuda_stream
-        for i, (name, _, _) in enumerate(self.CALLS):
-            if events is not None:
-                events[i].record()
-            getattr(self, "call_" + name)(s)
+        cur = T.cuda.current_stream()
         if events is not None:
+            s = cur.cuda_stream
+            for i, (name, _, _) in enumerate(self.CALLS):
+                events[i].record()
+                getattr(self, "call_" + name)(s)
             events[len(self.CALLS)].record()
+            return
+        if self._side is None:
+            self._side, self._forked, self._joined = T.cuda.Stream(), T.cuda.Event(), T.cuda.Event()
+        self._forked.record(cur)
+        self._side.wait_event(self._forked)
+        with T.cuda.stream(self._side):
+            self._stage("me", self._side.cuda_stream)
+            self._joined.record(self._side)
+        for st in ("tx", "cdef", "rest"):
+            self._stage(st, cur.cuda_stream)
+        cur.wait_event(self._joined)
