@@ -280,6 +280,7 @@ __device__ void stage_cdef_tile(uint16_t* tile, const PIX* plane, int stride, in
     (void)plane_w; (void)plane_h;
     const int py0 = fbr * bh - yoff, px0 = fbc * bw - xoff;
     constexpr int kPairs = (64 + 16) / 2;  // columns 0..79 are the ones ever read
+#pragma unroll 4
     for (int i = threadIdx.x; i < kTileRows * kPairs; i += blockDim.x) {
         const int r = i / kPairs, c = (i - r * kPairs) * 2;
         const int rr = r - (3 - yoff), cc = c - (8 - xoff);  // cc is even, xsize is a multiple of 4: the pair is in or out together

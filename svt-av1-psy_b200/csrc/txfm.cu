@@ -170,8 +170,11 @@ trio_txfm_kernel(const int16_t* __restrict__ src_base, const PIX* __restrict__ p
                  const uint8_t* __restrict__ qm_base, const SvtB200TrioItem* __restrict__ items, int n_items,
                  uint16_t* __restrict__ eobs) {
     extern __shared__ __align__(16) int32_t tsm[];
-    constexpr int TEAMS = TEAM >= 64 ? 1 : THREADS / TEAM, PLANE = TEAM * (TEAM + 1), MOVERS = TEAM >= 64 ? THREADS : TEAM;
-    const int     team  = TEAM >= 64 ? 0 : threadIdx.x / TEAM, tid = TEAM >= 64 ? threadIdx.x : threadIdx.x % TEAM;
+    // big blocks are few: one block per CTA (SOLO), all THREADS move its data, the first TEAM run the passes --
+    // the block's critical path is global-memory round trips, and 4x the movers means 4x fewer of them
+    constexpr bool SOLO = TEAM >= 32;
+    constexpr int  TEAMS = SOLO ? 1 : THREADS / TEAM, PLANE = TEAM * (TEAM + 1), MOVERS = SOLO ? THREADS : TEAM;
+    const int      team  = SOLO ? 0 : threadIdx.x / TEAM, tid = SOLO ? threadIdx.x : threadIdx.x % TEAM;
     int32_t*      A     = tsm + (size_t)team * 2 * PLANE;
     int32_t*      B     = A + PLANE;
     __shared__ int s_eob;
@@ -186,22 +189,24 @@ trio_txfm_kernel(const int16_t* __restrict__ src_base, const PIX* __restrict__ p
         {   // ---- forward (fwd_txfm_kernel) ----
             const int16_t* src = src_base + item.fwd.src_off;
             const int P1 = W + 1, P2 = H + 1, sstride = item.fwd.src_stride;
+#pragma unroll 4
             for (int idx = tid; idx < W * H; idx += MOVERS) {
                 const int r = idx >> lgW, c = idx & (W - 1);
                 const int rr = cfg.f_ud ? (H - 1 - r) : r;
                 A[r * P1 + c] = round_shift_arr((int32_t)src[(size_t)rr * sstride + c], -cfg.f_s0);
             }
-            team_sync<TEAM>();
+            team_sync<TEAM, SOLO>();
             txfm_pass_1d<TEAM, false, true>(cfg.f_tc, A, H, W, P1, cfg.f_cbc, 0, tid);  // rows >= Hp of the result are not needed
-            team_sync<TEAM>();
+            team_sync<TEAM, SOLO>();
+#pragma unroll 4
             for (int idx = tid; idx < W * Hp; idx += MOVERS) {  // only the Hp rows that survive the packing
                 const int r = idx >> lgW, c = idx & (W - 1);
                 const int cc = cfg.f_lr ? (W - 1 - c) : c;
                 B[cc * P2 + r] = round_shift_arr(A[r * P1 + c], -cfg.f_s1);
             }
-            team_sync<TEAM>();
+            team_sync<TEAM, SOLO>();
             txfm_pass_1d<TEAM, false, true>(cfg.f_tr, B, W, Hp, P2, cfg.f_cbr, 0, tid);
-            team_sync<TEAM>();
+            team_sync<TEAM, SOLO>();
         }
         {   // ---- quantise the (packed) coefficients; the dequantised levels become the inverse's input plane ----
             const SvtB200QuantItem qi = item.quant;
@@ -212,8 +217,9 @@ trio_txfm_kernel(const int16_t* __restrict__ src_base, const PIX* __restrict__ p
             int32_t*       dqc = dq_base ? dq_base + qi.dq_off : nullptr;
             const int P2 = H + 1, P1i = H + 1;  // forward result: B[c*P2 + r]; inverse input: A[c*P1i + r]
             const int row_clamp = bd + 8;
-            if (TEAM >= 64 && threadIdx.x == 0) s_eob = 0;
+            if (SOLO && threadIdx.x == 0) s_eob = 0;
             int eob = 0;
+#pragma unroll 4
             for (int idx = tid; idx < W * H; idx += MOVERS) {
                 const int r = idx >> lgW, c = idx & (W - 1);
                 int32_t   dq = 0;
@@ -231,7 +237,7 @@ trio_txfm_kernel(const int16_t* __restrict__ src_base, const PIX* __restrict__ p
                 }
                 A[c * P1i + r] = dq;  // rows first: element = column, vector = row
             }
-            if constexpr (TEAM >= 64) {
+            if constexpr (SOLO) {
                 __syncthreads();
                 if (eob) atomicMax(&s_eob, eob);
                 __syncthreads();
@@ -241,7 +247,7 @@ trio_txfm_kernel(const int16_t* __restrict__ src_base, const PIX* __restrict__ p
 #pragma unroll
                 for (int o = TEAM / 2; o > 0; o >>= 1) eob = max(eob, __shfl_xor_sync(mask, eob, o));
                 if (tid == 0) eobs[it] = (uint16_t)eob;
-                team_sync<TEAM>();
+                team_sync<TEAM, SOLO>();
             }
         }
         {   // ---- inverse + reconstruction (inv_txfm_kernel) ----
@@ -250,19 +256,21 @@ trio_txfm_kernel(const int16_t* __restrict__ src_base, const PIX* __restrict__ p
             const int opt_row = bd == 8 ? 16 : (bd == 10 ? 18 : 20);
             const int opt_col = bd == 12 ? 18 : 16;
             txfm_pass_1d<TEAM, true, true>(cfg.i_tr, A, W, Hp, P1, cfg.i_cbr, opt_row, tid);  // rows >= Hp are zero and stay zero
-            team_sync<TEAM>();
+            team_sync<TEAM, SOLO>();
+#pragma unroll 4
             for (int idx = tid; idx < W * H; idx += MOVERS) {
                 const int r = idx >> lgW, c = idx & (W - 1);
                 const int cs = cfg.i_lr ? (W - 1 - c) : c;
                 B[r * P2 + c] = clamp_bits(round_shift_arr(A[cs * P1 + r], -cfg.i_s0), col_clamp);
             }
-            team_sync<TEAM>();
+            team_sync<TEAM, SOLO>();
             txfm_pass_1d<TEAM, true, true>(cfg.i_tc, B, H, W, P2, cfg.i_cbc, opt_col, tid);
-            team_sync<TEAM>();
+            team_sync<TEAM, SOLO>();
             const PIX* pr = pred_base + item.inv.pred_off;
             PIX*       pw = recon_base + item.inv.recon_off;
             const long long int_max = (1ll << (7 + bd)) - 1 + (914ll << (bd - 7));
             const int       pix_max = (1 << bd) - 1;
+#pragma unroll 4
             for (int idx = tid; idx < W * H; idx += MOVERS) {
                 const int r = idx >> lgW, c = idx & (W - 1);
                 const int rs = cfg.i_ud ? (H - 1 - r) : r;
@@ -272,7 +280,7 @@ trio_txfm_kernel(const int16_t* __restrict__ src_base, const PIX* __restrict__ p
                 p            = p < 0 ? 0 : (p > pix_max ? pix_max : p);
                 pw[(size_t)r * item.inv.recon_stride + c] = (PIX)p;
             }
-            team_sync<TEAM>();
+            team_sync<TEAM, SOLO>();
         }
     }
 }
@@ -340,7 +348,7 @@ template <int TEAM, typename PIX>
 static void launch_trio_class(const int16_t* d_src, const PIX* d_pred, PIX* d_recon, int32_t* d_q, int32_t* d_dq, const int16_t* d_iscan,
                               const uint8_t* d_qm, const SvtB200TrioItem* d_items, int n, uint16_t* d_eobs, cudaStream_t st) {
     if (n <= 0) return;
-    constexpr int    THREADS = class_threads<TEAM>(), TEAMS = TEAM >= 64 ? 1 : THREADS / TEAM;
+    constexpr int    THREADS = TEAM == 32 ? 128 : class_threads<TEAM>(), TEAMS = TEAM >= 32 ? 1 : THREADS / TEAM;
     constexpr size_t smem = (size_t)TEAMS * 2 * TEAM * (TEAM + 1) * 4;
     static bool attr = false;
     if (!attr) { set_smem_attr(trio_txfm_kernel<TEAM, THREADS, PIX>, smem); attr = true; }

@@ -61,9 +61,9 @@ __device__ __forceinline__ int32_t clamp_bits(int32_t v, int bit) {
 
 // Team barrier.  Teams of < 32 threads share a warp with other teams that may be running a different
 // block shape, so they synchronise on their own lane mask; a 64-thread team is a whole CTA.
-template <int TEAM>
+template <int TEAM, bool SOLO = false>  // SOLO: the team is alone in its CTA and the whole CTA helps moving its data
 __device__ __forceinline__ void team_sync() {
-    if constexpr (TEAM >= 64)
+    if constexpr (TEAM >= 64 || SOLO)
         __syncthreads();
     else if constexpr (TEAM == 32)
         __syncwarp();

@@ -39,6 +39,7 @@ wiener_convolve_kernel(const PIX* __restrict__ src_base, PIX* __restrict__ dst_b
         const PIX* src = src_base + u.src_off;
         PIX*       dst = dst_base + u.dst_off;
         const int sw = w + 8, sh = h + 7;  // rows -3..h+3, cols -3..w+4
+#pragma unroll 4
         for (int i = threadIdx.x; i < sw * sh; i += blockDim.x) {
             const int r = i / sw, c = i - r * sw;
             // the 8th tap is read by the reference too (multiplied by its coefficient); the column
