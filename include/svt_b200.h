@@ -528,6 +528,15 @@ typedef struct SvtB200MeParams {
 /* replicate the w x h interior at (org_x, org_y) of an 8-bit device plane into its padding
  * (svt_aom_generate_padding / svt_extend_frame) */
 SVT_B200_API int svt_b200_extend_plane_dev(uint8_t* d_buf, int stride, int w, int h, int org_x, int org_y, void* stream);
+/* the same for up to 4 planes (a picture's Y, Cb, Cr) in one launch */
+typedef struct SvtB200PlaneExtent {
+    uint8_t* buf;     /* first byte of the padded plane */
+    int32_t  stride;
+    int32_t  w, h;    /* interior size */
+    int32_t  org_x, org_y; /* interior origin = padding widths */
+    int32_t  reserved;
+} SvtB200PlaneExtent;
+SVT_B200_API int svt_b200_extend_planes_dev(const SvtB200PlaneExtent* planes, int n_planes, void* stream);
 /* fills the 1/4 and 1/16 planes (interior + replicated padding) from the full plane */
 SVT_B200_API int svt_b200_build_hme_pyramid_dev(const SvtB200MePicture* pic, void* stream);
 /* cur / refs / params are HOST structs holding device plane pointers.  Outputs (device):

@@ -139,17 +139,32 @@ __device__ __forceinline__ void cdef_load_taps(const uint16_t* in, int s, int di
 // The filtered pixel for one (primary, secondary) strength.  constrain() (cdef.c:85-93) with a zero
 // threshold yields zero by itself here: max(0, 0 - (|d| >> shift)) = 0.  The reference accumulates in
 // int16; |sum| <= 2*(4+2)*240 + 4*(2+1)*64 for 12-bit content, so the int32 sum below is the same number.
+// The sum splits into a primary part (4 taps, depends on the primary strength only) and a secondary part
+// (8 taps, depends on the secondary strength only): candidate strengths that share one of the two share
+// that half of the work.
+__device__ __forceinline__ int cdef_constrained(const CdefTaps& T, int slot, int thr, int sh) {
+    return min(T.ad[slot], max(0, thr - (T.ad[slot] >> sh))) * T.sg[slot];
+}
+__device__ __forceinline__ int cdef_primary_sum(const CdefTaps& T, int pri, int pri_damping, int coeff_shift) {
+    const int sh  = max(0, pri_damping - msb32((uint32_t)pri));
+    const int pk0 = cdef_constrained(T, 0, pri, sh) + cdef_constrained(T, 1, pri, sh);
+    const int pk1 = cdef_constrained(T, 2, pri, sh) + cdef_constrained(T, 3, pri, sh);
+    const int odd = (pri >> coeff_shift) & 1;
+    return (odd ? 3 : 4) * pk0 + (odd ? 3 : 2) * pk1;
+}
+__device__ __forceinline__ int cdef_secondary_sum(const CdefTaps& T, int sec, int sec_damping) {
+    const int sh  = max(0, sec_damping - msb32((uint32_t)sec));
+    const int sk0 = cdef_constrained(T, 4, sec, sh) + cdef_constrained(T, 5, sec, sh) + cdef_constrained(T, 6, sec, sh) + cdef_constrained(T, 7, sec, sh);
+    const int sk1 = cdef_constrained(T, 8, sec, sh) + cdef_constrained(T, 9, sec, sh) + cdef_constrained(T, 10, sec, sh) + cdef_constrained(T, 11, sec, sh);
+    return 2 * sk0 + sk1;
+}
+__device__ __forceinline__ int cdef_finish_px(const CdefTaps& T, int x, int sum) {
+    const int y = x + ((8 + sum - (sum < 0)) >> 4);
+    return y < T.mn ? T.mn : (y > T.mx ? T.mx : y);
+}
 __device__ __forceinline__ int cdef_eval_taps(const CdefTaps& T, int x, int pri, int sec, int pri_damping, int sec_damping,
                                               int coeff_shift) {
-    const int shp = max(0, pri_damping - msb32((uint32_t)pri)), shs = max(0, sec_damping - msb32((uint32_t)sec));
-    auto c = [&](int slot, int thr, int sh) { return min(T.ad[slot], max(0, thr - (T.ad[slot] >> sh))) * T.sg[slot]; };
-    const int pk0 = c(0, pri, shp) + c(1, pri, shp), pk1 = c(2, pri, shp) + c(3, pri, shp);
-    const int sk0 = c(4, sec, shs) + c(5, sec, shs) + c(6, sec, shs) + c(7, sec, shs);
-    const int sk1 = c(8, sec, shs) + c(9, sec, shs) + c(10, sec, shs) + c(11, sec, shs);
-    const int odd = (pri >> coeff_shift) & 1;
-    const int sum = (odd ? 3 : 4) * pk0 + (odd ? 3 : 2) * pk1 + 2 * sk0 + sk1;
-    const int y   = x + ((8 + sum - (sum < 0)) >> 4);
-    return y < T.mn ? T.mn : (y > T.mx ? T.mx : y);
+    return cdef_finish_px(T, x, cdef_primary_sum(T, pri, pri_damping, coeff_shift) + cdef_secondary_sum(T, sec, sec_damping));
 }
 // one filtered pixel; `in` points at the pixel, s = tile pitch
 __device__ __forceinline__ int cdef_filter_px(const uint16_t* in, int s, int pri_strength, int sec_strength, int dir,
@@ -402,15 +417,32 @@ cdef_search_kernel(SvtB200CdefFrame f, const uint8_t* __restrict__ skip8x8, cons
                     if (!todo) continue;  // CTA-uniform
                     CdefTaps T;
                     cdef_load_taps(in, kTP, pass ? 0 : dirb, x, T);
+                    // the primary half is recomputed when the primary strength changes, the secondary half
+                    // once per distinct secondary code (0..3) of this pass
+                    int last_pri = -1, psum = 0, sec1 = 0, sec2 = 0, sec3 = 0;
+                    unsigned have = 0;
 #pragma unroll 1
                     for (int gi = 0; gi < ng; gi++) {
                         if (!((todo >> gi) & 1)) continue;  // CTA-uniform
                         const int sv = strengths[g0 + gi];
-                        const int pri = (sv / 4) << cs;
-                        int sec = sv % 4;
-                        sec = (sec + (sec == 3)) << cs;
-                        const int t = pli ? pri : cdef_adjust_strength(pri, var);
-                        const unsigned int y = live ? (unsigned int)cdef_eval_taps(T, x, t, sec, damping, damping, cs) : 0u;
+                        const int pri_code = sv >> 2, sec_code = sv & 3;  // sv >= 0 here
+                        if (pri_code != last_pri) {  // CTA-uniform
+                            const int pri = pri_code << cs;
+                            psum     = pri_code ? cdef_primary_sum(T, pli ? pri : cdef_adjust_strength(pri, var), damping, cs) : 0;
+                            last_pri = pri_code;
+                        }
+                        int ssum = 0;
+                        if (sec_code) {  // CTA-uniform
+                            if (!((have >> sec_code) & 1)) {
+                                const int v = cdef_secondary_sum(T, (sec_code + (sec_code == 3)) << cs, damping);
+                                if (sec_code == 1) sec1 = v;
+                                else if (sec_code == 2) sec2 = v;
+                                else sec3 = v;
+                                have |= 1u << sec_code;
+                            }
+                            ssum = sec_code == 1 ? sec1 : (sec_code == 2 ? sec2 : sec3);
+                        }
+                        const unsigned int y = live ? (unsigned int)cdef_finish_px(T, x, psum + ssum) : 0u;
                         if (pli == 0) {
                             // five moments of the block (<= 64 pixels of <= 12 bits: fit 32 bits)
                             unsigned int ss = y, sdv = o, s2 = y * y, d2 = o * o, sdp = y * o;

@@ -354,6 +354,38 @@ extern "C" void svt_b200_downsample_2d(uint8_t* input_samples, uint32_t input_st
     for (uint32_t r = 0; r < oh; r++) memcpy(decim_samples + (size_t)r * decim_stride, l->h<uint8_t>(o_out) + (size_t)r * ow, ow);
 }
 
+struct PadPlanes {
+    SvtB200PlaneExtent p[4];
+};
+// several planes in one launch: blockIdx.y = plane
+__global__ void pad_planes_kernel(const __grid_constant__ PadPlanes pl) {
+    const SvtB200PlaneExtent& e = pl.p[blockIdx.y];
+    const int tw = e.w + 2 * e.org_x, th = e.h + 2 * e.org_y;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < tw * th; idx += gridDim.x * blockDim.x) {
+        const int y = idx / tw, x = idx - y * tw;
+        if (x >= e.org_x && x < e.org_x + e.w && y >= e.org_y && y < e.org_y + e.h) continue;
+        const int sx = min(max(x, e.org_x), e.org_x + e.w - 1), sy = min(max(y, e.org_y), e.org_y + e.h - 1);
+        e.buf[(size_t)y * e.stride + x] = e.buf[(size_t)sy * e.stride + sx];
+    }
+}
+
+extern "C" int svt_b200_extend_planes_dev(const SvtB200PlaneExtent* planes, int n_planes, void* stream) {
+    require_ready();
+    if (!planes || n_planes <= 0 || n_planes > 4) return SVT_B200_ERR_BAD_ARG;
+    PadPlanes pl;
+    memset(&pl, 0, sizeof(pl));
+    int tn = 0;
+    for (int i = 0; i < n_planes; i++) {
+        if (!planes[i].buf || planes[i].w <= 0 || planes[i].h <= 0) return SVT_B200_ERR_BAD_ARG;
+        pl.p[i] = planes[i];
+        const int t = (planes[i].w + 2 * planes[i].org_x) * (planes[i].h + 2 * planes[i].org_y);
+        tn = t > tn ? t : tn;
+    }
+    pad_planes_kernel<<<dim3(grid_for((tn + 255) / 256, 4), n_planes), 256, 0, (cudaStream_t)stream>>>(pl);
+    B200_LAUNCH_CHECK();
+    return SVT_B200_OK;
+}
+
 extern "C" int svt_b200_extend_plane_dev(uint8_t* d_buf, int stride, int w, int h, int org_x, int org_y, void* stream) {
     require_ready();
     if (!d_buf || w <= 0 || h <= 0) return SVT_B200_ERR_BAD_ARG;

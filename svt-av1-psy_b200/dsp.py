@@ -438,6 +438,15 @@ lib.svt_b200_extend_plane_dev.argtypes = [vp, ct.c_int, ct.c_int, ct.c_int, ct.c
 lib.svt_b200_extend_plane_dev.restype = ct.c_int
 
 
+class PlaneExtent(ct.Structure):  # SvtB200PlaneExtent
+    _fields_ = [("buf", ct.c_void_p), ("stride", ct.c_int32), ("w", ct.c_int32), ("h", ct.c_int32), ("org_x", ct.c_int32),
+                ("org_y", ct.c_int32), ("reserved", ct.c_int32)]
+
+
+lib.svt_b200_extend_planes_dev.argtypes = [ct.POINTER(PlaneExtent), ct.c_int, vp]
+lib.svt_b200_extend_planes_dev.restype = ct.c_int
+
+
 def unbound_symbols():
     """declared C-ABI symbols that have no ctypes signature yet (calling those would truncate pointers)"""
     from . import declared_symbols

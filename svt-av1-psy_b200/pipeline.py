@@ -21,6 +21,7 @@ class FramePipeline:
     def __init__(self, wl, torch, device="cuda"):
         self.wl, self.torch = wl, torch
         self._side = self._forked = self._joined = None
+        self._extents = None
         self.tx_counts = (ct.c_int * dsp.TXFM_CLASSES)(*wl.tx_class_counts)
         W, H = wl.width, wl.height
         T = torch
@@ -202,11 +203,14 @@ class FramePipeline:
 
     def call_rest_extend(self, s):
         wl = self.wl
-        off, _ = wl.padded_offsets()
-        for p in range(3):  # svt_extend_frame: restoration reads beyond the picture edge
-            th, st = wl.padded_shape(p)
-            w, h = wl.plane_dims[p]
-            assert lib.svt_b200_extend_plane_dev(self.cdef_out.data_ptr() + off[p], st, w, h, wl.PAD, wl.PAD, s) == 0
+        if self._extents is None:  # svt_extend_frame: restoration reads beyond the picture edge
+            off, _ = wl.padded_offsets()
+            self._extents = (dsp.PlaneExtent * 3)()
+            for p in range(3):
+                th, st = wl.padded_shape(p)
+                w, h = wl.plane_dims[p]
+                self._extents[p] = dsp.PlaneExtent(self.cdef_out.data_ptr() + off[p], st, w, h, wl.PAD, wl.PAD, 0)
+        assert lib.svt_b200_extend_planes_dev(self._extents, 3, s) == 0
 
     def call_wiener_stats(self, s):
         rc = lib.svt_b200_compute_stats_batch_dev(self.cdef_out.data_ptr(), self.cur_flat.data_ptr(), self.stats_items.data_ptr(),
