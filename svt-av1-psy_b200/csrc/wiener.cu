@@ -9,12 +9,14 @@
 //     per pixel the wiener_win^2 window of (dgd - avg) is the vector y (column-major), x = src - avg;
 //     M[k] += y[k] x, H[k][l] += y[k] y[l]; high bit depth divides by 4 / 16 at the end (truncating).
 //
-// B200 mapping of the statistics (the one dense contraction on the path): a warp walks DOWN one
-// pixel column; lane (a,b), a<=b, owns the 7x7 tile of H that pairs window column a with window
-// column b, and keeps the two 7-pixel vertical strips in registers as a sliding window -- 2 loads
-// feed 49 multiply-accumulates per pixel.  The 7 diagonal lanes also accumulate M.  Products are
-// accumulated in int32 for as many pixels as cannot overflow, then flushed to the int64 totals with
-// 64-bit atomics; a finalize kernel mirrors the triangle and applies the bit-depth divider.
+// B200 mapping of the statistics (the one dense contraction on the path):
+//   8-bit pixels -> stats_mma_kernel: exact f16 x f16 -> f32 tensor-core MMA (see the comment above it);
+//   10/12-bit    -> stats_accum_kernel: a warp walks DOWN one pixel column; lane (a,b), a<=b, owns the 7x7
+//   tile of H that pairs window column a with window column b and keeps the two 7-pixel vertical strips
+//   in registers as a sliding window -- 2 loads feed 49 multiply-accumulates per pixel; products are
+//   accumulated in int32 for as many pixels as cannot overflow, then flushed to int64.
+// Both write per-CTA int64 partials; stats_finalize_kernel adds them, mirrors the triangle and applies
+// the bit-depth divider.
 #include <cuda_fp16.h>
 
 #include "common.cuh"
