@@ -181,14 +181,39 @@ def time_reference(wl, steps, warmup):
 # clocks sampling (nvidia-smi) during the timed region
 # ------------------------------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock + throttle reasons sampled DURING the timed region: NVML in-process (a sample every ~0.5 ms --
+    the timed region is only tens of milliseconds long), nvidia-smi as the fallback."""
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+    BITS = [0x8, 0x40, 0x20, 0x4]  # nvmlClocksEventReason{HwSlowdown,HwThermalSlowdown,SwThermalSlowdown,SwPowerCap}
 
-    def __init__(self, index):
+    def __init__(self, index, bus_id=None):
         self.samples, self.index, self.stop_flag, self.th = [], index, False, None
+        self.nvml = self.handle = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.handle = pynvml.nvmlDeviceGetHandleByPciBusId(bus_id) if bus_id else pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM)
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
 
     def _run(self):
         while not self.stop_flag:
+            if self.nvml is not None:
+                try:
+                    mhz = self.nvml.nvmlDeviceGetClockInfo(self.handle, self.nvml.NVML_CLOCK_SM)
+                    try:
+                        mask = self.nvml.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+                    except Exception:
+                        mask = self.nvml.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                    self.samples.append([str(mhz), str(self.max_mhz)] + ["Active" if mask & b else "Not Active" for b in self.BITS])
+                except Exception:
+                    pass
+                time.sleep(0.0005)
+                continue
             try:
                 o = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
                                    capture_output=True, text=True, timeout=5).stdout.strip()
@@ -207,12 +232,12 @@ class ClockSampler:
         if self.th:
             self.th.join(timeout=6)
         if not self.samples:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock query unavailable"]}
         sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
         mx = max(int(s[1]) for s in self.samples if s[1].isdigit())
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for s in self.samples for i in range(4) if len(s) > 2 + i and s[2 + i].lower().startswith("active")})
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": reasons, "samples": len(self.samples)}
+        reasons = sorted({self.NAMES[i] for s in self.samples for i in range(4) if len(s) > 2 + i and s[2 + i].lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": reasons, "samples": len(self.samples),
+                "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -226,6 +251,7 @@ def main():
     ap.add_argument("--height", type=int, default=1080)
     ap.add_argument("--check", action="store_true", help="compare one frame of B200 output with the reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--one-stream", action="store_true", help="all frames on one compute stream (no frame-level overlap)")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying one CUDA graph per step")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -241,6 +267,7 @@ def main():
               "l2": "steps rotate over %d distinct frame sets (~65 MB each, >126 MB L2 in total)" % N_FRAME_SETS,
               "parallelism": "frame-parallel x%d (no data-path collective; recon exchange = all_gather of the filtered frame)" % world,
               "overlap": "ME (source pictures only) on a side stream, concurrent with the transform->CDEF->restoration chain of the same step",
+              "streams": "1 compute stream" if args.one_stream else "2 compute streams: consecutive (independent) frames alternate between them",
               "launch": "eager" if args.no_graph else "one CUDA graph replay per step (the step's kernel launches captured once per frame set)"}
 
     if args.impl == "reference":
@@ -274,7 +301,10 @@ def main():
     sets = [FramePipeline(FrameWorkload(args.width, args.height, seed=20260923 + 17 * (rank * N_FRAME_SETS + i)), torch) for i in range(N_FRAME_SETS)]
     wl0 = sets[0].wl
     stream = torch.cuda.Stream()
-    gathered = torch.empty((world,) + tuple(sets[0].final.shape), dtype=torch.uint8, device="cuda") if world > 1 else None
+    # consecutive frames alternate between two compute streams: independent pictures in flight at once, as in
+    # the encoder's picture-parallel pipeline; frame set k always runs on stream k % 2
+    streams = [stream, torch.cuda.Stream()] if not args.one_stream else [stream, stream]
+    gathered = [torch.empty((world,) + tuple(sets[0].final.shape), dtype=torch.uint8, device="cuda") for _ in range(2)] if world > 1 else None
 
     def barrier():
         torch.cuda.synchronize()
@@ -296,25 +326,29 @@ def main():
     def capture_graphs():
         for k, fp in enumerate(sets):
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g, stream=stream):
+            with torch.cuda.graph(g, stream=streams[k % 2]):
                 fp.step()
             graphs[k] = g
 
     def run(n, e2e, stage_acc=None):
         ev = [[torch.cuda.Event(enable_timing=True) for _ in range(N_CALLS + 1)] for _ in range(n)] if stage_acc is not None else None
-        with torch.cuda.stream(stream):
-            start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            start.record()
-            for i in range(n):
+        start, end, tail = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), torch.cuda.Event()
+        start.record(stream)
+        streams[1].wait_event(start)
+        for i in range(n):
+            st = stream if ev else streams[i % 2]  # the per-call profile runs strictly serially
+            with torch.cuda.stream(st):
                 fp = sets[i % N_FRAME_SETS]
                 if e2e:
                     fp.load_inputs()
                 enqueue_step(i, ev[i] if ev else None)
                 if world > 1:  # reconstructed-reference exchange (the path's one real collective)
-                    dist.all_gather_into_tensor(gathered.view(-1), fp.final)
+                    dist.all_gather_into_tensor(gathered[i % 2].view(-1), fp.final)
                 if e2e:
                     fp.read_outputs()
-            end.record()
+        tail.record(streams[1])
+        stream.wait_event(tail)
+        end.record(stream)
         torch.cuda.synchronize()
         if stage_acc is not None:
             for i in range(n):
@@ -341,12 +375,13 @@ def main():
                     s_in.wait_event(ev_out[i - N_FRAME_SETS])
                 fp.load_inputs()
                 ev_in[i].record(s_in)
-            with torch.cuda.stream(stream):
-                stream.wait_event(ev_in[i])
+            cs = streams[i % 2]
+            with torch.cuda.stream(cs):
+                cs.wait_event(ev_in[i])
                 enqueue_step(i)
                 if world > 1:
-                    dist.all_gather_into_tensor(gathered.view(-1), fp.final)
-                ev_done[i].record(stream)
+                    dist.all_gather_into_tensor(gathered[i % 2].view(-1), fp.final)
+                ev_done[i].record(cs)
             with torch.cuda.stream(s_out):
                 s_out.wait_event(ev_done[i])
                 fp.read_outputs()
@@ -371,7 +406,13 @@ def main():
         capture_graphs()
         run(warmup, False)
     barrier()
-    sampler = ClockSampler(local_rank)
+    bus_id = None
+    try:  # NVML enumerates physical devices: address this rank's GPU by PCI id, not by (visible) index
+        pr = torch.cuda.get_device_properties(local_rank)
+        bus_id = "%08X:%02X:%02X.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+    except Exception:
+        bus_id = None
+    sampler = ClockSampler(local_rank, bus_id)
     sampler.start()
     ms = run(args.steps, False)
     barrier()

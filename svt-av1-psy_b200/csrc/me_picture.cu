@@ -17,6 +17,8 @@
 //   full-pel items) -> fullpel_search.
 // The search kernels are the ones behind the T1 entry points (sad.cu / me_pyramid.cu); the small
 // prepare/finish kernels only do the reference's window arithmetic, one thread per (ref, b64, region).
+#include <map>
+
 #include "common.cuh"
 #include "sad_small.cuh"
 #include "../../include/svt_b200.h"
@@ -305,11 +307,11 @@ struct MeWorkspace {
     SvtB200MePicture* refs = nullptr;
     SvtB200MeParams* prm = nullptr;
 };
-static MeWorkspace g_me_ws;
+// one workspace per stream: calls enqueued on different streams may execute concurrently
+static std::map<cudaStream_t, MeWorkspace> g_me_ws;
 static std::mutex  g_me_mu;
 
-static void me_ws_reserve(size_t pairs) {
-    MeWorkspace& w = g_me_ws;
+static void me_ws_reserve(MeWorkspace& w, size_t pairs) {
     if (pairs <= w.cap) return;
     auto fr = [](void* p) { if (p) cudaFree(p); };
     fr(w.items); fr(w.res); fr(w.side); fr(w.fp_items); fr(w.refs); fr(w.prm);
@@ -423,8 +425,8 @@ extern "C" int svt_b200_me_picture_dev(const SvtB200MePicture* cur, const SvtB20
     const int b64_w = (cur->width[2] + 63) >> 6, b64_h = (cur->height[2] + 63) >> 6, n_b64 = b64_w * b64_h;
     const int pairs = n_refs * n_b64, n4 = pairs * 4;
     std::lock_guard<std::mutex> lk(g_me_mu);
-    me_ws_reserve((size_t)pairs);
-    MeWorkspace& w = g_me_ws;
+    MeWorkspace& w = g_me_ws[st];
+    me_ws_reserve(w, (size_t)pairs);
     const int g = grid_for((n4 + 255) / 256, 8);
     int max_l0_w = 8, max_l0_h = 1, max_pos[3] = {1, 1, 1};
     for (int r = 0; r < n_refs; r++) {

@@ -19,6 +19,8 @@
 // the bit-depth divider.
 #include <cuda_fp16.h>
 
+#include <map>
+
 #include "common.cuh"
 #include "../../include/svt_b200.h"
 
@@ -487,9 +489,14 @@ stats_finalize_kernel(const long long* __restrict__ partial, int parts, const Sv
     else M_out[(size_t)it * 49 + (e - win2 * win2)] = v / divider;
 }
 
-static long long* g_stats_acc = nullptr;
-static unsigned long long* g_stats_avg = nullptr;
-static size_t     g_stats_cap = 0;
+// scratch of the batch call (per-CTA partials, pixel totals), one per stream: calls enqueued on
+// different streams may execute concurrently
+struct StatsScratch {
+    long long*          acc = nullptr;
+    unsigned long long* tot = nullptr;
+    size_t              cap = 0;
+};
+static std::map<cudaStream_t, StatsScratch> g_stats;
 static std::mutex g_stats_mu;
 
 template <typename PIX>
@@ -623,17 +630,18 @@ extern "C" int svt_b200_compute_stats_batch_dev(const void* d_dgd, const void* d
     require_ready();
     if (n_items <= 0) return n_items == 0 ? SVT_B200_OK : SVT_B200_ERR_BAD_ARG;
     std::lock_guard<std::mutex> lk(g_stats_mu);
-    if ((size_t)n_items > g_stats_cap) {
-        if (g_stats_acc) { cudaFree(g_stats_acc); cudaFree(g_stats_avg); }
-        g_stats_cap = (size_t)n_items * 2;
-        B200_CUDA_CHECK(cudaMalloc(&g_stats_acc, g_stats_cap * kStatsMaxParts * 2450 * 8));
-        B200_CUDA_CHECK(cudaMalloc(&g_stats_avg, g_stats_cap * 8));
+    StatsScratch& sc = g_stats[(cudaStream_t)stream];
+    if ((size_t)n_items > sc.cap) {
+        if (sc.acc) { cudaFree(sc.acc); cudaFree(sc.tot); }
+        sc.cap = (size_t)n_items * 2;
+        B200_CUDA_CHECK(cudaMalloc(&sc.acc, sc.cap * kStatsMaxParts * 2450 * 8));
+        B200_CUDA_CHECK(cudaMalloc(&sc.tot, sc.cap * 8));
     }
     if (bit_depth > 8)
         launch_stats<uint16_t>((const uint16_t*)d_dgd, (const uint16_t*)d_src, d_items, n_items, bit_depth, (long long*)d_M, (long long*)d_H,
-                               g_stats_acc, g_stats_avg, (cudaStream_t)stream);
+                               sc.acc, sc.tot, (cudaStream_t)stream);
     else
-        launch_stats<uint8_t>((const uint8_t*)d_dgd, (const uint8_t*)d_src, d_items, n_items, 8, (long long*)d_M, (long long*)d_H, g_stats_acc,
-                              g_stats_avg, (cudaStream_t)stream);
+        launch_stats<uint8_t>((const uint8_t*)d_dgd, (const uint8_t*)d_src, d_items, n_items, 8, (long long*)d_M, (long long*)d_H, sc.acc,
+                              sc.tot, (cudaStream_t)stream);
     return SVT_B200_OK;
 }

@@ -45,3 +45,43 @@ def test_cdef_apply_recomputes_directions_when_none_given(b200, refc):
     assert torch.equal(want, fp.cdef_out)
     assert dsp.lib.svt_b200_cdef_apply_frame_dev(ct.byref(f), fp.skip.data_ptr(), fp.fb_idx.data_ptr(), fp.app_y.data_ptr(),
                                                  fp.app_uv.data_ptr(), fp.cdef_dir.data_ptr(), None, oy, ocb, ocr, sy, sc, s) == -4  # SVT_B200_ERR_BAD_ARG
+
+
+def test_two_frames_in_flight_on_two_streams(b200, refc):
+    """bench.py keeps two independent frames in flight on two streams (CUDA-graph replays); every library
+    scratch buffer is per stream, so the concurrent results must equal the one-at-a-time results."""
+    import torch
+    from svt_av1_psy_b200.pipeline import FramePipeline
+    from svt_av1_psy_b200.workload import FrameWorkload
+    fps = [FramePipeline(FrameWorkload(384, 256, seed=1234 + 7 * k), torch) for k in range(2)]
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    names = ("me_sad", "me_mv", "qcoeff", "eobs", "recon", "cdef_mse", "cdef_out", "M", "Hm", "final")
+    want = []
+    for fp, st in zip(fps, streams):  # one at a time (also warms up every lazily allocated scratch)
+        with torch.cuda.stream(st):
+            fp.load_inputs()
+            fp.step()
+        torch.cuda.synchronize()
+        want.append([getattr(fp, n).clone() for n in names])
+    graphs = []
+    for fp, st in zip(fps, streams):
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=st):
+            fp.step()
+        graphs.append(g)
+    for rep in range(6):
+        for fp in fps:
+            for n in ("qcoeff", "eobs", "cdef_mse", "M", "Hm", "final", "me_sad"):
+                getattr(fp, n).zero_()
+        torch.cuda.synchronize()
+        for g, st in zip(graphs, streams):
+            with torch.cuda.stream(st):
+                g.replay() if rep % 2 == 0 else None
+        if rep % 2:  # eager launches, interleaved call by call
+            for fp, st in zip(fps, streams):
+                with torch.cuda.stream(st):
+                    fp.step()
+        torch.cuda.synchronize()
+        for fp, w in zip(fps, want):
+            for n, t in zip(names, w):
+                assert torch.equal(getattr(fp, n), t), (rep, n)
