@@ -31,7 +31,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "1080p preset-8 hot-path (ME + transform/quant + CDEF + Wiener) frames/sec"
-N_FRAME_SETS = 4  # rotated between steps so that consecutive steps do not hit a warm L2
+N_FRAME_SETS = 8  # rotated between steps: no step finds its inputs in L2, and (e2e) up to 8 frames are in flight
 N_CALLS = 8       # len(FramePipeline.CALLS): the T2 entry points one frame goes through
 # dram__bytes_read.sum + dram__bytes_write.sum of the call's dominant kernel, per launch, from the ncu --set full
 # capture of this same command (profiles/README.md says which file); None = not captured for that call
@@ -252,6 +252,7 @@ def main():
     ap.add_argument("--check", action="store_true", help="compare one frame of B200 output with the reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--one-stream", action="store_true", help="all frames on one compute stream (no frame-level overlap)")
+    ap.add_argument("--streams", type=int, default=4, help="compute streams that consecutive frames alternate between (1, 2 or 4)")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying one CUDA graph per step")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -267,7 +268,7 @@ def main():
               "l2": "steps rotate over %d distinct frame sets (~65 MB each, >126 MB L2 in total)" % N_FRAME_SETS,
               "parallelism": "frame-parallel x%d (no data-path collective; recon exchange = all_gather of the filtered frame)" % world,
               "overlap": "ME (source pictures only) on a side stream, concurrent with the transform->CDEF->restoration chain of the same step",
-              "streams": "1 compute stream" if args.one_stream else "2 compute streams: consecutive (independent) frames alternate between them",
+              "streams": "1 compute stream" if args.one_stream else "%d compute streams: consecutive (independent) frames alternate between them" % args.streams,
               "launch": "eager" if args.no_graph else "one CUDA graph replay per step (the step's kernel launches captured once per frame set)"}
 
     if args.impl == "reference":
@@ -303,8 +304,10 @@ def main():
     stream = torch.cuda.Stream()
     # consecutive frames alternate between two compute streams: independent pictures in flight at once, as in
     # the encoder's picture-parallel pipeline; frame set k always runs on stream k % 2
-    streams = [stream, torch.cuda.Stream()] if not args.one_stream else [stream, stream]
-    gathered = [torch.empty((world,) + tuple(sets[0].final.shape), dtype=torch.uint8, device="cuda") for _ in range(2)] if world > 1 else None
+    n_streams = 1 if args.one_stream else args.streams
+    assert n_streams in (1, 2, 4), "--streams must divide the %d frame sets" % N_FRAME_SETS
+    streams = [stream] + [torch.cuda.Stream() for _ in range(n_streams - 1)]
+    gathered = [torch.empty((world,) + tuple(sets[0].final.shape), dtype=torch.uint8, device="cuda") for _ in range(N_FRAME_SETS)] if world > 1 else None
 
     def barrier():
         torch.cuda.synchronize()
@@ -326,7 +329,7 @@ def main():
     def capture_graphs():
         for k, fp in enumerate(sets):
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g, stream=streams[k % 2]):
+            with torch.cuda.graph(g, stream=streams[k % n_streams]):
                 fp.step()
             graphs[k] = g
 
@@ -334,20 +337,22 @@ def main():
         ev = [[torch.cuda.Event(enable_timing=True) for _ in range(N_CALLS + 1)] for _ in range(n)] if stage_acc is not None else None
         start, end, tail = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), torch.cuda.Event()
         start.record(stream)
-        streams[1].wait_event(start)
+        for x in streams[1:]:
+            x.wait_event(start)
         for i in range(n):
-            st = stream if ev else streams[i % 2]  # the per-call profile runs strictly serially
+            st = stream if ev else streams[i % n_streams]  # the per-call profile runs strictly serially
             with torch.cuda.stream(st):
                 fp = sets[i % N_FRAME_SETS]
                 if e2e:
                     fp.load_inputs()
                 enqueue_step(i, ev[i] if ev else None)
                 if world > 1:  # reconstructed-reference exchange (the path's one real collective)
-                    dist.all_gather_into_tensor(gathered[i % 2].view(-1), fp.final)
+                    dist.all_gather_into_tensor(gathered[i % N_FRAME_SETS].view(-1), fp.final)
                 if e2e:
                     fp.read_outputs()
-        tail.record(streams[1])
-        stream.wait_event(tail)
+        for x in streams[1:]:
+            tail.record(x)
+            stream.wait_event(tail)
         end.record(stream)
         torch.cuda.synchronize()
         if stage_acc is not None:
@@ -375,12 +380,12 @@ def main():
                     s_in.wait_event(ev_out[i - N_FRAME_SETS])
                 fp.load_inputs()
                 ev_in[i].record(s_in)
-            cs = streams[i % 2]
+            cs = streams[i % n_streams]
             with torch.cuda.stream(cs):
                 cs.wait_event(ev_in[i])
                 enqueue_step(i)
                 if world > 1:
-                    dist.all_gather_into_tensor(gathered[i % 2].view(-1), fp.final)
+                    dist.all_gather_into_tensor(gathered[i % N_FRAME_SETS].view(-1), fp.final)
                 ev_done[i].record(cs)
             with torch.cuda.stream(s_out):
                 s_out.wait_event(ev_done[i])

@@ -41,15 +41,30 @@ __global__ void downsample_2d_kernel(const uint8_t* __restrict__ in, int in_stri
         out[(size_t)oy * out_stride + ox] = (uint8_t)((s + 2) >> 2);
     }
 }
-// replicate the w x h interior (at (org_x, org_y)) into the surrounding padding (svt_aom_generate_padding)
-__global__ void pad_plane_kernel(uint8_t* buf, int stride, int w, int h, int org_x, int org_y) {
-    const int tw = w + 2 * org_x, th = h + 2 * org_y;
-    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < tw * th; idx += gridDim.x * blockDim.x) {
-        const int y = idx / tw, x = idx - y * tw;
-        if (x >= org_x && x < org_x + w && y >= org_y && y < org_y + h) continue;
-        const int sx = min(max(x, org_x), org_x + w - 1), sy = min(max(y, org_y), org_y + h - 1);
-        buf[(size_t)y * stride + x] = buf[(size_t)sy * stride + sx];
+// replicate the w x h interior (at (org_x, org_y)) into the surrounding padding (svt_aom_generate_padding);
+// only the border elements are visited: top band, bottom band, then the left/right strips of the interior rows
+__device__ __forceinline__ void pad_border_element(uint8_t* buf, int stride, int w, int h, int org_x, int org_y, int idx) {
+    const int tw = w + 2 * org_x, band = org_y * tw;
+    int x, y;
+    if (idx < 2 * band) {
+        const int j = idx < band ? idx : idx - band;
+        y = j / tw + (idx < band ? 0 : org_y + h);
+        x = j % tw;
+    } else {
+        const int j = idx - 2 * band, xx = j % (2 * org_x);
+        y = org_y + j / (2 * org_x);
+        x = xx < org_x ? xx : w + xx;
     }
+    const int sx = min(max(x, org_x), org_x + w - 1), sy = min(max(y, org_y), org_y + h - 1);
+    buf[(size_t)y * stride + x] = buf[(size_t)sy * stride + sx];
+}
+__host__ __device__ __forceinline__ int pad_border_count(int w, int h, int org_x, int org_y) {
+    return 2 * org_y * (w + 2 * org_x) + 2 * org_x * h;
+}
+__global__ void pad_plane_kernel(uint8_t* buf, int stride, int w, int h, int org_x, int org_y) {
+    const int n = pad_border_count(w, h, org_x, org_y);
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += gridDim.x * blockDim.x)
+        pad_border_element(buf, stride, w, h, org_x, org_y, idx);
 }
 
 // ---- HME window arithmetic (shared by the three levels) ---------------------------------------
@@ -362,13 +377,9 @@ struct PadPlanes {
 // several planes in one launch: blockIdx.y = plane
 __global__ void pad_planes_kernel(const __grid_constant__ PadPlanes pl) {
     const SvtB200PlaneExtent& e = pl.p[blockIdx.y];
-    const int tw = e.w + 2 * e.org_x, th = e.h + 2 * e.org_y;
-    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < tw * th; idx += gridDim.x * blockDim.x) {
-        const int y = idx / tw, x = idx - y * tw;
-        if (x >= e.org_x && x < e.org_x + e.w && y >= e.org_y && y < e.org_y + e.h) continue;
-        const int sx = min(max(x, e.org_x), e.org_x + e.w - 1), sy = min(max(y, e.org_y), e.org_y + e.h - 1);
-        e.buf[(size_t)y * e.stride + x] = e.buf[(size_t)sy * e.stride + sx];
-    }
+    const int n = pad_border_count(e.w, e.h, e.org_x, e.org_y);
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += gridDim.x * blockDim.x)
+        pad_border_element(e.buf, e.stride, e.w, e.h, e.org_x, e.org_y, idx);
 }
 
 extern "C" int svt_b200_extend_planes_dev(const SvtB200PlaneExtent* planes, int n_planes, void* stream) {
@@ -380,7 +391,7 @@ extern "C" int svt_b200_extend_planes_dev(const SvtB200PlaneExtent* planes, int 
     for (int i = 0; i < n_planes; i++) {
         if (!planes[i].buf || planes[i].w <= 0 || planes[i].h <= 0) return SVT_B200_ERR_BAD_ARG;
         pl.p[i] = planes[i];
-        const int t = (planes[i].w + 2 * planes[i].org_x) * (planes[i].h + 2 * planes[i].org_y);
+        const int t = pad_border_count(planes[i].w, planes[i].h, planes[i].org_x, planes[i].org_y);
         tn = t > tn ? t : tn;
     }
     pad_planes_kernel<<<dim3(grid_for((tn + 255) / 256, 4), n_planes), 256, 0, (cudaStream_t)stream>>>(pl);
@@ -391,7 +402,8 @@ extern "C" int svt_b200_extend_planes_dev(const SvtB200PlaneExtent* planes, int 
 extern "C" int svt_b200_extend_plane_dev(uint8_t* d_buf, int stride, int w, int h, int org_x, int org_y, void* stream) {
     require_ready();
     if (!d_buf || w <= 0 || h <= 0) return SVT_B200_ERR_BAD_ARG;
-    const int tn = (w + 2 * org_x) * (h + 2 * org_y);
+    const int tn = pad_border_count(w, h, org_x, org_y);
+    if (tn <= 0) return SVT_B200_OK;
     pad_plane_kernel<<<grid_for((tn + 255) / 256, 8), 256, 0, (cudaStream_t)stream>>>(d_buf, stride, w, h, org_x, org_y);
     B200_LAUNCH_CHECK();
     return SVT_B200_OK;
@@ -409,7 +421,7 @@ extern "C" int svt_b200_build_hme_pyramid_dev(const SvtB200MePicture* pic, void*
         const int n = pic->width[lvl] * pic->height[lvl];
         downsample_2d_kernel<<<grid_for((n + 255) / 256, 8), 256, 0, st>>>(in, pic->stride[s], pic->width[s], pic->height[s], out, pic->stride[lvl], 2);
         B200_LAUNCH_CHECK();
-        const int tn = (pic->width[lvl] + 2 * pic->org_x[lvl]) * (pic->height[lvl] + 2 * pic->org_y[lvl]);
+        const int tn = pad_border_count(pic->width[lvl], pic->height[lvl], pic->org_x[lvl], pic->org_y[lvl]);
         pad_plane_kernel<<<grid_for((tn + 255) / 256, 8), 256, 0, st>>>(const_cast<uint8_t*>(pic->plane[lvl]), pic->stride[lvl], pic->width[lvl],
                                                                       pic->height[lvl], pic->org_x[lvl], pic->org_y[lvl]);
         B200_LAUNCH_CHECK();
