@@ -299,8 +299,8 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dsp.init(local_rank)
-    sets = [FramePipeline(FrameWorkload(args.width, args.height, seed=20260923 + 17 * (rank * N_FRAME_SETS + i)), torch) for i in range(N_FRAME_SETS)]
-    wl0 = sets[0].wl
+    wl0 = FrameWorkload(args.width, args.height, seed=20260923 + 17 * rank * N_FRAME_SETS)
+    sets = [FramePipeline(wl0 if i == 0 else wl0.with_seed(20260923 + 17 * (rank * N_FRAME_SETS + i)), torch) for i in range(N_FRAME_SETS)]
     stream = torch.cuda.Stream()
     # consecutive frames alternate between two compute streams: independent pictures in flight at once, as in
     # the encoder's picture-parallel pipeline; frame set k always runs on stream k % 2

@@ -398,9 +398,11 @@ cdef_search_kernel(SvtB200CdefFrame f, const uint8_t* __restrict__ skip8x8, cons
             for (int i = threadIdx.x; i < kGChunk * 64 * 5; i += blockDim.x) (&s_blk[0][0][0])[i] = 0;
             if (threadIdx.x < kGChunk) s_acc[threadIdx.x] = 0;
             unsigned with_pri = 0, without_pri = 0;  // which strengths of the chunk have / lack a primary part
+            bool     sec_without_pri = false;         // ... and whether any of the latter has a secondary part
             for (int gi = 0; gi < ng; gi++) {
                 const int sv = strengths[g0 + gi];
                 if (sv >= 0) (sv / 4 ? with_pri : without_pri) |= 1u << gi;
+                if (sv > 0 && sv / 4 == 0) sec_without_pri = true;
             }
             __syncthreads();
             for (int idx = threadIdx.x; idx < ((count * ppb + 31) & ~31); idx += blockDim.x) {  // whole warps stay in the loop (shuffles)
@@ -415,8 +417,11 @@ cdef_search_kernel(SvtB200CdefFrame f, const uint8_t* __restrict__ skip8x8, cons
                 for (int pass = 0; pass < 2; pass++) {
                     const unsigned todo = pass ? without_pri : with_pri;
                     if (!todo) continue;  // CTA-uniform
+                    // a candidate with neither a primary nor a secondary part leaves the pixel unchanged
+                    // (sum = 0, and x lies inside [min, max] of its own neighbourhood): no taps needed
                     CdefTaps T;
-                    cdef_load_taps(in, kTP, pass ? 0 : dirb, x, T);
+                    const bool taps = pass == 0 || sec_without_pri;  // CTA-uniform
+                    if (taps) cdef_load_taps(in, kTP, pass ? 0 : dirb, x, T);
                     // the primary half is recomputed when the primary strength changes, the secondary half
                     // once per distinct secondary code (0..3) of this pass
                     int last_pri = -1, psum = 0, sec1 = 0, sec2 = 0, sec3 = 0;
@@ -442,7 +447,7 @@ cdef_search_kernel(SvtB200CdefFrame f, const uint8_t* __restrict__ skip8x8, cons
                             }
                             ssum = sec_code == 1 ? sec1 : (sec_code == 2 ? sec2 : sec3);
                         }
-                        const unsigned int y = live ? (unsigned int)cdef_finish_px(T, x, psum + ssum) : 0u;
+                        const unsigned int y = live ? (unsigned int)(taps ? cdef_finish_px(T, x, psum + ssum) : x) : 0u;
                         if (pli == 0) {
                             // five moments of the block (<= 64 pixels of <= 12 bits: fit 32 bits)
                             unsigned int ss = y, sdv = o, s2 = y * y, d2 = o * o, sdp = y * o;

@@ -58,20 +58,30 @@ class FrameWorkload:
     def __init__(self, width=1920, height=1080, seed=20260923, n_refs=2):
         assert width % 8 == 0 and height % 8 == 0
         self.width, self.height, self.n_refs = width, height, n_refs
-        seq = synth_sequence(width, height, n_refs + 1, seed)
-        self.cur = seq[1]
-        self.refs = [seq[0], seq[2]][:n_refs]
+        self._set_pictures(seed)
         self.me_shapes = dsp.me_plane_shapes(width, height)
         # M8 / 1080p / crf 30 / distance 1 (module docstring)
         self.me_params = [dict(hme_l0_sa_w=16, hme_l0_sa_h=4, hme_l1_sa_w=8, hme_l1_sa_h=3, hme_l2_sa_w=8, hme_l2_sa_h=3, me_sa_w=8,
                                me_sa_h=3, hme_sub_sad=1, me_sub_sad=1, check_zero_centre=1) for _ in range(n_refs)]
         self.plane_dims = [(width, height), (width // 2, height // 2), (width // 2, height // 2)]
-        # prediction = previous picture (zero-motion inter prediction); residual = cur - pred
-        self.pred = [self.refs[0][p] for p in range(3)]
-        self.residual = [self.cur[p].astype(np.int16) - self.pred[p].astype(np.int16) for p in range(3)]
         self._build_tx_items()
         self._build_cdef()
         self._build_rest()
+
+    def _set_pictures(self, seed):
+        seq = synth_sequence(self.width, self.height, self.n_refs + 1, seed)
+        self.cur = seq[1]
+        self.refs = [seq[0], seq[2]][:self.n_refs]
+        # prediction = previous picture (zero-motion inter prediction); residual = cur - pred
+        self.pred = [self.refs[0][p] for p in range(3)]
+        self.residual = [self.cur[p].astype(np.int16) - self.pred[p].astype(np.int16) for p in range(3)]
+
+    def with_seed(self, seed):
+        """the same work lists (they do not depend on the content) over another synthetic sequence"""
+        import copy
+        w = copy.copy(self)
+        w._set_pictures(seed)
+        return w
 
     # -- planes as flat buffers ---------------------------------------------------------------------
     def flat_offsets(self, itemsize_elems=1):
