@@ -104,21 +104,26 @@ __device__ int cdef_find_dir_dev(const T* img, int stride, int* var, int coeff_s
 }
 
 // Taps of one pixel along direction `dir` (cdef.c:262-302), reduced to what every candidate strength
-// shares: |tap - x|, its sign, and the min / max over the taps that are inside the picture.
-// Slots 0..3 primary (k=0: +,-; k=1: +,-), 4..7 secondary k=0, 8..11 secondary k=1.
+// shares, two taps per 32-bit register (16-bit halves; every value fits: pixels <= 4095, CDEF_VERY_LARGE =
+// 0x7f7f, |differences| <= 0x7f7f): the signed differences tap - x, their magnitudes, and the min / max over
+// the taps that are inside the picture.  Pairs: 0 = primary k=0 (+,-), 1 = primary k=1, 2..3 = secondary
+// k=0, 4..5 = secondary k=1.  The packed min/max/add instructions used (VIMNMX.16x2, VIADD.16x2) are native.
 struct CdefTaps {
-    int ad[12];
-    int sg[12];
-    int mn, mx;
+    uint32_t d[6];   // signed differences
+    uint32_t ad[6];  // |differences|
+    int      mn, mx;
 };
 __device__ __forceinline__ void cdef_load_taps(const uint16_t* in, int s, int dir, int x, CdefTaps& T) {
-    int mx = x, mn = x;
-    auto put = [&](int slot, int v) {
-        const int diff = v - x;
-        T.ad[slot] = abs(diff);
-        T.sg[slot] = diff < 0 ? -1 : 1;
-        mx = max(mx, v == kVeryLarge ? 0 : v);  // CDEF_VERY_LARGE marks "outside": never the maximum
-        mn = min(mn, v);
+    const uint32_t xx = (uint32_t)x * 0x10001u, nxx = __vneg2(xx);
+    uint32_t       mx2 = xx, mn2 = xx;
+    auto put = [&](int pair, uint32_t lo, uint32_t hi) {
+        const uint32_t p = lo | (hi << 16);
+        T.d[pair]  = __vadd2(p, nxx);
+        T.ad[pair] = __vmaxu2(p, xx) - __vminu2(p, xx);  // halves are >= 0: no borrow between them
+        // CDEF_VERY_LARGE marks "outside the picture": never the maximum.  Bit 14 tells it from a pixel.
+        const uint32_t vl = (p >> 14) & 0x00010001u;
+        mx2 = __vmaxu2(mx2, p - vl * (uint32_t)kVeryLarge);
+        mn2 = __vminu2(mn2, p);
     };
     const int d2 = (dir + 2) & 7, d6 = (dir + 6) & 7;
 #pragma unroll
@@ -126,37 +131,40 @@ __device__ __forceinline__ void cdef_load_taps(const uint16_t* in, int s, int di
         const int po  = c_cdef_dir[dir][k][0] * s + c_cdef_dir[dir][k][1];
         const int s0o = c_cdef_dir[d2][k][0] * s + c_cdef_dir[d2][k][1];
         const int s2o = c_cdef_dir[d6][k][0] * s + c_cdef_dir[d6][k][1];
-        put(2 * k, in[po]);
-        put(2 * k + 1, in[-po]);
-        put(4 + 4 * k, in[s0o]);
-        put(5 + 4 * k, in[-s0o]);
-        put(6 + 4 * k, in[s2o]);
-        put(7 + 4 * k, in[-s2o]);
+        put(k, in[po], in[-po]);
+        put(2 + 2 * k, in[s0o], in[-s0o]);
+        put(3 + 2 * k, in[s2o], in[-s2o]);
     }
-    T.mn = mn;
-    T.mx = mx;
+    T.mn = (int)min(mn2 & 0xffffu, mn2 >> 16);
+    T.mx = (int)max(mx2 & 0xffffu, mx2 >> 16);
 }
-// The filtered pixel for one (primary, secondary) strength.  constrain() (cdef.c:85-93) with a zero
-// threshold yields zero by itself here: max(0, 0 - (|d| >> shift)) = 0.  The reference accumulates in
-// int16; |sum| <= 2*(4+2)*240 + 4*(2+1)*64 for 12-bit content, so the int32 sum below is the same number.
+// constrain() (cdef.c:85-93) of the two taps of a pair, summed with weight w each:
+// sign(d) * min(|d|, max(0, thr - (|d| >> shift))) = clamp(d, -m, m) with m = thr - min(|d| >> shift, thr).
+// A zero threshold gives m = 0 and so zero by itself.  The reference accumulates in int16; |sum| <=
+// 2*(4+2)*240 + 4*(2+1)*64 for 12-bit content, so the int32 sum is the same number.
+__device__ __forceinline__ int cdef_pair_sum(const CdefTaps& T, int pair, uint32_t thr2, int sh, uint32_t shmask, int wbytes, int acc) {
+    const uint32_t t1 = (T.ad[pair] >> sh) & shmask;
+    const uint32_t m  = thr2 - __vminu2(t1, thr2);
+    const uint32_t v  = __vmins2(__vmaxs2(T.d[pair], __vneg2(m)), m);
+    return __dp2a_lo((int)v, wbytes, acc);
+}
 // The sum splits into a primary part (4 taps, depends on the primary strength only) and a secondary part
 // (8 taps, depends on the secondary strength only): candidate strengths that share one of the two share
 // that half of the work.
-__device__ __forceinline__ int cdef_constrained(const CdefTaps& T, int slot, int thr, int sh) {
-    return min(T.ad[slot], max(0, thr - (T.ad[slot] >> sh))) * T.sg[slot];
-}
 __device__ __forceinline__ int cdef_primary_sum(const CdefTaps& T, int pri, int pri_damping, int coeff_shift) {
-    const int sh  = max(0, pri_damping - msb32((uint32_t)pri));
-    const int pk0 = cdef_constrained(T, 0, pri, sh) + cdef_constrained(T, 1, pri, sh);
-    const int pk1 = cdef_constrained(T, 2, pri, sh) + cdef_constrained(T, 3, pri, sh);
-    const int odd = (pri >> coeff_shift) & 1;
-    return (odd ? 3 : 4) * pk0 + (odd ? 3 : 2) * pk1;
+    const int      sh = max(0, pri_damping - msb32((uint32_t)pri));
+    const uint32_t thr2 = (uint32_t)pri * 0x10001u, shmask = (0xffffu >> sh) * 0x10001u;
+    const int      odd = (pri >> coeff_shift) & 1;
+    int            sum = cdef_pair_sum(T, 0, thr2, sh, shmask, odd ? 0x0303 : 0x0404, 0);
+    return cdef_pair_sum(T, 1, thr2, sh, shmask, odd ? 0x0303 : 0x0202, sum);
 }
 __device__ __forceinline__ int cdef_secondary_sum(const CdefTaps& T, int sec, int sec_damping) {
-    const int sh  = max(0, sec_damping - msb32((uint32_t)sec));
-    const int sk0 = cdef_constrained(T, 4, sec, sh) + cdef_constrained(T, 5, sec, sh) + cdef_constrained(T, 6, sec, sh) + cdef_constrained(T, 7, sec, sh);
-    const int sk1 = cdef_constrained(T, 8, sec, sh) + cdef_constrained(T, 9, sec, sh) + cdef_constrained(T, 10, sec, sh) + cdef_constrained(T, 11, sec, sh);
-    return 2 * sk0 + sk1;
+    const int      sh = max(0, sec_damping - msb32((uint32_t)sec));
+    const uint32_t thr2 = (uint32_t)sec * 0x10001u, shmask = (0xffffu >> sh) * 0x10001u;
+    int            sum = cdef_pair_sum(T, 2, thr2, sh, shmask, 0x0202, 0);
+    sum = cdef_pair_sum(T, 3, thr2, sh, shmask, 0x0202, sum);
+    sum = cdef_pair_sum(T, 4, thr2, sh, shmask, 0x0101, sum);
+    return cdef_pair_sum(T, 5, thr2, sh, shmask, 0x0101, sum);
 }
 __device__ __forceinline__ int cdef_finish_px(const CdefTaps& T, int x, int sum) {
     const int y = x + ((8 + sum - (sum < 0)) >> 4);
