@@ -348,8 +348,9 @@ cdef_search_kernel(SvtB200CdefFrame f, const uint8_t* __restrict__ skip8x8, cons
     __shared__ uint8_t  s_list[64];  // by*8+bx of the non-skip 8x8s, raster order (svt_sb_compute_cdef_list)
     __shared__ int      s_count;
     __shared__ unsigned s_ballot[2];
-    __shared__ unsigned long long s_acc[kGChunk];
-    __shared__ unsigned int       s_blk[kGChunk][64][5];  // luma: per strength, per block: sum_s, sum_d, sum_s2, sum_d2, sum_sd
+    __shared__ int                s_sv[kGChunk];          // the chunk's strength codes (-1 = not tested)
+    __shared__ unsigned long long s_dist[kGChunk][64];    // per strength, per block: distortion
+    __shared__ unsigned int       s_blk[kGChunk][64][5];  // per strength, per block: luma sum_s, sum_d, sum_s2, sum_d2, sum_sd; chroma [0] = sse
     const int nhfb = (f.width + 63) >> 6, nvfb = (f.height + 63) >> 6, nfb = nhfb * nvfb;
     const int cs = f.bit_depth > 8 ? f.bit_depth - 8 : 0;
     const int w8 = (f.width + 7) >> 3, h8 = (f.height + 7) >> 3;
@@ -404,7 +405,7 @@ cdef_search_kernel(SvtB200CdefFrame f, const uint8_t* __restrict__ skip8x8, cons
         for (int g0 = 0; g0 < n_strengths; g0 += kGChunk) {
             const int ng = min(kGChunk, n_strengths - g0);
             for (int i = threadIdx.x; i < kGChunk * 64 * 5; i += blockDim.x) (&s_blk[0][0][0])[i] = 0;
-            if (threadIdx.x < kGChunk) s_acc[threadIdx.x] = 0;
+            if ((int)threadIdx.x < ng) s_sv[threadIdx.x] = strengths[g0 + threadIdx.x];
             unsigned with_pri = 0, without_pri = 0;  // which strengths of the chunk have / lack a primary part
             bool     sec_without_pri = false;         // ... and whether any of the latter has a secondary part
             for (int gi = 0; gi < ng; gi++) {
@@ -437,7 +438,7 @@ cdef_search_kernel(SvtB200CdefFrame f, const uint8_t* __restrict__ skip8x8, cons
 #pragma unroll 1
                     for (int gi = 0; gi < ng; gi++) {
                         if (!((todo >> gi) & 1)) continue;  // CTA-uniform
-                        const int sv = strengths[g0 + gi];
+                        const int sv = s_sv[gi];
                         const int pri_code = sv >> 2, sec_code = sv & 3;  // sv >= 0 here
                         if (pri_code != last_pri) {  // CTA-uniform
                             const int pri = pri_code << cs;
@@ -476,28 +477,28 @@ cdef_search_kernel(SvtB200CdefFrame f, const uint8_t* __restrict__ skip8x8, cons
                             }
                         } else {
                             const int e = (int)o - (int)y;
-                            unsigned int se = (unsigned int)(e * e);
-                            for (int sh = 16; sh > 0; sh >>= 1) se += __shfl_xor_sync(0xffffffffu, se, sh);
-                            if ((threadIdx.x & 31) == 0 && se) atomicAdd(&s_acc[gi], (unsigned long long)se);
+                            unsigned int se = (unsigned int)(e * e);  // a block's 16 pixels of <= 12 bits: fits 32 bits
+                            for (int sh = seg >> 1; sh > 0; sh >>= 1) se += __shfl_xor_sync(0xffffffffu, se, sh);
+                            if (live && (idx & (seg - 1)) == 0 && se) atomicAdd(&s_blk[gi][bi][0], se);
                         }
                     }
                 }
             }
             __syncthreads();
-            if (pli == 0) {
-                for (int q = threadIdx.x; q < ng * count; q += blockDim.x) {
-                    const int gi = q / count, bi = q - gi * count;
-                    if (strengths_y[g0 + gi] < 0) continue;
-                    const unsigned int* sb = s_blk[gi][bi];
-                    atomicAdd(&s_acc[gi], cdef_dist_from_sums(sb[0], sb[1], sb[2], sb[3], sb[4], cs));
-                }
-                __syncthreads();
+            // per (strength, block): the block's distortion (luma: the psy formula on its five moments)
+            for (int q = threadIdx.x; q < ng * count; q += blockDim.x) {
+                const int gi = q / count, bi = q - gi * count;
+                const unsigned int* sb = s_blk[gi][bi];
+                s_dist[gi][bi] = pli == 0 ? cdef_dist_from_sums(sb[0], sb[1], sb[2], sb[3], sb[4], cs) : (unsigned long long)sb[0];
             }
+            __syncthreads();
             if ((int)threadIdx.x < ng) {
-                const int g = g0 + threadIdx.x, sv = strengths[g];
+                const int g = g0 + threadIdx.x, sv = s_sv[threadIdx.x];
+                unsigned long long acc = 0;
+                for (int bi = 0; bi < count; bi++) acc += s_dist[threadIdx.x][bi];
                 unsigned long long* m = mse + (size_t)((pli ? 1 : 0) * nfb + fb) * n_strengths + g;
                 // enc: mse_seg = (sum >> 2*coeff_shift) * subsampling_factor; untested chroma = default_mse_uv*64
-                const unsigned long long v = sv >= 0 ? (s_acc[threadIdx.x] >> (2 * cs)) * (unsigned long long)subs : 0;
+                const unsigned long long v = sv >= 0 ? (acc >> (2 * cs)) * (unsigned long long)subs : 0;
                 if (pli == 0) *m = v;
                 else atomicAdd(m, sv < 0 ? (pli == 1 ? 1040400ull * 64ull : 0ull) : v);
             }
