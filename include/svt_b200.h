@@ -75,6 +75,17 @@ SVT_B200_API void svt_b200_sad_loop_kernel(uint8_t* src, uint32_t src_stride, ui
 SVT_B200_API uint32_t svt_b200_nxm_sad_kernel(const uint8_t* src, uint32_t src_stride, const uint8_t* ref,
                                               uint32_t ref_stride, uint32_t height, uint32_t width);
 
+/* T1: svt_aom_sadMxN and svt_aom_sadMxNx4d (aom_dsp_rtcd.h:275-403; C: compute_sad_c.c:104-215): the single-block
+ * SADs of mode decision, M = width, N = height; x4d = the same source block against four references. */
+#define SVT_B200_DECL_SAD(M, N)                                                                                      \
+    SVT_B200_API uint32_t svt_b200_aom_sad##M##x##N(const uint8_t* src, int src_stride, const uint8_t* ref, int ref_stride); \
+    SVT_B200_API void svt_b200_aom_sad##M##x##N##x4d(const uint8_t* src, int src_stride, const uint8_t* const ref_array[], \
+                                                     int ref_stride, uint32_t* sad_array);
+SVT_B200_DECL_SAD(128, 128) SVT_B200_DECL_SAD(128, 64) SVT_B200_DECL_SAD(64, 128) SVT_B200_DECL_SAD(64, 64) SVT_B200_DECL_SAD(64, 32) SVT_B200_DECL_SAD(64, 16) SVT_B200_DECL_SAD(32, 64) SVT_B200_DECL_SAD(32, 32)
+SVT_B200_DECL_SAD(32, 16) SVT_B200_DECL_SAD(32, 8) SVT_B200_DECL_SAD(16, 64) SVT_B200_DECL_SAD(16, 32) SVT_B200_DECL_SAD(16, 16) SVT_B200_DECL_SAD(16, 8) SVT_B200_DECL_SAD(16, 4) SVT_B200_DECL_SAD(8, 32)
+SVT_B200_DECL_SAD(8, 16) SVT_B200_DECL_SAD(8, 8) SVT_B200_DECL_SAD(8, 4) SVT_B200_DECL_SAD(4, 16) SVT_B200_DECL_SAD(4, 8) SVT_B200_DECL_SAD(4, 4)
+#undef SVT_B200_DECL_SAD
+
 /* T2 work item: one full search.  Offsets are in bytes from the plane base pointers given to the
  * batch call.  src_stride/ref_stride are the row pitches used for BLOCK rows (2x the plane pitch in
  * SUB_SAD mode, motion_estimation.c:463-481); ref_step is the pitch between SEARCH rows (the
@@ -125,6 +136,9 @@ SVT_B200_API int svt_b200_txfm_valid(int tx_size, int tx_type);
  * Input of the inverse is min(W,32) x min(H,32) packed coefficients (inv_transforms.c:2567-2686). */
 SVT_B200_API void svt_b200_fwd_txfm2d(int16_t* input, int32_t* output, uint32_t input_stride, int tx_type,
                                       int tx_size, uint8_t bit_depth);
+/* level 0 = full, 1 = N2, 2 = N4 (see the _N2 / _N4 named forms below) */
+SVT_B200_API void svt_b200_fwd_txfm2d_partial(int16_t* input, int32_t* output, uint32_t input_stride, int tx_type,
+                                              int tx_size, uint8_t bit_depth, int level);
 SVT_B200_API void svt_b200_inv_txfm2d_add(const int32_t* input, uint16_t* output_r, int32_t stride_r,
                                           uint16_t* output_w, int32_t stride_w, int tx_type, int tx_size, int32_t bd);
 /* svt_av1_inv_txfm_add (common_dsp_rtcd.h:144; C: inv_transforms.c:3177): 8-bit pixels. */
@@ -139,6 +153,16 @@ SVT_B200_DECL_FWD(4x4) SVT_B200_DECL_FWD(8x8) SVT_B200_DECL_FWD(16x16) SVT_B200_
 SVT_B200_DECL_FWD(4x8) SVT_B200_DECL_FWD(8x4) SVT_B200_DECL_FWD(8x16) SVT_B200_DECL_FWD(16x8) SVT_B200_DECL_FWD(16x32)
 SVT_B200_DECL_FWD(32x16) SVT_B200_DECL_FWD(32x64) SVT_B200_DECL_FWD(64x32) SVT_B200_DECL_FWD(4x16) SVT_B200_DECL_FWD(16x4)
 SVT_B200_DECL_FWD(8x32) SVT_B200_DECL_FWD(32x8) SVT_B200_DECL_FWD(16x64) SVT_B200_DECL_FWD(64x16)
+/* svt_av1_fwd_txfm2d_WxH_N2 / _N4 (aom_dsp_rtcd.h:131-245; C: av1_tranform_two_d_core_N2_c / _N4_c,
+ * transforms.c:5202, 6769): only the top-left (W/2 x H/2) / (W/4 x H/4) coefficients, the rest zero. */
+SVT_B200_DECL_FWD(4x4_N2) SVT_B200_DECL_FWD(8x8_N2) SVT_B200_DECL_FWD(16x16_N2) SVT_B200_DECL_FWD(32x32_N2) SVT_B200_DECL_FWD(64x64_N2)
+SVT_B200_DECL_FWD(4x8_N2) SVT_B200_DECL_FWD(8x4_N2) SVT_B200_DECL_FWD(8x16_N2) SVT_B200_DECL_FWD(16x8_N2) SVT_B200_DECL_FWD(16x32_N2)
+SVT_B200_DECL_FWD(32x16_N2) SVT_B200_DECL_FWD(32x64_N2) SVT_B200_DECL_FWD(64x32_N2) SVT_B200_DECL_FWD(4x16_N2) SVT_B200_DECL_FWD(16x4_N2)
+SVT_B200_DECL_FWD(8x32_N2) SVT_B200_DECL_FWD(32x8_N2) SVT_B200_DECL_FWD(16x64_N2) SVT_B200_DECL_FWD(64x16_N2)
+SVT_B200_DECL_FWD(4x4_N4) SVT_B200_DECL_FWD(8x8_N4) SVT_B200_DECL_FWD(16x16_N4) SVT_B200_DECL_FWD(32x32_N4) SVT_B200_DECL_FWD(64x64_N4)
+SVT_B200_DECL_FWD(4x8_N4) SVT_B200_DECL_FWD(8x4_N4) SVT_B200_DECL_FWD(8x16_N4) SVT_B200_DECL_FWD(16x8_N4) SVT_B200_DECL_FWD(16x32_N4)
+SVT_B200_DECL_FWD(32x16_N4) SVT_B200_DECL_FWD(32x64_N4) SVT_B200_DECL_FWD(64x32_N4) SVT_B200_DECL_FWD(4x16_N4) SVT_B200_DECL_FWD(16x4_N4)
+SVT_B200_DECL_FWD(8x32_N4) SVT_B200_DECL_FWD(32x8_N4) SVT_B200_DECL_FWD(16x64_N4) SVT_B200_DECL_FWD(64x16_N4)
 #undef SVT_B200_DECL_FWD
 #define SVT_B200_DECL_INV_A(WxH)                                                                                \
     SVT_B200_API void svt_b200_av1_inv_txfm2d_add_##WxH(const int32_t* input, uint16_t* output_r, int32_t stride_r, \
@@ -167,7 +191,9 @@ typedef struct SvtB200FwdTxfmItem {
     uint32_t src_stride;
     uint8_t  tx_size;
     uint8_t  tx_type;
-    uint16_t reserved;   /* bit 0: packed output -- only the top-left min(W,32) x min(H,32) coefficients are
+    uint16_t reserved;   /* bits 1-2: 1 = N2, 2 = N4 partial transform (coefficients outside the top-left half /
+                            quarter of each dimension are written as zero);
+                            bit 0: packed output -- only the top-left min(W,32) x min(H,32) coefficients are
                             written, at stride min(W,32) (the re-pack half of svt_handle_transform64x64 etc.,
                             transforms.c:2374-2542); dst must then hold min(W,32)*min(H,32) int32 */
 } SvtB200FwdTxfmItem;

@@ -417,3 +417,37 @@ extern "C" uint32_t svt_b200_nxm_sad_kernel(const uint8_t* src, uint32_t src_str
     l->sync();
     return *l->h<uint32_t>(o_out);
 }
+
+// ---- T1: svt_aom_sadMxN / svt_aom_sadMxNx4d (aom_dsp_rtcd.h:275-403; C: compute_sad_c.c:104-215) ----
+#define B200_SAD_MXN(M, N)                                                                                          \
+    extern "C" uint32_t svt_b200_aom_sad##M##x##N(const uint8_t* src, int src_stride, const uint8_t* ref, int ref_stride) { \
+        return svt_b200_nxm_sad_kernel(src, (uint32_t)src_stride, ref, (uint32_t)ref_stride, N, M);                \
+    }                                                                                                               \
+    extern "C" void svt_b200_aom_sad##M##x##N##x4d(const uint8_t* src, int src_stride, const uint8_t* const ref_array[], \
+                                                   int ref_stride, uint32_t* sad_array) {                           \
+        for (int i = 0; i < 4; i++)                                                                                 \
+            sad_array[i] = svt_b200_nxm_sad_kernel(src, (uint32_t)src_stride, ref_array[i], (uint32_t)ref_stride, N, M); \
+    }
+B200_SAD_MXN(128, 128)
+B200_SAD_MXN(128, 64)
+B200_SAD_MXN(64, 128)
+B200_SAD_MXN(64, 64)
+B200_SAD_MXN(64, 32)
+B200_SAD_MXN(64, 16)
+B200_SAD_MXN(32, 64)
+B200_SAD_MXN(32, 32)
+B200_SAD_MXN(32, 16)
+B200_SAD_MXN(32, 8)
+B200_SAD_MXN(16, 64)
+B200_SAD_MXN(16, 32)
+B200_SAD_MXN(16, 16)
+B200_SAD_MXN(16, 8)
+B200_SAD_MXN(16, 4)
+B200_SAD_MXN(8, 32)
+B200_SAD_MXN(8, 16)
+B200_SAD_MXN(8, 8)
+B200_SAD_MXN(8, 4)
+B200_SAD_MXN(4, 16)
+B200_SAD_MXN(4, 8)
+B200_SAD_MXN(4, 4)
+#undef B200_SAD_MXN

@@ -63,6 +63,7 @@ fwd_txfm_kernel(const int16_t* __restrict__ src_base, int32_t* __restrict__ dst_
         const int16_t* src = src_base + item.src_off;
         int32_t*       dst = dst_base + item.dst_off;
         const int P1 = W + 1, P2 = H + 1;
+        const int part_shift = (item.reserved >> 1) & 3;  // 0 full, 1 = N2, 2 = N4
         // load, optional up/down flip, pre-shift (transforms.c:2286-2294)
         for (int idx = tid; idx < W * H; idx += MOVERS) {
             const int r = idx >> lgW, c = idx & (W - 1);
@@ -86,6 +87,9 @@ fwd_txfm_kernel(const int16_t* __restrict__ src_base, int32_t* __restrict__ dst_
             const int r = idx >> lgW, c = idx & (W - 1);
             int32_t   v = round_shift_arr(B[c * P2 + r], -cfg.f_s2);
             if (rect == 1 || rect == -1) v = round_shift64((long long)v * kNewSqrt2, 12);
+            // N2 / N4 (av1_tranform_two_d_core_N2_c / _N4_c, transforms.c:5202, 6769): the top-left half / quarter
+            // of every dimension, identical to the full transform's values there, zero everywhere else
+            if (part_shift && (r >= max(H >> part_shift, 1) || c >= max(W >> part_shift, 1))) v = 0;
             if (item.reserved & 1) {  // packed output: keep the top-left min(W,32) x min(H,32) (svt_handle_transform64x64 repack, transforms.c:2374)
                 const int Wp = W > 32 ? 32 : W, Hp = H > 32 ? 32 : H;
                 if (r < Hp && c < Wp) dst[r * Wp + c] = v;
@@ -450,8 +454,17 @@ extern "C" int svt_b200_txfm_trio_batch_dev(const int16_t* d_residual, const voi
 // ---- T1: svt_av1_fwd_txfm2d_WxH (aom_dsp_rtcd.h:121-197; C: transforms.c:2388-2631) ----------------
 extern "C" void svt_b200_fwd_txfm2d(int16_t* input, int32_t* output, uint32_t input_stride, int tx_type, int tx_size,
                                     uint8_t bit_depth) {
+    svt_b200_fwd_txfm2d_partial(input, output, input_stride, tx_type, tx_size, bit_depth, 0);
+}
+
+extern "C" void svt_b200_fwd_txfm2d_partial(int16_t* input, int32_t* output, uint32_t input_stride, int tx_type, int tx_size,
+                                            uint8_t bit_depth, int level) {
     (void)bit_depth;  // the forward arithmetic does not depend on it (stage ranges are assert-only)
     require_ready();
+    if (level < 0 || level > 2) {
+        fprintf(stderr, "[svt_b200] FATAL: partial-transform level %d\n", level);
+        abort();
+    }
     const int W = tx_w(tx_size), H = tx_h(tx_size);
     if (!host_txcfg(tx_size, tx_type).valid) {
         fprintf(stderr, "[svt_b200] FATAL: invalid (tx_size=%d, tx_type=%d)\n", tx_size, tx_type);
@@ -467,6 +480,7 @@ extern "C" void svt_b200_fwd_txfm2d(int16_t* input, int32_t* output, uint32_t in
     it->src_stride = W;
     it->tx_size = (uint8_t)tx_size;
     it->tx_type = (uint8_t)tx_type;
+    it->reserved = (uint16_t)(level << 1);
     l->h2d(0, in_end);
     launch_fwd_txfm(l->d<int16_t>(o_src), l->d<int32_t>(o_dst), l->d<SvtB200FwdTxfmItem>(o_it), 1, tx_class(tx_size), l->stream);
     l->d2h(o_dst, (size_t)W * H * 4);
@@ -573,6 +587,19 @@ extern "C" void svt_b200_inv_txfm_add_8bit(const int32_t* dqcoeff, uint8_t* dst_
 B200_FWD(4x4, 0) B200_FWD(8x8, 1) B200_FWD(16x16, 2) B200_FWD(32x32, 3) B200_FWD(64x64, 4) B200_FWD(4x8, 5) B200_FWD(8x4, 6)
 B200_FWD(8x16, 7) B200_FWD(16x8, 8) B200_FWD(16x32, 9) B200_FWD(32x16, 10) B200_FWD(32x64, 11) B200_FWD(64x32, 12)
 B200_FWD(4x16, 13) B200_FWD(16x4, 14) B200_FWD(8x32, 15) B200_FWD(32x8, 16) B200_FWD(16x64, 17) B200_FWD(64x16, 18)
+#define B200_FWD_PART(WxH, SZ)                                                                                  \
+    extern "C" void svt_b200_av1_fwd_txfm2d_##WxH##_N2(int16_t* input, int32_t* output, uint32_t input_stride,   \
+                                                       int transform_type, uint8_t bit_depth) {                  \
+        svt_b200_fwd_txfm2d_partial(input, output, input_stride, transform_type, SZ, bit_depth, 1);              \
+    }                                                                                                           \
+    extern "C" void svt_b200_av1_fwd_txfm2d_##WxH##_N4(int16_t* input, int32_t* output, uint32_t input_stride,   \
+                                                       int transform_type, uint8_t bit_depth) {                  \
+        svt_b200_fwd_txfm2d_partial(input, output, input_stride, transform_type, SZ, bit_depth, 2);              \
+    }
+B200_FWD_PART(4x4, 0) B200_FWD_PART(8x8, 1) B200_FWD_PART(16x16, 2) B200_FWD_PART(32x32, 3) B200_FWD_PART(64x64, 4) B200_FWD_PART(4x8, 5)
+B200_FWD_PART(8x4, 6) B200_FWD_PART(8x16, 7) B200_FWD_PART(16x8, 8) B200_FWD_PART(16x32, 9) B200_FWD_PART(32x16, 10) B200_FWD_PART(32x64, 11)
+B200_FWD_PART(64x32, 12) B200_FWD_PART(4x16, 13) B200_FWD_PART(16x4, 14) B200_FWD_PART(8x32, 15) B200_FWD_PART(32x8, 16) B200_FWD_PART(16x64, 17)
+B200_FWD_PART(64x16, 18)
 #define B200_INV_A(WxH, SZ)                                                                                     \
     extern "C" void svt_b200_av1_inv_txfm2d_add_##WxH(const int32_t* input, uint16_t* output_r, int32_t stride_r, \
                                                       uint16_t* output_w, int32_t stride_w, int tx_type, int32_t bd) { \

@@ -140,6 +140,8 @@ INV_ITEM_DTYPE = np.dtype([("coef_off", "<u8"), ("pred_off", "<u8"), ("recon_off
                            ("reserved", "u1"), ("reserved2", "<u4")])
 assert FWD_ITEM_DTYPE.itemsize == 24 and INV_ITEM_DTYPE.itemsize == 40
 
+lib.svt_b200_fwd_txfm2d_partial.argtypes = [vp, vp, ct.c_uint32, ct.c_int, ct.c_int, ct.c_uint8, ct.c_int]
+lib.svt_b200_fwd_txfm2d_partial.restype = None
 lib.svt_b200_txfm_valid.argtypes = [ct.c_int, ct.c_int]
 lib.svt_b200_txfm_valid.restype = ct.c_int
 lib.svt_b200_fwd_txfm2d.argtypes = [vp, vp, ct.c_uint32, ct.c_int, ct.c_int, ct.c_uint8]
@@ -172,6 +174,17 @@ def svt_av1_fwd_txfm2d(residual, stride, tx_type, tx_size, bit_depth=8, named=Fa
         f(_ptr(residual), _ptr(out), stride, tx_type, bit_depth)
     else:
         lib.svt_b200_fwd_txfm2d(_ptr(residual), _ptr(out), stride, tx_type, tx_size, bit_depth)
+    return out
+
+
+def svt_av1_fwd_txfm2d_partial(residual, stride, tx_type, tx_size, level, bit_depth=8, named=False):
+    """svt_av1_fwd_txfm2d_WxH_N2 (level 1) / _N4 (level 2); the output buffer is pre-filled with a sentinel
+    so that the test also sees that every element is written."""
+    out = np.full(TX_W[tx_size] * TX_H[tx_size], 0x5a5a5a5a, np.int32)
+    if named:
+        getattr(lib, "svt_b200_av1_fwd_txfm2d_%s_N%d" % (TX_NAME[tx_size], 2 * level))(_ptr(residual), _ptr(out), stride, tx_type, bit_depth)
+    else:
+        lib.svt_b200_fwd_txfm2d_partial(_ptr(residual), _ptr(out), stride, tx_type, tx_size, bit_depth, level)
     return out
 
 
@@ -447,6 +460,16 @@ lib.svt_b200_extend_planes_dev.argtypes = [ct.POINTER(PlaneExtent), ct.c_int, vp
 lib.svt_b200_extend_planes_dev.restype = ct.c_int
 
 
+SAD_SIZES = [(128, 128), (128, 64), (64, 128), (64, 64), (64, 32), (64, 16), (32, 64), (32, 32), (32, 16), (32, 8), (16, 64), (16, 32), (16, 16), (16, 8), (16, 4), (8, 32), (8, 16), (8, 8), (8, 4), (4, 16), (4, 8), (4, 4)]  # (width, height) of the svt_aom_sadMxN family
+for _m, _n in SAD_SIZES:
+    _f = getattr(lib, "svt_b200_aom_sad%dx%d" % (_m, _n))
+    _f.argtypes = [vp, ct.c_int, vp, ct.c_int]
+    _f.restype = ct.c_uint32
+    _f = getattr(lib, "svt_b200_aom_sad%dx%dx4d" % (_m, _n))
+    _f.argtypes = [vp, ct.c_int, ct.POINTER(ct.c_void_p), ct.c_int, vp]
+    _f.restype = None
+
+
 def unbound_symbols():
     """declared C-ABI symbols that have no ctypes signature yet (calling those would truncate pointers)"""
     from . import declared_symbols
@@ -454,9 +477,10 @@ def unbound_symbols():
             ("svt_b200_shutdown", "svt_b200_sm_count", "svt_b200_launch_count", "svt_b200_version")]
 
 for _i, _n in enumerate(TX_NAME):
-    _f = getattr(lib, "svt_b200_av1_fwd_txfm2d_" + _n)
-    _f.argtypes = [vp, vp, ct.c_uint32, ct.c_int, ct.c_uint8]
-    _f.restype = None
+    for _sfx in ("", "_N2", "_N4"):
+        _f = getattr(lib, "svt_b200_av1_fwd_txfm2d_" + _n + _sfx)
+        _f.argtypes = [vp, vp, ct.c_uint32, ct.c_int, ct.c_uint8]
+        _f.restype = None
     _g = getattr(lib, "svt_b200_av1_inv_txfm2d_add_" + _n)
     _base = [vp, vp, ct.c_int32, vp, ct.c_int32, ct.c_int]
     if _i in (0, 1, 2, 3, 4):

@@ -103,3 +103,32 @@ def test_sad_search_batch_picture(b200, oracle):
         want = sad_loop_call(lib, fn, cur, int(it["src_off"]), pitch, refp, int(it["ref_off"]), pitch, int(it["block_h"]),
                              int(it["block_w"]), pitch, 0, int(it["sa_w"]), int(it["sa_h"]))
         assert (int(rr["best_sad"]), int(rr["x"]), int(rr["y"])) == want
+
+
+def test_aom_sad_mxn_and_x4d(b200, oracle):
+    """svt_aom_sadMxN / svt_aom_sadMxNx4d (22 sizes): against the reference C functions when oracle/_ref is
+    there, else against the plain definition; strides larger than the block, unaligned reference origins."""
+    import ctypes as ct
+    r = rng(77)
+    for (m, n) in b200.SAD_SIZES:
+        ss, rs = m + 3, m + 13
+        src = r.integers(0, 256, n * ss + 8).astype(np.uint8)
+        refs = [r.integers(0, 256, n * rs + 16).astype(np.uint8) for _ in range(4)]
+        offs = [0, 1, 2, 5]
+
+        def plain(ref, off):
+            a = src[:n * ss].reshape(n, ss)[:, :m].astype(np.int64)
+            b = ref[off:off + n * rs].reshape(n, rs)[:, :m].astype(np.int64)
+            return int(np.abs(a - b).sum())
+        want = [plain(refs[i], offs[i]) for i in range(4)]
+        if oracle.ref is not None:
+            f = getattr(oracle.ref, "svt_aom_sad%dx%d_c" % (m, n))
+            f.restype = ct.c_uint32
+            for i in range(4):
+                assert f(ct.c_void_p(src.ctypes.data), ss, ct.c_void_p(refs[i].ctypes.data + offs[i]), rs) == want[i]
+        got1 = getattr(b200.lib, "svt_b200_aom_sad%dx%d" % (m, n))(src.ctypes.data, ss, refs[0].ctypes.data + offs[0], rs)
+        assert got1 == want[0], (m, n)
+        arr = (ct.c_void_p * 4)(*[refs[i].ctypes.data + offs[i] for i in range(4)])
+        out = np.zeros(4, np.uint32)
+        getattr(b200.lib, "svt_b200_aom_sad%dx%dx4d" % (m, n))(src.ctypes.data, ss, arr, rs, out.ctypes.data)
+        assert list(out) == want, (m, n)

@@ -5,8 +5,8 @@ import numpy as np
 import pytest
 
 from helpers import rng
-from txfm_helpers import (TX_H, TX_W, coeff_input, mask_written, port_fwd, port_inv, ref_fwd, ref_inv, residual_input,
-                          valid)
+from txfm_helpers import (TX_H, TX_W, coeff_input, mask_written, port_fwd, port_inv, ref_fwd, ref_fwd_partial, ref_inv,
+                          residual_input, valid)
 
 pytestmark = pytest.mark.gpu
 
@@ -42,6 +42,30 @@ def test_fwd_txfm_all_sizes_types(b200, oracle, kind):
                 want = chk(res, stride, ty, sz, bd)
                 got = b200.svt_av1_fwd_txfm2d(res, stride, ty, sz, bd, named=(bd == 10))
                 assert np.array_equal(got, want), (sz, ty, bd, kind)
+
+
+@pytest.mark.parametrize("level", [1, 2])
+def test_fwd_txfm_partial_n2_n4(b200, oracle, level):
+    """svt_av1_fwd_txfm2d_WxH_N2 / _N4: the top-left half / quarter of every dimension, zero elsewhere
+    (the reference's own N2/N4 C kernels when oracle/_ref is there, else the masked full transform)."""
+    chk = _fwd_checker(oracle)
+    r = rng(22 + level)
+    for sz in range(19):
+        w, h = TX_W[sz], TX_H[sz]
+        for ty in range(16):
+            if not valid(sz, ty):
+                continue
+            for kind in ("random", "max"):
+                res, stride = residual_input(r, sz, 8, kind)
+                if oracle.ref is not None:
+                    want = ref_fwd_partial(oracle.ref, res, stride, ty, sz, level)
+                else:
+                    want = chk(res, stride, ty, sz, 8).reshape(h, w).copy()
+                    want[max(h >> level, 1):, :] = 0
+                    want[:, max(w >> level, 1):] = 0
+                    want = want.reshape(-1)
+                got = b200.svt_av1_fwd_txfm2d_partial(res, stride, ty, sz, level, named=(kind == "max"))
+                assert np.array_equal(got, want), (sz, ty, level, kind)
 
 
 @pytest.mark.parametrize("kind", ["real", "sparse", "dc", "extreme", "zero"])

@@ -28,6 +28,17 @@ def ref_fwd(ref, residual, stride, ty, sz, bd=8):
     return out[:TX_W[sz] * TX_H[sz]]
 
 
+def ref_fwd_partial(ref, residual, stride, ty, sz, level, bd=8):
+    """the reference's N2 (level 1) / N4 (level 2) forward transform (transforms.c:5202-6990)"""
+    n = "N%d" % (2 * level)
+    name = ("svt_aom_transform_two_d_%dx%d_%s_c" if sz <= 4 else "svt_av1_fwd_txfm2d_%dx%d_%s_c") % (TX_W[sz], TX_H[sz], n)
+    f = getattr(ref, name)
+    f.restype = None
+    out = np.full(TX_W[sz] * TX_H[sz] + 64, 0x5a5a5a5a, np.int32)
+    f(ct.c_void_p(residual.ctypes.data), ct.c_void_p(out.ctypes.data), ct.c_uint32(stride), ct.c_int(ty), ct.c_uint8(bd))
+    return out[:TX_W[sz] * TX_H[sz]]
+
+
 def port_fwd(port, residual, stride, ty, sz):
     out = np.zeros(TX_W[sz] * TX_H[sz], np.int32)
     port.port_fwd_txfm2d.restype = None
