@@ -36,9 +36,10 @@ N_CALLS = 8       # len(FramePipeline.CALLS): the T2 entry points one frame goes
 # dram__bytes_read.sum + dram__bytes_write.sum of the call's dominant kernel, per launch, from the ncu --set full
 # capture of this same command (profiles/README.md says which file); None = not captured for that call
 NCU_DRAM_SOURCE = "profiles/r1_top_kernels_ncu_raw.csv (ncu --set full, one launch of the call's main kernel)"
-NCU_DRAM_BYTES = {"cdef_search": 4981760 + 0,          # cdef_search_kernel: read + write (the mse output stays in L2)
+NCU_DRAM_BYTES = {"cdef_search": 4995584 + 0,          # cdef_search_kernel: read + write (the mse output stays in L2)
                   "wiener_stats": 6377728 + 0,         # stats_mma_kernel
-                  "me_search": 7325952 + 108288 + 6755072}  # hme_fused_kernel (r + w) + fullpel_search_kernel
+                  "txfm_trio": 999680 + 2682880 + 4361216 + 4520704 + 4305152 + 220000,  # the five class kernels (r + w)
+                  "me_search": 7329024 + 12288 + 6755072}  # hme_fused_kernel (r + w) + fullpel_search_kernel  # hme_fused_kernel (r + w) + fullpel_search_kernel
 
 
 # ------------------------------------------------------------------------------------------------------
