@@ -317,25 +317,6 @@ def main():
         torch.cuda.synchronize()
 
     graphs = [None] * N_FRAME_SETS
-    s_comm = torch.cuda.Stream() if world > 1 else None
-    comm_done = [None] * N_FRAME_SETS  # event of the last exchange that read frame set k's filtered frame
-
-    def exchange(i, cs):
-        """reconstructed-reference exchange (the path's one real collective): all_gather of the filtered frame
-        on a communication stream of its own, so that the compute streams never wait for the other ranks"""
-        k = i % N_FRAME_SETS
-        ready = torch.cuda.Event()
-        ready.record(cs)
-        s_comm.wait_event(ready)
-        with torch.cuda.stream(s_comm):
-            dist.all_gather_into_tensor(gathered[k].view(-1), sets[k].final)
-            comm_done[k] = torch.cuda.Event()
-            comm_done[k].record(s_comm)
-
-    def wait_exchange_of_set(i, cs):
-        k = i % N_FRAME_SETS
-        if comm_done[k] is not None:  # the frame set's previous result is still being sent
-            cs.wait_event(comm_done[k])
 
     def enqueue_step(i, events=None):
         """one frame of hot-path work on the current stream: replay of the frame set's CUDA graph (the ~35
@@ -365,14 +346,12 @@ def main():
                 fp = sets[i % N_FRAME_SETS]
                 if e2e:
                     fp.load_inputs()
-                if world > 1:
-                    wait_exchange_of_set(i, st)
                 enqueue_step(i, ev[i] if ev else None)
-                if world > 1:
-                    exchange(i, st)
+                if world > 1:  # reconstructed-reference exchange (the path's one real collective)
+                    dist.all_gather_into_tensor(gathered[i % N_FRAME_SETS].view(-1), fp.final)
                 if e2e:
                     fp.read_outputs()
-        for x in streams[1:] + ([s_comm] if world > 1 else []):
+        for x in streams[1:]:
             tail.record(x)
             stream.wait_event(tail)
         end.record(stream)
@@ -405,21 +384,15 @@ def main():
             cs = streams[i % n_streams]
             with torch.cuda.stream(cs):
                 cs.wait_event(ev_in[i])
-                if world > 1:
-                    wait_exchange_of_set(i, cs)
                 enqueue_step(i)
                 if world > 1:
-                    exchange(i, cs)
+                    dist.all_gather_into_tensor(gathered[i % N_FRAME_SETS].view(-1), fp.final)
                 ev_done[i].record(cs)
             with torch.cuda.stream(s_out):
                 s_out.wait_event(ev_done[i])
                 fp.read_outputs()
                 ev_out[i].record(s_out)
         stream.wait_event(ev_out[n - 1])
-        if world > 1:
-            tail = torch.cuda.Event()
-            tail.record(s_comm)
-            stream.wait_event(tail)
         end.record(stream)
         torch.cuda.synchronize()
         return start.elapsed_time(end)
