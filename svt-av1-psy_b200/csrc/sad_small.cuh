@@ -43,12 +43,97 @@ __device__ __forceinline__ SvtB200SadSearchResult sad_key_to_result(unsigned lon
     return r;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Blocks whose width is a multiple of 16 (the HME / ME blocks: 16, 32, 64 wide): a lane owns a
+// (block row, 16-pixel chunk) UNIT, keeps its 4 source words in registers and, per tile of 8 horizontally
+// adjacent search positions, fetches the 7 aligned reference words that cover the 23 bytes those
+// positions touch, normalises them once to the row's byte alignment and evaluates the 8 positions with
+// compile-time funnel shifts: 4 x (SHF + VABSDIFF4) per position, no loads inside.  Units of one search
+// spread over the lanes (several per lane when the block has more than 32); when the block has fewer
+// than 32 units the lanes split into groups that take different position tiles.  Partial sums are added
+// across the lanes of a group with shuffles.
+// ---------------------------------------------------------------------------------------------------
+template <int NB>  // NB = bytes that are certainly needed (their words are read without an index clamp)
+__device__ __forceinline__ void sad_load_run(const uint8_t* p, int nbytes, uint32_t (&out)[6]) {
+    // out[j] = bytes [4j, 4j+4) counted from p, for the first 24 bytes; only aligned words holding one of
+    // the first `nbytes` bytes are read (others repeat the last valid word: their bytes are never used)
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    const uint32_t* w0 = reinterpret_cast<const uint32_t*>(a & ~uintptr_t(3));
+    const int       shift = (int)(a & 3) * 8, last = (int)(((a & 3) + nbytes - 1) >> 2);
+    uint32_t w[7];
+#pragma unroll
+    for (int j = 0; j < 7; j++) w[j] = __ldg(w0 + (j <= (NB - 1) / 4 ? j : min(j, last)));
+#pragma unroll
+    for (int j = 0; j < 6; j++) out[j] = __funnelshift_r(w[j], w[j + 1], shift);
+}
+
+__device__ __forceinline__ unsigned long long sad_search_warp_w16(const uint8_t* __restrict__ src0, const uint8_t* __restrict__ ref0,
+                                                                  const SvtB200SadSearchItem& item, int lane) {
+    const int bw = item.block_w, bh = item.block_h, sa_w = item.sa_w, sa_h = item.sa_h;
+    const bool skip = (bw == 16 && bh <= 16 && item.skip_search_line);
+    const int  lgc = bw == 64 ? 2 : (bw == 32 ? 1 : 0), chunks = 1 << lgc, units = bh << lgc;
+    // lanes per group: the smallest power of two >= min(units, 32) (>= chunks, so a lane keeps its chunk)
+    int gl = 1;
+    while (gl < 32 && gl < units) gl <<= 1;
+    const int groups = 32 / gl, grp = lane / gl, ul = lane - grp * gl;
+    const int xtiles = (sa_w + 7) >> 3, tiles = xtiles * sa_h;
+    const int c = ul & (chunks - 1), r_first = ul >> lgc, r_step = gl >> lgc;
+    const uint8_t* src_u = src0 + (size_t)r_first * item.src_stride + 16 * c;  // this lane's first unit
+    const uint8_t* ref_u = ref0 + (size_t)r_first * item.ref_stride + 16 * c;
+    const size_t   src_adv = (size_t)r_step * item.src_stride, ref_adv = (size_t)r_step * item.ref_stride;
+    unsigned long long best = ~0ull;
+    int y = 0, xt = grp;  // this group's tile, advanced by `groups` tiles per round
+    while (xt >= xtiles) { xt -= xtiles; y++; }
+    for (int t0 = 0; t0 < tiles; t0 += groups) {
+        const bool tile_on = y < sa_h;
+        const int  yy = tile_on ? y : sa_h - 1, x0 = (tile_on ? xt : 0) * 8;  // idle groups shadow a valid tile and drop the result
+        const int  npos = min(8, sa_w - x0);
+        const bool line_on = !(skip && ((yy & 1) == 0));
+        uint32_t   acc[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) acc[i] = 0;
+        if (line_on) {
+            const uint8_t* ps = src_u;
+            const uint8_t* pr = ref_u + (size_t)yy * item.ref_step + x0;
+            for (int r = r_first; r < bh; r += r_step, ps += src_adv, pr += ref_adv) {
+                uint32_t sw[6], rw[6];
+                sad_load_run<16>(ps, 16, sw);
+                sad_load_run<16>(pr, 16 + npos - 1, rw);
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    const int ws = i >> 2, sh = (i & 3) * 8;
+#pragma unroll
+                    for (int k = 0; k < 4; k++)
+                        acc[i] = __vsadu4(sw[k], sh ? __funnelshift_r(rw[k + ws], rw[k + ws + 1], sh) : rw[k + ws]) + acc[i];
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            uint32_t a = acc[i];
+            for (int o = gl >> 1; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+            if (tile_on && i < npos && line_on && a < 0xffffffu) {
+                const unsigned long long key = ((unsigned long long)a << 32) | ((unsigned long long)(uint32_t)yy << 16) | (unsigned long long)(uint32_t)(x0 + i);
+                best = key < best ? key : best;
+            }
+        }
+        xt += groups;
+        while (xt >= xtiles) { xt -= xtiles; y++; }
+    }
+    for (int o = 16; o >= gl && o > 0; o >>= 1) {  // the groups looked at different tiles
+        const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+        best = other < best ? other : best;
+    }
+    return best;
+}
+
 // all 32 lanes call; every lane returns the winning key (~0ull when no position qualifies)
 __device__ __forceinline__ unsigned long long sad_search_warp(const uint8_t* __restrict__ src0, const uint8_t* __restrict__ ref0,
                                                               const SvtB200SadSearchItem& item, int lane) {
     const int bw = item.block_w, bh = item.block_h, sa_w = item.sa_w, sa_h = item.sa_h;
     unsigned long long best = ~0ull;
     if (sa_w <= 0 || sa_h <= 0 || bw <= 0 || bh <= 0) return best;
+    if (bw == 16 || bw == 32 || bw == 64) return sad_search_warp_w16(src0, ref0, item, lane);
     const bool     skip = (bw == 16 && bh <= 16 && item.skip_search_line);
     const int      xs = lane & 7, slice = lane >> 3;
     const int      nw = (bw + 3) >> 2, tail = bw & 3;
