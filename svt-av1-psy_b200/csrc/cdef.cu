@@ -7,13 +7,17 @@
 // svt_search_one_dual_c (:627-690), the tile build of cdef_seg_search (Source/Lib/Codec/cdef_process.c:
 // 106-352: CDEF_VERY_LARGE outside the frame, pre-filter neighbours inside).
 //
-// B200 mapping (T2): one CTA per 64x64 filter block.  The CTA stages the padded 16-bit tile of each
-// plane in shared memory once, finds the 64 luma directions (one thread per 8x8), then for every
-// candidate strength filters all non-skip blocks straight from the tile -- one thread per block row --
-// and reduces the distortion against the source picture with 8-lane shuffles; the filtered pixels of
-// the search never leave registers.  The luma distortion's double-precision formula is evaluated
-// with round-to-nearest intrinsics in the reference's operand order (FMA contraction is disabled
-// for the whole library), which makes it IEEE-identical to the C code.
+// B200 mapping (T2): a frame-wide kernel finds direction and variance of every non-skip 8x8 (one
+// thread per block, the 64 pixels in registers).  Search and apply run one CTA per (64x64 filter block,
+// plane): the padded 16-bit tile of the plane is staged in shared memory once and every filtered pixel
+// is one thread.  A pixel's 12 taps are fetched once per direction, as signed differences and magnitudes
+// packed two per register, and shared by all candidate strengths; the filter sum is separable into a
+// primary and a secondary half, each evaluated once per distinct strength value with native packed
+// 16-bit min/max/add and 2-way dot-product instructions.  Distortion moments are reduced with shuffles
+// into per-block 32-bit accumulators in shared memory; the filtered pixels of the search never leave
+// registers.  The luma distortion's double-precision formula is evaluated with round-to-nearest
+// intrinsics in the reference's operand order (FMA contraction is disabled for the whole library),
+// which makes it IEEE-identical to the C code.
 #include <mutex>
 
 #include "common.cuh"
@@ -27,13 +31,6 @@ constexpr int kTileRows  = 64 + 6;
 constexpr int kGChunk    = 8;       // candidate strengths evaluated between two CTA barriers of the search
 
 __device__ __forceinline__ int msb32(uint32_t n) { return 31 - __clz(n); }
-__device__ __forceinline__ int cdef_constrain(int diff, int threshold, int damping) {
-    if (!threshold) return 0;
-    const int shift = max(0, damping - msb32((uint32_t)threshold));
-    const int ad    = abs(diff);
-    const int v     = min(ad, max(0, threshold - (ad >> shift)));
-    return diff < 0 ? -v : v;
-}
 __device__ __forceinline__ int cdef_adjust_strength(int strength, int var) {
     const int i = (var >> 6) ? min(msb32((uint32_t)(var >> 6)), 12) : 0;
     return var ? (strength * (4 + i) + 8) >> 4 : 0;

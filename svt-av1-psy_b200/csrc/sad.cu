@@ -5,8 +5,9 @@
 //     for x in [0,sa_w):  sad(x,y) = sum |src[r*src_stride+c] - ref[y*ref_step + x + r*ref_stride + c]|
 //     strict '<' update  => the FIRST minimum in raster order wins.
 //
-// B200 design.  One CTA per work item (grid-stride over the list, so one launch serves a whole
-// picture's searches).  The block and a tile of the search window are staged in shared memory as
+// B200 design.  Searches of at most 256 positions (every HME / ME refinement of the presets in scope) take
+// the warp-per-search path of sad_small.cuh; larger areas the tiled kernel below: one CTA per work item
+// (grid-stride over the list, so one launch serves a whole picture's searches).  The block and a tile of the search window are staged in shared memory as
 // 32-bit words; a thread owns M search positions x, x+4, ... x+4(M-1) of one search row so that the
 // window words it assembles with a funnel shift are re-used M times against each source word
 // (the same sliding trick mpsadbw gives AVX2, but on VABSDIFF4.U8.ACC).  Block rows are split
