@@ -35,6 +35,13 @@ void txfm_tables_init() {
     B200_CUDA_CHECK(cudaMemcpyToSymbol(c_sinpi, sinv, sizeof(sinv)));
 }
 
+// ints between the shared-memory areas (two planes) of consecutive teams.  Teams that share a warp must not
+// land on the same banks: a team of T lanes covers T banks with its odd pitch, so the stride is made
+// congruent to T modulo 32.
+__host__ __device__ constexpr int team_stride(int team) {
+    return team == 4 ? 68 : (team == 8 ? 152 : (team == 16 ? 560 : 2 * team * (team + 1)));
+}
+
 __host__ __device__ inline int rect_log_ratio(int w, int h) {  // get_rect_tx_log_ratio
     if (w == h) return 0;
     if (w > h) return w == 2 * h ? 1 : (w == 4 * h ? 2 : 3);
@@ -52,7 +59,7 @@ fwd_txfm_kernel(const int16_t* __restrict__ src_base, int32_t* __restrict__ dst_
     // a 64-point block is alone in its CTA: all THREADS move data, the first 64 run the passes
     constexpr int TEAMS = TEAM >= 64 ? 1 : THREADS / TEAM, PLANE = TEAM * (TEAM + 1), MOVERS = TEAM >= 64 ? THREADS : TEAM;
     const int     team  = TEAM >= 64 ? 0 : threadIdx.x / TEAM, tid = TEAM >= 64 ? threadIdx.x : threadIdx.x % TEAM;
-    int32_t*      A     = tsm + (size_t)team * 2 * PLANE;
+    int32_t*      A     = tsm + (size_t)team * team_stride(TEAM);
     int32_t*      B     = A + PLANE;
 
     for (int it = blockIdx.x * TEAMS + team; it < n_items; it += gridDim.x * TEAMS) {
@@ -111,7 +118,7 @@ inv_txfm_kernel(const int32_t* __restrict__ coef_base, const PIX* __restrict__ p
     // a 64-point block is alone in its CTA: all THREADS move data, the first 64 run the passes
     constexpr int TEAMS = TEAM >= 64 ? 1 : THREADS / TEAM, PLANE = TEAM * (TEAM + 1), MOVERS = TEAM >= 64 ? THREADS : TEAM;
     const int     team  = TEAM >= 64 ? 0 : threadIdx.x / TEAM, tid = TEAM >= 64 ? threadIdx.x : threadIdx.x % TEAM;
-    int32_t*      A     = tsm + (size_t)team * 2 * PLANE;
+    int32_t*      A     = tsm + (size_t)team * team_stride(TEAM);
     int32_t*      B     = A + PLANE;
 
     for (int it = blockIdx.x * TEAMS + team; it < n_items; it += gridDim.x * TEAMS) {
@@ -179,7 +186,7 @@ trio_txfm_kernel(const int16_t* __restrict__ src_base, const PIX* __restrict__ p
     constexpr bool SOLO = TEAM >= 32;
     constexpr int  TEAMS = SOLO ? 1 : THREADS / TEAM, PLANE = TEAM * (TEAM + 1), MOVERS = SOLO ? THREADS : TEAM;
     const int      team  = SOLO ? 0 : threadIdx.x / TEAM, tid = SOLO ? threadIdx.x : threadIdx.x % TEAM;
-    int32_t*      A     = tsm + (size_t)team * 2 * PLANE;
+    int32_t*      A     = tsm + (size_t)team * team_stride(TEAM);
     int32_t*      B     = A + PLANE;
     __shared__ int s_eob;
 
@@ -306,7 +313,7 @@ template <int TEAM> constexpr int class_threads() { return TEAM == 16 ? 128 : (T
 template <int TEAM>
 static void launch_fwd_class(const int16_t* d_src, int32_t* d_dst, const SvtB200FwdTxfmItem* d_items, int n, cudaStream_t st) {
     constexpr int    THREADS = class_threads<TEAM>(), TEAMS = TEAM >= 64 ? 1 : THREADS / TEAM;
-    constexpr size_t smem = (size_t)TEAMS * 2 * TEAM * (TEAM + 1) * 4;
+    constexpr size_t smem = (size_t)TEAMS * team_stride(TEAM) * 4;
     static bool attr = false;
     if (!attr) { set_smem_attr(fwd_txfm_kernel<TEAM, THREADS>, smem); attr = true; }
     const int per_sm = (int)((200 * 1024) / (smem + 1024)) < 2048 / THREADS ? (int)((200 * 1024) / (smem + 1024)) : 2048 / THREADS;
@@ -328,7 +335,7 @@ template <int TEAM, typename PIX>
 static void launch_inv_class(const int32_t* d_coef, const PIX* d_pred, PIX* d_recon, const SvtB200InvTxfmItem* d_items, int n,
                              cudaStream_t st) {
     constexpr int    THREADS = class_threads<TEAM>(), TEAMS = TEAM >= 64 ? 1 : THREADS / TEAM;
-    constexpr size_t smem = (size_t)TEAMS * 2 * TEAM * (TEAM + 1) * 4;
+    constexpr size_t smem = (size_t)TEAMS * team_stride(TEAM) * 4;
     static bool attr = false;
     if (!attr) { set_smem_attr(inv_txfm_kernel<TEAM, THREADS, PIX>, smem); attr = true; }
     const int per_sm = (int)((200 * 1024) / (smem + 1024)) < 2048 / THREADS ? (int)((200 * 1024) / (smem + 1024)) : 2048 / THREADS;
@@ -353,7 +360,7 @@ static void launch_trio_class(const int16_t* d_src, const PIX* d_pred, PIX* d_re
                               const uint8_t* d_qm, const SvtB200TrioItem* d_items, int n, uint16_t* d_eobs, cudaStream_t st) {
     if (n <= 0) return;
     constexpr int    THREADS = TEAM == 32 ? 128 : class_threads<TEAM>(), TEAMS = TEAM >= 32 ? 1 : THREADS / TEAM;
-    constexpr size_t smem = (size_t)TEAMS * 2 * TEAM * (TEAM + 1) * 4;
+    constexpr size_t smem = (size_t)TEAMS * team_stride(TEAM) * 4;
     static bool attr = false;
     if (!attr) { set_smem_attr(trio_txfm_kernel<TEAM, THREADS, PIX>, smem); attr = true; }
     const int per_sm = (int)((200 * 1024) / (smem + 1024)) < 2048 / THREADS ? (int)((200 * 1024) / (smem + 1024)) : 2048 / THREADS;
