@@ -329,6 +329,11 @@ def main():
 
     def capture_graphs():
         for k, fp in enumerate(sets):
+            # one eager step on the stream the graph will be captured on: every lazily allocated library
+            # workspace (they are per stream) exists before the capture, which must not allocate
+            with torch.cuda.stream(streams[k % n_streams]):
+                fp.step()
+            torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g, stream=streams[k % n_streams]):
                 fp.step()

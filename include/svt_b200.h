@@ -211,6 +211,15 @@ typedef struct SvtB200InvTxfmItem {
     uint32_t reserved2;
 } SvtB200InvTxfmItem;
 
+/* T1: svt_handle_transform{16x64,32x64,64x16,64x32,64x64}{,_N2_N4} (aom_dsp_rtcd.h:216-240; C: transforms.c:2374-2543):
+ * returns the energy of the coefficients outside the kept top-left min(W,32) x min(H,32) and re-packs the
+ * kept rows of a 64-wide block to stride 32, in place. */
+#define SVT_B200_DECL_HANDLE(WxH)                                         \
+    SVT_B200_API uint64_t svt_b200_handle_transform##WxH(int32_t* output); \
+    SVT_B200_API uint64_t svt_b200_handle_transform##WxH##_N2_N4(int32_t* output);
+SVT_B200_DECL_HANDLE(16x64) SVT_B200_DECL_HANDLE(32x64) SVT_B200_DECL_HANDLE(64x16) SVT_B200_DECL_HANDLE(64x32) SVT_B200_DECL_HANDLE(64x64)
+#undef SVT_B200_DECL_HANDLE
+
 /* A transform block is processed by a team of max(W,H) threads; its "team class" is
  * log2(max(W,H)) - 2 (0: 4x4 .. 4: the 64-point sizes).  Items must be ordered by class: the
  * n_per_class[0] class-0 items first, then class 1, ...; within a class, keeping equal (tx_size,

@@ -585,6 +585,56 @@ extern "C" void svt_b200_inv_txfm_add_8bit(const int32_t* dqcoeff, uint8_t* dst_
     for (int r = 0; r < H; r++) memcpy(dst_w + (size_t)r * stride_w, l->h<uint8_t>(o_out) + r * W, W);
 }
 
+// ---- T1: svt_handle_transform{16x64,32x64,64x16,64x32,64x64}{,_N2_N4} (aom_dsp_rtcd.h:216-240; C: transforms.c:2374-2543)
+// Energy of the coefficients a 64-point transform drops (everything outside the top-left
+// min(W,32) x min(H,32)), then, for 64-wide blocks, the in-place re-pack of the kept rows to stride 32
+// (rows 1..Hp-1 move to offset 32*row; nothing else of the buffer is touched, exactly like the memcpy loop
+// of the reference).  The N2_N4 variants only re-pack and return 0.
+namespace b200 {
+__global__ void __launch_bounds__(256)
+handle_transform_kernel(int32_t* __restrict__ buf, int W, int H, int with_energy, unsigned long long* __restrict__ energy) {
+    __shared__ int32_t            keep[32 * 32];
+    __shared__ unsigned long long tot;
+    const int Wp = W > 32 ? 32 : W, Hp = H > 32 ? 32 : H;
+    if (threadIdx.x == 0) tot = 0;
+    __syncthreads();
+    unsigned long long e = 0;
+    for (int i = threadIdx.x; i < W * H; i += blockDim.x) {
+        const int r = i / W, c = i - r * W;
+        const int32_t v = buf[i];
+        if (r < Hp && c < Wp) keep[r * 32 + c] = v;
+        else if (with_energy) e += (unsigned long long)((long long)v * (long long)v);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
+    if ((threadIdx.x & 31) == 0 && e) atomicAdd(&tot, e);
+    __syncthreads();
+    if (W == 64)
+        for (int i = threadIdx.x; i < (Hp - 1) * 32; i += blockDim.x) buf[32 + i] = keep[32 + i];  // rows 1..Hp-1
+    if (threadIdx.x == 0) *energy = tot;
+}
+}  // namespace b200
+
+static uint64_t handle_transform_t1(int32_t* output, int W, int H, int with_energy) {
+    require_ready();
+    LaneGuard l;
+    const size_t n = (size_t)W * H;
+    size_t o_buf = l->alloc(n * 4), o_e = l->alloc(16);
+    memcpy(l->h<int32_t>(o_buf), output, n * 4);
+    l->h2d(o_buf, n * 4);
+    handle_transform_kernel<<<1, 256, 0, l->stream>>>(l->d<int32_t>(o_buf), W, H, with_energy, l->d<unsigned long long>(o_e));
+    B200_LAUNCH_CHECK();
+    l->d2h(o_buf, (o_e + 16) - o_buf);
+    l->sync();
+    memcpy(output, l->h<int32_t>(o_buf), n * 4);
+    return (uint64_t)*l->h<unsigned long long>(o_e);
+}
+#define B200_HANDLE(WxH, W, H)                                                                                    \
+    extern "C" uint64_t svt_b200_handle_transform##WxH(int32_t* output) { return handle_transform_t1(output, W, H, 1); } \
+    extern "C" uint64_t svt_b200_handle_transform##WxH##_N2_N4(int32_t* output) { return W == 64 ? handle_transform_t1(output, W, H, 0) : 0; }
+B200_HANDLE(16x64, 16, 64) B200_HANDLE(32x64, 32, 64) B200_HANDLE(64x16, 64, 16) B200_HANDLE(64x32, 64, 32) B200_HANDLE(64x64, 64, 64)
+#undef B200_HANDLE
+
 // ---- named T1 wrappers: one symbol per reference function pointer --------------------------------
 #define B200_FWD(WxH, SZ)                                                                                       \
     extern "C" void svt_b200_av1_fwd_txfm2d_##WxH(int16_t* input, int32_t* output, uint32_t input_stride,        \

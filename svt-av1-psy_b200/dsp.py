@@ -470,6 +470,12 @@ for _m, _n in SAD_SIZES:
     _f.restype = None
 
 
+for _n in ("16x64", "32x64", "64x16", "64x32", "64x64"):
+    for _sfx in ("", "_N2_N4"):
+        _f = getattr(lib, "svt_b200_handle_transform" + _n + _sfx)
+        _f.argtypes = [vp]
+        _f.restype = ct.c_uint64
+
 def unbound_symbols():
     """declared C-ABI symbols that have no ctypes signature yet (calling those would truncate pointers)"""
     from . import declared_symbols

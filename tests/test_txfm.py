@@ -123,3 +123,28 @@ def test_fwd_txfm_batch_mixed_sizes(b200, oracle):
         n = TX_W[sz] * TX_H[sz]
         want = chk(plane[int(it["src_off"]):], W, ty, sz, 8)
         assert np.array_equal(coeff[int(it["dst_off"]):int(it["dst_off"]) + n], want), (sz, ty)
+
+
+def test_handle_transform_energy_and_repack(b200, oracle):
+    """svt_handle_transformWxH / _N2_N4: energy of the dropped coefficients + in-place re-pack, whole buffer compared."""
+    import ctypes as ct
+    r = rng(31)
+    for name, (w, h) in {"16x64": (16, 64), "32x64": (32, 64), "64x16": (64, 16), "64x32": (64, 32), "64x64": (64, 64)}.items():
+        for sfx in ("", "_N2_N4"):
+            x = r.integers(-(1 << 20), 1 << 20, w * h).astype(np.int32)
+            want = x.copy()
+            if oracle.ref is not None:
+                f = getattr(oracle.ref, "svt_handle_transform%s%s_c" % (name, sfx))
+                f.restype = ct.c_uint64
+                e_want = f(ct.c_void_p(want.ctypes.data))
+            else:
+                a = want.reshape(h, w).astype(np.int64)
+                wp, hp = min(w, 32), min(h, 32)
+                e_want = 0 if sfx else int((a * a).sum() - (a[:hp, :wp] ** 2).sum())
+                if w == 64:
+                    keep = a[:hp, :32].astype(np.int32).copy()
+                    want[32:hp * 32] = keep.reshape(-1)[32:]
+            got = x.copy()
+            e_got = getattr(b200.lib, "svt_b200_handle_transform%s%s" % (name, sfx))(got.ctypes.data)
+            assert e_got == e_want, (name, sfx)
+            assert np.array_equal(got, want), (name, sfx)
