@@ -85,3 +85,34 @@ def test_two_frames_in_flight_on_two_streams(b200, refc):
         for fp, w in zip(fps, want):
             for n, t in zip(names, w):
                 assert torch.equal(getattr(fp, n), t), (rep, n)
+
+
+@pytest.mark.parametrize("size", [(384, 256), (640, 360)])
+def test_frame_matches_committed_golden_fixture(b200, size):
+    """tests/golden/frame_WxH.json holds the SHA-256 of every output of the frame as computed by the reference's
+    own C kernels (tools/make_golden.py, run where /root/reference exists).  Needs no oracle at run time."""
+    import hashlib
+    import json
+    import os
+    import numpy as np
+    import torch
+    from svt_av1_psy_b200.pipeline import FramePipeline
+    from svt_av1_psy_b200.workload import FrameWorkload
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "frame_%dx%d.json" % size)))
+    fp = FramePipeline(FrameWorkload(size[0], size[1], seed=g["seed"]), torch)
+    fp.load_inputs()
+    fp.step()
+    torch.cuda.synchronize()
+
+    def digest(t):
+        return hashlib.sha256(np.ascontiguousarray(t.cpu().numpy()).view(np.uint8).tobytes()).hexdigest()
+    got = {"me_sad": fp.me_sad, "me_mv": fp.me_mv, "hme_centre": fp.me_centre, "qcoeff": fp.qcoeff, "dqcoeff": fp.dqcoeff, "eob": fp.eobs,
+           "recon": fp.recon, "cdef_mse": fp.cdef_mse, "cdef_dir": fp.cdef_dir, "cdef_out": fp.cdef_out, "wiener_M": fp.M,
+           "wiener_H": fp.Hm, "final": fp.final}
+    bad = [k for k, t in got.items() if digest(t) != g["sha256"][k]]
+    assert not bad, bad
+    # the forward coefficients only exist on the 3-call transform chain
+    s = torch.cuda.current_stream().cuda_stream
+    fp.call_fwd_txfm(s)
+    torch.cuda.synchronize()
+    assert digest(fp.coeff) == g["sha256"]["coeff"]

@@ -251,3 +251,17 @@ def test_ref_driver_me_matches_numpy_driver_and_avx2_tier(oracle, refc):
         for x, y in zip(b, c):
             assert np.array_equal(x, y)
     refc.ref_set_tier(0)
+
+
+def test_committed_golden_fixtures_are_what_the_reference_computes(oracle, refc):
+    """tests/golden/*.json (used by the GPU tests where oracle/_ref may be absent) against the reference run here"""
+    import json
+    import os
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "tools"))
+    import make_golden
+    for name in sorted(os.listdir(os.path.join(root, "tests", "golden"))):
+        g = json.load(open(os.path.join(root, "tests", "golden", name)))
+        now = make_golden.golden_for(g["width"], g["height"], g["seed"])
+        assert now["sha256"] == g["sha256"], name
