@@ -311,7 +311,7 @@ def main():
     # consecutive frames alternate between two compute streams: independent pictures in flight at once, as in
     # the encoder's picture-parallel pipeline; frame set k always runs on stream k % 2
     n_streams = 1 if args.one_stream else args.streams
-    assert n_streams in (1, 2, 4), "--streams must divide the %d frame sets" % N_FRAME_SETS
+    assert n_streams in (1, 2, 4, 8), "--streams must divide the %d frame sets" % N_FRAME_SETS
     streams = [stream] + [torch.cuda.Stream() for _ in range(n_streams - 1)]
     gathered = [torch.empty((world,) + tuple(sets[0].final.shape), dtype=torch.uint8, device="cuda") for _ in range(N_FRAME_SETS)] if world > 1 else None
 
