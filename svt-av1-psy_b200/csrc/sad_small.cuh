@@ -76,6 +76,7 @@ __device__ __forceinline__ unsigned long long sad_search_warp_w16(const uint8_t*
     int gl = 1;
     while (gl < 32 && gl < units) gl <<= 1;
     const int groups = 32 / gl, grp = lane / gl, ul = lane - grp * gl;
+    const unsigned grpmask = (gl == 32 ? 0xffffffffu : ((1u << gl) - 1u)) << (grp * gl);
     const int xtiles = (sa_w + 7) >> 3, tiles = xtiles * sa_h;
     const int c = ul & (chunks - 1), r_first = ul >> lgc, r_step = gl >> lgc;
     const uint8_t* src_u = src0 + (size_t)r_first * item.src_stride + 16 * c;  // this lane's first unit
@@ -110,8 +111,7 @@ __device__ __forceinline__ unsigned long long sad_search_warp_w16(const uint8_t*
         }
 #pragma unroll
         for (int i = 0; i < 8; i++) {
-            uint32_t a = acc[i];
-            for (int o = gl >> 1; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+            const uint32_t a = __reduce_add_sync(grpmask, acc[i]);  // REDUX over the lanes of the group
             if (tile_on && i < npos && line_on && a < 0xffffffu) {
                 const unsigned long long key = ((unsigned long long)a << 32) | ((unsigned long long)(uint32_t)yy << 16) | (unsigned long long)(uint32_t)(x0 + i);
                 best = key < best ? key : best;
