@@ -518,3 +518,29 @@ void ref_wiener_units_8bit(const uint8_t* src, uint8_t* dst, const RefWienerUnit
     g_wu.src = src; g_wu.dst = dst; g_wu.units = units;
     par_for(n, 16, wiener_body);
 }
+
+/* ---- a13 groundwork: one restoration unit through the reference's own stripe loop ------------------------
+ * svt_av1_loop_restoration_filter_unit (restoration.c:1067-1135) with need_boundaries = 1, RESTORE_WIENER, 8 bit.
+ * `data` / `dst` point at pixel (0,0) of the plane; limits = {h_start, h_end, v_start, v_end}; tile = {left, top,
+ * right, bottom}; above/below = the saved stripe-boundary lines (RESTORATION_CTX_VERT rows per stripe, `bstride`
+ * bytes per row, logical column x at byte x + RESTORATION_EXTRA_HORZ is handled by the caller's pointer). */
+void ref_lr_filter_unit_wiener_8bit(uint8_t* data, int stride, uint8_t* dst, int dst_stride, const int32_t* limits,
+                                    const int16_t* hfilter, const int16_t* vfilter, uint8_t* above, uint8_t* below, int bstride,
+                                    const int32_t* tile, int tile_stripe0, int ss_x, int ss_y, int optimized_lr) {
+    RestorationTileLimits lim = {limits[0], limits[1], limits[2], limits[3]};
+    RestorationUnitInfo   rui;
+    memset(&rui, 0, sizeof(rui));
+    rui.restoration_type = RESTORE_WIENER;
+    memcpy(rui.wiener_info.hfilter, hfilter, 8 * sizeof(int16_t));
+    memcpy(rui.wiener_info.vfilter, vfilter, 8 * sizeof(int16_t));
+    RestorationStripeBoundaries rsb;
+    rsb.stripe_boundary_above  = above;
+    rsb.stripe_boundary_below  = below;
+    rsb.stripe_boundary_stride = bstride;
+    rsb.stripe_boundary_size   = 0;
+    RestorationLineBuffers* rlbs = (RestorationLineBuffers*)malloc(sizeof(RestorationLineBuffers));
+    Av1PixelRect            tr   = {tile[0], tile[1], tile[2], tile[3]};
+    svt_av1_loop_restoration_filter_unit(1, &lim, &rui, &rsb, rlbs, &tr, tile_stripe0, ss_x, ss_y, 0, 8, data, stride, dst,
+                                         dst_stride, NULL, optimized_lr);
+    free(rlbs);
+}

@@ -265,3 +265,39 @@ def test_committed_golden_fixtures_are_what_the_reference_computes(oracle, refc)
         g = json.load(open(os.path.join(root, "tests", "golden", name)))
         now = make_golden.golden_for(g["width"], g["height"], g["seed"])
         assert now["sha256"] == g["sha256"], name
+
+
+def test_port_lr_unit_with_stripe_boundaries_matches_reference(oracle, refc):
+    """SURVEY 8 a13 groundwork: one restoration unit filtered stripe by stripe with the saved boundary lines
+    (svt_av1_loop_restoration_filter_unit, restoration.c:1067-1135) -- our restatement against the reference."""
+    import ctypes as ct
+    r = np.random.default_rng(33)
+    refc.ref_lr_filter_unit_wiener_8bit.restype = None
+    oracle.port.port_lr_filter_unit_wiener_8bit.restype = None
+    PAD = 32
+    for ss in (0, 1):
+        W, Hh = (328 >> ss), (200 >> ss)
+        stride = W + 2 * PAD
+        plane = r.integers(0, 256, (Hh + 2 * PAD) * stride).astype(np.uint8)
+        origin = PAD * stride + PAD
+        nstripes = (Hh + (8 >> ss) + (64 >> ss) - 1) // (64 >> ss) + 1
+        bstride = ((W + 8 + 31) // 32) * 32
+        above = r.integers(0, 256, 2 * nstripes * bstride).astype(np.uint8)
+        below = r.integers(0, 256, 2 * nstripes * bstride).astype(np.uint8)
+        tile = np.array([0, 0, W, Hh], np.int32)
+        ru = 128 >> ss
+        for opt in (0, 1):
+            for (hs, he, vs, ve) in [(0, min(ru, W), 0, min(ru + (ru // 2), Hh)), (ru, W, 0, Hh), (0, W, (ru - (8 >> ss)), Hh),
+                                     (ru, min(2 * ru, W), ru - (8 >> ss), min(2 * ru - (8 >> ss), Hh))]:
+                t0, t1, t2 = int(r.integers(-5, 11)), int(r.integers(-23, 9)), int(r.integers(-17, 47))
+                taps = np.array([t0, t1, t2, -2 * (t0 + t1 + t2), t2, t1, t0, 0], np.int16)
+                limits = np.array([hs, he, vs, ve], np.int32)
+                outs = []
+                for fn, src in ((refc.ref_lr_filter_unit_wiener_8bit, plane.copy()), (oracle.port.port_lr_filter_unit_wiener_8bit, plane.copy())):
+                    dst = np.full_like(plane, 7)
+                    fn(ct.c_void_p(src.ctypes.data + origin), stride, ct.c_void_p(dst.ctypes.data + origin), stride,
+                       ct.c_void_p(limits.ctypes.data), ct.c_void_p(taps.ctypes.data), ct.c_void_p(taps.ctypes.data),
+                       ct.c_void_p(above.ctypes.data), ct.c_void_p(below.ctypes.data), bstride, ct.c_void_p(tile.ctypes.data), 0, ss, ss, opt)
+                    assert np.array_equal(src, plane), "the picture must be left as it was"
+                    outs.append(dst)
+                assert np.array_equal(outs[0], outs[1]), (ss, opt, hs, he, vs, ve)
