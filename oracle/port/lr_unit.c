@@ -15,9 +15,13 @@ void port_wiener_convolve(const uint16_t* src, ptrdiff_t ss, uint16_t* dst, ptrd
 
 enum { PROC_UNIT = 64, UNIT_OFFSET = 8, BORDER = 3, CTX_VERT = 2, EXTRA_HORZ = 4 };
 
-void port_lr_filter_unit_wiener_8bit(const uint8_t* data, int stride, uint8_t* dst, int dst_stride, const int32_t* limits,
-                                     const int16_t* hfilter, const int16_t* vfilter, const uint8_t* above, const uint8_t* below,
-                                     int bstride, const int32_t* tile, int tile_stripe0, int ss_x, int ss_y, int optimized_lr) {
+void port_sgr_apply(const uint16_t* dat, int w, int h, int stride, int eps, const int32_t* xqd, uint16_t* dst, int ds, int bd);
+
+/* rtype 0: Wiener (hfilter, vfilter); 1: self-guided (ep, xqd) */
+static void lr_filter_unit_8bit(int rtype, const uint8_t* data, int stride, uint8_t* dst, int dst_stride, const int32_t* limits,
+                                const int16_t* hfilter, const int16_t* vfilter, int ep, const int32_t* xqd, const uint8_t* above,
+                                const uint8_t* below, int bstride, const int32_t* tile, int tile_stripe0, int ss_x, int ss_y,
+                                int optimized_lr) {
     const int h_start = limits[0], h_end = limits[1], v_start = limits[2], v_end = limits[3];
     const int tile_top = tile[1], tile_bottom = tile[3];
     const int unit_w = h_end - h_start, unit_h = v_end - v_start;
@@ -59,11 +63,15 @@ void port_lr_filter_unit_wiener_8bit(const uint8_t* data, int stride, uint8_t* d
             if (copy_below)
                 for (int c = 0; c < line_w; c++) win[(h + 2 + BORDER) * pitch + c] = win[(h + 1 + BORDER) * pitch + c];
         }
-        /* svt_aom_wiener_filter_stripe: 64-column processing units, the last one rounded up to a multiple of 16 */
+        /* svt_aom_wiener_filter_stripe: 64-column processing units, the last one rounded up to a multiple of 16;
+         * svt_aom_sgrproj_filter_stripe: 64-column units, the last one exactly as wide as what is left */
         for (int j = 0; j < unit_w; j += procw) {
-            int w = (unit_w - j + 15) & ~15;
+            int w = rtype == 0 ? ((unit_w - j + 15) & ~15) : unit_w - j;
             if (w > procw) w = procw;
-            port_wiener_convolve(win + BORDER * pitch + EXTRA_HORZ + j, pitch, out, 64, hfilter, vfilter, w, h, 3, 11, 8, 1);
+            if (rtype == 0)
+                port_wiener_convolve(win + BORDER * pitch + EXTRA_HORZ + j, pitch, out, 64, hfilter, vfilter, w, h, 3, 11, 8, 1);
+            else
+                port_sgr_apply(win + BORDER * pitch + EXTRA_HORZ + j, w, h, pitch, ep, xqd, out, 64, 8);
             for (int r = 0; r < h; r++)
                 for (int c = 0; c < w; c++) dst[(ptrdiff_t)(vs + r) * dst_stride + h_start + j + c] = (uint8_t)out[r * 64 + c];
         }
@@ -71,4 +79,18 @@ void port_lr_filter_unit_wiener_8bit(const uint8_t* data, int stride, uint8_t* d
     }
     free(win);
     free(out);
+}
+
+void port_lr_filter_unit_wiener_8bit(const uint8_t* data, int stride, uint8_t* dst, int dst_stride, const int32_t* limits,
+                                     const int16_t* hfilter, const int16_t* vfilter, const uint8_t* above, const uint8_t* below,
+                                     int bstride, const int32_t* tile, int tile_stripe0, int ss_x, int ss_y, int optimized_lr) {
+    lr_filter_unit_8bit(0, data, stride, dst, dst_stride, limits, hfilter, vfilter, 0, NULL, above, below, bstride, tile, tile_stripe0,
+                        ss_x, ss_y, optimized_lr);
+}
+
+void port_lr_filter_unit_sgrproj_8bit(const uint8_t* data, int stride, uint8_t* dst, int dst_stride, const int32_t* limits, int ep,
+                                      const int32_t* xqd, const uint8_t* above, const uint8_t* below, int bstride, const int32_t* tile,
+                                      int tile_stripe0, int ss_x, int ss_y, int optimized_lr) {
+    lr_filter_unit_8bit(1, data, stride, dst, dst_stride, limits, NULL, NULL, ep, xqd, above, below, bstride, tile, tile_stripe0, ss_x,
+                        ss_y, optimized_lr);
 }

@@ -524,15 +524,39 @@ void ref_wiener_units_8bit(const uint8_t* src, uint8_t* dst, const RefWienerUnit
  * `data` / `dst` point at pixel (0,0) of the plane; limits = {h_start, h_end, v_start, v_end}; tile = {left, top,
  * right, bottom}; above/below = the saved stripe-boundary lines (RESTORATION_CTX_VERT rows per stripe, `bstride`
  * bytes per row, logical column x at byte x + RESTORATION_EXTRA_HORZ is handled by the caller's pointer). */
+static void lr_filter_unit_8bit(const RestorationUnitInfo* ruip, uint8_t* data, int stride, uint8_t* dst, int dst_stride,
+                                const int32_t* limits, uint8_t* above, uint8_t* below, int bstride, const int32_t* tile,
+                                int tile_stripe0, int ss_x, int ss_y, int optimized_lr);
+
 void ref_lr_filter_unit_wiener_8bit(uint8_t* data, int stride, uint8_t* dst, int dst_stride, const int32_t* limits,
                                     const int16_t* hfilter, const int16_t* vfilter, uint8_t* above, uint8_t* below, int bstride,
                                     const int32_t* tile, int tile_stripe0, int ss_x, int ss_y, int optimized_lr) {
-    RestorationTileLimits lim = {limits[0], limits[1], limits[2], limits[3]};
-    RestorationUnitInfo   rui;
+    RestorationUnitInfo rui;
     memset(&rui, 0, sizeof(rui));
     rui.restoration_type = RESTORE_WIENER;
     memcpy(rui.wiener_info.hfilter, hfilter, 8 * sizeof(int16_t));
     memcpy(rui.wiener_info.vfilter, vfilter, 8 * sizeof(int16_t));
+    lr_filter_unit_8bit(&rui, data, stride, dst, dst_stride, limits, above, below, bstride, tile, tile_stripe0, ss_x, ss_y, optimized_lr);
+}
+
+/* the same with the self-guided filter (svt_aom_sgrproj_filter_stripe, restoration.c:994-1015) */
+void ref_lr_filter_unit_sgrproj_8bit(uint8_t* data, int stride, uint8_t* dst, int dst_stride, const int32_t* limits, int ep,
+                                     const int32_t* xqd, uint8_t* above, uint8_t* below, int bstride, const int32_t* tile,
+                                     int tile_stripe0, int ss_x, int ss_y, int optimized_lr) {
+    RestorationUnitInfo rui;
+    memset(&rui, 0, sizeof(rui));
+    rui.restoration_type    = RESTORE_SGRPROJ;
+    rui.sgrproj_info.ep     = ep;
+    rui.sgrproj_info.xqd[0] = xqd[0];
+    rui.sgrproj_info.xqd[1] = xqd[1];
+    lr_filter_unit_8bit(&rui, data, stride, dst, dst_stride, limits, above, below, bstride, tile, tile_stripe0, ss_x, ss_y, optimized_lr);
+}
+
+static void lr_filter_unit_8bit(const RestorationUnitInfo* ruip, uint8_t* data, int stride, uint8_t* dst, int dst_stride,
+                                const int32_t* limits, uint8_t* above, uint8_t* below, int bstride, const int32_t* tile,
+                                int tile_stripe0, int ss_x, int ss_y, int optimized_lr) {
+    RestorationTileLimits lim = {limits[0], limits[1], limits[2], limits[3]};
+    RestorationUnitInfo   rui = *ruip;
     RestorationStripeBoundaries rsb;
     rsb.stripe_boundary_above  = above;
     rsb.stripe_boundary_below  = below;
@@ -540,7 +564,9 @@ void ref_lr_filter_unit_wiener_8bit(uint8_t* data, int stride, uint8_t* dst, int
     rsb.stripe_boundary_size   = 0;
     RestorationLineBuffers* rlbs = (RestorationLineBuffers*)malloc(sizeof(RestorationLineBuffers));
     Av1PixelRect            tr   = {tile[0], tile[1], tile[2], tile[3]};
+    int32_t*                tmp  = (int32_t*)malloc(RESTORATION_TMPBUF_SIZE);
     svt_av1_loop_restoration_filter_unit(1, &lim, &rui, &rsb, rlbs, &tr, tile_stripe0, ss_x, ss_y, 0, 8, data, stride, dst,
-                                         dst_stride, NULL, optimized_lr);
+                                         dst_stride, tmp, optimized_lr);
+    free(tmp);
     free(rlbs);
 }

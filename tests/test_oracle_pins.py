@@ -301,3 +301,20 @@ def test_port_lr_unit_with_stripe_boundaries_matches_reference(oracle, refc):
                     assert np.array_equal(src, plane), "the picture must be left as it was"
                     outs.append(dst)
                 assert np.array_equal(outs[0], outs[1]), (ss, opt, hs, he, vs, ve)
+                # the self-guided filter through the same stripe machinery
+                ep = int(r.integers(0, 16))
+                xqd = np.array([int(r.integers(-96, 32)), int(r.integers(-32, 96))], np.int32)
+                if ep >= 14:
+                    xqd[1] = 0 if ep == 14 else xqd[1]  # r1 == 0 sets are legal with any xqd; keep the draw simple
+                outs = []
+                refc.ref_lr_filter_unit_sgrproj_8bit.restype = None
+                oracle.port.port_lr_filter_unit_sgrproj_8bit.restype = None
+                for fn in (refc.ref_lr_filter_unit_sgrproj_8bit, oracle.port.port_lr_filter_unit_sgrproj_8bit):
+                    src = plane.copy()
+                    dst = np.full_like(plane, 7)
+                    fn(ct.c_void_p(src.ctypes.data + origin), stride, ct.c_void_p(dst.ctypes.data + origin), stride,
+                       ct.c_void_p(limits.ctypes.data), ep, ct.c_void_p(xqd.ctypes.data), ct.c_void_p(above.ctypes.data),
+                       ct.c_void_p(below.ctypes.data), bstride, ct.c_void_p(tile.ctypes.data), 0, ss, ss, opt)
+                    assert np.array_equal(src, plane)
+                    outs.append(dst)
+                assert np.array_equal(outs[0], outs[1]), ("sgr", ss, opt, hs, he, vs, ve, ep)
