@@ -37,6 +37,7 @@ METRIC = "1080p preset-8 encoded frames/sec at 1/2/4/8 B200 vs reference AVX2 on
 METRIC_SCOPE = "hot path only (SURVEY 8: ME + transform/quant/inverse + CDEF + Wiener of one 1080p preset-8 frame per step), not a full encode"
 N_FRAME_SETS = 8  # rotated between steps: no step finds its inputs in L2, and (e2e) up to 8 frames are in flight
 N_CALLS = 8       # len(FramePipeline.CALLS): the T2 entry points one frame goes through
+EXCH_BATCH = 4    # pictures per reconstructed-reference exchange (one mini-GOP slice per NCCL group launch)
 # dram__bytes_read.sum + dram__bytes_write.sum of the call's dominant kernel, per launch, from the ncu --set full
 # capture of this same command (profiles/README.md says which file); None = not captured for that call
 NCU_DRAM_SOURCE = "profiles/r1_top_kernels_ncu_raw.csv (ncu --set full, one launch of the call's main kernel)"
@@ -47,139 +48,75 @@ NCU_DRAM_BYTES = {"cdef_search": 4995584 + 0,          # cdef_search_kernel: rea
 
 
 # ------------------------------------------------------------------------------------------------------
-# reference arm: the reference's own kernels over the same work lists (oracle/ref_driver.c)
+# reference arm: the reference's own kernels over the same work lists (oracle/ref_driver.c), whole frames
+# in flight on a persistent core-pinned thread pool.  Imports NOTHING from the product package.
 # ------------------------------------------------------------------------------------------------------
-def aligned_zeros(n, dtype, align=64):
-    """numpy array whose data pointer is `align`-byte aligned (the AVX2 kernels use aligned stores)"""
-    isz = np.dtype(dtype).itemsize
-    raw = np.zeros(n * isz + align, np.uint8)
-    off = (-raw.ctypes.data) % align
-    return raw[off:off + n * isz].view(dtype)
-
-
-class RefFrame:
-    def __init__(self, wl, ref):
-        from oracle import support as me_np
-        self.wl, self.ref = wl, ref
-        W, H = wl.width, wl.height
-        self.cur_pyr = me_np.build_pyramid_np(wl.cur[0], W, H, wl.me_shapes)
-        self.ref_pyrs = [me_np.build_pyramid_np(r[0], W, H, wl.me_shapes) for r in wl.refs]
-        self.cur_desc = me_np.ref_pic_desc(self.cur_pyr, wl.me_shapes)
-        self.ref_descs = (me_np.RefMePicture * wl.n_refs)(*[me_np.ref_pic_desc(p, wl.me_shapes) for p in self.ref_pyrs])
-        self.prm = (me_np.RefMeParams * wl.n_refs)()
-        for i, p in enumerate(wl.me_params):
-            for k, v in p.items():
-                setattr(self.prm[i], k, v)
-        nb = ((W + 63) // 64) * ((H + 63) // 64)
-        self.me_sad = np.zeros((wl.n_refs, nb, 85), np.uint32)
-        self.me_mv = np.zeros_like(self.me_sad)
-        self.me_c = np.zeros((wl.n_refs, nb, 2), np.int16)
-        self.me_hs = np.zeros((wl.n_refs, nb), np.uint64)
-        self.cur_flat = np.concatenate([p.reshape(-1) for p in wl.cur])
-        res = np.concatenate([p.reshape(-1) for p in wl.residual])
-        self.residual = aligned_zeros(res.size, np.int16)
-        self.residual[:] = res
-        _, n_pad = wl.padded_offsets()
-        self.pred = self._pad_planes(wl.pred)
-        self.recon = np.zeros(n_pad, np.uint8)
-        self.cdef_out = np.zeros(n_pad, np.uint8)
-        self.final = np.zeros(n_pad, np.uint8)
-        self.coeff = aligned_zeros(wl.n_coeffs, np.int32)
-        self.q = aligned_zeros(wl.n_coeffs, np.int32)
-        self.dq = aligned_zeros(wl.n_coeffs, np.int32)
-        self.eobs = np.zeros(len(wl.quant_items), np.uint16)
-        self.fwd = np.ascontiguousarray(wl.fwd_items)
-        self.inv = np.ascontiguousarray(wl.inv_items)
-        self.qi = np.ascontiguousarray(wl.quant_items)
-        self.mse = np.zeros((2, nb, len(wl.cdef_str_y)), np.uint64)
-        self.dirs = np.zeros((nb, 64), np.uint8)
-        self.vars = np.zeros((nb, 64), np.int32)
-        self.M = np.zeros((len(wl.stats_items), 49), np.int64)
-        self.Hm = np.zeros((len(wl.stats_items), 2401), np.int64)
-        for f in ("ref_me_picture", "ref_fwd_txfm_batch", "ref_quant_batch", "ref_inv_txfm_batch_8bit", "ref_cdef_search_frame",
-                  "ref_cdef_apply_frame", "ref_compute_stats_batch", "ref_wiener_units_8bit"):
-            getattr(ref, f).restype = None
-
-    def _pad_planes(self, planes):
-        wl = self.wl
-        off, n = wl.padded_offsets()
-        buf = np.zeros(n, np.uint8)
-        for p in range(3):
-            th, st = wl.padded_shape(p)
-            w, h = wl.plane_dims[p]
-            buf[off[p]:off[p] + th * st].reshape(th, st)[:, :w + 2 * wl.PAD] = np.pad(planes[p], wl.PAD, mode="edge")
-        return buf
-
-    def _extend(self, buf):
-        wl = self.wl
-        off, _ = wl.padded_offsets()
-        for p in range(3):
-            th, st = wl.padded_shape(p)
-            w, h = wl.plane_dims[p]
-            v = buf[off[p]:off[p] + th * st].reshape(th, st)
-            v[:, :w + 2 * wl.PAD] = np.pad(v[wl.PAD:wl.PAD + h, wl.PAD:wl.PAD + w], wl.PAD, mode="edge")
-
-    def _cdef_frame(self):
-        from oracle import support as me_np
-        wl = self.wl
-        off, _ = wl.padded_offsets()
-        soff, _ = wl.flat_offsets()
-        f = me_np.RefCdefFrame()
-        ptrs = []
-        for p in range(3):
-            th, st = wl.padded_shape(p)
-            ptrs.append(self.recon.ctypes.data + off[p] + wl.PAD * st + wl.PAD)
-        f.recon_y, f.recon_cb, f.recon_cr = ptrs
-        f.src_y, f.src_cb, f.src_cr = [self.cur_flat.ctypes.data + soff[p] for p in range(3)]
-        f.recon_stride_y, f.recon_stride_c = wl.padded_shape(0)[1], wl.padded_shape(1)[1]
-        f.src_stride_y, f.src_stride_c = wl.plane_dims[0][0], wl.plane_dims[1][0]
-        f.width, f.height, f.bit_depth, f.damping, f.subsampling_factor = wl.width, wl.height, 8, wl.cdef_damping, wl.cdef_subsampling
-        return f
-
-    def step(self):
-        wl, ref = self.wl, self.ref
-        P = lambda a, o=0: ct.c_void_p(a.ctypes.data + o)  # noqa: E731
-        # ME (the numpy pyramid build is input preparation and stays outside, like the resident refs)
-        ref.ref_me_picture(ct.byref(self.cur_desc), self.ref_descs, self.prm, wl.n_refs, P(self.me_sad), P(self.me_mv), P(self.me_c), P(self.me_hs))
-        ref.ref_fwd_txfm_batch(P(self.residual), P(self.coeff), P(self.fwd), len(self.fwd))
-        ref.ref_quant_batch(P(self.coeff), P(self.q), P(self.dq), P(wl.scan_table), P(wl.iscan_table), P(wl.qm_table), P(self.qi), len(self.qi), P(self.eobs))
-        ref.ref_inv_txfm_batch_8bit(P(self.dq), P(self.pred), P(self.recon), P(self.inv), len(self.inv))
-        f = self._cdef_frame()
-        ref.ref_cdef_search_frame(ct.byref(f), P(wl.skip8x8), P(wl.cdef_str_y), P(wl.cdef_str_uv), len(wl.cdef_str_y), P(self.mse), P(self.dirs),
-                                  P(self.vars))
-        np.copyto(self.cdef_out, self.recon)
-        off, _ = wl.padded_offsets()
-        outs = [self.cdef_out.ctypes.data + off[p] + wl.PAD * wl.padded_shape(p)[1] + wl.PAD for p in range(3)]
-        ref.ref_cdef_apply_frame(ct.byref(f), P(wl.skip8x8), P(wl.cdef_fb_idx), P(wl.cdef_apply_y), P(wl.cdef_apply_uv), ct.c_void_p(outs[0]),
-                                 ct.c_void_p(outs[1]), ct.c_void_p(outs[2]), wl.padded_shape(0)[1], wl.padded_shape(1)[1])
-        self._extend(self.cdef_out)
-        ref.ref_compute_stats_batch(P(self.cdef_out), P(self.cur_flat), P(np.ascontiguousarray(wl.stats_items)), len(wl.stats_items), P(self.M),
-                                    P(self.Hm))
-        ref.ref_wiener_units_8bit(P(self.cdef_out), P(self.final), P(np.ascontiguousarray(wl.wiener_units)), len(wl.wiener_units))
+REF_TIER_NAME = {0: "c", 1: "avx2-intrinsics (inverse transform: the reference's intrinsics AVX2/SSE4.1 kernels; the dav1d NASM kernels cannot be assembled here)"}
 
 
 def load_reference():
     import oracle
     if oracle.ref is None:
-        return None, "port", 0
+        return None, 0
     tier = oracle.ref.ref_set_tier(1)
-    return oracle.ref, ("reference" if tier == 1 else "reference"), tier
+    return oracle.ref, (1 if tier == 1 else 0)
 
 
-def time_reference(wl, steps, warmup):
-    ref, kind, tier = load_reference()
+def make_workloads(args, rank, n_sets):
+    """the frame sets of this rank: same work lists, different synthetic content"""
+    from oracle.frame_ref import load_workload_module
+    W = load_workload_module()
+    w, h, bd, preset = W.CONFIGS[args.config]
+    if args.width:
+        w, h = args.width, args.height
+    wl0 = W.FrameWorkload(w, h, seed=20260923 + 17 * rank * N_FRAME_SETS, bit_depth=bd, preset=preset)
+    return W, [wl0 if i == 0 else wl0.with_seed(20260923 + 17 * (rank * N_FRAME_SETS + i)) for i in range(n_sets)]
+
+
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def time_reference_frames(ref, frames, n_frames, n_threads, warm_frames):
+    from oracle.frame_ref import run_frames
+    run_frames(ref, frames, max(warm_frames, n_threads), n_threads)  # every worker touches its private buffers once
+    return run_frames(ref, frames, n_frames, n_threads)
+
+
+def reference_arm(args, wls, steps, warmup, budget_s=60.0, scaling=True):
+    """-> dict(fps, ms, cores, tier, inner_repeats, scaling) or None.  A step = one whole frame; `steps` frames form a
+    batch and the batch is repeated back to back (one continuous stream of frames, no barrier between repeats) so
+    that every host thread has several frames to work through."""
+    from oracle.frame_ref import RefFrame
+    ref, tier = load_reference()
     if ref is None:
         return None
-    fr = RefFrame(wl, ref)
-    cores = ref.ref_num_threads()
-    for _ in range(warmup):
-        fr.step()
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        fr.step()
-    dt = time.perf_counter() - t0
-    return dict(fps=steps / dt, ms=1e3 * dt / steps, cores=cores, kind=kind,
-                tier="avx2-intrinsics (inverse transform: C, no NASM)" if tier == 1 else "c", frame=fr)
+    frames = [RefFrame(w, ref) for w in wls]
+    cores = host_threads()
+    # one frame, single thread: sizes the sample
+    t1 = time_reference_frames(ref, frames, 1, 1, 1)
+    per_thread_fps = 1.0 / t1
+    want = max(steps, 6 * cores)                               # >= 6 frames per thread: the tail wave costs < 15 %
+    cap = max(steps, int(budget_s * per_thread_fps * cores))   # bounded by the time budget
+    n_frames = min(want, cap)
+    reps = max(1, -(-n_frames // steps))
+    n_frames = reps * steps
+    dt = time_reference_frames(ref, frames, n_frames, cores, warmup)
+    out = dict(fps=n_frames / dt, ms=1e3 * dt / n_frames, cores=cores, tier=REF_TIER_NAME[tier], inner_repeats=reps, frames=n_frames,
+               single_thread_fps=per_thread_fps)
+    if scaling:
+        curve = {"1": round(per_thread_fps, 3)}
+        for t in (8, 32, 64):
+            if t < cores:
+                n = max(2 * t, min(6 * t, int(10.0 * per_thread_fps * t)))
+                curve[str(t)] = round(n / time_reference_frames(ref, frames, n, t, t), 3)
+        curve[str(cores)] = round(out["fps"], 3)
+        out["scaling"] = curve
+        ref.ref_set_threads(cores)
+    return out
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -252,52 +189,49 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--width", type=int, default=1920)
-    ap.add_argument("--height", type=int, default=1080)
+    ap.add_argument("--config", type=int, default=1, choices=[0, 1, 2, 3, 4], help="BASELINE.json configs[k] (default 1: 1080p 8-bit preset 8)")
+    ap.add_argument("--width", type=int, default=0, help="override the configuration's picture size (tests)")
+    ap.add_argument("--height", type=int, default=0)
     ap.add_argument("--check", action="store_true", help="compare one frame of B200 output with the reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--one-stream", action="store_true", help="all frames on one compute stream (no frame-level overlap)")
-    ap.add_argument("--streams", type=int, default=4, help="compute streams that consecutive frames alternate between (1, 2 or 4)")
+    ap.add_argument("--streams", type=int, default=4, help="compute streams that consecutive frames alternate between (1, 2, 4 or 8)")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying one CUDA graph per step")
+    ap.add_argument("--min-time", type=float, default=0.3, help="minimum length (s) of each timed region: the steps-long loop is repeated")
+    ap.add_argument("--ref-budget", type=float, default=60.0, help="reference arm: upper bound (s) of CPU time for the timed sample")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     warmup = max(args.warmup, 3)
 
-    import svt_av1_psy_b200  # noqa: F401  (ImportError = library not built: there is no fallback)
-    from svt_av1_psy_b200.workload import FrameWorkload
-
-    config = {"workload": "configs[1]: 1920x1080 8-bit 4:2:0 synthetic, preset 8 CRF 30 hot path (ME 2 refs + TX + CDEF + Wiener), 1 frame/step",
-              "width": args.width, "height": args.height, "frame_sets": N_FRAME_SETS,
-              "l2": "steps rotate over %d distinct frame sets (~65 MB each, >126 MB L2 in total)" % N_FRAME_SETS,
-              "parallelism": "frame-parallel x%d (no data-path collective; recon exchange = all_gather of the filtered frame)" % world,
-              "overlap": "ME (source pictures only) on a side stream, concurrent with the transform->CDEF->restoration chain of the same step",
-              "streams": "1 compute stream" if args.one_stream else "%d compute streams: consecutive (independent) frames alternate between them" % args.streams,
-              "launch": "eager" if args.no_graph else "one CUDA graph replay per step (the step's kernel launches captured once per frame set)"}
-
     if args.impl == "reference":
+        # the reference's CPU implementation on the host cores; rank 0 alone works, nothing of the product is imported
         if rank != 0:
             return
-        wl = FrameWorkload(args.width, args.height)
-        steps = min(args.steps, 5)
-        t = time_reference(wl, steps, min(warmup, 1))
+        W, wls = make_workloads(args, 0, N_FRAME_SETS)
+        config = base_config(args, W, wls[0], world, reference=True)
+        t = reference_arm(args, wls, args.steps, warmup, budget_s=args.ref_budget)
         if t is None:
             print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libsvtav1_ref.so is not built"}))
             return
+        config["frames_in_flight"] = "one whole frame per host thread, persistent core-pinned pool (%d threads), %d frame sets" % (t["cores"], N_FRAME_SETS)
         out = {"impl": "reference", "metric": METRIC, "metric_scope": METRIC_SCOPE, "value": round(t["fps"], 3), "unit": "frames/s",
-               "n_gpus": args.gpus, "steps": steps,
-               "warmup": min(warmup, 1), "ms_per_step": round(t["ms"], 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-               "dtype": "u8", "data": "synthetic", "config": config,
+               "n_gpus": args.gpus, "steps": args.steps, "warmup": warmup, "inner_repeats": t["inner_repeats"],
+               "ms_per_step": round(t["ms"], 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+               "dtype": "u8" if wls[0].bit_depth == 8 else "u16", "data": "synthetic", "config": config,
                "cpu_baseline": {"value": round(t["fps"], 3), "unit": "frames/s", "cores": t["cores"], "kind": "reference",
-                                "sample": "%d full frames, tier %s" % (steps, t["tier"])},
+                                "sample": "%d whole frames in flight over %d pinned threads (%d x %d steps), tier %s" %
+                                          (t["frames"], t["cores"], t["inner_repeats"], args.steps, t["tier"]),
+                                "scaling": t.get("scaling"), "single_thread_ms_per_frame": round(1e3 / t["single_thread_fps"], 2)},
                "e2e": {"value": round(t["fps"], 3), "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(out))
         return
 
+    import svt_av1_psy_b200  # noqa: F401  (ImportError = library not built: there is no fallback)
     import torch
     import torch.distributed as dist
-    from svt_av1_psy_b200 import dsp
+    from svt_av1_psy_b200 import dsp, sharding
     from svt_av1_psy_b200.pipeline import FramePipeline
     assert len(FramePipeline.CALLS) == N_CALLS
     torch.cuda.set_device(local_rank)
@@ -305,15 +239,18 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dsp.init(local_rank)
-    wl0 = FrameWorkload(args.width, args.height, seed=20260923 + 17 * rank * N_FRAME_SETS)
-    sets = [FramePipeline(wl0 if i == 0 else wl0.with_seed(20260923 + 17 * (rank * N_FRAME_SETS + i)), torch) for i in range(N_FRAME_SETS)]
+    W, wls = make_workloads(args, rank, N_FRAME_SETS)
+    wl0 = wls[0]
+    config = base_config(args, W, wl0, world, reference=False)
+    sets = [FramePipeline(w, torch) for w in wls]
     stream = torch.cuda.Stream()
-    # consecutive frames alternate between two compute streams: independent pictures in flight at once, as in
-    # the encoder's picture-parallel pipeline; frame set k always runs on stream k % 2
     n_streams = 1 if args.one_stream else args.streams
     assert n_streams in (1, 2, 4, 8), "--streams must divide the %d frame sets" % N_FRAME_SETS
     streams = [stream] + [torch.cuda.Stream() for _ in range(n_streams - 1)]
-    gathered = [torch.empty((world,) + tuple(sets[0].final.shape), dtype=torch.uint8, device="cuda") for _ in range(N_FRAME_SETS)] if world > 1 else None
+    # reconstructed-reference exchange (the path's one real exchange): owner -> consumers, batched per
+    # mini-GOP of EXCH_BATCH pictures, on a dedicated communication stream
+    comm = torch.cuda.Stream() if world > 1 else None
+    exch = sharding.ReconExchange(dist, rank, world, sets[0].final, EXCH_BATCH) if world > 1 else None
 
     def barrier():
         torch.cuda.synchronize()
@@ -324,8 +261,8 @@ def main():
     graphs = [None] * N_FRAME_SETS
 
     def enqueue_step(i, events=None):
-        """one frame of hot-path work on the current stream: replay of the frame set's CUDA graph (the ~35
-        kernel launches of a step captured once; same kernels, same work) or, for per-call timing, eager"""
+        """one frame of hot-path work on the current stream: replay of the frame set's CUDA graph (the kernel
+        launches of a step captured once; same kernels, same work) or, for per-call timing, eager"""
         g = graphs[i % N_FRAME_SETS]
         if g is not None and events is None:
             g.replay()
@@ -344,26 +281,58 @@ def main():
                 fp.step()
             graphs[k] = g
 
-    def run(n, e2e, stage_acc=None):
+    class Exchanger:
+        """per timed loop: hands every finished picture to the communication stream in mini-GOP batches and keeps
+        a frame set from being overwritten before its picture has left"""
+        def __init__(self, n):
+            self.done = [torch.cuda.Event() for _ in range(n)]
+            self.sent = {}     # batch index -> event recorded on the comm stream after the batch's exchange
+            self.works = []
+
+        def before_step(self, i, cs):
+            j = i - N_FRAME_SETS
+            if exch is not None and j >= 0 and (j // EXCH_BATCH) in self.sent:
+                cs.wait_event(self.sent[j // EXCH_BATCH])
+
+        def after_step(self, i, cs, n):
+            if exch is None:
+                return
+            self.done[i].record(cs)
+            if (i + 1) % EXCH_BATCH == 0 or i == n - 1:
+                b0 = (i // EXCH_BATCH) * EXCH_BATCH
+                with torch.cuda.stream(comm):
+                    for k in range(b0, i + 1):
+                        comm.wait_event(self.done[k])
+                    self.works += exch.post([sets[k % N_FRAME_SETS].final for k in range(b0, i + 1)])
+                    exch.wait(self.works)  # (stream-ordered) the comm stream continues after the group has completed
+                    self.works = []
+                    ev = torch.cuda.Event()
+                    ev.record(comm)
+                    self.sent[i // EXCH_BATCH] = ev
+
+        def finish(self, main):
+            if exch is not None:
+                main.wait_stream(comm)
+
+    def run(n, stage_acc=None):
         ev = [[torch.cuda.Event(enable_timing=True) for _ in range(N_CALLS + 1)] for _ in range(n)] if stage_acc is not None else None
         start, end, tail = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), torch.cuda.Event()
+        ex = Exchanger(n)
         start.record(stream)
         for x in streams[1:]:
             x.wait_event(start)
+        if comm is not None:
+            comm.wait_event(start)
         for i in range(n):
             st = stream if ev else streams[i % n_streams]  # the per-call profile runs strictly serially
             with torch.cuda.stream(st):
-                fp = sets[i % N_FRAME_SETS]
-                if e2e:
-                    fp.load_inputs()
+                ex.before_step(i, st)
                 enqueue_step(i, ev[i] if ev else None)
-                if world > 1:  # reconstructed-reference exchange (the path's one real collective)
-                    dist.all_gather_into_tensor(gathered[i % N_FRAME_SETS].view(-1), fp.final)
-                if e2e:
-                    fp.read_outputs()
+                ex.after_step(i, st, n)
         for x in streams[1:]:
             tail.record(x)
             stream.wait_event(tail)
+        ex.finish(stream)
         end.record(stream)
         torch.cuda.synchronize()
         if stage_acc is not None:
@@ -381,46 +350,59 @@ def main():
         ev_in = [torch.cuda.Event() for _ in range(n)]
         ev_done = [torch.cuda.Event() for _ in range(n)]
         ev_out = [torch.cuda.Event() for _ in range(n)]
+        ex = Exchanger(n)
         start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         start.record(stream)
         s_in.wait_event(start)
+        if comm is not None:
+            comm.wait_event(start)
         for i in range(n):
             fp = sets[i % N_FRAME_SETS]
             with torch.cuda.stream(s_in):
                 if i >= N_FRAME_SETS:
                     s_in.wait_event(ev_out[i - N_FRAME_SETS])
+                    ex.before_step(i, s_in)
                 fp.load_inputs()
                 ev_in[i].record(s_in)
             cs = streams[i % n_streams]
             with torch.cuda.stream(cs):
                 cs.wait_event(ev_in[i])
                 enqueue_step(i)
-                if world > 1:
-                    dist.all_gather_into_tensor(gathered[i % N_FRAME_SETS].view(-1), fp.final)
                 ev_done[i].record(cs)
+                ex.after_step(i, cs, n)
             with torch.cuda.stream(s_out):
                 s_out.wait_event(ev_done[i])
                 fp.read_outputs()
                 ev_out[i].record(s_out)
         stream.wait_event(ev_out[n - 1])
+        ex.finish(stream)
         end.record(stream)
         torch.cuda.synchronize()
         return start.elapsed_time(end)
+
+    def timed(fn, steps):
+        """the steps-long loop, repeated until the timed regions add up to >= --min-time; median region"""
+        first = fn(steps)
+        reps = int(min(60, max(1, -(-args.min_time * 1e3 // max(first, 1e-3)))))
+        vals = [fn(steps) for _ in range(reps)]
+        vals.sort()
+        return vals[len(vals) // 2], reps
 
     if args.check and rank == 0:
         check_against_reference(sets[0], torch)
 
     # ---- resident-input timing ---------------------------------------------------------------------------
-    run(warmup, False)
+    run(warmup)
     barrier()
     # per-call profile: eager launches with an event around every T2 call (not part of the timed value)
     l0 = dsp.launch_count()
     call_ms = [0.0] * N_CALLS
-    ms_eager = run(args.steps, False, call_ms)
-    launches = dsp.launch_count() - l0
+    prof_steps = min(args.steps, 40)
+    ms_eager = run(prof_steps, call_ms)
+    launches_per_step = (dsp.launch_count() - l0) / prof_steps
     if not args.no_graph:
         capture_graphs()
-        run(warmup, False)
+        run(warmup)
     barrier()
     bus_id = None
     try:  # NVML enumerates physical devices: address this rank's GPU by PCI id, not by (visible) index
@@ -430,12 +412,12 @@ def main():
         bus_id = None
     sampler = ClockSampler(local_rank, bus_id)
     sampler.start()
-    ms = run(args.steps, False)
+    ms, reps = timed(run, args.steps)
     barrier()
     # ---- end-to-end timing -----------------------------------------------------------------------------------
     run_e2e(warmup)
     barrier()
-    ms_e2e = run_e2e(args.steps)
+    ms_e2e, reps_e2e = timed(run_e2e, args.steps)
     clocks = sampler.stop()
     t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -449,7 +431,7 @@ def main():
     fps = world * args.steps / (ms / 1e3)
     fps_e2e = world * args.steps / (ms_e2e / 1e3)
     alg = wl0.algorithmic_bytes()
-    call_ms = [x / args.steps for x in call_ms]
+    call_ms = [x / prof_steps for x in call_ms]
     calls = FramePipeline.CALLS
     names = list(FramePipeline.STAGES)
     stage_ms = [sum(call_ms[i] for i, c in enumerate(calls) if c[1] == st) for st in names]
@@ -461,6 +443,7 @@ def main():
     except Exception:
         pass
     src = "MEASURED_PEAKS.json" if peaks else "fallback of /opt/skills/guides/B200_PROFILING.md"
+    ncu_bytes = NCU_DRAM_BYTES.get(dom_name) if args.config == 1 and not args.width else None
     if dom_name == "wiener_stats":  # the one dense contraction of the path: exact f16 MMA on the tensor cores
         flops = 2.0 * wl0.wiener_stats_macs()
         peak = float(peaks.get("bf16_tflops", peaks.get("dense_bf16_tflops", 2250.0)))
@@ -473,30 +456,54 @@ def main():
         roofline = {"bound": "hbm", "achieved": round(ach, 2), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 5),
                     "algorithmic_bytes_per_call": alg[dom_name],
                     "note": "integer kernel working out of shared-memory tiles: instruction/latency bound, not HBM bound (SURVEY 8d)"}
+        if dom_name == "txfm_trio":  # SURVEY 8(d)'s figure counts the unfused chain's intermediates; what the fused call must move is less
+            fm = alg["txfm_trio_fused_min"]
+            roofline["fused_min_bytes_per_call"] = fm
+            roofline["frac_fused_min"] = round(fm / (call_ms[dom] / 1e3) / 1e9 / peak, 5)
     roofline.update({"call": dom_name, "kernel": dom_kernels, "ms_per_call": round(call_ms[dom], 4), "peak_source": src,
-                     "traffic": NCU_DRAM_BYTES.get(dom_name), "traffic_source": NCU_DRAM_SOURCE if dom_name in NCU_DRAM_BYTES else None})
+                     "traffic": ncu_bytes, "traffic_source": NCU_DRAM_SOURCE if ncu_bytes is not None else None})
     out = {"metric": METRIC, "value": round(fps, 2), "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": warmup,
-           "ms_per_step": round(ms / args.steps, 4), "metric_scope": METRIC_SCOPE, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+           "inner_repeats": reps, "timed_region_ms": round(ms, 3),
+           "ms_per_step": round(ms / args.steps, 4), "metric_scope": METRIC_SCOPE, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "u8" if wl0.bit_depth == 8 else "u16",
            "data": "synthetic", "config": config, "clocks": clocks,
            "e2e": {"value": round(fps_e2e, 2), "unit": "frames/s", "h2d_bytes_per_step": int(sets[0].h2d_bytes), "d2h_bytes_per_step": int(sets[0].d2h_bytes),
-                   "ms_per_step": round(ms_e2e / args.steps, 4)},
-           "gpu_launches": int(launches), "eager_ms_per_step": round(ms_eager / args.steps, 4), "roofline": roofline,
+                   "ms_per_step": round(ms_e2e / args.steps, 4), "inner_repeats": reps_e2e},
+           "gpu_launches": int(round(launches_per_step * args.steps)), "gpu_launches_per_step": round(launches_per_step, 1),
+           "eager_ms_per_step": round(ms_eager / prof_steps, 4), "roofline": roofline,
            "stages_ms": {n: round(v, 4) for n, v in zip(names, stage_ms)},
            "calls_ms": {c[0]: round(v, 4) for c, v in zip(calls, call_ms)},
            "calls_algorithmic_gbs": {c[0]: round(alg[c[0]] / (v / 1e3) / 1e9, 2) for c, v in zip(calls, call_ms) if v > 0}}
+    if world > 1:
+        out["exchange"] = {"pattern": "owner -> %d consumers (point-to-point), batched per %d pictures, dedicated comm stream" % (len(exch.consumers), EXCH_BATCH),
+                           "bytes_sent_per_step_per_rank": int(exch.bytes_sent_per_frame)}
     if world == 1 and not args.no_cpu_baseline:
-        t = time_reference(wl0, 2, 1)
+        t = reference_arm(args, wls, args.steps, 3, budget_s=min(args.ref_budget, 20.0), scaling=False)
         if t is not None:
             out["cpu_baseline"] = {"value": round(t["fps"], 3), "unit": "frames/s", "cores": t["cores"], "kind": "reference",
-                                   "sample": "2 full frames of the same workload, tier %s" % t["tier"]}
+                                   "sample": "%d whole frames of the same workload in flight over %d pinned host threads, tier %s" %
+                                             (t["frames"], t["cores"], t["tier"])}
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
 
 
+def base_config(args, W, wl, world, reference):
+    cfg = {"workload": W.CONFIG_NAMES[args.config], "width": wl.width, "height": wl.height, "bit_depth": wl.bit_depth, "preset": wl.preset,
+           "frame_sets": N_FRAME_SETS,
+           "l2": "steps rotate over %d distinct frame sets (>= 65 MB each, > the 126 MB L2 in total)" % N_FRAME_SETS,
+           "parallelism": "frame-parallel x%d (no data-path collective; reconstructed reference pictures go owner -> consumers)" % world}
+    if not reference:
+        cfg.update({"overlap": "ME (source pictures only) on a side stream, concurrent with the transform->CDEF->restoration chain of the same step",
+                    "streams": "1 compute stream" if args.one_stream else "%d compute streams: consecutive (independent) frames alternate between them" % args.streams,
+                    "launch": "eager" if args.no_graph else "one CUDA graph replay per step (the step's kernel launches captured once per frame set)"})
+    return cfg
+
+
 def check_against_reference(fp, torch):
     """one frame through both arms, every output compared bit for bit"""
-    ref, _, _ = load_reference()
+    from oracle.frame_ref import RefFrame
+    ref, _ = load_reference()
     assert ref is not None, "oracle/_ref missing"
     ref.ref_set_tier(0)
     fr = RefFrame(fp.wl, ref)
@@ -530,9 +537,11 @@ def check_against_reference(fp, torch):
              ("eob/3-call", fp.eobs, fr.eobs), ("recon/3-call", fp.recon, fr.recon)]
     compare(split)
     cmp = cmp + split
+    ref.ref_set_tier(1)
     if bad:
         raise SystemExit("PARITY FAILURE vs reference: " + ", ".join(bad))
     print("parity vs reference C tier: all %d outputs bit-exact" % len(cmp), file=sys.stderr)
+    return len(cmp)
 
 
 if __name__ == "__main__":

@@ -316,7 +316,8 @@ typedef struct SvtB200HadamardItem {
     uint32_t src_stride;
     uint32_t size;       /* 4, 8, 16 or 32 */
 } SvtB200HadamardItem;
-/* T2: fused Hadamard + sum|coeff| per item; d_coeff_or_null may be NULL (SATD only). */
+/* T2: fused Hadamard + sum|coeff| per item; d_coeff_or_null may be NULL (SATD only).  An item whose size is not
+ * 4, 8, 16 or 32 gets d_satd[i] = -1 and writes no coefficients. */
 SVT_B200_API int svt_b200_hadamard_satd_batch_dev(const int16_t* d_residual, const SvtB200HadamardItem* d_items,
                                                   int n_items, int32_t* d_coeff_or_null, int32_t* d_satd, void* stream);
 
@@ -566,10 +567,10 @@ SVT_B200_API int svt_b200_extend_plane_dev(uint8_t* d_buf, int stride, int w, in
 /* the same for up to 4 planes (a picture's Y, Cb, Cr) in one launch */
 typedef struct SvtB200PlaneExtent {
     uint8_t* buf;     /* first byte of the padded plane */
-    int32_t  stride;
+    int32_t  stride;  /* in pixels */
     int32_t  w, h;    /* interior size */
     int32_t  org_x, org_y; /* interior origin = padding widths */
-    int32_t  reserved;
+    int32_t  pixel_bytes;  /* 0 or 1: 8-bit samples; 2: 16-bit samples (high-bit-depth planes) */
 } SvtB200PlaneExtent;
 SVT_B200_API int svt_b200_extend_planes_dev(const SvtB200PlaneExtent* planes, int n_planes, void* stream);
 /* fills the 1/4 and 1/16 planes (interior + replicated padding) from the full plane */

@@ -9,7 +9,12 @@
  * pixel-level computation is done by reference code.  Nothing here is used by the product.
  *
  * Not available in this build of the AVX2 tier (needs NASM): the dav1d inverse transforms -- the
- * inverse-transform leg always runs the reference C kernels (stated in DESIGN.md / bench output). */
+ * inverse-transform leg runs the reference's intrinsics-only AVX2 inverse instead (av1_inv_txfm_avx2.c,
+ * highbd_inv_txfm_avx2.c; stated in DESIGN.md / bench output). */
+#define _GNU_SOURCE
+#include <sched.h>
+#include <time.h>
+#include <stdio.h>
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
@@ -21,38 +26,104 @@
 #include "cdef.h"
 #include "restoration.h"
 #include "convolve.h"
+#include "inv_transforms.h"
 
 
-/* ---- minimal pthread parallel-for (no OpenMP runtime in this image) ------------------------------- */
-typedef void (*ParBody)(int i);
-static struct { ParBody body; int n, chunk; volatile int next; } g_par;
+/* ---- persistent, core-pinned worker pool -------------------------------------------------------------
+ * T-1 worker threads are created ONCE (ref_set_threads) and parked on a condition variable; the calling
+ * thread takes part in every parallel-for.  Worker t is pinned to the t-th CPU of the process affinity mask.
+ * A body invoked from inside a worker (whole frames in flight, ref_frames_run) runs nested loops serially. */
+typedef void (*ParBody)(void* ctx, int i);
+static struct {
+    pthread_mutex_t mu; pthread_cond_t cv_work, cv_done;
+    pthread_t th[256]; int n_workers; int quit; unsigned gen; int active;
+    ParBody body; void* ctx; int n, chunk; volatile int next; int max_workers;
+} g_pool = {PTHREAD_MUTEX_INITIALIZER, PTHREAD_COND_INITIALIZER, PTHREAD_COND_INITIALIZER};
 static int g_threads = 0;
-static void* par_worker(void* arg) {
-    (void)arg;
+static __thread int t_in_worker = 0;
+static __thread int t_worker_id = 0;
+
+static void pool_drain(void) {
     for (;;) {
-        const int s = __atomic_fetch_add(&g_par.next, g_par.chunk, __ATOMIC_RELAXED);
-        if (s >= g_par.n) break;
-        const int e = s + g_par.chunk < g_par.n ? s + g_par.chunk : g_par.n;
-        for (int i = s; i < e; i++) g_par.body(i);
+        const int s = __atomic_fetch_add(&g_pool.next, g_pool.chunk, __ATOMIC_RELAXED);
+        if (s >= g_pool.n) break;
+        const int e = s + g_pool.chunk < g_pool.n ? s + g_pool.chunk : g_pool.n;
+        for (int i = s; i < e; i++) g_pool.body(g_pool.ctx, i);
     }
+}
+static void* pool_worker(void* arg) {
+    const int id = (int)(intptr_t)arg;
+    t_in_worker = 1;
+    t_worker_id = id;
+    unsigned seen = 0;
+    pthread_mutex_lock(&g_pool.mu);
+    for (;;) {
+        while (!g_pool.quit && g_pool.gen == seen) pthread_cond_wait(&g_pool.cv_work, &g_pool.mu);
+        if (g_pool.quit) break;
+        seen = g_pool.gen;
+        const int take = id <= g_pool.max_workers;
+        pthread_mutex_unlock(&g_pool.mu);
+        if (take) pool_drain();
+        pthread_mutex_lock(&g_pool.mu);
+        if (--g_pool.active == 0) pthread_cond_signal(&g_pool.cv_done);
+    }
+    pthread_mutex_unlock(&g_pool.mu);
     return NULL;
+}
+static void pool_stop(void) {
+    if (!g_pool.n_workers) return;
+    pthread_mutex_lock(&g_pool.mu);
+    g_pool.quit = 1;
+    pthread_cond_broadcast(&g_pool.cv_work);
+    pthread_mutex_unlock(&g_pool.mu);
+    for (int t = 0; t < g_pool.n_workers; t++) pthread_join(g_pool.th[t], NULL);
+    g_pool.n_workers = 0;
+    g_pool.quit = 0;
 }
 int ref_set_threads(int n) {
     if (n <= 0) n = (int)sysconf(_SC_NPROCESSORS_ONLN);
     if (n > 256) n = 256;
     if (n < 1) n = 1;
+    if (n == g_threads && g_pool.n_workers == n - 1) return n;
+    pool_stop();
     g_threads = n;
+    cpu_set_t mask;
+    int cpus[1024], nc = 0;
+    if (sched_getaffinity(0, sizeof(mask), &mask) == 0)
+        for (int c = 0; c < CPU_SETSIZE && nc < 1024; c++)
+            if (CPU_ISSET(c, &mask)) cpus[nc++] = c;
+    for (int t = 0; t < n - 1; t++) {
+        pthread_create(&g_pool.th[t], NULL, pool_worker, (void*)(intptr_t)(t + 1));
+        if (nc > 1) { /* worker t+1 -> CPU (t+1) mod nc; the caller keeps whatever CPU it has */
+            cpu_set_t one;
+            CPU_ZERO(&one);
+            CPU_SET(cpus[(t + 1) % nc], &one);
+            pthread_setaffinity_np(g_pool.th[t], sizeof(one), &one);
+        }
+    }
+    g_pool.n_workers = n - 1;
     return n;
 }
 int ref_num_threads(void) { return g_threads ? g_threads : ref_set_threads(0); }
-static void par_for(int n, int chunk, ParBody body) {
-    const int T = ref_num_threads();
-    g_par.body = body; g_par.n = n; g_par.chunk = chunk; g_par.next = 0;
-    pthread_t th[256];
-    const int nt = T < n ? T : (n > 0 ? n : 1);
-    for (int t = 1; t < nt; t++) pthread_create(&th[t], NULL, par_worker, NULL);
-    par_worker(NULL);
-    for (int t = 1; t < nt; t++) pthread_join(th[t], NULL);
+void ref_pool_shutdown(void) { pool_stop(); g_threads = 0; }
+static void par_for(int n, int chunk, ParBody body, void* ctx) {
+    if (t_in_worker || ref_num_threads() == 1 || n <= chunk) {
+        for (int i = 0; i < n; i++) body(ctx, i);
+        return;
+    }
+    pthread_mutex_lock(&g_pool.mu);
+    g_pool.body = body; g_pool.ctx = ctx; g_pool.n = n; g_pool.chunk = chunk; g_pool.next = 0;
+    g_pool.max_workers = g_pool.n_workers;
+    g_pool.active = g_pool.n_workers;
+    g_pool.gen++;
+    pthread_cond_broadcast(&g_pool.cv_work);
+    pthread_mutex_unlock(&g_pool.mu);
+    t_in_worker = 1; /* nested par_for calls made by the body on this thread run inline too */
+    pool_drain();
+    t_in_worker = 0;
+    pthread_mutex_lock(&g_pool.mu);
+    while (g_pool.active) pthread_cond_wait(&g_pool.cv_done, &g_pool.mu);
+    pthread_mutex_unlock(&g_pool.mu);
 }
 
 /* ---- tier selection ------------------------------------------------------------------------------ */
@@ -78,6 +149,7 @@ int ref_set_tier(int avx2) {
     svt_aom_quantize_b                        = svt_aom_quantize_b_avx2;
     svt_av1_quantize_b_qm                     = svt_av1_quantize_b_qm_avx2;
     svt_cdef_filter_block                     = svt_cdef_filter_block_avx2;
+    svt_cdef_filter_block_8xn_16              = svt_cdef_filter_block_8xn_16_avx2; /* called BY the AVX2 filter (common_dsp_rtcd.c:819) */
     svt_aom_cdef_find_dir                     = svt_aom_cdef_find_dir_avx2;
     svt_aom_cdef_find_dir_dual                = svt_aom_cdef_find_dir_dual_avx2;
     svt_compute_cdef_dist_8bit                = svt_aom_compute_cdef_dist_8bit_avx2;
@@ -85,6 +157,52 @@ int ref_set_tier(int avx2) {
     svt_aom_copy_rect8_8bit_to_16bit          = svt_aom_copy_rect8_8bit_to_16bit_avx2;
     svt_av1_compute_stats                     = svt_av1_compute_stats_avx2;
     svt_av1_wiener_convolve_add_src           = svt_av1_wiener_convolve_add_src_avx2;
+    /* 8-bit inverse transform: the intrinsics-only AVX2 implementation the reference itself binds when the
+     * dav1d NASM kernels cannot be used (common_dsp_rtcd.c:522-523) */
+    svt_av1_inv_txfm_add                      = svt_av1_inv_txfm_add_avx2;
+    /* 4-point and rectangular forward transforms (aom_dsp_rtcd.c:421-439) */
+    svt_av1_fwd_txfm2d_4x4   = svt_av1_fwd_txfm2d_4x4_sse4_1;
+    svt_av1_fwd_txfm2d_4x8   = svt_av1_fwd_txfm2d_4x8_avx2;
+    svt_av1_fwd_txfm2d_4x16  = svt_av1_fwd_txfm2d_4x16_avx2;
+    svt_av1_fwd_txfm2d_8x4   = svt_av1_fwd_txfm2d_8x4_avx2;
+    svt_av1_fwd_txfm2d_8x16  = svt_av1_fwd_txfm2d_8x16_avx2;
+    svt_av1_fwd_txfm2d_8x32  = svt_av1_fwd_txfm2d_8x32_avx2;
+    svt_av1_fwd_txfm2d_16x4  = svt_av1_fwd_txfm2d_16x4_avx2;
+    svt_av1_fwd_txfm2d_16x8  = svt_av1_fwd_txfm2d_16x8_avx2;
+    svt_av1_fwd_txfm2d_16x32 = svt_av1_fwd_txfm2d_16x32_avx2;
+    svt_av1_fwd_txfm2d_16x64 = svt_av1_fwd_txfm2d_16x64_avx2;
+    svt_av1_fwd_txfm2d_32x8  = svt_av1_fwd_txfm2d_32x8_avx2;
+    svt_av1_fwd_txfm2d_32x16 = svt_av1_fwd_txfm2d_32x16_avx2;
+    svt_av1_fwd_txfm2d_32x64 = svt_av1_fwd_txfm2d_32x64_avx2;
+    svt_av1_fwd_txfm2d_64x16 = svt_av1_fwd_txfm2d_64x16_avx2;
+    svt_av1_fwd_txfm2d_64x32 = svt_av1_fwd_txfm2d_64x32_avx2;
+    /* high bit depth (10-bit configurations) */
+    svt_aom_highbd_quantize_b                 = svt_aom_highbd_quantize_b_avx2;
+    svt_av1_highbd_quantize_fp                = svt_av1_highbd_quantize_fp_avx2;
+    svt_av1_highbd_quantize_fp_qm             = svt_av1_highbd_quantize_fp_qm_avx2;
+    svt_av1_compute_stats_highbd              = svt_av1_compute_stats_highbd_avx2;
+    svt_av1_highbd_wiener_convolve_add_src    = svt_av1_highbd_wiener_convolve_add_src_avx2;
+    /* 16-bit inverse transforms: the intrinsics (non-dav1d) AVX2 functions of highbd_inv_txfm_avx2.c for the
+     * square sizes, the SSE4.1 intrinsics the rtcd table lists for the rest (common_dsp_rtcd.c:501-519) */
+    svt_av1_inv_txfm2d_add_4x4   = svt_av1_inv_txfm2d_add_4x4_avx2;
+    svt_av1_inv_txfm2d_add_8x8   = svt_av1_inv_txfm2d_add_8x8_avx2;
+    svt_av1_inv_txfm2d_add_16x16 = svt_av1_inv_txfm2d_add_16x16_avx2;
+    svt_av1_inv_txfm2d_add_32x32 = svt_av1_inv_txfm2d_add_32x32_avx2;
+    svt_av1_inv_txfm2d_add_64x64 = svt_av1_inv_txfm2d_add_64x64_avx2;
+    svt_av1_inv_txfm2d_add_4x8   = svt_av1_inv_txfm2d_add_4x8_sse4_1;
+    svt_av1_inv_txfm2d_add_8x4   = svt_av1_inv_txfm2d_add_8x4_sse4_1;
+    svt_av1_inv_txfm2d_add_4x16  = svt_av1_inv_txfm2d_add_4x16_sse4_1;
+    svt_av1_inv_txfm2d_add_16x4  = svt_av1_inv_txfm2d_add_16x4_sse4_1;
+    svt_av1_inv_txfm2d_add_8x16  = svt_av1_highbd_inv_txfm_add_avx2;
+    svt_av1_inv_txfm2d_add_16x8  = svt_av1_highbd_inv_txfm_add_avx2;
+    svt_av1_inv_txfm2d_add_8x32  = svt_av1_highbd_inv_txfm_add_avx2;
+    svt_av1_inv_txfm2d_add_32x8  = svt_av1_highbd_inv_txfm_add_avx2;
+    svt_av1_inv_txfm2d_add_16x32 = svt_av1_highbd_inv_txfm_add_avx2;
+    svt_av1_inv_txfm2d_add_32x16 = svt_av1_highbd_inv_txfm_add_avx2;
+    svt_av1_inv_txfm2d_add_16x64 = svt_av1_highbd_inv_txfm_add_avx2;
+    svt_av1_inv_txfm2d_add_64x16 = svt_av1_highbd_inv_txfm_add_avx2;
+    svt_av1_inv_txfm2d_add_32x64 = svt_av1_highbd_inv_txfm_add_avx2;
+    svt_av1_inv_txfm2d_add_64x32 = svt_av1_highbd_inv_txfm_add_avx2;
     return 1;
 }
 
@@ -135,16 +253,16 @@ static void fullpel_b64(const uint8_t* src, uint32_t ss, const uint8_t* ref, uin
     }
 }
 
-static struct { const RefMePicture* cur; const RefMePicture* refs; const RefMeParams* prm; int n_refs; uint32_t* best_sad; uint32_t* best_mv; int16_t* hme_centre; uint64_t* hme_sad; } g_ref_me_picture;
-static void ref_me_picture_body(int i) {
-    const RefMePicture* cur = g_ref_me_picture.cur;
-    const RefMePicture* refs = g_ref_me_picture.refs;
-    const RefMeParams* prm = g_ref_me_picture.prm;
-    int n_refs = g_ref_me_picture.n_refs;
-    uint32_t* best_sad = g_ref_me_picture.best_sad;
-    uint32_t* best_mv = g_ref_me_picture.best_mv;
-    int16_t* hme_centre = g_ref_me_picture.hme_centre;
-    uint64_t* hme_sad = g_ref_me_picture.hme_sad;
+typedef struct { const RefMePicture* cur; const RefMePicture* refs; const RefMeParams* prm; int n_refs; uint32_t* best_sad; uint32_t* best_mv; int16_t* hme_centre; uint64_t* hme_sad; } MeCtx;
+static void ref_me_picture_body(void* vctx, int i) {
+    const MeCtx* c = (const MeCtx*)vctx;
+    const RefMePicture* cur = c->cur;
+    const RefMePicture* refs = c->refs;
+    const RefMeParams* prm = c->prm;
+    uint32_t* best_sad = c->best_sad;
+    uint32_t* best_mv = c->best_mv;
+    int16_t* hme_centre = c->hme_centre;
+    uint64_t* hme_sad = c->hme_sad;
     const int W = cur->width[2], H = cur->height[2], b64_w = (W + 63) >> 6, b64_h = (H + 63) >> 6, nb = b64_w * b64_h;
     {
         const int r = i / nb, b = i % nb, bx = b % b64_w, by = b / b64_w;
@@ -230,23 +348,16 @@ static void ref_me_picture_body(int i) {
 }
 void ref_me_picture(const RefMePicture* cur, const RefMePicture* refs, const RefMeParams* prm, int n_refs, uint32_t* best_sad,
                     uint32_t* best_mv, int16_t* hme_centre, uint64_t* hme_sad) {
-    g_ref_me_picture.cur = cur;
-    g_ref_me_picture.refs = refs;
-    g_ref_me_picture.prm = prm;
-    g_ref_me_picture.n_refs = n_refs;
-    g_ref_me_picture.best_sad = best_sad;
-    g_ref_me_picture.best_mv = best_mv;
-    g_ref_me_picture.hme_centre = hme_centre;
-    g_ref_me_picture.hme_sad = hme_sad;
+    MeCtx c = {cur, refs, prm, n_refs, best_sad, best_mv, hme_centre, hme_sad};
     const int W = cur->width[2], H = cur->height[2], b64_w = (W + 63) >> 6, b64_h = (H + 63) >> 6, nb = b64_w * b64_h;
-    par_for(n_refs * nb, 4, ref_me_picture_body);
-
+    par_for(n_refs * nb, 4, ref_me_picture_body, &c);
 }
 
 
 /* ---- transform / quantize / inverse over a block list ---------------------------------------------
  * the trio of svt_aom_estimate_transform -> svt_aom_quantize_inv_quantize -> inverse,
- * one call per block, 8-bit pixels, "fp" quantizer with quantisation matrices (PSY default). */
+ * one call per block; 8-bit or 10-bit pixels (the reference's CONVERT_TO_BYTEPTR disguise for 16-bit
+ * planes, full_loop.c:1843-1846), "fp" quantizer with quantisation matrices (PSY default). */
 typedef struct { uint64_t src_off, dst_off; uint32_t src_stride; uint8_t tx_size, tx_type; uint16_t reserved; } RefFwdItem;
 typedef struct { uint64_t coef_off, pred_off, recon_off; uint32_t pred_stride, recon_stride; uint8_t tx_size, tx_type, bd, reserved; uint32_t reserved2; } RefInvItem;
 typedef struct {
@@ -256,60 +367,68 @@ typedef struct {
 static const int TXW[19] = {4, 8, 16, 32, 64, 4, 8, 8, 16, 16, 32, 32, 64, 4, 16, 8, 32, 16, 64};
 static const int TXH[19] = {4, 8, 16, 32, 64, 8, 4, 16, 8, 32, 16, 64, 32, 16, 4, 32, 8, 64, 16};
 
-static void fwd_one(int16_t* in, int32_t* out, uint32_t stride, int ty, int sz) {
+static void fwd_one(int16_t* in, int32_t* out, uint32_t stride, int ty, int sz, int bd) {
     switch (sz) {
-    case 0: svt_av1_transform_two_d_4x4_c(in, out, stride, ty, 8); break; /* no intrinsics-only AVX2 4x4 */
-    case 1: svt_av1_fwd_txfm2d_8x8(in, out, stride, ty, 8); break;
-    case 2: svt_av1_fwd_txfm2d_16x16(in, out, stride, ty, 8); break;
-    case 3: svt_av1_fwd_txfm2d_32x32(in, out, stride, ty, 8); break;
-    case 4: svt_av1_fwd_txfm2d_64x64(in, out, stride, ty, 8); break;
-    case 5: svt_av1_fwd_txfm2d_4x8(in, out, stride, ty, 8); break;
-    case 6: svt_av1_fwd_txfm2d_8x4(in, out, stride, ty, 8); break;
-    case 7: svt_av1_fwd_txfm2d_8x16(in, out, stride, ty, 8); break;
-    case 8: svt_av1_fwd_txfm2d_16x8(in, out, stride, ty, 8); break;
-    case 9: svt_av1_fwd_txfm2d_16x32(in, out, stride, ty, 8); break;
-    case 10: svt_av1_fwd_txfm2d_32x16(in, out, stride, ty, 8); break;
-    case 11: svt_av1_fwd_txfm2d_32x64(in, out, stride, ty, 8); break;
-    case 12: svt_av1_fwd_txfm2d_64x32(in, out, stride, ty, 8); break;
-    case 13: svt_av1_fwd_txfm2d_4x16(in, out, stride, ty, 8); break;
-    case 14: svt_av1_fwd_txfm2d_16x4(in, out, stride, ty, 8); break;
-    case 15: svt_av1_fwd_txfm2d_8x32(in, out, stride, ty, 8); break;
-    case 16: svt_av1_fwd_txfm2d_32x8(in, out, stride, ty, 8); break;
-    case 17: svt_av1_fwd_txfm2d_16x64(in, out, stride, ty, 8); break;
-    default: svt_av1_fwd_txfm2d_64x16(in, out, stride, ty, 8); break;
+    case 0: svt_av1_fwd_txfm2d_4x4(in, out, stride, ty, bd); break;
+    case 1: svt_av1_fwd_txfm2d_8x8(in, out, stride, ty, bd); break;
+    case 2: svt_av1_fwd_txfm2d_16x16(in, out, stride, ty, bd); break;
+    case 3: svt_av1_fwd_txfm2d_32x32(in, out, stride, ty, bd); break;
+    case 4: svt_av1_fwd_txfm2d_64x64(in, out, stride, ty, bd); break;
+    case 5: svt_av1_fwd_txfm2d_4x8(in, out, stride, ty, bd); break;
+    case 6: svt_av1_fwd_txfm2d_8x4(in, out, stride, ty, bd); break;
+    case 7: svt_av1_fwd_txfm2d_8x16(in, out, stride, ty, bd); break;
+    case 8: svt_av1_fwd_txfm2d_16x8(in, out, stride, ty, bd); break;
+    case 9: svt_av1_fwd_txfm2d_16x32(in, out, stride, ty, bd); break;
+    case 10: svt_av1_fwd_txfm2d_32x16(in, out, stride, ty, bd); break;
+    case 11: svt_av1_fwd_txfm2d_32x64(in, out, stride, ty, bd); break;
+    case 12: svt_av1_fwd_txfm2d_64x32(in, out, stride, ty, bd); break;
+    case 13: svt_av1_fwd_txfm2d_4x16(in, out, stride, ty, bd); break;
+    case 14: svt_av1_fwd_txfm2d_16x4(in, out, stride, ty, bd); break;
+    case 15: svt_av1_fwd_txfm2d_8x32(in, out, stride, ty, bd); break;
+    case 16: svt_av1_fwd_txfm2d_32x8(in, out, stride, ty, bd); break;
+    case 17: svt_av1_fwd_txfm2d_16x64(in, out, stride, ty, bd); break;
+    default: svt_av1_fwd_txfm2d_64x16(in, out, stride, ty, bd); break;
     }
 }
 
+typedef struct {
+    const int16_t* residual; int32_t *coeff, *q, *dq; const int16_t *scan, *iscan; const uint8_t* qm;
+    const RefFwdItem* fwd; const RefQuantItem* qi; const RefInvItem* inv; uint16_t* eobs;
+    const void* pred; void* recon; int bd;
+} TxCtx;
 
-static struct { const int16_t* residual; int32_t* coeff; const RefFwdItem* items; } g_fwd;
-static void fwd_body(int i) {
-    const RefFwdItem* it = &g_fwd.items[i];
+static void fwd_body(void* vctx, int i) {
+    const TxCtx* c = (const TxCtx*)vctx;
+    const RefFwdItem* it = &c->fwd[i];
     const int W = TXW[it->tx_size], H = TXH[it->tx_size];
     if ((it->reserved & 1) && (W > 32 || H > 32)) {
         /* packed output: the re-pack half of svt_handle_transform64x64 & co (transforms.c:2374-2542) */
         DECLARE_ALIGNED(64, int32_t, tmp[64 * 64]);
         const int Wp = W > 32 ? 32 : W, Hp = H > 32 ? 32 : H;
-        fwd_one((int16_t*)g_fwd.residual + it->src_off, tmp, it->src_stride, it->tx_type, it->tx_size);
-        for (int r = 0; r < Hp; r++) memcpy(g_fwd.coeff + it->dst_off + (size_t)r * Wp, tmp + (size_t)r * W, (size_t)Wp * sizeof(int32_t));
+        fwd_one((int16_t*)c->residual + it->src_off, tmp, it->src_stride, it->tx_type, it->tx_size, c->bd);
+        for (int r = 0; r < Hp; r++) memcpy(c->coeff + it->dst_off + (size_t)r * Wp, tmp + (size_t)r * W, (size_t)Wp * sizeof(int32_t));
         return;
     }
-    fwd_one((int16_t*)g_fwd.residual + it->src_off, g_fwd.coeff + it->dst_off, it->src_stride, it->tx_type, it->tx_size);
+    fwd_one((int16_t*)c->residual + it->src_off, c->coeff + it->dst_off, it->src_stride, it->tx_type, it->tx_size, c->bd);
 }
-void ref_fwd_txfm_batch(const int16_t* residual, int32_t* coeff, const RefFwdItem* items, int n) {
-    g_fwd.residual = residual; g_fwd.coeff = coeff; g_fwd.items = items;
-    par_for(n, 64, fwd_body);
+void ref_fwd_txfm_batch_bd(const int16_t* residual, int32_t* coeff, const RefFwdItem* items, int n, int bd) {
+    TxCtx c;
+    memset(&c, 0, sizeof(c));
+    c.residual = residual; c.coeff = coeff; c.fwd = items; c.bd = bd;
+    par_for(n, 64, fwd_body, &c);
 }
+void ref_fwd_txfm_batch(const int16_t* residual, int32_t* coeff, const RefFwdItem* items, int n) { ref_fwd_txfm_batch_bd(residual, coeff, items, n, 8); }
 
-static struct { const int32_t* coeff; int32_t *q, *dq; const int16_t *scan, *iscan; const uint8_t* qm; const RefQuantItem* items; uint16_t* eobs; } g_q;
-static void quant_body(int i) {
-    const int32_t* coeff = g_q.coeff;
-    int32_t *q = g_q.q, *dq = g_q.dq;
-    uint16_t* eobs = g_q.eobs;
-    const RefQuantItem* it = &g_q.items[i];
-    const uint8_t* wm = it->qm_off == 0xffffffffu ? NULL : g_q.qm + it->qm_off;
-    const uint8_t* im = it->iqm_off == 0xffffffffu ? NULL : g_q.qm + it->iqm_off;
-    const int16_t* sc = g_q.scan + it->scan_off;
-    const int16_t* isc = g_q.iscan + it->scan_off; /* the SIMD tiers derive eob from the inverse scan */
+static void quant_body(void* vctx, int i) {
+    const TxCtx* c = (const TxCtx*)vctx;
+    const int32_t* coeff = c->coeff;
+    int32_t *q = c->q, *dq = c->dq;
+    uint16_t* eobs = c->eobs;
+    const RefQuantItem* it = &c->qi[i];
+    const uint8_t* wm = it->qm_off == 0xffffffffu ? NULL : c->qm + it->qm_off;
+    const uint8_t* im = it->iqm_off == 0xffffffffu ? NULL : c->qm + it->iqm_off;
+    const int16_t* sc = c->scan + it->scan_off;
+    const int16_t* isc = c->iscan + it->scan_off; /* the SIMD tiers derive eob from the inverse scan */
     /* MacroblockPlane tables are int16[8] = {DC, AC x 7}; the SIMD tiers load all eight lanes */
     DECLARE_ALIGNED(16, int16_t, zbin[8]);
     DECLARE_ALIGNED(16, int16_t, round[8]);
@@ -339,33 +458,43 @@ static void quant_body(int i) {
     else if (it->mode == 1)
         svt_aom_highbd_quantize_b(coeff + it->coeff_off, it->n_coeffs, zbin, round, quant, quant_shift, q + it->q_off,
                                   dq + it->dq_off, dequant, &eobs[i], sc, isc, wm, im, it->log_scale);
-    else
+    else if (wm || im)
         svt_av1_highbd_quantize_fp_qm(coeff + it->coeff_off, it->n_coeffs, zbin, round, quant, quant_shift, q + it->q_off,
                                       dq + it->dq_off, dequant, &eobs[i], sc, isc, wm, im, it->log_scale);
+    else
+        svt_av1_highbd_quantize_fp(coeff + it->coeff_off, it->n_coeffs, zbin, round, quant, quant_shift, q + it->q_off,
+                                   dq + it->dq_off, dequant, &eobs[i], sc, isc, it->log_scale);
 }
 void ref_quant_batch(const int32_t* coeff, int32_t* q, int32_t* dq, const int16_t* scan, const int16_t* iscan, const uint8_t* qm,
                      const RefQuantItem* items, int n, uint16_t* eobs) {
-    g_q.coeff = coeff; g_q.q = q; g_q.dq = dq; g_q.scan = scan; g_q.iscan = iscan; g_q.qm = qm; g_q.items = items; g_q.eobs = eobs;
-    par_for(n, 64, quant_body);
+    TxCtx c;
+    memset(&c, 0, sizeof(c));
+    c.coeff = (int32_t*)coeff; c.q = q; c.dq = dq; c.scan = scan; c.iscan = iscan; c.qm = qm; c.qi = items; c.eobs = eobs;
+    par_for(n, 64, quant_body, &c);
 }
 
-static struct { const int32_t* coeff; const uint8_t* pred; uint8_t* recon; const RefInvItem* items; } g_inv;
-static void inv_body(int i) {
-    const RefInvItem* it = &g_inv.items[i];
-    TxfmParam tp;
-    memset(&tp, 0, sizeof(tp));
-    tp.tx_type = it->tx_type;
-    tp.tx_size = it->tx_size;
-    tp.eob = TXW[it->tx_size] * TXH[it->tx_size]; /* full block */
-    if (tp.eob > 1024) tp.eob = 1024;
-    tp.bd = 8;
-    tp.is_hbd = 1;
-    svt_av1_inv_txfm_add((const TranLow*)(g_inv.coeff + it->coef_off), (uint8_t*)g_inv.pred + it->pred_off, (int32_t)it->pred_stride,
-                         g_inv.recon + it->recon_off, (int32_t)it->recon_stride, &tp);
+/* svt_aom_inv_transform_recon8bit / svt_aom_inv_transform_recon (inv_transforms.c:3087,3148): the reference's own
+ * wrappers; read and write planes differ, so they pass the maximum eob themselves */
+static void inv_body(void* vctx, int i) {
+    const TxCtx* c = (const TxCtx*)vctx;
+    const RefInvItem* it = &c->inv[i];
+    if (c->bd == 8)
+        svt_aom_inv_transform_recon8bit((int32_t*)c->dq + it->coef_off, (uint8_t*)c->pred + it->pred_off, it->pred_stride,
+                                        (uint8_t*)c->recon + it->recon_off, it->recon_stride, (TxSize)it->tx_size, (TxType)it->tx_type,
+                                        PLANE_TYPE_Y, 0, 0);
+    else
+        svt_aom_inv_transform_recon((int32_t*)c->dq + it->coef_off, CONVERT_TO_BYTEPTR((uint16_t*)c->pred + it->pred_off), it->pred_stride,
+                                    CONVERT_TO_BYTEPTR((uint16_t*)c->recon + it->recon_off), it->recon_stride, (TxSize)it->tx_size,
+                                    (uint32_t)c->bd, (TxType)it->tx_type, PLANE_TYPE_Y, 0, 0);
+}
+void ref_inv_txfm_batch_bd(const int32_t* coeff, const void* pred, void* recon, const RefInvItem* items, int n, int bd) {
+    TxCtx c;
+    memset(&c, 0, sizeof(c));
+    c.dq = (int32_t*)coeff; c.pred = pred; c.recon = recon; c.inv = items; c.bd = bd;
+    par_for(n, 64, inv_body, &c);
 }
 void ref_inv_txfm_batch_8bit(const int32_t* coeff, const uint8_t* pred, uint8_t* recon, const RefInvItem* items, int n) {
-    g_inv.coeff = coeff; g_inv.pred = pred; g_inv.recon = recon; g_inv.items = items;
-    par_for(n, 64, inv_body);
+    ref_inv_txfm_batch_bd(coeff, pred, recon, items, n, 8);
 }
 
 /* ---- CDEF picture search / apply (cdef_seg_search, cdef_process.c:106-352; svt_av1_cdef_frame) ----- */
@@ -374,13 +503,13 @@ typedef struct {
     int32_t recon_stride_y, recon_stride_c, src_stride_y, src_stride_c, width, height, bit_depth, damping, subsampling_factor, reserved;
 } RefCdefFrame;
 
-static void cdef_tile(uint16_t* inbuf, const uint8_t* plane, int stride, int fbr, int fbc, int nvfb, int nhfb, int fbs, int vsz, int hsz) {
+static void cdef_tile(uint16_t* inbuf, const void* plane, int stride, int fbr, int fbc, int nvfb, int nhfb, int fbs, int vsz, int hsz, int is16) {
     uint16_t* in = inbuf + CDEF_VBORDER * CDEF_BSTRIDE + CDEF_HBORDER;
     for (int i = 0; i < CDEF_BSTRIDE * (64 + 2 * CDEF_VBORDER); i++) inbuf[i] = CDEF_VERY_LARGE;
     const int yoff = CDEF_VBORDER * (fbr != 0), xoff = CDEF_HBORDER * (fbc != 0);
     const int ysize = vsz + CDEF_VBORDER * (fbr + 1 < nvfb) + yoff, xsize = hsz + CDEF_HBORDER * (fbc + 1 < nhfb) + xoff;
-    svt_aom_copy_rect8_8bit_to_16bit(&in[-yoff * CDEF_BSTRIDE - xoff], CDEF_BSTRIDE, plane + (ptrdiff_t)(fbr * fbs - yoff) * stride + fbc * fbs - xoff,
-                                     stride, ysize, xsize);
+    svt_aom_copy_sb8_16(&in[-yoff * CDEF_BSTRIDE - xoff], CDEF_BSTRIDE, (const uint8_t*)plane, fbr * fbs - yoff, fbc * fbs - xoff, stride, ysize, xsize,
+                        is16 ? true : false);
 }
 static int cdef_list(const RefCdefFrame* f, const uint8_t* skip8x8, int fbr, int fbc, CdefList* dlist) {
     const int w8 = (f->width + 7) >> 3, h8 = (f->height + 7) >> 3;
@@ -393,15 +522,17 @@ static int cdef_list(const RefCdefFrame* f, const uint8_t* skip8x8, int fbr, int
     return cnt;
 }
 
-static struct { const RefCdefFrame* f; const uint8_t* skip; const int *sy, *su; int ng; uint64_t* mse; uint8_t* dir; int32_t* var; } g_cs;
-static void cdef_search_body(int fb) {
-    const RefCdefFrame* f = g_cs.f;
-    const int ng = g_cs.ng;
-    uint64_t* mse = g_cs.mse;
+typedef struct { const RefCdefFrame* f; const uint8_t* skip; const int *sy, *su; int ng; uint64_t* mse; uint8_t* dir; int32_t* var; } CdefSearchCtx;
+static void cdef_search_body(void* vctx, int fb) {
+    const CdefSearchCtx* c = (const CdefSearchCtx*)vctx;
+    const RefCdefFrame* f = c->f;
+    const int ng = c->ng;
+    uint64_t* mse = c->mse;
+    const int is16 = f->bit_depth > 8, coeff_shift = f->bit_depth - 8, psz = is16 ? 2 : 1;
     const int nhfb = (f->width + 63) >> 6, nvfb = (f->height + 63) >> 6, nfb = nhfb * nvfb;
     const int fbr = fb / nhfb, fbc = fb % nhfb;
     CdefList dlist[64];
-    const int cnt = cdef_list(f, g_cs.skip, fbr, fbc, dlist);
+    const int cnt = cdef_list(f, c->skip, fbr, fbc, dlist);
     if (!cnt) {
         for (int g = 0; g < ng; g++) mse[(size_t)fb * ng + g] = mse[(size_t)(nfb + fb) * ng + g] = 0;
         return;
@@ -417,44 +548,49 @@ static void cdef_search_body(int fb) {
         const uint8_t* src = (const uint8_t*)(pli == 0 ? f->src_y : (pli == 1 ? f->src_cb : f->src_cr));
         const int rs = pli ? f->recon_stride_c : f->recon_stride_y, ss = pli ? f->src_stride_c : f->src_stride_y;
         const int hsz = fbs < pw - fbc * fbs ? fbs : pw - fbc * fbs, vsz = fbs < ph - fbr * fbs ? fbs : ph - fbr * fbs;
-        cdef_tile(inbuf, rec, rs, fbr, fbc, nvfb, nhfb, fbs, vsz, hsz);
+        cdef_tile(inbuf, rec, rs, fbr, fbc, nvfb, nhfb, fbs, vsz, hsz, is16);
         uint16_t* in = inbuf + CDEF_VBORDER * CDEF_BSTRIDE + CDEF_HBORDER;
         int subs = f->subsampling_factor;
         if (subs > (dec ? 1 : 4)) subs = dec ? 1 : 4;
         for (int g = 0; g < ng; g++) {
             uint64_t* m = &mse[(size_t)((pli ? 1 : 0) * nfb + fb) * ng + g];
-            const int sv = pli ? g_cs.su[g] : g_cs.sy[g];
+            const int sv = pli ? c->su[g] : c->sy[g];
             if (sv < 0) { *m = (uint64_t)1040400 * 64; continue; }
             const int pri = sv / CDEF_SEC_STRENGTHS, sec = sv % CDEF_SEC_STRENGTHS;
-            svt_cdef_filter_fb((uint8_t*)tmp_dst, NULL, 0, in, dec, dec, dir, &dirinit, var, pli, dlist, cnt, pri, sec + (sec == 3), f->damping,
-                               f->damping, 0, (uint8_t)subs);
-            const uint64_t d = svt_compute_cdef_dist_8bit(src + (size_t)(fbr * fbs) * ss + fbc * fbs, ss, (uint8_t*)tmp_dst, dlist, cnt,
-                                                          dec ? BLOCK_4X4 : BLOCK_8X8, 0, pli, (uint8_t)subs);
+            svt_cdef_filter_fb(is16 ? NULL : (uint8_t*)tmp_dst, is16 ? tmp_dst : NULL, 0, in, dec, dec, dir, &dirinit, var, pli, dlist, cnt, pri,
+                               sec + (sec == 3), f->damping, f->damping, coeff_shift, (uint8_t)subs);
+            const uint8_t* sp = src + ((size_t)(fbr * fbs) * ss + fbc * fbs) * psz;
+            const uint64_t d = is16 ? svt_compute_cdef_dist_16bit((const uint16_t*)sp, ss, tmp_dst, dlist, cnt, dec ? BLOCK_4X4 : BLOCK_8X8, coeff_shift,
+                                                                  pli, (uint8_t)subs)
+                                    : svt_compute_cdef_dist_8bit(sp, ss, (uint8_t*)tmp_dst, dlist, cnt, dec ? BLOCK_4X4 : BLOCK_8X8, coeff_shift, pli,
+                                                                 (uint8_t)subs);
             if (pli == 2) *m += d * subs;
             else *m = d * subs;
         }
     }
     for (int k = 0; k < cnt; k++) {
-        g_cs.dir[(size_t)fb * 64 + dlist[k].by * 8 + dlist[k].bx] = dir[dlist[k].by][dlist[k].bx];
-        g_cs.var[(size_t)fb * 64 + dlist[k].by * 8 + dlist[k].bx] = var[dlist[k].by][dlist[k].bx];
+        c->dir[(size_t)fb * 64 + dlist[k].by * 8 + dlist[k].bx] = dir[dlist[k].by][dlist[k].bx];
+        c->var[(size_t)fb * 64 + dlist[k].by * 8 + dlist[k].bx] = var[dlist[k].by][dlist[k].bx];
     }
 }
 void ref_cdef_search_frame(const RefCdefFrame* f, const uint8_t* skip8x8, const int* str_y, const int* str_uv, int ng, uint64_t* mse, uint8_t* dir_out,
                            int32_t* var_out) {
-    g_cs.f = f; g_cs.skip = skip8x8; g_cs.sy = str_y; g_cs.su = str_uv; g_cs.ng = ng; g_cs.mse = mse; g_cs.dir = dir_out; g_cs.var = var_out;
-    par_for(((f->width + 63) >> 6) * ((f->height + 63) >> 6), 1, cdef_search_body);
+    CdefSearchCtx c = {f, skip8x8, str_y, str_uv, ng, mse, dir_out, var_out};
+    par_for(((f->width + 63) >> 6) * ((f->height + 63) >> 6), 2, cdef_search_body, &c);
 }
 
-static struct { const RefCdefFrame* f; const uint8_t* skip; const int8_t* idx; const int *ys, *us; uint8_t *oy, *ocb, *ocr; int os_y, os_c; } g_ca;
-static void cdef_apply_body(int fb) {
-    const RefCdefFrame* f = g_ca.f;
+typedef struct { const RefCdefFrame* f; const uint8_t* skip; const int8_t* idx; const int *ys, *us; void *oy, *ocb, *ocr; int os_y, os_c; } CdefApplyCtx;
+static void cdef_apply_body(void* vctx, int fb) {
+    const CdefApplyCtx* c = (const CdefApplyCtx*)vctx;
+    const RefCdefFrame* f = c->f;
+    const int is16 = f->bit_depth > 8, coeff_shift = f->bit_depth - 8;
     const int nhfb = (f->width + 63) >> 6, nvfb = (f->height + 63) >> 6;
     const int fbr = fb / nhfb, fbc = fb % nhfb;
-    if (g_ca.idx[fb] < 0) return;
-    const int ys = g_ca.ys[g_ca.idx[fb]], us = g_ca.us[g_ca.idx[fb]];
+    if (c->idx[fb] < 0) return;
+    const int ys = c->ys[c->idx[fb]], us = c->us[c->idx[fb]];
     if (!ys && !us) return;
     CdefList dlist[64];
-    const int cnt = cdef_list(f, g_ca.skip, fbr, fbc, dlist);
+    const int cnt = cdef_list(f, c->skip, fbr, fbc, dlist);
     if (!cnt) return;
     DECLARE_ALIGNED(32, uint16_t, inbuf[CDEF_INBUF_SIZE]);
     uint8_t dir[CDEF_NBLOCKS][CDEF_NBLOCKS];
@@ -463,60 +599,218 @@ static void cdef_apply_body(int fb) {
     for (int pli = 0; pli < 3; pli++) {
         const int dec = pli ? 1 : 0, fbs = 64 >> dec, pw = f->width >> dec, ph = f->height >> dec;
         const uint8_t* rec = (const uint8_t*)(pli == 0 ? f->recon_y : (pli == 1 ? f->recon_cb : f->recon_cr));
-        uint8_t* out = pli == 0 ? g_ca.oy : (pli == 1 ? g_ca.ocb : g_ca.ocr);
-        const int rs = pli ? f->recon_stride_c : f->recon_stride_y, os = pli ? g_ca.os_c : g_ca.os_y;
+        void* out = pli == 0 ? c->oy : (pli == 1 ? c->ocb : c->ocr);
+        const int rs = pli ? f->recon_stride_c : f->recon_stride_y, os = pli ? c->os_c : c->os_y;
         const int hsz = fbs < pw - fbc * fbs ? fbs : pw - fbc * fbs, vsz = fbs < ph - fbr * fbs ? fbs : ph - fbr * fbs;
-        cdef_tile(inbuf, rec, rs, fbr, fbc, nvfb, nhfb, fbs, vsz, hsz);
+        cdef_tile(inbuf, rec, rs, fbr, fbc, nvfb, nhfb, fbs, vsz, hsz, is16);
         uint16_t* in = inbuf + CDEF_VBORDER * CDEF_BSTRIDE + CDEF_HBORDER;
         const int sv = pli ? us : ys, pri = sv / CDEF_SEC_STRENGTHS, sec = sv % CDEF_SEC_STRENGTHS;
+        const size_t o = (size_t)(fbr * fbs) * os + fbc * fbs;
         if (pli == 0 || pri || sec)
-            svt_cdef_filter_fb(out + (size_t)(fbr * fbs) * os + fbc * fbs, NULL, os, in, dec, dec, dir, &dirinit, var, pli, dlist, cnt, pri,
-                               sec + (sec == 3), f->damping, f->damping, 0, 1);
+            svt_cdef_filter_fb(is16 ? NULL : (uint8_t*)out + o, is16 ? (uint16_t*)out + o : NULL, os, in, dec, dec, dir, &dirinit, var, pli, dlist, cnt,
+                               pri, sec + (sec == 3), f->damping, f->damping, coeff_shift, 1);
     }
 }
-void ref_cdef_apply_frame(const RefCdefFrame* f, const uint8_t* skip8x8, const int8_t* fb_idx, const int* y_str, const int* uv_str, uint8_t* out_y,
-                          uint8_t* out_cb, uint8_t* out_cr, int os_y, int os_c) {
-    g_ca.f = f; g_ca.skip = skip8x8; g_ca.idx = fb_idx; g_ca.ys = y_str; g_ca.us = uv_str; g_ca.oy = out_y; g_ca.ocb = out_cb; g_ca.ocr = out_cr;
-    g_ca.os_y = os_y; g_ca.os_c = os_c;
-    par_for(((f->width + 63) >> 6) * ((f->height + 63) >> 6), 1, cdef_apply_body);
+void ref_cdef_apply_frame(const RefCdefFrame* f, const uint8_t* skip8x8, const int8_t* fb_idx, const int* y_str, const int* uv_str, void* out_y,
+                          void* out_cb, void* out_cr, int os_y, int os_c) {
+    CdefApplyCtx c = {f, skip8x8, fb_idx, y_str, uv_str, out_y, out_cb, out_cr, os_y, os_c};
+    par_for(((f->width + 63) >> 6) * ((f->height + 63) >> 6), 2, cdef_apply_body, &c);
 }
 
 /* ---- Wiener statistics / filter over unit lists ------------------------------------------------------ */
 typedef struct { uint64_t dgd_off, src_off; int32_t dgd_stride, src_stride, h_start, h_end, v_start, v_end, wiener_win, reserved; } RefStatsItem;
 typedef struct { uint64_t src_off, dst_off; int32_t src_stride, dst_stride; uint16_t w, h; uint32_t reserved; int16_t hfilter[8], vfilter[8]; } RefWienerUnit;
 
-static struct { const uint8_t *dgd, *src; const RefStatsItem* items; int64_t *M, *H; } g_st;
-static void stats_body(int i) {
-    int64_t m[WIENER_WIN2], h[WIENER_WIN2 * WIENER_WIN2];
-    const RefStatsItem* it = &g_st.items[i];
-    svt_av1_compute_stats(it->wiener_win, g_st.dgd + it->dgd_off, g_st.src + it->src_off, it->h_start, it->h_end, it->v_start, it->v_end,
-                          it->dgd_stride, it->src_stride, m, h);
+typedef struct { const void *dgd, *src; const RefStatsItem* items; int64_t *M, *H; int bd; } StatsCtx;
+static void stats_body(void* vctx, int i) {
+    const StatsCtx* c = (const StatsCtx*)vctx;
+    DECLARE_ALIGNED(64, int64_t, m[WIENER_WIN2 + 7]);
+    DECLARE_ALIGNED(64, int64_t, h[WIENER_WIN2 * WIENER_WIN2 + 7]);
+    const RefStatsItem* it = &c->items[i];
+    if (c->bd == 8)
+        svt_av1_compute_stats(it->wiener_win, (const uint8_t*)c->dgd + it->dgd_off, (const uint8_t*)c->src + it->src_off, it->h_start, it->h_end,
+                              it->v_start, it->v_end, it->dgd_stride, it->src_stride, m, h);
+    else /* restoration_pick.c:1305-1318: 16-bit planes travel as CONVERT_TO_BYTEPTR disguises */
+        svt_av1_compute_stats_highbd(it->wiener_win, CONVERT_TO_BYTEPTR((const uint16_t*)c->dgd + it->dgd_off),
+                                     CONVERT_TO_BYTEPTR((const uint16_t*)c->src + it->src_off), it->h_start, it->h_end, it->v_start, it->v_end,
+                                     it->dgd_stride, it->src_stride, m, h, (EbBitDepth)c->bd);
     const int w2 = it->wiener_win * it->wiener_win;
-    memcpy(g_st.M + (size_t)i * 49, m, sizeof(int64_t) * w2);
-    memcpy(g_st.H + (size_t)i * 2401, h, sizeof(int64_t) * w2 * w2);
+    memcpy(c->M + (size_t)i * 49, m, sizeof(int64_t) * w2);
+    memcpy(c->H + (size_t)i * 2401, h, sizeof(int64_t) * w2 * w2);
+}
+void ref_compute_stats_batch_bd(const void* dgd, const void* src, const RefStatsItem* items, int n, int64_t* M, int64_t* H, int bd) {
+    StatsCtx c = {dgd, src, items, M, H, bd};
+    par_for(n, 1, stats_body, &c);
 }
 void ref_compute_stats_batch(const uint8_t* dgd, const uint8_t* src, const RefStatsItem* items, int n, int64_t* M, int64_t* H) {
-    g_st.dgd = dgd; g_st.src = src; g_st.items = items; g_st.M = M; g_st.H = H;
-    par_for(n, 1, stats_body);
+    ref_compute_stats_batch_bd(dgd, src, items, n, M, H, 8);
 }
 
-static struct { const uint8_t* src; uint8_t* dst; const RefWienerUnit* units; } g_wu;
-static void wiener_body(int i) {
-    const RefWienerUnit* u = &g_wu.units[i];
+typedef struct { const void* src; void* dst; const RefWienerUnit* units; int bd; } WienerCtx;
+static void wiener_body(void* vctx, int i) {
+    const WienerCtx* c = (const WienerCtx*)vctx;
+    const RefWienerUnit* u = &c->units[i];
     /* the reference derives the kernel base by masking the low address bits (convolve.c:48-56) */
     DECLARE_ALIGNED(256, int16_t, fx[128]);
     DECLARE_ALIGNED(256, int16_t, fy[128]);
     memcpy(fx, u->hfilter, 16);
     memcpy(fy, u->vfilter, 16);
-    ConvolveParams cp;
-    memset(&cp, 0, sizeof(cp));
-    cp.round_0 = WIENER_ROUND0_BITS;
-    cp.round_1 = 2 * FILTER_BITS - cp.round_0;
-    svt_av1_wiener_convolve_add_src(g_wu.src + u->src_off, u->src_stride, g_wu.dst + u->dst_off, u->dst_stride, fx, fy, u->w, u->h, &cp);
+    const ConvolveParams cp = get_conv_params_wiener(c->bd);
+    if (c->bd == 8)
+        svt_av1_wiener_convolve_add_src((const uint8_t*)c->src + u->src_off, u->src_stride, (uint8_t*)c->dst + u->dst_off, u->dst_stride, fx, fy, u->w,
+                                        u->h, &cp);
+    else /* svt_aom_wiener_filter_stripe_highbd, restoration.c */
+        svt_av1_highbd_wiener_convolve_add_src(CONVERT_TO_BYTEPTR((const uint16_t*)c->src + u->src_off), u->src_stride,
+                                               CONVERT_TO_BYTEPTR((uint16_t*)c->dst + u->dst_off), u->dst_stride, fx, fy, u->w, u->h, &cp, c->bd);
 }
-void ref_wiener_units_8bit(const uint8_t* src, uint8_t* dst, const RefWienerUnit* units, int n) {
-    g_wu.src = src; g_wu.dst = dst; g_wu.units = units;
-    par_for(n, 16, wiener_body);
+void ref_wiener_units_bd(const void* src, void* dst, const RefWienerUnit* units, int n, int bd) {
+    WienerCtx c = {src, dst, units, bd};
+    par_for(n, 16, wiener_body, &c);
+}
+void ref_wiener_units_8bit(const uint8_t* src, uint8_t* dst, const RefWienerUnit* units, int n) { ref_wiener_units_bd(src, dst, units, n, 8); }
+
+/* ---- whole frames --------------------------------------------------------------------------------------
+ * One RefFrameJob = every buffer and work list of one frame of hot-path work (bench.py / FrameWorkload).
+ * ref_frame_step runs the frame's calls in path order (each call's loop parallel over the pool when called
+ * from the main thread); ref_frames_run keeps WHOLE FRAMES IN FLIGHT instead, one frame per pool thread, each
+ * worker running its frame's calls serially into its own private output buffers -- how the encoder uses the
+ * host cores (picture-level parallelism, enc_handle.c:770-781). */
+typedef struct RefFrameJob {
+    int32_t width, height, bit_depth, n_refs;
+    const RefMePicture* cur; const RefMePicture* refs; const RefMeParams* prm;
+    uint32_t* me_sad; uint32_t* me_mv; int16_t* me_centre; uint64_t* me_hme_sad;
+    const int16_t* residual; int32_t *coeff, *q, *dq; const int16_t *scan, *iscan; const uint8_t* qm;
+    const RefFwdItem* fwd; const RefQuantItem* qi; const RefInvItem* inv; uint16_t* eobs;
+    int64_t n_tx, n_coeffs;
+    const void* pred; void* recon; void* cdef_out; void* final; const void* src;
+    int64_t padded_elems;          /* pixels of one padded Y|U|V buffer */
+    int64_t plane_off[3];          /* first pixel of each padded plane (including its border) */
+    int32_t plane_stride[3], plane_w[3], plane_h[3], pad;
+    int64_t src_off[3]; int32_t src_stride[3]; int32_t reserved0;
+    const uint8_t* skip; const int32_t *str_y, *str_uv; int32_t n_str, damping, subsampling, reserved1;
+    uint64_t* mse; uint8_t* dir; int32_t* var;
+    const int8_t* fb_idx; const int32_t *apply_y, *apply_uv;
+    const RefStatsItem* stats; int64_t *M, *H; const RefWienerUnit* units; int32_t n_stats, n_units;
+} RefFrameJob;
+
+static void job_cdef_frame(const RefFrameJob* j, RefCdefFrame* f) {
+    const int psz = j->bit_depth > 8 ? 2 : 1;
+    const void** rec[3] = {&f->recon_y, &f->recon_cb, &f->recon_cr};
+    const void** src[3] = {&f->src_y, &f->src_cb, &f->src_cr};
+    for (int p = 0; p < 3; p++) {
+        *rec[p] = (const uint8_t*)j->recon + (size_t)(j->plane_off[p] + (int64_t)j->pad * j->plane_stride[p] + j->pad) * psz;
+        *src[p] = (const uint8_t*)j->src + (size_t)j->src_off[p] * psz;
+    }
+    f->recon_stride_y = j->plane_stride[0]; f->recon_stride_c = j->plane_stride[1];
+    f->src_stride_y = j->src_stride[0]; f->src_stride_c = j->src_stride[1];
+    f->width = j->width; f->height = j->height; f->bit_depth = j->bit_depth; f->damping = j->damping; f->subsampling_factor = j->subsampling;
+    f->reserved = 0;
+}
+/* svt_extend_frame: replicate the picture edge into the padded border (restoration reads beyond the edge) */
+static void job_extend(const RefFrameJob* j, void* buf) {
+    const int psz = j->bit_depth > 8 ? 2 : 1, pad = j->pad;
+    for (int p = 0; p < 3; p++) {
+        const int w = j->plane_w[p], h = j->plane_h[p], st = j->plane_stride[p];
+        uint8_t* base = (uint8_t*)buf + (size_t)j->plane_off[p] * psz;
+        for (int y = 0; y < h; y++) {
+            uint8_t* row = base + ((size_t)(pad + y) * st) * psz;
+            if (psz == 1) {
+                memset(row, row[pad], pad);
+                memset(row + pad + w, row[pad + w - 1], pad);
+            } else {
+                uint16_t* r16 = (uint16_t*)row;
+                for (int x = 0; x < pad; x++) { r16[x] = r16[pad]; r16[pad + w + x] = r16[pad + w - 1]; }
+            }
+        }
+        const size_t rb = (size_t)(w + 2 * pad) * psz;
+        for (int y = 0; y < pad; y++) {
+            memcpy(base + ((size_t)y * st) * psz, base + ((size_t)pad * st) * psz, rb);
+            memcpy(base + ((size_t)(pad + h + y) * st) * psz, base + ((size_t)(pad + h - 1) * st) * psz, rb);
+        }
+    }
+}
+static void tx_chain_body(void* vctx, int i) { fwd_body(vctx, i); quant_body(vctx, i); inv_body(vctx, i); }
+
+static int g_trace = -1;
+#define TRACE(x) do { if (g_trace < 0) g_trace = getenv("REF_TRACE") != NULL; if (g_trace) { fprintf(stderr, "[ref] %s\n", x); fflush(stderr); } } while (0)
+void ref_frame_step(const RefFrameJob* j) {
+    TRACE("me");
+    const int nb = ((j->width + 63) >> 6) * ((j->height + 63) >> 6), psz = j->bit_depth > 8 ? 2 : 1;
+    MeCtx me = {j->cur, j->refs, j->prm, j->n_refs, j->me_sad, j->me_mv, j->me_centre, j->me_hme_sad};
+    par_for(j->n_refs * nb, 4, ref_me_picture_body, &me);
+    TRACE("tx");
+    TxCtx tx = {j->residual, j->coeff, j->q, j->dq, j->scan, j->iscan, j->qm, j->fwd, j->qi, j->inv, j->eobs, j->pred, j->recon, j->bit_depth};
+    par_for((int)j->n_tx, 64, tx_chain_body, &tx); /* per block: transform -> quantise -> inverse, as mode decision / enc-dec do */
+    TRACE("cdef search");
+    RefCdefFrame f;
+    job_cdef_frame(j, &f);
+    CdefSearchCtx cs = {&f, j->skip, j->str_y, j->str_uv, j->n_str, j->mse, j->dir, j->var};
+    par_for(nb, 2, cdef_search_body, &cs);
+    memcpy(j->cdef_out, j->recon, (size_t)j->padded_elems * psz); /* svt_av1_cdef_frame filters in place; the search input is kept */
+    void* outp[3];
+    for (int p = 0; p < 3; p++) outp[p] = (uint8_t*)j->cdef_out + (size_t)(j->plane_off[p] + (int64_t)j->pad * j->plane_stride[p] + j->pad) * psz;
+    TRACE("cdef apply");
+    CdefApplyCtx ca = {&f, j->skip, j->fb_idx, j->apply_y, j->apply_uv, outp[0], outp[1], outp[2], j->plane_stride[0], j->plane_stride[1]};
+    par_for(nb, 2, cdef_apply_body, &ca);
+    TRACE("extend");
+    job_extend(j, j->cdef_out);
+    TRACE("stats");
+    StatsCtx st = {j->cdef_out, j->src, j->stats, j->M, j->H, j->bit_depth};
+    par_for(j->n_stats, 1, stats_body, &st);
+    TRACE("wiener");
+    WienerCtx wu = {j->cdef_out, j->final, j->units, j->bit_depth};
+    par_for(j->n_units, 16, wiener_body, &wu);
+}
+
+/* private output buffers of one pool thread (allocated on first use, grown when a larger job arrives) */
+typedef struct { size_t cap[16]; void* buf[16]; } WorkerBufs;
+static __thread WorkerBufs t_bufs;
+static void* wb(int k, size_t bytes) {
+    if (t_bufs.cap[k] < bytes) {
+        free(t_bufs.buf[k]);
+        if (posix_memalign(&t_bufs.buf[k], 64, bytes + 64)) abort();
+        memset(t_bufs.buf[k], 0, bytes); /* first touch on the worker's own NUMA node */
+        t_bufs.cap[k] = bytes;
+    }
+    return t_bufs.buf[k];
+}
+typedef struct { const RefFrameJob* sets; int n_sets; } FramesCtx;
+static void frame_body(void* vctx, int i) {
+    const FramesCtx* c = (const FramesCtx*)vctx;
+    RefFrameJob j = c->sets[i % c->n_sets];
+    const size_t nb = (size_t)((j.width + 63) >> 6) * ((j.height + 63) >> 6), psz = j.bit_depth > 8 ? 2 : 1;
+    j.me_sad = wb(0, (size_t)j.n_refs * nb * 85 * 4);
+    j.me_mv = wb(1, (size_t)j.n_refs * nb * 85 * 4);
+    j.me_centre = wb(2, (size_t)j.n_refs * nb * 4);
+    j.me_hme_sad = wb(3, (size_t)j.n_refs * nb * 8);
+    j.coeff = wb(4, (size_t)j.n_coeffs * 4);
+    j.q = wb(5, (size_t)j.n_coeffs * 4);
+    j.dq = wb(6, (size_t)j.n_coeffs * 4);
+    j.eobs = wb(7, (size_t)j.n_tx * 2);
+    j.recon = wb(8, (size_t)j.padded_elems * psz);
+    j.cdef_out = wb(9, (size_t)j.padded_elems * psz);
+    j.final = wb(10, (size_t)j.padded_elems * psz);
+    j.mse = wb(11, 2 * nb * (size_t)j.n_str * 8);
+    j.dir = wb(12, nb * 64);
+    j.var = wb(13, nb * 64 * 4);
+    j.M = wb(14, (size_t)j.n_stats * 49 * 8);
+    j.H = wb(15, (size_t)j.n_stats * 2401 * 8);
+    ref_frame_step(&j);
+}
+/* n_frames whole frames, frame i on job set i % n_sets, spread over `n_threads` pool threads (<= 0: all);
+ * returns the wall-clock seconds of the batch */
+double ref_frames_run(const RefFrameJob* sets, int n_sets, int n_frames, int n_threads) {
+    ref_set_threads(n_threads);
+    FramesCtx c = {sets, n_sets};
+    struct timespec t0, t1;
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    if (ref_num_threads() == 1) {
+        for (int i = 0; i < n_frames; i++) frame_body(&c, i);
+    } else {
+        par_for(n_frames, 1, frame_body, &c);
+    }
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    return (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
 }
 
 /* ---- a13 groundwork: one restoration unit through the reference's own stripe loop ------------------------

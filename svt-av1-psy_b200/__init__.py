@@ -25,11 +25,21 @@ if not _os.path.exists(LIB_PATH):
 lib = _ct.CDLL(LIB_PATH)
 
 
-def declared_symbols():
-    """Names of all functions declared SVT_B200_API in include/svt_b200.h."""
+EXPORTS_PATH = _os.path.join(_PKG_DIR, "exports.txt")
+
+
+def header_symbols():
+    """Names of all functions declared in include/svt_b200.h, by preprocessing it (needs gcc: build / test time only)."""
     import subprocess as _sp
     txt = _sp.run(["gcc", "-E", "-P", HEADER_PATH], capture_output=True, text=True, check=True).stdout
     return sorted(set(_re.findall(r"\b(svt_b200_\w+)\s*\(", txt)))
+
+
+def declared_symbols():
+    """The C ABI's function names: exports.txt, written from the header when the library is built
+    (__graft_entry__.build_cuda) and committed, so that importing needs neither gcc nor the header."""
+    with open(EXPORTS_PATH) as f:
+        return sorted(x.strip() for x in f if x.strip())
 
 
 def check_exports():

@@ -107,6 +107,10 @@ hadamard_kernel(const int16_t* __restrict__ src_base, const SvtB200HadamardItem*
     for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
         const SvtB200HadamardItem item = items[it];
         const int n = item.size;
+        if (n != 4 && n != 8 && n != 16 && n != 32) {  // not a Hadamard size: sentinel result, nothing else touched (block-uniform branch)
+            if (threadIdx.x == 0 && satd_out) satd_out[it] = -1;
+            continue;
+        }
         if (threadIdx.x == 0) s_sum = 0;
         for (int i = threadIdx.x; i < n * n; i += blockDim.x)
             s_in[i] = src_base[item.src_off + (size_t)(i / n) * item.src_stride + (i % n)];

@@ -43,7 +43,8 @@ __global__ void downsample_2d_kernel(const uint8_t* __restrict__ in, int in_stri
 }
 // replicate the w x h interior (at (org_x, org_y)) into the surrounding padding (svt_aom_generate_padding);
 // only the border elements are visited: top band, bottom band, then the left/right strips of the interior rows
-__device__ __forceinline__ void pad_border_element(uint8_t* buf, int stride, int w, int h, int org_x, int org_y, int idx) {
+template <typename PIX>
+__device__ __forceinline__ void pad_border_element(PIX* buf, int stride, int w, int h, int org_x, int org_y, int idx) {
     const int tw = w + 2 * org_x, band = org_y * tw;
     int x, y;
     if (idx < 2 * band) {
@@ -379,7 +380,8 @@ __global__ void pad_planes_kernel(const __grid_constant__ PadPlanes pl) {
     const SvtB200PlaneExtent& e = pl.p[blockIdx.y];
     const int n = pad_border_count(e.w, e.h, e.org_x, e.org_y);
     for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += gridDim.x * blockDim.x)
-        pad_border_element(e.buf, e.stride, e.w, e.h, e.org_x, e.org_y, idx);
+        if (e.pixel_bytes == 2) pad_border_element(reinterpret_cast<uint16_t*>(e.buf), e.stride, e.w, e.h, e.org_x, e.org_y, idx);
+        else pad_border_element(e.buf, e.stride, e.w, e.h, e.org_x, e.org_y, idx);
 }
 
 extern "C" int svt_b200_extend_planes_dev(const SvtB200PlaneExtent* planes, int n_planes, void* stream) {

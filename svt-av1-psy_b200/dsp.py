@@ -9,6 +9,7 @@ import ctypes as ct
 import numpy as np
 
 from . import lib
+from .layout import *  # noqa: F401,F403  (struct dtypes, enum values and plane geometry: pure numpy, shared with the CPU arm)
 
 c_u8p = ct.POINTER(ct.c_uint8)
 c_u16p = ct.POINTER(ct.c_uint16)
@@ -35,10 +36,6 @@ class SadSearchItem(ct.Structure):
                 ("skip_search_line", ct.c_uint16), ("reserved", ct.c_uint16)]
 
 
-SAD_ITEM_DTYPE = np.dtype([("src_off", "<u8"), ("ref_off", "<u8"), ("src_stride", "<u4"), ("ref_stride", "<u4"),
-                           ("ref_step", "<u4"), ("block_w", "<u2"), ("block_h", "<u2"), ("sa_w", "<i2"),
-                           ("sa_h", "<i2"), ("skip_search_line", "<u2"), ("reserved", "<u2")])
-SAD_RESULT_DTYPE = np.dtype([("best_sad", "<u4"), ("x", "<i2"), ("y", "<i2")])
 assert SAD_ITEM_DTYPE.itemsize == ct.sizeof(SadSearchItem) == 40
 
 # ------------------------------------------------------------------------------------------------
@@ -123,22 +120,9 @@ def sad_search_batch_host(src_plane, ref_plane, items):
 # ------------------------------------------------------------------------------------------------
 # K5 / K6 transforms
 # ------------------------------------------------------------------------------------------------
-TX_W = [4, 8, 16, 32, 64, 4, 8, 8, 16, 16, 32, 32, 64, 4, 16, 8, 32, 16, 64]
-TX_H = [4, 8, 16, 32, 64, 8, 4, 16, 8, 32, 16, 64, 32, 16, 4, 32, 8, 64, 16]
-TX_NAME = ["%dx%d" % (w, h) for w, h in zip(TX_W, TX_H)]
-TXFM_CLASSES = 5  # SVT_B200_TXFM_CLASSES
 
 
-def txfm_team_class(tx_size):
-    """log2(max(W, H)) - 2: the order key of the transform batch calls (svt_b200_txfm_team_class)."""
-    return {4: 0, 8: 1, 16: 2, 32: 3, 64: 4}[max(TX_W[tx_size], TX_H[tx_size])]
 
-FWD_ITEM_DTYPE = np.dtype([("src_off", "<u8"), ("dst_off", "<u8"), ("src_stride", "<u4"), ("tx_size", "u1"),
-                           ("tx_type", "u1"), ("reserved", "<u2")])
-INV_ITEM_DTYPE = np.dtype([("coef_off", "<u8"), ("pred_off", "<u8"), ("recon_off", "<u8"), ("pred_stride", "<u4"),
-                           ("recon_stride", "<u4"), ("tx_size", "u1"), ("tx_type", "u1"), ("bd", "u1"),
-                           ("reserved", "u1"), ("reserved2", "<u4")])
-assert FWD_ITEM_DTYPE.itemsize == 24 and INV_ITEM_DTYPE.itemsize == 40
 
 lib.svt_b200_fwd_txfm2d_partial.argtypes = [vp, vp, ct.c_uint32, ct.c_int, ct.c_int, ct.c_uint8, ct.c_int]
 lib.svt_b200_fwd_txfm2d_partial.restype = None
@@ -211,15 +195,6 @@ def fwd_txfm_batch_host(residual, coeff, items):
 # ------------------------------------------------------------------------------------------------
 # K7 quantize / dequantize
 # ------------------------------------------------------------------------------------------------
-QUANT_B_LBD, QUANT_B_HBD, QUANT_FP_LBD, QUANT_FP_HBD = 0, 1, 2, 3
-NO_QM = 0xffffffff
-QUANT_ITEM_DTYPE = np.dtype([("coeff_off", "<u8"), ("q_off", "<u8"), ("dq_off", "<u8"), ("scan_off", "<u4"),
-                             ("qm_off", "<u4"), ("iqm_off", "<u4"), ("n_coeffs", "<u4"), ("zbin", "<i2", 2),
-                             ("round", "<i2", 2), ("quant", "<i2", 2), ("quant_shift", "<i2", 2), ("dequant", "<i2", 2),
-                             ("mode", "u1"), ("log_scale", "u1"), ("reserved", "<u2")])
-assert QUANT_ITEM_DTYPE.itemsize == 64
-TRIO_ITEM_DTYPE = np.dtype([("fwd", FWD_ITEM_DTYPE), ("quant", QUANT_ITEM_DTYPE), ("inv", INV_ITEM_DTYPE)])  # SvtB200TrioItem
-assert TRIO_ITEM_DTYPE.itemsize == 128
 lib.svt_b200_txfm_trio_batch_dev.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, ct.POINTER(ct.c_int), vp, ct.c_int, vp]
 lib.svt_b200_txfm_trio_batch_dev.restype = ct.c_int
 _QA = [vp, ct.c_ssize_t, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
@@ -258,11 +233,6 @@ def quantize(name, coeff, tables, scan, qm=None, iqm=None, log_scale=None):
 # ------------------------------------------------------------------------------------------------
 # K4 Hadamard / SATD, K2 SAD pyramid + full-pel search
 # ------------------------------------------------------------------------------------------------
-HADAMARD_ITEM_DTYPE = np.dtype([("src_off", "<u8"), ("coeff_off", "<u8"), ("src_stride", "<u4"), ("size", "<u4")])
-FULLPEL_ITEM_DTYPE = np.dtype([("src_off", "<u8"), ("ref_off", "<u8"), ("src_stride", "<u4"), ("ref_stride", "<u4"),
-                               ("sa_w", "<i2"), ("sa_h", "<i2"), ("org_x", "<i2"), ("org_y", "<i2"), ("sub_sad", "u1"),
-                               ("reserved", "u1", 7)])
-assert HADAMARD_ITEM_DTYPE.itemsize == 24 and FULLPEL_ITEM_DTYPE.itemsize == 40
 for _n in ("4x4", "8x8", "16x16", "32x32"):
     _f = getattr(lib, "svt_b200_aom_hadamard_" + _n)
     _f.argtypes = [vp, ct.c_ssize_t, vp]
@@ -360,12 +330,6 @@ class ConvolveParams(ct.Structure):
                 ("use_dist_wtd_comp_avg", ct.c_int32)]
 
 
-WIENER_UNIT_DTYPE = np.dtype([("src_off", "<u8"), ("dst_off", "<u8"), ("src_stride", "<i4"), ("dst_stride", "<i4"), ("w", "<u2"),
-                              ("h", "<u2"), ("reserved", "<u4"), ("hfilter", "<i2", 8), ("vfilter", "<i2", 8)])
-STATS_ITEM_DTYPE = np.dtype([("dgd_off", "<u8"), ("src_off", "<u8"), ("dgd_stride", "<i4"), ("src_stride", "<i4"),
-                             ("h_start", "<i4"), ("h_end", "<i4"), ("v_start", "<i4"), ("v_end", "<i4"), ("wiener_win", "<i4"),
-                             ("reserved", "<i4")])
-assert WIENER_UNIT_DTYPE.itemsize == 64 and STATS_ITEM_DTYPE.itemsize == 48
 lib.svt_b200_av1_wiener_convolve_add_src.argtypes = [vp, ct.c_ssize_t, vp, ct.c_ssize_t, vp, vp, ct.c_int32, ct.c_int32,
                                                      ct.POINTER(ConvolveParams)]
 lib.svt_b200_av1_wiener_convolve_add_src.restype = None
@@ -384,9 +348,6 @@ lib.svt_b200_compute_stats_batch_dev.restype = ct.c_int
 # ------------------------------------------------------------------------------------------------
 # K10 / K12 self-guided restoration
 # ------------------------------------------------------------------------------------------------
-SGR_UNIT_DTYPE = np.dtype([("dgd_off", "<u8"), ("flt0_off", "<u8"), ("flt1_off", "<u8"), ("dgd_stride", "<i4"), ("flt_stride", "<i4"),
-                           ("w", "<u2"), ("h", "<u2"), ("params_idx", "<u2"), ("reserved", "<u2")])
-assert SGR_UNIT_DTYPE.itemsize == 40
 lib.svt_b200_av1_selfguided_restoration.argtypes = [vp, ct.c_int32, ct.c_int32, ct.c_int32, vp, vp, ct.c_int32, ct.c_int32, ct.c_int32,
                                                     ct.c_int32]
 lib.svt_b200_av1_selfguided_restoration.restype = None
@@ -423,17 +384,6 @@ lib.svt_b200_build_hme_pyramid_dev.restype = ct.c_int
 lib.svt_b200_me_picture_dev.argtypes = [ct.POINTER(MePicture), ct.POINTER(MePicture), ct.POINTER(MeParams), ct.c_int, vp, vp, vp, vp, vp]
 lib.svt_b200_me_picture_dev.restype = ct.c_int
 
-ME_PAD = (16, 32, 72)  # padding of the 1/16, 1/4 and full luma planes (the reference uses 16 / 32 / 64+)
-
-
-def me_plane_shapes(width, height):
-    """[(h_total, w_total, org, w, h)] for levels 0 (1/16), 1 (1/4), 2 (full); strides are 16-byte multiples"""
-    out = []
-    for lvl in range(3):
-        w, h, pad = width >> (2 - lvl), height >> (2 - lvl), ME_PAD[lvl]
-        stride = (w + 2 * pad + 15) & ~15
-        out.append((h + 2 * pad, stride, pad, w, h))
-    return out
 
 
 def me_picture_desc(planes, width, height):
@@ -453,14 +403,13 @@ lib.svt_b200_extend_plane_dev.restype = ct.c_int
 
 class PlaneExtent(ct.Structure):  # SvtB200PlaneExtent
     _fields_ = [("buf", ct.c_void_p), ("stride", ct.c_int32), ("w", ct.c_int32), ("h", ct.c_int32), ("org_x", ct.c_int32),
-                ("org_y", ct.c_int32), ("reserved", ct.c_int32)]
+                ("org_y", ct.c_int32), ("pixel_bytes", ct.c_int32)]
 
 
 lib.svt_b200_extend_planes_dev.argtypes = [ct.POINTER(PlaneExtent), ct.c_int, vp]
 lib.svt_b200_extend_planes_dev.restype = ct.c_int
 
 
-SAD_SIZES = [(128, 128), (128, 64), (64, 128), (64, 64), (64, 32), (64, 16), (32, 64), (32, 32), (32, 16), (32, 8), (16, 64), (16, 32), (16, 16), (16, 8), (16, 4), (8, 32), (8, 16), (8, 8), (8, 4), (4, 16), (4, 8), (4, 4)]  # (width, height) of the svt_aom_sadMxN family
 for _m, _n in SAD_SIZES:
     _f = getattr(lib, "svt_b200_aom_sad%dx%d" % (_m, _n))
     _f.argtypes = [vp, ct.c_int, vp, ct.c_int]

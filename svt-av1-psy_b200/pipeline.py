@@ -25,13 +25,15 @@ class FramePipeline:
         self.tx_counts = (ct.c_int * dsp.TXFM_CLASSES)(*wl.tx_class_counts)
         W, H = wl.width, wl.height
         T = torch
+        self.bd, self.psz = wl.bit_depth, wl.pixel_bytes
+        pix = T.uint8 if self.psz == 1 else T.int16  # torch has no uint16 arithmetic; the planes are only storage here
         # ---- ME: padded pyramids (current + references) -------------------------------------------
         self.cur_planes = [T.zeros((s[0], s[1]), dtype=T.uint8, device=device) for s in wl.me_shapes]
         self.ref_planes = [[T.zeros((s[0], s[1]), dtype=T.uint8, device=device) for s in wl.me_shapes] for _ in range(wl.n_refs)]
         pad = wl.me_shapes[2][2]
         self._full_pad = pad
         for r, ref in enumerate(wl.refs):
-            self._upload_full(self.ref_planes[r], ref[0])
+            self._upload_full(self.ref_planes[r], wl.me_luma(ref))
             d = dsp.me_picture_desc(self.ref_planes[r], W, H)
             assert lib.svt_b200_build_hme_pyramid_dev(ct.byref(d), None) == 0
         self.cur_desc = dsp.me_picture_desc(self.cur_planes, W, H)
@@ -49,12 +51,12 @@ class FramePipeline:
         # ---- TX ---------------------------------------------------------------------------------------
         _, n_flat = wl.flat_offsets()
         _, n_pad = wl.padded_offsets()
-        self.cur_flat = T.zeros(n_flat, dtype=T.uint8, device=device)      # source picture Y|U|V
+        self.cur_flat = T.zeros(n_flat, dtype=pix, device=device)          # source picture Y|U|V
         self.residual = T.zeros(n_flat, dtype=T.int16, device=device)
-        self.pred = T.zeros(n_pad, dtype=T.uint8, device=device)           # padded planes
-        self.recon = T.zeros(n_pad, dtype=T.uint8, device=device)
-        self.cdef_out = T.zeros(n_pad, dtype=T.uint8, device=device)
-        self.final = T.zeros(n_pad, dtype=T.uint8, device=device)
+        self.pred = T.zeros(n_pad, dtype=pix, device=device)               # padded planes
+        self.recon = T.zeros(n_pad, dtype=pix, device=device)
+        self.cdef_out = T.zeros(n_pad, dtype=pix, device=device)
+        self.final = T.zeros(n_pad, dtype=pix, device=device)
         self.coeff = T.zeros(wl.n_coeffs, dtype=T.int32, device=device)
         self.qcoeff = T.zeros_like(self.coeff)
         self.dqcoeff = T.zeros_like(self.coeff)
@@ -80,9 +82,12 @@ class FramePipeline:
         self.M = T.zeros((len(wl.stats_items), 49), dtype=T.int64, device=device)
         self.Hm = T.zeros((len(wl.stats_items), 2401), dtype=T.int64, device=device)
         # ---- host staging for the end-to-end arm ------------------------------------------------------
-        self.h_cur = T.from_numpy(np.concatenate([p.reshape(-1) for p in wl.cur])).pin_memory()
+        as_t = (lambda a: T.from_numpy(a)) if self.psz == 1 else (lambda a: T.from_numpy(a.view(np.int16)))
+        self.h_cur = as_t(np.concatenate([p.reshape(-1) for p in wl.cur])).pin_memory()
         self.h_res = T.from_numpy(np.concatenate([p.reshape(-1) for p in wl.residual])).pin_memory()
-        self.h_pred = T.from_numpy(self._pad_planes(wl.pred)).pin_memory()
+        self.h_pred = as_t(self._pad_planes(wl.pred)).pin_memory()
+        # 10-bit input: the 8-bit luma open-loop ME searches is made by the picture-input stage on the host
+        self.h_luma8 = None if self.psz == 1 else T.from_numpy(np.ascontiguousarray(wl.me_luma(wl.cur))).pin_memory()
         self.h_out = {k: T.empty_like(v, device="cpu").pin_memory() for k, v in
                       dict(me_sad=self.me_sad, me_mv=self.me_mv, q=self.qcoeff, eobs=self.eobs, mse=self.cdef_mse, M=self.M, H=self.Hm,
                            final=self.final).items()}
@@ -93,7 +98,7 @@ class FramePipeline:
     def _pad_planes(self, planes):
         wl = self.wl
         off, n = wl.padded_offsets()
-        buf = np.zeros(n, np.uint8)
+        buf = np.zeros(n, wl.pixel_dtype)
         for p in range(3):
             th, st = wl.padded_shape(p)
             w, h = wl.plane_dims[p]
@@ -117,9 +122,9 @@ class FramePipeline:
         for p in range(3):
             if padded:
                 th, st = wl.padded_shape(p)
-                out.append((flat.data_ptr() + off[p] + wl.PAD * st + wl.PAD, st))
+                out.append((flat.data_ptr() + (off[p] + wl.PAD * st + wl.PAD) * self.psz, st))
             else:
-                out.append((flat.data_ptr() + off[p], wl.plane_dims[p][0]))
+                out.append((flat.data_ptr() + off[p] * self.psz, wl.plane_dims[p][0]))
         return out
 
     def load_inputs(self, stream=None):
@@ -129,8 +134,11 @@ class FramePipeline:
         self.residual.copy_(self.h_res, non_blocking=True)
         self.pred.copy_(self.h_pred, non_blocking=True)
         W, H, pad = self.wl.width, self.wl.height, self._full_pad
-        # the full-resolution luma of the ME pyramid is the padded source picture
-        self.cur_planes[2][pad:pad + H, pad:pad + W].copy_(self.cur_flat[:W * H].view(H, W))
+        # the full-resolution luma of the ME pyramid is the padded (8-bit) source picture
+        if self.psz == 1:
+            self.cur_planes[2][pad:pad + H, pad:pad + W].copy_(self.cur_flat[:W * H].view(H, W))
+        else:
+            self.cur_planes[2][pad:pad + H, pad:pad + W].copy_(self.h_luma8, non_blocking=True)
         s = T.cuda.current_stream().cuda_stream
         assert lib.svt_b200_extend_plane_dev(self.cur_planes[2].data_ptr(), self.cur_planes[2].stride(0), W, H, pad, pad, s) == 0
 
@@ -141,7 +149,7 @@ class FramePipeline:
 
     @property
     def h2d_bytes(self):
-        return self.h_cur.numel() + self.h_res.numel() * 2 + self.h_pred.numel()
+        return (self.h_cur.numel() + self.h_pred.numel()) * self.psz + self.h_res.numel() * 2 + (0 if self.h_luma8 is None else self.h_luma8.numel())
 
     @property
     def d2h_bytes(self):
@@ -159,7 +167,7 @@ class FramePipeline:
     def call_txfm_trio(self, s):
         rc = lib.svt_b200_txfm_trio_batch_dev(self.residual.data_ptr(), self.pred.data_ptr(), self.recon.data_ptr(), self.qcoeff.data_ptr(),
                                               self.dqcoeff.data_ptr(), self.iscan.data_ptr(), self.qm.data_ptr(), self.trio_items.data_ptr(),
-                                              self.tx_counts, self.eobs.data_ptr(), 1, s)
+                                              self.tx_counts, self.eobs.data_ptr(), self.psz, s)
         assert rc == 0
 
     # the same three steps as separate calls (TPL / MD use them individually); results are identical
@@ -174,7 +182,7 @@ class FramePipeline:
 
     def call_inv_txfm(self, s):
         rc = lib.svt_b200_inv_txfm_batch_dev(self.dqcoeff.data_ptr(), self.pred.data_ptr(), self.recon.data_ptr(), self.inv_items.data_ptr(),
-                                             self.tx_counts, 1, s)
+                                             self.tx_counts, self.psz, s)
         assert rc == 0
 
     def cdef_frame(self, recon_flat):
@@ -183,7 +191,7 @@ class FramePipeline:
         (f.recon_y, sy), (f.recon_cb, sc), (f.recon_cr, _) = self.plane_views(recon_flat, True)
         (f.src_y, ssy), (f.src_cb, ssc), (f.src_cr, _) = self.plane_views(self.cur_flat, False)
         f.recon_stride_y, f.recon_stride_c, f.src_stride_y, f.src_stride_c = sy, sc, ssy, ssc
-        f.width, f.height, f.bit_depth, f.damping, f.subsampling_factor = wl.width, wl.height, 8, wl.cdef_damping, wl.cdef_subsampling
+        f.width, f.height, f.bit_depth, f.damping, f.subsampling_factor = wl.width, wl.height, self.bd, wl.cdef_damping, wl.cdef_subsampling
         return f
 
     def call_cdef_search(self, s):
@@ -209,23 +217,23 @@ class FramePipeline:
             for p in range(3):
                 th, st = wl.padded_shape(p)
                 w, h = wl.plane_dims[p]
-                self._extents[p] = dsp.PlaneExtent(self.cdef_out.data_ptr() + off[p], st, w, h, wl.PAD, wl.PAD, 0)
+                self._extents[p] = dsp.PlaneExtent(self.cdef_out.data_ptr() + off[p] * self.psz, st, w, h, wl.PAD, wl.PAD, self.psz)
         assert lib.svt_b200_extend_planes_dev(self._extents, 3, s) == 0
 
     def call_wiener_stats(self, s):
         rc = lib.svt_b200_compute_stats_batch_dev(self.cdef_out.data_ptr(), self.cur_flat.data_ptr(), self.stats_items.data_ptr(),
-                                                  len(self.wl.stats_items), 8, self.M.data_ptr(), self.Hm.data_ptr(), s)
+                                                  len(self.wl.stats_items), self.bd, self.M.data_ptr(), self.Hm.data_ptr(), s)
         assert rc == 0
 
     def call_wiener_filter(self, s):
         rc = lib.svt_b200_wiener_units_dev(self.cdef_out.data_ptr(), self.final.data_ptr(), self.wiener_units.data_ptr(),
-                                           len(self.wl.wiener_units), 8, s)
+                                           len(self.wl.wiener_units), self.bd, s)
         assert rc == 0
 
     STAGES = ("me", "tx", "cdef", "rest")
     # (call, stage it belongs to, the kernels it launches)
     CALLS = (("me_pyramid", "me", "downsample_2d_kernel+pad_plane_kernel"),
-             ("me_search", "me", "hme_prepare/sad_search_small/hme_finish x3 + me_centre_kernel + fullpel_search_kernel"),
+             ("me_search", "me", "hme_fused_kernel + fullpel_search_kernel"),
              ("txfm_trio", "tx", "trio_txfm_kernel<4..64> (forward transform + quantise + inverse transform fused)"),
              ("cdef_search", "cdef", "cdef_dir_kernel+cdef_search_kernel"),
              ("cdef_apply", "cdef", "cdef_apply_kernel"),

@@ -16,13 +16,37 @@ Everything here is plain numpy data preparation; it performs no DSP.
 """
 import numpy as np
 
-from . import dsp
+try:
+    from . import layout as dsp  # struct dtypes / geometry only: no library is loaded by this module
+except ImportError:  # loaded stand-alone (bench.py's CPU reference arm must not import the product package)
+    import layout as dsp
 
 TX_W, TX_H = dsp.TX_W, dsp.TX_H
 
+# Search / filter settings per encoder preset, derived from the reference's own tables for CRF 25-30, reference
+# distance 1, non-screen content (enc_mode_config.c:138-345 ME/HME search areas with their qp modulation,
+# :875-1110 + :1736-1747 CDEF search level; motion_estimation.c:1800-1866 for the per-region L0 area):
+#   M8: HME L0 16x4 / region, full-pel 8x3;   CDEF level 7 (subsampling 4)
+#   M6: HME L0 16x8,          full-pel 8x8;   CDEF level 5 (3 + 3 strengths, every row, chroma first pass only)
+#   M4: HME L0 16x8,          full-pel 24x24; CDEF level 5
+PRESETS = {
+    8: dict(hme_l0=(16, 4), me_sa=(8, 3), cdef_y=[0, 4, 9, 17, 20, 35], cdef_uv=[0, 4, 8, 17, -1, 20], cdef_subsampling=4),
+    6: dict(hme_l0=(16, 8), me_sa=(8, 8), cdef_y=[0, 28, 60, 2, 30, 62], cdef_uv=[0, 28, 60, -1, -1, -1], cdef_subsampling=1),
+    4: dict(hme_l0=(16, 8), me_sa=(24, 24), cdef_y=[0, 28, 60, 2, 30, 62], cdef_uv=[0, 28, 60, -1, -1, -1], cdef_subsampling=1),
+}
+# BASELINE.json configs[k] -> (width, height, bit_depth, preset)
+CONFIGS = {0: (640, 360, 8, 8), 1: (1920, 1080, 8, 8), 2: (1920, 1080, 10, 6), 3: (3840, 2160, 8, 8), 4: (3840, 2160, 10, 4)}
+CONFIG_NAMES = {
+    0: "configs[0]: 640x360 8-bit 4:2:0 synthetic hot path (the reference's CPU-runnable case; M8 search settings)",
+    1: "configs[1]: 1920x1080 8-bit 4:2:0 synthetic, preset 8 CRF 30 hot path (ME 2 refs + TX + CDEF + Wiener), 1 frame/step",
+    2: "configs[2]: 1920x1080 10-bit (HBD path) synthetic, preset 6 CRF 25 hot path, 1 frame/step",
+    3: "configs[3]: 3840x2160 8-bit 4:2:0 synthetic, preset 8 hot path, 1 frame/step (frame-parallel across GPUs)",
+    4: "configs[4]: 3840x2160 10-bit synthetic, preset 4, CDEF + restoration hot path, 1 frame/step",
+}
 
-def synth_sequence(width, height, n_frames, seed=20260923):
-    """list of (Y, U, V) uint8 planes"""
+
+def synth_sequence(width, height, n_frames, seed=20260923, bit_depth=8):
+    """list of (Y, U, V) planes: uint8, or uint16 holding `bit_depth`-bit samples"""
     r = np.random.default_rng(seed)
     pw, ph = width + 64 + 3 * n_frames, height + 64 + n_frames
     pano = np.full((ph, pw), 128.0)
@@ -34,7 +58,11 @@ def synth_sequence(width, height, n_frames, seed=20260923):
         y = pano[32 + t:32 + t + height, 32 + 3 * t:32 + 3 * t + width] + r.normal(0, 2, (height, width))
         yy = np.clip(y, 0, 255)
         c = 128 + 0.25 * (yy[0::2, 0::2] - 128)
-        frames.append((yy.astype(np.uint8), np.clip(c + 3, 0, 255).astype(np.uint8), np.clip(c - 3, 0, 255).astype(np.uint8)))
+        if bit_depth == 8:
+            frames.append((yy.astype(np.uint8), np.clip(c + 3, 0, 255).astype(np.uint8), np.clip(c - 3, 0, 255).astype(np.uint8)))
+        else:  # the same content with real low-order bits
+            sc, mx = 1 << (bit_depth - 8), (1 << bit_depth) - 1
+            frames.append(tuple(np.clip(np.rint(v * sc), 0, mx).astype(np.uint16) for v in (yy, np.clip(c + 3, 0, 255), np.clip(c - 3, 0, 255))))
     return frames
 
 
@@ -55,21 +83,34 @@ def quant_tables(d_dc, d_ac):
 class FrameWorkload:
     PAD = 16  # border of the reconstruction planes (restoration reads 3(+1) pixels beyond the picture)
 
-    def __init__(self, width=1920, height=1080, seed=20260923, n_refs=2):
-        assert width % 8 == 0 and height % 8 == 0
-        self.width, self.height, self.n_refs = width, height, n_refs
+    def __init__(self, width=1920, height=1080, seed=20260923, n_refs=2, bit_depth=8, preset=8):
+        assert width % 8 == 0 and height % 8 == 0 and bit_depth in (8, 10) and preset in PRESETS
+        self.width, self.height, self.n_refs, self.bit_depth, self.preset = width, height, n_refs, bit_depth, preset
+        self.pixel_bytes = 1 if bit_depth == 8 else 2
+        self.pixel_dtype = np.uint8 if bit_depth == 8 else np.uint16
         self._set_pictures(seed)
         self.me_shapes = dsp.me_plane_shapes(width, height)
-        # M8 / 1080p / crf 30 / distance 1 (module docstring)
-        self.me_params = [dict(hme_l0_sa_w=16, hme_l0_sa_h=4, hme_l1_sa_w=8, hme_l1_sa_h=3, hme_l2_sa_w=8, hme_l2_sa_h=3, me_sa_w=8,
-                               me_sa_h=3, hme_sub_sad=1, me_sub_sad=1, check_zero_centre=1) for _ in range(n_refs)]
+        ps = PRESETS[preset]
+        self.me_params = [dict(hme_l0_sa_w=ps["hme_l0"][0], hme_l0_sa_h=ps["hme_l0"][1], hme_l1_sa_w=8, hme_l1_sa_h=3, hme_l2_sa_w=8,
+                               hme_l2_sa_h=3, me_sa_w=ps["me_sa"][0], me_sa_h=ps["me_sa"][1], hme_sub_sad=1, me_sub_sad=1,
+                               check_zero_centre=1) for _ in range(n_refs)]
         self.plane_dims = [(width, height), (width // 2, height // 2), (width // 2, height // 2)]
         self._build_tx_items()
         self._build_cdef()
         self._build_rest()
 
+    @classmethod
+    def from_config(cls, k, seed=20260923):
+        w, h, bd, preset = CONFIGS[k]
+        return cls(w, h, seed=seed, bit_depth=bd, preset=preset)
+
+    def me_luma(self, planes):
+        """the 8-bit luma open-loop ME searches: the picture itself, or the 8 MSBs of a 10-bit picture (the
+        reference keeps that plane for every input, pic_analysis / EbPaReferenceObject)"""
+        return planes[0] if self.bit_depth == 8 else (planes[0] >> (self.bit_depth - 8)).astype(np.uint8)
+
     def _set_pictures(self, seed):
-        seq = synth_sequence(self.width, self.height, self.n_refs + 1, seed)
+        seq = synth_sequence(self.width, self.height, self.n_refs + 1, seed, self.bit_depth)
         self.cur = seq[1]
         self.refs = [seq[0], seq[2]][:self.n_refs]
         # prediction = previous picture (zero-motion inter prediction); residual = cur - pred
@@ -138,7 +179,7 @@ class FrameWorkload:
                             n = min(bw, 32) * min(bh, 32)
                             fwd.append((res_off[p] + y * pw + x, coef_pos, pw, sz, ty, 1))
                             rpos = rec_off[p] + (self.PAD + y) * st + self.PAD + x
-                            inv.append((coef_pos, rpos, rpos, st, st, sz, ty, 8, 0, 0))
+                            inv.append((coef_pos, rpos, rpos, st, st, sz, ty, self.bit_depth, 0, 0))
                             qnt.append((coef_pos, sz))
                             coef_pos += n
                             sizes_used.add(sz)
@@ -163,7 +204,7 @@ class FrameWorkload:
         self.scan_table = np.concatenate(scan_parts)
         self.iscan_table = np.concatenate([np.argsort(sc).astype(np.int16) for sc in scan_parts])  # inverse permutations
         self.qm_table = np.concatenate(qm_parts)
-        t = quant_tables(52, 61)
+        t = quant_tables(52 << (self.bit_depth - 8), 61 << (self.bit_depth - 8))  # dc/ac step of qindex ~120, scaled with the bit depth
         q = np.zeros(len(qnt), dtype=dsp.QUANT_ITEM_DTYPE)
         cp = np.array([c for c, _ in qnt], np.uint64)
         szs = np.array([s for _, s in qnt])
@@ -174,7 +215,7 @@ class FrameWorkload:
         q["n_coeffs"] = [min(TX_W[s], 32) * min(TX_H[s], 32) for s in szs]
         for name in ("zbin", "round", "quant", "quant_shift", "dequant"):
             q[name] = t[name]
-        q["mode"] = dsp.QUANT_FP_LBD
+        q["mode"] = dsp.QUANT_FP_LBD if self.bit_depth == 8 else dsp.QUANT_FP_HBD
         # log_scale of av1_get_tx_scale: 0 up to 256 coefficients... 1 for 512/1024, 2 for 64x64-class
         q["log_scale"] = [2 if TX_W[s] * TX_H[s] > 1024 else (1 if TX_W[s] * TX_H[s] > 256 else 0) for s in szs]
         self.quant_items = q
@@ -193,10 +234,11 @@ class FrameWorkload:
     def _build_cdef(self):
         r = np.random.default_rng(11)
         self.skip8x8 = (r.random(((self.height + 7) // 8, (self.width + 7) // 8)) < 0.10).astype(np.uint8)
-        self.cdef_str_y = np.array([0, 4, 9, 17, 20, 35], np.int32)
-        self.cdef_str_uv = np.array([0, 4, 8, 17, -1, 20], np.int32)
+        ps = PRESETS[self.preset]
+        self.cdef_str_y = np.array(ps["cdef_y"], np.int32)
+        self.cdef_str_uv = np.array(ps["cdef_uv"], np.int32)
         self.cdef_damping = 3 + (120 >> 6)
-        self.cdef_subsampling = 4  # CDEF search level of M8 (enc_mode_config.c:1066-1088)
+        self.cdef_subsampling = ps["cdef_subsampling"]  # CdefSearchControls.subsampling_factor of the preset's search level
         nfb = ((self.width + 63) // 64) * ((self.height + 63) // 64)
         self.cdef_fb_idx = (np.arange(nfb) % 4).astype(np.int8)
         self.cdef_apply_y = np.array([4, 9, 17, 0], np.int32)
@@ -232,20 +274,22 @@ class FrameWorkload:
 
     # -- algorithmic bytes per frame -----------------------------------------------------------
     def algorithmic_bytes(self):
-        """SURVEY 8(d) figures, per call of the frame pipeline (8-bit: bpp = 1)"""
-        W, H, R = self.width, self.height, self.n_refs
+        """SURVEY 8(d) figures, per call of the frame pipeline (bpp = bytes per pixel)"""
+        W, H, R, bpp = self.width, self.height, self.n_refs, self.pixel_bytes
         n64 = ((W + 63) // 64) * ((H + 63) // 64)
         N = int(1.5 * W * H)  # samples = transform coefficients of the final pass
         calls = {
             "me_pyramid": int(1.3125 * W * H),                                    # full-res read + the two decimated levels written
             "me_search": int((1 + R) * 1.3125 * W * H + n64 * R * 85 * 8),        # every pyramid read once + SAD/MV out
-            "fwd_txfm": 6 * N, "quant": 12 * N, "inv_txfm": 6 * N,               # (22 + 2 bpp) N in total
-            "txfm_trio": 24 * N,                                                  # the three steps fused: SURVEY's figure for the chain
-            "cdef_search": int(2 * N + n64 * 2 * len(self.cdef_str_y) * 8),       # recon + source in, mse out
-            "cdef_apply": 2 * N,                                                  # recon in, filtered out
+            "fwd_txfm": 6 * N, "quant": 12 * N, "inv_txfm": (4 + 2 * bpp) * N,    # (22 + 2 bpp) N in total
+            "txfm_trio": (22 + 2 * bpp) * N,                                      # SURVEY 8(d)'s figure for the unfused chain
+            # what the FUSED call has to move: residual (2N) + prediction in, qcoeff + dqcoeff (4N each) + recon out
+            "txfm_trio_fused_min": (2 + 8 + 2 * bpp) * N,
+            "cdef_search": int(2 * bpp * N + n64 * 2 * len(self.cdef_str_y) * 8),  # recon + source in, mse out
+            "cdef_apply": 2 * bpp * N,                                            # recon in, filtered out
             "rest_extend": 0,
-            "wiener_stats": int(2 * N + len(self.stats_items) * (49 + 2401) * 8),
-            "wiener_filter": 2 * N,
+            "wiener_stats": int(2 * bpp * N + len(self.stats_items) * (49 + 2401) * 8),
+            "wiener_filter": 2 * bpp * N,
         }
         stage_of = {"me_pyramid": "me", "me_search": "me", "txfm_trio": "tx", "cdef_search": "cdef",
                     "cdef_apply": "cdef", "rest_extend": "rest", "wiener_stats": "rest", "wiener_filter": "rest"}

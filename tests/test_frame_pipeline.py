@@ -6,13 +6,23 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("size", [(384, 256), (1920, 1080)])
-def test_frame_pipeline_matches_reference(b200, refc, size):
+# (width, height, bit_depth, preset): small cases + every BASELINE.json configuration (configs[1..4]) at full size
+FRAME_CASES = [(384, 256, 8, 8), (384, 256, 10, 6), (448, 320, 10, 4), (1920, 1080, 8, 8), (1920, 1080, 10, 6), (3840, 2160, 8, 8),
+               (3840, 2160, 10, 4)]
+
+
+@pytest.mark.parametrize("case", FRAME_CASES, ids=lambda c: "%dx%d_b%d_m%d" % c)
+def test_frame_pipeline_matches_reference(b200, refc, case):
+    """every output of the T2 frame pipeline == the reference's own kernels (8-bit: svt_av1_inv_txfm_add, svt_av1_compute_stats,
+    svt_av1_wiener_convolve_add_src ...; 10-bit: svt_aom_inv_transform_recon with CONVERT_TO_BYTEPTR planes as in
+    full_loop.c:1843-1846, svt_av1_highbd_quantize_fp_qm, svt_compute_cdef_dist_16bit, svt_av1_compute_stats_highbd,
+    svt_av1_highbd_wiener_convolve_add_src as in restoration.c:933)"""
     import torch
     import bench
     from svt_av1_psy_b200.pipeline import FramePipeline
     from svt_av1_psy_b200.workload import FrameWorkload
-    fp = FramePipeline(FrameWorkload(*size), torch)
+    w, h, bd, m = case
+    fp = FramePipeline(FrameWorkload(w, h, bit_depth=bd, preset=m), torch)
     bench.check_against_reference(fp, torch)
     # size-independent property: a second pass over the same inputs is idempotent
     a = fp.final.clone(), fp.qcoeff.clone(), fp.me_mv.clone()
@@ -87,8 +97,8 @@ def test_two_frames_in_flight_on_two_streams(b200, refc):
                 assert torch.equal(getattr(fp, n), t), (rep, n)
 
 
-@pytest.mark.parametrize("size", [(384, 256), (640, 360)])
-def test_frame_matches_committed_golden_fixture(b200, size):
+@pytest.mark.parametrize("name", ["frame_384x256", "frame_640x360", "frame_384x256_b10_m6", "frame_640x360_b10_m4"])
+def test_frame_matches_committed_golden_fixture(b200, name):
     """tests/golden/frame_WxH.json holds the SHA-256 of every output of the frame as computed by the reference's
     own C kernels (tools/make_golden.py, run where /root/reference exists).  Needs no oracle at run time."""
     import hashlib
@@ -98,8 +108,8 @@ def test_frame_matches_committed_golden_fixture(b200, size):
     import torch
     from svt_av1_psy_b200.pipeline import FramePipeline
     from svt_av1_psy_b200.workload import FrameWorkload
-    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "frame_%dx%d.json" % size)))
-    fp = FramePipeline(FrameWorkload(size[0], size[1], seed=g["seed"]), torch)
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", name + ".json")))
+    fp = FramePipeline(FrameWorkload(g["width"], g["height"], seed=g["seed"], bit_depth=g.get("bit_depth", 8), preset=g.get("preset", 8)), torch)
     fp.load_inputs()
     fp.step()
     torch.cuda.synchronize()

@@ -263,7 +263,7 @@ def test_committed_golden_fixtures_are_what_the_reference_computes(oracle, refc)
     import make_golden
     for name in sorted(os.listdir(os.path.join(root, "tests", "golden"))):
         g = json.load(open(os.path.join(root, "tests", "golden", name)))
-        now = make_golden.golden_for(g["width"], g["height"], g["seed"])
+        now = make_golden.golden_for(g["width"], g["height"], g["seed"], g.get("bit_depth", 8), g.get("preset", 8))
         assert now["sha256"] == g["sha256"], name
 
 

@@ -12,32 +12,32 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 
-import bench  # noqa: E402
-from svt_av1_psy_b200.workload import FrameWorkload  # noqa: E402
+import oracle  # noqa: E402
+from oracle.frame_ref import RefFrame, load_workload_module  # noqa: E402
 
 
 def digest(a):
     return hashlib.sha256(np.ascontiguousarray(a).view(np.uint8).tobytes()).hexdigest()
 
 
-def golden_for(width, height, seed=20260923):
-    ref, _, _ = bench.load_reference()
+def golden_for(width, height, seed=20260923, bit_depth=8, preset=8):
+    ref = oracle.ref
     assert ref is not None, "oracle/_ref is not built"
     ref.ref_set_tier(0)
-    wl = FrameWorkload(width, height, seed=seed)
-    fr = bench.RefFrame(wl, ref)
+    wl = load_workload_module().FrameWorkload(width, height, seed=seed, bit_depth=bit_depth, preset=preset)
+    fr = RefFrame(wl, ref)
     fr.step()
     outs = {"me_sad": fr.me_sad, "me_mv": fr.me_mv, "hme_centre": fr.me_c, "coeff": fr.coeff, "qcoeff": fr.q, "dqcoeff": fr.dq,
             "eob": fr.eobs, "recon": fr.recon, "cdef_mse": fr.mse, "cdef_dir": fr.dirs, "cdef_out": fr.cdef_out,
             "wiener_M": fr.M, "wiener_H": fr.Hm, "final": fr.final}
-    return {"width": width, "height": height, "seed": seed, "reference_tier": "C (ref_set_tier(0))",
+    return {"width": width, "height": height, "seed": seed, "bit_depth": bit_depth, "preset": preset, "reference_tier": "C (ref_set_tier(0))",
             "sha256": {k: digest(v) for k, v in outs.items()},
             "shape": {k: list(np.asarray(v).shape) for k, v in outs.items()}}
 
 
 if __name__ == "__main__":
-    for (w, h) in ((384, 256), (640, 360)):
-        g = golden_for(w, h)
-        path = os.path.join(ROOT, "tests", "golden", "frame_%dx%d.json" % (w, h))
+    for (w, h, bd, m) in ((384, 256, 8, 8), (640, 360, 8, 8), (384, 256, 10, 6), (640, 360, 10, 4)):
+        g = golden_for(w, h, bit_depth=bd, preset=m)
+        path = os.path.join(ROOT, "tests", "golden", "frame_%dx%d%s.json" % (w, h, "" if (bd, m) == (8, 8) else "_b%d_m%d" % (bd, m)))
         json.dump(g, open(path, "w"), indent=1, sort_keys=True)
         print("wrote", path)
