@@ -8,13 +8,14 @@
 
 A "step" = the hot-path DSP work of ONE 1920x1080 8-bit 4:2:0 frame at preset-8 / CRF-30 settings
 (svt-av1-psy_b200/workload.py): open-loop ME (HME pyramid + 85-PU full-pel search, 2 references),
-forward transform + quantize + inverse/reconstruction of every sample, CDEF search + apply, Wiener
-statistics + filter.  Prints ONE JSON line (rank 0).
+residual + forward transform + quantize + inverse/reconstruction of every sample, CDEF search + apply,
+Wiener statistics + filter.  Prints ONE JSON line (rank 0).
 
 `value`  : frames/s with every input already resident in HBM (CUDA events on the launch stream).
-`e2e`    : same metric through the host-buffer path: per step the source picture, residual and
-           prediction are copied from pinned host memory and the ME results, quantised coefficients,
-           CDEF costs, Wiener statistics and the filtered picture are read back, inside the timed region.
+`e2e`    : same metric through the host-buffer path: per step the source picture and the prediction are copied
+           from pinned host memory (the residual is formed on the device) and the ME results, per-block eobs +
+           eob-bounded scan-order levels, CDEF costs, Wiener statistics and the filtered picture are read back,
+           inside the timed region.
 """
 import argparse
 import ctypes as ct
@@ -36,7 +37,7 @@ sys.path.insert(0, ROOT)
 METRIC = "1080p preset-8 encoded frames/sec at 1/2/4/8 B200 vs reference AVX2 on host"
 METRIC_SCOPE = "hot path only (SURVEY 8: ME + transform/quant/inverse + CDEF + Wiener of one 1080p preset-8 frame per step), not a full encode"
 N_FRAME_SETS = 8  # rotated between steps: no step finds its inputs in L2, and (e2e) up to 8 frames are in flight
-N_CALLS = 8       # len(FramePipeline.CALLS): the T2 entry points one frame goes through
+N_CALLS = 9       # len(FramePipeline.CALLS): the T2 entry points one frame goes through
 EXCH_BATCH = 4    # pictures per reconstructed-reference exchange (one mini-GOP slice per NCCL group launch)
 # dram__bytes_read.sum + dram__bytes_write.sum of the call's dominant kernel, per launch, from the ncu --set full
 # capture of this same command (profiles/README.md says which file); None = not captured for that call
@@ -86,7 +87,7 @@ def time_reference_frames(ref, frames, n_frames, n_threads, warm_frames):
     return run_frames(ref, frames, n_frames, n_threads)
 
 
-def reference_arm(args, wls, steps, warmup, budget_s=60.0, scaling=True):
+def reference_arm(args, wls, steps, warmup, budget_s=60.0):
     """-> dict(fps, ms, cores, tier, inner_repeats, scaling) or None.  A step = one whole frame; `steps` frames form a
     batch and the batch is repeated back to back (one continuous stream of frames, no barrier between repeats) so
     that every host thread has several frames to work through."""
@@ -96,27 +97,46 @@ def reference_arm(args, wls, steps, warmup, budget_s=60.0, scaling=True):
         return None
     frames = [RefFrame(w, ref) for w in wls]
     cores = host_threads()
-    # one frame, single thread: sizes the sample
+    # one frame, single thread: sizes the samples
     t1 = time_reference_frames(ref, frames, 1, 1, 1)
     per_thread_fps = 1.0 / t1
-    want = max(steps, 6 * cores)                               # >= 6 frames per thread: the tail wave costs < 15 %
-    cap = max(steps, int(budget_s * per_thread_fps * cores))   # bounded by the time budget
+    # thread-count sweep: "all the host threads it can use" is whatever count is FASTEST on this box (SMT siblings, a CPU
+    # quota of the container or other tenants can make the full logical count slower than a smaller pool)
+    curve = {"1": round(per_thread_fps, 3)}
+    best_t, best_fps = 1, per_thread_fps
+    for t in sorted({8, 16, 32, 64, 96, cores}):
+        if t <= 1 or t > cores:
+            continue
+        n = max(2 * t, min(6 * t, int(0.08 * budget_s * per_thread_fps * t)))
+        f = n / time_reference_frames(ref, frames, n, t, t)
+        curve[str(t)] = round(f, 3)
+        if f > best_fps:
+            best_t, best_fps = t, f
+    want = max(steps, 6 * best_t)                               # >= 6 frames per thread: the tail wave costs < 15 %
+    cap = max(steps, int(0.5 * budget_s * best_fps))            # bounded by the time budget
     n_frames = min(want, cap)
     reps = max(1, -(-n_frames // steps))
     n_frames = reps * steps
-    dt = time_reference_frames(ref, frames, n_frames, cores, warmup)
-    out = dict(fps=n_frames / dt, ms=1e3 * dt / n_frames, cores=cores, tier=REF_TIER_NAME[tier], inner_repeats=reps, frames=n_frames,
-               single_thread_fps=per_thread_fps)
-    if scaling:
-        curve = {"1": round(per_thread_fps, 3)}
-        for t in (8, 32, 64):
-            if t < cores:
-                n = max(2 * t, min(6 * t, int(10.0 * per_thread_fps * t)))
-                curve[str(t)] = round(n / time_reference_frames(ref, frames, n, t, t), 3)
-        curve[str(cores)] = round(out["fps"], 3)
-        out["scaling"] = curve
-        ref.ref_set_threads(cores)
+    dt = time_reference_frames(ref, frames, n_frames, best_t, warmup)
+    out = dict(fps=n_frames / dt, ms=1e3 * dt / n_frames, cores=best_t, host_cpus=cores, tier=REF_TIER_NAME[tier], inner_repeats=reps,
+               frames=n_frames, single_thread_fps=per_thread_fps, scaling=curve, cpu_quota=cpu_quota())
+    ref.ref_set_threads(best_t)
     return out
+
+
+def cpu_quota():
+    """the container's CPU bandwidth limit (cgroup v2 cpu.max / v1 cfs quota), in CPUs; None = unlimited / unknown"""
+    try:
+        q, p = open("/sys/fs/cgroup/cpu.max").read().split()
+        return None if q == "max" else round(int(q) / int(p), 2)
+    except Exception:
+        pass
+    try:
+        q = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+        p = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+        return None if q <= 0 else round(q / p, 2)
+    except Exception:
+        return None
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -215,7 +235,7 @@ def main():
         if t is None:
             print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libsvtav1_ref.so is not built"}))
             return
-        config["frames_in_flight"] = "one whole frame per host thread, persistent core-pinned pool (%d threads), %d frame sets" % (t["cores"], N_FRAME_SETS)
+        config["frames_in_flight"] = "one whole frame per host thread, persistent core-pinned pool (%d threads = the fastest count of the sweep on %d host CPUs), %d frame sets" % (t["cores"], t["host_cpus"], N_FRAME_SETS)
         out = {"impl": "reference", "metric": METRIC, "metric_scope": METRIC_SCOPE, "value": round(t["fps"], 3), "unit": "frames/s",
                "n_gpus": args.gpus, "steps": args.steps, "warmup": warmup, "inner_repeats": t["inner_repeats"],
                "ms_per_step": round(t["ms"], 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -223,7 +243,8 @@ def main():
                "cpu_baseline": {"value": round(t["fps"], 3), "unit": "frames/s", "cores": t["cores"], "kind": "reference",
                                 "sample": "%d whole frames in flight over %d pinned threads (%d x %d steps), tier %s" %
                                           (t["frames"], t["cores"], t["inner_repeats"], args.steps, t["tier"]),
-                                "scaling": t.get("scaling"), "single_thread_ms_per_frame": round(1e3 / t["single_thread_fps"], 2)},
+                                "scaling": t.get("scaling"), "host_cpus": t["host_cpus"], "cpu_quota": t["cpu_quota"],
+                                "single_thread_ms_per_frame": round(1e3 / t["single_thread_fps"], 2)},
                "e2e": {"value": round(t["fps"], 3), "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(out))
         return
@@ -343,15 +364,28 @@ def main():
 
     s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
 
+    D2H_LAG = 2  # the variable-size part of a frame's results is requested this many frames later (its size has arrived by then)
+    d2h_level_bytes = [0, 0]  # bytes, frames
+
     def run_e2e(n):
         """host buffers -> device -> host, every step; the three phases of consecutive frames overlap on
         three streams (copy-in / compute / copy-out), ordered with events; a frame set is re-used only
-        after its previous results have been read back."""
+        after its previous results have been read back.  Results travel in two parts: the fixed-size outputs
+        (with the level offsets), then -- D2H_LAG frames later, when the host knows sum(eob) -- exactly that many levels."""
         ev_in = [torch.cuda.Event() for _ in range(n)]
         ev_done = [torch.cuda.Event() for _ in range(n)]
+        ev_small = [torch.cuda.Event() for _ in range(n)]
         ev_out = [torch.cuda.Event() for _ in range(n)]
         ex = Exchanger(n)
         start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+        def finish_frame(k):
+            ev_small[k].synchronize()  # host wait, but on work enqueued D2H_LAG frames ago: the pipeline stays full
+            with torch.cuda.stream(s_out):
+                d2h_level_bytes[0] += sets[k % N_FRAME_SETS].read_levels()
+                d2h_level_bytes[1] += 1
+                ev_out[k].record(s_out)
+
         start.record(stream)
         s_in.wait_event(start)
         if comm is not None:
@@ -373,7 +407,11 @@ def main():
             with torch.cuda.stream(s_out):
                 s_out.wait_event(ev_done[i])
                 fp.read_outputs()
-                ev_out[i].record(s_out)
+                ev_small[i].record(s_out)
+            if i >= D2H_LAG:
+                finish_frame(i - D2H_LAG)
+        for k in range(max(0, n - D2H_LAG), n):
+            finish_frame(k)
         stream.wait_event(ev_out[n - 1])
         ex.finish(stream)
         end.record(stream)
@@ -467,7 +505,9 @@ def main():
            "ms_per_step": round(ms / args.steps, 4), "metric_scope": METRIC_SCOPE, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "u8" if wl0.bit_depth == 8 else "u16",
            "data": "synthetic", "config": config, "clocks": clocks,
-           "e2e": {"value": round(fps_e2e, 2), "unit": "frames/s", "h2d_bytes_per_step": int(sets[0].h2d_bytes), "d2h_bytes_per_step": int(sets[0].d2h_bytes),
+           "e2e": {"value": round(fps_e2e, 2), "unit": "frames/s", "h2d_bytes_per_step": int(sets[0].h2d_bytes),
+                   "d2h_bytes_per_step": int(sets[0].d2h_fixed_bytes + d2h_level_bytes[0] / max(1, d2h_level_bytes[1])),
+                   "d2h_note": "fixed-size results + sum(eob) scan-order levels (%d-byte), averaged over the timed frames" % sets[0].level_bytes,
                    "ms_per_step": round(ms_e2e / args.steps, 4), "inner_repeats": reps_e2e},
            "gpu_launches": int(round(launches_per_step * args.steps)), "gpu_launches_per_step": round(launches_per_step, 1),
            "eager_ms_per_step": round(ms_eager / prof_steps, 4), "roofline": roofline,
@@ -478,11 +518,11 @@ def main():
         out["exchange"] = {"pattern": "owner -> %d consumers (point-to-point), batched per %d pictures, dedicated comm stream" % (len(exch.consumers), EXCH_BATCH),
                            "bytes_sent_per_step_per_rank": int(exch.bytes_sent_per_frame)}
     if world == 1 and not args.no_cpu_baseline:
-        t = reference_arm(args, wls, args.steps, 3, budget_s=min(args.ref_budget, 20.0), scaling=False)
+        t = reference_arm(args, wls, args.steps, 3, budget_s=min(args.ref_budget, 20.0))
         if t is not None:
             out["cpu_baseline"] = {"value": round(t["fps"], 3), "unit": "frames/s", "cores": t["cores"], "kind": "reference",
-                                   "sample": "%d whole frames of the same workload in flight over %d pinned host threads, tier %s" %
-                                             (t["frames"], t["cores"], t["tier"])}
+                                   "sample": "%d whole frames of the same workload in flight over %d pinned host threads (fastest count on %d CPUs), tier %s" %
+                                             (t["frames"], t["cores"], t["host_cpus"], t["tier"]), "scaling": t["scaling"]}
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
@@ -527,13 +567,29 @@ def check_against_reference(fp, torch):
     # the frame step uses the fused transform call; the same chain as three separate calls (which also
     # materialises the forward coefficients) must give the same answers
     s = torch.cuda.current_stream().cuda_stream
-    for t in (fp.qcoeff, fp.dqcoeff, fp.eobs, fp.recon):
+    # the packed levels: block i's first eob levels in scan order at offsets[i] == what the entropy coder reads from the reference's buffers
+    offs = fp.level_offsets.cpu().numpy().view(np.uint32)
+    lv = fp.levels.cpu().numpy()
+    eobs_ref = fr.eobs.astype(np.int64)
+    want_offs = np.concatenate([[0], np.cumsum(eobs_ref)])
+    if not np.array_equal(offs[:len(want_offs)], want_offs) or offs[len(want_offs)] != 0:
+        bad.append("level_offsets")
+    else:
+        qi, scan = fp.wl.quant_items, fp.wl.scan_table
+        for i in range(0, len(qi), max(1, len(qi) // 4000)):  # every block of a small picture, a dense sample of a large one
+            e = int(eobs_ref[i])
+            w = fr.q[int(qi["q_off"][i]) + scan[int(qi["scan_off"][i]):int(qi["scan_off"][i]) + e].astype(np.int64)]
+            if not np.array_equal(lv[want_offs[i]:want_offs[i] + e].astype(np.int64), w.astype(np.int64)):
+                bad.append("levels[block %d]" % i)
+                break
+    for t in (fp.qcoeff, fp.dqcoeff, fp.eobs, fp.recon, fp.residual):
         t.zero_()
+    fp.call_residual(s)
     fp.call_fwd_txfm(s)
     fp.call_quant(s)
     fp.call_inv_txfm(s)
     torch.cuda.synchronize()
-    split = [("coeff", fp.coeff, fr.coeff), ("qcoeff/3-call", fp.qcoeff, fr.q), ("dqcoeff/3-call", fp.dqcoeff, fr.dq),
+    split = [("residual", fp.residual, fr.residual), ("coeff", fp.coeff, fr.coeff), ("qcoeff/3-call", fp.qcoeff, fr.q), ("dqcoeff/3-call", fp.dqcoeff, fr.dq),
              ("eob/3-call", fp.eobs, fr.eobs), ("recon/3-call", fp.recon, fr.recon)]
     compare(split)
     cmp = cmp + split

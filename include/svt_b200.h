@@ -300,6 +300,36 @@ SVT_B200_API int svt_b200_txfm_trio_batch_dev(const int16_t* d_residual, const v
                                               const SvtB200TrioItem* d_items, const int n_per_class[SVT_B200_TXFM_CLASSES],
                                               uint16_t* d_eobs, int pixel_bytes, void* stream);
 
+/* The same chain with the residual formed on the fly: residual = source - prediction (svt_aom_residual_kernel,
+ * pic_operators.c; rtcd svt_residual_kernel8bit / svt_residual_kernel16bit) for the block at fwd.src_off / fwd.src_stride
+ * of the SOURCE picture plane and inv.pred_off / inv.pred_stride of the prediction; no int16 residual plane exists. */
+SVT_B200_API int svt_b200_residual_txfm_trio_batch_dev(const void* d_source, const void* d_pred, void* d_recon, int32_t* d_qcoeff,
+                                                       int32_t* d_dqcoeff, const int16_t* d_iscan, const uint8_t* d_qm,
+                                                       const SvtB200TrioItem* d_items, const int n_per_class[SVT_B200_TXFM_CLASSES],
+                                                       uint16_t* d_eobs, int pixel_bytes, void* stream);
+
+/* T2: svt_aom_residual_kernel over up to 3 planes in one launch (offsets / strides in elements). */
+typedef struct SvtB200ResidualPlane {
+    uint64_t src_off, pred_off, res_off;
+    int32_t  src_stride, pred_stride, res_stride;
+    int32_t  w, h;
+    int32_t  reserved;
+} SvtB200ResidualPlane;
+typedef struct SvtB200ResidualPlanes { SvtB200ResidualPlane p[3]; } SvtB200ResidualPlanes;
+SVT_B200_API int svt_b200_residual_planes_dev(const void* d_source, const void* d_pred, int16_t* d_residual,
+                                              const SvtB200ResidualPlanes* planes, int n_planes, int pixel_bytes, void* stream);
+
+/* T2: eob-bounded scan-order packing of a batch's quantised levels -- what the entropy coder consumes.  d_offsets[i]
+ * (n_items + 2 entries: exclusive prefix sum of d_eobs; d_offsets[n_items] = total; d_offsets[n_items + 1] = number of
+ * levels that did not fit level_bytes) locates block i's first level in d_levels; block i contributes d_eobs[i] levels,
+ * qcoeff[scan[0..eob)] of its coefficient block.  level_bytes = 2 (int16: the levels of 8-bit pictures fit, as the
+ * reference's 16-bit-lane low-bit-depth quantizers rely on) or 4 (int32, high bit depth).  Levels beyond `capacity` are
+ * dropped (the caller sees total > capacity and re-issues with a larger buffer).  d_scan is the scan table addressed by
+ * quant.scan_off. */
+SVT_B200_API int svt_b200_pack_levels_dev(const int32_t* d_qcoeff, const int16_t* d_scan, const SvtB200TrioItem* d_items,
+                                          const uint16_t* d_eobs, int n_items, uint32_t* d_offsets, void* d_levels,
+                                          int level_bytes, uint32_t capacity, void* stream);
+
 /* ------------------------------------------------------------------------------------------ */
 /* K4  Hadamard / SATD  (reference: Source/Lib/C_DEFAULT/picture_operators_c.c:188-330)        */
 /* ------------------------------------------------------------------------------------------ */

@@ -157,6 +157,8 @@ int ref_set_tier(int avx2) {
     svt_aom_copy_rect8_8bit_to_16bit          = svt_aom_copy_rect8_8bit_to_16bit_avx2;
     svt_av1_compute_stats                     = svt_av1_compute_stats_avx2;
     svt_av1_wiener_convolve_add_src           = svt_av1_wiener_convolve_add_src_avx2;
+    svt_residual_kernel8bit                   = svt_residual_kernel8bit_avx2;
+    svt_residual_kernel16bit                  = svt_residual_kernel16bit_avx2;
     /* 8-bit inverse transform: the intrinsics-only AVX2 implementation the reference itself binds when the
      * dav1d NASM kernels cannot be used (common_dsp_rtcd.c:522-523) */
     svt_av1_inv_txfm_add                      = svt_av1_inv_txfm_add_avx2;
@@ -395,7 +397,22 @@ typedef struct {
     const int16_t* residual; int32_t *coeff, *q, *dq; const int16_t *scan, *iscan; const uint8_t* qm;
     const RefFwdItem* fwd; const RefQuantItem* qi; const RefInvItem* inv; uint16_t* eobs;
     const void* pred; void* recon; int bd;
+    const void* srcpix; int16_t* residual_w; int skip_zero_blocks;
 } TxCtx;
+
+/* svt_aom_residual_kernel (coding_loop.c:69, called per transform block at :393,:471,:518): residual = source - prediction */
+static void residual_body(void* vctx, int i) {
+    const TxCtx* c = (const TxCtx*)vctx;
+    const RefFwdItem* it = &c->fwd[i];
+    const RefInvItem* iv = &c->inv[i];
+    const int W = TXW[it->tx_size], H = TXH[it->tx_size];
+    if (c->bd == 8)
+        svt_residual_kernel8bit((uint8_t*)c->srcpix + it->src_off, it->src_stride, (uint8_t*)c->pred + iv->pred_off, iv->pred_stride,
+                                c->residual_w + it->src_off, it->src_stride, (uint32_t)W, (uint32_t)H);
+    else
+        svt_residual_kernel16bit((uint16_t*)c->srcpix + it->src_off, it->src_stride, (uint16_t*)c->pred + iv->pred_off, iv->pred_stride,
+                                 c->residual_w + it->src_off, it->src_stride, (uint32_t)W, (uint32_t)H);
+}
 
 static void fwd_body(void* vctx, int i) {
     const TxCtx* c = (const TxCtx*)vctx;
@@ -478,6 +495,15 @@ void ref_quant_batch(const int32_t* coeff, int32_t* q, int32_t* dq, const int16_
 static void inv_body(void* vctx, int i) {
     const TxCtx* c = (const TxCtx*)vctx;
     const RefInvItem* it = &c->inv[i];
+    if (c->skip_zero_blocks && c->eobs[i] == 0) {
+        /* no coefficient survived: the encode pass does not run the inverse (coding_loop.c:601,632,655), the
+         * reconstruction is the prediction */
+        const int W = TXW[it->tx_size], H = TXH[it->tx_size], psz = c->bd > 8 ? 2 : 1;
+        for (int r = 0; r < H; r++)
+            memcpy((uint8_t*)c->recon + (it->recon_off + (size_t)r * it->recon_stride) * psz,
+                   (const uint8_t*)c->pred + (it->pred_off + (size_t)r * it->pred_stride) * psz, (size_t)W * psz);
+        return;
+    }
     if (c->bd == 8)
         svt_aom_inv_transform_recon8bit((int32_t*)c->dq + it->coef_off, (uint8_t*)c->pred + it->pred_off, it->pred_stride,
                                         (uint8_t*)c->recon + it->recon_off, it->recon_stride, (TxSize)it->tx_size, (TxType)it->tx_type,
@@ -679,7 +705,7 @@ typedef struct RefFrameJob {
     int32_t width, height, bit_depth, n_refs;
     const RefMePicture* cur; const RefMePicture* refs; const RefMeParams* prm;
     uint32_t* me_sad; uint32_t* me_mv; int16_t* me_centre; uint64_t* me_hme_sad;
-    const int16_t* residual; int32_t *coeff, *q, *dq; const int16_t *scan, *iscan; const uint8_t* qm;
+    int16_t* residual; int32_t *coeff, *q, *dq; const int16_t *scan, *iscan; const uint8_t* qm;
     const RefFwdItem* fwd; const RefQuantItem* qi; const RefInvItem* inv; uint16_t* eobs;
     int64_t n_tx, n_coeffs;
     const void* pred; void* recon; void* cdef_out; void* final; const void* src;
@@ -729,7 +755,7 @@ static void job_extend(const RefFrameJob* j, void* buf) {
         }
     }
 }
-static void tx_chain_body(void* vctx, int i) { fwd_body(vctx, i); quant_body(vctx, i); inv_body(vctx, i); }
+static void tx_chain_body(void* vctx, int i) { residual_body(vctx, i); fwd_body(vctx, i); quant_body(vctx, i); inv_body(vctx, i); }
 
 static int g_trace = -1;
 #define TRACE(x) do { if (g_trace < 0) g_trace = getenv("REF_TRACE") != NULL; if (g_trace) { fprintf(stderr, "[ref] %s\n", x); fflush(stderr); } } while (0)
@@ -739,8 +765,9 @@ void ref_frame_step(const RefFrameJob* j) {
     MeCtx me = {j->cur, j->refs, j->prm, j->n_refs, j->me_sad, j->me_mv, j->me_centre, j->me_hme_sad};
     par_for(j->n_refs * nb, 4, ref_me_picture_body, &me);
     TRACE("tx");
-    TxCtx tx = {j->residual, j->coeff, j->q, j->dq, j->scan, j->iscan, j->qm, j->fwd, j->qi, j->inv, j->eobs, j->pred, j->recon, j->bit_depth};
-    par_for((int)j->n_tx, 64, tx_chain_body, &tx); /* per block: transform -> quantise -> inverse, as mode decision / enc-dec do */
+    TxCtx tx = {j->residual, j->coeff, j->q, j->dq, j->scan, j->iscan, j->qm, j->fwd, j->qi, j->inv, j->eobs, j->pred, j->recon, j->bit_depth,
+                j->src, j->residual, 1};
+    par_for((int)j->n_tx, 64, tx_chain_body, &tx); /* per block: residual -> transform -> quantise -> inverse, as enc-dec does */
     TRACE("cdef search");
     RefCdefFrame f;
     job_cdef_frame(j, &f);
@@ -763,7 +790,7 @@ void ref_frame_step(const RefFrameJob* j) {
 }
 
 /* private output buffers of one pool thread (allocated on first use, grown when a larger job arrives) */
-typedef struct { size_t cap[16]; void* buf[16]; } WorkerBufs;
+typedef struct { size_t cap[17]; void* buf[17]; } WorkerBufs;
 static __thread WorkerBufs t_bufs;
 static void* wb(int k, size_t bytes) {
     if (t_bufs.cap[k] < bytes) {
@@ -795,6 +822,9 @@ static void frame_body(void* vctx, int i) {
     j.var = wb(13, nb * 64 * 4);
     j.M = wb(14, (size_t)j.n_stats * 49 * 8);
     j.H = wb(15, (size_t)j.n_stats * 2401 * 8);
+    int64_t res_elems = 0;
+    for (int p = 0; p < 3; p++) res_elems = j.src_off[p] + (int64_t)j.src_stride[p] * j.plane_h[p];
+    j.residual = wb(16, (size_t)res_elems * 2);
     ref_frame_step(&j);
 }
 /* n_frames whole frames, frame i on job set i % n_sets, spread over `n_threads` pool threads (<= 0: all);

@@ -176,7 +176,8 @@ inv_txfm_kernel(const int32_t* __restrict__ coef_base, const PIX* __restrict__ p
 // ------------------------------------------------------------------------------------------------
 template <int TEAM, int THREADS, typename PIX>
 __global__ void __launch_bounds__(THREADS)
-trio_txfm_kernel(const int16_t* __restrict__ src_base, const PIX* __restrict__ pred_base, PIX* __restrict__ recon_base,
+trio_txfm_kernel(const int16_t* __restrict__ src_base, const PIX* __restrict__ srcpix_base /*non-null: residual = source - prediction, formed here*/,
+                 const PIX* __restrict__ pred_base, PIX* __restrict__ recon_base,
                  int32_t* __restrict__ q_base, int32_t* __restrict__ dq_base /*may be null*/, const int16_t* __restrict__ iscan_base,
                  const uint8_t* __restrict__ qm_base, const SvtB200TrioItem* __restrict__ items, int n_items,
                  uint16_t* __restrict__ eobs) {
@@ -198,13 +199,26 @@ trio_txfm_kernel(const int16_t* __restrict__ src_base, const PIX* __restrict__ p
         const int   rect = rect_log_ratio(W, H);
         const int   Wp = W > 32 ? 32 : W, Hp = H > 32 ? 32 : H;
         {   // ---- forward (fwd_txfm_kernel) ----
-            const int16_t* src = src_base + item.fwd.src_off;
             const int P1 = W + 1, P2 = H + 1, sstride = item.fwd.src_stride;
+            if (srcpix_base) {  // svt_aom_residual_kernel fused in: the source picture shares the residual plane's geometry
+                const PIX* sp = srcpix_base + item.fwd.src_off;
+                const PIX* pp = pred_base + item.inv.pred_off;
+                const int  pstride = item.inv.pred_stride;
 #pragma unroll 4
-            for (int idx = tid; idx < W * H; idx += MOVERS) {
-                const int r = idx >> lgW, c = idx & (W - 1);
-                const int rr = cfg.f_ud ? (H - 1 - r) : r;
-                A[r * P1 + c] = round_shift_arr((int32_t)src[(size_t)rr * sstride + c], -cfg.f_s0);
+                for (int idx = tid; idx < W * H; idx += MOVERS) {
+                    const int r = idx >> lgW, c = idx & (W - 1);
+                    const int rr = cfg.f_ud ? (H - 1 - r) : r;
+                    const int32_t d = (int32_t)sp[(size_t)rr * sstride + c] - (int32_t)pp[(size_t)rr * pstride + c];
+                    A[r * P1 + c] = round_shift_arr(d, -cfg.f_s0);
+                }
+            } else {
+                const int16_t* src = src_base + item.fwd.src_off;
+#pragma unroll 4
+                for (int idx = tid; idx < W * H; idx += MOVERS) {
+                    const int r = idx >> lgW, c = idx & (W - 1);
+                    const int rr = cfg.f_ud ? (H - 1 - r) : r;
+                    A[r * P1 + c] = round_shift_arr((int32_t)src[(size_t)rr * sstride + c], -cfg.f_s0);
+                }
             }
             team_sync<TEAM, SOLO>();
             txfm_pass_1d<TEAM, false, true>(cfg.f_tc, A, H, W, P1, cfg.f_cbc, 0, tid);  // rows >= Hp of the result are not needed
@@ -219,6 +233,7 @@ trio_txfm_kernel(const int16_t* __restrict__ src_base, const PIX* __restrict__ p
             txfm_pass_1d<TEAM, false, true>(cfg.f_tr, B, W, Hp, P2, cfg.f_cbr, 0, tid);
             team_sync<TEAM, SOLO>();
         }
+        int block_eob = 0;
         {   // ---- quantise the (packed) coefficients; the dequantised levels become the inverse's input plane ----
             const SvtB200QuantItem qi = item.quant;
             const uint8_t* qm  = qi.qm_off == SVT_B200_NO_QM ? nullptr : qm_base + qi.qm_off;
@@ -252,7 +267,8 @@ trio_txfm_kernel(const int16_t* __restrict__ src_base, const PIX* __restrict__ p
                 __syncthreads();
                 if (eob) atomicMax(&s_eob, eob);
                 __syncthreads();
-                if (threadIdx.x == 0) eobs[it] = (uint16_t)s_eob;
+                eob = s_eob;
+                if (threadIdx.x == 0) eobs[it] = (uint16_t)eob;
             } else {
                 const unsigned mask = TEAM == 32 ? 0xffffffffu : (((1u << TEAM) - 1u) << ((threadIdx.x & 31) / TEAM * TEAM));
 #pragma unroll
@@ -260,8 +276,22 @@ trio_txfm_kernel(const int16_t* __restrict__ src_base, const PIX* __restrict__ p
                 if (tid == 0) eobs[it] = (uint16_t)eob;
                 team_sync<TEAM, SOLO>();
             }
+            block_eob = eob;
         }
-        {   // ---- inverse + reconstruction (inv_txfm_kernel) ----
+        if (block_eob == 0) {
+            // every level is zero: the inverse of an all-zero plane is zero, the reconstruction is the prediction
+            // (the encode pass takes the same shortcut, coding_loop.c: eob == 0 -> prediction copied); team-uniform branch
+            const PIX* pr = pred_base + item.inv.pred_off;
+            PIX*       pw = recon_base + item.inv.recon_off;
+            if (pr != pw) {
+#pragma unroll 4
+                for (int idx = tid; idx < W * H; idx += MOVERS) {
+                    const int r = idx >> lgW, c = idx & (W - 1);
+                    pw[(size_t)r * item.inv.recon_stride + c] = pr[(size_t)r * item.inv.pred_stride + c];
+                }
+            }
+            team_sync<TEAM, SOLO>();
+        } else {   // ---- inverse + reconstruction (inv_txfm_kernel) ----
             const int P1 = H + 1, P2 = W + 1;
             const int col_clamp = (bd + 6) > 16 ? (bd + 6) : 16;
             const int opt_row = bd == 8 ? 16 : (bd == 10 ? 18 : 20);
@@ -356,7 +386,7 @@ void launch_inv_txfm(const int32_t* d_coef, const PIX* d_pred, PIX* d_recon, con
 }
 
 template <int TEAM, typename PIX>
-static void launch_trio_class(const int16_t* d_src, const PIX* d_pred, PIX* d_recon, int32_t* d_q, int32_t* d_dq, const int16_t* d_iscan,
+static void launch_trio_class(const int16_t* d_src, const PIX* d_srcpix, const PIX* d_pred, PIX* d_recon, int32_t* d_q, int32_t* d_dq, const int16_t* d_iscan,
                               const uint8_t* d_qm, const SvtB200TrioItem* d_items, int n, uint16_t* d_eobs, cudaStream_t st) {
     if (n <= 0) return;
     constexpr int    THREADS = TEAM == 32 ? 128 : class_threads<TEAM>(), TEAMS = TEAM >= 32 ? 1 : THREADS / TEAM;
@@ -364,12 +394,12 @@ static void launch_trio_class(const int16_t* d_src, const PIX* d_pred, PIX* d_re
     static bool attr = false;
     if (!attr) { set_smem_attr(trio_txfm_kernel<TEAM, THREADS, PIX>, smem); attr = true; }
     const int per_sm = (int)((200 * 1024) / (smem + 1024)) < 2048 / THREADS ? (int)((200 * 1024) / (smem + 1024)) : 2048 / THREADS;
-    trio_txfm_kernel<TEAM, THREADS, PIX><<<grid_for((n + TEAMS - 1) / TEAMS, per_sm), THREADS, smem, st>>>(d_src, d_pred, d_recon, d_q, d_dq, d_iscan, d_qm,
-                                                                                                     d_items, n, d_eobs);
+    trio_txfm_kernel<TEAM, THREADS, PIX><<<grid_for((n + TEAMS - 1) / TEAMS, per_sm), THREADS, smem, st>>>(d_src, d_srcpix, d_pred, d_recon, d_q, d_dq, d_iscan,
+                                                                                                     d_qm, d_items, n, d_eobs);
     B200_LAUNCH_CHECK();
 }
 template <typename PIX>
-static void launch_trio(const int16_t* d_src, const PIX* d_pred, PIX* d_recon, int32_t* d_q, int32_t* d_dq, const int16_t* d_iscan,
+static void launch_trio(const int16_t* d_src, const PIX* d_srcpix, const PIX* d_pred, PIX* d_recon, int32_t* d_q, int32_t* d_dq, const int16_t* d_iscan,
                         const uint8_t* d_qm, const SvtB200TrioItem* d_items, const int* n_per_class, uint16_t* d_eobs, cudaStream_t user) {
     int first[SVT_B200_TXFM_CLASSES + 1] = {0};
     for (int c = 0; c < SVT_B200_TXFM_CLASSES; c++) first[c + 1] = first[c] + n_per_class[c];
@@ -380,11 +410,11 @@ static void launch_trio(const int16_t* d_src, const PIX* d_pred, PIX* d_recon, i
         uint16_t* eo = d_eobs + first[c];
         const int n = n_per_class[c];
         switch (c) {
-        case 0: launch_trio_class<4, PIX>(d_src, d_pred, d_recon, d_q, d_dq, d_iscan, d_qm, it, n, eo, st); break;
-        case 1: launch_trio_class<8, PIX>(d_src, d_pred, d_recon, d_q, d_dq, d_iscan, d_qm, it, n, eo, st); break;
-        case 2: launch_trio_class<16, PIX>(d_src, d_pred, d_recon, d_q, d_dq, d_iscan, d_qm, it, n, eo, st); break;
-        case 3: launch_trio_class<32, PIX>(d_src, d_pred, d_recon, d_q, d_dq, d_iscan, d_qm, it, n, eo, st); break;
-        default: launch_trio_class<64, PIX>(d_src, d_pred, d_recon, d_q, d_dq, d_iscan, d_qm, it, n, eo, st); break;
+        case 0: launch_trio_class<4, PIX>(d_src, d_srcpix, d_pred, d_recon, d_q, d_dq, d_iscan, d_qm, it, n, eo, st); break;
+        case 1: launch_trio_class<8, PIX>(d_src, d_srcpix, d_pred, d_recon, d_q, d_dq, d_iscan, d_qm, it, n, eo, st); break;
+        case 2: launch_trio_class<16, PIX>(d_src, d_srcpix, d_pred, d_recon, d_q, d_dq, d_iscan, d_qm, it, n, eo, st); break;
+        case 3: launch_trio_class<32, PIX>(d_src, d_srcpix, d_pred, d_recon, d_q, d_dq, d_iscan, d_qm, it, n, eo, st); break;
+        default: launch_trio_class<64, PIX>(d_src, d_srcpix, d_pred, d_recon, d_q, d_dq, d_iscan, d_qm, it, n, eo, st); break;
         }
     }
     join_streams(fj, user);
@@ -441,20 +471,137 @@ extern "C" int svt_b200_inv_txfm_batch_dev(const int32_t* d_coeff, const void* d
     return SVT_B200_OK;
 }
 
+static int trio_entry(const int16_t* d_residual, const void* d_source, const void* d_pred, void* d_recon, int32_t* d_qcoeff,
+                      int32_t* d_dqcoeff, const int16_t* d_iscan, const uint8_t* d_qm, const SvtB200TrioItem* d_items,
+                      const int n_per_class[SVT_B200_TXFM_CLASSES], uint16_t* d_eobs, int pixel_bytes, void* stream) {
+    require_ready();
+    if (!n_per_class || !d_iscan || !d_qcoeff || !d_eobs || (pixel_bytes != 1 && pixel_bytes != 2)) return SVT_B200_ERR_BAD_ARG;
+    if (!d_residual == !d_source) return SVT_B200_ERR_BAD_ARG;  // exactly one of the two inputs
+    for (int c = 0; c < SVT_B200_TXFM_CLASSES; c++)
+        if (n_per_class[c] < 0) return SVT_B200_ERR_BAD_ARG;
+    if (pixel_bytes == 1)
+        launch_trio<uint8_t>(d_residual, (const uint8_t*)d_source, (const uint8_t*)d_pred, (uint8_t*)d_recon, d_qcoeff, d_dqcoeff, d_iscan, d_qm,
+                             d_items, n_per_class, d_eobs, (cudaStream_t)stream);
+    else
+        launch_trio<uint16_t>(d_residual, (const uint16_t*)d_source, (const uint16_t*)d_pred, (uint16_t*)d_recon, d_qcoeff, d_dqcoeff, d_iscan, d_qm,
+                              d_items, n_per_class, d_eobs, (cudaStream_t)stream);
+    return SVT_B200_OK;
+}
 extern "C" int svt_b200_txfm_trio_batch_dev(const int16_t* d_residual, const void* d_pred, void* d_recon, int32_t* d_qcoeff,
                                             int32_t* d_dqcoeff, const int16_t* d_iscan, const uint8_t* d_qm,
                                             const SvtB200TrioItem* d_items, const int n_per_class[SVT_B200_TXFM_CLASSES],
                                             uint16_t* d_eobs, int pixel_bytes, void* stream) {
+    return trio_entry(d_residual, nullptr, d_pred, d_recon, d_qcoeff, d_dqcoeff, d_iscan, d_qm, d_items, n_per_class, d_eobs, pixel_bytes, stream);
+}
+extern "C" int svt_b200_residual_txfm_trio_batch_dev(const void* d_source, const void* d_pred, void* d_recon, int32_t* d_qcoeff,
+                                                     int32_t* d_dqcoeff, const int16_t* d_iscan, const uint8_t* d_qm,
+                                                     const SvtB200TrioItem* d_items, const int n_per_class[SVT_B200_TXFM_CLASSES],
+                                                     uint16_t* d_eobs, int pixel_bytes, void* stream) {
+    return trio_entry(nullptr, d_source, d_pred, d_recon, d_qcoeff, d_dqcoeff, d_iscan, d_qm, d_items, n_per_class, d_eobs, pixel_bytes, stream);
+}
+
+// ---- svt_aom_residual_kernel (pic_operators.c:218; rtcd svt_residual_kernel8bit / 16bit, common_dsp_rtcd.h) on planes -----
+template <typename PIX>
+__global__ void residual_planes_kernel(const PIX* __restrict__ src, const PIX* __restrict__ pred, int16_t* __restrict__ res,
+                                       const __grid_constant__ SvtB200ResidualPlanes pl) {
+    const SvtB200ResidualPlane& e = pl.p[blockIdx.y];
+    const long long n = (long long)e.w * e.h;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (long long)gridDim.x * blockDim.x) {
+        const int y = (int)(idx / e.w), x = (int)(idx - (long long)y * e.w);
+        res[e.res_off + (size_t)y * e.res_stride + x] =
+            (int16_t)((int)src[e.src_off + (size_t)y * e.src_stride + x] - (int)pred[e.pred_off + (size_t)y * e.pred_stride + x]);
+    }
+}
+extern "C" int svt_b200_residual_planes_dev(const void* d_source, const void* d_pred, int16_t* d_residual, const SvtB200ResidualPlanes* planes,
+                                            int n_planes, int pixel_bytes, void* stream) {
     require_ready();
-    if (!n_per_class || !d_iscan || !d_qcoeff || !d_eobs || (pixel_bytes != 1 && pixel_bytes != 2)) return SVT_B200_ERR_BAD_ARG;
-    for (int c = 0; c < SVT_B200_TXFM_CLASSES; c++)
-        if (n_per_class[c] < 0) return SVT_B200_ERR_BAD_ARG;
+    if (!planes || n_planes <= 0 || n_planes > 3 || (pixel_bytes != 1 && pixel_bytes != 2)) return SVT_B200_ERR_BAD_ARG;
+    long long mx = 0;
+    for (int i = 0; i < n_planes; i++) mx = mx > (long long)planes->p[i].w * planes->p[i].h ? mx : (long long)planes->p[i].w * planes->p[i].h;
+    const dim3 grid(grid_for((mx + 255) / 256, 8), n_planes);
     if (pixel_bytes == 1)
-        launch_trio<uint8_t>(d_residual, (const uint8_t*)d_pred, (uint8_t*)d_recon, d_qcoeff, d_dqcoeff, d_iscan, d_qm, d_items, n_per_class, d_eobs,
-                             (cudaStream_t)stream);
+        residual_planes_kernel<uint8_t><<<grid, 256, 0, (cudaStream_t)stream>>>((const uint8_t*)d_source, (const uint8_t*)d_pred, d_residual, *planes);
     else
-        launch_trio<uint16_t>(d_residual, (const uint16_t*)d_pred, (uint16_t*)d_recon, d_qcoeff, d_dqcoeff, d_iscan, d_qm, d_items, n_per_class,
-                              d_eobs, (cudaStream_t)stream);
+        residual_planes_kernel<uint16_t><<<grid, 256, 0, (cudaStream_t)stream>>>((const uint16_t*)d_source, (const uint16_t*)d_pred, d_residual, *planes);
+    B200_LAUNCH_CHECK();
+    return SVT_B200_OK;
+}
+
+// ---- eob-bounded scan-order packing of the quantised levels (what the entropy coder consumes: the first eob levels of
+// each block in scan order, coding_loop.c / entropy_coding.c) -- the device->host transfer of a picture's coefficients then
+// carries sum(eob) levels instead of every coefficient position --------------------------------------------------------------
+// pass 1: exclusive prefix sum of the eobs (one CTA; a picture has a few tens of thousands of blocks)
+__global__ void __launch_bounds__(1024) eob_scan_kernel(const uint16_t* __restrict__ eobs, int n, uint32_t* __restrict__ offs /*[n+1]*/) {
+    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_carry;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int base = 0; base < n; base += 1024) {
+        const int i = base + threadIdx.x;
+        const uint32_t v = i < n ? eobs[i] : 0;
+        uint32_t x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += y;
+        }
+        if (lane == 31) s_warp[warp] = x;
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t w = s_warp[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xffffffffu, w, o);
+                if (lane >= o) w += y;
+            }
+            s_warp[lane] = w;
+        }
+        __syncthreads();
+        const uint32_t incl = x + (warp ? s_warp[warp - 1] : 0) + s_carry;
+        if (i < n) offs[i] = incl - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { offs[n] = s_carry; offs[n + 1] = 0; }
+}
+// pass 2: one warp per block copies its first eob levels, scan order
+template <typename LVL>
+__global__ void __launch_bounds__(256) pack_levels_kernel(const int32_t* __restrict__ q_base, const int16_t* __restrict__ scan_base,
+                                                           const SvtB200TrioItem* __restrict__ items, const uint16_t* __restrict__ eobs,
+                                                           uint32_t* __restrict__ offs, int n, LVL* __restrict__ out, uint32_t cap) {
+    const int lane = threadIdx.x & 31;
+    for (int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); b < n; b += gridDim.x * (blockDim.x >> 5)) {
+        const int eob = eobs[b];
+        if (!eob) continue;
+        const SvtB200QuantItem& qi = items[b].quant;
+        const int32_t* q = q_base + qi.q_off;
+        const int16_t* sc = scan_base + qi.scan_off;
+        const uint32_t o = offs[b];
+        for (int k = lane; k < eob; k += 32) {
+            if (o + k >= cap) continue;
+            const int32_t v = q[sc[k]];
+            if (sizeof(LVL) == 2 && (v < -32768 || v > 32767)) atomicAdd(&offs[n + 1], 1u);  // cannot happen for 8-bit pictures; counted, never silent
+            out[o + k] = (LVL)v;
+        }
+    }
+}
+extern "C" int svt_b200_pack_levels_dev(const int32_t* d_qcoeff, const int16_t* d_scan, const SvtB200TrioItem* d_items, const uint16_t* d_eobs,
+                                        int n_items, uint32_t* d_offsets, void* d_levels, int level_bytes, uint32_t capacity, void* stream) {
+    require_ready();
+    if (n_items < 0 || !d_offsets || !d_levels || (level_bytes != 2 && level_bytes != 4)) return SVT_B200_ERR_BAD_ARG;
+    eob_scan_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(d_eobs, n_items, d_offsets);
+    B200_LAUNCH_CHECK();
+    if (n_items) {
+        if (level_bytes == 2)
+            pack_levels_kernel<int16_t><<<grid_for((n_items + 7) / 8, 8), 256, 0, (cudaStream_t)stream>>>(d_qcoeff, d_scan, d_items, d_eobs, d_offsets,
+                                                                                                        n_items, (int16_t*)d_levels, capacity);
+        else
+            pack_levels_kernel<int32_t><<<grid_for((n_items + 7) / 8, 8), 256, 0, (cudaStream_t)stream>>>(d_qcoeff, d_scan, d_items, d_eobs, d_offsets,
+                                                                                                        n_items, (int32_t*)d_levels, capacity);
+        B200_LAUNCH_CHECK();
+    }
     return SVT_B200_OK;
 }
 

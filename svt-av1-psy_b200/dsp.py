@@ -206,6 +206,23 @@ for _n, _extra in (("aom_quantize_b", [vp, vp, ct.c_int32]), ("aom_highbd_quanti
     _f = getattr(lib, "svt_b200_" + _n)
     _f.argtypes = _QA + _extra
     _f.restype = None
+lib.svt_b200_residual_txfm_trio_batch_dev.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, ct.POINTER(ct.c_int), vp, ct.c_int, vp]
+lib.svt_b200_residual_txfm_trio_batch_dev.restype = ct.c_int
+
+
+class ResidualPlane(ct.Structure):  # SvtB200ResidualPlane
+    _fields_ = [("src_off", ct.c_uint64), ("pred_off", ct.c_uint64), ("res_off", ct.c_uint64), ("src_stride", ct.c_int32),
+                ("pred_stride", ct.c_int32), ("res_stride", ct.c_int32), ("w", ct.c_int32), ("h", ct.c_int32), ("reserved", ct.c_int32)]
+
+
+class ResidualPlanes(ct.Structure):
+    _fields_ = [("p", ResidualPlane * 3)]
+
+
+lib.svt_b200_residual_planes_dev.argtypes = [vp, vp, vp, ct.POINTER(ResidualPlanes), ct.c_int, ct.c_int, vp]
+lib.svt_b200_residual_planes_dev.restype = ct.c_int
+lib.svt_b200_pack_levels_dev.argtypes = [vp, vp, vp, vp, ct.c_int, vp, vp, ct.c_int, ct.c_uint32, vp]
+lib.svt_b200_pack_levels_dev.restype = ct.c_int
 lib.svt_b200_quant_batch_dev.argtypes = [vp, vp, vp, vp, vp, vp, vp, ct.c_int, vp, vp]
 lib.svt_b200_quant_batch_dev.restype = ct.c_int
 

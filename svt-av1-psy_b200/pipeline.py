@@ -84,13 +84,18 @@ class FramePipeline:
         # ---- host staging for the end-to-end arm ------------------------------------------------------
         as_t = (lambda a: T.from_numpy(a)) if self.psz == 1 else (lambda a: T.from_numpy(a.view(np.int16)))
         self.h_cur = as_t(np.concatenate([p.reshape(-1) for p in wl.cur])).pin_memory()
-        self.h_res = T.from_numpy(np.concatenate([p.reshape(-1) for p in wl.residual])).pin_memory()
         self.h_pred = as_t(self._pad_planes(wl.pred)).pin_memory()
         # 10-bit input: the 8-bit luma open-loop ME searches is made by the picture-input stage on the host
         self.h_luma8 = None if self.psz == 1 else T.from_numpy(np.ascontiguousarray(wl.me_luma(wl.cur))).pin_memory()
-        self.h_out = {k: T.empty_like(v, device="cpu").pin_memory() for k, v in
-                      dict(me_sad=self.me_sad, me_mv=self.me_mv, q=self.qcoeff, eobs=self.eobs, mse=self.cdef_mse, M=self.M, H=self.Hm,
-                           final=self.final).items()}
+        # what the host-side stages consume: ME results, per-block eobs + the eob-bounded scan-order levels (entropy coder),
+        # CDEF costs, Wiener statistics (the host solves the filters), the filtered picture
+        self.n_tx = len(wl.quant_items)
+        self.level_bytes = 2 if self.bd == 8 else 4
+        self.levels = T.zeros(wl.n_coeffs, dtype=T.int16 if self.level_bytes == 2 else T.int32, device=device)
+        self.level_offsets = T.zeros(self.n_tx + 2, dtype=T.int32, device=device)
+        self.h_out = {k: T.empty_like(v, device="cpu").pin_memory() for k, v in self._small_outputs().items()}
+        self.h_levels = T.empty_like(self.levels, device="cpu").pin_memory()
+        self._res_planes = None
         self.load_inputs()
         T.cuda.synchronize()
 
@@ -131,7 +136,6 @@ class FramePipeline:
         """host -> device copy of one frame's inputs (source picture, residual, prediction)"""
         T = self.torch
         self.cur_flat.copy_(self.h_cur, non_blocking=True)
-        self.residual.copy_(self.h_res, non_blocking=True)
         self.pred.copy_(self.h_pred, non_blocking=True)
         W, H, pad = self.wl.width, self.wl.height, self._full_pad
         # the full-resolution luma of the ME pyramid is the padded (8-bit) source picture
@@ -142,17 +146,30 @@ class FramePipeline:
         s = T.cuda.current_stream().cuda_stream
         assert lib.svt_b200_extend_plane_dev(self.cur_planes[2].data_ptr(), self.cur_planes[2].stride(0), W, H, pad, pad, s) == 0
 
+    def _small_outputs(self):
+        return dict(me_sad=self.me_sad, me_mv=self.me_mv, eobs=self.eobs, level_offsets=self.level_offsets, mse=self.cdef_mse, M=self.M, H=self.Hm,
+                    final=self.final)
+
     def read_outputs(self):
-        for k, src in dict(me_sad=self.me_sad, me_mv=self.me_mv, q=self.qcoeff, eobs=self.eobs, mse=self.cdef_mse, M=self.M, H=self.Hm,
-                           final=self.final).items():
+        """device -> host, part 1: everything of fixed size (includes the level offsets, whose last entries say how many levels follow)"""
+        for k, src in self._small_outputs().items():
             self.h_out[k].copy_(src, non_blocking=True)
+
+    def read_levels(self):
+        """part 2, once part 1 has arrived: exactly sum(eob) levels.  Returns the bytes copied."""
+        total = int(self.h_out["level_offsets"][self.n_tx])
+        assert int(self.h_out["level_offsets"][self.n_tx + 1]) == 0, "a quantised level did not fit the packed format"
+        total = min(total, self.levels.numel())
+        if total:
+            self.h_levels[:total].copy_(self.levels[:total], non_blocking=True)
+        return total * self.level_bytes
 
     @property
     def h2d_bytes(self):
-        return (self.h_cur.numel() + self.h_pred.numel()) * self.psz + self.h_res.numel() * 2 + (0 if self.h_luma8 is None else self.h_luma8.numel())
+        return (self.h_cur.numel() + self.h_pred.numel()) * self.psz + (0 if self.h_luma8 is None else self.h_luma8.numel())
 
     @property
-    def d2h_bytes(self):
+    def d2h_fixed_bytes(self):
         return sum(v.numel() * v.element_size() for v in self.h_out.values())
 
     # -- the calls of one frame, in path order (each is one T2 entry point of include/svt_b200.h) -----------
@@ -165,9 +182,30 @@ class FramePipeline:
         assert rc == 0
 
     def call_txfm_trio(self, s):
-        rc = lib.svt_b200_txfm_trio_batch_dev(self.residual.data_ptr(), self.pred.data_ptr(), self.recon.data_ptr(), self.qcoeff.data_ptr(),
-                                              self.dqcoeff.data_ptr(), self.iscan.data_ptr(), self.qm.data_ptr(), self.trio_items.data_ptr(),
-                                              self.tx_counts, self.eobs.data_ptr(), self.psz, s)
+        """residual (source - prediction) -> transform -> quantise -> inverse / reconstruction, one fused call"""
+        rc = lib.svt_b200_residual_txfm_trio_batch_dev(self.cur_flat.data_ptr(), self.pred.data_ptr(), self.recon.data_ptr(), self.qcoeff.data_ptr(),
+                                                       self.dqcoeff.data_ptr(), self.iscan.data_ptr(), self.qm.data_ptr(), self.trio_items.data_ptr(),
+                                                       self.tx_counts, self.eobs.data_ptr(), self.psz, s)
+        assert rc == 0
+
+    def call_pack_levels(self, s):
+        rc = lib.svt_b200_pack_levels_dev(self.qcoeff.data_ptr(), self.scan.data_ptr(), self.trio_items.data_ptr(), self.eobs.data_ptr(), self.n_tx,
+                                          self.level_offsets.data_ptr(), self.levels.data_ptr(), self.level_bytes, self.levels.numel(), s)
+        assert rc == 0
+
+    def call_residual(self, s):
+        """svt_aom_residual_kernel over the three planes (the un-fused chain materialises the residual)"""
+        wl = self.wl
+        if self._res_planes is None:
+            off, _ = wl.padded_offsets()
+            soff, _ = wl.flat_offsets()
+            self._res_planes = dsp.ResidualPlanes()
+            for p in range(3):
+                th, st = wl.padded_shape(p)
+                w, h = wl.plane_dims[p]
+                self._res_planes.p[p] = dsp.ResidualPlane(soff[p], off[p] + wl.PAD * st + wl.PAD, soff[p], w, st, w, w, h, 0)
+        rc = lib.svt_b200_residual_planes_dev(self.cur_flat.data_ptr(), self.pred.data_ptr(), self.residual.data_ptr(), ct.byref(self._res_planes), 3,
+                                              self.psz, s)
         assert rc == 0
 
     # the same three steps as separate calls (TPL / MD use them individually); results are identical
@@ -234,7 +272,8 @@ class FramePipeline:
     # (call, stage it belongs to, the kernels it launches)
     CALLS = (("me_pyramid", "me", "downsample_2d_kernel+pad_plane_kernel"),
              ("me_search", "me", "hme_fused_kernel + fullpel_search_kernel"),
-             ("txfm_trio", "tx", "trio_txfm_kernel<4..64> (forward transform + quantise + inverse transform fused)"),
+             ("txfm_trio", "tx", "trio_txfm_kernel<4..64> (residual + forward transform + quantise + inverse transform fused)"),
+             ("pack_levels", "tx", "eob_scan_kernel+pack_levels_kernel"),
              ("cdef_search", "cdef", "cdef_dir_kernel+cdef_search_kernel"),
              ("cdef_apply", "cdef", "cdef_apply_kernel"),
              ("rest_extend", "rest", "pad_plane_kernel"),

@@ -6,8 +6,9 @@ kernels hand to the dispatched DSP functions for one 8-bit 4:2:0 picture at M8 /
 (search geometry from enc_mode_config.c:138-345 with qp 30, reference distance 1):
 
   ME     HME L0 4 regions of 16x4, L1/L2 8x3, full-pel 8x3, SUB_SAD, 2 references, every 64x64 block
-  TX     forward transform -> fp quantizer with quantisation matrices (PSY default) -> inverse +
-         reconstruction, every luma and chroma sample once, in a 64..4 transform-size mix
+  TX     residual (source - motion-compensated prediction) -> forward transform -> fp quantizer with
+         quantisation matrices (PSY default) -> inverse + reconstruction (skipped for all-zero blocks, as the
+         encode pass does), every luma and chroma sample once, in a 64..4 transform-size mix
   CDEF   strength search over 6 (luma, chroma) candidates on the non-skip 8x8 blocks, then apply
   REST   Wiener statistics (7x7 luma, 5x5 chroma) per restoration unit + separable Wiener filter
 
@@ -113,9 +114,18 @@ class FrameWorkload:
         seq = synth_sequence(self.width, self.height, self.n_refs + 1, seed, self.bit_depth)
         self.cur = seq[1]
         self.refs = [seq[0], seq[2]][:self.n_refs]
-        # prediction = previous picture (zero-motion inter prediction); residual = cur - pred
-        self.pred = [self.refs[0][p] for p in range(3)]
+        # prediction = the previous picture displaced by the sequence's global motion (the panorama pans (3, 1) luma
+        # pixels per frame): an integer-pel motion-compensated inter prediction, edge-clamped like a padded reference.
+        # Luma residual = the sensor noise of the two pictures; chroma keeps the half-pel mismatch of its (1.5, 0.5) motion.
+        self.pred = [self._shift(self.refs[0][p], *((3, 1) if p == 0 else (2, 1))) for p in range(3)]
         self.residual = [self.cur[p].astype(np.int16) - self.pred[p].astype(np.int16) for p in range(3)]
+
+    @staticmethod
+    def _shift(plane, dx, dy):
+        h, w = plane.shape
+        ys = np.clip(np.arange(h) + dy, 0, h - 1)
+        xs = np.clip(np.arange(w) + dx, 0, w - 1)
+        return np.ascontiguousarray(plane[np.ix_(ys, xs)])
 
     def with_seed(self, seed):
         """the same work lists (they do not depend on the content) over another synthetic sequence"""
@@ -283,15 +293,16 @@ class FrameWorkload:
             "me_search": int((1 + R) * 1.3125 * W * H + n64 * R * 85 * 8),        # every pyramid read once + SAD/MV out
             "fwd_txfm": 6 * N, "quant": 12 * N, "inv_txfm": (4 + 2 * bpp) * N,    # (22 + 2 bpp) N in total
             "txfm_trio": (22 + 2 * bpp) * N,                                      # SURVEY 8(d)'s figure for the unfused chain
-            # what the FUSED call has to move: residual (2N) + prediction in, qcoeff + dqcoeff (4N each) + recon out
-            "txfm_trio_fused_min": (2 + 8 + 2 * bpp) * N,
+            # what the FUSED call has to move: source + prediction in, qcoeff + dqcoeff (4N each) + recon out
+            "txfm_trio_fused_min": (8 + 3 * bpp) * N,    # source + prediction in, qcoeff + dqcoeff + recon out
+            "pack_levels": 6 * N,                                                 # upper bound: every level read (4 B) and written (<= 4 B) once more
             "cdef_search": int(2 * bpp * N + n64 * 2 * len(self.cdef_str_y) * 8),  # recon + source in, mse out
             "cdef_apply": 2 * bpp * N,                                            # recon in, filtered out
             "rest_extend": 0,
             "wiener_stats": int(2 * bpp * N + len(self.stats_items) * (49 + 2401) * 8),
             "wiener_filter": 2 * bpp * N,
         }
-        stage_of = {"me_pyramid": "me", "me_search": "me", "txfm_trio": "tx", "cdef_search": "cdef",
+        stage_of = {"me_pyramid": "me", "me_search": "me", "txfm_trio": "tx", "pack_levels": "tx", "cdef_search": "cdef",
                     "cdef_apply": "cdef", "rest_extend": "rest", "wiener_stats": "rest", "wiener_filter": "rest"}
         out = dict(calls)
         for st in ("me", "tx", "cdef", "rest"):

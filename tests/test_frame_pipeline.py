@@ -123,6 +123,8 @@ def test_frame_matches_committed_golden_fixture(b200, name):
     assert not bad, bad
     # the forward coefficients only exist on the 3-call transform chain
     s = torch.cuda.current_stream().cuda_stream
+    fp.call_residual(s)
     fp.call_fwd_txfm(s)
     torch.cuda.synchronize()
+    assert digest(fp.residual) == g["sha256"]["residual"]
     assert digest(fp.coeff) == g["sha256"]["coeff"]
