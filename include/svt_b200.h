@@ -145,10 +145,12 @@ SVT_B200_API void svt_b200_inv_txfm2d_add(const int32_t* input, uint16_t* output
 SVT_B200_API void svt_b200_inv_txfm_add_8bit(const int32_t* dqcoeff, uint8_t* dst_r, int32_t stride_r, uint8_t* dst_w,
                                              int32_t stride_w, int tx_type, int tx_size);
 
-/* T1 named forms, one per reference pointer, identical argument lists. */
+/* T1 named forms, one per reference pointer, identical argument lists.  TxType / TxSize / BlockSize are
+ * ATTRIBUTE_PACKED one-byte enums in the reference (Source/Lib/Codec/definitions.h:849-878,972-995): they are
+ * uint8_t here, so the prototypes are assignment-compatible with the rtcd pointers without casts. */
 #define SVT_B200_DECL_FWD(WxH)                                                                              \
     SVT_B200_API void svt_b200_av1_fwd_txfm2d_##WxH(int16_t* input, int32_t* output, uint32_t input_stride, \
-                                                    int transform_type, uint8_t bit_depth);
+                                                    uint8_t transform_type /* TxType: 1-byte packed enum */, uint8_t bit_depth);
 SVT_B200_DECL_FWD(4x4) SVT_B200_DECL_FWD(8x8) SVT_B200_DECL_FWD(16x16) SVT_B200_DECL_FWD(32x32) SVT_B200_DECL_FWD(64x64)
 SVT_B200_DECL_FWD(4x8) SVT_B200_DECL_FWD(8x4) SVT_B200_DECL_FWD(8x16) SVT_B200_DECL_FWD(16x8) SVT_B200_DECL_FWD(16x32)
 SVT_B200_DECL_FWD(32x16) SVT_B200_DECL_FWD(32x64) SVT_B200_DECL_FWD(64x32) SVT_B200_DECL_FWD(4x16) SVT_B200_DECL_FWD(16x4)
@@ -166,15 +168,15 @@ SVT_B200_DECL_FWD(8x32_N4) SVT_B200_DECL_FWD(32x8_N4) SVT_B200_DECL_FWD(16x64_N4
 #undef SVT_B200_DECL_FWD
 #define SVT_B200_DECL_INV_A(WxH)                                                                                \
     SVT_B200_API void svt_b200_av1_inv_txfm2d_add_##WxH(const int32_t* input, uint16_t* output_r, int32_t stride_r, \
-                                                        uint16_t* output_w, int32_t stride_w, int tx_type, int32_t bd);
+                                                        uint16_t* output_w, int32_t stride_w, uint8_t tx_type, int32_t bd);
 #define SVT_B200_DECL_INV_B(WxH)                                                                                \
     SVT_B200_API void svt_b200_av1_inv_txfm2d_add_##WxH(const int32_t* input, uint16_t* output_r, int32_t stride_r, \
-                                                        uint16_t* output_w, int32_t stride_w, int tx_type,       \
-                                                        int tx_size, int32_t bd);
+                                                        uint16_t* output_w, int32_t stride_w, uint8_t tx_type,   \
+                                                        uint8_t tx_size, int32_t bd);
 #define SVT_B200_DECL_INV_C(WxH)                                                                                \
     SVT_B200_API void svt_b200_av1_inv_txfm2d_add_##WxH(const int32_t* input, uint16_t* output_r, int32_t stride_r, \
-                                                        uint16_t* output_w, int32_t stride_w, int tx_type,       \
-                                                        int tx_size, int32_t eob, int32_t bd);
+                                                        uint16_t* output_w, int32_t stride_w, uint8_t tx_type,   \
+                                                        uint8_t tx_size, int32_t eob, int32_t bd);
 SVT_B200_DECL_INV_A(4x4) SVT_B200_DECL_INV_A(8x8) SVT_B200_DECL_INV_A(16x16) SVT_B200_DECL_INV_A(32x32) SVT_B200_DECL_INV_A(64x64)
 SVT_B200_DECL_INV_B(4x8) SVT_B200_DECL_INV_B(8x4) SVT_B200_DECL_INV_B(4x16) SVT_B200_DECL_INV_B(16x4)
 SVT_B200_DECL_INV_C(8x16) SVT_B200_DECL_INV_C(16x8) SVT_B200_DECL_INV_C(16x32) SVT_B200_DECL_INV_C(32x16) SVT_B200_DECL_INV_C(32x8)
@@ -412,10 +414,10 @@ SVT_B200_API void     svt_b200_cdef_filter_block(uint8_t* dst8, uint16_t* dst16,
 SVT_B200_API void     svt_b200_aom_copy_rect8_8bit_to_16bit(uint16_t* dst, int32_t dstride, const uint8_t* src,
                                                             int32_t sstride, int32_t v, int32_t h);
 SVT_B200_API uint64_t svt_b200_compute_cdef_dist_16bit(const uint16_t* dst, int32_t dstride, const uint16_t* src,
-                                                       const SvtB200CdefList* dlist, int32_t cdef_count, int32_t bsize,
+                                                       const SvtB200CdefList* dlist, int32_t cdef_count, uint8_t bsize /* BlockSize */,
                                                        int32_t coeff_shift, int32_t pli, uint8_t subsampling_factor);
 SVT_B200_API uint64_t svt_b200_compute_cdef_dist_8bit(const uint8_t* dst8, int32_t dstride, const uint8_t* src8,
-                                                      const SvtB200CdefList* dlist, int32_t cdef_count, int32_t bsize,
+                                                      const SvtB200CdefList* dlist, int32_t cdef_count, uint8_t bsize /* BlockSize */,
                                                       int32_t coeff_shift, int32_t pli, uint8_t subsampling_factor);
 SVT_B200_API uint64_t svt_b200_search_one_dual(int* lev0, int* lev1, int nb_strengths, uint64_t** mse[2], int sb_count,
                                                int start_gi, int end_gi);

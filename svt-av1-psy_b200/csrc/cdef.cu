@@ -675,12 +675,12 @@ static uint64_t cdef_dist_t1(const T* dst, int32_t dstride, const T* src, const 
     return *l->h<uint64_t>(o_o);
 }
 extern "C" uint64_t svt_b200_compute_cdef_dist_16bit(const uint16_t* dst, int32_t dstride, const uint16_t* src,
-                                                     const SvtB200CdefList* dlist, int32_t cdef_count, int32_t bsize,
+                                                     const SvtB200CdefList* dlist, int32_t cdef_count, uint8_t bsize,
                                                      int32_t coeff_shift, int32_t pli, uint8_t subsampling_factor) {
     return cdef_dist_t1<uint16_t>(dst, dstride, src, (const uint8_t*)dlist, cdef_count, bsize, coeff_shift, pli, subsampling_factor);
 }
 extern "C" uint64_t svt_b200_compute_cdef_dist_8bit(const uint8_t* dst8, int32_t dstride, const uint8_t* src8,
-                                                    const SvtB200CdefList* dlist, int32_t cdef_count, int32_t bsize,
+                                                    const SvtB200CdefList* dlist, int32_t cdef_count, uint8_t bsize,
                                                     int32_t coeff_shift, int32_t pli, uint8_t subsampling_factor) {
     return cdef_dist_t1<uint8_t>(dst8, dstride, src8, (const uint8_t*)dlist, cdef_count, bsize, coeff_shift, pli, subsampling_factor);
 }

@@ -785,7 +785,7 @@ B200_HANDLE(16x64, 16, 64) B200_HANDLE(32x64, 32, 64) B200_HANDLE(64x16, 64, 16)
 // ---- named T1 wrappers: one symbol per reference function pointer --------------------------------
 #define B200_FWD(WxH, SZ)                                                                                       \
     extern "C" void svt_b200_av1_fwd_txfm2d_##WxH(int16_t* input, int32_t* output, uint32_t input_stride,        \
-                                                  int transform_type, uint8_t bit_depth) {                       \
+                                                  uint8_t transform_type, uint8_t bit_depth) {                       \
         svt_b200_fwd_txfm2d(input, output, input_stride, transform_type, SZ, bit_depth);                         \
     }
 B200_FWD(4x4, 0) B200_FWD(8x8, 1) B200_FWD(16x16, 2) B200_FWD(32x32, 3) B200_FWD(64x64, 4) B200_FWD(4x8, 5) B200_FWD(8x4, 6)
@@ -793,11 +793,11 @@ B200_FWD(8x16, 7) B200_FWD(16x8, 8) B200_FWD(16x32, 9) B200_FWD(32x16, 10) B200_
 B200_FWD(4x16, 13) B200_FWD(16x4, 14) B200_FWD(8x32, 15) B200_FWD(32x8, 16) B200_FWD(16x64, 17) B200_FWD(64x16, 18)
 #define B200_FWD_PART(WxH, SZ)                                                                                  \
     extern "C" void svt_b200_av1_fwd_txfm2d_##WxH##_N2(int16_t* input, int32_t* output, uint32_t input_stride,   \
-                                                       int transform_type, uint8_t bit_depth) {                  \
+                                                       uint8_t transform_type, uint8_t bit_depth) {                  \
         svt_b200_fwd_txfm2d_partial(input, output, input_stride, transform_type, SZ, bit_depth, 1);              \
     }                                                                                                           \
     extern "C" void svt_b200_av1_fwd_txfm2d_##WxH##_N4(int16_t* input, int32_t* output, uint32_t input_stride,   \
-                                                       int transform_type, uint8_t bit_depth) {                  \
+                                                       uint8_t transform_type, uint8_t bit_depth) {                  \
         svt_b200_fwd_txfm2d_partial(input, output, input_stride, transform_type, SZ, bit_depth, 2);              \
     }
 B200_FWD_PART(4x4, 0) B200_FWD_PART(8x8, 1) B200_FWD_PART(16x16, 2) B200_FWD_PART(32x32, 3) B200_FWD_PART(64x64, 4) B200_FWD_PART(4x8, 5)
@@ -806,20 +806,20 @@ B200_FWD_PART(64x32, 12) B200_FWD_PART(4x16, 13) B200_FWD_PART(16x4, 14) B200_FW
 B200_FWD_PART(64x16, 18)
 #define B200_INV_A(WxH, SZ)                                                                                     \
     extern "C" void svt_b200_av1_inv_txfm2d_add_##WxH(const int32_t* input, uint16_t* output_r, int32_t stride_r, \
-                                                      uint16_t* output_w, int32_t stride_w, int tx_type, int32_t bd) { \
+                                                      uint16_t* output_w, int32_t stride_w, uint8_t tx_type, int32_t bd) { \
         svt_b200_inv_txfm2d_add(input, output_r, stride_r, output_w, stride_w, tx_type, SZ, bd);                 \
     }
 #define B200_INV_B(WxH, SZ)                                                                                     \
     extern "C" void svt_b200_av1_inv_txfm2d_add_##WxH(const int32_t* input, uint16_t* output_r, int32_t stride_r, \
-                                                      uint16_t* output_w, int32_t stride_w, int tx_type,         \
-                                                      int tx_size, int32_t bd) {                                 \
+                                                      uint16_t* output_w, int32_t stride_w, uint8_t tx_type,     \
+                                                      uint8_t tx_size, int32_t bd) {                             \
         (void)tx_size;                                                                                           \
         svt_b200_inv_txfm2d_add(input, output_r, stride_r, output_w, stride_w, tx_type, SZ, bd);                 \
     }
 #define B200_INV_C(WxH, SZ)                                                                                     \
     extern "C" void svt_b200_av1_inv_txfm2d_add_##WxH(const int32_t* input, uint16_t* output_r, int32_t stride_r, \
-                                                      uint16_t* output_w, int32_t stride_w, int tx_type,         \
-                                                      int tx_size, int32_t eob, int32_t bd) {                    \
+                                                      uint16_t* output_w, int32_t stride_w, uint8_t tx_type,     \
+                                                      uint8_t tx_size, int32_t eob, int32_t bd) {                \
         (void)tx_size;                                                                                           \
         (void)eob;                                                                                               \
         svt_b200_inv_txfm2d_add(input, output_r, stride_r, output_w, stride_w, tx_type, SZ, bd);                 \

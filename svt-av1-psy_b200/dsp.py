@@ -153,7 +153,7 @@ def svt_av1_fwd_txfm2d(residual, stride, tx_type, tx_size, bit_depth=8, named=Fa
     out = np.zeros(TX_W[tx_size] * TX_H[tx_size], np.int32)
     if named:
         f = getattr(lib, "svt_b200_av1_fwd_txfm2d_" + TX_NAME[tx_size])
-        f.argtypes = [vp, vp, ct.c_uint32, ct.c_int, ct.c_uint8]
+        f.argtypes = [vp, vp, ct.c_uint32, ct.c_uint8, ct.c_uint8]
         f.restype = None
         f(_ptr(residual), _ptr(out), stride, tx_type, bit_depth)
     else:
@@ -317,7 +317,7 @@ lib.svt_b200_aom_copy_rect8_8bit_to_16bit.argtypes = [vp, ct.c_int32, vp, ct.c_i
 lib.svt_b200_aom_copy_rect8_8bit_to_16bit.restype = None
 for _n in ("16bit", "8bit"):
     _f = getattr(lib, "svt_b200_compute_cdef_dist_" + _n)
-    _f.argtypes = [vp, ct.c_int32, vp, vp, ct.c_int32, ct.c_int32, ct.c_int32, ct.c_int32, ct.c_uint8]
+    _f.argtypes = [vp, ct.c_int32, vp, vp, ct.c_int32, ct.c_uint8, ct.c_int32, ct.c_int32, ct.c_uint8]
     _f.restype = ct.c_uint64
 lib.svt_b200_search_one_dual.argtypes = [vp, vp, ct.c_int, vp, ct.c_int, ct.c_int, ct.c_int]
 lib.svt_b200_search_one_dual.restype = ct.c_uint64
@@ -451,16 +451,16 @@ def unbound_symbols():
 for _i, _n in enumerate(TX_NAME):
     for _sfx in ("", "_N2", "_N4"):
         _f = getattr(lib, "svt_b200_av1_fwd_txfm2d_" + _n + _sfx)
-        _f.argtypes = [vp, vp, ct.c_uint32, ct.c_int, ct.c_uint8]
+        _f.argtypes = [vp, vp, ct.c_uint32, ct.c_uint8, ct.c_uint8]
         _f.restype = None
     _g = getattr(lib, "svt_b200_av1_inv_txfm2d_add_" + _n)
-    _base = [vp, vp, ct.c_int32, vp, ct.c_int32, ct.c_int]
+    _base = [vp, vp, ct.c_int32, vp, ct.c_int32, ct.c_uint8]
     if _i in (0, 1, 2, 3, 4):
         _g.argtypes = _base + [ct.c_int32]
     elif _i in (5, 6, 13, 14):
-        _g.argtypes = _base + [ct.c_int, ct.c_int32]
+        _g.argtypes = _base + [ct.c_uint8, ct.c_int32]
     else:
-        _g.argtypes = _base + [ct.c_int, ct.c_int32, ct.c_int32]
+        _g.argtypes = _base + [ct.c_uint8, ct.c_int32, ct.c_int32]
     _g.restype = None
 
 

@@ -267,6 +267,44 @@ def test_committed_golden_fixtures_are_what_the_reference_computes(oracle, refc)
         assert now["sha256"] == g["sha256"], name
 
 
+def _lr_case(lib, kind, seed=34):
+    """a fixed set of restoration units (luma and chroma geometry, both optimized_lr modes, interior / edge units) through
+    lib.ref_lr_filter_unit_{wiener,sgrproj}_8bit -- i.e. the reference's svt_av1_loop_restoration_filter_unit with whatever
+    the dispatch pointers of `lib` currently hold.  Returns the filtered planes."""
+    import ctypes as ct
+    r = np.random.default_rng(seed)
+    fn = getattr(lib, "ref_lr_filter_unit_%s_8bit" % kind)
+    fn.restype = None
+    PAD, outs = 32, []
+    for ss in (0, 1):
+        W, Hh = (328 >> ss), (200 >> ss)
+        stride = W + 2 * PAD
+        plane = r.integers(0, 256, (Hh + 2 * PAD) * stride).astype(np.uint8)
+        origin = PAD * stride + PAD
+        nstripes = (Hh + (8 >> ss) + (64 >> ss) - 1) // (64 >> ss) + 1
+        bstride = ((W + 8 + 31) // 32) * 32
+        above = r.integers(0, 256, 2 * nstripes * bstride).astype(np.uint8)
+        below = r.integers(0, 256, 2 * nstripes * bstride).astype(np.uint8)
+        tile = np.array([0, 0, W, Hh], np.int32)
+        ru = 128 >> ss
+        for opt in (0, 1):
+            for (hs, he, vs, ve) in [(0, min(ru, W), 0, min(ru + (ru // 2), Hh)), (ru, W, 0, Hh), (0, W, (ru - (8 >> ss)), Hh)]:
+                limits = np.array([hs, he, vs, ve], np.int32)
+                src, dst = plane.copy(), np.full_like(plane, 7)
+                V = lambda a, o=0: ct.c_void_p(a.ctypes.data + o)  # noqa: E731
+                if kind == "wiener":
+                    t0, t1, t2 = int(r.integers(-5, 11)), int(r.integers(-23, 9)), int(r.integers(-17, 47))
+                    taps = np.array([t0, t1, t2, -2 * (t0 + t1 + t2), t2, t1, t0, 0], np.int16)
+                    fn(V(src, origin), stride, V(dst, origin), stride, V(limits), V(taps), V(taps), V(above), V(below), bstride, V(tile), 0, ss, ss, opt)
+                else:
+                    ep = int(r.integers(0, 14))
+                    xqd = np.array([int(r.integers(-96, 32)), int(r.integers(-32, 96))], np.int32)
+                    fn(V(src, origin), stride, V(dst, origin), stride, V(limits), ep, V(xqd), V(above), V(below), bstride, V(tile), 0, ss, ss, opt)
+                assert np.array_equal(src, plane)
+                outs.append(dst)
+    return outs
+
+
 def test_port_lr_unit_with_stripe_boundaries_matches_reference(oracle, refc):
     """SURVEY 8 a13 groundwork: one restoration unit filtered stripe by stripe with the saved boundary lines
     (svt_av1_loop_restoration_filter_unit, restoration.c:1067-1135) -- our restatement against the reference."""
