@@ -96,12 +96,16 @@ static uint64_t b200_cdef_dist_8bit(const uint8_t* dst8, int32_t dstride, const 
 }
 
 static int g_count = 0;
-#define BIND(ptr, fn) do { (ptr) = (fn); g_count++; } while (0)
+static unsigned g_groups = ~0u, g_cur = 0; /* SVT_B200_RTCD_GROUPS (debug): bit mask of the kernel groups to install, default all */
+#define GROUP(bit) g_cur = (bit)
+#define BIND(ptr, fn) do { if (g_groups & g_cur) { (ptr) = (fn); g_count++; } } while (0)
 #define BIND_FWD(WxH)                                                    \
     BIND(svt_av1_fwd_txfm2d_##WxH, svt_b200_av1_fwd_txfm2d_##WxH);        \
     BIND(svt_av1_fwd_txfm2d_##WxH##_N2, svt_b200_av1_fwd_txfm2d_##WxH##_N2); \
     BIND(svt_av1_fwd_txfm2d_##WxH##_N4, svt_b200_av1_fwd_txfm2d_##WxH##_N4); \
-    BIND(svt_av1_inv_txfm2d_add_##WxH, svt_b200_av1_inv_txfm2d_add_##WxH)
+    g_cur = 8u;                                                           \
+    BIND(svt_av1_inv_txfm2d_add_##WxH, svt_b200_av1_inv_txfm2d_add_##WxH); \
+    g_cur = 4u
 #define BIND_SAD(MxN)                                        \
     BIND(svt_aom_sad##MxN, svt_b200_aom_sad##MxN);            \
     BIND(svt_aom_sad##MxN##x4d, svt_b200_aom_sad##MxN##x4d)
@@ -115,6 +119,11 @@ int svt_b200_install_rtcd(int device) {
     const int rc = svt_b200_init(device);
     if (rc != SVT_B200_OK && rc != SVT_B200_ERR_ALREADY_INIT) return rc;
     g_count = 0;
+    {
+        const char* m = getenv("SVT_B200_RTCD_GROUPS");
+        g_groups = (m && *m) ? (unsigned)strtoul(m, NULL, 0) : ~0u;
+    }
+    GROUP(1u);
     /* K1 / K2 / K3: SAD search, SAD pyramid, single SADs (aom_dsp_rtcd.h:779,842-856,275-403) */
     BIND(svt_sad_loop_kernel, svt_b200_sad_loop_kernel);
     BIND(svt_nxm_sad_kernel, svt_b200_nxm_sad_kernel);
@@ -127,17 +136,21 @@ int svt_b200_install_rtcd(int device) {
     BIND_SAD(128x128); BIND_SAD(128x64); BIND_SAD(64x128); BIND_SAD(64x64); BIND_SAD(64x32); BIND_SAD(64x16); BIND_SAD(32x64); BIND_SAD(32x32);
     BIND_SAD(32x16); BIND_SAD(32x8); BIND_SAD(16x64); BIND_SAD(16x32); BIND_SAD(16x16); BIND_SAD(16x8); BIND_SAD(16x4); BIND_SAD(8x32);
     BIND_SAD(8x16); BIND_SAD(8x8); BIND_SAD(8x4); BIND_SAD(4x16); BIND_SAD(4x8); BIND_SAD(4x4);
+    GROUP(2u);
     /* K4: Hadamard / SATD (svt_aom_hadamard_4x4 is a #define to the C function in the reference, not a pointer) */
     BIND(svt_aom_hadamard_8x8, svt_b200_aom_hadamard_8x8);
     BIND(svt_aom_hadamard_16x16, svt_b200_aom_hadamard_16x16);
     BIND(svt_aom_hadamard_32x32, svt_b200_aom_hadamard_32x32);
     BIND(svt_aom_satd, svt_b200_aom_satd);
+    GROUP(4u);
     /* K5 / K6: forward (full, N2, N4) and inverse transforms, 19 sizes */
     BIND_FWD(4x4); BIND_FWD(8x8); BIND_FWD(16x16); BIND_FWD(32x32); BIND_FWD(64x64); BIND_FWD(4x8); BIND_FWD(8x4); BIND_FWD(8x16);
     BIND_FWD(16x8); BIND_FWD(16x32); BIND_FWD(32x16); BIND_FWD(32x64); BIND_FWD(64x32); BIND_FWD(4x16); BIND_FWD(16x4); BIND_FWD(8x32);
     BIND_FWD(32x8); BIND_FWD(16x64); BIND_FWD(64x16);
     BIND_HANDLE(16x64); BIND_HANDLE(32x64); BIND_HANDLE(64x16); BIND_HANDLE(64x32); BIND_HANDLE(64x64);
+    GROUP(8u);
     BIND(svt_av1_inv_txfm_add, b200_av1_inv_txfm_add);
+    GROUP(16u);
     /* K7: quantizers */
     BIND(svt_aom_quantize_b, svt_b200_aom_quantize_b);
     BIND(svt_aom_highbd_quantize_b, svt_b200_aom_highbd_quantize_b);
@@ -149,6 +162,7 @@ int svt_b200_install_rtcd(int device) {
     BIND(svt_av1_quantize_fp_qm, svt_b200_av1_quantize_fp_qm);
     BIND(svt_av1_highbd_quantize_fp, svt_b200_av1_highbd_quantize_fp);
     BIND(svt_av1_highbd_quantize_fp_qm, svt_b200_av1_highbd_quantize_fp_qm);
+    GROUP(32u);
     /* K8: CDEF */
     BIND(svt_aom_cdef_find_dir, svt_b200_aom_cdef_find_dir);
     BIND(svt_aom_cdef_find_dir_dual, svt_b200_aom_cdef_find_dir_dual);
@@ -157,11 +171,13 @@ int svt_b200_install_rtcd(int device) {
     BIND(svt_compute_cdef_dist_16bit, b200_cdef_dist_16bit);
     BIND(svt_compute_cdef_dist_8bit, b200_cdef_dist_8bit);
     BIND(svt_search_one_dual, svt_b200_search_one_dual);
+    GROUP(64u);
     /* K9 / K11: Wiener filter + statistics */
     BIND(svt_av1_wiener_convolve_add_src, b200_wiener_convolve_add_src);
     BIND(svt_av1_highbd_wiener_convolve_add_src, b200_highbd_wiener_convolve_add_src);
     BIND(svt_av1_compute_stats, svt_b200_av1_compute_stats);
     BIND(svt_av1_compute_stats_highbd, b200_compute_stats_highbd);
+    GROUP(128u);
     /* K10 / K12: self-guided restoration */
     BIND(svt_av1_selfguided_restoration, b200_selfguided_restoration);
     BIND(svt_apply_selfguided_restoration, b200_apply_selfguided_restoration);

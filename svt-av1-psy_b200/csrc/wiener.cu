@@ -237,10 +237,17 @@ stats_accum_kernel(const PIX* __restrict__ dgd_base, const PIX* __restrict__ src
         for (int r0 = s.v_start; r0 < s.v_end; r0 += kStatsTileH) {
             const int nrows = min(kStatsTileH, s.v_end - r0);
             __syncthreads();
-            // rows r0-3 .. r0+nrows+2, columns c0-3 .. c0+ncols+2 as (pixel - avg)
-            for (int t = threadIdx.x; t < (nrows + 6) * (ncols + 6); t += blockDim.x) {
-                const int rr = t / (ncols + 6), cc = t - rr * (ncols + 6);
-                s_d[rr * kStatsPitch + cc] = (int16_t)((int)dgd[(ptrdiff_t)(r0 - 3 + rr) * s.dgd_stride + c0 - 3 + cc] - avg);
+            // rows r0-3 .. r0+nrows+2, columns c0-3 .. c0+ncols+2 as (pixel - avg); nothing outside the window the reference
+            // itself reads (half = win / 2 pixels around the unit) is touched -- a caller's buffer ends there
+            {
+                const int hw = s.wiener_win >> 1;
+                const int vlo = s.v_start - hw, vhi = s.v_end + hw, hlo = s.h_start - hw, hhi = s.h_end + hw;
+                for (int t = threadIdx.x; t < (nrows + 6) * (ncols + 6); t += blockDim.x) {
+                    const int rr = t / (ncols + 6), cc = t - rr * (ncols + 6);
+                    const int row = r0 - 3 + rr, col = c0 - 3 + cc;
+                    const bool in = row >= vlo && row < vhi && col >= hlo && col < hhi;
+                    s_d[rr * kStatsPitch + cc] = in ? (int16_t)((int)dgd[(ptrdiff_t)row * s.dgd_stride + col] - avg) : (int16_t)0;
+                }
             }
             for (int t = threadIdx.x; t < nrows * ncols; t += blockDim.x) {
                 const int rr = t / ncols, cc = t - rr * ncols;
