@@ -556,6 +556,54 @@ SVT_B200_API int svt_b200_sgr_units_dev(const void* d_dgd, const SvtB200SgrUnit*
                                         int32_t* d_flt1, int bit_depth, int max_w, int max_h, void* stream);
 
 /* ------------------------------------------------------------------------------------------ */
+/* a13  loop-restoration drivers  (reference: Source/Lib/Codec/restoration.c:257-435,1067-1294,  */
+/*      1506-1700; restoration_pick.c:103)                                                      */
+/* ------------------------------------------------------------------------------------------ */
+/* One plane of a picture for the restoration stage.  All pointers are DEVICE memory addressing pixel (0,0); strides
+ * in pixels; pixels are uint8 (bit_depth 8) or uint16.  boundary_above / boundary_below use the layout of the
+ * reference's RestorationStripeBoundaries (restoration.h): row 2 * stripe + i (i = 0, 1), boundary_stride pixels per
+ * row, logical column x stored at index x + 4 (RESTORATION_EXTRA_HORZ), columns -4 .. width + 3 filled. */
+typedef struct SvtB200LrPlane {
+    const void* deblocked;   /* loop-filtered picture BEFORE CDEF: source of the interior stripe-boundary lines */
+    const void* cdef;        /* CDEF output: the restoration input; source of the picture-top / -bottom lines */
+    void*       dst;         /* restored output (cm->rst_frame) */
+    const void* src;         /* source picture, only for svt_b200_lr_unit_sse_dev */
+    void*       boundary_above;
+    void*       boundary_below;
+    int32_t     stride_deblocked, stride_cdef, stride_dst, stride_src;
+    int32_t     boundary_stride; /* svt_b200_lr_boundary_stride(width) */
+    int32_t     width, height;   /* crop size of this plane */
+    int32_t     ss_x, ss_y;      /* 1 for the chroma planes of 4:2:0 */
+    int32_t     unit_size;       /* rst_info[plane].restoration_unit_size (power of two, >= 64 >> ss_x) */
+    int32_t     reserved;
+} SvtB200LrPlane;
+
+/* RestorationUnitInfo (restoration.h) flattened: restoration_type 0 = RESTORE_NONE, 1 = RESTORE_WIENER, 2 = RESTORE_SGRPROJ */
+typedef struct SvtB200LrUnitInfo {
+    int32_t restoration_type;
+    int32_t sgr_ep;       /* SgrprojInfo.ep */
+    int32_t sgr_xqd[2];   /* SgrprojInfo.xqd */
+    int16_t hfilter[8];   /* WienerInfo.hfilter (7 taps + 0) */
+    int16_t vfilter[8];
+} SvtB200LrUnitInfo;
+
+SVT_B200_API int svt_b200_lr_num_stripes(int plane_height, int ss_y);   /* rows of 2 lines in each boundary buffer */
+SVT_B200_API int svt_b200_lr_boundary_stride(int plane_width);
+SVT_B200_API int svt_b200_lr_units_per_dim(int size, int unit_size);    /* svt_av1_lr_count_units_in_tile */
+/* svt_av1_loop_restoration_save_boundary_lines (restoration.c:1682): after_cdef = 0 saves the deblocked lines of the
+ * interior stripe boundaries (read from `deblocked`), after_cdef = 1 the CDEF lines at the top / bottom of the picture
+ * (read from `cdef`); call once each, as the reference does around CDEF. */
+SVT_B200_API int svt_b200_lr_save_boundary_lines_dev(const SvtB200LrPlane* planes, int n_planes, int after_cdef, int bit_depth, void* stream);
+/* svt_av1_loop_restoration_filter_frame (restoration.c:1179): every unit of every plane, stripe by stripe with the saved
+ * boundary lines, into `dst`.  d_units[p]: DEVICE array of the plane's units in raster order
+ * (svt_b200_lr_units_per_dim(height) rows x svt_b200_lr_units_per_dim(width) columns).  The picture itself is not
+ * modified (the reference's in-place save / restore of the rows around a stripe is not needed) and needs no border. */
+SVT_B200_API int svt_b200_lr_filter_frame_dev(const SvtB200LrPlane* planes, int n_planes, const SvtB200LrUnitInfo* const d_units[3],
+                                              int optimized_lr, int bit_depth, void* stream);
+/* sse_restoration_unit (restoration_pick.c:103) for every unit: d_sse[p][unit] = sum (dst - src)^2 over the unit's limits */
+SVT_B200_API int svt_b200_lr_unit_sse_dev(const SvtB200LrPlane* planes, int n_planes, int64_t* const d_sse[3], int bit_depth, void* stream);
+
+/* ------------------------------------------------------------------------------------------ */
 /* K13 + T2 open-loop ME for a whole picture  (reference: pic_analysis_process.c:130-160,      */
 /*      2138-2190; motion_estimation.c:781-2390; me_process.c:97-291)                          */
 /* ------------------------------------------------------------------------------------------ */

@@ -894,3 +894,76 @@ static void lr_filter_unit_8bit(const RestorationUnitInfo* ruip, uint8_t* data, 
     free(tmp);
     free(rlbs);
 }
+
+/* ---- a13: whole-plane restoration through the reference's own functions ---------------------------------------------
+ * boundary lines: svt_aom_save_tile_row_boundary_lines (restoration.c:1606), which only reads frm_size and the
+ * subsampling flags of Av1Common; plane filter: the unit loop of foreach_rest_unit_in_tile (:1247-1294, static there,
+ * restated) around the reference's svt_av1_loop_restoration_filter_unit (:1067). */
+#include "pcs.h"
+typedef struct { int32_t restoration_type, sgr_ep, sgr_xqd[2]; int16_t hfilter[8], vfilter[8]; } RefLrUnitInfo;
+
+void ref_lr_save_boundaries(void* plane_px00, int stride, int w, int h, int bit_depth, int plane, int frame_w, int frame_h, int after_cdef,
+                            void* above, void* below, int bstride) {
+    Av1Common* cm = (Av1Common*)calloc(1, sizeof(Av1Common));
+    cm->frm_size.frame_width = (uint16_t)frame_w;
+    cm->frm_size.frame_height = (uint16_t)frame_h;
+    cm->frm_size.superres_upscaled_width = (uint16_t)frame_w;
+    cm->frm_size.superres_upscaled_height = (uint16_t)frame_h;
+    cm->frm_size.superres_denominator = 8;
+    cm->subsampling_x = cm->subsampling_y = 1;
+    RestorationStripeBoundaries rsb;
+    memset(&rsb, 0, sizeof(rsb));
+    rsb.stripe_boundary_above = (uint8_t*)above;
+    rsb.stripe_boundary_below = (uint8_t*)below;
+    rsb.stripe_boundary_stride = bstride;
+    svt_aom_save_tile_row_boundary_lines((uint8_t*)plane_px00, stride, w, h, bit_depth > 8, plane, cm, after_cdef, &rsb);
+    free(cm);
+}
+
+/* data: pixel (0,0) of a plane with >= 3 pixels of writable border (the reference extends it in place, :1223) */
+void ref_lr_filter_plane(void* data, int stride, void* dst, int dst_stride, int w, int h, int ss_x, int ss_y, int bit_depth, int unit_size,
+                         const RefLrUnitInfo* units, void* above, void* below, int bstride, int optimized_lr) {
+    const int highbd = bit_depth > 8;
+    uint8_t* data8 = highbd ? CONVERT_TO_BYTEPTR((uint16_t*)data) : (uint8_t*)data;
+    uint8_t* dst8 = highbd ? CONVERT_TO_BYTEPTR((uint16_t*)dst) : (uint8_t*)dst;
+    svt_extend_frame(data8, w, h, stride, RESTORATION_BORDER, RESTORATION_BORDER, highbd);
+    RestorationStripeBoundaries rsb;
+    memset(&rsb, 0, sizeof(rsb));
+    rsb.stripe_boundary_above = (uint8_t*)above;
+    rsb.stripe_boundary_below = (uint8_t*)below;
+    rsb.stripe_boundary_stride = bstride;
+    RestorationLineBuffers* rlbs = (RestorationLineBuffers*)malloc(sizeof(RestorationLineBuffers));
+    int32_t* tmp = (int32_t*)malloc(RESTORATION_TMPBUF_SIZE);
+    Av1PixelRect tile = {0, 0, w, h};
+    tile.left = 0; tile.top = 0; tile.right = w; tile.bottom = h;
+    const int hunits = (w + (unit_size >> 1)) / unit_size > 1 ? (w + (unit_size >> 1)) / unit_size : 1;
+    const int ext = unit_size * 3 / 2, voff = RESTORATION_UNIT_OFFSET >> ss_y;
+    int y0 = 0, i = 0;
+    while (y0 < h) {
+        const int rem_h = h - y0, uh = rem_h < ext ? rem_h : unit_size;
+        RestorationTileLimits lim;
+        lim.v_start = y0; lim.v_end = y0 + uh;
+        lim.v_start = lim.v_start - voff > 0 ? lim.v_start - voff : 0;
+        if (lim.v_end < h) lim.v_end -= voff;
+        int x0 = 0, j = 0;
+        while (x0 < w) {
+            const int rem_w = w - x0, uw = rem_w < ext ? rem_w : unit_size;
+            lim.h_start = x0; lim.h_end = x0 + uw;
+            const RefLrUnitInfo* u = &units[i * hunits + j];
+            RestorationUnitInfo  rui;
+            memset(&rui, 0, sizeof(rui));
+            rui.restoration_type = (RestorationType)u->restoration_type;
+            memcpy(rui.wiener_info.hfilter, u->hfilter, 16);
+            memcpy(rui.wiener_info.vfilter, u->vfilter, 16);
+            rui.sgrproj_info.ep = u->sgr_ep;
+            rui.sgrproj_info.xqd[0] = u->sgr_xqd[0];
+            rui.sgrproj_info.xqd[1] = u->sgr_xqd[1];
+            svt_av1_loop_restoration_filter_unit(1, &lim, &rui, &rsb, rlbs, &tile, 0, ss_x, ss_y, highbd, bit_depth, data8, stride, dst8, dst_stride,
+                                                 tmp, optimized_lr);
+            x0 += uw; j++;
+        }
+        y0 += uh; i++;
+    }
+    free(tmp);
+    free(rlbs);
+}

@@ -381,6 +381,29 @@ lib.svt_b200_sgr_units_dev.argtypes = [vp, vp, ct.c_int, vp, vp, ct.c_int, ct.c_
 lib.svt_b200_sgr_units_dev.restype = ct.c_int
 
 # ------------------------------------------------------------------------------------------------
+# a13 loop-restoration drivers
+# ------------------------------------------------------------------------------------------------
+class LrPlane(ct.Structure):  # SvtB200LrPlane
+    _fields_ = [("deblocked", vp), ("cdef", vp), ("dst", vp), ("src", vp), ("boundary_above", vp), ("boundary_below", vp),
+                ("stride_deblocked", ct.c_int32), ("stride_cdef", ct.c_int32), ("stride_dst", ct.c_int32), ("stride_src", ct.c_int32),
+                ("boundary_stride", ct.c_int32), ("width", ct.c_int32), ("height", ct.c_int32), ("ss_x", ct.c_int32), ("ss_y", ct.c_int32),
+                ("unit_size", ct.c_int32), ("reserved", ct.c_int32)]
+
+
+lib.svt_b200_lr_num_stripes.argtypes = [ct.c_int, ct.c_int]
+lib.svt_b200_lr_num_stripes.restype = ct.c_int
+lib.svt_b200_lr_boundary_stride.argtypes = [ct.c_int]
+lib.svt_b200_lr_boundary_stride.restype = ct.c_int
+lib.svt_b200_lr_units_per_dim.argtypes = [ct.c_int, ct.c_int]
+lib.svt_b200_lr_units_per_dim.restype = ct.c_int
+lib.svt_b200_lr_save_boundary_lines_dev.argtypes = [ct.POINTER(LrPlane), ct.c_int, ct.c_int, ct.c_int, vp]
+lib.svt_b200_lr_save_boundary_lines_dev.restype = ct.c_int
+lib.svt_b200_lr_filter_frame_dev.argtypes = [ct.POINTER(LrPlane), ct.c_int, ct.POINTER(vp), ct.c_int, ct.c_int, vp]
+lib.svt_b200_lr_filter_frame_dev.restype = ct.c_int
+lib.svt_b200_lr_unit_sse_dev.argtypes = [ct.POINTER(LrPlane), ct.c_int, ct.POINTER(vp), ct.c_int, vp]
+lib.svt_b200_lr_unit_sse_dev.restype = ct.c_int
+
+# ------------------------------------------------------------------------------------------------
 # K13 + T2 open-loop ME for a whole picture
 # ------------------------------------------------------------------------------------------------
 class MePicture(ct.Structure):

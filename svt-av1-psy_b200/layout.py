@@ -65,3 +65,6 @@ def me_plane_shapes(width, height):
     return out
 
 SAD_SIZES = [(128, 128), (128, 64), (64, 128), (64, 64), (64, 32), (64, 16), (32, 64), (32, 32), (32, 16), (32, 8), (16, 64), (16, 32), (16, 16), (16, 8), (16, 4), (8, 32), (8, 16), (8, 8), (8, 4), (4, 16), (4, 8), (4, 4)]  # (width, height) of the svt_aom_sadMxN family
+
+LR_UNIT_DTYPE = np.dtype([("restoration_type", "<i4"), ("sgr_ep", "<i4"), ("sgr_xqd", "<i4", 2), ("hfilter", "<i2", 8), ("vfilter", "<i2", 8)])  # SvtB200LrUnitInfo
+assert LR_UNIT_DTYPE.itemsize == 48
