@@ -37,7 +37,7 @@ sys.path.insert(0, ROOT)
 METRIC = "1080p preset-8 encoded frames/sec at 1/2/4/8 B200 vs reference AVX2 on host"
 METRIC_SCOPE = "hot path only (SURVEY 8: ME + transform/quant/inverse + CDEF + Wiener of one 1080p preset-8 frame per step), not a full encode"
 N_FRAME_SETS = 8  # rotated between steps: no step finds its inputs in L2, and (e2e) up to 8 frames are in flight
-N_CALLS = 9       # len(FramePipeline.CALLS): the T2 entry points one frame goes through
+N_CALLS = 10      # len(FramePipeline.CALLS): the T2 entry points one frame goes through
 EXCH_BATCH = 4    # pictures per reconstructed-reference exchange (one mini-GOP slice per NCCL group launch)
 # dram__bytes_read.sum + dram__bytes_write.sum of the call's dominant kernel, per launch, from the ncu --set full
 # capture of this same command (profiles/README.md says which file); None = not captured for that call

@@ -43,7 +43,9 @@ class RefFrameJob(ct.Structure):
                 ("n_str", ct.c_int32), ("damping", ct.c_int32), ("subsampling", ct.c_int32), ("reserved1", ct.c_int32),
                 ("mse", vp), ("dir", vp), ("var", vp),
                 ("fb_idx", vp), ("apply_y", vp), ("apply_uv", vp),
-                ("stats", vp), ("M", vp), ("H", vp), ("units", vp), ("n_stats", ct.c_int32), ("n_units", ct.c_int32)]
+                ("stats", vp), ("M", vp), ("H", vp), ("units", vp), ("n_stats", ct.c_int32), ("n_units", ct.c_int32),
+                ("lr_units", vp * 3), ("lr_above", vp * 3), ("lr_below", vp * 3), ("lr_unit_size", ct.c_int32 * 3), ("lr_bstride", ct.c_int32 * 3),
+                ("lr_stripes", ct.c_int32 * 3), ("reserved2", ct.c_int32)]
 
 
 def aligned_zeros(n, dtype, align=64):
@@ -102,7 +104,9 @@ class RefFrame:
         self.dirs = np.zeros((nb, 64), np.uint8)
         self.vars = np.zeros((nb, 64), np.int32)
         self.stats = np.ascontiguousarray(wl.stats_items)
-        self.units = np.ascontiguousarray(wl.wiener_units)
+        self.lr_units = [np.ascontiguousarray(u) for u in wl.lr_units]
+        self.lr_above = [np.zeros(2 * wl.lr_num_stripes(p) * wl.lr_boundary_stride(p), pix) for p in range(3)]
+        self.lr_below = [np.zeros(2 * wl.lr_num_stripes(p) * wl.lr_boundary_stride(p), pix) for p in range(3)]
         self.M = np.zeros((len(wl.stats_items), 49), np.int64)
         self.Hm = np.zeros((len(wl.stats_items), 2401), np.int64)
         self.job = self._make_job()
@@ -142,8 +146,11 @@ class RefFrame:
         j.n_str, j.damping, j.subsampling = len(wl.cdef_str_y), wl.cdef_damping, wl.cdef_subsampling
         j.mse, j.dir, j.var = P(self.mse), P(self.dirs), P(self.vars)
         j.fb_idx, j.apply_y, j.apply_uv = P(wl.cdef_fb_idx), P(wl.cdef_apply_y), P(wl.cdef_apply_uv)
-        j.stats, j.M, j.H, j.units = P(self.stats), P(self.M), P(self.Hm), P(self.units)
-        j.n_stats, j.n_units = len(self.stats), len(self.units)
+        j.stats, j.M, j.H, j.units = P(self.stats), P(self.M), P(self.Hm), None
+        j.n_stats, j.n_units = len(self.stats), 0
+        for p in range(3):
+            j.lr_units[p], j.lr_above[p], j.lr_below[p] = P(self.lr_units[p]), P(self.lr_above[p]), P(self.lr_below[p])
+            j.lr_unit_size[p], j.lr_bstride[p], j.lr_stripes[p] = wl.lr_unit_size[p], wl.lr_boundary_stride(p), wl.lr_num_stripes(p)
         return j
 
     def step(self):

@@ -701,6 +701,11 @@ void ref_wiener_units_8bit(const uint8_t* src, uint8_t* dst, const RefWienerUnit
  * from the main thread); ref_frames_run keeps WHOLE FRAMES IN FLIGHT instead, one frame per pool thread, each
  * worker running its frame's calls serially into its own private output buffers -- how the encoder uses the
  * host cores (picture-level parallelism, enc_handle.c:770-781). */
+typedef struct { int32_t restoration_type, sgr_ep, sgr_xqd[2]; int16_t hfilter[8], vfilter[8]; } RefLrUnitInfo;
+void ref_lr_save_boundaries(void* plane_px00, int stride, int w, int h, int bit_depth, int plane, int frame_w, int frame_h, int after_cdef,
+                            void* above, void* below, int bstride);
+void ref_lr_filter_plane(void* data, int stride, void* dst, int dst_stride, int w, int h, int ss_x, int ss_y, int bit_depth, int unit_size,
+                         const RefLrUnitInfo* units, void* above, void* below, int bstride, int optimized_lr);
 typedef struct RefFrameJob {
     int32_t width, height, bit_depth, n_refs;
     const RefMePicture* cur; const RefMePicture* refs; const RefMeParams* prm;
@@ -717,6 +722,7 @@ typedef struct RefFrameJob {
     uint64_t* mse; uint8_t* dir; int32_t* var;
     const int8_t* fb_idx; const int32_t *apply_y, *apply_uv;
     const RefStatsItem* stats; int64_t *M, *H; const RefWienerUnit* units; int32_t n_stats, n_units;
+    const RefLrUnitInfo* lr_units[3]; void* lr_above[3]; void* lr_below[3]; int32_t lr_unit_size[3], lr_bstride[3], lr_stripes[3], reserved2;
 } RefFrameJob;
 
 static void job_cdef_frame(const RefFrameJob* j, RefCdefFrame* f) {
@@ -755,6 +761,13 @@ static void job_extend(const RefFrameJob* j, void* buf) {
         }
     }
 }
+static void lr_plane_body(void* vjob, int p) {
+    const RefFrameJob* j = (const RefFrameJob*)vjob;
+    const int psz = j->bit_depth > 8 ? 2 : 1, ss = p ? 1 : 0;
+    const size_t o = (size_t)(j->plane_off[p] + (int64_t)j->pad * j->plane_stride[p] + j->pad) * psz;
+    ref_lr_filter_plane((uint8_t*)j->cdef_out + o, j->plane_stride[p], (uint8_t*)j->final + o, j->plane_stride[p], j->plane_w[p], j->plane_h[p], ss, ss,
+                        j->bit_depth, j->lr_unit_size[p], j->lr_units[p], j->lr_above[p], j->lr_below[p], j->lr_bstride[p], 0);
+}
 static void tx_chain_body(void* vctx, int i) { residual_body(vctx, i); fwd_body(vctx, i); quant_body(vctx, i); inv_body(vctx, i); }
 
 static int g_trace = -1;
@@ -769,6 +782,10 @@ void ref_frame_step(const RefFrameJob* j) {
                 j->src, j->residual, 1};
     par_for((int)j->n_tx, 64, tx_chain_body, &tx); /* per block: residual -> transform -> quantise -> inverse, as enc-dec does */
     TRACE("cdef search");
+    /* svt_av1_loop_restoration_save_boundary_lines(frame, cm, 0) on the deblocked picture, before CDEF (dlf_process.c / cdef_process.c) */
+    for (int p = 0; p < 3; p++)
+        ref_lr_save_boundaries((uint8_t*)j->recon + (size_t)(j->plane_off[p] + (int64_t)j->pad * j->plane_stride[p] + j->pad) * psz, j->plane_stride[p],
+                               j->plane_w[p], j->plane_h[p], j->bit_depth, p, j->width, j->height, 0, j->lr_above[p], j->lr_below[p], j->lr_bstride[p]);
     RefCdefFrame f;
     job_cdef_frame(j, &f);
     CdefSearchCtx cs = {&f, j->skip, j->str_y, j->str_uv, j->n_str, j->mse, j->dir, j->var};
@@ -784,13 +801,16 @@ void ref_frame_step(const RefFrameJob* j) {
     TRACE("stats");
     StatsCtx st = {j->cdef_out, j->src, j->stats, j->M, j->H, j->bit_depth};
     par_for(j->n_stats, 1, stats_body, &st);
-    TRACE("wiener");
-    WienerCtx wu = {j->cdef_out, j->final, j->units, j->bit_depth};
-    par_for(j->n_units, 16, wiener_body, &wu);
+    TRACE("restoration");
+    /* ... (cm, 1) after CDEF, then svt_av1_loop_restoration_filter_frame: every unit, stripe by stripe (rest_process.c:663-745) */
+    for (int p = 0; p < 3; p++)
+        ref_lr_save_boundaries(outp[p], j->plane_stride[p], j->plane_w[p], j->plane_h[p], j->bit_depth, p, j->width, j->height, 1, j->lr_above[p],
+                               j->lr_below[p], j->lr_bstride[p]);
+    par_for(3, 1, lr_plane_body, (void*)j);
 }
 
 /* private output buffers of one pool thread (allocated on first use, grown when a larger job arrives) */
-typedef struct { size_t cap[17]; void* buf[17]; } WorkerBufs;
+typedef struct { size_t cap[23]; void* buf[23]; } WorkerBufs;
 static __thread WorkerBufs t_bufs;
 static void* wb(int k, size_t bytes) {
     if (t_bufs.cap[k] < bytes) {
@@ -825,6 +845,11 @@ static void frame_body(void* vctx, int i) {
     int64_t res_elems = 0;
     for (int p = 0; p < 3; p++) res_elems = j.src_off[p] + (int64_t)j.src_stride[p] * j.plane_h[p];
     j.residual = wb(16, (size_t)res_elems * 2);
+    for (int p = 0; p < 3; p++) {
+        const size_t bb = (size_t)2 * j.lr_stripes[p] * j.lr_bstride[p] * psz;
+        j.lr_above[p] = wb(17 + 2 * p, bb);
+        j.lr_below[p] = wb(18 + 2 * p, bb);
+    }
     ref_frame_step(&j);
 }
 /* n_frames whole frames, frame i on job set i % n_sets, spread over `n_threads` pool threads (<= 0: all);
@@ -900,7 +925,6 @@ static void lr_filter_unit_8bit(const RestorationUnitInfo* ruip, uint8_t* data, 
  * subsampling flags of Av1Common; plane filter: the unit loop of foreach_rest_unit_in_tile (:1247-1294, static there,
  * restated) around the reference's svt_av1_loop_restoration_filter_unit (:1067). */
 #include "pcs.h"
-typedef struct { int32_t restoration_type, sgr_ep, sgr_xqd[2]; int16_t hfilter[8], vfilter[8]; } RefLrUnitInfo;
 
 void ref_lr_save_boundaries(void* plane_px00, int stride, int w, int h, int bit_depth, int plane, int frame_w, int frame_h, int after_cdef,
                             void* above, void* below, int bstride) {

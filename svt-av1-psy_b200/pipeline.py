@@ -78,7 +78,10 @@ class FramePipeline:
         self.app_y, self.app_uv = _t(T, wl.cdef_apply_y), _t(T, wl.cdef_apply_uv)
         # ---- REST -------------------------------------------------------------------------------------
         self.stats_items = _t(T, wl.stats_items.view(np.uint8))
-        self.wiener_units = _t(T, wl.wiener_units.view(np.uint8))
+        self.lr_units = [_t(T, u.view(np.uint8)) for u in wl.lr_units]
+        self.lr_above = [T.zeros(2 * wl.lr_num_stripes(p) * wl.lr_boundary_stride(p), dtype=pix, device=device) for p in range(3)]
+        self.lr_below = [T.zeros(2 * wl.lr_num_stripes(p) * wl.lr_boundary_stride(p), dtype=pix, device=device) for p in range(3)]
+        self._lr_planes = None
         self.M = T.zeros((len(wl.stats_items), 49), dtype=T.int64, device=device)
         self.Hm = T.zeros((len(wl.stats_items), 2401), dtype=T.int64, device=device)
         # ---- host staging for the end-to-end arm ------------------------------------------------------
@@ -263,10 +266,31 @@ class FramePipeline:
                                                   len(self.wl.stats_items), self.bd, self.M.data_ptr(), self.Hm.data_ptr(), s)
         assert rc == 0
 
+    def lr_planes(self):
+        """SvtB200LrPlane x 3: deblocked = the reconstruction before CDEF, cdef = the CDEF output, dst = the restored picture"""
+        if self._lr_planes is None:
+            wl = self.wl
+            self._lr_planes = (dsp.LrPlane * 3)()
+            rec, cdf, fin = self.plane_views(self.recon, True), self.plane_views(self.cdef_out, True), self.plane_views(self.final, True)
+            src = self.plane_views(self.cur_flat, False)
+            for p in range(3):
+                w, h = wl.plane_dims[p]
+                ss = 1 if p else 0
+                self._lr_planes[p] = dsp.LrPlane(rec[p][0], cdf[p][0], fin[p][0], src[p][0], self.lr_above[p].data_ptr(), self.lr_below[p].data_ptr(),
+                                                 rec[p][1], cdf[p][1], fin[p][1], src[p][1], wl.lr_boundary_stride(p), w, h, ss, ss, wl.lr_unit_size[p], 0)
+            self._lr_unit_ptrs = (ct.c_void_p * 3)(*[u.data_ptr() for u in self.lr_units])
+        return self._lr_planes
+
+    def call_lr_boundaries(self, s):
+        """svt_av1_loop_restoration_save_boundary_lines, both passes (deblocked lines from the reconstruction, CDEF lines from cdef_out)"""
+        pl = self.lr_planes()
+        assert lib.svt_b200_lr_save_boundary_lines_dev(pl, 3, 0, self.bd, s) == 0
+        assert lib.svt_b200_lr_save_boundary_lines_dev(pl, 3, 1, self.bd, s) == 0
+
     def call_wiener_filter(self, s):
-        rc = lib.svt_b200_wiener_units_dev(self.cdef_out.data_ptr(), self.final.data_ptr(), self.wiener_units.data_ptr(),
-                                           len(self.wl.wiener_units), self.bd, s)
-        assert rc == 0
+        """svt_av1_loop_restoration_filter_frame: every unit of the three planes, stripe by stripe with the saved boundary lines"""
+        pl = self.lr_planes()
+        assert lib.svt_b200_lr_filter_frame_dev(pl, 3, self._lr_unit_ptrs, 0, self.bd, s) == 0
 
     STAGES = ("me", "tx", "cdef", "rest")
     # (call, stage it belongs to, the kernels it launches)
@@ -276,9 +300,10 @@ class FramePipeline:
              ("pack_levels", "tx", "eob_scan_kernel+pack_levels_kernel"),
              ("cdef_search", "cdef", "cdef_dir_kernel+cdef_search_kernel"),
              ("cdef_apply", "cdef", "cdef_apply_kernel"),
+             ("lr_boundaries", "rest", "lr_save_boundary_kernel x2"),
              ("rest_extend", "rest", "pad_plane_kernel"),
              ("wiener_stats", "rest", "stats_sum_kernel+stats_mma_kernel+stats_finalize_kernel"),
-             ("wiener_filter", "rest", "wiener_convolve_kernel"))
+             ("wiener_filter", "rest", "lr_filter_kernel (striped restoration of the whole picture)"))
 
     def _stage(self, stage, s):
         for name, st, _ in self.CALLS:

@@ -10,7 +10,8 @@ kernels hand to the dispatched DSP functions for one 8-bit 4:2:0 picture at M8 /
          quantisation matrices (PSY default) -> inverse + reconstruction (skipped for all-zero blocks, as the
          encode pass does), every luma and chroma sample once, in a 64..4 transform-size mix
   CDEF   strength search over 6 (luma, chroma) candidates on the non-skip 8x8 blocks, then apply
-  REST   Wiener statistics (7x7 luma, 5x5 chroma) per restoration unit + separable Wiener filter
+  REST   Wiener statistics (7x7 luma, 5x5 chroma) per restoration unit + the striped loop-restoration filter of the
+         whole picture (64-row stripes offset by 8, saved deblocked / CDEF boundary lines, separable Wiener per unit)
 
 Content follows SURVEY.md 8(d): multi-octave block noise panorama + global pan + sensor noise, seeded.
 Everything here is plain numpy data preparation; it performs no DSP.
@@ -255,32 +256,55 @@ class FrameWorkload:
         self.cdef_apply_uv = np.array([4, 8, 0, 0], np.int32)
 
     # -- restoration ------------------------------------------------------------------------------------------
+    @staticmethod
+    def lr_unit_ranges(size, unit_size, off):
+        """[(start, end)] of the restoration units along one dimension: units of `unit_size`, the last one absorbs a
+        remainder below 1.5 units (foreach_rest_unit_in_tile, restoration.c:1247-1294); with off > 0 (rows) every unit is
+        shifted up by the 8-luma-row stripe offset"""
+        n = max((size + (unit_size >> 1)) // unit_size, 1)
+        out = []
+        for i in range(n):
+            s0 = max(0, i * unit_size - off)
+            e0 = size if i == n - 1 else (i + 1) * unit_size - off
+            out.append((s0, e0))
+        return out
+
     def _build_rest(self):
         r = np.random.default_rng(13)
         rec_off, _ = self.padded_offsets()
         src_off, _ = self.flat_offsets()
-        stats, units = [], []
+        stats, self.lr_units, self.lr_unit_size = [], [], []
         for p in range(3):
             pw, ph = self.plane_dims[p]
             th, st = self.padded_shape(p)
             ru = 256 if p == 0 else 128
             win = 7 if p == 0 else 5
-            for y0 in range(0, ph, ru):
-                for x0 in range(0, pw, ru):
-                    x1, y1 = min(x0 + ru, pw), min(y0 + ru, ph)
+            cols, rows = self.lr_unit_ranges(pw, ru, 0), self.lr_unit_ranges(ph, ru, 8 >> (1 if p else 0))
+            units = np.zeros(len(rows) * len(cols), dtype=dsp.LR_UNIT_DTYPE)
+            k = 0
+            for (y0, y1) in rows:
+                for (x0, x1) in cols:
+                    # search_wiener_seg: statistics over the unit's limits (restoration_pick.c:1281-1330)
                     stats.append((rec_off[p] + self.PAD * st + self.PAD, src_off[p], st, pw, x0, x1, y0, y1, win, 0))
                     t0, t1, t2 = int(r.integers(-5, 11)), int(r.integers(-23, 9)), int(r.integers(-17, 47))
                     taps = np.array([t0, t1, t2, -2 * (t0 + t1 + t2), t2, t1, t0, 0], np.int16)
                     if p:
                         taps[0] = taps[6] = 0  # chroma uses the 5-tap window
                         taps[3] = -2 * (taps[1] + taps[2])
-                    for uy in range(y0, y1, 64):
-                        for ux in range(x0, x1, 64):
-                            uw, uh = min(64, x1 - ux), min(64, y1 - uy)
-                            pos = rec_off[p] + (self.PAD + uy) * st + self.PAD + ux
-                            units.append((pos, pos, st, st, uw, uh, 0, taps, taps))
+                    units["restoration_type"][k] = 1  # RESTORE_WIENER (the self-guided filter is off at these presets, SURVEY F8)
+                    units["hfilter"][k] = taps
+                    units["vfilter"][k] = taps
+                    k += 1
+            self.lr_units.append(units)
+            self.lr_unit_size.append(ru)
         self.stats_items = np.array(stats, dtype=dsp.STATS_ITEM_DTYPE)
-        self.wiener_units = np.array(units, dtype=dsp.WIENER_UNIT_DTYPE)
+
+    def lr_num_stripes(self, p):
+        ss = 1 if p else 0
+        return (self.plane_dims[p][1] + (8 >> ss) + (64 >> ss) - 1) // (64 >> ss)
+
+    def lr_boundary_stride(self, p):
+        return (self.plane_dims[p][0] + 8 + 31) & ~31
 
     # -- algorithmic bytes per frame (SURVEY.md 8d) -----------------------------------------------------------
     def algorithmic_bytes(self):
@@ -300,10 +324,11 @@ class FrameWorkload:
             "cdef_apply": 2 * bpp * N,                                            # recon in, filtered out
             "rest_extend": 0,
             "wiener_stats": int(2 * bpp * N + len(self.stats_items) * (49 + 2401) * 8),
+            "lr_boundaries": 0,                                                   # 4 lines per 64-row stripe: ~6 % of a plane, not counted
             "wiener_filter": 2 * bpp * N,
         }
         stage_of = {"me_pyramid": "me", "me_search": "me", "txfm_trio": "tx", "pack_levels": "tx", "cdef_search": "cdef",
-                    "cdef_apply": "cdef", "rest_extend": "rest", "wiener_stats": "rest", "wiener_filter": "rest"}
+                    "cdef_apply": "cdef", "lr_boundaries": "rest", "rest_extend": "rest", "wiener_stats": "rest", "wiener_filter": "rest"}
         out = dict(calls)
         for st in ("me", "tx", "cdef", "rest"):
             out[st] = sum(v for k, v in calls.items() if stage_of.get(k) == st)
