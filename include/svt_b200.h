@@ -326,9 +326,9 @@ SVT_B200_API int svt_b200_residual_planes_dev(const void* d_source, const void* 
  * levels that did not fit level_bytes) locates block i's first level in d_levels; block i contributes d_eobs[i] levels,
  * qcoeff[scan[0..eob)] of its coefficient block.  level_bytes = 2 (int16: the levels of 8-bit pictures fit, as the
  * reference's 16-bit-lane low-bit-depth quantizers rely on) or 4 (int32, high bit depth).  Levels beyond `capacity` are
- * dropped (the caller sees total > capacity and re-issues with a larger buffer).  d_scan is the scan table addressed by
- * quant.scan_off. */
-SVT_B200_API int svt_b200_pack_levels_dev(const int32_t* d_qcoeff, const int16_t* d_scan, const SvtB200TrioItem* d_items,
+ * dropped (the caller sees total > capacity and re-issues with a larger buffer).  d_iscan is the INVERSE scan table
+ * (the `iscan` argument of the reference quantizers) addressed by quant.scan_off: blocks are read in raster order. */
+SVT_B200_API int svt_b200_pack_levels_dev(const int32_t* d_qcoeff, const int16_t* d_iscan, const SvtB200TrioItem* d_items,
                                           const uint16_t* d_eobs, int n_items, uint32_t* d_offsets, void* d_levels,
                                           int level_bytes, uint32_t capacity, void* stream);
 
@@ -575,7 +575,8 @@ typedef struct SvtB200LrPlane {
     int32_t     width, height;   /* crop size of this plane */
     int32_t     ss_x, ss_y;      /* 1 for the chroma planes of 4:2:0 */
     int32_t     unit_size;       /* rst_info[plane].restoration_unit_size (power of two, >= 64 >> ss_x) */
-    int32_t     reserved;
+    int32_t     frame_restoration_type; /* rst_info[plane].frame_restoration_type: 1 = RESTORE_WIENER promises that no unit of the
+                                           plane is RESTORE_SGRPROJ (smaller shared-memory footprint); anything else = any unit type */
 } SvtB200LrPlane;
 
 /* RestorationUnitInfo (restoration.h) flattened: restoration_type 0 = RESTORE_NONE, 1 = RESTORE_WIENER, 2 = RESTORE_SGRPROJ */

@@ -24,6 +24,8 @@
 #include "../../include/svt_b200.h"
 
 namespace b200 {
+bool launch_fullpel_tma(const SvtB200MePicture* cur, const SvtB200MePicture* refs, int n_refs, int n_b64, const SvtB200FullpelItem* d_items,
+                        int n_items, uint32_t* d_best_sad, uint32_t* d_best_mv, cudaStream_t st);  // me_pyramid.cu
 
 void launch_sad_search(const uint8_t* d_src, const uint8_t* d_ref, const SvtB200SadSearchItem* d_items, int n,
                        SvtB200SadSearchResult* d_results, size_t smem, int max_positions, cudaStream_t st);
@@ -457,6 +459,7 @@ extern "C" int svt_b200_me_picture_dev(const SvtB200MePicture* cur, const SvtB20
         memcpy(tab.prm, params, n_refs * sizeof(SvtB200MeParams));
         hme_fused_kernel<<<pairs, 128, 0, st>>>(*cur, tab, n_refs, n_b64, b64_w, d_hme_centre, d_hme_sad, w.fp_items);
         B200_LAUNCH_CHECK();
+        if (launch_fullpel_tma(cur, refs, n_refs, n_b64, w.fp_items, pairs, d_best_sad, d_best_mv, st)) return SVT_B200_OK;
         return svt_b200_fullpel_search_batch_dev(nullptr, nullptr, w.fp_items, pairs, d_best_sad, d_best_mv, stream);
     }
     B200_CUDA_CHECK(cudaMemcpyAsync(w.refs, refs, n_refs * sizeof(SvtB200MePicture), cudaMemcpyHostToDevice, st));
@@ -477,5 +480,6 @@ extern "C" int svt_b200_me_picture_dev(const SvtB200MePicture* cur, const SvtB20
     me_centre_kernel<<<grid_for((pairs * 32 + 255) / 256, 8), 256, 0, st>>>(*cur, w.refs, w.prm, n_refs, n_b64, b64_w, w.x[2], w.y[2], w.sad[2],
                                                                           d_hme_centre, d_hme_sad, w.fp_items);
     B200_LAUNCH_CHECK();
+    if (launch_fullpel_tma(cur, refs, n_refs, n_b64, w.fp_items, pairs, d_best_sad, d_best_mv, st)) return SVT_B200_OK;
     return svt_b200_fullpel_search_batch_dev(nullptr, nullptr, w.fp_items, pairs, d_best_sad, d_best_mv, stream);
 }

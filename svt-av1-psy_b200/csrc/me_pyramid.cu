@@ -11,6 +11,8 @@
 // order (y outer, x inner), i.e. "first minimum in raster order" per PU -- reproduced here as the
 // minimum of the 64-bit key (sad << 32 | raster index).  Result layout = me_context.h:54-75
 // (64x64 at 0, 32x32 at 1..4, 16x16 at 5..20, 8x8 at 21..84).
+#include <cuda.h>
+#include <mutex>
 #include "common.cuh"
 #include "../../include/svt_b200.h"
 
@@ -166,42 +168,120 @@ __device__ __forceinline__ void stage_rows(uint32_t* dst, int nwords, int rows, 
     }
 }
 
+// ---- TMA plumbing (sm_100a): one elected thread arms an mbarrier with the byte count and issues cp.async.bulk.tensor;
+// the box lands in shared memory with no per-thread address arithmetic, alignment fix-up or funnel shifts --------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
+}
+
+constexpr int kFpTmaRefs = 8;                     // reference pictures per launch that can be addressed through tensor maps
+constexpr int kFpBoxW = 80, kFpBoxH = kFpLines;   // bytes x rows of one window box (kFpTW + 63 = 79 bytes used)
+struct FpTma {
+    CUtensorMap cur, ref[kFpTmaRefs];             // 2-D byte tensors over the padded full-resolution luma planes
+    const uint8_t* cur_base;
+    const uint8_t* ref_base[kFpTmaRefs];
+    int32_t cur_pitch, ref_pitch[kFpTmaRefs];
+    int32_t n_b64;                                // items are ordered (reference, b64)
+};
+
+// TMA = true (open-loop ME of a picture, svt_b200_me_picture_dev): source block and search-window boxes arrive by TMA,
+// double-buffered -- the box of the next (item, chunk) is in flight while the current one is searched.
+// TMA = false (svt_b200_fullpel_search_batch_dev on caller planes of unknown extent): staged by the threads.
+template <bool TMA>
 __global__ void __launch_bounds__(kFpThreads)
 fullpel_search_kernel(const uint8_t* __restrict__ src_plane, const uint8_t* __restrict__ ref_plane,
                       const SvtB200FullpelItem* __restrict__ items, int n_items, uint32_t* __restrict__ best_sad,
-                      uint32_t* __restrict__ best_mv) {
-    __shared__ uint32_t S[64 * 16];
-    __shared__ uint32_t W[kFpLines * kFpLW];
+                      uint32_t* __restrict__ best_mv, const __grid_constant__ FpTma tm) {
+    constexpr int LW = TMA ? kFpBoxW / 4 : kFpLW;  // words per staged window line
+    __shared__ __align__(128) uint32_t Sbuf[TMA ? 2 : 1][64 * 16];
+    __shared__ __align__(128) uint32_t Wbuf[TMA ? 2 : 1][TMA ? (((kFpBoxW / 4) * kFpBoxH + 31) & ~31) : kFpLines * kFpLW];  // every TMA buffer starts 128-byte aligned
     __shared__ uint32_t sad8[kFpTW * kFpTH][65];
     __shared__ uint32_t sadpu[kFpTW * kFpTH][21];  // 64x64, 4 x 32x32, 16 x 16x16 of every position
     __shared__ unsigned long long best[85];
+    __shared__ uint64_t bars[2];
 
-    for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+    // issue the boxes of chunk (y0, x0) of item `it` into buffer `b` (one thread)
+    auto issue = [&](int it, int y0, int x0, int b, int sbuf, bool with_src) {
+        const SvtB200FullpelItem& item = items[it];
+        const int r = it / tm.n_b64;
+        const size_t roff = (size_t)(item.ref_off - (uint64_t)(uintptr_t)tm.ref_base[r]);
+        const int ry = (int)(roff / (size_t)tm.ref_pitch[r]), rx = (int)(roff - (size_t)ry * tm.ref_pitch[r]);
+        mbar_expect_tx(&bars[b], (uint32_t)(kFpBoxW * kFpBoxH + (with_src ? 64 * 64 : 0)));
+        tma_load_2d(Wbuf[b], &tm.ref[r], rx + x0, ry + y0, &bars[b]);
+        if (with_src) {
+            const size_t soff = (size_t)(item.src_off - (uint64_t)(uintptr_t)tm.cur_base);
+            const int sy = (int)(soff / (size_t)tm.cur_pitch), sx = (int)(soff - (size_t)sy * tm.cur_pitch);
+            tma_load_2d(Sbuf[sbuf], &tm.cur, sx, sy, &bars[b]);
+        }
+    };
+    if (TMA) {
+        if (threadIdx.x == 0) {
+            mbar_init(&bars[0], 1);
+            mbar_init(&bars[1], 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        if (threadIdx.x == 0 && (int)blockIdx.x < n_items) issue(blockIdx.x, 0, 0, 0, 0, true);
+    }
+    int n = 0, k = 0;  // n: boxes consumed so far (buffer n & 1, phase (n >> 1) & 1); k: items processed by this CTA
+
+    for (int it = blockIdx.x; it < n_items; it += gridDim.x, k++) {
         const SvtB200FullpelItem item = items[it];
         const int sa_w = item.sa_w, sa_h = item.sa_h, sub = item.sub_sad;
         if (threadIdx.x < 85) best[threadIdx.x] = ((unsigned long long)(128u * 128u * 255u) << 32) | 0xffffffffull;
+        const uint32_t* S = Sbuf[TMA ? (k & 1) : 0];
         // flat staging: every thread's words are independent loads, so one global round trip covers the block
-        stage_rows(S, 16, 64, src_plane + item.src_off, item.src_stride, 64);
+        if (!TMA) stage_rows(Sbuf[0], 16, 64, src_plane + item.src_off, item.src_stride, 64);
         for (int y0 = 0; y0 < sa_h; y0 += kFpTH) {
             const int th = min(kFpTH, sa_h - y0);
             for (int x0 = 0; x0 < sa_w; x0 += kFpTW) {
                 const int tw = min(kFpTW, sa_w - x0);
                 __syncthreads();
-                stage_rows(W, kFpLW, th + 63, ref_plane + item.ref_off + (size_t)y0 * item.ref_stride + x0, item.ref_stride, tw + 63);
-                __syncthreads();
-                // 8x8 SADs: unit = (position, 8x8 block), stored in z-order so that the four 8x8 of a 16x16
-                // (and the four 16x16 of a 32x32) are neighbours
-                const int npos = tw * th;
-                for (int u = threadIdx.x; u < npos * 64; u += kFpThreads) {
-                    const int pos = u >> 6, blk = u & 63;
-                    const int by = blk >> 3, bx = blk & 7;
+                const uint32_t* W = Wbuf[TMA ? (n & 1) : 0];
+                if (TMA) {
+                    if (threadIdx.x == 0) {  // prefetch the next box: next chunk of this item, else the first chunk of the CTA's next item
+                        int nx = x0 + kFpTW, ny = y0, nit = it;
+                        bool src = false;
+                        if (nx >= sa_w) { nx = 0; ny = y0 + kFpTH; }
+                        if (ny >= sa_h) { ny = 0; nit = it + gridDim.x; src = true; }
+                        if (nit < n_items) issue(nit, ny, nx, (n + 1) & 1, (k + 1) & 1, src);
+                    }
+                    while (!mbar_try_wait(&bars[n & 1], (uint32_t)((n >> 1) & 1))) {}
+                    n++;
+                } else {
+                    stage_rows(Wbuf[0], kFpLW, th + 63, ref_plane + item.ref_off + (size_t)y0 * item.ref_stride + x0, item.ref_stride, tw + 63);
+                    __syncthreads();
+                }
+                // 8x8 SADs: unit = (position, 8x8 block).  A warp takes one block row `by`, the 8 block columns and 4 consecutive
+                // positions: lanes that differ in position read the same window words (broadcast), lanes that differ in column read
+                // words 2 apart -- conflict free at any line pitch.  Results are stored in z-order so that the four 8x8 of a 16x16
+                // (and the four 16x16 of a 32x32) are neighbours.
+                const int npos = tw * th, ngrp = (npos + 3) >> 2;
+                for (int u = threadIdx.x; u < ngrp * 256; u += kFpThreads) {
+                    const int lane = u & 31, wi = u >> 5;
+                    const int bx = lane & 7, by = wi & 7, pos = (wi >> 3) * 4 + (lane >> 3);
+                    if (pos >= npos) continue;
                     const int py = pos / tw, px = pos - py * tw;
                     const int a8 = (px & 3) * 8, wb = (px >> 2) + 2 * bx;
                     uint32_t  acc = 0;
 #pragma unroll
                     for (int r = 0; r < 8; r++) {
                         if (sub && (r & 1)) continue;
-                        const uint32_t* L = W + (py + 8 * by + r) * kFpLW + wb;
+                        const uint32_t* L = W + (py + 8 * by + r) * LW + wb;
                         const uint32_t* Sr = S + (8 * by + r) * 16 + 2 * bx;
                         const uint32_t w0 = L[0], w1 = L[1], w2 = L[2];
                         acc = __vsadu4(Sr[0], __funnelshift_r(w0, w1, a8)) + acc;
@@ -259,6 +339,59 @@ fullpel_search_kernel(const uint8_t* __restrict__ src_plane, const uint8_t* __re
         }
         __syncthreads();
     }
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        B200_CUDA_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+        if (q != cudaDriverEntryPointSuccess || !p) {
+            fprintf(stderr, "[svt_b200] FATAL: cuTensorMapEncodeTiled is not available from this driver\n");
+            abort();
+        }
+        fn = (EncodeTiledFn)p;
+    });
+    return fn;
+}
+// 2-D byte tensor over a padded 8-bit plane (base 16-byte aligned, pitch a multiple of 16: the layout rule of every plane of
+// this library), box = box_w x box_h bytes, no swizzle; elements outside the plane read as zero
+static bool make_plane_map(CUtensorMap* m, const uint8_t* base, int pitch, int rows, int box_w, int box_h) {
+    if ((reinterpret_cast<uintptr_t>(base) & 15) || (pitch & 15) || pitch <= 0 || rows <= 0) return false;
+    const cuuint64_t dims[2] = {(cuuint64_t)pitch, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)pitch};
+    const cuuint32_t box[2] = {(cuuint32_t)box_w, (cuuint32_t)box_h};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = encode_tiled_fn()(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<uint8_t*>(base), dims, strides, box, estr,
+                                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+// full-pel search of a picture's (reference, b64) items through TMA; false = geometry not expressible (caller falls back)
+bool launch_fullpel_tma(const SvtB200MePicture* cur, const SvtB200MePicture* refs, int n_refs, int n_b64, const SvtB200FullpelItem* d_items,
+                        int n_items, uint32_t* d_best_sad, uint32_t* d_best_mv, cudaStream_t st) {
+    if (n_refs > kFpTmaRefs) return false;
+    FpTma tm;
+    memset(&tm, 0, sizeof(tm));
+    auto rows_of = [](const SvtB200MePicture& p) { return p.height[2] + 2 * p.org_y[2]; };
+    if (!make_plane_map(&tm.cur, cur->plane[2], cur->stride[2], rows_of(*cur), 64, 64)) return false;
+    tm.cur_base = cur->plane[2];
+    tm.cur_pitch = cur->stride[2];
+    for (int r = 0; r < n_refs; r++) {
+        if (!make_plane_map(&tm.ref[r], refs[r].plane[2], refs[r].stride[2], rows_of(refs[r]), kFpBoxW, kFpBoxH)) return false;
+        tm.ref_base[r] = refs[r].plane[2];
+        tm.ref_pitch[r] = refs[r].stride[2];
+    }
+    tm.n_b64 = n_b64;
+    fullpel_search_kernel<true><<<grid_for(n_items, 4), kFpThreads, 0, st>>>(nullptr, nullptr, d_items, n_items, d_best_sad, d_best_mv, tm);
+    B200_LAUNCH_CHECK();
+    return true;
 }
 
 }  // namespace b200
@@ -381,8 +514,11 @@ extern "C" int svt_b200_fullpel_search_batch_dev(const uint8_t* d_src_plane, con
                                                  uint32_t* d_best_mv, void* stream) {
     require_ready();
     if (n_items <= 0) return n_items == 0 ? SVT_B200_OK : SVT_B200_ERR_BAD_ARG;
-    fullpel_search_kernel<<<grid_for(n_items, 4), kFpThreads, 0, (cudaStream_t)stream>>>(d_src_plane, d_ref_plane, d_items, n_items,
-                                                                                       d_best_sad, d_best_mv);
+    FpTma none;
+    memset(&none, 0, sizeof(none));
+    none.n_b64 = 1;
+    fullpel_search_kernel<false><<<grid_for(n_items, 4), kFpThreads, 0, (cudaStream_t)stream>>>(d_src_plane, d_ref_plane, d_items, n_items,
+                                                                                              d_best_sad, d_best_mv, none);
     B200_LAUNCH_CHECK();
     return SVT_B200_OK;
 }

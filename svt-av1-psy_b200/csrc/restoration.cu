@@ -84,6 +84,7 @@ constexpr int kLrTilePitch = 72;
 constexpr size_t kLrSmem = (size_t)kLrTilePitch * (64 + 8) * 2                 // staged tile
                            + (size_t)2 * 66 * 66 * 4                            // A / B planes (also the Wiener intermediate)
                            + (size_t)2 * 64 * 64 * 4;                           // flt0 / flt1
+constexpr size_t kLrSmemWiener = (size_t)kLrTilePitch * (64 + 8) * 2 + (size_t)(64 + 8) * 64 * 2;  // tile + horizontal-pass intermediate
 
 template <typename PIX>
 __global__ void __launch_bounds__(256) lr_filter_kernel(const __grid_constant__ LrPlanes pl, const SvtB200LrUnitInfo* __restrict__ units0,
@@ -117,31 +118,35 @@ __global__ void __launch_bounds__(256) lr_filter_kernel(const __grid_constant__ 
     const PIX* above = reinterpret_cast<const PIX*>(p.boundary_above);
     const PIX* below = reinterpret_cast<const PIX*>(p.boundary_below);
     const int sw = w + 8, sh = h + 7;  // rows -3 .. h+3, columns -3 .. w+4
-    for (int i = threadIdx.x; i < sw * sh; i += blockDim.x) {
-        const int tr = i / sw, tc = i - tr * sw;
-        const int r = tr - 3, xx = x0 + tc - 3;
-        // the picture is extended by RESTORATION_BORDER pixels of edge replication before filtering (svt_extend_frame, :1223)
-        const int xc = xx < 0 ? 0 : (xx >= g.W ? g.W - 1 : xx);
-        int yy = y0 + r;
-        uint16_t v;
+    // one warp per tile row: where the row comes from (picture, saved above / below line, neighbouring row) is decided once
+    // per row, the copy itself is a coalesced run
+    for (int tr = threadIdx.x >> 5; tr < sh; tr += blockDim.x >> 5) {
+        const int r = tr - 3;
+        const PIX* rowp;
+        bool from_lines = false;
         if (r < 0 && copy_above && !optimized_lr) {
-            const int br = 2 * s + (r + 2 > 0 ? r + 2 : 0);                      // rows -3,-2,-1 <- saved lines 0,0,1
-            const int bx = xx < -4 ? -4 : (xx > g.W + 3 ? g.W + 3 : xx);
-            v = (uint16_t)above[(size_t)br * p.boundary_stride + bx + 4];
+            rowp = above + (size_t)(2 * s + (r + 2 > 0 ? r + 2 : 0)) * p.boundary_stride + 4;   // rows -3,-2,-1 <- saved lines 0,0,1
+            from_lines = true;
         } else if (r >= h && copy_below && !optimized_lr) {
             const int k = r - h;
-            const int br = 2 * s + (k < 1 ? k : 1);                              // rows h,h+1,h+2 <- saved lines 0,1,1
-            const int bx = xx < -4 ? -4 : (xx > g.W + 3 ? g.W + 3 : xx);
-            v = (uint16_t)below[(size_t)br * p.boundary_stride + bx + 4];
+            rowp = below + (size_t)(2 * s + (k < 1 ? k : 1)) * p.boundary_stride + 4;           // rows h,h+1,h+2 <- saved lines 0,1,1
+            from_lines = true;
         } else {
+            int yy = y0 + r;
             if (optimized_lr) {  // only the outermost context row is replaced, by its inner neighbour (:339-359)
                 if (r == -3 && copy_above) yy = y0 - 2;
                 if (r == h + 2 && copy_below) yy = y1 + 1;
             }
+            // the picture is extended by RESTORATION_BORDER pixels of edge replication before filtering (svt_extend_frame, :1223)
             yy = yy < 0 ? 0 : (yy >= g.H ? g.H - 1 : yy);
-            v = (uint16_t)data[(size_t)yy * p.stride_cdef + xc];
+            rowp = data + (size_t)yy * p.stride_cdef;
         }
-        tile[tr * kLrTilePitch + tc] = v;
+        const int lo = from_lines ? -4 : 0, hi = from_lines ? g.W + 3 : g.W - 1;  // the saved lines carry 4 extended columns each side
+        for (int tc = threadIdx.x & 31; tc < sw; tc += 32) {
+            int xx = x0 + tc - 3;
+            xx = xx < lo ? lo : (xx > hi ? hi : xx);
+            tile[tr * kLrTilePitch + tc] = (uint16_t)rowp[xx];
+        }
     }
     __syncthreads();
     int32_t* AB = reinterpret_cast<int32_t*>(lsm + (size_t)kLrTilePitch * (64 + 8) * 2);
@@ -153,6 +158,7 @@ __global__ void __launch_bounds__(256) lr_filter_kernel(const __grid_constant__ 
         return;
     }
     // RESTORE_SGRPROJ: svt_aom_sgrproj_filter_stripe -> svt_apply_selfguided_restoration (:957-992)
+    if (p.frame_restoration_type == 1) __trap();  // the caller declared a Wiener-only plane: the launch has no room for this filter
     int32_t* A = AB;
     int32_t* B = A + 66 * 66;
     int32_t* f0 = B + 66 * 66;
@@ -275,10 +281,14 @@ extern "C" int svt_b200_lr_filter_frame_dev(const SvtB200LrPlane* planes, int n_
             a = true;
         }
     }
+    // planes whose frame_restoration_type rules the self-guided filter out need only the Wiener footprint (more CTAs per SM)
+    bool sgr_possible = false;
+    for (int i = 0; i < n_planes; i++) sgr_possible |= planes[i].frame_restoration_type != 1;
+    const size_t smem = sgr_possible ? kLrSmem : kLrSmemWiener;
     const dim3 grid(max_chunks, max_stripes, n_planes);
     const SvtB200LrUnitInfo *u0 = d_units[0], *u1 = n_planes > 1 ? d_units[1] : nullptr, *u2 = n_planes > 2 ? d_units[2] : nullptr;
-    if (bit_depth == 8) lr_filter_kernel<uint8_t><<<grid, 256, kLrSmem, (cudaStream_t)stream>>>(pl, u0, u1, u2, optimized_lr ? 1 : 0, 8);
-    else lr_filter_kernel<uint16_t><<<grid, 256, kLrSmem, (cudaStream_t)stream>>>(pl, u0, u1, u2, optimized_lr ? 1 : 0, bit_depth);
+    if (bit_depth == 8) lr_filter_kernel<uint8_t><<<grid, 256, smem, (cudaStream_t)stream>>>(pl, u0, u1, u2, optimized_lr ? 1 : 0, 8);
+    else lr_filter_kernel<uint16_t><<<grid, 256, smem, (cudaStream_t)stream>>>(pl, u0, u1, u2, optimized_lr ? 1 : 0, bit_depth);
     B200_LAUNCH_CHECK();
     return SVT_B200_OK;
 }

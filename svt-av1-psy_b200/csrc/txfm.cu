@@ -10,6 +10,8 @@
 // running the generated straight-line network on its vector in registers (txfm_tables.cuh).  The
 // block sits in shared memory in element-major order with an odd pitch, so the passes and the
 // transposing hand-over are bank-conflict free; residual loads / coefficient stores are coalesced rows.
+#include <map>
+#include <mutex>
 #include "txfm_tables.cuh"
 #include "quant_one.cuh"
 #include "../../include/svt_b200.h"
@@ -530,78 +532,108 @@ extern "C" int svt_b200_residual_planes_dev(const void* d_source, const void* d_
 // ---- eob-bounded scan-order packing of the quantised levels (what the entropy coder consumes: the first eob levels of
 // each block in scan order, coding_loop.c / entropy_coding.c) -- the device->host transfer of a picture's coefficients then
 // carries sum(eob) levels instead of every coefficient position --------------------------------------------------------------
-// pass 1: exclusive prefix sum of the eobs (one CTA; a picture has a few tens of thousands of blocks)
-__global__ void __launch_bounds__(1024) eob_scan_kernel(const uint16_t* __restrict__ eobs, int n, uint32_t* __restrict__ offs /*[n+1]*/) {
-    __shared__ uint32_t s_warp[32];
-    __shared__ uint32_t s_carry;
-    if (threadIdx.x == 0) s_carry = 0;
+// pass 1: per-chunk sums of the eobs (1024 blocks per CTA); pass 2 scans its own chunk, adds the sums of the chunks before
+// it (a picture has a few tens of chunks) and scatters the levels
+constexpr int kPackChunk = 1024;
+__global__ void __launch_bounds__(256) eob_chunk_sum_kernel(const uint16_t* __restrict__ eobs, int n, uint32_t* __restrict__ sums) {
+    __shared__ uint32_t s_tot;
+    if (threadIdx.x == 0) s_tot = 0;
     __syncthreads();
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int base = 0; base < n; base += 1024) {
-        const int i = base + threadIdx.x;
-        const uint32_t v = i < n ? eobs[i] : 0;
-        uint32_t x = v;
+    const int base = blockIdx.x * kPackChunk;
+    uint32_t acc = 0;
+    for (int i = threadIdx.x; i < kPackChunk; i += blockDim.x) acc += base + i < n ? eobs[base + i] : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(&s_tot, acc);
+    __syncthreads();
+    if (threadIdx.x == 0) sums[blockIdx.x] = s_tot;
+}
+// one CTA per chunk of 1024 blocks: offsets of the chunk (shared-memory scan), then one warp per block reads the block's
+// coefficients in RASTER order (coalesced) and writes each level with scan position < eob to its place -- the scatter stays
+// inside the block's eob-long output run
+template <typename LVL>
+__global__ void __launch_bounds__(1024) pack_levels_kernel(const int32_t* __restrict__ q_base, const int16_t* __restrict__ iscan_base,
+                                                            const SvtB200TrioItem* __restrict__ items, const uint16_t* __restrict__ eobs,
+                                                            const uint32_t* __restrict__ sums, uint32_t* __restrict__ offs, int n, LVL* __restrict__ out,
+                                                            uint32_t cap) {
+    __shared__ uint32_t s_off[kPackChunk];
+    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_base;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, base = blockIdx.x * kPackChunk, i = base + threadIdx.x;
+    if (threadIdx.x == 0) {
+        uint32_t b = 0;
+        for (int c = 0; c < (int)blockIdx.x; c++) b += sums[c];
+        s_base = b;
+        if (blockIdx.x == gridDim.x - 1) { offs[n] = b + sums[blockIdx.x]; offs[n + 1] = 0; }
+    }
+    const uint32_t v = i < n ? eobs[i] : 0;
+    uint32_t x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+    }
+    if (lane == 31) s_warp[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = s_warp[lane];
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
-            if (lane >= o) x += y;
+            const uint32_t y = __shfl_up_sync(0xffffffffu, w, o);
+            if (lane >= o) w += y;
         }
-        if (lane == 31) s_warp[warp] = x;
-        __syncthreads();
-        if (warp == 0) {
-            uint32_t w = s_warp[lane];
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t y = __shfl_up_sync(0xffffffffu, w, o);
-                if (lane >= o) w += y;
-            }
-            s_warp[lane] = w;
-        }
-        __syncthreads();
-        const uint32_t incl = x + (warp ? s_warp[warp - 1] : 0) + s_carry;
-        if (i < n) offs[i] = incl - v;
-        __syncthreads();
-        if (threadIdx.x == 1023) s_carry = incl;
-        __syncthreads();
+        s_warp[lane] = w;
     }
-    if (threadIdx.x == 0) { offs[n] = s_carry; offs[n + 1] = 0; }
-}
-// pass 2: one warp per block copies its first eob levels, scan order
-template <typename LVL>
-__global__ void __launch_bounds__(256) pack_levels_kernel(const int32_t* __restrict__ q_base, const int16_t* __restrict__ scan_base,
-                                                           const SvtB200TrioItem* __restrict__ items, const uint16_t* __restrict__ eobs,
-                                                           uint32_t* __restrict__ offs, int n, LVL* __restrict__ out, uint32_t cap) {
-    const int lane = threadIdx.x & 31;
-    for (int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); b < n; b += gridDim.x * (blockDim.x >> 5)) {
-        const int eob = eobs[b];
+    __syncthreads();
+    const uint32_t excl = x - v + (warp ? s_warp[warp - 1] : 0) + s_base;
+    s_off[threadIdx.x] = excl;
+    if (i < n) offs[i] = excl;
+    __syncthreads();
+    const int nb = min(kPackChunk, n - base);
+    for (int b = warp; b < nb; b += 32) {
+        const int eob = eobs[base + b];
         if (!eob) continue;
-        const SvtB200QuantItem& qi = items[b].quant;
+        const SvtB200QuantItem& qi = items[base + b].quant;
         const int32_t* q = q_base + qi.q_off;
-        const int16_t* sc = scan_base + qi.scan_off;
-        const uint32_t o = offs[b];
-        for (int k = lane; k < eob; k += 32) {
-            if (o + k >= cap) continue;
-            const int32_t v = q[sc[k]];
-            if (sizeof(LVL) == 2 && (v < -32768 || v > 32767)) atomicAdd(&offs[n + 1], 1u);  // cannot happen for 8-bit pictures; counted, never silent
-            out[o + k] = (LVL)v;
+        const int16_t* isc = iscan_base + qi.scan_off;
+        const uint32_t o = s_off[b];
+        const int nc = qi.n_coeffs;
+        for (int rc = lane; rc < nc; rc += 32) {
+            const int k = isc[rc];
+            if (k >= eob || o + k >= cap) continue;
+            const int32_t lv = q[rc];
+            if (sizeof(LVL) == 2 && (lv < -32768 || lv > 32767)) atomicAdd(&offs[n + 1], 1u);  // cannot happen for 8-bit pictures; counted, never silent
+            out[o + k] = (LVL)lv;
         }
     }
 }
-extern "C" int svt_b200_pack_levels_dev(const int32_t* d_qcoeff, const int16_t* d_scan, const SvtB200TrioItem* d_items, const uint16_t* d_eobs,
+extern "C" int svt_b200_pack_levels_dev(const int32_t* d_qcoeff, const int16_t* d_iscan, const SvtB200TrioItem* d_items, const uint16_t* d_eobs,
                                         int n_items, uint32_t* d_offsets, void* d_levels, int level_bytes, uint32_t capacity, void* stream) {
     require_ready();
-    if (n_items < 0 || !d_offsets || !d_levels || (level_bytes != 2 && level_bytes != 4)) return SVT_B200_ERR_BAD_ARG;
-    eob_scan_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(d_eobs, n_items, d_offsets);
-    B200_LAUNCH_CHECK();
-    if (n_items) {
-        if (level_bytes == 2)
-            pack_levels_kernel<int16_t><<<grid_for((n_items + 7) / 8, 8), 256, 0, (cudaStream_t)stream>>>(d_qcoeff, d_scan, d_items, d_eobs, d_offsets,
-                                                                                                        n_items, (int16_t*)d_levels, capacity);
-        else
-            pack_levels_kernel<int32_t><<<grid_for((n_items + 7) / 8, 8), 256, 0, (cudaStream_t)stream>>>(d_qcoeff, d_scan, d_items, d_eobs, d_offsets,
-                                                                                                        n_items, (int32_t*)d_levels, capacity);
-        B200_LAUNCH_CHECK();
+    if (n_items <= 0 || !d_offsets || !d_levels || !d_iscan || (level_bytes != 2 && level_bytes != 4)) return SVT_B200_ERR_BAD_ARG;
+    const int chunks = (n_items + kPackChunk - 1) / kPackChunk;
+    if (chunks > 4096) return SVT_B200_ERR_BAD_ARG;  // the chunk sums live in the tail of the offsets buffer's lane scratch
+    static std::mutex mu;
+    static std::map<cudaStream_t, uint32_t*> sums_of;  // per-stream scratch: concurrent frames on different streams do not share it
+    uint32_t* d_sums;
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        auto it = sums_of.find((cudaStream_t)stream);
+        if (it == sums_of.end()) {
+            B200_CUDA_CHECK(cudaMalloc(&d_sums, 4096 * sizeof(uint32_t)));
+            sums_of[(cudaStream_t)stream] = d_sums;
+        } else
+            d_sums = it->second;
     }
+    eob_chunk_sum_kernel<<<chunks, 256, 0, (cudaStream_t)stream>>>(d_eobs, n_items, d_sums);
+    B200_LAUNCH_CHECK();
+    if (level_bytes == 2)
+        pack_levels_kernel<int16_t><<<chunks, 1024, 0, (cudaStream_t)stream>>>(d_qcoeff, d_iscan, d_items, d_eobs, d_sums, d_offsets, n_items,
+                                                                              (int16_t*)d_levels, capacity);
+    else
+        pack_levels_kernel<int32_t><<<chunks, 1024, 0, (cudaStream_t)stream>>>(d_qcoeff, d_iscan, d_items, d_eobs, d_sums, d_offsets, n_items,
+                                                                              (int32_t*)d_levels, capacity);
+    B200_LAUNCH_CHECK();
     return SVT_B200_OK;
 }
 

@@ -387,7 +387,7 @@ class LrPlane(ct.Structure):  # SvtB200LrPlane
     _fields_ = [("deblocked", vp), ("cdef", vp), ("dst", vp), ("src", vp), ("boundary_above", vp), ("boundary_below", vp),
                 ("stride_deblocked", ct.c_int32), ("stride_cdef", ct.c_int32), ("stride_dst", ct.c_int32), ("stride_src", ct.c_int32),
                 ("boundary_stride", ct.c_int32), ("width", ct.c_int32), ("height", ct.c_int32), ("ss_x", ct.c_int32), ("ss_y", ct.c_int32),
-                ("unit_size", ct.c_int32), ("reserved", ct.c_int32)]
+                ("unit_size", ct.c_int32), ("frame_restoration_type", ct.c_int32)]
 
 
 lib.svt_b200_lr_num_stripes.argtypes = [ct.c_int, ct.c_int]

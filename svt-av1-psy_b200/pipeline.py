@@ -192,7 +192,7 @@ class FramePipeline:
         assert rc == 0
 
     def call_pack_levels(self, s):
-        rc = lib.svt_b200_pack_levels_dev(self.qcoeff.data_ptr(), self.scan.data_ptr(), self.trio_items.data_ptr(), self.eobs.data_ptr(), self.n_tx,
+        rc = lib.svt_b200_pack_levels_dev(self.qcoeff.data_ptr(), self.iscan.data_ptr(), self.trio_items.data_ptr(), self.eobs.data_ptr(), self.n_tx,
                                           self.level_offsets.data_ptr(), self.levels.data_ptr(), self.level_bytes, self.levels.numel(), s)
         assert rc == 0
 
@@ -277,7 +277,8 @@ class FramePipeline:
                 w, h = wl.plane_dims[p]
                 ss = 1 if p else 0
                 self._lr_planes[p] = dsp.LrPlane(rec[p][0], cdf[p][0], fin[p][0], src[p][0], self.lr_above[p].data_ptr(), self.lr_below[p].data_ptr(),
-                                                 rec[p][1], cdf[p][1], fin[p][1], src[p][1], wl.lr_boundary_stride(p), w, h, ss, ss, wl.lr_unit_size[p], 0)
+                                                 rec[p][1], cdf[p][1], fin[p][1], src[p][1], wl.lr_boundary_stride(p), w, h, ss, ss, wl.lr_unit_size[p],
+                                                 1)  # frame_restoration_type = RESTORE_WIENER for every plane of this workload
             self._lr_unit_ptrs = (ct.c_void_p * 3)(*[u.data_ptr() for u in self.lr_units])
         return self._lr_planes
 
@@ -297,7 +298,7 @@ class FramePipeline:
     CALLS = (("me_pyramid", "me", "downsample_2d_kernel+pad_plane_kernel"),
              ("me_search", "me", "hme_fused_kernel + fullpel_search_kernel"),
              ("txfm_trio", "tx", "trio_txfm_kernel<4..64> (residual + forward transform + quantise + inverse transform fused)"),
-             ("pack_levels", "tx", "eob_scan_kernel+pack_levels_kernel"),
+             ("pack_levels", "tx", "eob_chunk_sum_kernel+pack_levels_kernel"),
              ("cdef_search", "cdef", "cdef_dir_kernel+cdef_search_kernel"),
              ("cdef_apply", "cdef", "cdef_apply_kernel"),
              ("lr_boundaries", "rest", "lr_save_boundary_kernel x2"),
