@@ -189,7 +189,11 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, i
 }
 
 constexpr int kFpTmaRefs = 8;                     // reference pictures per launch that can be addressed through tensor maps
-constexpr int kFpBoxW = 80, kFpBoxH = kFpLines;   // bytes x rows of one window box (kFpTW + 63 = 79 bytes used)
+// A box must START on a 16-byte boundary of global memory (measured on this GPU with tools/probe/tma_probe.cu: any other
+// innermost coordinate of a 1-byte tensor raises "illegal instruction"), a search window starts anywhere: the box is taken from
+// the aligned address below it, 16 bytes wider, and the positions are addressed with the residual byte offset.
+constexpr int kFpBoxW = 96, kFpBoxH = kFpLines;   // bytes x rows of one window box (15 + kFpTW + 63 = 94 bytes used)
+constexpr int kFpSrcBoxW = 80;                    // source block: 64 bytes + up to 12 of alignment slack (word-aligned origins only)
 struct FpTma {
     CUtensorMap cur, ref[kFpTmaRefs];             // 2-D byte tensors over the padded full-resolution luma planes
     const uint8_t* cur_base;
@@ -207,7 +211,8 @@ fullpel_search_kernel(const uint8_t* __restrict__ src_plane, const uint8_t* __re
                       const SvtB200FullpelItem* __restrict__ items, int n_items, uint32_t* __restrict__ best_sad,
                       uint32_t* __restrict__ best_mv, const __grid_constant__ FpTma tm) {
     constexpr int LW = TMA ? kFpBoxW / 4 : kFpLW;  // words per staged window line
-    __shared__ __align__(128) uint32_t Sbuf[TMA ? 2 : 1][64 * 16];
+    constexpr int SW = TMA ? kFpSrcBoxW / 4 : 16;  // words per staged source line
+    __shared__ __align__(128) uint32_t Sbuf[TMA ? 2 : 1][64 * (TMA ? kFpSrcBoxW / 4 : 16)];
     __shared__ __align__(128) uint32_t Wbuf[TMA ? 2 : 1][TMA ? (((kFpBoxW / 4) * kFpBoxH + 31) & ~31) : kFpLines * kFpLW];  // every TMA buffer starts 128-byte aligned
     __shared__ uint32_t sad8[kFpTW * kFpTH][65];
     __shared__ uint32_t sadpu[kFpTW * kFpTH][21];  // 64x64, 4 x 32x32, 16 x 16x16 of every position
@@ -220,12 +225,12 @@ fullpel_search_kernel(const uint8_t* __restrict__ src_plane, const uint8_t* __re
         const int r = it / tm.n_b64;
         const size_t roff = (size_t)(item.ref_off - (uint64_t)(uintptr_t)tm.ref_base[r]);
         const int ry = (int)(roff / (size_t)tm.ref_pitch[r]), rx = (int)(roff - (size_t)ry * tm.ref_pitch[r]);
-        mbar_expect_tx(&bars[b], (uint32_t)(kFpBoxW * kFpBoxH + (with_src ? 64 * 64 : 0)));
-        tma_load_2d(Wbuf[b], &tm.ref[r], rx + x0, ry + y0, &bars[b]);
+        mbar_expect_tx(&bars[b], (uint32_t)(kFpBoxW * kFpBoxH + (with_src ? kFpSrcBoxW * 64 : 0)));
+        tma_load_2d(Wbuf[b], &tm.ref[r], (rx + x0) & ~15, ry + y0, &bars[b]);
         if (with_src) {
             const size_t soff = (size_t)(item.src_off - (uint64_t)(uintptr_t)tm.cur_base);
             const int sy = (int)(soff / (size_t)tm.cur_pitch), sx = (int)(soff - (size_t)sy * tm.cur_pitch);
-            tma_load_2d(Sbuf[sbuf], &tm.cur, sx, sy, &bars[b]);
+            tma_load_2d(Sbuf[sbuf], &tm.cur, sx & ~15, sy, &bars[b]);
         }
     };
     if (TMA) {
@@ -243,7 +248,15 @@ fullpel_search_kernel(const uint8_t* __restrict__ src_plane, const uint8_t* __re
         const SvtB200FullpelItem item = items[it];
         const int sa_w = item.sa_w, sa_h = item.sa_h, sub = item.sub_sad;
         if (threadIdx.x < 85) best[threadIdx.x] = ((unsigned long long)(128u * 128u * 255u) << 32) | 0xffffffffull;
+        int rx0 = 0;  // column of the window origin / word offset of the source block inside their aligned boxes
         const uint32_t* S = Sbuf[TMA ? (k & 1) : 0];
+        if (TMA) {
+            const int r = it / tm.n_b64;
+            const size_t roff = (size_t)(item.ref_off - (uint64_t)(uintptr_t)tm.ref_base[r]);
+            rx0 = (int)(roff % (size_t)tm.ref_pitch[r]);
+            const size_t soff = (size_t)(item.src_off - (uint64_t)(uintptr_t)tm.cur_base);
+            S += ((int)(soff % (size_t)tm.cur_pitch) & 15) >> 2;
+        }
         // flat staging: every thread's words are independent loads, so one global round trip covers the block
         if (!TMA) stage_rows(Sbuf[0], 16, 64, src_plane + item.src_off, item.src_stride, 64);
         for (int y0 = 0; y0 < sa_h; y0 += kFpTH) {
@@ -271,18 +284,19 @@ fullpel_search_kernel(const uint8_t* __restrict__ src_plane, const uint8_t* __re
                 // words 2 apart -- conflict free at any line pitch.  Results are stored in z-order so that the four 8x8 of a 16x16
                 // (and the four 16x16 of a 32x32) are neighbours.
                 const int npos = tw * th, ngrp = (npos + 3) >> 2;
+                const int dx = TMA ? ((rx0 + x0) & 15) : 0;
                 for (int u = threadIdx.x; u < ngrp * 256; u += kFpThreads) {
                     const int lane = u & 31, wi = u >> 5;
                     const int bx = lane & 7, by = wi & 7, pos = (wi >> 3) * 4 + (lane >> 3);
                     if (pos >= npos) continue;
                     const int py = pos / tw, px = pos - py * tw;
-                    const int a8 = (px & 3) * 8, wb = (px >> 2) + 2 * bx;
+                    const int a8 = ((px + dx) & 3) * 8, wb = ((px + dx) >> 2) + 2 * bx;
                     uint32_t  acc = 0;
 #pragma unroll
                     for (int r = 0; r < 8; r++) {
                         if (sub && (r & 1)) continue;
                         const uint32_t* L = W + (py + 8 * by + r) * LW + wb;
-                        const uint32_t* Sr = S + (8 * by + r) * 16 + 2 * bx;
+                        const uint32_t* Sr = S + (8 * by + r) * SW + 2 * bx;
                         const uint32_t w0 = L[0], w1 = L[1], w2 = L[2];
                         acc = __vsadu4(Sr[0], __funnelshift_r(w0, w1, a8)) + acc;
                         acc = __vsadu4(Sr[1], __funnelshift_r(w1, w2, a8)) + acc;
@@ -380,7 +394,8 @@ bool launch_fullpel_tma(const SvtB200MePicture* cur, const SvtB200MePicture* ref
     FpTma tm;
     memset(&tm, 0, sizeof(tm));
     auto rows_of = [](const SvtB200MePicture& p) { return p.height[2] + 2 * p.org_y[2]; };
-    if (!make_plane_map(&tm.cur, cur->plane[2], cur->stride[2], rows_of(*cur), 64, 64)) return false;
+    if (cur->org_x[2] & 3) return false;  // the source block must start on a word of its aligned box
+    if (!make_plane_map(&tm.cur, cur->plane[2], cur->stride[2], rows_of(*cur), kFpSrcBoxW, 64)) return false;
     tm.cur_base = cur->plane[2];
     tm.cur_pitch = cur->stride[2];
     for (int r = 0; r < n_refs; r++) {
