@@ -741,6 +741,7 @@ static uint8_t*   g_cdef_dir = nullptr;  // direction/variance scratch for apply
 static int32_t*   g_cdef_var = nullptr;
 static size_t     g_cdef_cap = 0;
 static std::mutex g_cdef_mu;
+static ResetHook  g_cdef_reset([] { std::lock_guard<std::mutex> lk(g_cdef_mu); g_cdef_dir = nullptr; g_cdef_var = nullptr; g_cdef_cap = 0; });
 
 extern "C" int svt_b200_cdef_apply_frame_dev(const SvtB200CdefFrame* frame, const uint8_t* d_skip8x8, const int8_t* d_fb_strength_idx,
                                              const int* d_y_strength, const int* d_uv_strength, const uint8_t* d_dir,
@@ -755,10 +756,9 @@ extern "C" int svt_b200_cdef_apply_frame_dev(const SvtB200CdefFrame* frame, cons
     if (!d_dir) {  // calls that share the scratch are serialised on the host (the stream orders the device side)
         lk.lock();
         if ((size_t)nfb > g_cdef_cap) {
-            if (g_cdef_dir) { cudaFree(g_cdef_dir); cudaFree(g_cdef_var); }
             g_cdef_cap = (size_t)nfb * 2;
-            B200_CUDA_CHECK(cudaMalloc(&g_cdef_dir, g_cdef_cap * 64));
-            B200_CUDA_CHECK(cudaMalloc(&g_cdef_var, g_cdef_cap * 64 * 4));
+            g_cdef_dir = (uint8_t*)scratch_alloc(g_cdef_cap * 64);
+            g_cdef_var = (int32_t*)scratch_alloc(g_cdef_cap * 64 * 4);
         }
         if (frame->bit_depth > 8) cdef_dir_kernel<uint16_t><<<(nblk + 127) / 128, 128, 0, st>>>(*frame, d_skip8x8, g_cdef_dir, g_cdef_var);
         else cdef_dir_kernel<uint8_t><<<(nblk + 127) / 128, 128, 0, st>>>(*frame, d_skip8x8, g_cdef_dir, g_cdef_var);

@@ -63,6 +63,12 @@ struct Context {
     std::mutex          mu;
     std::vector<Lane*>  lanes;
     unsigned long long  launches = 0;  // kernels launched by this library (bench "gpu_launches")
+    // lifetime of module state (svt_b200_shutdown -> svt_b200_init on another device must not meet anything of the old one)
+    int                          epoch = 0;      // bumped by every successful svt_b200_init
+    std::vector<void*>           scratch;        // every device scratch buffer of every module: freed at shutdown, never earlier
+    std::vector<void (*)()>      resets;         // per-module "forget your cached pointers" hooks
+    std::vector<cudaStream_t>    side_streams;   // ForkJoin handles of all host threads
+    std::vector<cudaEvent_t>     side_events;
 };
 
 Context& ctx();
@@ -70,6 +76,12 @@ void     require_ready();  // aborts loudly when svt_b200_init() has not succeed
 Lane*    lane_acquire();
 void     lane_release(Lane* l);
 void     count_launch(int n = 1);
+// Device scratch owned by the library.  A module that outgrows a buffer takes a new one and leaves the old one alone:
+// a CUDA graph captured earlier may still reference it.  Everything is released by svt_b200_shutdown().
+void*    scratch_alloc(size_t bytes);
+void     register_reset(void (*fn)());  // fn drops the module's cached scratch pointers / capacities (called at shutdown)
+int      epoch();                       // changes with every (re-)initialisation: per-function attributes are re-applied
+struct ResetHook { explicit ResetHook(void (*fn)()) { register_reset(fn); } };
 void     txfm_tables_init();  // txfm.cu: uploads the transform constant tables
 
 // Side streams for calls whose launches are independent of each other: fork_streams() makes the side
@@ -79,7 +91,7 @@ struct ForkJoin {
     static constexpr int kSide = 3;
     cudaStream_t side[kSide];
     cudaEvent_t  forked, done[kSide];
-    bool         ready = false;
+    int          epoch = -1;  // the initialisation these handles belong to
 };
 ForkJoin& fork_streams(cudaStream_t user);
 void      join_streams(ForkJoin& fj, cudaStream_t user);

@@ -63,6 +63,23 @@ void lane_release(Lane* l) {
     l->busy = false;
 }
 
+void* scratch_alloc(size_t bytes) {
+    void* p = nullptr;
+    B200_CUDA_CHECK(cudaMalloc(&p, bytes ? bytes : 1));
+    std::lock_guard<std::mutex> lk(g_ctx.mu);
+    g_ctx.scratch.push_back(p);
+    return p;
+}
+// the hooks register from static initialisers of other translation units: the list must not depend on the construction
+// order of namespace-scope objects, hence function-local statics
+static std::vector<void (*)()>& reset_list() { static std::vector<void (*)()> v; return v; }
+static std::mutex& reset_mu() { static std::mutex m; return m; }
+void register_reset(void (*fn)()) {
+    std::lock_guard<std::mutex> lk(reset_mu());
+    reset_list().push_back(fn);
+}
+int epoch() { return g_ctx.epoch; }
+
 void count_launch(int n) { __atomic_fetch_add(&g_ctx.launches, (unsigned long long)n, __ATOMIC_RELAXED); }
 
 }  // namespace b200
@@ -89,6 +106,7 @@ extern "C" int svt_b200_init(int device) {
     c.sm_count = p.multiProcessorCount;
     c.max_smem = (int)p.sharedMemPerBlockOptin;
     txfm_tables_init();
+    c.epoch++;
     c.ready    = true;
     return SVT_B200_OK;
 }
@@ -106,6 +124,18 @@ extern "C" void svt_b200_shutdown(void) {
         delete l;
     }
     c.lanes.clear();
+    cudaDeviceSynchronize();
+    {
+        std::lock_guard<std::mutex> rl(reset_mu());
+        for (void (*fn)() : reset_list()) fn();   // modules forget their cached scratch / per-stream state ...
+    }
+    if (false) for (void (*fn)() : c.resets) fn();           // modules forget their cached scratch / per-stream state ...
+    for (void* p : c.scratch) cudaFree(p);        // ... and the scratch itself goes (nothing was freed before: captured graphs)
+    c.scratch.clear();
+    for (cudaStream_t s : c.side_streams) cudaStreamDestroy(s);
+    for (cudaEvent_t e : c.side_events) cudaEventDestroy(e);
+    c.side_streams.clear();
+    c.side_events.clear();
     c.ready = false;
 }
 
@@ -117,13 +147,21 @@ namespace b200 {
 
 ForkJoin& fork_streams(cudaStream_t user) {
     static thread_local ForkJoin fj;
-    if (!fj.ready) {
+    if (fj.epoch != g_ctx.epoch) {  // first use by this host thread, or the library was shut down and re-initialised since
         for (int i = 0; i < ForkJoin::kSide; i++) {
             B200_CUDA_CHECK(cudaStreamCreateWithFlags(&fj.side[i], cudaStreamNonBlocking));
             B200_CUDA_CHECK(cudaEventCreateWithFlags(&fj.done[i], cudaEventDisableTiming));
         }
         B200_CUDA_CHECK(cudaEventCreateWithFlags(&fj.forked, cudaEventDisableTiming));
-        fj.ready = true;
+        {
+            std::lock_guard<std::mutex> lk(g_ctx.mu);
+            for (int i = 0; i < ForkJoin::kSide; i++) {
+                g_ctx.side_streams.push_back(fj.side[i]);
+                g_ctx.side_events.push_back(fj.done[i]);
+            }
+            g_ctx.side_events.push_back(fj.forked);
+        }
+        fj.epoch = g_ctx.epoch;
     }
     B200_CUDA_CHECK(cudaEventRecord(fj.forked, user));
     for (int i = 0; i < ForkJoin::kSide; i++) B200_CUDA_CHECK(cudaStreamWaitEvent(fj.side[i], fj.forked, 0));

@@ -331,23 +331,22 @@ static std::mutex  g_me_mu;
 
 static void me_ws_reserve(MeWorkspace& w, size_t pairs) {
     if (pairs <= w.cap) return;
-    auto fr = [](void* p) { if (p) cudaFree(p); };
-    fr(w.items); fr(w.res); fr(w.side); fr(w.fp_items); fr(w.refs); fr(w.prm);
-    for (int l = 0; l < 3; l++) { fr(w.x[l]); fr(w.y[l]); fr(w.sad[l]); }
+    // a larger picture arrived on this stream: NEW buffers; the old ones stay valid (a captured graph may replay them) until shutdown
     w.cap = pairs * 2;
     const size_t n4 = w.cap * 4;
-    B200_CUDA_CHECK(cudaMalloc(&w.items, n4 * sizeof(SvtB200SadSearchItem)));
-    B200_CUDA_CHECK(cudaMalloc(&w.res, n4 * sizeof(SvtB200SadSearchResult)));
-    B200_CUDA_CHECK(cudaMalloc(&w.side, n4 * sizeof(HmeSide)));
+    w.items = (SvtB200SadSearchItem*)scratch_alloc(n4 * sizeof(SvtB200SadSearchItem));
+    w.res = (SvtB200SadSearchResult*)scratch_alloc(n4 * sizeof(SvtB200SadSearchResult));
+    w.side = (HmeSide*)scratch_alloc(n4 * sizeof(HmeSide));
     for (int l = 0; l < 3; l++) {
-        B200_CUDA_CHECK(cudaMalloc(&w.x[l], n4 * 2));
-        B200_CUDA_CHECK(cudaMalloc(&w.y[l], n4 * 2));
-        B200_CUDA_CHECK(cudaMalloc(&w.sad[l], n4 * 8));
+        w.x[l] = (int16_t*)scratch_alloc(n4 * 2);
+        w.y[l] = (int16_t*)scratch_alloc(n4 * 2);
+        w.sad[l] = (uint64_t*)scratch_alloc(n4 * 8);
     }
-    B200_CUDA_CHECK(cudaMalloc(&w.fp_items, w.cap * sizeof(SvtB200FullpelItem)));
-    B200_CUDA_CHECK(cudaMalloc(&w.refs, 16 * sizeof(SvtB200MePicture)));
-    B200_CUDA_CHECK(cudaMalloc(&w.prm, 16 * sizeof(SvtB200MeParams)));
+    w.fp_items = (SvtB200FullpelItem*)scratch_alloc(w.cap * sizeof(SvtB200FullpelItem));
+    w.refs = (SvtB200MePicture*)scratch_alloc(16 * sizeof(SvtB200MePicture));
+    w.prm = (SvtB200MeParams*)scratch_alloc(16 * sizeof(SvtB200MeParams));
 }
+static ResetHook g_me_reset([] { std::lock_guard<std::mutex> lk(g_me_mu); g_me_ws.clear(); });
 
 }  // namespace b200
 

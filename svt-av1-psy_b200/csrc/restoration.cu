@@ -272,8 +272,10 @@ extern "C" int svt_b200_lr_filter_frame_dev(const SvtB200LrPlane* planes, int n_
     }
     static std::mutex mu;
     static bool attr8 = false, attr16 = false;
+    static int  attr_epoch = -1;
     {
         std::lock_guard<std::mutex> lk(mu);
+        if (attr_epoch != epoch()) { attr8 = attr16 = false; attr_epoch = epoch(); }
         bool& a = bit_depth == 8 ? attr8 : attr16;
         if (!a) {
             if (bit_depth == 8) B200_CUDA_CHECK(cudaFuncSetAttribute(lr_filter_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLrSmem));

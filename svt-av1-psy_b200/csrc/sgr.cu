@@ -154,8 +154,10 @@ static void launch_sgr(const PIX* d_dgd, const SvtB200SgrUnit* d_units, int n, i
     const size_t smem = sgr_smem(max_w, max_h);
     static std::mutex mu;
     static size_t set8 = 0, set16 = 0;
+    static int    set_epoch = -1;
     {
         std::lock_guard<std::mutex> lk(mu);
+        if (set_epoch != epoch()) { set8 = set16 = 0; set_epoch = epoch(); }
         size_t& s = sizeof(PIX) == 1 ? set8 : set16;
         if (smem > 48 * 1024 && smem > s) {
             B200_CUDA_CHECK(cudaFuncSetAttribute(sgr_filter_kernel<PIX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(ctx().max_smem - 1024)));

@@ -346,8 +346,8 @@ template <int TEAM>
 static void launch_fwd_class(const int16_t* d_src, int32_t* d_dst, const SvtB200FwdTxfmItem* d_items, int n, cudaStream_t st) {
     constexpr int    THREADS = class_threads<TEAM>(), TEAMS = TEAM >= 64 ? 1 : THREADS / TEAM;
     constexpr size_t smem = (size_t)TEAMS * team_stride(TEAM) * 4;
-    static bool attr = false;
-    if (!attr) { set_smem_attr(fwd_txfm_kernel<TEAM, THREADS>, smem); attr = true; }
+    static int attr = -1;  // the initialisation (epoch) the attribute was applied in
+    if (attr != epoch()) { set_smem_attr(fwd_txfm_kernel<TEAM, THREADS>, smem); attr = epoch(); }
     const int per_sm = (int)((200 * 1024) / (smem + 1024)) < 2048 / THREADS ? (int)((200 * 1024) / (smem + 1024)) : 2048 / THREADS;
     fwd_txfm_kernel<TEAM, THREADS><<<grid_for((n + TEAMS - 1) / TEAMS, per_sm), THREADS, smem, st>>>(d_src, d_dst, d_items, n);
     B200_LAUNCH_CHECK();
@@ -368,8 +368,8 @@ static void launch_inv_class(const int32_t* d_coef, const PIX* d_pred, PIX* d_re
                              cudaStream_t st) {
     constexpr int    THREADS = class_threads<TEAM>(), TEAMS = TEAM >= 64 ? 1 : THREADS / TEAM;
     constexpr size_t smem = (size_t)TEAMS * team_stride(TEAM) * 4;
-    static bool attr = false;
-    if (!attr) { set_smem_attr(inv_txfm_kernel<TEAM, THREADS, PIX>, smem); attr = true; }
+    static int attr = -1;  // the initialisation (epoch) the attribute was applied in
+    if (attr != epoch()) { set_smem_attr(inv_txfm_kernel<TEAM, THREADS, PIX>, smem); attr = epoch(); }
     const int per_sm = (int)((200 * 1024) / (smem + 1024)) < 2048 / THREADS ? (int)((200 * 1024) / (smem + 1024)) : 2048 / THREADS;
     inv_txfm_kernel<TEAM, THREADS, PIX><<<grid_for((n + TEAMS - 1) / TEAMS, per_sm), THREADS, smem, st>>>(d_coef, d_pred, d_recon, d_items, n);
     B200_LAUNCH_CHECK();
@@ -393,8 +393,8 @@ static void launch_trio_class(const int16_t* d_src, const PIX* d_srcpix, const P
     if (n <= 0) return;
     constexpr int    THREADS = TEAM == 32 ? 128 : class_threads<TEAM>(), TEAMS = TEAM >= 32 ? 1 : THREADS / TEAM;
     constexpr size_t smem = (size_t)TEAMS * team_stride(TEAM) * 4;
-    static bool attr = false;
-    if (!attr) { set_smem_attr(trio_txfm_kernel<TEAM, THREADS, PIX>, smem); attr = true; }
+    static int attr = -1;  // the initialisation (epoch) the attribute was applied in
+    if (attr != epoch()) { set_smem_attr(trio_txfm_kernel<TEAM, THREADS, PIX>, smem); attr = epoch(); }
     const int per_sm = (int)((200 * 1024) / (smem + 1024)) < 2048 / THREADS ? (int)((200 * 1024) / (smem + 1024)) : 2048 / THREADS;
     trio_txfm_kernel<TEAM, THREADS, PIX><<<grid_for((n + TEAMS - 1) / TEAMS, per_sm), THREADS, smem, st>>>(d_src, d_srcpix, d_pred, d_recon, d_q, d_dq, d_iscan,
                                                                                                      d_qm, d_items, n, d_eobs);
@@ -532,12 +532,14 @@ extern "C" int svt_b200_residual_planes_dev(const void* d_source, const void* d_
 // ---- eob-bounded scan-order packing of the quantised levels (what the entropy coder consumes: the first eob levels of
 // each block in scan order, coding_loop.c / entropy_coding.c) -- the device->host transfer of a picture's coefficients then
 // carries sum(eob) levels instead of every coefficient position --------------------------------------------------------------
-// pass 1: per-chunk sums of the eobs (1024 blocks per CTA); pass 2 scans its own chunk, adds the sums of the chunks before
-// it (a picture has a few tens of chunks) and scatters the levels
-constexpr int kPackChunk = 1024;
-__global__ void __launch_bounds__(256) eob_chunk_sum_kernel(const uint16_t* __restrict__ eobs, int n, uint32_t* __restrict__ sums) {
+// pass 1: per-chunk sums of the eobs (256 blocks per CTA); pass 2 scans its own chunk, adds the sums of the chunks before
+// it (a picture has a few hundred chunks) and scatters the levels
+constexpr int kPackChunk = 256;
+__global__ void __launch_bounds__(256) eob_chunk_sum_kernel(const uint16_t* __restrict__ eobs, int n, uint32_t* __restrict__ sums,
+                                                            uint32_t* __restrict__ offs) {
     __shared__ uint32_t s_tot;
     if (threadIdx.x == 0) s_tot = 0;
+    if (threadIdx.x == 0 && blockIdx.x == 0) offs[n + 1] = 0;  // the count of levels that did not fit (pass 2 adds to it)
     __syncthreads();
     const int base = blockIdx.x * kPackChunk;
     uint32_t acc = 0;
@@ -548,11 +550,11 @@ __global__ void __launch_bounds__(256) eob_chunk_sum_kernel(const uint16_t* __re
     __syncthreads();
     if (threadIdx.x == 0) sums[blockIdx.x] = s_tot;
 }
-// one CTA per chunk of 1024 blocks: offsets of the chunk (shared-memory scan), then one warp per block reads the block's
+// one CTA per chunk of 256 blocks: offsets of the chunk (shared-memory scan), then one warp per block reads the block's
 // coefficients in RASTER order (coalesced) and writes each level with scan position < eob to its place -- the scatter stays
 // inside the block's eob-long output run
 template <typename LVL>
-__global__ void __launch_bounds__(1024) pack_levels_kernel(const int32_t* __restrict__ q_base, const int16_t* __restrict__ iscan_base,
+__global__ void __launch_bounds__(kPackChunk) pack_levels_kernel(const int32_t* __restrict__ q_base, const int16_t* __restrict__ iscan_base,
                                                             const SvtB200TrioItem* __restrict__ items, const uint16_t* __restrict__ eobs,
                                                             const uint32_t* __restrict__ sums, uint32_t* __restrict__ offs, int n, LVL* __restrict__ out,
                                                             uint32_t cap) {
@@ -560,12 +562,17 @@ __global__ void __launch_bounds__(1024) pack_levels_kernel(const int32_t* __rest
     __shared__ uint32_t s_warp[32];
     __shared__ uint32_t s_base;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, base = blockIdx.x * kPackChunk, i = base + threadIdx.x;
-    if (threadIdx.x == 0) {
+    if (threadIdx.x == 0) s_base = 0;
+    __syncthreads();
+    {   // levels of all chunks before this one
         uint32_t b = 0;
-        for (int c = 0; c < (int)blockIdx.x; c++) b += sums[c];
-        s_base = b;
-        if (blockIdx.x == gridDim.x - 1) { offs[n] = b + sums[blockIdx.x]; offs[n + 1] = 0; }
+        for (int c = threadIdx.x; c < (int)blockIdx.x; c += blockDim.x) b += sums[c];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) b += __shfl_xor_sync(0xffffffffu, b, o);
+        if (lane == 0 && b) atomicAdd(&s_base, b);
     }
+    __syncthreads();
+    if (threadIdx.x == 0 && blockIdx.x == gridDim.x - 1) offs[n] = s_base + sums[blockIdx.x];
     const uint32_t v = i < n ? eobs[i] : 0;
     uint32_t x = v;
 #pragma unroll
@@ -576,7 +583,7 @@ __global__ void __launch_bounds__(1024) pack_levels_kernel(const int32_t* __rest
     if (lane == 31) s_warp[warp] = x;
     __syncthreads();
     if (warp == 0) {
-        uint32_t w = s_warp[lane];
+        uint32_t w = lane < (kPackChunk >> 5) ? s_warp[lane] : 0;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const uint32_t y = __shfl_up_sync(0xffffffffu, w, o);
@@ -590,7 +597,7 @@ __global__ void __launch_bounds__(1024) pack_levels_kernel(const int32_t* __rest
     if (i < n) offs[i] = excl;
     __syncthreads();
     const int nb = min(kPackChunk, n - base);
-    for (int b = warp; b < nb; b += 32) {
+    for (int b = warp; b < nb; b += (kPackChunk >> 5)) {
         const int eob = eobs[base + b];
         if (!eob) continue;
         const SvtB200QuantItem& qi = items[base + b].quant;
@@ -619,19 +626,20 @@ extern "C" int svt_b200_pack_levels_dev(const int32_t* d_qcoeff, const int16_t* 
     {
         std::lock_guard<std::mutex> lk(mu);
         auto it = sums_of.find((cudaStream_t)stream);
+        static ResetHook hook([] { sums_of.clear(); });
         if (it == sums_of.end()) {
-            B200_CUDA_CHECK(cudaMalloc(&d_sums, 4096 * sizeof(uint32_t)));
+            d_sums = (uint32_t*)scratch_alloc(4096 * sizeof(uint32_t));
             sums_of[(cudaStream_t)stream] = d_sums;
         } else
             d_sums = it->second;
     }
-    eob_chunk_sum_kernel<<<chunks, 256, 0, (cudaStream_t)stream>>>(d_eobs, n_items, d_sums);
+    eob_chunk_sum_kernel<<<chunks, 256, 0, (cudaStream_t)stream>>>(d_eobs, n_items, d_sums, d_offsets);
     B200_LAUNCH_CHECK();
     if (level_bytes == 2)
-        pack_levels_kernel<int16_t><<<chunks, 1024, 0, (cudaStream_t)stream>>>(d_qcoeff, d_iscan, d_items, d_eobs, d_sums, d_offsets, n_items,
+        pack_levels_kernel<int16_t><<<chunks, kPackChunk, 0, (cudaStream_t)stream>>>(d_qcoeff, d_iscan, d_items, d_eobs, d_sums, d_offsets, n_items,
                                                                               (int16_t*)d_levels, capacity);
     else
-        pack_levels_kernel<int32_t><<<chunks, 1024, 0, (cudaStream_t)stream>>>(d_qcoeff, d_iscan, d_items, d_eobs, d_sums, d_offsets, n_items,
+        pack_levels_kernel<int32_t><<<chunks, kPackChunk, 0, (cudaStream_t)stream>>>(d_qcoeff, d_iscan, d_items, d_eobs, d_sums, d_offsets, n_items,
                                                                               (int32_t*)d_levels, capacity);
     B200_LAUNCH_CHECK();
     return SVT_B200_OK;

@@ -477,6 +477,7 @@ struct StatsScratch {
 };
 static std::map<cudaStream_t, StatsScratch> g_stats;
 static std::mutex g_stats_mu;
+static ResetHook g_stats_reset([] { std::lock_guard<std::mutex> lk(g_stats_mu); g_stats.clear(); });
 
 template <typename PIX>
 static void launch_stats(const PIX* d_dgd, const PIX* d_src, const SvtB200StatsItem* d_items, int n, int bd, long long* d_M,
@@ -611,10 +612,9 @@ extern "C" int svt_b200_compute_stats_batch_dev(const void* d_dgd, const void* d
     std::lock_guard<std::mutex> lk(g_stats_mu);
     StatsScratch& sc = g_stats[(cudaStream_t)stream];
     if ((size_t)n_items > sc.cap) {
-        if (sc.acc) { cudaFree(sc.acc); cudaFree(sc.tot); }
-        sc.cap = (size_t)n_items * 2;
-        B200_CUDA_CHECK(cudaMalloc(&sc.acc, sc.cap * kStatsMaxParts * 2450 * 8));
-        B200_CUDA_CHECK(cudaMalloc(&sc.tot, sc.cap * 8));
+        sc.cap = (size_t)n_items * 2;  // new buffers; the old ones live on until shutdown (captured graphs may replay them)
+        sc.acc = (long long*)scratch_alloc(sc.cap * kStatsMaxParts * 2450 * 8);
+        sc.tot = (unsigned long long*)scratch_alloc(sc.cap * 8);
     }
     if (bit_depth > 8)
         launch_stats<uint16_t>((const uint16_t*)d_dgd, (const uint16_t*)d_src, d_items, n_items, bit_depth, (long long*)d_M, (long long*)d_H,

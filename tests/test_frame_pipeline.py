@@ -128,3 +128,38 @@ def test_frame_matches_committed_golden_fixture(b200, name):
     torch.cuda.synchronize()
     assert digest(fp.residual) == g["sha256"]["residual"]
     assert digest(fp.coeff) == g["sha256"]["coeff"]
+
+
+def test_shutdown_then_init_again_leaves_no_stale_state():
+    """svt_b200_shutdown() releases every module's scratch, side streams and cached attributes; a second svt_b200_init() in the
+    same process must work from a clean slate (stale per-stream workspaces / skipped cudaFuncSetAttribute)"""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = r"""
+import sys
+sys.path.insert(0, %r)
+import torch
+import svt_av1_psy_b200 as pkg
+from svt_av1_psy_b200.pipeline import FramePipeline
+from svt_av1_psy_b200.workload import FrameWorkload
+outs = []
+for rnd in range(3):
+    pkg.init(0)
+    fp = FramePipeline(FrameWorkload(384, 256, bit_depth=8 if rnd != 1 else 10, preset=8 if rnd != 1 else 6), torch)
+    fp.step()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        fp.step()
+    g.replay()
+    torch.cuda.synchronize()
+    outs.append((int(fp.final.to(torch.int64).sum()), int(fp.me_sad.to(torch.int64).sum()), int(fp.Hm.sum())))
+    del g, fp
+    torch.cuda.synchronize()
+    pkg.shutdown()
+assert outs[0] == outs[2], outs
+print("REINIT_OK", outs)
+""" % root
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "REINIT_OK" in r.stdout, (r.stdout[-500:], r.stderr[-2000:])
