@@ -532,8 +532,7 @@ extern "C" int svt_b200_residual_planes_dev(const void* d_source, const void* d_
 // ---- eob-bounded scan-order packing of the quantised levels (what the entropy coder consumes: the first eob levels of
 // each block in scan order, coding_loop.c / entropy_coding.c) -- the device->host transfer of a picture's coefficients then
 // carries sum(eob) levels instead of every coefficient position --------------------------------------------------------------
-// pass 1: per-chunk sums of the eobs (256 blocks per CTA); pass 2 scans its own chunk, adds the sums of the chunks before
-// it (a picture has a few hundred chunks) and scatters the levels
+// pass 1: per-chunk sums of the eobs (256 blocks per CTA; a picture has a few hundred chunks)
 constexpr int kPackChunk = 256;
 __global__ void __launch_bounds__(256) eob_chunk_sum_kernel(const uint16_t* __restrict__ eobs, int n, uint32_t* __restrict__ sums,
                                                             uint32_t* __restrict__ offs) {
@@ -550,21 +549,16 @@ __global__ void __launch_bounds__(256) eob_chunk_sum_kernel(const uint16_t* __re
     __syncthreads();
     if (threadIdx.x == 0) sums[blockIdx.x] = s_tot;
 }
-// one CTA per chunk of 256 blocks: offsets of the chunk (shared-memory scan), then one warp per block reads the block's
-// coefficients in RASTER order (coalesced) and writes each level with scan position < eob to its place -- the scatter stays
-// inside the block's eob-long output run
-template <typename LVL>
-__global__ void __launch_bounds__(kPackChunk) pack_levels_kernel(const int32_t* __restrict__ q_base, const int16_t* __restrict__ iscan_base,
-                                                            const SvtB200TrioItem* __restrict__ items, const uint16_t* __restrict__ eobs,
-                                                            const uint32_t* __restrict__ sums, uint32_t* __restrict__ offs, int n, LVL* __restrict__ out,
-                                                            uint32_t cap) {
-    __shared__ uint32_t s_off[kPackChunk];
+// pass 2, one CTA per chunk of 256 blocks: exclusive offsets of the chunk (warp + shared-memory scan) on top of the levels of all
+// chunks before it
+__global__ void __launch_bounds__(kPackChunk) eob_offsets_kernel(const uint16_t* __restrict__ eobs, const uint32_t* __restrict__ sums,
+                                                                 uint32_t* __restrict__ offs, int n) {
     __shared__ uint32_t s_warp[32];
     __shared__ uint32_t s_base;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, base = blockIdx.x * kPackChunk, i = base + threadIdx.x;
     if (threadIdx.x == 0) s_base = 0;
     __syncthreads();
-    {   // levels of all chunks before this one
+    {
         uint32_t b = 0;
         for (int c = threadIdx.x; c < (int)blockIdx.x; c += blockDim.x) b += sums[c];
 #pragma unroll
@@ -592,25 +586,39 @@ __global__ void __launch_bounds__(kPackChunk) pack_levels_kernel(const int32_t* 
         s_warp[lane] = w;
     }
     __syncthreads();
-    const uint32_t excl = x - v + (warp ? s_warp[warp - 1] : 0) + s_base;
-    s_off[threadIdx.x] = excl;
-    if (i < n) offs[i] = excl;
-    __syncthreads();
-    const int nb = min(kPackChunk, n - base);
-    for (int b = warp; b < nb; b += (kPackChunk >> 5)) {
-        const int eob = eobs[base + b];
+    if (i < n) offs[i] = x - v + (warp ? s_warp[warp - 1] : 0) + s_base;
+}
+// pass 3, one warp per block, as many warps in flight as the GPU holds: the block's coefficients are read in RASTER order
+// (coalesced, four independent loads per lane in flight) and each level with scan position < eob goes to its place -- the scatter
+// stays inside the block's eob-long output run
+template <typename LVL>
+__global__ void __launch_bounds__(256) pack_levels_kernel(const int32_t* __restrict__ q_base, const int16_t* __restrict__ iscan_base,
+                                                           const SvtB200TrioItem* __restrict__ items, const uint16_t* __restrict__ eobs,
+                                                           uint32_t* __restrict__ offs, int n, LVL* __restrict__ out, uint32_t cap) {
+    const int lane = threadIdx.x & 31;
+    for (int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); b < n; b += gridDim.x * (blockDim.x >> 5)) {
+        const int eob = eobs[b];
         if (!eob) continue;
-        const SvtB200QuantItem& qi = items[base + b].quant;
+        const SvtB200QuantItem& qi = items[b].quant;
         const int32_t* q = q_base + qi.q_off;
         const int16_t* isc = iscan_base + qi.scan_off;
-        const uint32_t o = s_off[b];
+        const uint32_t o = offs[b];
         const int nc = qi.n_coeffs;
-        for (int rc = lane; rc < nc; rc += 32) {
-            const int k = isc[rc];
-            if (k >= eob || o + k >= cap) continue;
-            const int32_t lv = q[rc];
-            if (sizeof(LVL) == 2 && (lv < -32768 || lv > 32767)) atomicAdd(&offs[n + 1], 1u);  // cannot happen for 8-bit pictures; counted, never silent
-            out[o + k] = (LVL)lv;
+        for (int rc0 = 0; rc0 < nc; rc0 += 128) {
+            int k[4];
+            int32_t lv[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int rc = rc0 + 32 * j + lane;
+                k[j] = rc < nc ? (int)isc[rc] : 0x7fff;
+                lv[j] = rc < nc ? q[rc] : 0;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                if (k[j] >= eob || o + k[j] >= cap) continue;
+                if (sizeof(LVL) == 2 && (lv[j] < -32768 || lv[j] > 32767)) atomicAdd(&offs[n + 1], 1u);  // cannot happen for 8-bit pictures; counted, never silent
+                out[o + k[j]] = (LVL)lv[j];
+            }
         }
     }
 }
@@ -635,12 +643,15 @@ extern "C" int svt_b200_pack_levels_dev(const int32_t* d_qcoeff, const int16_t* 
     }
     eob_chunk_sum_kernel<<<chunks, 256, 0, (cudaStream_t)stream>>>(d_eobs, n_items, d_sums, d_offsets);
     B200_LAUNCH_CHECK();
+    eob_offsets_kernel<<<chunks, kPackChunk, 0, (cudaStream_t)stream>>>(d_eobs, d_sums, d_offsets, n_items);
+    B200_LAUNCH_CHECK();
+    const int grid = grid_for((n_items + 7) / 8, 8);
     if (level_bytes == 2)
-        pack_levels_kernel<int16_t><<<chunks, kPackChunk, 0, (cudaStream_t)stream>>>(d_qcoeff, d_iscan, d_items, d_eobs, d_sums, d_offsets, n_items,
-                                                                              (int16_t*)d_levels, capacity);
+        pack_levels_kernel<int16_t><<<grid, 256, 0, (cudaStream_t)stream>>>(d_qcoeff, d_iscan, d_items, d_eobs, d_offsets, n_items, (int16_t*)d_levels,
+                                                                           capacity);
     else
-        pack_levels_kernel<int32_t><<<chunks, kPackChunk, 0, (cudaStream_t)stream>>>(d_qcoeff, d_iscan, d_items, d_eobs, d_sums, d_offsets, n_items,
-                                                                              (int32_t*)d_levels, capacity);
+        pack_levels_kernel<int32_t><<<grid, 256, 0, (cudaStream_t)stream>>>(d_qcoeff, d_iscan, d_items, d_eobs, d_offsets, n_items, (int32_t*)d_levels,
+                                                                           capacity);
     B200_LAUNCH_CHECK();
     return SVT_B200_OK;
 }

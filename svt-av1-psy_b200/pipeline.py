@@ -298,7 +298,7 @@ class FramePipeline:
     CALLS = (("me_pyramid", "me", "downsample_2d_kernel+pad_plane_kernel"),
              ("me_search", "me", "hme_fused_kernel + fullpel_search_kernel"),
              ("txfm_trio", "tx", "trio_txfm_kernel<4..64> (residual + forward transform + quantise + inverse transform fused)"),
-             ("pack_levels", "tx", "eob_chunk_sum_kernel+pack_levels_kernel"),
+             ("pack_levels", "tx", "eob_chunk_sum_kernel+eob_offsets_kernel+pack_levels_kernel"),
              ("cdef_search", "cdef", "cdef_dir_kernel+cdef_search_kernel"),
              ("cdef_apply", "cdef", "cdef_apply_kernel"),
              ("lr_boundaries", "rest", "lr_save_boundary_kernel x2"),

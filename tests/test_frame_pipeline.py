@@ -148,9 +148,12 @@ outs = []
 for rnd in range(3):
     pkg.init(0)
     fp = FramePipeline(FrameWorkload(384, 256, bit_depth=8 if rnd != 1 else 10, preset=8 if rnd != 1 else 6), torch)
-    fp.step()
+    st = torch.cuda.Stream()
+    with torch.cuda.stream(st):
+        fp.step()          # the library's per-stream scratch is created outside the capture
+    torch.cuda.synchronize()
     g = torch.cuda.CUDAGraph()
-    with torch.cuda.graph(g):
+    with torch.cuda.graph(g, stream=st):
         fp.step()
     g.replay()
     torch.cuda.synchronize()
