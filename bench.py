@@ -258,7 +258,9 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        import datetime
+        # a mismatched exchange must fail within minutes, not hang the box
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), timeout=datetime.timedelta(seconds=180))
     dsp.init(local_rank)
     W, wls = make_workloads(args, rank, N_FRAME_SETS)
     wl0 = wls[0]
@@ -421,6 +423,10 @@ def main():
     def timed(fn, steps):
         """the steps-long loop, repeated until the timed regions add up to >= --min-time; median region"""
         first = fn(steps)
+        if world > 1:  # every rank must run the SAME number of loops (each loop posts point-to-point exchanges): agree on the slowest rank's time
+            t = torch.tensor([first], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            first = float(t[0])
         reps = int(min(60, max(1, -(-args.min_time * 1e3 // max(first, 1e-3)))))
         vals = [fn(steps) for _ in range(reps)]
         vals.sort()
