@@ -366,6 +366,7 @@ def main():
 
     s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
 
+    host_enqueue = [0.0, 0]  # seconds the host spent enqueueing e2e frames, frames
     D2H_LAG = 2  # the variable-size part of a frame's results is requested this many frames later (its size has arrived by then)
     d2h_level_bytes = [0, 0]  # bytes, frames
 
@@ -388,6 +389,7 @@ def main():
                 d2h_level_bytes[1] += 1
                 ev_out[k].record(s_out)
 
+        t_host = time.perf_counter()
         start.record(stream)
         s_in.wait_event(start)
         if comm is not None:
@@ -417,6 +419,8 @@ def main():
         stream.wait_event(ev_out[n - 1])
         ex.finish(stream)
         end.record(stream)
+        host_enqueue[0] += time.perf_counter() - t_host
+        host_enqueue[1] += n
         torch.cuda.synchronize()
         return start.elapsed_time(end)
 
@@ -514,7 +518,8 @@ def main():
            "e2e": {"value": round(fps_e2e, 2), "unit": "frames/s", "h2d_bytes_per_step": int(sets[0].h2d_bytes),
                    "d2h_bytes_per_step": int(sets[0].d2h_fixed_bytes + d2h_level_bytes[0] / max(1, d2h_level_bytes[1])),
                    "d2h_note": "fixed-size results + sum(eob) scan-order levels (%d-byte), averaged over the timed frames" % sets[0].level_bytes,
-                   "ms_per_step": round(ms_e2e / args.steps, 4), "inner_repeats": reps_e2e},
+                   "ms_per_step": round(ms_e2e / args.steps, 4), "inner_repeats": reps_e2e,
+                   "host_enqueue_ms_per_step": round(1e3 * host_enqueue[0] / max(1, host_enqueue[1]), 4)},
            "gpu_launches": int(round(launches_per_step * args.steps)), "gpu_launches_per_step": round(launches_per_step, 1),
            "eager_ms_per_step": round(ms_eager / prof_steps, 4), "roofline": roofline,
            "stages_ms": {n: round(v, 4) for n, v in zip(names, stage_ms)},

@@ -24,6 +24,7 @@
 #include "common.cuh"
 #include "wiener_unit.cuh"
 #include "../../include/svt_b200.h"
+#include "wiener_stats_lag.cuh"
 
 namespace b200 {
 
@@ -479,9 +480,46 @@ static std::map<cudaStream_t, StatsScratch> g_stats;
 static std::mutex g_stats_mu;
 static ResetHook g_stats_reset([] { std::lock_guard<std::mutex> lk(g_stats_mu); g_stats.clear(); });
 
+template <typename PIX, int WIN>
+static void launch_lag_bulk(const PIX* d_dgd, const PIX* d_src, const SvtB200StatsItem* d_items, int n, int cpi, unsigned long long* acc,
+                            cudaStream_t st) {
+    constexpr size_t smem = lag_bulk_smem<PIX, WIN>();
+    static int attr = -1;
+    if (attr != epoch()) {
+        if (smem > 48 * 1024)
+            B200_CUDA_CHECK(cudaFuncSetAttribute(stats_lag_bulk_kernel<PIX, WIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr = epoch();
+    }
+    stats_lag_bulk_kernel<PIX, WIN><<<dim3(cpi, n), 256, smem, st>>>(d_dgd, d_src, d_items, acc);
+    B200_LAUNCH_CHECK();
+}
+
+// Wiener statistics of a batch of units by lag sums (wiener_stats_lag.cuh)
 template <typename PIX>
 static void launch_stats(const PIX* d_dgd, const PIX* d_src, const SvtB200StatsItem* d_items, int n, int bd, long long* d_M,
                          long long* d_H, long long* d_acc, unsigned long long* d_tot, cudaStream_t st) {
+    const int divider = bd == 12 ? 16 : (bd == 10 ? 4 : 1);
+    int cpi = (ctx().sm_count * 8) / (n > 0 ? n : 1);  // CTAs per unit: ~8 resident CTAs per SM over the batch
+    if (cpi < 1) cpi = 1;
+    if (cpi > 64) cpi = 64;
+    unsigned long long* acc = reinterpret_cast<unsigned long long*>(d_acc);
+    B200_CUDA_CHECK(cudaMemsetAsync(d_tot, 0, (size_t)n * sizeof(unsigned long long), st));
+    B200_CUDA_CHECK(cudaMemsetAsync(acc, 0, (size_t)n * kLagItemWords * sizeof(unsigned long long), st));
+    stats_sum_kernel<PIX><<<n * kSumParts, 256, 0, st>>>(d_dgd, d_items, d_tot);
+    B200_LAUNCH_CHECK();
+    // one launch per window size; units of another size leave at once (a batch mixes 7x7 luma with 5x5 chroma units)
+    launch_lag_bulk<PIX, 7>(d_dgd, d_src, d_items, n, cpi, acc, st);
+    launch_lag_bulk<PIX, 5>(d_dgd, d_src, d_items, n, cpi, acc, st);
+    launch_lag_bulk<PIX, 3>(d_dgd, d_src, d_items, n, cpi, acc, st);
+    stats_lag_edges_kernel<PIX><<<dim3(kLagSlots, n), 256, 0, st>>>(d_dgd, d_items, acc);
+    B200_LAUNCH_CHECK();
+    stats_lag_finalize_kernel<PIX><<<dim3((49 * 50 / 2 + 49 + 127) / 128, n), 128, 0, st>>>(d_dgd, d_items, acc, d_tot, divider, d_M, d_H);
+    B200_LAUNCH_CHECK();
+}
+
+template <typename PIX>
+static void launch_stats_old(const PIX* d_dgd, const PIX* d_src, const SvtB200StatsItem* d_items, int n, int bd, long long* d_M,
+                             long long* d_H, long long* d_acc, unsigned long long* d_tot, cudaStream_t st) {
     const int maxv = (1 << bd) - 1;
     long long fp = 2147483647ll / ((long long)maxv * maxv);
     if (fp > 30000) fp = 30000;

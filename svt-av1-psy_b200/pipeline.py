@@ -17,6 +17,26 @@ def _t(torch, arr, dtype=None):
     return t.cuda(non_blocking=False)
 
 
+class _Arena:
+    """one contiguous device buffer + its pinned host twin, carved into typed views at 256-byte aligned offsets: a frame's
+    inputs (or fixed-size results) then cross PCIe in ONE copy instead of one per array"""
+
+    def __init__(self, torch, specs, device):
+        self.torch = torch
+        off, self.slots = 0, {}
+        for name, dtype, shape in specs:
+            n = int(np.prod(shape)) * torch.empty(0, dtype=dtype).element_size()
+            self.slots[name] = (off, n, dtype, tuple(shape))
+            off = (off + n + 255) & ~255
+        self.nbytes = off
+        self.dev = torch.zeros(off, dtype=torch.uint8, device=device)
+        self.host = torch.zeros(off, dtype=torch.uint8).pin_memory()
+
+    def view(self, name, host=False):
+        off, n, dtype, shape = self.slots[name]
+        return (self.host if host else self.dev)[off:off + n].view(dtype).view(shape)
+
+
 class FramePipeline:
     def __init__(self, wl, torch, device="cuda"):
         self.wl, self.torch = wl, torch
@@ -44,23 +64,30 @@ class FramePipeline:
                 setattr(self.me_prm[i], k, v)
         nb = ((W + 63) // 64) * ((H + 63) // 64)
         self.n_b64 = nb
-        self.me_sad = T.zeros((wl.n_refs, nb, 85), dtype=T.int32, device=device)
-        self.me_mv = T.zeros_like(self.me_sad)
+        _, n_flat = wl.flat_offsets()
+        _, n_pad = wl.padded_offsets()
+        self.n_tx = len(wl.quant_items)
+        # everything the host-side stages read back, in one arena (one device -> host copy per frame)
+        self._out = _Arena(T, [("me_sad", T.int32, (wl.n_refs, nb, 85)), ("me_mv", T.int32, (wl.n_refs, nb, 85)), ("eobs", T.int16, (self.n_tx,)),
+                               ("level_offsets", T.int32, (self.n_tx + 2,)), ("mse", T.int64, (2, nb, len(wl.cdef_str_y))),
+                               ("M", T.int64, (len(wl.stats_items), 49)), ("H", T.int64, (len(wl.stats_items), 2401)), ("final", pix, (n_pad,))], device)
+        # ... and what arrives from the host per frame (source picture + prediction): one host -> device copy
+        self._in = _Arena(T, [("cur", pix, (n_flat,)), ("pred", pix, (n_pad,))], device)
+        self.me_sad = self._out.view("me_sad")
+        self.me_mv = self._out.view("me_mv")
         self.me_centre = T.zeros((wl.n_refs, nb, 2), dtype=T.int16, device=device)
         self.me_hme_sad = T.zeros((wl.n_refs, nb), dtype=T.int64, device=device)
         # ---- TX ---------------------------------------------------------------------------------------
-        _, n_flat = wl.flat_offsets()
-        _, n_pad = wl.padded_offsets()
-        self.cur_flat = T.zeros(n_flat, dtype=pix, device=device)          # source picture Y|U|V
+        self.cur_flat = self._in.view("cur")                               # source picture Y|U|V
         self.residual = T.zeros(n_flat, dtype=T.int16, device=device)
-        self.pred = T.zeros(n_pad, dtype=pix, device=device)               # padded planes
+        self.pred = self._in.view("pred")                                  # padded planes
         self.recon = T.zeros(n_pad, dtype=pix, device=device)
         self.cdef_out = T.zeros(n_pad, dtype=pix, device=device)
-        self.final = T.zeros(n_pad, dtype=pix, device=device)
+        self.final = self._out.view("final")
         self.coeff = T.zeros(wl.n_coeffs, dtype=T.int32, device=device)
         self.qcoeff = T.zeros_like(self.coeff)
         self.dqcoeff = T.zeros_like(self.coeff)
-        self.eobs = T.zeros(len(wl.quant_items), dtype=T.int16, device=device)
+        self.eobs = self._out.view("eobs")
         self.fwd_items = _t(T, wl.fwd_items.view(np.uint8))
         self.inv_items = _t(T, wl.inv_items.view(np.uint8))
         self.quant_items = _t(T, wl.quant_items.view(np.uint8))
@@ -71,7 +98,7 @@ class FramePipeline:
         # ---- CDEF -------------------------------------------------------------------------------------
         self.skip = _t(T, wl.skip8x8)
         self.str_y, self.str_uv = _t(T, wl.cdef_str_y), _t(T, wl.cdef_str_uv)
-        self.cdef_mse = T.zeros((2, nb, len(wl.cdef_str_y)), dtype=T.int64, device=device)
+        self.cdef_mse = self._out.view("mse")
         self.cdef_dir = T.zeros((nb, 64), dtype=T.uint8, device=device)
         self.cdef_var = T.zeros((nb, 64), dtype=T.int32, device=device)
         self.fb_idx = _t(T, wl.cdef_fb_idx)
@@ -82,21 +109,22 @@ class FramePipeline:
         self.lr_above = [T.zeros(2 * wl.lr_num_stripes(p) * wl.lr_boundary_stride(p), dtype=pix, device=device) for p in range(3)]
         self.lr_below = [T.zeros(2 * wl.lr_num_stripes(p) * wl.lr_boundary_stride(p), dtype=pix, device=device) for p in range(3)]
         self._lr_planes = None
-        self.M = T.zeros((len(wl.stats_items), 49), dtype=T.int64, device=device)
-        self.Hm = T.zeros((len(wl.stats_items), 2401), dtype=T.int64, device=device)
+        self.M = self._out.view("M")
+        self.Hm = self._out.view("H")
         # ---- host staging for the end-to-end arm ------------------------------------------------------
         as_t = (lambda a: T.from_numpy(a)) if self.psz == 1 else (lambda a: T.from_numpy(a.view(np.int16)))
-        self.h_cur = as_t(np.concatenate([p.reshape(-1) for p in wl.cur])).pin_memory()
-        self.h_pred = as_t(self._pad_planes(wl.pred)).pin_memory()
+        self.h_cur = self._in.view("cur", host=True)
+        self.h_pred = self._in.view("pred", host=True)
+        self.h_cur.copy_(as_t(np.concatenate([p.reshape(-1) for p in wl.cur])))
+        self.h_pred.copy_(as_t(self._pad_planes(wl.pred)))
         # 10-bit input: the 8-bit luma open-loop ME searches is made by the picture-input stage on the host
         self.h_luma8 = None if self.psz == 1 else T.from_numpy(np.ascontiguousarray(wl.me_luma(wl.cur))).pin_memory()
         # what the host-side stages consume: ME results, per-block eobs + the eob-bounded scan-order levels (entropy coder),
         # CDEF costs, Wiener statistics (the host solves the filters), the filtered picture
-        self.n_tx = len(wl.quant_items)
         self.level_bytes = 2 if self.bd == 8 else 4
         self.levels = T.zeros(wl.n_coeffs, dtype=T.int16 if self.level_bytes == 2 else T.int32, device=device)
-        self.level_offsets = T.zeros(self.n_tx + 2, dtype=T.int32, device=device)
-        self.h_out = {k: T.empty_like(v, device="cpu").pin_memory() for k, v in self._small_outputs().items()}
+        self.level_offsets = self._out.view("level_offsets")
+        self.h_out = {k: self._out.view(k, host=True) for k in self._out.slots}
         self.h_levels = T.empty_like(self.levels, device="cpu").pin_memory()
         self._res_planes = None
         self.load_inputs()
@@ -138,8 +166,7 @@ class FramePipeline:
     def load_inputs(self, stream=None):
         """host -> device copy of one frame's inputs (source picture, residual, prediction)"""
         T = self.torch
-        self.cur_flat.copy_(self.h_cur, non_blocking=True)
-        self.pred.copy_(self.h_pred, non_blocking=True)
+        self._in.dev.copy_(self._in.host, non_blocking=True)  # source picture + prediction in one transfer
         W, H, pad = self.wl.width, self.wl.height, self._full_pad
         # the full-resolution luma of the ME pyramid is the padded (8-bit) source picture
         if self.psz == 1:
@@ -149,14 +176,10 @@ class FramePipeline:
         s = T.cuda.current_stream().cuda_stream
         assert lib.svt_b200_extend_plane_dev(self.cur_planes[2].data_ptr(), self.cur_planes[2].stride(0), W, H, pad, pad, s) == 0
 
-    def _small_outputs(self):
-        return dict(me_sad=self.me_sad, me_mv=self.me_mv, eobs=self.eobs, level_offsets=self.level_offsets, mse=self.cdef_mse, M=self.M, H=self.Hm,
-                    final=self.final)
-
     def read_outputs(self):
-        """device -> host, part 1: everything of fixed size (includes the level offsets, whose last entries say how many levels follow)"""
-        for k, src in self._small_outputs().items():
-            self.h_out[k].copy_(src, non_blocking=True)
+        """device -> host, part 1: everything of fixed size in one transfer (includes the level offsets, whose last entries say how
+        many levels follow)"""
+        self._out.host.copy_(self._out.dev, non_blocking=True)
 
     def read_levels(self):
         """part 2, once part 1 has arrived: exactly sum(eob) levels.  Returns the bytes copied."""
@@ -173,7 +196,7 @@ class FramePipeline:
 
     @property
     def d2h_fixed_bytes(self):
-        return sum(v.numel() * v.element_size() for v in self.h_out.values())
+        return sum(n for (_, n, _, _) in self._out.slots.values())
 
     # -- the calls of one frame, in path order (each is one T2 entry point of include/svt_b200.h) -----------
     def call_me_pyramid(self, s):
