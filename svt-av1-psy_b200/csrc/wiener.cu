@@ -511,7 +511,7 @@ static void launch_stats(const PIX* d_dgd, const PIX* d_src, const SvtB200StatsI
     launch_lag_bulk<PIX, 7>(d_dgd, d_src, d_items, n, cpi, acc, st);
     launch_lag_bulk<PIX, 5>(d_dgd, d_src, d_items, n, cpi, acc, st);
     launch_lag_bulk<PIX, 3>(d_dgd, d_src, d_items, n, cpi, acc, st);
-    stats_lag_edges_kernel<PIX><<<dim3(kLagSlots, n), 256, 0, st>>>(d_dgd, d_items, acc);
+    stats_lag_edges_kernel<PIX><<<n, 256, 0, st>>>(d_dgd, d_items, acc);
     B200_LAUNCH_CHECK();
     stats_lag_finalize_kernel<PIX><<<dim3((49 * 50 / 2 + 49 + 127) / 128, n), 128, 0, st>>>(d_dgd, d_items, acc, d_tot, divider, d_M, d_H);
     B200_LAUNCH_CHECK();

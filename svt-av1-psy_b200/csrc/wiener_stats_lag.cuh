@@ -75,11 +75,16 @@ stats_lag_bulk_kernel(const PIX* __restrict__ dgd_base, const PIX* __restrict__ 
     const PIX* dgd = dgd_base + s.dgd_off;
     const PIX* src = src_base + s.src_off;
     const int g = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    unsigned long long totH[2 * WIN - 1], totM[WIN], totY = 0, totX = 0;
+    __shared__ unsigned long long s_tot[kLagAccStride];  // the CTA's share of CC / sum x Y / sum x, flushed to global at the end
+    for (int i = threadIdx.x; i < kLagAccStride; i += blockDim.x) s_tot[i] = 0;
+    unsigned long long* acc = acc_base + (size_t)blockIdx.y * kLagItemWords;
+    // warp-wide sum of a 32-bit partial (a work unit's partial cannot overflow: 8 rows x 512 columns / 32 lanes of <= 2 x 4095^2)
+    auto wsum = [&](uint32_t v) {
+        unsigned long long t = v;
 #pragma unroll
-    for (int k = 0; k < 2 * WIN - 1; k++) totH[k] = 0;
-#pragma unroll
-    for (int k = 0; k < WIN; k++) totM[k] = 0;
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        return t;
+    };
     const int nbands = (h + kLagBandRows - 1) / kLagBandRows, nsegs = (w + kLagSegW - 1) / kLagSegW;
     for (int wu = blockIdx.x; wu < nbands * nsegs; wu += gridDim.x) {
         const int band = wu / nsegs, seg = wu - band * nsegs;
@@ -91,11 +96,14 @@ stats_lag_bulk_kernel(const PIX* __restrict__ dgd_base, const PIX* __restrict__ 
             PIX* yb = reinterpret_cast<PIX*>(Yt);
             constexpr int PPR = PITCH * 4 / S;  // pixels per tile row
             const int trows = (b1 - b0) + 3 * HALF;
-            for (int i = threadIdx.x; i < trows * PPR; i += blockDim.x) {
-                const int tr = i / PPR, tc = i - tr * PPR;
+            // only the columns this segment can touch (a 128-wide chroma unit does not pay for a 512-wide tile)
+            int spx = P::OFFP + xw + 2 * WIN + 2 * G;
+            spx = spx < PPR ? (spx + G - 1) / G * G : PPR;
+            for (int i = threadIdx.x; i < trows * spx; i += blockDim.x) {
+                const int tr = i / spx, tc = i - tr * spx;
                 const int u = b0 - HALF + tr, v = cv0 + c0 - P::OFFP + tc;
                 const bool in = u >= vs - HALF && u < ve + HALF && v >= hs - HALF && v < he + HALF;
-                yb[i] = in ? dgd[(ptrdiff_t)u * s.dgd_stride + v] : (PIX)0;
+                yb[tr * PPR + tc] = in ? dgd[(ptrdiff_t)u * s.dgd_stride + v] : (PIX)0;
             }
             PIX* xb = reinterpret_cast<PIX*>(Xt);
             constexpr int XPR = XPITCH * 4 / S;
@@ -112,14 +120,25 @@ stats_lag_bulk_kernel(const PIX* __restrict__ dgd_base, const PIX* __restrict__ 
         for (int k = 0; k < WIN; k++) accM[k] = 0;
         const int ncw = (cw + G - 1) / G, nxw = (xw + G - 1) / G;  // words of a core row / of a unit row of this segment
         if (g < WIN) {
-            // ---- H lags with dy = g: A = core word of row u, partner words from row u + g ---------------------------------------
+            // ---- H lags with dy = g: A = core-column word of row u, partner words from row u + g.  Core rows add up in accH (-> CC);
+            // the unit's edge rows [vs - HALF, vs + HALF) and [ve - HALF, ve + HALF) are done the same way but each keeps its own sums
+            // (-> RS).  Band b covers unit rows [b0, b1); the HALF rows above the unit ride with band 0, the HALF below with the last.
             const int dy = g;
-            for (int u = max(b0, cu0); u < min(b1, cu1); u++) {
-                const uint32_t* arow = Yt + (u - (b0 - HALF)) * PITCH + OFFB / 4;
-                const uint32_t* brow = Yt + (u + dy - (b0 - HALF)) * PITCH;
+            const int a0 = band == 0 ? vs - HALF : b0, a1 = (b1 == ve) ? ve + HALF : b1;
+            for (int u = a0; u < a1; u++) {
+                if (u + dy >= ve + HALF) break;  // partner row outside the halo: no shifted rectangle uses it
+                const bool core_row = u >= cu0 && u < cu1;
+                // rows [b0 - HALF, b0) of later bands were handled as rows of the previous band
+                const int trow = u - (b0 - HALF);
+                if (trow < 0 || trow + dy >= (b1 - b0) + 3 * HALF) continue;
+                uint32_t accR[2 * WIN - 1];
+#pragma unroll
+                for (int k = 0; k < 2 * WIN - 1; k++) accR[k] = 0;
+                const uint32_t* arow = Yt + trow * PITCH + OFFB / 4;
+                const uint32_t* brow = Yt + (trow + dy) * PITCH;
                 for (int wc = lane; wc < ncw; wc += 32) {
                     uint32_t a = arow[wc];
-                    const int rem = cw - wc * G;  // pixels of this word inside the core
+                    const int rem = cw - wc * G;  // pixels of this word inside the core columns
                     if (rem < G) a &= (1u << (rem * 8 * S)) - 1u;
                     uint32_t win_w[NW];
 #pragma unroll
@@ -129,7 +148,21 @@ stats_lag_bulk_kernel(const PIX* __restrict__ dgd_base, const PIX* __restrict__ 
                         const int dx = k - (WIN - 1);
                         const int rel = OFFB + dx * S;  // byte offset of the partner inside the window (compile-time after unrolling)
                         const uint32_t b = (rel & 3) ? __funnelshift_r(win_w[rel >> 2], win_w[(rel >> 2) + 1], (rel & 3) * 8) : win_w[rel >> 2];
-                        if (dy > 0 || dx >= 0) accH[k] = P::mac(a, b, accH[k]);
+                        if (dy > 0 || dx >= 0) accR[k] = P::mac(a, b, accR[k]);
+                    }
+                }
+                if (core_row) {
+#pragma unroll
+                    for (int k = 0; k < 2 * WIN - 1; k++) accH[k] += accR[k];
+                } else {  // edge row: slot index of u in the unit's edge-row list
+                    int ei = -1;
+                    for (int i = 0; i < 4 * HALF; i++)
+                        if (lag_edge_line(vs, ve, HALF, i) == u) ei = i;
+#pragma unroll
+                    for (int k = 0; k < 2 * WIN - 1; k++) {
+                        if (!(dy > 0 || k >= WIN - 1)) continue;
+                        const unsigned long long t = wsum(accR[k]);
+                        if (lane == 0 && t && ei >= 0) atomicAdd(&acc[kLagAccStride + (dy * 13 + (k - (WIN - 1)) + 6) * kLagEdge + ei], t);
                     }
                 }
             }
@@ -153,14 +186,27 @@ stats_lag_bulk_kernel(const PIX* __restrict__ dgd_base, const PIX* __restrict__ 
                 }
             }
         } else if (g == WIN) {
-            // ---- plain sums: Y over the core rows of the band ("ones" lag), x over the unit rows -----------------------------------
-            for (int u = max(b0, cu0); u < min(b1, cu1); u++) {
-                const uint32_t* arow = Yt + (u - (b0 - HALF)) * PITCH + OFFB / 4;
+            // ---- plain sums: Y over the core rows ("ones" lag; edge rows -> its RS), x over the unit rows --------------------------------
+            const int a0 = band == 0 ? vs - HALF : b0, a1 = (b1 == ve) ? ve + HALF : b1;
+            for (int u = a0; u < a1; u++) {
+                const int trow = u - (b0 - HALF);
+                if (trow < 0 || trow >= (b1 - b0) + 3 * HALF) continue;
+                const bool core_row = u >= cu0 && u < cu1;
+                uint32_t accR = 0;
+                const uint32_t* arow = Yt + trow * PITCH + OFFB / 4;
                 for (int wc = lane; wc < ncw; wc += 32) {
                     uint32_t a = arow[wc];
                     const int rem = cw - wc * G;
                     if (rem < G) a &= (1u << (rem * 8 * S)) - 1u;
-                    accY = P::mac(a, P::ONES, accY);
+                    accR = P::mac(a, P::ONES, accR);
+                }
+                if (core_row) accY += accR;
+                else {
+                    int ei = -1;
+                    for (int i = 0; i < 4 * HALF; i++)
+                        if (lag_edge_line(vs, ve, HALF, i) == u) ei = i;
+                    const unsigned long long t = wsum(accR);
+                    if (lane == 0 && t && ei >= 0) atomicAdd(&acc[kLagAccStride + kLagOnes * kLagEdge + ei], t);
                 }
             }
             for (int u = b0; u < b1; u++) {
@@ -168,30 +214,27 @@ stats_lag_bulk_kernel(const PIX* __restrict__ dgd_base, const PIX* __restrict__ 
                 for (int wc = lane; wc < nxw; wc += 32) accX = P::mac(arow[wc], P::ONES, accX);
             }
         }
-        // a work unit's 32-bit partial sums cannot overflow (8 rows x 512 columns / 32 lanes of <= 2 x 4095^2); across work units: 64 bit
+        // the work unit's partial sums: warp-reduce, then into the CTA's 64-bit totals
+        if (g < WIN) {
 #pragma unroll
-        for (int k = 0; k < 2 * WIN - 1; k++) totH[k] += accH[k];
+            for (int k = 0; k < 2 * WIN - 1; k++) {
+                if (!(g > 0 || k >= WIN - 1)) continue;
+                const unsigned long long t = wsum(accH[k]);
+                if (lane == 0 && t) atomicAdd(&s_tot[g * 13 + (k - (WIN - 1)) + 6], t);
+            }
 #pragma unroll
-        for (int k = 0; k < WIN; k++) totM[k] += accM[k];
-        totY += accY;
-        totX += accX;
+            for (int k = 0; k < WIN; k++) {
+                const unsigned long long t = wsum(accM[k]);
+                if (lane == 0 && t) atomicAdd(&s_tot[kLagSlots + k * WIN + g], t);  // p = (kc + half) * win + (lr + half)
+            }
+        } else if (g == WIN) {
+            const unsigned long long ty = wsum(accY), tx = wsum(accX);
+            if (lane == 0) { atomicAdd(&s_tot[kLagOnes], ty); atomicAdd(&s_tot[kLagSlots + 49], tx); }
+        }
     }
-    unsigned long long* acc = acc_base + (size_t)blockIdx.y * kLagItemWords;
-    auto flush = [&](unsigned long long t, int slot) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-        if (lane == 0 && t) atomicAdd(&acc[slot], t);
-    };
-    if (g < WIN) {
-#pragma unroll
-        for (int k = 0; k < 2 * WIN - 1; k++)
-            if (g > 0 || k >= WIN - 1) flush(totH[k], g * 13 + (k - (WIN - 1)) + 6);
-#pragma unroll
-        for (int k = 0; k < WIN; k++) flush(totM[k], kLagSlots + k * WIN + g);  // p = (kc + half) * win + (lr + half)
-    } else if (g == WIN) {
-        flush(totY, kLagOnes);
-        flush(totX, kLagSlots + 49);
-    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < kLagAccStride; i += blockDim.x)
+        if (s_tot[i]) atomicAdd(&acc[i], s_tot[i]);
 }
 
 template <typename PIX, int WIN>
@@ -202,44 +245,50 @@ constexpr size_t lag_bulk_smem() {
     return (size_t)((kLagBandRows + 3 * (WIN >> 1)) * PITCH + kLagBandRows * XPITCH) * 4;
 }
 
-// RS(lag, edge row u) = sum over the core columns of P(u, v); CS(lag, edge column v) = sum over the core rows.  grid = (92, items)
+// CS(lag, edge column v) = sum over the core rows of P(u, v): one warp per (edge column, dy), lanes over the rows, all dx of the
+// dy at once (the 2 win - 1 partners of a row are neighbours).  RS is produced by the bulk kernel.  grid = (units), 8 warps
 template <typename PIX>
 __global__ void __launch_bounds__(256)
 stats_lag_edges_kernel(const PIX* __restrict__ dgd_base, const SvtB200StatsItem* __restrict__ items, unsigned long long* __restrict__ acc_base) {
-    const SvtB200StatsItem s = items[blockIdx.y];
-    const int win = s.wiener_win, half = win >> 1, slot = blockIdx.x;
-    const bool ones = slot == kLagOnes;
-    const int dy = ones ? 0 : slot / 13, dx = ones ? 0 : slot % 13 - 6;
-    if (!ones && (dy >= win || dx <= -win || dx >= win || (dy == 0 && dx < 0))) return;
+    const SvtB200StatsItem s = items[blockIdx.x];
+    const int win = s.wiener_win, half = win >> 1;
     const int hs = s.h_start, he = s.h_end, vs = s.v_start, ve = s.v_end;
-    const int cu0 = vs + half, cu1 = ve - half, cv0 = hs + half, cv1 = he - half;
+    const int cu0 = vs + half, cu1 = ve - half;
     const PIX* dgd = dgd_base + s.dgd_off;
-    unsigned long long* out = acc_base + (size_t)blockIdx.y * kLagItemWords + kLagAccStride;
+    unsigned long long* CS = acc_base + (size_t)blockIdx.x * kLagItemWords + kLagAccStride + kLagSlots * kLagEdge;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int line = warp; line < 2 * kLagEdge; line += 8) {
-        const bool is_row = line < kLagEdge;
-        const int i = is_row ? line : line - kLagEdge;
-        unsigned long long t = 0;
-        if (i < 4 * half) {
-            if (is_row) {
-                const int u = lag_edge_line(vs, ve, half, i);
-                if (u != 0x7fffffff && u + dy < ve + half)
-                    for (int v = cv0 + lane; v < cv1; v += 32) {
-                        const unsigned long long a = dgd[(ptrdiff_t)u * s.dgd_stride + v];
-                        t += ones ? a : a * (unsigned long long)dgd[(ptrdiff_t)(u + dy) * s.dgd_stride + v + dx];
-                    }
-            } else {
-                const int v = lag_edge_line(hs, he, half, i);
-                if (v != 0x7fffffff && v + dx >= hs - half && v + dx < he + half)
-                    for (int u = cu0 + lane; u < cu1; u += 32) {
-                        const unsigned long long a = dgd[(ptrdiff_t)u * s.dgd_stride + v];
-                        t += ones ? a : a * (unsigned long long)dgd[(ptrdiff_t)(u + dy) * s.dgd_stride + v + dx];
-                    }
+    for (int job = warp; job < 4 * half * (win + 1); job += 8) {
+        const int i = job / (win + 1), dy = job - i * (win + 1);  // dy == win: the "ones" lag
+        const int v = lag_edge_line(hs, he, half, i);
+        if (v == 0x7fffffff) continue;
+        if (dy == win) {
+            unsigned long long t = 0;
+            for (int u = cu0 + lane; u < cu1; u += 32) t += dgd[(ptrdiff_t)u * s.dgd_stride + v];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+            if (lane == 0) CS[kLagOnes * kLagEdge + i] = t;
+            continue;
+        }
+        unsigned long long t[13];
+#pragma unroll
+        for (int k = 0; k < 13; k++) t[k] = 0;
+        for (int u = cu0 + lane; u < cu1; u += 32) {
+            const unsigned long long a = dgd[(ptrdiff_t)u * s.dgd_stride + v];
+            const PIX* prow = dgd + (ptrdiff_t)(u + dy) * s.dgd_stride + v;
+#pragma unroll
+            for (int k = 0; k < 13; k++) {
+                const int dx = k - 6;
+                if (dx > -win && dx < win && v + dx >= hs - half && v + dx < he + half) t[k] += a * (unsigned long long)prow[dx];
             }
         }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-        if (lane == 0) out[(size_t)(is_row ? 0 : kLagSlots * kLagEdge) + slot * kLagEdge + i] = t;
+        for (int k = 0; k < 13; k++) {
+            unsigned long long x = t[k];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+            const int dx = k - 6;
+            if (lane == 0 && dx > -win && dx < win && (dy > 0 || dx >= 0)) CS[(dy * 13 + k) * kLagEdge + i] = x;
+        }
     }
 }
 
@@ -280,14 +329,18 @@ stats_lag_finalize_kernel(const PIX* __restrict__ dgd_base, const SvtB200StatsIt
     const int win = s.wiener_win, half = win >> 1, win2 = win * win;
     const int npairs = win2 * (win2 + 1) / 2;
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= npairs + win2) return;
     const unsigned long long* acc = acc_base + (size_t)it * kLagItemWords;
     const PIX* dgd = dgd_base + s.dgd_off;
+    __shared__ long long s_sy[49];  // plain pixel sums of the win^2 shifted rectangles (every H and M entry needs two / one of them)
+    if (threadIdx.x < win2) s_sy[threadIdx.x] = lag_rect_sum<PIX>(dgd, s, acc, kLagOnes, true, 0, 0, threadIdx.x % win - half, threadIdx.x / win - half);
+    __syncthreads();
+    if (e >= npairs + win2) return;
     const long long N = (long long)(s.h_end - s.h_start) * (s.v_end - s.v_start);
     const long long avg = (long long)(tot[it] / (unsigned long long)N);  // find_average
     if (e >= npairs) {  // M[p] = sum x y_p - a sum x - a sum Y_p + N a^2
         const int p = e - npairs, kc = p / win - half, lr = p % win - half;
-        const long long sy = lag_rect_sum<PIX>(dgd, s, acc, kLagOnes, true, 0, 0, lr, kc);
+        const long long sy = s_sy[p];
+        (void)kc; (void)lr;
         const long long m = (long long)acc[kLagSlots + p] - avg * (long long)acc[kLagSlots + 49] - avg * sy + N * avg * avg;
         M_out[(size_t)it * 49 + p] = m / divider;
         return;
@@ -300,8 +353,7 @@ stats_lag_finalize_kernel(const PIX* __restrict__ dgd_base, const SvtB200StatsIt
     int dy = lq - lp, dx = kq - kp, ar = lp, ac = kp;
     if (dy < 0 || (dy == 0 && dx < 0)) { dy = -dy; dx = -dx; ar = lq; ac = kq; }
     const long long syy = lag_rect_sum<PIX>(dgd, s, acc, dy * 13 + dx + 6, false, dy, dx, ar, ac);
-    const long long sp = lag_rect_sum<PIX>(dgd, s, acc, kLagOnes, true, 0, 0, lp, kp);
-    const long long sq = p == q ? sp : lag_rect_sum<PIX>(dgd, s, acc, kLagOnes, true, 0, 0, lq, kq);
+    const long long sp = s_sy[p], sq = s_sy[q];
     const long long hv = (syy - avg * (sp + sq) + N * avg * avg) / divider;
     H_out[(size_t)it * 2401 + p * win2 + q] = hv;
     H_out[(size_t)it * 2401 + q * win2 + p] = hv;
