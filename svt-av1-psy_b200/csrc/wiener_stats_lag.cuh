@@ -99,17 +99,20 @@ stats_lag_bulk_kernel(const PIX* __restrict__ dgd_base, const PIX* __restrict__ 
             // only the columns this segment can touch (a 128-wide chroma unit does not pay for a 512-wide tile)
             int spx = P::OFFP + xw + 2 * WIN + 2 * G;
             spx = spx < PPR ? (spx + G - 1) / G * G : PPR;
-            for (int i = threadIdx.x; i < trows * spx; i += blockDim.x) {
-                const int tr = i / spx, tc = i - tr * spx;
-                const int u = b0 - HALF + tr, v = cv0 + c0 - P::OFFP + tc;
-                const bool in = u >= vs - HALF && u < ve + HALF && v >= hs - HALF && v < he + HALF;
-                yb[tr * PPR + tc] = in ? dgd[(ptrdiff_t)u * s.dgd_stride + v] : (PIX)0;
+            for (int tr = g; tr < trows; tr += 8) {  // a warp per tile row: no index division, coalesced runs
+                const int u = b0 - HALF + tr;
+                const bool rin = u >= vs - HALF && u < ve + HALF;
+                const PIX* grow = dgd + (ptrdiff_t)u * s.dgd_stride + (cv0 + c0 - P::OFFP);
+                PIX* trow_p = yb + tr * PPR;
+                const int vlo = hs - HALF - (cv0 + c0 - P::OFFP), vhi = he + HALF - (cv0 + c0 - P::OFFP);  // valid tile columns
+                for (int tc = lane; tc < spx; tc += 32) trow_p[tc] = (rin && tc >= vlo && tc < vhi) ? grow[tc] : (PIX)0;
             }
             PIX* xb = reinterpret_cast<PIX*>(Xt);
             constexpr int XPR = XPITCH * 4 / S;
-            for (int i = threadIdx.x; i < (b1 - b0) * XPR; i += blockDim.x) {
-                const int tr = i / XPR, tc = i - tr * XPR;
-                xb[i] = tc < xw ? src[(ptrdiff_t)(b0 + tr) * s.src_stride + hs + c0 + tc] : (PIX)0;
+            const int xsp = min(XPR, (xw + G - 1) / G * G + G);
+            for (int tr = g; tr < b1 - b0; tr += 8) {
+                const PIX* grow = src + (ptrdiff_t)(b0 + tr) * s.src_stride + hs + c0;
+                for (int tc = lane; tc < xsp; tc += 32) xb[tr * XPR + tc] = tc < xw ? grow[tc] : (PIX)0;
             }
         }
         __syncthreads();
