@@ -367,7 +367,7 @@ def main():
     s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
 
     host_enqueue = [0.0, 0]  # seconds the host spent enqueueing e2e frames, frames
-    D2H_LAG = 2  # the variable-size part of a frame's results is requested this many frames later (its size has arrived by then)
+    D2H_LAG = 5  # the variable-size part of a frame's results is requested this many frames later (its size has arrived by then; < N_FRAME_SETS)
     d2h_level_bytes = [0, 0]  # bytes, frames
 
     def run_e2e(n):

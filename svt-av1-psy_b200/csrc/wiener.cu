@@ -494,10 +494,16 @@ static void launch_lag_bulk(const PIX* d_dgd, const PIX* d_src, const SvtB200Sta
     B200_LAUNCH_CHECK();
 }
 
-// Wiener statistics of a batch of units by lag sums (wiener_stats_lag.cuh)
+template <typename PIX>
+static void launch_stats_old(const PIX* d_dgd, const PIX* d_src, const SvtB200StatsItem* d_items, int n, int bd, long long* d_M,
+                             long long* d_H, long long* d_acc, unsigned long long* d_tot, cudaStream_t st);
+
+// Wiener statistics of a batch of units: 8-bit pictures on the tensor cores (stats_mma_kernel), 10 / 12 bit by lag sums
+// (wiener_stats_lag.cuh) -- both exact
 template <typename PIX>
 static void launch_stats(const PIX* d_dgd, const PIX* d_src, const SvtB200StatsItem* d_items, int n, int bd, long long* d_M,
                          long long* d_H, long long* d_acc, unsigned long long* d_tot, cudaStream_t st) {
+    if (sizeof(PIX) == 1) return launch_stats_old<PIX>(d_dgd, d_src, d_items, n, bd, d_M, d_H, d_acc, d_tot, st);
     const int divider = bd == 12 ? 16 : (bd == 10 ? 4 : 1);
     int cpi = (ctx().sm_count * 8) / (n > 0 ? n : 1);  // CTAs per unit: ~8 resident CTAs per SM over the batch
     if (cpi < 1) cpi = 1;
@@ -511,7 +517,7 @@ static void launch_stats(const PIX* d_dgd, const PIX* d_src, const SvtB200StatsI
     launch_lag_bulk<PIX, 7>(d_dgd, d_src, d_items, n, cpi, acc, st);
     launch_lag_bulk<PIX, 5>(d_dgd, d_src, d_items, n, cpi, acc, st);
     launch_lag_bulk<PIX, 3>(d_dgd, d_src, d_items, n, cpi, acc, st);
-    stats_lag_edges_kernel<PIX><<<n, 256, 0, st>>>(d_dgd, d_items, acc);
+    stats_lag_edges_kernel<PIX><<<dim3(kLagEdge, n), 256, 0, st>>>(d_dgd, d_items, acc);
     B200_LAUNCH_CHECK();
     stats_lag_finalize_kernel<PIX><<<dim3((49 * 50 / 2 + 49 + 127) / 128, n), 128, 0, st>>>(d_dgd, d_items, acc, d_tot, divider, d_M, d_H);
     B200_LAUNCH_CHECK();

@@ -11,8 +11,11 @@
 //                       + sum of the edge-column sums CS(lag, v) ...   + the <= (2 half)^2 corner products,
 // with RAW pixels (no mean removed: products are non-negative, 8-bit pictures take four multiply-accumulates per DP4A) and
 // the mean folded back in at the end:  sum (y-a)(z-a) = sum yz - a (sum y + sum z) + N a^2  (a = the integer average).
-// That is (2 win - 1) win - (win - 1) = 85 lags + 49 cross lags for M per pixel instead of 1274 -- an order of magnitude
-// fewer operations than the tensor-core formulation needs, identical results, same code for 8 / 10 / 12 bit.
+// That is (2 win - 1) win - (win - 1) = 85 lags + 49 cross lags for M per pixel instead of 1274, identical results, same code for
+// 8 / 10 / 12 bit.  Measured (1080p, ncu): the 8-bit form still costs more instructions than the exact-f16 tensor-core Gram
+// matrix (57 M vs 31 M warp instructions per picture -- the partner extraction dominates), so 8-bit pictures stay on
+// stats_mma_kernel; for 10 / 12 bit, where no exact tensor-core form exists, it replaces the 49-MAC-per-pixel integer kernel
+// and halves the call.
 //
 //   stats_lag_bulk_kernel   CC of every lag, sum x Y(shift) for M, plain pixel sums: one CTA per (8-row band, unit); warp g owns
 //                           the lags with dy = g and the M shifts with lr = g - half; partner words come from a 5 / 7 word
@@ -249,18 +252,19 @@ constexpr size_t lag_bulk_smem() {
 }
 
 // CS(lag, edge column v) = sum over the core rows of P(u, v): one warp per (edge column, dy), lanes over the rows, all dx of the
-// dy at once (the 2 win - 1 partners of a row are neighbours).  RS is produced by the bulk kernel.  grid = (units), 8 warps
+// dy at once (the 2 win - 1 partners of a row are neighbours).  RS is produced by the bulk kernel.  grid = (12 edge columns, units), 8 warps
 template <typename PIX>
 __global__ void __launch_bounds__(256)
 stats_lag_edges_kernel(const PIX* __restrict__ dgd_base, const SvtB200StatsItem* __restrict__ items, unsigned long long* __restrict__ acc_base) {
-    const SvtB200StatsItem s = items[blockIdx.x];
+    const SvtB200StatsItem s = items[blockIdx.y];
     const int win = s.wiener_win, half = win >> 1;
     const int hs = s.h_start, he = s.h_end, vs = s.v_start, ve = s.v_end;
     const int cu0 = vs + half, cu1 = ve - half;
     const PIX* dgd = dgd_base + s.dgd_off;
-    unsigned long long* CS = acc_base + (size_t)blockIdx.x * kLagItemWords + kLagAccStride + kLagSlots * kLagEdge;
+    unsigned long long* CS = acc_base + (size_t)blockIdx.y * kLagItemWords + kLagAccStride + kLagSlots * kLagEdge;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int job = warp; job < 4 * half * (win + 1); job += 8) {
+    if ((int)blockIdx.x >= 4 * half) return;  // grid.x = 12 edge columns of the 7x7 geometry
+    for (int job = blockIdx.x * (win + 1) + warp; job < (blockIdx.x + 1) * (win + 1); job += 8) {
         const int i = job / (win + 1), dy = job - i * (win + 1);  // dy == win: the "ones" lag
         const int v = lag_edge_line(hs, he, half, i);
         if (v == 0x7fffffff) continue;
