@@ -56,6 +56,11 @@ SVT_B200_API void               svt_b200_shutdown(void);
 SVT_B200_API int                svt_b200_sm_count(void);
 SVT_B200_API unsigned long long svt_b200_launch_count(void); /* kernels launched so far by this library */
 SVT_B200_API const char*        svt_b200_version(void);
+/* Asynchronous copies on a caller stream -- the host-buffer half of a T2 call (kind 0: pinned host -> device, 1: device ->
+ * pinned host, 2: device -> device).  The caller keeps the buffers alive until the stream has passed the copy. */
+SVT_B200_API int svt_b200_copy_async(void* dst, const void* src, size_t bytes, int kind, void* stream);
+SVT_B200_API int svt_b200_copy2d_async(void* dst, size_t dst_pitch, const void* src, size_t src_pitch, size_t width_bytes, size_t rows,
+                                       int kind, void* stream);
 
 /* ------------------------------------------------------------------------------------------ */
 /* K1/K3  SAD search + single SADs  (reference: Source/Lib/C_DEFAULT/compute_sad_c.c)           */

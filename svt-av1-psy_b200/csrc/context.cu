@@ -139,6 +139,21 @@ extern "C" void svt_b200_shutdown(void) {
     c.ready = false;
 }
 
+// plain asynchronous copies on a caller stream (the host-buffer side of the T2 calls: pinned host <-> device, device <-> device)
+extern "C" int svt_b200_copy_async(void* dst, const void* src, size_t bytes, int kind, void* stream) {
+    if (!dst || !src || kind < 0 || kind > 2) return SVT_B200_ERR_BAD_ARG;
+    const cudaMemcpyKind k = kind == 0 ? cudaMemcpyHostToDevice : (kind == 1 ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice);
+    if (bytes) B200_CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, k, (cudaStream_t)stream));
+    return SVT_B200_OK;
+}
+extern "C" int svt_b200_copy2d_async(void* dst, size_t dst_pitch, const void* src, size_t src_pitch, size_t width_bytes, size_t rows, int kind,
+                                     void* stream) {
+    if (!dst || !src || kind < 0 || kind > 2) return SVT_B200_ERR_BAD_ARG;
+    const cudaMemcpyKind k = kind == 0 ? cudaMemcpyHostToDevice : (kind == 1 ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice);
+    if (width_bytes && rows) B200_CUDA_CHECK(cudaMemcpy2DAsync(dst, dst_pitch, src, src_pitch, width_bytes, rows, k, (cudaStream_t)stream));
+    return SVT_B200_OK;
+}
+
 extern "C" int svt_b200_sm_count(void) { return ctx().ready ? ctx().sm_count : 0; }
 extern "C" unsigned long long svt_b200_launch_count(void) { return ctx().launches; }
 extern "C" const char* svt_b200_version(void) { return "svt_b200 0.1 (sm_100a)"; }

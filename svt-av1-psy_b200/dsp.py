@@ -47,6 +47,10 @@ lib.svt_b200_shutdown.restype = None
 lib.svt_b200_sm_count.restype = ct.c_int
 lib.svt_b200_launch_count.restype = ct.c_ulonglong
 lib.svt_b200_version.restype = ct.c_char_p
+lib.svt_b200_copy_async.argtypes = [vp, vp, ct.c_size_t, ct.c_int, vp]
+lib.svt_b200_copy_async.restype = ct.c_int
+lib.svt_b200_copy2d_async.argtypes = [vp, ct.c_size_t, vp, ct.c_size_t, ct.c_size_t, ct.c_size_t, ct.c_int, vp]
+lib.svt_b200_copy2d_async.restype = ct.c_int
 
 lib.svt_b200_sad_loop_kernel.argtypes = [vp, ct.c_uint32, vp, ct.c_uint32, ct.c_uint32, ct.c_uint32, c_u64p, c_i16p,
                                          c_i16p, ct.c_uint32, ct.c_uint8, ct.c_int16, ct.c_int16]

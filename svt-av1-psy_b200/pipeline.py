@@ -126,6 +126,7 @@ class FramePipeline:
         self.level_offsets = self._out.view("level_offsets")
         self.h_out = {k: self._out.view(k, host=True) for k in self._out.slots}
         self.h_levels = T.empty_like(self.levels, device="cpu").pin_memory()
+        self._h_offs = self.h_out["level_offsets"].numpy()  # numpy view of the pinned buffer: cheap scalar reads on the host
         self._res_planes = None
         self.load_inputs()
         T.cuda.synchronize()
@@ -164,30 +165,28 @@ class FramePipeline:
         return out
 
     def load_inputs(self, stream=None):
-        """host -> device copy of one frame's inputs (source picture, residual, prediction)"""
-        T = self.torch
-        self._in.dev.copy_(self._in.host, non_blocking=True)  # source picture + prediction in one transfer
-        W, H, pad = self.wl.width, self.wl.height, self._full_pad
-        # the full-resolution luma of the ME pyramid is the padded (8-bit) source picture
-        if self.psz == 1:
-            self.cur_planes[2][pad:pad + H, pad:pad + W].copy_(self.cur_flat[:W * H].view(H, W))
-        else:
-            self.cur_planes[2][pad:pad + H, pad:pad + W].copy_(self.h_luma8, non_blocking=True)
-        s = T.cuda.current_stream().cuda_stream
-        assert lib.svt_b200_extend_plane_dev(self.cur_planes[2].data_ptr(), self.cur_planes[2].stride(0), W, H, pad, pad, s) == 0
+        """host -> device copy of one frame's inputs (source picture + prediction: one transfer; a 10-bit picture also brings the
+        8-bit luma the picture-input stage made for open-loop ME) on `stream` (a raw CUDA stream handle; default: torch's current)"""
+        s = self.torch.cuda.current_stream().cuda_stream if stream is None else stream
+        lib.svt_b200_copy_async(self._in.dev.data_ptr(), self._in.host.data_ptr(), self._in.nbytes, 0, s)
+        if self.psz != 1:
+            W, H, pad = self.wl.width, self.wl.height, self._full_pad
+            p2 = self.cur_planes[2]
+            lib.svt_b200_copy2d_async(p2.data_ptr() + pad * p2.stride(0) + pad, p2.stride(0), self.h_luma8.data_ptr(), W, W, H, 0, s)
 
-    def read_outputs(self):
+    def read_outputs(self, stream=None):
         """device -> host, part 1: everything of fixed size in one transfer (includes the level offsets, whose last entries say how
         many levels follow)"""
-        self._out.host.copy_(self._out.dev, non_blocking=True)
+        s = self.torch.cuda.current_stream().cuda_stream if stream is None else stream
+        lib.svt_b200_copy_async(self._out.host.data_ptr(), self._out.dev.data_ptr(), self._out.nbytes, 1, s)
 
-    def read_levels(self):
+    def read_levels(self, stream=None):
         """part 2, once part 1 has arrived: exactly sum(eob) levels.  Returns the bytes copied."""
-        total = int(self.h_out["level_offsets"][self.n_tx])
-        assert int(self.h_out["level_offsets"][self.n_tx + 1]) == 0, "a quantised level did not fit the packed format"
+        s = self.torch.cuda.current_stream().cuda_stream if stream is None else stream
+        total = int(self._h_offs[self.n_tx])
+        assert int(self._h_offs[self.n_tx + 1]) == 0, "a quantised level did not fit the packed format"
         total = min(total, self.levels.numel())
-        if total:
-            self.h_levels[:total].copy_(self.levels[:total], non_blocking=True)
+        lib.svt_b200_copy_async(self.h_levels.data_ptr(), self.levels.data_ptr(), total * self.level_bytes, 1, s)
         return total * self.level_bytes
 
     @property
@@ -200,6 +199,12 @@ class FramePipeline:
 
     # -- the calls of one frame, in path order (each is one T2 entry point of include/svt_b200.h) -----------
     def call_me_pyramid(self, s):
+        """the padded full-resolution luma of the ME pyramid (8-bit pictures: the source luma itself) + the two decimated levels"""
+        W, H, pad = self.wl.width, self.wl.height, self._full_pad
+        p2 = self.cur_planes[2]
+        if self.psz == 1:
+            lib.svt_b200_copy2d_async(p2.data_ptr() + pad * p2.stride(0) + pad, p2.stride(0), self.cur_flat.data_ptr(), W, W, H, 2, s)
+        assert lib.svt_b200_extend_plane_dev(p2.data_ptr(), p2.stride(0), W, H, pad, pad, s) == 0
         assert lib.svt_b200_build_hme_pyramid_dev(ct.byref(self.cur_desc), s) == 0
 
     def call_me_search(self, s):
