@@ -346,6 +346,16 @@ SVT_B200_API void svt_b200_aom_hadamard_8x8(const int16_t* src_diff, ptrdiff_t s
 SVT_B200_API void svt_b200_aom_hadamard_16x16(const int16_t* src_diff, ptrdiff_t src_stride, int32_t* coeff);
 SVT_B200_API void svt_b200_aom_hadamard_32x32(const int16_t* src_diff, ptrdiff_t src_stride, int32_t* coeff);
 SVT_B200_API int  svt_b200_aom_satd(const int32_t* coeff, int length);
+/* T1: hadamard_path (aom_dsp_rtcd.h:582; C: enc_mode_config.c:2147-2212): SATD cost of a prediction block, transform block by
+ * transform block (8-bit input / prediction).  SvtB200Buf2D has the layout of the reference's Buf2D (definitions.h:243-249);
+ * `bsize` is the reference's 1-byte BlockSize.  Like the reference's loop, the call leaves the last transform block's residual
+ * (int16, residual.stride) in residual.buf and its coefficients in coeff.buf. */
+typedef struct SvtB200Buf2D { uint8_t* buf; uint8_t* buf0; int width; int height; int stride; } SvtB200Buf2D;
+SVT_B200_API uint32_t svt_b200_hadamard_path(SvtB200Buf2D residual, SvtB200Buf2D coeff, SvtB200Buf2D input, SvtB200Buf2D pred, uint8_t bsize);
+/* T1: svt_av1_fwht4x4 (aom_dsp_rtcd.h:208; C: transforms.c:3099): the Walsh-Hadamard transform of lossless 4x4 blocks */
+SVT_B200_API void svt_b200_av1_fwht4x4(int16_t* input, int32_t* output, uint32_t stride);
+/* T1: svt_av1_compute_cul_level (aom_dsp_rtcd.h:904; C: full_loop.c:1449) */
+SVT_B200_API uint8_t svt_b200_av1_compute_cul_level(const int16_t* const scan, const int32_t* const quant_coeff, uint16_t* eob);
 
 typedef struct SvtB200HadamardItem {
     uint64_t src_off;    /* int16 residual elements */

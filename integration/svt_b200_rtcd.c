@@ -95,6 +95,14 @@ static uint64_t b200_cdef_dist_8bit(const uint8_t* dst8, int32_t dstride, const 
                                            subsampling_factor);
 }
 
+static uint32_t b200_hadamard_path(Buf2D residual, Buf2D coeff, Buf2D input, Buf2D pred, BlockSize bsize) {
+    SvtB200Buf2D r = {residual.buf, residual.buf0, residual.width, residual.height, residual.stride};
+    SvtB200Buf2D c = {coeff.buf, coeff.buf0, coeff.width, coeff.height, coeff.stride};
+    SvtB200Buf2D i = {input.buf, input.buf0, input.width, input.height, input.stride};
+    SvtB200Buf2D p = {pred.buf, pred.buf0, pred.width, pred.height, pred.stride};
+    return svt_b200_hadamard_path(r, c, i, p, (uint8_t)bsize);
+}
+
 static int g_count = 0;
 static unsigned g_groups = ~0u, g_cur = 0; /* SVT_B200_RTCD_GROUPS (debug): bit mask of the kernel groups to install, default all */
 #define GROUP(bit) g_cur = (bit)
@@ -142,6 +150,7 @@ int svt_b200_install_rtcd(int device) {
     BIND(svt_aom_hadamard_16x16, svt_b200_aom_hadamard_16x16);
     BIND(svt_aom_hadamard_32x32, svt_b200_aom_hadamard_32x32);
     BIND(svt_aom_satd, svt_b200_aom_satd);
+    BIND(hadamard_path, b200_hadamard_path);
     GROUP(4u);
     /* K5 / K6: forward (full, N2, N4) and inverse transforms, 19 sizes */
     BIND_FWD(4x4); BIND_FWD(8x8); BIND_FWD(16x16); BIND_FWD(32x32); BIND_FWD(64x64); BIND_FWD(4x8); BIND_FWD(8x4); BIND_FWD(8x16);
@@ -150,6 +159,8 @@ int svt_b200_install_rtcd(int device) {
     BIND_HANDLE(16x64); BIND_HANDLE(32x64); BIND_HANDLE(64x16); BIND_HANDLE(64x32); BIND_HANDLE(64x64);
     GROUP(8u);
     BIND(svt_av1_inv_txfm_add, b200_av1_inv_txfm_add);
+    GROUP(4u);
+    BIND(svt_av1_fwht4x4, svt_b200_av1_fwht4x4);
     GROUP(16u);
     /* K7: quantizers */
     BIND(svt_aom_quantize_b, svt_b200_aom_quantize_b);
@@ -162,6 +173,7 @@ int svt_b200_install_rtcd(int device) {
     BIND(svt_av1_quantize_fp_qm, svt_b200_av1_quantize_fp_qm);
     BIND(svt_av1_highbd_quantize_fp, svt_b200_av1_highbd_quantize_fp);
     BIND(svt_av1_highbd_quantize_fp_qm, svt_b200_av1_highbd_quantize_fp_qm);
+    BIND(svt_av1_compute_cul_level, svt_b200_av1_compute_cul_level);
     GROUP(32u);
     /* K8: CDEF */
     BIND(svt_aom_cdef_find_dir, svt_b200_aom_cdef_find_dir);

@@ -166,9 +166,155 @@ static void hadamard_t1(const int16_t* src_diff, ptrdiff_t src_stride, int32_t* 
     memcpy(coeff, l->h<int32_t>(o_c), (size_t)n * n * 4);
 }
 
+// ---- hadamard_path (enc_mode_config.c:2147-2212): residual -> Hadamard -> SATD of every transform block of a prediction block ----
+// one CTA per transform block; the last block also leaves its residual / coefficients behind, as the reference's loop does
+struct HadPathArgs {
+    const uint8_t* input; const uint8_t* pred; int in_stride, pred_stride, n /*tx size 4..32*/, blocks_per_row, n_blocks;
+};
+__global__ void __launch_bounds__(128)
+hadamard_path_kernel(const __grid_constant__ HadPathArgs a, int32_t* __restrict__ satd_out, int16_t* __restrict__ last_res, int32_t* __restrict__ last_coeff) {
+    __shared__ int16_t s_in[1024], s_t1[1024], s_t2[1024];
+    __shared__ int32_t s_out[1024];
+    __shared__ int32_t s_sum;
+    const int blk = blockIdx.x, n = a.n, brow = blk / a.blocks_per_row, bcol = blk - brow * a.blocks_per_row;
+    if (threadIdx.x == 0) s_sum = 0;
+    const uint8_t* ip = a.input + (size_t)(brow * n) * a.in_stride + bcol * n;
+    const uint8_t* pp = a.pred + (size_t)(brow * n) * a.pred_stride + bcol * n;
+    for (int i = threadIdx.x; i < n * n; i += blockDim.x) {
+        const int r = i / n, c = i - r * n;
+        s_in[i] = (int16_t)((int)ip[(size_t)r * a.in_stride + c] - (int)pp[(size_t)r * a.pred_stride + c]);
+    }
+    __syncthreads();
+    hadamard_block(s_in, n, s_t1, s_t2, s_out);
+    int32_t acc = 0;
+    for (int i = threadIdx.x; i < n * n; i += blockDim.x) {
+        const int32_t v = s_out[i];
+        acc += v < 0 ? -v : v;
+        if (blk == a.n_blocks - 1) { last_coeff[i] = v; last_res[i] = s_in[i]; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(&s_sum, acc);
+    __syncthreads();
+    if (threadIdx.x == 0) satd_out[blk] = s_sum;
+}
+
+// svt_av1_fwht4x4_c (transforms.c:3099-3150): the reversible Walsh-Hadamard of lossless blocks
+__global__ void fwht4x4_kernel(const int16_t* __restrict__ in /*4x4 packed*/, int32_t* __restrict__ out) {
+    __shared__ long long t[16];
+    const int i = threadIdx.x;
+    if (i < 4) {
+        long long a1 = in[0 * 4 + i], b1 = in[1 * 4 + i], c1 = in[2 * 4 + i], d1 = in[3 * 4 + i];
+        a1 += b1; d1 = d1 - c1;
+        const long long e1 = (a1 - d1) >> 1;
+        b1 = e1 - b1; c1 = e1 - c1; a1 -= c1; d1 += b1;
+        t[4 * i + 0] = a1; t[4 * i + 1] = c1; t[4 * i + 2] = d1; t[4 * i + 3] = b1;
+    }
+    __syncthreads();
+    if (i < 4) {
+        long long a1 = (int32_t)t[4 * 0 + i], b1 = (int32_t)t[4 * 1 + i], c1 = (int32_t)t[4 * 2 + i], d1 = (int32_t)t[4 * 3 + i];
+        a1 += b1; d1 -= c1;
+        const long long e1 = (a1 - d1) >> 1;
+        b1 = e1 - b1; c1 = e1 - c1; a1 -= c1; d1 += b1;
+        out[4 * 0 + i] = (int32_t)(a1 * 4); out[4 * 1 + i] = (int32_t)(c1 * 4); out[4 * 2 + i] = (int32_t)(d1 * 4); out[4 * 3 + i] = (int32_t)(b1 * 4);
+    }
+}
+
+// svt_av1_compute_cul_level_c (full_loop.c:1449-1465): min(63, sum of |level| over the first eob scan positions), DC sign in bits 6-7
+__global__ void cul_level_kernel(const int16_t* __restrict__ scan, const int32_t* __restrict__ q, int eob, int32_t* __restrict__ out) {
+    __shared__ unsigned int s;
+    if (threadIdx.x == 0) s = 0;
+    __syncthreads();
+    unsigned int acc = 0;
+    for (int c = threadIdx.x; c < eob; c += blockDim.x) {
+        const int32_t v = q[scan[c]];
+        const unsigned int l = (unsigned int)(v < 0 ? -(long long)v : v);
+        acc += l > 63u ? 63u : l;  // a single level >= 63 already saturates the result: clamping keeps the sum from wrapping
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(&s, acc);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int32_t cul = (int32_t)(s < 63u ? s : 63u);
+        const int32_t dc = q[0];
+        if (dc < 0) cul |= 1 << 6;
+        else if (dc > 0) cul += 2 << 6;
+        *out = cul;
+    }
+}
+
 }  // namespace b200
 
 using namespace b200;
+
+// T1: hadamard_path (aom_dsp_rtcd.h:582).  Buf2D = {uint8_t* buf; uint8_t* buf0; int width, height, stride} (definitions.h:243).
+extern "C" uint32_t svt_b200_hadamard_path(SvtB200Buf2D residual, SvtB200Buf2D coeff, SvtB200Buf2D input, SvtB200Buf2D pred, uint8_t bsize) {
+    static const uint8_t wide[22] = {4, 4, 8, 8, 8, 16, 16, 16, 32, 32, 32, 64, 64, 64, 128, 128, 4, 16, 8, 32, 16, 64};           // block_size_wide
+    static const uint8_t maxtx[22] = {4, 4, 4, 8, 8, 8, 16, 16, 16, 32, 32, 32, 64, 64, 64, 64, 4, 4, 8, 8, 16, 16};                // max_txsize_lookup, in pixels
+    require_ready();
+    if (bsize >= 22) { fprintf(stderr, "[svt_b200] FATAL: hadamard_path: bad block size %d\n", bsize); abort(); }
+    const int n = maxtx[bsize] > 32 ? 32 : maxtx[bsize];  // AOMMIN(TX_32X32, max_txsize_lookup[bsize])
+    const int side = wide[bsize];                          // the reference walks block_size_wide in BOTH directions
+    const int per_row = side / n, nblk = per_row * per_row;
+    LaneGuard l;
+    size_t o_in = l->alloc((size_t)side * side), o_pr = l->alloc((size_t)side * side);
+    size_t in_end = l->used;
+    size_t o_satd = l->alloc((size_t)nblk * 4), o_res = l->alloc((size_t)n * n * 2), o_co = l->alloc((size_t)n * n * 4);
+    for (int r = 0; r < side; r++) {
+        memcpy(l->h<uint8_t>(o_in) + (size_t)r * side, input.buf + (size_t)r * input.stride, side);
+        memcpy(l->h<uint8_t>(o_pr) + (size_t)r * side, pred.buf + (size_t)r * pred.stride, side);
+    }
+    l->h2d(0, in_end);
+    HadPathArgs a = {l->d<uint8_t>(o_in), l->d<uint8_t>(o_pr), side, side, n, per_row, nblk};
+    hadamard_path_kernel<<<nblk, 128, 0, l->stream>>>(a, l->d<int32_t>(o_satd), l->d<int16_t>(o_res), l->d<int32_t>(o_co));
+    B200_LAUNCH_CHECK();
+    l->d2h(o_satd, (o_co + (size_t)n * n * 4) - o_satd);
+    l->sync();
+    uint32_t cost = 0;
+    for (int i = 0; i < nblk; i++) cost += (uint32_t)l->h<int32_t>(o_satd)[i];
+    // the loop of the reference leaves the LAST block's residual (at its stride) and coefficients in the caller's buffers
+    int16_t* rb = reinterpret_cast<int16_t*>(residual.buf);
+    for (int r = 0; r < n; r++) memcpy(rb + (size_t)r * residual.stride, l->h<int16_t>(o_res) + (size_t)r * n, (size_t)n * 2);
+    memcpy(coeff.buf, l->h<int32_t>(o_co), (size_t)n * n * 4);
+    return cost;
+}
+
+// T1: svt_av1_fwht4x4 (aom_dsp_rtcd.h:208)
+extern "C" void svt_b200_av1_fwht4x4(int16_t* input, int32_t* output, uint32_t stride) {
+    require_ready();
+    LaneGuard l;
+    size_t o_in = l->alloc(32);
+    size_t in_end = l->used;
+    size_t o_out = l->alloc(64);
+    for (int r = 0; r < 4; r++) memcpy(l->h<int16_t>(o_in) + 4 * r, input + (size_t)r * stride, 8);
+    l->h2d(0, in_end);
+    fwht4x4_kernel<<<1, 32, 0, l->stream>>>(l->d<int16_t>(o_in), l->d<int32_t>(o_out));
+    B200_LAUNCH_CHECK();
+    l->d2h(o_out, 64);
+    l->sync();
+    memcpy(output, l->h<int32_t>(o_out), 64);
+}
+
+// T1: svt_av1_compute_cul_level (aom_dsp_rtcd.h:904)
+extern "C" uint8_t svt_b200_av1_compute_cul_level(const int16_t* const scan, const int32_t* const quant_coeff, uint16_t* eob) {
+    require_ready();
+    const int n = *eob;
+    int maxpos = 0;
+    for (int c = 0; c < n; c++) maxpos = scan[c] > maxpos ? scan[c] : maxpos;
+    LaneGuard l;
+    size_t o_sc = l->alloc((size_t)(n > 0 ? n : 1) * 2), o_q = l->alloc((size_t)(maxpos + 1) * 4);
+    size_t in_end = l->used;
+    size_t o_out = l->alloc(16);
+    if (n) memcpy(l->h<int16_t>(o_sc), scan, (size_t)n * 2);
+    memcpy(l->h<int32_t>(o_q), quant_coeff, (size_t)(maxpos + 1) * 4);
+    l->h2d(0, in_end);
+    cul_level_kernel<<<1, 128, 0, l->stream>>>(l->d<int16_t>(o_sc), l->d<int32_t>(o_q), n, l->d<int32_t>(o_out));
+    B200_LAUNCH_CHECK();
+    l->d2h(o_out, 4);
+    l->sync();
+    return (uint8_t)*l->h<int32_t>(o_out);
+}
 
 extern "C" void svt_b200_aom_hadamard_4x4(const int16_t* src_diff, ptrdiff_t src_stride, int32_t* coeff) { hadamard_t1(src_diff, src_stride, coeff, 4); }
 extern "C" void svt_b200_aom_hadamard_8x8(const int16_t* src_diff, ptrdiff_t src_stride, int32_t* coeff) { hadamard_t1(src_diff, src_stride, coeff, 8); }

@@ -260,6 +260,16 @@ for _n in ("4x4", "8x8", "16x16", "32x32"):
     _f.restype = None
 lib.svt_b200_aom_satd.argtypes = [vp, ct.c_int]
 lib.svt_b200_aom_satd.restype = ct.c_int
+class Buf2D(ct.Structure):  # SvtB200Buf2D == the reference's Buf2D
+    _fields_ = [("buf", vp), ("buf0", vp), ("width", ct.c_int), ("height", ct.c_int), ("stride", ct.c_int)]
+
+
+lib.svt_b200_hadamard_path.argtypes = [Buf2D, Buf2D, Buf2D, Buf2D, ct.c_uint8]
+lib.svt_b200_hadamard_path.restype = ct.c_uint32
+lib.svt_b200_av1_fwht4x4.argtypes = [vp, vp, ct.c_uint32]
+lib.svt_b200_av1_fwht4x4.restype = None
+lib.svt_b200_av1_compute_cul_level.argtypes = [vp, vp, vp]
+lib.svt_b200_av1_compute_cul_level.restype = ct.c_uint8
 lib.svt_b200_hadamard_satd_batch_dev.argtypes = [vp, vp, ct.c_int, vp, vp, vp]
 lib.svt_b200_hadamard_satd_batch_dev.restype = ct.c_int
 lib.svt_b200_ext_all_sad_calculation_8x8_16x16.argtypes = [vp, ct.c_uint32, vp, ct.c_uint32, ct.c_uint32, vp, vp, vp, vp,

@@ -111,3 +111,54 @@ def test_fullpel_search_batch(b200, oracle):
         want = mh.ref_fullpel(oracle.ref, *args) if oracle.ref is not None else mh.port_fullpel(oracle.port, *args)
         assert np.array_equal(sad[i], want[0]), i
         assert np.array_equal(mv[i], want[1]), i
+
+
+def test_hadamard_path_fwht_and_cul_level(b200, refc):
+    """the remaining dispatched helpers of the SATD / transform / quantiser group against the reference's C functions:
+    hadamard_path_c (enc_mode_config.c:2147, all 22 block sizes, incl. the residual / coefficients it leaves behind),
+    svt_av1_fwht4x4_c (transforms.c:3099) and svt_av1_compute_cul_level_c (full_loop.c:1449)"""
+    import ctypes as ct
+    r = rng(61)
+
+    class Buf2D(ct.Structure):
+        _fields_ = [("buf", ct.c_void_p), ("buf0", ct.c_void_p), ("width", ct.c_int), ("height", ct.c_int), ("stride", ct.c_int)]
+    refc.hadamard_path_c.argtypes = [Buf2D] * 4 + [ct.c_uint8]
+    refc.hadamard_path_c.restype = ct.c_uint32
+    wide = [4, 4, 8, 8, 8, 16, 16, 16, 32, 32, 32, 64, 64, 64, 128, 128, 4, 16, 8, 32, 16, 64]
+    for bsize in range(22):
+        side, stride = wide[bsize], 160
+        inp = r.integers(0, 256, stride * 130, dtype=np.uint8)
+        prd = r.integers(0, 256, stride * 130, dtype=np.uint8)
+        if bsize % 3 == 0:
+            inp[:], prd[:] = 255, 0  # largest residuals
+        outs = []
+        for fn, B in ((refc.hadamard_path_c, Buf2D), (b200.lib.svt_b200_hadamard_path, b200.Buf2D)):
+            res = np.full(40 * 40, -77, np.int16)
+            cof = np.full(32 * 32, -77, np.int32)
+            cost = fn(B(res.ctypes.data, None, 0, 0, 40), B(cof.ctypes.data, None, 0, 0, side), B(inp.ctypes.data, None, 0, 0, stride),
+                      B(prd.ctypes.data, None, 0, 0, stride), bsize)
+            outs.append((int(cost), res, cof))
+        assert outs[0][0] == outs[1][0], (bsize, outs[0][0], outs[1][0])
+        assert np.array_equal(outs[0][1], outs[1][1]) and np.array_equal(outs[0][2], outs[1][2]), bsize
+    refc.svt_av1_fwht4x4_c.restype = None
+    for k in range(40):
+        stride = 4 + (k % 5)
+        src = r.integers(-1023 if k % 2 else -255, 1024 if k % 2 else 256, 4 * stride).astype(np.int16)
+        want = np.zeros(16, np.int32); got = np.zeros(16, np.int32)
+        refc.svt_av1_fwht4x4_c(mh.P(src), mh.P(want), ct.c_uint32(stride))
+        b200.lib.svt_b200_av1_fwht4x4(mh.P(src), mh.P(got), stride)
+        assert np.array_equal(want, got), k
+    refc.svt_av1_compute_cul_level_c.restype = ct.c_uint8
+    for k in range(60):
+        n = [16, 64, 256, 1024][k % 4]
+        scan = r.permutation(n).astype(np.int16)
+        q = np.zeros(n, np.int32)
+        nz = r.integers(0, n, max(1, n // (2 + k % 7)))
+        q[nz] = r.integers(-3 if k % 3 else -200, 4 if k % 3 else 200, nz.size)
+        if k % 5 == 0:
+            q[0] = 0
+        for eob in (0, 1, n // 2, n):
+            e1, e2 = ct.c_uint16(eob), ct.c_uint16(eob)
+            want = refc.svt_av1_compute_cul_level_c(mh.P(scan), mh.P(q), ct.byref(e1))
+            got = b200.lib.svt_b200_av1_compute_cul_level(mh.P(scan), mh.P(q), ct.byref(e2))
+            assert want == got, (k, eob, want, got)
