@@ -39,13 +39,27 @@ METRIC_SCOPE = "hot path only (SURVEY 8: ME + transform/quant/inverse + CDEF + W
 N_FRAME_SETS = 8  # rotated between steps: no step finds its inputs in L2, and (e2e) up to 8 frames are in flight
 N_CALLS = 10      # len(FramePipeline.CALLS): the T2 entry points one frame goes through
 EXCH_BATCH = 4    # pictures per reconstructed-reference exchange (one mini-GOP slice per NCCL group launch)
-# dram__bytes_read.sum + dram__bytes_write.sum of the call's dominant kernel, per launch, from the ncu --set full
-# capture of this same command (profiles/README.md says which file); None = not captured for that call
-NCU_DRAM_SOURCE = "profiles/r1_top_kernels_ncu_raw.csv (ncu --set full, one launch of the call's main kernel)"
-NCU_DRAM_BYTES = {"cdef_search": 4995584 + 0,          # cdef_search_kernel: read + write (the mse output stays in L2)
-                  "wiener_stats": 6377728 + 0,         # stats_mma_kernel
-                  "txfm_trio": 999680 + 2682880 + 4361216 + 4520704 + 4305152 + 220000,  # the five class kernels (r + w)
-                  "me_search": 7329024 + 12288 + 6755072}  # hme_fused_kernel (r + w) + fullpel_search_kernel  # hme_fused_kernel (r + w) + fullpel_search_kernel
+# roofline.traffic: dram__bytes_read.sum + dram__bytes_write.sum of the dominant call's kernels, per launch, read from the committed ncu launch
+# list of tools/profile_step.py for the same configuration (profiles/README.md) -- None when no capture of that configuration is committed
+NCU_LAUNCHES = {1: "profiles/r2_launches_config1.csv", 2: "profiles/r2_launches_config2.csv"}
+CALL_KERNELS = {"me_pyramid": ("downsample_2d_kernel", "pad_plane_kernel"), "me_search": ("hme_fused_kernel", "fullpel_search_kernel"),
+                "txfm_trio": ("trio_txfm_kernel",), "pack_levels": ("eob_chunk_sum_kernel", "eob_offsets_kernel", "pack_levels_kernel"),
+                "cdef_search": ("cdef_dir_kernel", "cdef_search_kernel"), "cdef_apply": ("cdef_apply_kernel",),
+                "lr_boundaries": ("lr_save_boundary_kernel",), "rest_extend": ("pad_planes_kernel",),
+                "wiener_stats": ("stats_sum_kernel", "stats_mma_kernel", "stats_finalize_kernel", "stats_lag_"), "wiener_filter": ("lr_filter_kernel",)}
+
+
+def ncu_dram_bytes(config, call):
+    import csv
+    path = os.path.join(ROOT, NCU_LAUNCHES.get(config, ""))
+    if not os.path.isfile(path):
+        return None, None
+    tot, seen = 0.0, False
+    for r in csv.reader(open(path)):
+        if len(r) > 10 and r[0].isdigit() and r[-3].startswith("dram__bytes_") and any(k in r[4] for k in CALL_KERNELS.get(call, ())):
+            tot += float(r[-1].replace(",", "")) * {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(r[-2], 1.0)
+            seen = True
+    return (int(tot), NCU_LAUNCHES[config]) if seen else (None, None)
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -490,7 +504,7 @@ def main():
     except Exception:
         pass
     src = "MEASURED_PEAKS.json" if peaks else "fallback of /opt/skills/guides/B200_PROFILING.md"
-    ncu_bytes = NCU_DRAM_BYTES.get(dom_name) if args.config == 1 and not args.width else None
+    ncu_bytes, ncu_src = ncu_dram_bytes(args.config, dom_name) if not args.width else (None, None)
     if dom_name == "wiener_stats":  # the one dense contraction of the path: exact f16 MMA on the tensor cores
         flops = 2.0 * wl0.wiener_stats_macs()
         peak = float(peaks.get("bf16_tflops", peaks.get("dense_bf16_tflops", 2250.0)))
@@ -508,7 +522,7 @@ def main():
             roofline["fused_min_bytes_per_call"] = fm
             roofline["frac_fused_min"] = round(fm / (call_ms[dom] / 1e3) / 1e9 / peak, 5)
     roofline.update({"call": dom_name, "kernel": dom_kernels, "ms_per_call": round(call_ms[dom], 4), "peak_source": src,
-                     "traffic": ncu_bytes, "traffic_source": NCU_DRAM_SOURCE if ncu_bytes is not None else None})
+                     "traffic": ncu_bytes, "traffic_source": ("%s (ncu launch list of tools/profile_step.py, DRAM read + write of the call's kernels)" % ncu_src) if ncu_bytes is not None else None})
     out = {"metric": METRIC, "value": round(fps, 2), "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": warmup,
            "inner_repeats": reps, "timed_region_ms": round(ms, 3),
            "ms_per_step": round(ms / args.steps, 4), "metric_scope": METRIC_SCOPE, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
