@@ -14,8 +14,8 @@ Wiener statistics + filter.  Prints ONE JSON line (rank 0).
 `value`  : frames/s with every input already resident in HBM (CUDA events on the launch stream).
 `e2e`    : same metric through the host-buffer path: per step the source picture and the prediction are copied
            from pinned host memory (the residual is formed on the device) and the ME results, per-block eobs +
-           eob-bounded scan-order levels, CDEF costs, Wiener statistics and the filtered picture are read back,
-           inside the timed region.
+           eob-bounded scan-order levels, CDEF costs and Wiener statistics are read back, inside the timed region
+           (the restored picture stays on the device: it is the reference picture of later frames).
 """
 import argparse
 import ctypes as ct

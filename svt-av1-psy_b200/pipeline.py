@@ -67,10 +67,11 @@ class FramePipeline:
         _, n_flat = wl.flat_offsets()
         _, n_pad = wl.padded_offsets()
         self.n_tx = len(wl.quant_items)
-        # everything the host-side stages read back, in one arena (one device -> host copy per frame)
+        # everything the host-side stages read back, in one arena (one device -> host copy per frame).  The restored picture is NOT
+        # among it: it stays on the device as a reference picture (the host needs it only for recon output / PSNR)
         self._out = _Arena(T, [("me_sad", T.int32, (wl.n_refs, nb, 85)), ("me_mv", T.int32, (wl.n_refs, nb, 85)), ("eobs", T.int16, (self.n_tx,)),
                                ("level_offsets", T.int32, (self.n_tx + 2,)), ("mse", T.int64, (2, nb, len(wl.cdef_str_y))),
-                               ("M", T.int64, (len(wl.stats_items), 49)), ("H", T.int64, (len(wl.stats_items), 2401)), ("final", pix, (n_pad,))], device)
+                               ("M", T.int64, (len(wl.stats_items), 49)), ("H", T.int64, (len(wl.stats_items), 2401))], device)
         # ... and what arrives from the host per frame (source picture + prediction): one host -> device copy
         self._in = _Arena(T, [("cur", pix, (n_flat,)), ("pred", pix, (n_pad,))], device)
         self.me_sad = self._out.view("me_sad")
@@ -83,7 +84,7 @@ class FramePipeline:
         self.pred = self._in.view("pred")                                  # padded planes
         self.recon = T.zeros(n_pad, dtype=pix, device=device)
         self.cdef_out = T.zeros(n_pad, dtype=pix, device=device)
-        self.final = self._out.view("final")
+        self.final = T.zeros(n_pad, dtype=pix, device=device)
         self.coeff = T.zeros(wl.n_coeffs, dtype=T.int32, device=device)
         self.qcoeff = T.zeros_like(self.coeff)
         self.dqcoeff = T.zeros_like(self.coeff)
