@@ -16,6 +16,8 @@ kernels hand to the dispatched DSP functions for one 8-bit 4:2:0 picture at M8 /
 Content follows SURVEY.md 8(d): multi-octave block noise panorama + global pan + sensor noise, seeded.
 Everything here is plain numpy data preparation; it performs no DSP.
 """
+import os
+
 import numpy as np
 
 try:
@@ -68,10 +70,16 @@ def synth_sequence(width, height, n_frames, seed=20260923, bit_depth=8):
     return frames
 
 
-def zigzag_scan(w, h):
-    """a diagonal scan over a w x h (row-major, stride w) coefficient block"""
-    order = sorted(((y + x, y if (y + x) & 1 else x, y, x) for y in range(h) for x in range(w)))
-    return np.array([y * w + x for _, _, y, x in order], np.int16)
+_AV1_TABLES = None
+
+
+def av1_tables():
+    """the reference's scan orders and quantization matrices (see tools/dump_av1_tables.py for the layout)"""
+    global _AV1_TABLES
+    if _AV1_TABLES is None:
+        with np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "av1_tables.npz")) as z:
+            _AV1_TABLES = {k: z[k] for k in z.files}
+    return _AV1_TABLES
 
 
 def quant_tables(d_dc, d_ac):
@@ -191,38 +199,44 @@ class FrameWorkload:
                             fwd.append((res_off[p] + y * pw + x, coef_pos, pw, sz, ty, 1))
                             rpos = rec_off[p] + (self.PAD + y) * st + self.PAD + x
                             inv.append((coef_pos, rpos, rpos, st, st, sz, ty, self.bit_depth, 0, 0))
-                            qnt.append((coef_pos, sz))
+                            qnt.append((coef_pos, sz, ty, int(p > 0)))
                             coef_pos += n
                             sizes_used.add(sz)
         self.fwd_items = np.array(fwd, dtype=dsp.FWD_ITEM_DTYPE)
         self.inv_items = np.array(inv, dtype=dsp.INV_ITEM_DTYPE)
         self.n_coeffs = coef_pos
-        # scan / QM tables, one entry per transform size in use
-        scan_parts, qm_parts, scan_off, qm_off = [], [], {}, {}
+        # scan orders and quantization matrices: the reference's own tables (av1_tables.npz, dumped from the compiled reference by
+        # tools/dump_av1_tables.py).  One entry per (tx_size, tx_type) / (plane type, tx_size) in use.  QM levels as the encoder
+        # derives them for qindex 120 with its default --qm-min 2 --qm-max 15 / --chroma-qm-min 8 --chroma-qm-max 15
+        # (aom_get_qmlevel, md_config_process.c:189; defaults enc_settings.c:1058-1062)
+        tb = av1_tables()
+        self.qindex = 120
+        self.qm_level = (2 + (self.qindex * (15 + 1 - 2)) // 256, 8 + (self.qindex * (15 + 1 - 8)) // 256)
+        scan_parts, iscan_parts, qm_parts, scan_off, qm_off = [], [], [], {}, {}
         so = qo = 0
-        r = np.random.default_rng(7)
-        for sz in sorted(sizes_used):
-            w, h = min(TX_W[sz], 32), min(TX_H[sz], 32)
-            sc = zigzag_scan(w, h)
-            scan_off[sz] = so
-            scan_parts.append(sc)
-            so += sc.size
-            qm = r.integers(26, 40, w * h).astype(np.uint8)
-            iqm = r.integers(26, 40, w * h).astype(np.uint8)
-            qm_off[sz] = (qo, qo + w * h)
-            qm_parts += [qm, iqm]
-            qo += 2 * w * h
-        self.scan_table = np.concatenate(scan_parts)
-        self.iscan_table = np.concatenate([np.argsort(sc).astype(np.int16) for sc in scan_parts])  # inverse permutations
-        self.qm_table = np.concatenate(qm_parts)
+        for sz, ty in sorted({(s_, t_) for _, s_, t_, _ in qnt}):
+            n, o = int(tb["scan_len"][sz]), int(tb["scan_off"][sz, ty])
+            assert n == min(TX_W[sz], 32) * min(TX_H[sz], 32)
+            scan_off[sz, ty] = so
+            scan_parts.append(tb["scan"][o:o + n])
+            iscan_parts.append(tb["iscan"][o:o + n])
+            so += n
+        for sz, pt in sorted({(s_, c_) for _, s_, _, c_ in qnt}):
+            n, o = int(tb["scan_len"][sz]), int(tb["qm_off"][sz])
+            qm_off[sz, pt] = (qo, qo + n)
+            qm_parts += [tb["qm"][self.qm_level[pt], pt, o:o + n], tb["iqm"][self.qm_level[pt], pt, o:o + n]]
+            qo += 2 * n
+        self.scan_table = np.ascontiguousarray(np.concatenate(scan_parts), np.int16)
+        self.iscan_table = np.ascontiguousarray(np.concatenate(iscan_parts), np.int16)
+        self.qm_table = np.ascontiguousarray(np.concatenate(qm_parts), np.uint8)
         t = quant_tables(52 << (self.bit_depth - 8), 61 << (self.bit_depth - 8))  # dc/ac step of qindex ~120, scaled with the bit depth
         q = np.zeros(len(qnt), dtype=dsp.QUANT_ITEM_DTYPE)
-        cp = np.array([c for c, _ in qnt], np.uint64)
-        szs = np.array([s for _, s in qnt])
+        cp = np.array([c for c, _, _, _ in qnt], np.uint64)
+        szs = np.array([s for _, s, _, _ in qnt])
         q["coeff_off"] = q["q_off"] = q["dq_off"] = cp
-        q["scan_off"] = [scan_off[s] for s in szs]
-        q["qm_off"] = [qm_off[s][0] for s in szs]
-        q["iqm_off"] = [qm_off[s][1] for s in szs]
+        q["scan_off"] = [scan_off[s_, t_] for _, s_, t_, _ in qnt]
+        q["qm_off"] = [qm_off[s_, c_][0] for _, s_, _, c_ in qnt]
+        q["iqm_off"] = [qm_off[s_, c_][1] for _, s_, _, c_ in qnt]
         q["n_coeffs"] = [min(TX_W[s], 32) * min(TX_H[s], 32) for s in szs]
         for name in ("zbin", "round", "quant", "quant_shift", "dequant"):
             q[name] = t[name]

@@ -1,5 +1,5 @@
 #!/usr/bin/env python3
-"""One small frame (384x256) through the T2 pipeline, for `compute-sanitizer --tool memcheck|racecheck python
+"""One small frame (384x256, 8-bit then 10-bit) through the T2 pipeline, for `compute-sanitizer --tool memcheck|racecheck python
 tools/sanitize_smoke.py` on a GPU box (no oracle involved: this only drives the product library)."""
 import os
 import sys
@@ -12,8 +12,11 @@ from svt_av1_psy_b200.pipeline import FramePipeline  # noqa: E402
 from svt_av1_psy_b200.workload import FrameWorkload  # noqa: E402
 
 pkg.init(0)
-fp = FramePipeline(FrameWorkload(384, 256), torch)
-fp.load_inputs()
-fp.step()
-torch.cuda.synchronize()
-print("done", int(fp.final.sum()), int(fp.qcoeff.abs().sum()))
+for bd in (8, 10):  # 8-bit: HMMA statistics, u8 TMA maps; 10-bit: lag-sum statistics, u16 planes
+    fp = FramePipeline(FrameWorkload(384, 256, bit_depth=bd), torch)
+    fp.load_inputs()
+    fp.step()
+    fp.read_outputs()
+    fp.read_levels()
+    torch.cuda.synchronize()
+    print("done", bd, int(fp.final.sum()), int(fp.qcoeff.abs().sum()))
