@@ -42,7 +42,7 @@ EXCH_BATCH = 4    # pictures per reconstructed-reference exchange (one mini-GOP 
 # roofline.traffic: dram__bytes_read.sum + dram__bytes_write.sum of the dominant call's kernels, per launch, read from the committed ncu launch
 # list of tools/profile_step.py for the same configuration (profiles/README.md) -- None when no capture of that configuration is committed
 NCU_LAUNCHES = {1: "profiles/r2_launches_config1.csv", 2: "profiles/r2_launches_config2.csv"}
-CALL_KERNELS = {"me_pyramid": ("downsample_2d_kernel", "pad_plane_kernel"), "me_search": ("hme_fused_kernel", "fullpel_search_kernel"),
+CALL_KERNELS = {"me_pyramid": ("downsample_2d_kernel", "pad_plane_kernel"), "me_search": ("me_b64_hme_kernel", "fullpel_search_kernel", "me_b64_finish_kernel"),
                 "txfm_trio": ("trio_txfm_kernel",), "pack_levels": ("eob_chunk_sum_kernel", "eob_offsets_kernel", "pack_levels_kernel"),
                 "cdef_search": ("cdef_dir_kernel", "cdef_search_kernel"), "cdef_apply": ("cdef_apply_kernel",),
                 "lr_boundaries": ("lr_save_boundary_kernel",), "rest_extend": ("pad_planes_kernel",),
@@ -575,7 +575,8 @@ def check_against_reference(fp, torch):
     fp.load_inputs()
     fp.step()
     torch.cuda.synchronize()
-    cmp = [("me_sad", fp.me_sad, fr.me_sad), ("me_mv", fp.me_mv, fr.me_mv), ("hme_centre", fp.me_centre, fr.me_c),
+    from svt_av1_psy_b200.layout import ME_OUTPUT_NAMES
+    cmp = [(k, fp.me[f], fr.me[f]) for k, f in ME_OUTPUT_NAMES.items()] + [
            ("qcoeff", fp.qcoeff, fr.q), ("dqcoeff", fp.dqcoeff, fr.dq), ("eob", fp.eobs, fr.eobs), ("recon", fp.recon, fr.recon),
            ("cdef_mse", fp.cdef_mse, fr.mse), ("cdef_dir", fp.cdef_dir, fr.dirs), ("cdef_out", fp.cdef_out, fr.cdef_out), ("wiener_M", fp.M, fr.M),
            ("wiener_H", fp.Hm, fr.Hm), ("final", fp.final, fr.final)]

@@ -402,7 +402,11 @@ typedef struct SvtB200FullpelItem {
     int16_t  sa_w, sa_h;
     int16_t  org_x, org_y; /* x/y_search_area_origin */
     uint8_t  sub_sad;      /* me_search_method == SUB_SAD_SEARCH */
-    uint8_t  reserved[7];
+    uint8_t  seeded;       /* 1: the best arrays start from the SADs of one probe position (d_seed_sad of the seeded call), which
+                              wins ties -- integer_search_b64 evaluates the search centre first when the 8x8-variance control is
+                              on and does not reset p_sb_best_sad afterwards (motion_estimation.c:1358-1412) */
+    int16_t  seed_x, seed_y; /* MV of the probe position */
+    uint8_t  reserved[2];
 } SvtB200FullpelItem;
 SVT_B200_API int svt_b200_fullpel_search_batch_dev(const uint8_t* d_src_plane, const uint8_t* d_ref_plane,
                                                    const SvtB200FullpelItem* d_items, int n_items, uint32_t* d_best_sad,
@@ -677,6 +681,59 @@ SVT_B200_API int svt_b200_build_hme_pyramid_dev(const SvtB200MePicture* pic, voi
 SVT_B200_API int svt_b200_me_picture_dev(const SvtB200MePicture* cur, const SvtB200MePicture* refs,
                                          const SvtB200MeParams* params, int n_refs, uint32_t* d_best_sad,
                                          uint32_t* d_best_mv, int16_t* d_hme_centre, uint64_t* d_hme_sad, void* stream);
+
+/* ---- T2, the complete driver: svt_aom_motion_estimation_b64 (motion_estimation.c:3076) for every 64x64 block of a picture ----
+ * zz-SAD reference pruning (init_zz_sad :2391), pre-HME (prehme_b64 :1722), HME level 0/1/2 with the early exits and the
+ * pre-HME quadrant replacement (:1906-2180), final search centre (:2182), HME-based reference pruning and search-area divisors
+ * (hme_prune_ref_and_adjust_sr :2477), the integer-search area derivation incl. the 8x8-SAD-variance probe
+ * (integer_search_b64 :1249-1520), the 85-PU full-pel search, ME-based reference pruning (me_prune_ref :1522), candidate
+ * construction (construct_me_candidate_array* :2532-2840), per-size distortions (compute_distortion :2964) and the
+ * global-motion detection flags (perform_gm_detection :2842).
+ *
+ * SvtB200MeControls is the MeContext (me_context.h:366-509) control state AFTER svt_aom_sig_deriv_me (enc_mode_config.c:681),
+ * flattened, plus the few picture-level fields the driver reads.  The host derives it exactly as the encoder does and passes
+ * the result; tests obtain it from the reference's own derivation (oracle/ref_me_b64.c).  Not supported (the call returns
+ * SVT_B200_ERR_BAD_ARG): me_sr_adjustment level 2 (screen-content presets: its rule reads the full-pel result of another
+ * reference of the same block), ME_MCTF (temporal-filter ME). */
+typedef struct SvtB200MeControls {
+    int32_t n_list, n_ref[2];        /* num_of_list_to_search, num_of_ref_pic_to_search[] */
+    int32_t temporal_layer_index, is_ref, hierarchical_levels;
+    int32_t dist[2][4];              /* |picture_number - reference picture_number| */
+    int32_t enable_hme, enable_l0, enable_l1, enable_l2, hme_sub_sad, me_sub_sad;
+    int32_t hme_l0_min_w, hme_l0_min_h, hme_l0_max_w, hme_l0_max_h, hme_l1_w, hme_l1_h, hme_l2_w, hme_l2_h;
+    int32_t me_min_w, me_min_h, me_max_w, me_max_h;
+    int32_t prehme_enable, prehme_sa[2][4] /* [region]{min w, min h, max w, max h} */, prehme_skip_search_line, prehme_l1_early_exit;
+    int32_t prune_enable, prune_hme_th, prune_me_th, zz_sad_th, zz_sad_pct, phme_sad_th, phme_sad_pct;   /* MeHmeRefPruneCtrls */
+    int32_t sr_enable, sr_mv_length_th, sr_stationary_hme_sad_abs_th, sr_stationary_divisor, sr_hme_sad_abs_th, sr_low_hme_sad_divisor,
+        sr_distance_based_hme_resizing;                                                                /* MeSrCtrls */
+    int32_t var_enable, var_div4_th, var_div2_th, var_mult2_th;                                          /* Me8x8VarCtrls (uint32 values) */
+    int32_t mvsa_enable, mvsa_nearest_ref_only, mvsa_mv_size_th, mvsa_multiplier;                        /* MvBasedSearchAdj */
+    int32_t reduce_hme_l0_sr_th_min, reduce_hme_l0_sr_th_max;
+    int32_t me_early_exit_th, me_safe_limit_zz_th, prev_me_stage_based_exit_th, prune_me_candidates_th, use_best_unipred_cand_only;
+    int32_t similar_brightness_refs, only_l_bwd, enable_me_8x8, enable_me_16x16;
+    int32_t max_cand, max_refs, max_l0; /* MotionEstimationData: strides of me_candidate_array / me_mv_array (pcs.h:500-502) */
+    int32_t gm_enabled, gm_use_distance_based_active_th, resolution_le_480p;
+    int32_t reserved[5];
+} SvtB200MeControls;
+
+/* device buffers the call fills (all of them are overwritten completely).  n_pu = svt_b200_me_b64_num_pus(). */
+typedef struct SvtB200MeB64Results {
+    uint8_t*  total_me_candidate_index; /* [n_b64][n_pu]              MeSbResults (me_sb_results.h:44-52), raster PU order */
+    uint8_t*  me_candidate_array;       /* [n_b64][n_pu * max_cand]   MeCandidate bytes: direction | ref_idx_l0<<2 | ref_idx_l1<<4 | ref0_list<<6 | ref1_list<<7 */
+    uint32_t* me_mv_array;              /* [n_b64][n_pu * max_refs]   (y << 16) | (x & 0xffff), full-pel */
+    uint32_t* distortion;               /* [n_b64][6]: rc_me_distortion, me_64x64/32x32/16x16/8x8_distortion, me_8x8_cost_variance */
+    uint8_t*  flags;                    /* [n_b64][2]: stationary_block_present_sb, rc_me_allow_gm */
+    uint8_t*  do_ref;                   /* [n_b64][2][4]   references still alive after all pruning */
+    int16_t*  hme_centre;               /* [n_b64][2][4][2] search_results[].hme_sc_x / hme_sc_y */
+    uint32_t* zz_sad;                   /* [n_b64][2][4] */
+    uint32_t* best_sad;                 /* [n_refs][n_b64][85] p_sb_best_sad of every reference (list 0 first), ME z-order; pruned references: undefined */
+    uint32_t* best_mv;                  /* [n_refs][n_b64][85] */
+} SvtB200MeB64Results;
+/* 85, 21 or 5: the square PUs that carry candidates (me_sb_results_ctor, pcs.c:107-112) */
+SVT_B200_API int svt_b200_me_b64_num_pus(const SvtB200MeControls* ctrl);
+/* cur / refs / ctrl / out are HOST structs holding device pointers; refs = n_ref[0] list-0 pictures, then n_ref[1] list-1 pictures */
+SVT_B200_API int svt_b200_me_b64_picture_dev(const SvtB200MePicture* cur, const SvtB200MePicture* refs, const SvtB200MeControls* ctrl,
+                                             const SvtB200MeB64Results* out, void* stream);
 
 #ifdef __cplusplus
 }

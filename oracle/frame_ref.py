@@ -29,8 +29,8 @@ def load_workload_module():
 
 class RefFrameJob(ct.Structure):
     _fields_ = [("width", ct.c_int32), ("height", ct.c_int32), ("bit_depth", ct.c_int32), ("n_refs", ct.c_int32),
-                ("cur", vp), ("refs", vp), ("prm", vp),
-                ("me_sad", vp), ("me_mv", vp), ("me_centre", vp), ("me_hme_sad", vp),
+                ("cur", vp), ("refs", vp), ("me_cfg", vp),
+                ("me", me_np.RefMeB64Out),
                 ("residual", vp), ("coeff", vp), ("q", vp), ("dq", vp), ("scan", vp), ("iscan", vp), ("qm", vp),
                 ("fwd", vp), ("qi", vp), ("inv", vp), ("eobs", vp),
                 ("n_tx", ct.c_int64), ("n_coeffs", ct.c_int64),
@@ -46,6 +46,15 @@ class RefFrameJob(ct.Structure):
                 ("stats", vp), ("M", vp), ("H", vp), ("units", vp), ("n_stats", ct.c_int32), ("n_units", ct.c_int32),
                 ("lr_units", vp * 3), ("lr_above", vp * 3), ("lr_below", vp * 3), ("lr_unit_size", ct.c_int32 * 3), ("lr_bstride", ct.c_int32 * 3),
                 ("lr_stripes", ct.c_int32 * 3), ("reserved2", ct.c_int32)]
+
+
+def me_cfg_for(wl):
+    """the RefMeB64Cfg of the workload's ME picture (workload.ME_PICTURE and friends)"""
+    m = sys.modules[type(wl).__module__]
+    mp = wl.me_picture
+    return me_np.me_b64_cfg(preset=wl.preset, qp=mp["qp"], n_ref=mp["n_ref"], poc_dist=m.ME_DIST, temporal_layer_index=m.ME_TEMPORAL_LAYER,
+                            hierarchical_levels=m.ME_HIERARCHICAL_LEVELS, is_ref=m.ME_IS_REF, max_l=mp["max_l"], only_l_bwd=mp["only_l_bwd"],
+                            safe_limit_nref=mp["safe_limit_nref"], gm_enabled=mp["gm_enabled"])
 
 
 def aligned_zeros(n, dtype, align=64):
@@ -75,15 +84,14 @@ class RefFrame:
         self.ref_pyrs = [me_np.build_pyramid_np(wl.me_luma(r), W, H, wl.me_shapes) for r in wl.refs]
         self.cur_desc = me_np.ref_pic_desc(self.cur_pyr, wl.me_shapes)
         self.ref_descs = (me_np.RefMePicture * wl.n_refs)(*[me_np.ref_pic_desc(p, wl.me_shapes) for p in self.ref_pyrs])
-        self.prm = (me_np.RefMeParams * wl.n_refs)()
-        for i, p in enumerate(wl.me_params):
-            for k, v in p.items():
-                setattr(self.prm[i], k, v)
+        self.me_cfg = me_cfg_for(wl)
         nb = ((W + 63) // 64) * ((H + 63) // 64)
-        self.me_sad = np.zeros((wl.n_refs, nb, 85), np.uint32)
-        self.me_mv = np.zeros_like(self.me_sad)
-        self.me_c = np.zeros((wl.n_refs, nb, 2), np.int16)
-        self.me_hs = np.zeros((wl.n_refs, nb), np.uint64)
+        mc, mr, n_pu = wl.me_controls["max_cand"], wl.me_controls["max_refs"], wl.me_n_pu
+        # svt_aom_motion_estimation_b64's outputs: MeSbResults + the pcs distortion arrays + the per-reference state
+        self.me = {"total_me_candidate_index": np.zeros((nb, n_pu), np.uint8), "me_candidate_array": np.zeros((nb, n_pu * mc), np.uint8),
+                   "me_mv_array": np.zeros((nb, n_pu * mr), np.uint32), "distortion": np.zeros((nb, 6), np.uint32),
+                   "flags": np.zeros((nb, 2), np.uint8), "do_ref": np.zeros((nb, 2, 4), np.uint8),
+                   "hme_centre": np.zeros((nb, 2, 4, 2), np.int16), "zz_sad": np.zeros((nb, 2, 4), np.uint32)}
         self.cur_flat = np.concatenate([p.reshape(-1) for p in wl.cur])
         res = np.concatenate([p.reshape(-1) for p in wl.residual])
         self.residual = aligned_zeros(res.size, np.int16)
@@ -126,8 +134,10 @@ class RefFrame:
         j = RefFrameJob()
         P = lambda a: a.ctypes.data  # noqa: E731
         j.width, j.height, j.bit_depth, j.n_refs = wl.width, wl.height, wl.bit_depth, wl.n_refs
-        j.cur, j.refs, j.prm = ct.addressof(self.cur_desc), ct.addressof(self.ref_descs), ct.addressof(self.prm)
-        j.me_sad, j.me_mv, j.me_centre, j.me_hme_sad = P(self.me_sad), P(self.me_mv), P(self.me_c), P(self.me_hs)
+        j.cur, j.refs, j.me_cfg = ct.addressof(self.cur_desc), ct.addressof(self.ref_descs), ct.addressof(self.me_cfg)
+        for k, a in self.me.items():
+            setattr(j.me, k, P(a))
+        j.me.best_sad = j.me.best_mv = None
         j.residual, j.coeff, j.q, j.dq = P(self.residual), P(self.coeff), P(self.q), P(self.dq)
         j.scan, j.iscan, j.qm = P(wl.scan_table), P(wl.iscan_table), P(wl.qm_table)
         j.fwd, j.qi, j.inv, j.eobs = P(self.fwd), P(self.qi), P(self.inv), P(self.eobs)

@@ -105,6 +105,8 @@ int ref_set_threads(int n) {
     return n;
 }
 int ref_num_threads(void) { return g_threads ? g_threads : ref_set_threads(0); }
+static void par_for(int n, int chunk, ParBody body, void* ctx);
+void ref_par_for(int n, int chunk, ParBody body, void* ctx) { par_for(n, chunk, body, ctx); } /* for oracle/ref_me_b64.c */
 void ref_pool_shutdown(void) { pool_stop(); g_threads = 0; }
 static void par_for(int n, int chunk, ParBody body, void* ctx) {
     if (t_in_worker || ref_num_threads() == 1 || n <= chunk) {
@@ -212,7 +214,7 @@ int ref_set_tier(int avx2) {
  * restates hme_level_0/1/2 (motion_estimation.c:820-1113), set_final_seach_centre_sb (:2182-2390),
  * check_00_center (:1139-1210), integer_search_b64 (:1249-1520), open_loop_me_fullpel_search_sblock
  * (:781-817) for the controls the B200 T2 path honours. */
-typedef struct { const uint8_t* plane[3]; int32_t stride[3], org_x[3], org_y[3], width[3], height[3], reserved[2]; } RefMePicture;
+#include "ref_me_b64.h" /* RefMePicture + the complete driver (ref_me_b64.c) */
 typedef struct { int32_t hme_l0_sa_w, hme_l0_sa_h, hme_l1_sa_w, hme_l1_sa_h, hme_l2_sa_w, hme_l2_sa_h, me_sa_w, me_sa_h, hme_sub_sad, me_sub_sad, check_zero_centre, reserved; } RefMeParams;
 
 static void hme_clip(int16_t org, int16_t* origin, int16_t* sa, int16_t pad, int16_t pic, int round8) {
@@ -708,8 +710,8 @@ void ref_lr_filter_plane(void* data, int stride, void* dst, int dst_stride, int 
                          const RefLrUnitInfo* units, void* above, void* below, int bstride, int optimized_lr);
 typedef struct RefFrameJob {
     int32_t width, height, bit_depth, n_refs;
-    const RefMePicture* cur; const RefMePicture* refs; const RefMeParams* prm;
-    uint32_t* me_sad; uint32_t* me_mv; int16_t* me_centre; uint64_t* me_hme_sad;
+    const RefMePicture* cur; const RefMePicture* refs; const RefMeB64Cfg* me_cfg;
+    RefMeB64Out me; /* MeSbResults + distortions + per-reference state of svt_aom_motion_estimation_b64 (best_sad / best_mv unused: NULL) */
     int16_t* residual; int32_t *coeff, *q, *dq; const int16_t *scan, *iscan; const uint8_t* qm;
     const RefFwdItem* fwd; const RefQuantItem* qi; const RefInvItem* inv; uint16_t* eobs;
     int64_t n_tx, n_coeffs;
@@ -775,8 +777,11 @@ static int g_trace = -1;
 void ref_frame_step(const RefFrameJob* j) {
     TRACE("me");
     const int nb = ((j->width + 63) >> 6) * ((j->height + 63) >> 6), psz = j->bit_depth > 8 ? 2 : 1;
-    MeCtx me = {j->cur, j->refs, j->prm, j->n_refs, j->me_sad, j->me_mv, j->me_centre, j->me_hme_sad};
-    par_for(j->n_refs * nb, 4, ref_me_picture_body, &me);
+    {   /* the reference's own open-loop ME driver for every 64x64 block (oracle/ref_me_b64.c) */
+        RefMeControls ctrl;
+        RefMeB64Out   mo = j->me;
+        ref_me_b64_picture(j->cur, j->refs, j->me_cfg, &ctrl, &mo);
+    }
     TRACE("tx");
     TxCtx tx = {j->residual, j->coeff, j->q, j->dq, j->scan, j->iscan, j->qm, j->fwd, j->qi, j->inv, j->eobs, j->pred, j->recon, j->bit_depth,
                 j->src, j->residual, 1};
@@ -810,7 +815,7 @@ void ref_frame_step(const RefFrameJob* j) {
 }
 
 /* private output buffers of one pool thread (allocated on first use, grown when a larger job arrives) */
-typedef struct { size_t cap[23]; void* buf[23]; } WorkerBufs;
+typedef struct { size_t cap[32]; void* buf[32]; } WorkerBufs;
 static __thread WorkerBufs t_bufs;
 static void* wb(int k, size_t bytes) {
     if (t_bufs.cap[k] < bytes) {
@@ -826,10 +831,18 @@ static void frame_body(void* vctx, int i) {
     const FramesCtx* c = (const FramesCtx*)vctx;
     RefFrameJob j = c->sets[i % c->n_sets];
     const size_t nb = (size_t)((j.width + 63) >> 6) * ((j.height + 63) >> 6), psz = j.bit_depth > 8 ? 2 : 1;
-    j.me_sad = wb(0, (size_t)j.n_refs * nb * 85 * 4);
-    j.me_mv = wb(1, (size_t)j.n_refs * nb * 85 * 4);
-    j.me_centre = wb(2, (size_t)j.n_refs * nb * 4);
-    j.me_hme_sad = wb(3, (size_t)j.n_refs * nb * 8);
+    int n_pu, max_cand, max_refs;
+    ref_me_b64_sizes(j.me_cfg, j.width, j.height, &n_pu, &max_cand, &max_refs);
+    j.me.total_me_candidate_index = wb(0, nb * (size_t)n_pu);
+    j.me.me_candidate_array = wb(1, nb * (size_t)n_pu * max_cand);
+    j.me.me_mv_array = wb(2, nb * (size_t)n_pu * max_refs * 4);
+    j.me.distortion = wb(3, nb * 6 * 4);
+    j.me.flags = wb(23, nb * 2);
+    j.me.do_ref = wb(24, nb * 8);
+    j.me.hme_centre = wb(25, nb * 8 * 2 * 2);
+    j.me.zz_sad = wb(26, nb * 8 * 4);
+    j.me.best_sad = NULL;
+    j.me.best_mv = NULL;
     j.coeff = wb(4, (size_t)j.n_coeffs * 4);
     j.q = wb(5, (size_t)j.n_coeffs * 4);
     j.dq = wb(6, (size_t)j.n_coeffs * 4);

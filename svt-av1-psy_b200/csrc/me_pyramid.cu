@@ -209,7 +209,8 @@ template <bool TMA>
 __global__ void __launch_bounds__(kFpThreads)
 fullpel_search_kernel(const uint8_t* __restrict__ src_plane, const uint8_t* __restrict__ ref_plane,
                       const SvtB200FullpelItem* __restrict__ items, int n_items, uint32_t* __restrict__ best_sad,
-                      uint32_t* __restrict__ best_mv, const __grid_constant__ FpTma tm) {
+                      uint32_t* __restrict__ best_mv, const uint32_t* __restrict__ seed_sad /* [n_items][85] or null */,
+                      const __grid_constant__ FpTma tm) {
     constexpr int LW = TMA ? kFpBoxW / 4 : kFpLW;  // words per staged window line
     constexpr int SW = TMA ? kFpSrcBoxW / 4 : 16;  // words per staged source line
     __shared__ __align__(128) uint32_t Sbuf[TMA ? 2 : 1][64 * (TMA ? kFpSrcBoxW / 4 : 16)];
@@ -247,7 +248,10 @@ fullpel_search_kernel(const uint8_t* __restrict__ src_plane, const uint8_t* __re
     for (int it = blockIdx.x; it < n_items; it += gridDim.x, k++) {
         const SvtB200FullpelItem item = items[it];
         const int sa_w = item.sa_w, sa_h = item.sa_h, sub = item.sub_sad;
-        if (threadIdx.x < 85) best[threadIdx.x] = ((unsigned long long)(128u * 128u * 255u) << 32) | 0xffffffffull;
+        // key = sad << 32 | (scan index + 1); index 0 is the seed position (evaluated before the scan, so it wins ties)
+        if (threadIdx.x < 85)
+            best[threadIdx.x] = (item.seeded && seed_sad) ? ((unsigned long long)seed_sad[(size_t)it * 85 + threadIdx.x] << 32)
+                                                          : (((unsigned long long)(128u * 128u * 255u) << 32) | 0xffffffffull);
         int rx0 = 0;  // column of the window origin / word offset of the source block inside their aligned boxes
         const uint32_t* S = Sbuf[TMA ? (k & 1) : 0];
         if (TMA) {
@@ -332,7 +336,7 @@ fullpel_search_kernel(const uint8_t* __restrict__ src_plane, const uint8_t* __re
                         const uint32_t v = pu < 21 ? sadpu[pos][pu] : sad8[pos][pu - 21];
                         const int py = pos / tw, px = pos - py * tw;
                         const unsigned long long key =
-                            ((unsigned long long)v << 32) | (unsigned long long)(uint32_t)((y0 + py) * sa_w + (x0 + px));
+                            ((unsigned long long)v << 32) | (unsigned long long)(uint32_t)((y0 + py) * sa_w + (x0 + px) + 1);
                         b = key < b ? key : b;
                     }
                     best[pu] = b;
@@ -346,8 +350,10 @@ fullpel_search_kernel(const uint8_t* __restrict__ src_plane, const uint8_t* __re
             best_sad[(size_t)it * 85 + threadIdx.x] = (uint32_t)(b >> 32);
             if (idx == 0xffffffffu)
                 best_mv[(size_t)it * 85 + threadIdx.x] = 0;
+            else if (idx == 0)
+                best_mv[(size_t)it * 85 + threadIdx.x] = pack_mv(item.seed_x, item.seed_y);
             else {
-                const int y = (int)(idx / (uint32_t)sa_w), x = (int)(idx - (uint32_t)y * sa_w);
+                const int y = (int)((idx - 1) / (uint32_t)sa_w), x = (int)((idx - 1) - (uint32_t)y * sa_w);
                 best_mv[(size_t)it * 85 + threadIdx.x] = pack_mv(item.org_x + x, item.org_y + y);
             }
         }
@@ -389,7 +395,7 @@ static bool make_plane_map(CUtensorMap* m, const uint8_t* base, int pitch, int r
 
 // full-pel search of a picture's (reference, b64) items through TMA; false = geometry not expressible (caller falls back)
 bool launch_fullpel_tma(const SvtB200MePicture* cur, const SvtB200MePicture* refs, int n_refs, int n_b64, const SvtB200FullpelItem* d_items,
-                        int n_items, uint32_t* d_best_sad, uint32_t* d_best_mv, cudaStream_t st) {
+                        int n_items, uint32_t* d_best_sad, uint32_t* d_best_mv, cudaStream_t st, const uint32_t* d_seed_sad) {
     if (n_refs > kFpTmaRefs) return false;
     FpTma tm;
     memset(&tm, 0, sizeof(tm));
@@ -404,7 +410,7 @@ bool launch_fullpel_tma(const SvtB200MePicture* cur, const SvtB200MePicture* ref
         tm.ref_pitch[r] = refs[r].stride[2];
     }
     tm.n_b64 = n_b64;
-    fullpel_search_kernel<true><<<grid_for(n_items, 4), kFpThreads, 0, st>>>(nullptr, nullptr, d_items, n_items, d_best_sad, d_best_mv, tm);
+    fullpel_search_kernel<true><<<grid_for(n_items, 4), kFpThreads, 0, st>>>(nullptr, nullptr, d_items, n_items, d_best_sad, d_best_mv, d_seed_sad, tm);
     B200_LAUNCH_CHECK();
     return true;
 }
@@ -533,7 +539,7 @@ extern "C" int svt_b200_fullpel_search_batch_dev(const uint8_t* d_src_plane, con
     memset(&none, 0, sizeof(none));
     none.n_b64 = 1;
     fullpel_search_kernel<false><<<grid_for(n_items, 4), kFpThreads, 0, (cudaStream_t)stream>>>(d_src_plane, d_ref_plane, d_items, n_items,
-                                                                                              d_best_sad, d_best_mv, none);
+                                                                                              d_best_sad, d_best_mv, nullptr, none);
     B200_LAUNCH_CHECK();
     return SVT_B200_OK;
 }

@@ -439,6 +439,35 @@ lib.svt_b200_me_picture_dev.argtypes = [ct.POINTER(MePicture), ct.POINTER(MePict
 lib.svt_b200_me_picture_dev.restype = ct.c_int
 
 
+class MeControls(ct.Structure):  # SvtB200MeControls
+    _fields_ = [(n, ct.c_int32 if k == 1 else ct.c_int32 * k) for n, k in ME_CONTROL_FIELDS]
+
+    @classmethod
+    def from_dict(cls, d):
+        """d: field -> int (or a flat list for the array fields), e.g. the reference's derivation dumped by tools/dump_me_controls.py"""
+        c = cls()
+        for n, k in ME_CONTROL_FIELDS:
+            if n == "reserved" or n not in d:
+                continue
+            if k == 1:
+                setattr(c, n, int(d[n]))
+            else:
+                for i, v in enumerate(d[n]):
+                    getattr(c, n)[i] = int(v)
+        return c
+
+
+class MeB64Results(ct.Structure):  # SvtB200MeB64Results
+    _fields_ = [(n, vp) for n in ME_B64_RESULT_FIELDS]
+
+
+assert ct.sizeof(MeControls) == 4 * ME_CONTROL_WORDS
+lib.svt_b200_me_b64_num_pus.argtypes = [ct.POINTER(MeControls)]
+lib.svt_b200_me_b64_num_pus.restype = ct.c_int
+lib.svt_b200_me_b64_picture_dev.argtypes = [ct.POINTER(MePicture), ct.POINTER(MePicture), ct.POINTER(MeControls), ct.POINTER(MeB64Results), vp]
+lib.svt_b200_me_b64_picture_dev.restype = ct.c_int
+
+
 
 def me_picture_desc(planes, width, height):
     """planes: three 2-D uint8 torch CUDA tensors (padded buffers) as laid out by me_plane_shapes()"""

@@ -58,10 +58,8 @@ class FramePipeline:
             assert lib.svt_b200_build_hme_pyramid_dev(ct.byref(d), None) == 0
         self.cur_desc = dsp.me_picture_desc(self.cur_planes, W, H)
         self.ref_descs = (dsp.MePicture * wl.n_refs)(*[dsp.me_picture_desc(p, W, H) for p in self.ref_planes])
-        self.me_prm = (dsp.MeParams * wl.n_refs)()
-        for i, p in enumerate(wl.me_params):
-            for k, v in p.items():
-                setattr(self.me_prm[i], k, v)
+        self.me_ctrl = dsp.MeControls.from_dict(wl.me_controls)   # the MeContext controls of the workload's ME picture
+        assert lib.svt_b200_me_b64_num_pus(ct.byref(self.me_ctrl)) == wl.me_n_pu
         nb = ((W + 63) // 64) * ((H + 63) // 64)
         self.n_b64 = nb
         _, n_flat = wl.flat_offsets()
@@ -69,15 +67,24 @@ class FramePipeline:
         self.n_tx = len(wl.quant_items)
         # everything the host-side stages read back, in one arena (one device -> host copy per frame).  The restored picture is NOT
         # among it: it stays on the device as a reference picture (the host needs it only for recon output / PSNR)
-        self._out = _Arena(T, [("me_sad", T.int32, (wl.n_refs, nb, 85)), ("me_mv", T.int32, (wl.n_refs, nb, 85)), ("eobs", T.int16, (self.n_tx,)),
+        mc, mr, n_pu = wl.me_controls["max_cand"], wl.me_controls["max_refs"], wl.me_n_pu
+        self._out = _Arena(T, [("me_mv_array", T.int32, (nb, n_pu * mr)), ("me_distortion", T.int32, (nb, 6)),
+                               ("me_candidate_array", T.uint8, (nb, n_pu * mc)), ("me_total", T.uint8, (nb, n_pu)), ("me_flags", T.uint8, (nb, 2)),
+                               ("eobs", T.int16, (self.n_tx,)),
                                ("level_offsets", T.int32, (self.n_tx + 2,)), ("mse", T.int64, (2, nb, len(wl.cdef_str_y))),
                                ("M", T.int64, (len(wl.stats_items), 49)), ("H", T.int64, (len(wl.stats_items), 2401))], device)
         # ... and what arrives from the host per frame (source picture + prediction): one host -> device copy
         self._in = _Arena(T, [("cur", pix, (n_flat,)), ("pred", pix, (n_pad,))], device)
-        self.me_sad = self._out.view("me_sad")
-        self.me_mv = self._out.view("me_mv")
-        self.me_centre = T.zeros((wl.n_refs, nb, 2), dtype=T.int16, device=device)
-        self.me_hme_sad = T.zeros((wl.n_refs, nb), dtype=T.int64, device=device)
+        # ME results the host-side mode decision consumes (MeSbResults + the per-block distortions) ...
+        self.me = {"total_me_candidate_index": self._out.view("me_total"), "me_candidate_array": self._out.view("me_candidate_array"),
+                   "me_mv_array": self._out.view("me_mv_array"), "distortion": self._out.view("me_distortion"), "flags": self._out.view("me_flags"),
+                   # ... and the per-reference search state, which stays on the device
+                   "do_ref": T.zeros((nb, 2, 4), dtype=T.uint8, device=device), "hme_centre": T.zeros((nb, 2, 4, 2), dtype=T.int16, device=device),
+                   "zz_sad": T.zeros((nb, 2, 4), dtype=T.int32, device=device),
+                   "best_sad": T.zeros((wl.n_refs, nb, 85), dtype=T.int32, device=device), "best_mv": T.zeros((wl.n_refs, nb, 85), dtype=T.int32, device=device)}
+        self.me_out = dsp.MeB64Results()
+        for k, v in self.me.items():
+            setattr(self.me_out, k, v.data_ptr())
         # ---- TX ---------------------------------------------------------------------------------------
         self.cur_flat = self._in.view("cur")                               # source picture Y|U|V
         self.residual = T.zeros(n_flat, dtype=T.int16, device=device)
@@ -209,8 +216,8 @@ class FramePipeline:
         assert lib.svt_b200_build_hme_pyramid_dev(ct.byref(self.cur_desc), s) == 0
 
     def call_me_search(self, s):
-        rc = lib.svt_b200_me_picture_dev(ct.byref(self.cur_desc), self.ref_descs, self.me_prm, self.wl.n_refs, self.me_sad.data_ptr(),
-                                         self.me_mv.data_ptr(), self.me_centre.data_ptr(), self.me_hme_sad.data_ptr(), s)
+        """svt_aom_motion_estimation_b64 for every 64x64 block: pre-HME, HME, pruning, full-pel search, candidates, distortions"""
+        rc = lib.svt_b200_me_b64_picture_dev(ct.byref(self.cur_desc), self.ref_descs, ct.byref(self.me_ctrl), ct.byref(self.me_out), s)
         assert rc == 0
 
     def call_txfm_trio(self, s):
@@ -325,7 +332,7 @@ class FramePipeline:
     STAGES = ("me", "tx", "cdef", "rest")
     # (call, stage it belongs to, the kernels it launches)
     CALLS = (("me_pyramid", "me", "downsample_2d_kernel+pad_plane_kernel"),
-             ("me_search", "me", "hme_fused_kernel + fullpel_search_kernel"),
+             ("me_search", "me", "me_b64_hme_kernel + fullpel_search_kernel + me_b64_finish_kernel"),
              ("txfm_trio", "tx", "trio_txfm_kernel<4..64> (residual + forward transform + quantise + inverse transform fused)"),
              ("pack_levels", "tx", "eob_chunk_sum_kernel+eob_offsets_kernel+pack_levels_kernel"),
              ("cdef_search", "cdef", "cdef_dir_kernel+cdef_search_kernel"),

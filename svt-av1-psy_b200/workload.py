@@ -27,22 +27,55 @@ except ImportError:  # loaded stand-alone (bench.py's CPU reference arm must not
 
 TX_W, TX_H = dsp.TX_W, dsp.TX_H
 
-# Search / filter settings per encoder preset, derived from the reference's own tables for CRF 25-30, reference
-# distance 1, non-screen content (enc_mode_config.c:138-345 ME/HME search areas with their qp modulation,
-# :875-1110 + :1736-1747 CDEF search level; motion_estimation.c:1800-1866 for the per-region L0 area):
-#   M8: HME L0 16x4 / region, full-pel 8x3;   CDEF level 7 (subsampling 4)
-#   M6: HME L0 16x8,          full-pel 8x8;   CDEF level 5 (3 + 3 strengths, every row, chroma first pass only)
-#   M4: HME L0 16x8,          full-pel 24x24; CDEF level 5
+# CDEF search settings per encoder preset, from the reference's own tables for CRF 25-30, non-screen content
+# (enc_mode_config.c:875-1110 + :1736-1747 CDEF search level):
+#   M8: CDEF level 7 (subsampling 4);  M6 / M4: CDEF level 5 (3 + 3 strengths, every row, chroma first pass only)
 PRESETS = {
-    8: dict(hme_l0=(16, 4), me_sa=(8, 3), cdef_y=[0, 4, 9, 17, 20, 35], cdef_uv=[0, 4, 8, 17, -1, 20], cdef_subsampling=4),
-    6: dict(hme_l0=(16, 8), me_sa=(8, 8), cdef_y=[0, 28, 60, 2, 30, 62], cdef_uv=[0, 28, 60, -1, -1, -1], cdef_subsampling=1),
-    4: dict(hme_l0=(16, 8), me_sa=(24, 24), cdef_y=[0, 28, 60, 2, 30, 62], cdef_uv=[0, 28, 60, -1, -1, -1], cdef_subsampling=1),
+    8: dict(cdef_y=[0, 4, 9, 17, 20, 35], cdef_uv=[0, 4, 8, 17, -1, 20], cdef_subsampling=4),
+    6: dict(cdef_y=[0, 28, 60, 2, 30, 62], cdef_uv=[0, 28, 60, -1, -1, -1], cdef_subsampling=1),
+    4: dict(cdef_y=[0, 28, 60, 2, 30, 62], cdef_uv=[0, 28, 60, -1, -1, -1], cdef_subsampling=1),
 }
+# The picture whose open-loop ME the workload runs: a B picture of temporal layer 3 in the default 5-layer random-access
+# hierarchy, searching the reference counts the preset's MRP level tries on non-base pictures (set_mrp_ctrl,
+# enc_handle.c:3376-3600: level 10 for M8 CRF, 9 for M6, 5 for M4) at picture distances 1, 2, 3(, 4).  `max_l` = the counts
+# the ME result arrays are sized for (pd_process.c:3503-3519).  The MeContext controls of (preset, resolution class) are
+# the reference's own derivation (svt_aom_sig_deriv_me), dumped by tools/dump_me_controls.py into me_controls.json.
+ME_PICTURE = {
+    8: dict(qp=30, n_ref=(2, 2), max_l=(3, 2), only_l_bwd=1, safe_limit_nref=2, gm_enabled=0),
+    6: dict(qp=25, n_ref=(3, 2), max_l=(3, 2), only_l_bwd=1, safe_limit_nref=2, gm_enabled=0),
+    4: dict(qp=25, n_ref=(4, 3), max_l=(4, 3), only_l_bwd=1, safe_limit_nref=0, gm_enabled=1),
+}
+ME_TEMPORAL_LAYER, ME_HIERARCHICAL_LEVELS, ME_IS_REF = 3, 4, 1
+ME_DIST = ((-1, -2, -3, -4), (1, 2, 3, 0))  # picture-number difference of the references, list 0 (past) / list 1 (future)
+# svt_aom_derive_input_resolution (sequence_control_set.c:113-131; thresholds definitions.h:2051-2056): classes 0..6
+_RES_TH = (0x28500, 0x4CE00, 0xA1400, 0x16DA00, 0x535200, 0x140A000)
+
+
+def input_resolution_class(width, height):
+    return sum(1 for t in _RES_TH if width * height >= t)
+
+
+_ME_CONTROLS = None
+
+
+def me_controls(preset, width, height):
+    """SvtB200MeControls field -> value for the workload's ME picture (see ME_PICTURE) at this preset / resolution class"""
+    global _ME_CONTROLS
+    if _ME_CONTROLS is None:
+        import json
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "me_controls.json")) as f:
+            _ME_CONTROLS = json.load(f)
+    key = "m%d_class%d" % (preset, input_resolution_class(width, height))
+    if key not in _ME_CONTROLS:
+        raise KeyError("no ME controls for %s in me_controls.json: run tools/dump_me_controls.py where /root/reference exists" % key)
+    return _ME_CONTROLS[key]
+
+
 # BASELINE.json configs[k] -> (width, height, bit_depth, preset)
 CONFIGS = {0: (640, 360, 8, 8), 1: (1920, 1080, 8, 8), 2: (1920, 1080, 10, 6), 3: (3840, 2160, 8, 8), 4: (3840, 2160, 10, 4)}
 CONFIG_NAMES = {
     0: "configs[0]: 640x360 8-bit 4:2:0 synthetic hot path (the reference's CPU-runnable case; M8 search settings)",
-    1: "configs[1]: 1920x1080 8-bit 4:2:0 synthetic, preset 8 CRF 30 hot path (ME 2 refs + TX + CDEF + Wiener), 1 frame/step",
+    1: "configs[1]: 1920x1080 8-bit 4:2:0 synthetic, preset 8 CRF 30 hot path (ME 2+2 refs + TX + CDEF + Wiener), 1 frame/step",
     2: "configs[2]: 1920x1080 10-bit (HBD path) synthetic, preset 6 CRF 25 hot path, 1 frame/step",
     3: "configs[3]: 3840x2160 8-bit 4:2:0 synthetic, preset 8 hot path, 1 frame/step (frame-parallel across GPUs)",
     4: "configs[4]: 3840x2160 10-bit synthetic, preset 4, CDEF + restoration hot path, 1 frame/step",
@@ -93,17 +126,18 @@ def quant_tables(d_dc, d_ac):
 class FrameWorkload:
     PAD = 16  # border of the reconstruction planes (restoration reads 3(+1) pixels beyond the picture)
 
-    def __init__(self, width=1920, height=1080, seed=20260923, n_refs=2, bit_depth=8, preset=8):
+    def __init__(self, width=1920, height=1080, seed=20260923, bit_depth=8, preset=8):
         assert width % 8 == 0 and height % 8 == 0 and bit_depth in (8, 10) and preset in PRESETS
-        self.width, self.height, self.n_refs, self.bit_depth, self.preset = width, height, n_refs, bit_depth, preset
+        self.width, self.height, self.bit_depth, self.preset = width, height, bit_depth, preset
+        self.me_picture = ME_PICTURE[preset]
+        self.n_ref = self.me_picture["n_ref"]          # (list 0, list 1) reference pictures searched
+        self.n_refs = self.n_ref[0] + self.n_ref[1]
+        self.me_controls = me_controls(preset, width, height)
         self.pixel_bytes = 1 if bit_depth == 8 else 2
         self.pixel_dtype = np.uint8 if bit_depth == 8 else np.uint16
         self._set_pictures(seed)
         self.me_shapes = dsp.me_plane_shapes(width, height)
-        ps = PRESETS[preset]
-        self.me_params = [dict(hme_l0_sa_w=ps["hme_l0"][0], hme_l0_sa_h=ps["hme_l0"][1], hme_l1_sa_w=8, hme_l1_sa_h=3, hme_l2_sa_w=8,
-                               hme_l2_sa_h=3, me_sa_w=ps["me_sa"][0], me_sa_h=ps["me_sa"][1], hme_sub_sad=1, me_sub_sad=1,
-                               check_zero_centre=1) for _ in range(n_refs)]
+        self.me_n_pu = 85 if self.me_controls["enable_me_8x8"] else 21  # square PUs that carry ME candidates (enable_me_16x16 is always on)
         self.plane_dims = [(width, height), (width // 2, height // 2), (width // 2, height // 2)]
         self._build_tx_items()
         self._build_cdef()
@@ -120,9 +154,11 @@ class FrameWorkload:
         return planes[0] if self.bit_depth == 8 else (planes[0] >> (self.bit_depth - 8)).astype(np.uint8)
 
     def _set_pictures(self, seed):
-        seq = synth_sequence(self.width, self.height, self.n_refs + 1, seed, self.bit_depth)
-        self.cur = seq[1]
-        self.refs = [seq[0], seq[2]][:self.n_refs]
+        back, fwd = max(-d for d in ME_DIST[0][:self.n_ref[0]]), max((0,) + ME_DIST[1][:self.n_ref[1]])
+        seq = synth_sequence(self.width, self.height, back + fwd + 1, seed, self.bit_depth)
+        self.cur = seq[back]
+        # reference pictures in the order the ME call takes them: list 0 (nearest past first), then list 1 (nearest future first)
+        self.refs = [seq[back + d] for d in ME_DIST[0][:self.n_ref[0]]] + [seq[back + d] for d in ME_DIST[1][:self.n_ref[1]]]
         # prediction = the previous picture displaced by the sequence's global motion (the panorama pans (3, 1) luma
         # pixels per frame): an integer-pel motion-compensated inter prediction, edge-clamped like a padded reference.
         # Luma residual = the sensor noise of the two pictures; chroma keeps the half-pel mismatch of its (1.5, 0.5) motion.
@@ -328,7 +364,7 @@ class FrameWorkload:
         N = int(1.5 * W * H)  # samples = transform coefficients of the final pass
         calls = {
             "me_pyramid": int(1.3125 * W * H),                                    # full-res read + the two decimated levels written
-            "me_search": int((1 + R) * 1.3125 * W * H + n64 * R * 85 * 8),        # every pyramid read once + SAD/MV out
+            "me_search": int((1 + R) * 1.3125 * W * H + n64 * R * 85 * 8),        # every pyramid read once + SAD/MV per reference out
             "fwd_txfm": 6 * N, "quant": 12 * N, "inv_txfm": (4 + 2 * bpp) * N,    # (22 + 2 bpp) N in total
             "txfm_trio": (22 + 2 * bpp) * N,                                      # SURVEY 8(d)'s figure for the unfused chain
             # what the FUSED call has to move: source + prediction in, qcoeff + dqcoeff (4N each) + recon out

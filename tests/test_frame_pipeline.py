@@ -25,10 +25,10 @@ def test_frame_pipeline_matches_reference(b200, refc, case):
     fp = FramePipeline(FrameWorkload(w, h, bit_depth=bd, preset=m), torch)
     bench.check_against_reference(fp, torch)
     # size-independent property: a second pass over the same inputs is idempotent
-    a = fp.final.clone(), fp.qcoeff.clone(), fp.me_mv.clone()
+    a = fp.final.clone(), fp.qcoeff.clone(), fp.me["me_mv_array"].clone()
     fp.step()
     torch.cuda.synchronize()
-    assert torch.equal(a[0], fp.final) and torch.equal(a[1], fp.qcoeff) and torch.equal(a[2], fp.me_mv)
+    assert torch.equal(a[0], fp.final) and torch.equal(a[1], fp.qcoeff) and torch.equal(a[2], fp.me["me_mv_array"])
 
 
 def test_cdef_apply_recomputes_directions_when_none_given(b200, refc):
@@ -65,14 +65,15 @@ def test_two_frames_in_flight_on_two_streams(b200, refc):
     from svt_av1_psy_b200.workload import FrameWorkload
     fps = [FramePipeline(FrameWorkload(384, 256, seed=1234 + 7 * k), torch) for k in range(2)]
     streams = [torch.cuda.Stream(), torch.cuda.Stream()]
-    names = ("me_sad", "me_mv", "qcoeff", "eobs", "recon", "cdef_mse", "cdef_out", "M", "Hm", "final")
+    names = ("qcoeff", "eobs", "recon", "cdef_mse", "cdef_out", "M", "Hm", "final")
+    me_names = ("total_me_candidate_index", "me_candidate_array", "me_mv_array", "distortion", "best_sad")
     want = []
     for fp, st in zip(fps, streams):  # one at a time (also warms up every lazily allocated scratch)
         with torch.cuda.stream(st):
             fp.load_inputs()
             fp.step()
         torch.cuda.synchronize()
-        want.append([getattr(fp, n).clone() for n in names])
+        want.append([getattr(fp, n).clone() for n in names] + [fp.me[n].clone() for n in me_names])
     graphs = []
     for fp, st in zip(fps, streams):
         g = torch.cuda.CUDAGraph()
@@ -81,8 +82,10 @@ def test_two_frames_in_flight_on_two_streams(b200, refc):
         graphs.append(g)
     for rep in range(6):
         for fp in fps:
-            for n in ("qcoeff", "eobs", "cdef_mse", "M", "Hm", "final", "me_sad"):
+            for n in ("qcoeff", "eobs", "cdef_mse", "M", "Hm", "final"):
                 getattr(fp, n).zero_()
+            fp.me["me_mv_array"].zero_()
+            fp.me["best_sad"].zero_()
         torch.cuda.synchronize()
         for g, st in zip(graphs, streams):
             with torch.cuda.stream(st):
@@ -93,8 +96,8 @@ def test_two_frames_in_flight_on_two_streams(b200, refc):
                     fp.step()
         torch.cuda.synchronize()
         for fp, w in zip(fps, want):
-            for n, t in zip(names, w):
-                assert torch.equal(getattr(fp, n), t), (rep, n)
+            for n, t in zip(names + me_names, w):
+                assert torch.equal(getattr(fp, n) if n in names else fp.me[n], t), (rep, n)
 
 
 @pytest.mark.parametrize("name", ["frame_384x256", "frame_640x360", "frame_384x256_b10_m6", "frame_640x360_b10_m4"])
@@ -116,9 +119,10 @@ def test_frame_matches_committed_golden_fixture(b200, name):
 
     def digest(t):
         return hashlib.sha256(np.ascontiguousarray(t.cpu().numpy()).view(np.uint8).tobytes()).hexdigest()
-    got = {"me_sad": fp.me_sad, "me_mv": fp.me_mv, "hme_centre": fp.me_centre, "qcoeff": fp.qcoeff, "dqcoeff": fp.dqcoeff, "eob": fp.eobs,
+    got = {k: fp.me[f] for k, f in b200.ME_OUTPUT_NAMES.items()}
+    got.update({"qcoeff": fp.qcoeff, "dqcoeff": fp.dqcoeff, "eob": fp.eobs,
            "recon": fp.recon, "cdef_mse": fp.cdef_mse, "cdef_dir": fp.cdef_dir, "cdef_out": fp.cdef_out, "wiener_M": fp.M,
-           "wiener_H": fp.Hm, "final": fp.final}
+           "wiener_H": fp.Hm, "final": fp.final})
     bad = [k for k, t in got.items() if digest(t) != g["sha256"][k]]
     assert not bad, bad
     # the forward coefficients only exist on the 3-call transform chain
@@ -157,7 +161,7 @@ for rnd in range(3):
         fp.step()
     g.replay()
     torch.cuda.synchronize()
-    outs.append((int(fp.final.to(torch.int64).sum()), int(fp.me_sad.to(torch.int64).sum()), int(fp.Hm.sum())))
+    outs.append((int(fp.final.to(torch.int64).sum()), int(fp.me["distortion"].to(torch.int64).sum()), int(fp.Hm.sum())))
     del g, fp
     torch.cuda.synchronize()
     pkg.shutdown()

@@ -356,3 +356,18 @@ def test_port_lr_unit_with_stripe_boundaries_matches_reference(oracle, refc):
                     assert np.array_equal(src, plane)
                     outs.append(dst)
                 assert np.array_equal(outs[0], outs[1]), ("sgr", ss, opt, hs, he, vs, ve, ep)
+
+
+def test_me_controls_json_is_the_references_derivation(refc):
+    """svt-av1-psy_b200/me_controls.json (what the workload hands to svt_b200_me_b64_picture_dev) == svt_aom_sig_deriv_me of the
+    reference for every (preset, resolution class), re-derived here; and the two ctypes mirrors of the control struct agree"""
+    import importlib.util
+    import json
+    import os
+    from oracle import support as sp
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("dump_me_controls", os.path.join(root, "tools", "dump_me_controls.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    assert sp.ME_CONTROL_FIELDS == mod.layout.ME_CONTROL_FIELDS
+    assert mod.all_controls() == json.load(open(os.path.join(root, "svt-av1-psy_b200", "me_controls.json")))

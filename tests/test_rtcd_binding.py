@@ -110,9 +110,10 @@ def test_reference_process_loops_with_b200_pointers_match_c_goldens(b200, name):
     fr = RefFrame(wl, enc)
     fr.step()
     assert b200.launch_count() - l0 > 1000  # the work really went through libsvtav1_b200.so
-    outs = {"me_sad": fr.me_sad, "me_mv": fr.me_mv, "hme_centre": fr.me_c, "residual": fr.residual, "coeff": fr.coeff, "qcoeff": fr.q, "dqcoeff": fr.dq,
+    outs = {k: fr.me[f] for k, f in b200.ME_OUTPUT_NAMES.items()}
+    outs.update({"residual": fr.residual, "coeff": fr.coeff, "qcoeff": fr.q, "dqcoeff": fr.dq,
             "eob": fr.eobs, "recon": fr.recon, "cdef_mse": fr.mse, "cdef_dir": fr.dirs, "cdef_out": fr.cdef_out, "wiener_M": fr.M, "wiener_H": fr.Hm,
-            "final": fr.final}
+            "final": fr.final})
     # the residual kernel is not a B200 T1 pointer (it stays the reference's C function here): included because everything downstream reads it
     bad = [k for k, v in outs.items() if hashlib.sha256(np.ascontiguousarray(v).view(np.uint8).tobytes()).hexdigest() != g["sha256"][k]]
     assert not bad, bad

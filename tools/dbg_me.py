@@ -13,4 +13,4 @@ s = torch.cuda.current_stream().cuda_stream
 fp.call_me_pyramid(s)
 fp.call_me_search(s)
 torch.cuda.synchronize()
-print("me ok", int(fp.me_sad.sum()))
+print("me ok", int(fp.me["distortion"].sum()))

@@ -27,9 +27,10 @@ def golden_for(width, height, seed=20260923, bit_depth=8, preset=8):
     wl = load_workload_module().FrameWorkload(width, height, seed=seed, bit_depth=bit_depth, preset=preset)
     fr = RefFrame(wl, ref)
     fr.step()
-    outs = {"me_sad": fr.me_sad, "me_mv": fr.me_mv, "hme_centre": fr.me_c, "residual": fr.residual, "coeff": fr.coeff, "qcoeff": fr.q, "dqcoeff": fr.dq,
+    outs = {k: fr.me[f] for k, f in load_workload_module().dsp.ME_OUTPUT_NAMES.items()}
+    outs.update({"residual": fr.residual, "coeff": fr.coeff, "qcoeff": fr.q, "dqcoeff": fr.dq,
             "eob": fr.eobs, "recon": fr.recon, "cdef_mse": fr.mse, "cdef_dir": fr.dirs, "cdef_out": fr.cdef_out,
-            "wiener_M": fr.M, "wiener_H": fr.Hm, "final": fr.final}
+            "wiener_M": fr.M, "wiener_H": fr.Hm, "final": fr.final})
     return {"width": width, "height": height, "seed": seed, "bit_depth": bit_depth, "preset": preset, "reference_tier": "C (ref_set_tier(0))",
             "sha256": {k: digest(v) for k, v in outs.items()},
             "shape": {k: list(np.asarray(v).shape) for k, v in outs.items()}}
