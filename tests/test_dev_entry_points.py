@@ -71,7 +71,7 @@ def test_fullpel_search_batch_dev(b200, oracle):
             sa_w, sa_h, sub = cfgs[k % len(cfgs)]
             k += 1
             ox, oy = -(sa_w // 2) + (k % 5) - 2, -(sa_h // 2) + (k % 3) - 1
-            lst.append(((pad + by) * pitch + pad + bx, (pad + by + oy) * pitch + pad + bx + ox, pitch, pitch, sa_w, sa_h, ox, oy, sub, [0] * 7))
+            lst.append(((pad + by) * pitch + pad + bx, (pad + by + oy) * pitch + pad + bx + ox, pitch, pitch, sa_w, sa_h, ox, oy, sub, 0, 0, 0, [0, 0]))
     items = np.array(lst, dtype=b200.FULLPEL_ITEM_DTYPE)
     d_cur, d_ref, d_items = _dev(torch, cur), _dev(torch, refp), _dev(torch, items)
     d_sad = torch.zeros((len(items), 85), dtype=torch.int32, device="cuda")

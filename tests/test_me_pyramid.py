@@ -101,8 +101,8 @@ def test_fullpel_search_batch(b200, oracle):
         for bx in range(0, W, 64):
             sa_w, sa_h, sub = cfgs[k % len(cfgs)]; k += 1
             ox, oy = -(sa_w // 2) + (k % 5) - 2, -(sa_h // 2) + (k % 3) - 1
-            lst.append(((pad + by) * pitch + pad + bx, (pad + by + oy) * pitch + pad + bx + ox, pitch, pitch, sa_w, sa_h, ox, oy, sub,
-                        [0] * 7))
+            lst.append(((pad + by) * pitch + pad + bx, (pad + by + oy) * pitch + pad + bx + ox, pitch, pitch, sa_w, sa_h, ox, oy, sub, 0, 0, 0,
+                        [0, 0]))
     items = np.array(lst, dtype=b200.FULLPEL_ITEM_DTYPE)
     sad, mv = b200.fullpel_search_batch_host(cur, refp, items)
     for i, it in enumerate(items):
