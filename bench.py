@@ -229,6 +229,8 @@ def main():
     ap.add_argument("--check", action="store_true", help="compare one frame of B200 output with the reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--one-stream", action="store_true", help="all frames on one compute stream (no frame-level overlap)")
+    ap.add_argument("--e2e-copy-streams", action="store_true",
+                    help="end-to-end loop with dedicated copy-in / copy-out streams (default: a frame's copies ride on its own compute stream)")
     ap.add_argument("--streams", type=int, default=4, help="compute streams that consecutive frames alternate between (1, 2, 4 or 8)")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying one CUDA graph per step")
     ap.add_argument("--min-time", type=float, default=0.3, help="minimum length (s) of each timed region: the steps-long loop is repeated")
@@ -385,9 +387,10 @@ def main():
     d2h_level_bytes = [0, 0]  # bytes, frames
 
     def run_e2e(n):
-        """host buffers -> device -> host, every step; the three phases of consecutive frames overlap on
-        three streams (copy-in / compute / copy-out), ordered with events; a frame set is re-used only
-        after its previous results have been read back.  Results travel in two parts: the fixed-size outputs
+        """host buffers -> device -> host, every step: copy-in, graph replay and copy-out of a frame are enqueued back to back on
+        the frame's compute stream (consecutive frames use different streams, so the three phases of different frames overlap);
+        a frame set is re-used only after its previous results have been read back (same stream, later).  --e2e-copy-streams
+        uses dedicated copy streams ordered with events instead.  Results travel in two parts: the fixed-size outputs
         (with the level offsets), then -- D2H_LAG frames later, when the host knows sum(eob) -- exactly that many levels."""
         ev_in = [torch.cuda.Event() for _ in range(n)]
         ev_done = [torch.cuda.Event() for _ in range(n)]
@@ -406,6 +409,44 @@ def main():
 
         t_host = time.perf_counter()
         start.record(stream)
+        if not args.e2e_copy_streams:
+            # default: a frame's copy-in, its graph replay and its copy-out are enqueued on the frame's own compute stream (frames
+            # alternate between the compute streams, so the copies of one frame still overlap the kernels of the others); the host
+            # issues 3 library calls + 1 event per frame
+            def finish_frame(k):  # noqa: F811
+                ev_small[k].synchronize()  # host wait, but on work enqueued D2H_LAG frames ago: the pipeline stays full
+                cs = streams[k % n_streams]
+                d2h_level_bytes[0] += sets[k % N_FRAME_SETS].read_levels(cs.cuda_stream)
+                d2h_level_bytes[1] += 1
+            for x in streams[1:]:
+                x.wait_event(start)
+            if comm is not None:
+                comm.wait_event(start)
+            for i in range(n):
+                fp = sets[i % N_FRAME_SETS]
+                cs = streams[i % n_streams]
+                with torch.cuda.stream(cs):
+                    ex.before_step(i, cs)
+                    fp.load_inputs(cs.cuda_stream)
+                    enqueue_step(i)
+                    ex.after_step(i, cs, n)
+                    fp.read_outputs(cs.cuda_stream)
+                    ev_small[i].record(cs)
+                if i >= D2H_LAG:
+                    finish_frame(i - D2H_LAG)
+            for k in range(max(0, n - D2H_LAG), n):
+                finish_frame(k)
+            tail = torch.cuda.Event()
+            for x in streams[1:]:
+                tail.record(x)
+                stream.wait_event(tail)
+            ex.finish(stream)
+            end.record(stream)
+            host_enqueue[0] += time.perf_counter() - t_host
+            host_enqueue[1] += n
+            torch.cuda.synchronize()
+            return start.elapsed_time(end)
+        # --e2e-copy-streams: dedicated copy-in / copy-out streams, ordered with events (more host work per frame)
         s_in.wait_event(start)
         if comm is not None:
             comm.wait_event(start)

@@ -77,7 +77,9 @@ __device__ __forceinline__ unsigned long long sad_search_warp_w16(const uint8_t*
     while (gl < 32 && gl < units) gl <<= 1;
     const int groups = 32 / gl, grp = lane / gl, ul = lane - grp * gl;
     const unsigned grpmask = (gl == 32 ? 0xffffffffu : ((1u << gl) - 1u)) << (grp * gl);
-    const int xtiles = (sa_w + 7) >> 3, tiles = xtiles * sa_h;
+    // with line skipping only the odd search rows are evaluated (compute_sad_c.c:74-79): the tile walk visits just those
+    const int ny = skip ? (sa_h >> 1) : sa_h;
+    const int xtiles = (sa_w + 7) >> 3, tiles = xtiles * ny;
     const int c = ul & (chunks - 1), r_first = ul >> lgc, r_step = gl >> lgc;
     const uint8_t* src_u = src0 + (size_t)r_first * item.src_stride + 16 * c;  // this lane's first unit
     const uint8_t* ref_u = ref0 + (size_t)r_first * item.ref_stride + 16 * c;
@@ -86,10 +88,11 @@ __device__ __forceinline__ unsigned long long sad_search_warp_w16(const uint8_t*
     int y = 0, xt = grp;  // this group's tile, advanced by `groups` tiles per round
     while (xt >= xtiles) { xt -= xtiles; y++; }
     for (int t0 = 0; t0 < tiles; t0 += groups) {
-        const bool tile_on = y < sa_h;
-        const int  yy = tile_on ? y : sa_h - 1, x0 = (tile_on ? xt : 0) * 8;  // idle groups shadow a valid tile and drop the result
+        const bool tile_on = y < ny;
+        const int  yk = tile_on ? y : ny - 1, yy = skip ? 2 * yk + 1 : yk;  // idle groups shadow a valid tile and drop the result
+        const int  x0 = (tile_on ? xt : 0) * 8;
         const int  npos = min(8, sa_w - x0);
-        const bool line_on = !(skip && ((yy & 1) == 0));
+        const bool line_on = true;
         uint32_t   acc[8];
 #pragma unroll
         for (int i = 0; i < 8; i++) acc[i] = 0;
