@@ -76,7 +76,6 @@ __device__ __forceinline__ unsigned long long sad_search_warp_w16(const uint8_t*
     int gl = 1;
     while (gl < 32 && gl < units) gl <<= 1;
     const int groups = 32 / gl, grp = lane / gl, ul = lane - grp * gl;
-    const unsigned grpmask = (gl == 32 ? 0xffffffffu : ((1u << gl) - 1u)) << (grp * gl);
     // with line skipping only the odd search rows are evaluated (compute_sad_c.c:74-79): the tile walk visits just those
     const int ny = skip ? (sa_h >> 1) : sa_h;
     const int xtiles = (sa_w + 7) >> 3, tiles = xtiles * ny;
@@ -112,10 +111,43 @@ __device__ __forceinline__ unsigned long long sad_search_warp_w16(const uint8_t*
                 }
             }
         }
+        // Sum the 8 position accumulators over the lanes of the group.  Shuffle trees, not REDUX (__reduce_add_sync): measured on
+        // this GPU the one-instruction form costs several times a SHFL + IADD pair (profiles/README.md, CDEF search experiment).
+        // Lane distances >= 8 are plain butterflies; the last three steps halve the number of live accumulators each time
+        // (a lane keeps the half selected by its own lane bit and hands the other half over), so lane L ends up with the total of
+        // position L & 7: 7 shuffles instead of 24.
 #pragma unroll
-        for (int i = 0; i < 8; i++) {
-            const uint32_t a = __reduce_add_sync(grpmask, acc[i]);  // REDUX over the lanes of the group
-            if (tile_on && i < npos && line_on && a < 0xffffffu) {
+        for (int o = 16; o >= 8; o >>= 1) {
+            if (o < gl) {
+#pragma unroll
+                for (int i = 0; i < 8; i++) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
+            }
+        }
+        if (gl < 8) {  // blocks of fewer than 8 units (picture-edge slivers): groups of 1, 2 or 4 lanes, every lane ranks all 8 positions
+#pragma unroll
+            for (int o = 2; o >= 1; o >>= 1) {
+                if (o < gl) {
+#pragma unroll
+                    for (int i = 0; i < 8; i++) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                if (tile_on && i < npos && acc[i] < 0xffffffu) {
+                    const unsigned long long key = ((unsigned long long)acc[i] << 32) | ((unsigned long long)(uint32_t)yy << 16) | (unsigned long long)(uint32_t)(x0 + i);
+                    best = key < best ? key : best;
+                }
+            }
+        } else {
+            const bool b2 = lane & 4, b1 = lane & 2, b0 = lane & 1;
+            uint32_t   k4[4], k2[2];
+#pragma unroll
+            for (int i = 0; i < 4; i++) k4[i] = (b2 ? acc[i + 4] : acc[i]) + __shfl_xor_sync(0xffffffffu, b2 ? acc[i] : acc[i + 4], 4);
+#pragma unroll
+            for (int i = 0; i < 2; i++) k2[i] = (b1 ? k4[i + 2] : k4[i]) + __shfl_xor_sync(0xffffffffu, b1 ? k4[i] : k4[i + 2], 2);
+            const uint32_t a = (b0 ? k2[1] : k2[0]) + __shfl_xor_sync(0xffffffffu, b0 ? k2[0] : k2[1], 1);
+            const int      i = lane & 7;
+            if (tile_on && i < npos && a < 0xffffffu) {
                 const unsigned long long key = ((unsigned long long)a << 32) | ((unsigned long long)(uint32_t)yy << 16) | (unsigned long long)(uint32_t)(x0 + i);
                 best = key < best ? key : best;
             }
@@ -123,7 +155,7 @@ __device__ __forceinline__ unsigned long long sad_search_warp_w16(const uint8_t*
         xt += groups;
         while (xt >= xtiles) { xt -= xtiles; y++; }
     }
-    for (int o = 16; o >= gl && o > 0; o >>= 1) {  // the groups looked at different tiles
+    for (int o = 16; o > 0; o >>= 1) {  // every lane holds the best of its own position column / group: the minimum over the warp
         const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
         best = other < best ? other : best;
     }
