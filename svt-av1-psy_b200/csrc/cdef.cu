@@ -347,8 +347,7 @@ cdef_search_kernel(SvtB200CdefFrame f, const uint8_t* __restrict__ skip8x8, cons
     __shared__ unsigned s_ballot[2];
     __shared__ int                s_sv[kGChunk];          // the chunk's strength codes (-1 = not tested)
     __shared__ unsigned long long s_dist[kGChunk][64];    // per strength, per block: distortion
-    __shared__ unsigned int       s_blk[kGChunk][64][3];  // per strength, per block: luma sum_s, sum_s2, sum_sd (s = filtered); chroma [0] = sse
-    __shared__ unsigned int       s_src[64][2];           // per block: luma sum_d, sum_d2 of the source pixels (the same for every strength)
+    __shared__ unsigned int       s_blk[kGChunk][64][5];  // per strength, per block: luma sum_s, sum_d, sum_s2, sum_d2, sum_sd; chroma [0] = sse
     const int nhfb = (f.width + 63) >> 6, nvfb = (f.height + 63) >> 6, nfb = nhfb * nvfb;
     const int cs = f.bit_depth > 8 ? f.bit_depth - 8 : 0;
     const int w8 = (f.width + 7) >> 3, h8 = (f.height + 7) >> 3;
@@ -402,8 +401,7 @@ cdef_search_kernel(SvtB200CdefFrame f, const uint8_t* __restrict__ skip8x8, cons
         const int seg = min(ppb, 32);                          // lanes that share a block
         for (int g0 = 0; g0 < n_strengths; g0 += kGChunk) {
             const int ng = min(kGChunk, n_strengths - g0);
-            for (int i = threadIdx.x; i < kGChunk * 64 * 3; i += blockDim.x) (&s_blk[0][0][0])[i] = 0;
-            if (threadIdx.x < 128) (&s_src[0][0])[threadIdx.x] = 0;
+            for (int i = threadIdx.x; i < kGChunk * 64 * 5; i += blockDim.x) (&s_blk[0][0][0])[i] = 0;
             if ((int)threadIdx.x < ng) s_sv[threadIdx.x] = strengths[g0 + threadIdx.x];
             unsigned with_pri = 0, without_pri = 0;  // which strengths of the chunk have / lack a primary part
             bool     sec_without_pri = false;         // ... and whether any of the latter has a secondary part
@@ -421,20 +419,6 @@ cdef_search_kernel(SvtB200CdefFrame f, const uint8_t* __restrict__ skip8x8, cons
                 const uint16_t* in = tile + (3 + bsz * by + ri) * kTP + 8 + bsz * bx + j;
                 const unsigned int o = live ? (unsigned int)src[(size_t)(fbr * fbs + bsz * by + ri) * sstride + fbc * fbs + bsz * bx + j] : 0u;
                 const int x = in[0], var = s_var[b], dirb = s_dir[b];
-                // block sums over the seg lanes that share a block (seg is 16 or 32): shuffle trees -- measured here, the one-instruction
-                // REDUX form (__reduce_add_sync) is slower for these (cdef_search 92.6 -> 100.8 us under ncu at 1080p)
-                auto seg_sum = [&](unsigned int v) {
-                    for (int sh = seg >> 1; sh > 0; sh >>= 1) v += __shfl_xor_sync(0xffffffffu, v, sh);
-                    return v;
-                };
-                const bool leader = live && (idx & (seg - 1)) == 0;
-                if (pli == 0) {  // the source-only moments do not depend on the strength: once per pixel
-                    const unsigned int od = seg_sum(o), od2 = seg_sum(o * o);
-                    if (leader) {
-                        atomicAdd(&s_src[bi][0], od);
-                        atomicAdd(&s_src[bi][1], od2);
-                    }
-                }
 #pragma unroll 1
                 for (int pass = 0; pass < 2; pass++) {
                     const unsigned todo = pass ? without_pri : with_pri;
@@ -471,18 +455,28 @@ cdef_search_kernel(SvtB200CdefFrame f, const uint8_t* __restrict__ skip8x8, cons
                         }
                         const unsigned int y = live ? (unsigned int)(taps ? cdef_finish_px(T, x, psum + ssum) : x) : 0u;
                         if (pli == 0) {
-                            // three strength-dependent moments of the block (<= 64 pixels of <= 12 bits: fit 32 bits)
-                            const unsigned int ss = seg_sum(y), s2 = seg_sum(y * y), sdp = seg_sum(y * o);
-                            if (leader) {
+                            // five moments of the block (<= 64 pixels of <= 12 bits: fit 32 bits)
+                            unsigned int ss = y, sdv = o, s2 = y * y, d2 = o * o, sdp = y * o;
+                            for (int sh = seg >> 1; sh > 0; sh >>= 1) {
+                                ss += __shfl_xor_sync(0xffffffffu, ss, sh);
+                                sdv += __shfl_xor_sync(0xffffffffu, sdv, sh);
+                                s2 += __shfl_xor_sync(0xffffffffu, s2, sh);
+                                d2 += __shfl_xor_sync(0xffffffffu, d2, sh);
+                                sdp += __shfl_xor_sync(0xffffffffu, sdp, sh);
+                            }
+                            if (live && (idx & (seg - 1)) == 0) {
                                 unsigned int* sb = s_blk[gi][bi];
                                 atomicAdd(sb + 0, ss);
-                                atomicAdd(sb + 1, s2);
-                                atomicAdd(sb + 2, sdp);
+                                atomicAdd(sb + 1, sdv);
+                                atomicAdd(sb + 2, s2);
+                                atomicAdd(sb + 3, d2);
+                                atomicAdd(sb + 4, sdp);
                             }
                         } else {
                             const int e = (int)o - (int)y;
-                            const unsigned int se = seg_sum((unsigned int)(e * e));  // a block's 16 pixels of <= 12 bits: fits 32 bits
-                            if (leader && se) atomicAdd(&s_blk[gi][bi][0], se);
+                            unsigned int se = (unsigned int)(e * e);  // a block's 16 pixels of <= 12 bits: fits 32 bits
+                            for (int sh = seg >> 1; sh > 0; sh >>= 1) se += __shfl_xor_sync(0xffffffffu, se, sh);
+                            if (live && (idx & (seg - 1)) == 0 && se) atomicAdd(&s_blk[gi][bi][0], se);
                         }
                     }
                 }
@@ -492,7 +486,7 @@ cdef_search_kernel(SvtB200CdefFrame f, const uint8_t* __restrict__ skip8x8, cons
             for (int q = threadIdx.x; q < ng * count; q += blockDim.x) {
                 const int gi = q / count, bi = q - gi * count;
                 const unsigned int* sb = s_blk[gi][bi];
-                s_dist[gi][bi] = pli == 0 ? cdef_dist_from_sums(sb[0], s_src[bi][0], sb[1], s_src[bi][1], sb[2], cs) : (unsigned long long)sb[0];
+                s_dist[gi][bi] = pli == 0 ? cdef_dist_from_sums(sb[0], sb[1], sb[2], sb[3], sb[4], cs) : (unsigned long long)sb[0];
             }
             __syncthreads();
             if ((int)threadIdx.x < ng) {
