@@ -122,14 +122,15 @@ __device__ __forceinline__ void clip_window(int16_t org, int16_t& o, int16_t& sa
     if (round8) sa = (sa < 8) ? sa : (int16_t)(sa & ~0x07);
 }
 
-__global__ void __launch_bounds__(128)
+template <int PAR>  // references whose HME runs concurrently in a CTA (4 warps each)
+__global__ void __launch_bounds__(128 * PAR, PAR == 1 ? 4 : 3)
 me_b64_hme_kernel(const __grid_constant__ MeB64Table tab, int n_b64, int b64_w, SvtB200FullpelItem* __restrict__ items,
                   uint32_t* __restrict__ seed_sad, uint8_t* __restrict__ st_do_ref /*[n_b64][8]*/, int16_t* __restrict__ out_centre,
                   uint32_t* __restrict__ out_zz) {
     __shared__ B64State s;
     const SvtB200MeControls& c = tab.c;
     const SvtB200MePicture&  cur = tab.cur;
-    const int b = blockIdx.x, bx = b % b64_w, by = b / b64_w, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.x, bx = b % b64_w, by = b / b64_w, warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n_warps = blockDim.x >> 5;
     const int W = cur.width[2], H = cur.height[2];
     const int16_t org_x = (int16_t)(bx * 64), org_y = (int16_t)(by * 64);
     // me_ctx->b64_width / b64_height come from the 8-aligned picture size (:3093-3100)
@@ -163,7 +164,7 @@ me_b64_hme_kernel(const __grid_constant__ MeB64Table tab, int n_b64, int b64_w, 
 
     // ---- init_zz_sad -------------------------------------------------------------------------------------------------
     if (c.me_early_exit_th || c.me_safe_limit_zz_th) {
-        for (int p = warp; p < n_pairs; p += 4) {
+        for (int p = warp; p < n_pairs; p += n_warps) {
             const int l = pair_l(p), r = pair_r(p);
             if (!searched(c, l)) continue;
             const SvtB200MePicture& rp = tab.ref[l][r];
@@ -199,7 +200,7 @@ me_b64_hme_kernel(const __grid_constant__ MeB64Table tab, int n_b64, int b64_w, 
     if (c.prehme_enable) {
         const int max_r = max(c.n_ref[0], c.n_list > 1 ? c.n_ref[1] : 0);
         // unit = (reference index, search region); the warp walks list 0 then list 1 of its unit: list 1 may copy list 0's result
-        for (int u = warp; u < max_r * 2; u += 4) {
+        for (int u = warp; u < max_r * 2; u += n_warps) {
             const int r = u >> 1, sr = u & 1;
             for (int l = 0; l < c.n_list; l++) {
                 if (r >= c.n_ref[l]) continue;
@@ -287,82 +288,99 @@ me_b64_hme_kernel(const __grid_constant__ MeB64Table tab, int n_b64, int b64_w, 
         __syncthreads();
     }
 
-    // ---- HME level 0 / 1 / 2: warp = search region, references in order ---------------------------------------------------
+    // ---- HME level 0 / 1 / 2: warp = (reference, search region); `par` references at a time, in order ------------------------------
+    // (the only coupling between references inside these stages is the low-delay "reduce_hme_l0_sr" rule, which reads the level-0
+    //  centre of list 0 / reference 0: with it on, the references go one at a time)
     if (c.enable_hme) {
-        const int reg = warp;
-        for (int p = 0; p < n_pairs; p++) {
-            const int l = pair_l(p), r = pair_r(p);
+        const bool coupled = c.sr_enable && c.sr_distance_based_hme_resizing && c.reduce_hme_l0_sr_th_min && c.reduce_hme_l0_sr_th_max;
+        const int  par = coupled ? 1 : max(1, n_warps >> 2), reg = warp & 3;
+        // which branch of hme_level0_b64 a reference takes: 0 zz exit, 1 previous-stage exit, 2 pruned, 3 search, 4 not searched (base layer, list 1)
+        auto l0_kind = [&](int li, int ri) {
+            const int sr_i = s.ph_sad[li][ri][0] <= s.ph_sad[li][ri][1] ? 0 : 1;
+            if (c.me_early_exit_th && s.zz[li][ri] < ((uint32_t)c.me_early_exit_th >> 2)) return 0;
+            if (c.prev_me_stage_based_exit_th && s.ph_done[li][ri][sr_i] && s.ph_sad[li][ri][sr_i] < ((uint32_t)c.prev_me_stage_based_exit_th >> 4)) return 1;
+            if (!s.do_ref[li][ri]) return 2;
+            return searched(c, li) ? 3 : 4;
+        };
+        for (int p0 = 0; p0 < n_pairs; p0 += par) {
+            const int  p = p0 + (warp >> 2);
+            const bool on = (warp >> 2) < par && p < n_pairs;
+            const int  l = on ? pair_l(p) : 0, r = on ? pair_r(p) : 0;
             const SvtB200MePicture& rp = tab.ref[l][r];
             SvtB200MeParams prm;
             prm.hme_l1_sa_w = c.hme_l1_w; prm.hme_l1_sa_h = c.hme_l1_h; prm.hme_l2_sa_w = c.hme_l2_w; prm.hme_l2_sa_h = c.hme_l2_h;
             prm.hme_sub_sad = c.hme_sub_sad; prm.me_sub_sad = c.me_sub_sad; prm.check_zero_centre = 0; prm.reserved = 0;
             prm.me_sa_w = prm.me_sa_h = 0;
             prm.hme_l0_sa_w = prm.hme_l0_sa_h = 0;
-            const bool zz_exit = c.me_early_exit_th && s.zz[l][r] < ((uint32_t)c.me_early_exit_th >> 2);
+            const bool zz_exit = on && c.me_early_exit_th && s.zz[l][r] < ((uint32_t)c.me_early_exit_th >> 2);
             // ---- level 0 (hme_level0_b64)
             if (c.enable_l0) {
-                bool l0_search = false;
-                const int sr_i = s.ph_sad[l][r][0] <= s.ph_sad[l][r][1] ? 0 : 1;
-                if (zz_exit) {
-                    if (lane == 0) { s.lx[0][l][r][reg] = s.ly[0][l][r][reg] = 0; s.lsad[0][l][r][reg] = 0; }
-                } else if (c.prev_me_stage_based_exit_th && s.ph_done[l][r][sr_i] &&
-                           s.ph_sad[l][r][sr_i] < ((uint32_t)c.prev_me_stage_based_exit_th >> 4)) {
-                    if (lane == 0) { s.lx[0][l][r][reg] = s.ph_x[l][r][sr_i]; s.ly[0][l][r][reg] = s.ph_y[l][r][sr_i]; s.lsad[0][l][r][reg] = s.ph_sad[l][r][sr_i]; }
-                } else if (!s.do_ref[l][r]) {
-                    if (lane == 0) { s.lx[0][l][r][reg] = s.ly[0][l][r][reg] = 0; s.lsad[0][l][r][reg] = kMaxU32; }
-                } else if (searched(c, l)) {
-                    l0_search = true;
-                    // get_hme_l0_search_area
-                    int min_w = c.hme_l0_min_w, min_h = c.hme_l0_min_h, max_w = c.hme_l0_max_w, max_h = c.hme_l0_max_h;
-                    if (c.sr_enable && c.sr_distance_based_hme_resizing) {
-                        bool is_hor = true, is_ver = true, is_still = false;
-                        if (c.reduce_hme_l0_sr_th_min && c.reduce_hme_l0_sr_th_max && (l || r)) {
-                            const int mx = abs((int)s.lx[0][0][0][0]), my = abs((int)s.ly[0][0][0][0]);
-                            is_ver   = mx < c.reduce_hme_l0_sr_th_min && my > c.reduce_hme_l0_sr_th_max;
-                            is_hor   = mx > c.reduce_hme_l0_sr_th_max && my < c.reduce_hme_l0_sr_th_min;
-                            is_still = mx < c.reduce_hme_l0_sr_th_min * 3 && my < c.reduce_hme_l0_sr_th_min * 3;
+                if (on) {
+                    const int kind = l0_kind(l, r);
+                    const int sr_i = s.ph_sad[l][r][0] <= s.ph_sad[l][r][1] ? 0 : 1;
+                    if (kind == 0) {
+                        if (lane == 0) { s.lx[0][l][r][reg] = s.ly[0][l][r][reg] = 0; s.lsad[0][l][r][reg] = 0; }
+                    } else if (kind == 1) {
+                        if (lane == 0) { s.lx[0][l][r][reg] = s.ph_x[l][r][sr_i]; s.ly[0][l][r][reg] = s.ph_y[l][r][sr_i]; s.lsad[0][l][r][reg] = s.ph_sad[l][r][sr_i]; }
+                    } else if (kind == 2) {
+                        if (lane == 0) { s.lx[0][l][r][reg] = s.ly[0][l][r][reg] = 0; s.lsad[0][l][r][reg] = kMaxU32; }
+                    } else if (kind == 3) {
+                        // get_hme_l0_search_area
+                        int min_w = c.hme_l0_min_w, min_h = c.hme_l0_min_h, max_w = c.hme_l0_max_w, max_h = c.hme_l0_max_h;
+                        if (c.sr_enable && c.sr_distance_based_hme_resizing) {
+                            bool is_hor = true, is_ver = true, is_still = false;
+                            if (c.reduce_hme_l0_sr_th_min && c.reduce_hme_l0_sr_th_max && (l || r)) {
+                                const int mx = abs((int)s.lx[0][0][0][0]), my = abs((int)s.ly[0][0][0][0]);
+                                is_ver   = mx < c.reduce_hme_l0_sr_th_min && my > c.reduce_hme_l0_sr_th_max;
+                                is_hor   = mx > c.reduce_hme_l0_sr_th_max && my < c.reduce_hme_l0_sr_th_min;
+                                is_still = mx < c.reduce_hme_l0_sr_th_min * 3 && my < c.reduce_hme_l0_sr_th_min * 3;
+                            }
+                            int x_off = is_hor ? 1 : 2, y_off = is_ver ? 1 : 2;
+                            if (c.sr_enable == 2 && is_still) x_off = y_off = 4;
+                            min_w = (uint16_t)(min_w / (x_off + r)); min_h = (uint16_t)(min_h / (y_off + r));
+                            max_w = (uint16_t)(max_w / (x_off + r)); max_h = (uint16_t)(max_h / (y_off + r));
                         }
-                        int x_off = is_hor ? 1 : 2, y_off = is_ver ? 1 : 2;
-                        if (c.sr_enable == 2 && is_still) x_off = y_off = 4;
-                        min_w = (uint16_t)(min_w / (x_off + r)); min_h = (uint16_t)(min_h / (y_off + r));
-                        max_w = (uint16_t)(max_w / (x_off + r)); max_h = (uint16_t)(max_h / (y_off + r));
+                        const int f = scaled_distance(c.dist[l][r]);
+                        int16_t sa_w = (int16_t)(min_w / 2);
+                        sa_w = (int16_t)min(((sa_w * f) + 15) & ~0x0F, ((max_w / 2) + 15) & ~0x0F);
+                        int16_t sa_h = (int16_t)(min_h / 2);
+                        sa_h = (int16_t)min(sa_h * f, max_h / 2);
+                        prm.hme_l0_sa_w = sa_w;
+                        prm.hme_l0_sa_h = sa_h;
+                        SvtB200SadSearchItem it;
+                        HmeSide              sd;
+                        hme_make_item(cur, rp, prm, 0, reg & 1, reg >> 1, bx, by, 0, 0, it, sd);
+                        const SvtB200SadSearchResult q =
+                            sad_key_to_result(sad_search_warp((const uint8_t*)(uintptr_t)it.src_off, (const uint8_t*)(uintptr_t)it.ref_off, it, lane));
+                        int16_t  x, y;
+                        uint64_t sad;
+                        hme_finish_one(q, sd, prm, 0, x, y, sad);
+                        if (lane == 0) { s.lx[0][l][r][reg] = x; s.ly[0][l][r][reg] = y; s.lsad[0][l][r][reg] = sad; }
                     }
-                    const int f = scaled_distance(c.dist[l][r]);
-                    int16_t sa_w = (int16_t)(min_w / 2);
-                    sa_w = (int16_t)min(((sa_w * f) + 15) & ~0x0F, ((max_w / 2) + 15) & ~0x0F);
-                    int16_t sa_h = (int16_t)(min_h / 2);
-                    sa_h = (int16_t)min(sa_h * f, max_h / 2);
-                    prm.hme_l0_sa_w = sa_w;
-                    prm.hme_l0_sa_h = sa_h;
-                    SvtB200SadSearchItem it;
-                    HmeSide              sd;
-                    hme_make_item(cur, rp, prm, 0, reg & 1, reg >> 1, bx, by, 0, 0, it, sd);
-                    const SvtB200SadSearchResult q =
-                        sad_key_to_result(sad_search_warp((const uint8_t*)(uintptr_t)it.src_off, (const uint8_t*)(uintptr_t)it.ref_off, it, lane));
-                    int16_t  x, y;
-                    uint64_t sad;
-                    hme_finish_one(q, sd, prm, 0, x, y, sad);
-                    if (lane == 0) { s.lx[0][l][r][reg] = x; s.ly[0][l][r][reg] = y; s.lsad[0][l][r][reg] = sad; }
                 }
-                __syncthreads();  // the four regions' level-0 results are complete (every branch above is uniform over the CTA)
-                if (l0_search && c.prehme_enable) {  // replace the worst quadrant by the better pre-HME result
-                    if (threadIdx.x == 0) {
-                        uint64_t mx = 0;
-                        int      worst = 0;
-                        for (int g = 0; g < 3; g++)
-                            if (s.lsad[0][l][r][g] > mx) { mx = s.lsad[0][l][r][g]; worst = g; }
-                        if (s.lsad[0][l][r][3] > mx) worst = 3;
-                        if (s.ph_sad[l][r][sr_i] < s.lsad[0][l][r][worst]) {
-                            s.lsad[0][l][r][worst] = s.ph_sad[l][r][sr_i];
-                            s.lx[0][l][r][worst] = s.ph_x[l][r][sr_i];
-                            s.ly[0][l][r][worst] = s.ph_y[l][r][sr_i];
+                __syncthreads();  // the four regions' level-0 results of these references are complete
+                if (c.prehme_enable) {  // replace the worst quadrant of a searched reference by its better pre-HME result
+                    if ((int)threadIdx.x < par && p0 + (int)threadIdx.x < n_pairs) {
+                        const int li = pair_l(p0 + threadIdx.x), ri = pair_r(p0 + threadIdx.x);
+                        if (l0_kind(li, ri) == 3) {
+                            const int sr_i = s.ph_sad[li][ri][0] <= s.ph_sad[li][ri][1] ? 0 : 1;
+                            uint64_t  mx = 0;
+                            int       worst = 0;
+                            for (int g = 0; g < 3; g++)
+                                if (s.lsad[0][li][ri][g] > mx) { mx = s.lsad[0][li][ri][g]; worst = g; }
+                            if (s.lsad[0][li][ri][3] > mx) worst = 3;
+                            if (s.ph_sad[li][ri][sr_i] < s.lsad[0][li][ri][worst]) {
+                                s.lsad[0][li][ri][worst] = s.ph_sad[li][ri][sr_i];
+                                s.lx[0][li][ri][worst] = s.ph_x[li][ri][sr_i];
+                                s.ly[0][li][ri][worst] = s.ph_y[li][ri][sr_i];
+                            }
                         }
                     }
                     __syncthreads();
                 }
             }
             // ---- level 1 (hme_level1_b64)
-            if (c.enable_l1 && searched(c, l)) {
+            if (on && c.enable_l1 && searched(c, l)) {
                 if (zz_exit) {
                     if (lane == 0) { s.lx[1][l][r][reg] = s.ly[1][l][r][reg] = 0; s.lsad[1][l][r][reg] = 0; }
                 } else if (!s.do_ref[l][r]) {
@@ -383,7 +401,7 @@ me_b64_hme_kernel(const __grid_constant__ MeB64Table tab, int n_b64, int b64_w, 
                 __syncwarp();
             }
             // ---- level 2 (hme_level2_b64): no early exit, pruned references are searched as well
-            if (c.enable_l2 && searched(c, l)) {
+            if (on && c.enable_l2 && searched(c, l)) {
                 if (c.prev_me_stage_based_exit_th && s.lsad[1][l][r][reg] < ((uint32_t)c.prev_me_stage_based_exit_th >> 2)) {
                     if (lane == 0) { s.lx[2][l][r][reg] = s.lx[1][l][r][reg]; s.ly[2][l][r][reg] = s.ly[1][l][r][reg]; s.lsad[2][l][r][reg] = s.lsad[1][l][r][reg]; }
                 } else {
@@ -453,7 +471,7 @@ me_b64_hme_kernel(const __grid_constant__ MeB64Table tab, int n_b64, int b64_w, 
     __syncthreads();
 
     // ---- integer_search_b64: the search window of every live reference; warp = reference ------------------------------------------
-    for (int p = warp; p < n_pairs; p += 4) {
+    for (int p = warp; p < n_pairs; p += n_warps) {
         const int l = pair_l(p), r = pair_r(p);
         const SvtB200MePicture& rp = tab.ref[l][r];
         const size_t item_idx = (size_t)p * n_b64 + b;
@@ -803,7 +821,12 @@ extern "C" int svt_b200_me_b64_picture_dev(const SvtB200MePicture* cur, const Sv
     B200_CUDA_CHECK(cudaMemsetAsync(out->total_me_candidate_index, 0, (size_t)n_b64 * n_pu, st));
     B200_CUDA_CHECK(cudaMemsetAsync(out->me_candidate_array, 0, (size_t)n_b64 * n_pu * c.max_cand, st));
     B200_CUDA_CHECK(cudaMemsetAsync(out->me_mv_array, 0, (size_t)n_b64 * n_pu * c.max_refs * 4, st));
-    me_b64_hme_kernel<<<n_b64, 128, 0, st>>>(tab, n_b64, b64_w, w->items, w->seed, w->do_ref, out->hme_centre, out->zz_sad);
+    // two references of a block in flight per CTA pays off with many references (measured: 7 references at 2160p M4, ME call
+    // 1.025 -> 0.954 ms) and costs with few (4 references at 1080p M8: 0.125 -> 0.156 ms): profiles/README.md
+    if (n_refs >= 6)
+        me_b64_hme_kernel<2><<<n_b64, 256, 0, st>>>(tab, n_b64, b64_w, w->items, w->seed, w->do_ref, out->hme_centre, out->zz_sad);
+    else
+        me_b64_hme_kernel<1><<<n_b64, 128, 0, st>>>(tab, n_b64, b64_w, w->items, w->seed, w->do_ref, out->hme_centre, out->zz_sad);
     B200_LAUNCH_CHECK();
     if (!launch_fullpel_tma(cur, refs, n_refs, n_b64, w->items, pairs, out->best_sad, out->best_mv, st, w->seed)) {
         fprintf(stderr, "[svt_b200] svt_b200_me_b64_picture_dev: the luma planes do not meet the layout rule (16-byte aligned base and pitch)\n");
