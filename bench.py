@@ -576,7 +576,7 @@ def main():
                    "host_enqueue_ms_per_step": round(1e3 * host_enqueue[0] / max(1, host_enqueue[1]), 4)},
            "gpu_launches": int(round(launches_per_step * args.steps)), "gpu_launches_per_step": round(launches_per_step, 1),
            # serial sum of the per-call medians (the eager loop's wall time also holds one-off first-launch costs)
-           "eager_ms_per_step": round(sum(call_ms) / prof_steps, 4), "eager_loop_ms_per_step": round(ms_eager / prof_steps, 4), "roofline": roofline,
+           "eager_ms_per_step": round(sum(call_ms), 4), "eager_loop_ms_per_step": round(ms_eager / prof_steps, 4), "roofline": roofline,
            "stages_ms": {n: round(v, 4) for n, v in zip(names, stage_ms)},
            "calls_ms": {c[0]: round(v, 4) for c, v in zip(calls, call_ms)},
            "calls_algorithmic_gbs": {c[0]: round(alg[c[0]] / (v / 1e3) / 1e9, 2) for c, v in zip(calls, call_ms) if v > 0}}
