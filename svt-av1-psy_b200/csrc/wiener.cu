@@ -11,11 +11,8 @@
 //
 // B200 mapping of the statistics (the one dense contraction on the path):
 //   8-bit pixels -> stats_mma_kernel: exact f16 x f16 -> f32 tensor-core MMA (see the comment above it);
-//   10/12-bit    -> stats_accum_kernel: a warp walks DOWN one pixel column; lane (a,b), a<=b, owns the 7x7
-//   tile of H that pairs window column a with window column b and keeps the two 7-pixel vertical strips
-//   in registers as a sliding window -- 2 loads feed 49 multiply-accumulates per pixel; products are
-//   accumulated in int32 for as many pixels as cannot overflow, then flushed to int64.
-// Both write per-CTA int64 partials; stats_finalize_kernel adds them, mirrors the triangle and applies
+//   10/12-bit    -> the lag-sum kernels of wiener_stats_lag.cuh (H[p][q] depends only on the lag between the two samples).
+// The MMA kernel writes per-CTA int64 partials; stats_finalize_kernel adds them, mirrors the triangle and applies
 // the bit-depth divider.
 #include <cuda_fp16.h>
 
@@ -86,159 +83,10 @@ __device__ __forceinline__ int stats_average(const unsigned long long* tot, int 
     return (int)(tot[it] / (unsigned long long)((s.h_end - s.h_start) * (s.v_end - s.v_start)));
 }
 
-constexpr int kStatsWarps = 8;
 constexpr int kStatsMaxParts = 32;  // CTAs cooperating on one restoration unit
-constexpr int kStatsTileW = 32, kStatsTileH = 64, kStatsPitch = kStatsTileW + 6 + 2;
 
 // partial layout per (item, part): [0, 49*49) = H (upper-triangle tiles only), [2401, 2450) = M
 //
-// Data path is always the 7x7 geometry: a 5x5 (3x3) window is the centre of the 7x7 one, so the
-// lanes of a narrower window simply own the centred column pairs and only the centred 5 (3) strip
-// rows are flushed.  The row loop is unrolled by 7 so that the sliding strips live in a register
-// ring with compile-time indices -- the loop body is branch-free straight-line IMADs.
-template <typename PIX>
-__global__ void __launch_bounds__(kStatsWarps * 32)
-stats_accum_kernel(const PIX* __restrict__ dgd_base, const PIX* __restrict__ src_base, const SvtB200StatsItem* __restrict__ items,
-                   const unsigned long long* __restrict__ tot_in, int ctas_per_item, long long* __restrict__ partial, int flush_pixels) {
-    __shared__ unsigned long long s_acc[2450];
-    __shared__ int16_t s_d[(kStatsTileH + 6) * kStatsPitch];
-    __shared__ int16_t s_x[kStatsTileH * kStatsTileW];
-    const int it = blockIdx.x / ctas_per_item, part = blockIdx.x % ctas_per_item;
-    const SvtB200StatsItem s = items[it];
-    const int win = s.wiener_win, off = (7 - win) >> 1, win2 = win * win;  // off: first physical row/column of the window
-    const int avg = stats_average(tot_in, it, s);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int i = threadIdx.x; i < 2450; i += blockDim.x) s_acc[i] = 0;
-    __syncthreads();
-    // lane -> logical column pair (a, b), a <= b < win; idle lanes shadow pair (0,0) and never flush
-    int a = 0, b = 0;
-    bool live = false;
-    {
-        int t = lane;
-        for (int aa = 0; aa < win && !live; aa++) {
-            const int cnt = win - aa;
-            if (t < cnt) { a = aa; b = aa + t; live = true; }
-            else t -= cnt;
-        }
-    }
-    const bool diag = live && a == b;
-    const int pa = a + off, pb = b + off;  // physical columns inside the 7-wide strip
-    int hacc[49], macc[7];
-#pragma unroll
-    for (int i = 0; i < 49; i++) hacc[i] = 0;
-#pragma unroll
-    for (int i = 0; i < 7; i++) macc[i] = 0;
-    const PIX* dgd = dgd_base + s.dgd_off;
-    const PIX* src = src_base + s.src_off;
-    int pending = 0;
-    // int32 partial sums -> the CTA's int64 totals in shared memory (8 warps contend at most)
-    auto flush = [&]() {
-#pragma unroll
-        for (int l1 = 0; l1 < 7; l1++)
-#pragma unroll
-            for (int l2 = 0; l2 < 7; l2++) {
-                const int q1 = l1 - off, q2 = l2 - off;  // logical strip rows
-                if (live && q1 >= 0 && q1 < win && q2 >= 0 && q2 < win && hacc[l1 * 7 + l2])
-                    atomicAdd(&s_acc[(a * win + q1) * win2 + (b * win + q2)], (unsigned long long)(long long)hacc[l1 * 7 + l2]);
-                hacc[l1 * 7 + l2] = 0;
-            }
-#pragma unroll
-        for (int l1 = 0; l1 < 7; l1++) {
-            const int q1 = l1 - off;
-            if (diag && q1 >= 0 && q1 < win && macc[l1]) atomicAdd(&s_acc[2401 + a * win + q1], (unsigned long long)(long long)macc[l1]);
-            macc[l1] = 0;
-        }
-        pending = 0;
-    };
-    const int W = s.h_end - s.h_start;
-    for (int g = part; g * kStatsTileW < W; g += ctas_per_item) {
-        const int c0 = s.h_start + g * kStatsTileW, ncols = min(kStatsTileW, s.h_end - c0);
-        for (int r0 = s.v_start; r0 < s.v_end; r0 += kStatsTileH) {
-            const int nrows = min(kStatsTileH, s.v_end - r0);
-            __syncthreads();
-            // rows r0-3 .. r0+nrows+2, columns c0-3 .. c0+ncols+2 as (pixel - avg); nothing outside the window the reference
-            // itself reads (half = win / 2 pixels around the unit) is touched -- a caller's buffer ends there
-            {
-                const int hw = s.wiener_win >> 1;
-                const int vlo = s.v_start - hw, vhi = s.v_end + hw, hlo = s.h_start - hw, hhi = s.h_end + hw;
-                for (int t = threadIdx.x; t < (nrows + 6) * (ncols + 6); t += blockDim.x) {
-                    const int rr = t / (ncols + 6), cc = t - rr * (ncols + 6);
-                    const int row = r0 - 3 + rr, col = c0 - 3 + cc;
-                    const bool in = row >= vlo && row < vhi && col >= hlo && col < hhi;
-                    s_d[rr * kStatsPitch + cc] = in ? (int16_t)((int)dgd[(ptrdiff_t)row * s.dgd_stride + col] - avg) : (int16_t)0;
-                }
-            }
-            for (int t = threadIdx.x; t < nrows * ncols; t += blockDim.x) {
-                const int rr = t / ncols, cc = t - rr * ncols;
-                s_x[rr * kStatsTileW + cc] = (int16_t)((int)src[(ptrdiff_t)(r0 + rr) * s.src_stride + c0 + cc] - avg);
-            }
-            __syncthreads();
-            for (int k = 0; k < kStatsTileW / kStatsWarps; k++) {
-                const int cw = warp * (kStatsTileW / kStatsWarps) + k;
-                if (cw >= ncols) break;  // warp-uniform
-                if (pending + nrows > flush_pixels) flush();
-                pending += nrows;
-                const int16_t* da = s_d + cw + pa;
-                const int16_t* db = s_d + cw + pb;
-                const int16_t* dx = s_x + cw;
-                // register ring: slot (r mod 7) holds tile row r
-                int ra[7], rb[7];
-#pragma unroll
-                for (int l = 0; l < 6; l++) {
-                    ra[l] = da[l * kStatsPitch];
-                    rb[l] = db[l * kStatsPitch];
-                }
-                ra[6] = rb[6] = 0;
-                int i0 = 0;
-                for (; i0 + 7 <= nrows; i0 += 7) {
-#pragma unroll
-                    for (int t = 0; t < 7; t++) {
-                        // pixel row i0+t uses tile rows i0+t .. i0+t+6; the new one goes to slot (t+6) % 7
-                        ra[(t + 6) % 7] = da[(i0 + t + 6) * kStatsPitch];
-                        rb[(t + 6) % 7] = db[(i0 + t + 6) * kStatsPitch];
-                        const int x = dx[(i0 + t) * kStatsTileW];
-#pragma unroll
-                        for (int l1 = 0; l1 < 7; l1++) {
-#pragma unroll
-                            for (int l2 = 0; l2 < 7; l2++) hacc[l1 * 7 + l2] += ra[(t + l1) % 7] * rb[(t + l2) % 7];
-                            macc[l1] += ra[(t + l1) % 7] * x;
-                        }
-                    }
-                }
-                // tail (< 7 rows): same arithmetic with a shifting strip
-                if (i0 < nrows) {
-                    int ya[7], yb[7];
-#pragma unroll
-                    for (int l = 0; l < 6; l++) {
-                        ya[l + 1] = da[(i0 + l) * kStatsPitch];
-                        yb[l + 1] = db[(i0 + l) * kStatsPitch];
-                    }
-                    ya[0] = yb[0] = 0;
-                    for (int i = i0; i < nrows; i++) {
-#pragma unroll
-                        for (int l = 0; l < 6; l++) {
-                            ya[l] = ya[l + 1];
-                            yb[l] = yb[l + 1];
-                        }
-                        ya[6] = da[(i + 6) * kStatsPitch];
-                        yb[6] = db[(i + 6) * kStatsPitch];
-                        const int x = dx[i * kStatsTileW];
-#pragma unroll
-                        for (int l1 = 0; l1 < 7; l1++) {
-#pragma unroll
-                            for (int l2 = 0; l2 < 7; l2++) hacc[l1 * 7 + l2] += ya[l1] * yb[l2];
-                            macc[l1] += ya[l1] * x;
-                        }
-                    }
-                }
-            }
-        }
-    }
-    flush();
-    __syncthreads();
-    long long* P = partial + ((size_t)it * ctas_per_item + part) * 2450;
-    for (int i = threadIdx.x; i < 2450; i += blockDim.x) P[i] = (long long)s_acc[i];
-}
 
 // ---------------------------------------------------------------------------------------------
 // K11, 8-bit pixels: the contraction on the tensor cores.
@@ -495,7 +343,7 @@ static void launch_lag_bulk(const PIX* d_dgd, const PIX* d_src, const SvtB200Sta
 }
 
 template <typename PIX>
-static void launch_stats_old(const PIX* d_dgd, const PIX* d_src, const SvtB200StatsItem* d_items, int n, int bd, long long* d_M,
+static void launch_stats_mma(const PIX* d_dgd, const PIX* d_src, const SvtB200StatsItem* d_items, int n, int bd, long long* d_M,
                              long long* d_H, long long* d_acc, unsigned long long* d_tot, cudaStream_t st);
 
 // Wiener statistics of a batch of units: 8-bit pictures on the tensor cores (stats_mma_kernel), 10 / 12 bit by lag sums
@@ -503,7 +351,7 @@ static void launch_stats_old(const PIX* d_dgd, const PIX* d_src, const SvtB200St
 template <typename PIX>
 static void launch_stats(const PIX* d_dgd, const PIX* d_src, const SvtB200StatsItem* d_items, int n, int bd, long long* d_M,
                          long long* d_H, long long* d_acc, unsigned long long* d_tot, cudaStream_t st) {
-    if (sizeof(PIX) == 1) return launch_stats_old<PIX>(d_dgd, d_src, d_items, n, bd, d_M, d_H, d_acc, d_tot, st);
+    if constexpr (sizeof(PIX) == 1) return launch_stats_mma<PIX>(d_dgd, d_src, d_items, n, bd, d_M, d_H, d_acc, d_tot, st);
     const int divider = bd == 12 ? 16 : (bd == 10 ? 4 : 1);
     int cpi = (ctx().sm_count * 8) / (n > 0 ? n : 1);  // CTAs per unit: ~8 resident CTAs per SM over the batch
     if (cpi < 1) cpi = 1;
@@ -524,12 +372,8 @@ static void launch_stats(const PIX* d_dgd, const PIX* d_src, const SvtB200StatsI
 }
 
 template <typename PIX>
-static void launch_stats_old(const PIX* d_dgd, const PIX* d_src, const SvtB200StatsItem* d_items, int n, int bd, long long* d_M,
+static void launch_stats_mma(const PIX* d_dgd, const PIX* d_src, const SvtB200StatsItem* d_items, int n, int bd, long long* d_M,
                              long long* d_H, long long* d_acc, unsigned long long* d_tot, cudaStream_t st) {
-    const int maxv = (1 << bd) - 1;
-    long long fp = 2147483647ll / ((long long)maxv * maxv);
-    if (fp > 30000) fp = 30000;
-    if (fp < 1) fp = 1;
     const int divider = bd == 12 ? 16 : (bd == 10 ? 4 : 1);
     // CTAs per item: enough for ~6 resident CTAs per SM (the tensor-core kernel gives each of them 1-2 pixel tiles)
     int cpi = (ctx().sm_count * (sizeof(PIX) == 1 ? 6 : 4)) / (n > 0 ? n : 1);
@@ -538,11 +382,8 @@ static void launch_stats_old(const PIX* d_dgd, const PIX* d_src, const SvtB200St
     B200_CUDA_CHECK(cudaMemsetAsync(d_tot, 0, (size_t)n * sizeof(unsigned long long), st));
     stats_sum_kernel<PIX><<<n * kSumParts, 256, 0, st>>>(d_dgd, d_items, d_tot);
     B200_LAUNCH_CHECK();
-    if constexpr (sizeof(PIX) == 1) {
-        stats_mma_kernel<<<n * cpi, kMmaWarps * 32, 0, st>>>(d_dgd, d_src, d_items, d_tot, cpi, d_acc);
-    } else {
-        stats_accum_kernel<PIX><<<n * cpi, kStatsWarps * 32, 0, st>>>(d_dgd, d_src, d_items, d_tot, cpi, d_acc, (int)fp);
-    }
+    static_assert(sizeof(PIX) == 1, "the tensor-core statistics are the 8-bit path (high bit depth: wiener_stats_lag.cuh)");
+    stats_mma_kernel<<<n * cpi, kMmaWarps * 32, 0, st>>>(d_dgd, d_src, d_items, d_tot, cpi, d_acc);
     B200_LAUNCH_CHECK();
     stats_finalize_kernel<<<dim3((2450 + 255) / 256, n), 256, 0, st>>>(d_acc, cpi, d_items, divider, sizeof(PIX) == 1, d_M, d_H);
     B200_LAUNCH_CHECK();
