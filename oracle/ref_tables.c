@@ -49,3 +49,11 @@ int ref_qm_matrix(int level, int plane, int tx_size, uint8_t* qm, uint8_t* iqm) 
     }
     return -1;
 }
+
+/* the input-resolution class the preset tables key on (sequence_control_set.c:113) */
+#include "sequence_control_set.h"
+int ref_input_resolution_class(uint32_t input_size) {
+    EbInputResolution r;
+    svt_aom_derive_input_resolution(&r, input_size);
+    return (int)r;
+}

@@ -371,3 +371,38 @@ def test_me_controls_json_is_the_references_derivation(refc):
     spec.loader.exec_module(mod)
     assert sp.ME_CONTROL_FIELDS == mod.layout.ME_CONTROL_FIELDS
     assert mod.all_controls() == json.load(open(os.path.join(root, "svt-av1-psy_b200", "me_controls.json")))
+
+
+def test_committed_av1_tables_and_resolution_classes_are_the_references(refc):
+    """av1_tables.npz (scan orders, quantization matrices) == a fresh dump from the compiled reference; the workload's
+    resolution classes == svt_aom_derive_input_resolution over a sweep of picture sizes"""
+    import ctypes as ct
+    import os
+    import numpy as np
+    from oracle.frame_ref import load_workload_module
+    wlm = load_workload_module()
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    z = np.load(os.path.join(root, "svt-av1-psy_b200", "av1_tables.npz"))
+    i16p, u8p = ct.POINTER(ct.c_int16), ct.POINTER(ct.c_uint8)
+    refc.ref_scan_order.restype = ct.c_int
+    refc.ref_scan_order.argtypes = [ct.c_int, ct.c_int, i16p, i16p]
+    refc.ref_qm_matrix.restype = ct.c_int
+    refc.ref_qm_matrix.argtypes = [ct.c_int, ct.c_int, ct.c_int, u8p, u8p]
+    for sz in range(19):
+        n = int(z["scan_len"][sz])
+        for ty in range(16):
+            s, i = np.zeros(n, np.int16), np.zeros(n, np.int16)
+            assert refc.ref_scan_order(sz, ty, s.ctypes.data_as(i16p), i.ctypes.data_as(i16p)) == n
+            o = int(z["scan_off"][sz, ty])
+            assert np.array_equal(z["scan"][o:o + n], s) and np.array_equal(z["iscan"][o:o + n], i), (sz, ty)
+        for lv in (0, 8, 11, 14):
+            for pl in range(2):
+                q, iq = np.zeros(n, np.uint8), np.zeros(n, np.uint8)
+                assert refc.ref_qm_matrix(lv, pl, sz, q.ctypes.data_as(u8p), iq.ctypes.data_as(u8p)) == n
+                o = int(z["qm_off"][sz])
+                assert np.array_equal(z["qm"][lv, pl, o:o + n], q) and np.array_equal(z["iqm"][lv, pl, o:o + n], iq), (sz, lv, pl)
+    refc.ref_input_resolution_class.restype = ct.c_int
+    refc.ref_input_resolution_class.argtypes = [ct.c_uint32]
+    for (w, h) in [(64, 64), (352, 288), (416, 240), (640, 360), (640, 480), (854, 480), (1024, 576), (1280, 720), (1920, 1080), (2560, 1440),
+                   (3840, 2160), (4096, 2304), (7680, 4320)]:
+        assert wlm.input_resolution_class(w, h) == refc.ref_input_resolution_class(w * h), (w, h)
