@@ -111,45 +111,13 @@ static void me_b64_row(void* vctx, int by) {
     free(me);
 }
 
+/* the flattened controls come from the integration glue a maintainer would ship (integration/svt_b200_me_glue.c): the parity
+ * tests thereby check that mapping too.  RefMeControls and SvtB200MeControls are the same layout (static assert below). */
+#include "../include/svt_b200.h"
+#include "../integration/svt_b200_me_glue.h"
+_Static_assert(sizeof(RefMeControls) == sizeof(SvtB200MeControls), "control struct mirrors differ");
 static void flatten_controls(const MeB64Job* j, const MeContext* me, RefMeControls* c) {
-    const PictureParentControlSet* pcs = j->pcs;
-    memset(c, 0, sizeof(*c));
-    c->n_list = me->num_of_list_to_search; c->n_ref[0] = me->num_of_ref_pic_to_search[0]; c->n_ref[1] = me->num_of_ref_pic_to_search[1];
-    c->temporal_layer_index = me->temporal_layer_index; c->is_ref = me->is_ref; c->hierarchical_levels = pcs->hierarchical_levels;
-    for (int l = 0; l < 2; l++)
-        for (int r = 0; r < 4; r++) c->dist[l][r] = abs(j->cfg->ref_poc_dist_sign[l][r]);
-    c->enable_hme = me->enable_hme_flag; c->enable_l0 = me->enable_hme_level0_flag; c->enable_l1 = me->enable_hme_level1_flag; c->enable_l2 = me->enable_hme_level2_flag;
-    c->hme_sub_sad = me->hme_search_method == SUB_SAD_SEARCH; c->me_sub_sad = me->me_search_method == SUB_SAD_SEARCH;
-    c->hme_l0_min_w = me->hme_l0_sa.sa_min.width; c->hme_l0_min_h = me->hme_l0_sa.sa_min.height;
-    c->hme_l0_max_w = me->hme_l0_sa.sa_max.width; c->hme_l0_max_h = me->hme_l0_sa.sa_max.height;
-    c->hme_l1_w = me->hme_l1_sa.width; c->hme_l1_h = me->hme_l1_sa.height; c->hme_l2_w = me->hme_l2_sa.width; c->hme_l2_h = me->hme_l2_sa.height;
-    c->me_min_w = me->me_sa.sa_min.width; c->me_min_h = me->me_sa.sa_min.height; c->me_max_w = me->me_sa.sa_max.width; c->me_max_h = me->me_sa.sa_max.height;
-    c->prehme_enable = me->prehme_ctrl.enable;
-    for (int s = 0; s < 2; s++) {
-        c->prehme_sa[s][0] = me->prehme_ctrl.prehme_sa_cfg[s].sa_min.width; c->prehme_sa[s][1] = me->prehme_ctrl.prehme_sa_cfg[s].sa_min.height;
-        c->prehme_sa[s][2] = me->prehme_ctrl.prehme_sa_cfg[s].sa_max.width; c->prehme_sa[s][3] = me->prehme_ctrl.prehme_sa_cfg[s].sa_max.height;
-    }
-    c->prehme_skip_search_line = me->prehme_ctrl.skip_search_line; c->prehme_l1_early_exit = me->prehme_ctrl.l1_early_exit;
-    const MeHmeRefPruneCtrls* p = &me->me_hme_prune_ctrls;
-    c->prune_enable = p->enable_me_hme_ref_pruning; c->prune_hme_th = p->prune_ref_if_hme_sad_dev_bigger_than_th; c->prune_me_th = p->prune_ref_if_me_sad_dev_bigger_than_th;
-    c->zz_sad_th = (int32_t)p->zz_sad_th; c->zz_sad_pct = p->zz_sad_pct; c->phme_sad_th = (int32_t)p->phme_sad_th; c->phme_sad_pct = p->phme_sad_pct;
-    const MeSrCtrls* s = &me->me_sr_adjustment_ctrls;
-    c->sr_enable = s->enable_me_sr_adjustment; c->sr_mv_length_th = s->reduce_me_sr_based_on_mv_length_th; c->sr_stationary_hme_sad_abs_th = s->stationary_hme_sad_abs_th;
-    c->sr_stationary_divisor = s->stationary_me_sr_divisor; c->sr_hme_sad_abs_th = s->reduce_me_sr_based_on_hme_sad_abs_th;
-    c->sr_low_hme_sad_divisor = s->me_sr_divisor_for_low_hme_sad; c->sr_distance_based_hme_resizing = s->distance_based_hme_resizing;
-    c->var_enable = me->me_8x8_var_ctrls.enabled; c->var_div4_th = (int32_t)me->me_8x8_var_ctrls.me_sr_div4_th;
-    c->var_div2_th = (int32_t)me->me_8x8_var_ctrls.me_sr_div2_th; c->var_mult2_th = (int32_t)me->me_8x8_var_ctrls.me_sr_mult2_th;
-    c->mvsa_enable = me->mv_based_sa_adj.enabled; c->mvsa_nearest_ref_only = me->mv_based_sa_adj.nearest_ref_only;
-    c->mvsa_mv_size_th = me->mv_based_sa_adj.mv_size_th; c->mvsa_multiplier = me->mv_based_sa_adj.sa_multiplier;
-    c->reduce_hme_l0_sr_th_min = me->reduce_hme_l0_sr_th_min; c->reduce_hme_l0_sr_th_max = me->reduce_hme_l0_sr_th_max;
-    c->me_early_exit_th = (int32_t)me->me_early_exit_th; c->me_safe_limit_zz_th = (int32_t)me->me_safe_limit_zz_th;
-    c->prev_me_stage_based_exit_th = (int32_t)me->prev_me_stage_based_exit_th; c->prune_me_candidates_th = me->prune_me_candidates_th;
-    c->use_best_unipred_cand_only = me->use_best_unipred_cand_only;
-    c->similar_brightness_refs = pcs->similar_brightness_refs; c->only_l_bwd = j->scs->mrp_ctrls.only_l_bwd;
-    c->enable_me_8x8 = pcs->enable_me_8x8; c->enable_me_16x16 = pcs->enable_me_16x16;
-    c->max_cand = pcs->pa_me_data->max_cand; c->max_refs = pcs->pa_me_data->max_refs; c->max_l0 = pcs->pa_me_data->max_l0;
-    c->gm_enabled = pcs->gm_ctrls.enabled; c->gm_use_distance_based_active_th = pcs->gm_ctrls.use_distance_based_active_th;
-    c->resolution_le_480p = j->scs->input_resolution <= INPUT_SIZE_480p_RANGE;
+    svt_b200_me_controls_from_context(j->pcs, me, (SvtB200MeControls*)c);
 }
 
 /* number of square PUs that carry candidates (me_sb_results_ctor, pcs.c:107-112) */
@@ -245,7 +213,21 @@ int ref_me_b64_picture(const RefMePicture* cur, const RefMePicture* refs, const 
         free(me->p_eight_pos_sad16x16);
         free(me);
     }
-    if (out) ref_par_for(j.b64_h, 1, me_b64_row, &j);
+    if (out) {
+        ref_par_for(j.b64_h, 1, me_b64_row, &j);
+        /* round trip through the integration glue: storing the copied-out results back must reproduce the reference's own state */
+        uint8_t* t0 = (uint8_t*)malloc((size_t)nb * j.n_pu);
+        for (int b = 0; b < nb; b++) memcpy(t0 + (size_t)b * j.n_pu, pa->me_results[b]->total_me_candidate_index, (size_t)j.n_pu);
+        svt_b200_me_store_results(pcs, nb, j.n_pu, out->total_me_candidate_index, out->me_candidate_array, out->me_mv_array, out->distortion,
+                                  out->flags);
+        for (int b = 0; b < nb; b++)
+            if (memcmp(t0 + (size_t)b * j.n_pu, pa->me_results[b]->total_me_candidate_index, (size_t)j.n_pu) ||
+                pcs->rc_me_distortion[b] != out->distortion[(size_t)b * 6]) {
+                fprintf(stderr, "[oracle] svt_b200_me_store_results round trip differs at block %d\n", b);
+                abort();
+            }
+        free(t0);
+    }
     for (int b = 0; b < nb; b++) {
         free(pa->me_results[b]->me_mv_array); free(pa->me_results[b]->me_candidate_array); free(pa->me_results[b]->total_me_candidate_index);
         free(pa->me_results[b]);
