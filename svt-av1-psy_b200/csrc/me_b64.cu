@@ -15,8 +15,9 @@
 //   compute_distortion              :2964
 //   perform_gm_detection            :2842
 //
-// Launches:  (A) me_b64_hme_kernel   one CTA per 64x64 block, 4 warps.  The references are walked in the reference's order;
-//                inside a stage the four warps are the four HME search regions (or four references for the per-reference SADs).
+// Launches:  (A) me_b64_hme_kernel<PAR>  one CTA per 64x64 block, 4 * PAR warps.  The references are walked in the reference's
+//                order, PAR at a time (1, or 2 from six references up: measured); inside the HME stages a warp is one
+//                (reference, search region) pair, in the per-reference stages (zz SAD, pre-HME, window derivation) one reference.
 //                Decisions that couple references (pruning, carried-over centres) are taken by one thread between barriers.
 //                Writes one full-pel item per (reference, block) + the 85 SADs of the variance probe ("seed").
 //            (B) fullpel_search_kernel<TMA> (me_pyramid.cu) over the items, best arrays seeded with the probe.
